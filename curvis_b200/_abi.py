@@ -1,0 +1,157 @@
+"""ctypes mirror of include/curvis_gpu.h and the loader of libcurvis_b200.so.
+
+The library is the product: there is no Python/CPU compute path behind it.  Loading fails
+loudly when the shared object has not been built (``python -c "import __graft_entry__ as g;
+g.build()"`` or ``make -C curvis_b200/csrc``), and creating a context fails loudly when no
+sm_100 device is visible.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+ABI_VERSION = 1
+
+# curvis_status
+OK = 0
+ERR_INVALID_ARGUMENT = 1
+ERR_CAMERA_OUTSIDE_RADIUS = 2
+ERR_PARALLEL_VECTORS = 3
+ERR_INVALID_METRIC = 4
+ERR_NO_BACKGROUND = 5
+ERR_CUDA = 6
+ERR_OUT_OF_MEMORY = 7
+ERR_NO_DEVICE = 8
+ERR_UNSUPPORTED = 9
+
+METRIC_ELLIS, METRIC_INTERSTELLAR, METRIC_FLAT = 0, 1, 2
+PRECISION_F64, PRECISION_F32 = 0, 1
+SAMPLING_NEAREST, SAMPLING_BILINEAR = 0, 1
+
+
+class CurvisMetric(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("rho", C.c_double), ("m", C.c_double), ("a", C.c_double)]
+
+
+class CurvisCamera(C.Structure):
+    _fields_ = [
+        ("position", C.c_double * 4),
+        ("cam_to_world", C.c_double * 9),
+        ("focal_length", C.c_double),
+        ("sensor_width", C.c_double),
+        ("sensor_height", C.c_double),
+        ("resolution_width", C.c_uint32),
+        ("resolution_height", C.c_uint32),
+    ]
+
+
+class CurvisSim(C.Structure):
+    _fields_ = [
+        ("max_iterations", C.c_uint32),
+        ("_pad", C.c_uint32),
+        ("max_radius", C.c_double),
+        ("delta", C.c_double),
+        ("precision", C.c_int32),
+        ("sampling", C.c_int32),
+    ]
+
+
+class CurvisStats(C.Structure):
+    _fields_ = [
+        ("total_steps", C.c_uint64),
+        ("n_rays", C.c_uint64),
+        ("n_positive", C.c_uint64),
+        ("n_negative", C.c_uint64),
+        ("n_not_escaped", C.c_uint64),
+        ("n_clamped", C.c_uint64),
+        ("n_big_theta", C.c_uint64),
+        ("kernel_ms", C.c_double),
+        ("total_ms", C.c_double),
+    ]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+class CurvisRayRecord(C.Structure):
+    _fields_ = [
+        ("l", C.c_double), ("theta", C.c_double), ("phi", C.c_double),
+        ("p_l", C.c_double), ("p_theta", C.c_double), ("p_phi", C.c_double),
+        ("steps", C.c_uint32), ("side", C.c_int32), ("texel_x", C.c_uint32), ("texel_y", C.c_uint32),
+    ]
+
+
+# numpy view of curvis_ray_record (same layout, 64 bytes)
+RAY_RECORD_DTYPE = [
+    ("l", "<f8"), ("theta", "<f8"), ("phi", "<f8"), ("p_l", "<f8"), ("p_theta", "<f8"), ("p_phi", "<f8"),
+    ("steps", "<u4"), ("side", "<i4"), ("texel_x", "<u4"), ("texel_y", "<u4"),
+]
+
+# Every symbol include/curvis_gpu.h declares (tests assert the .so exports exactly these).
+EXPORTED_SYMBOLS = (
+    "curvis_ctx_create", "curvis_ctx_destroy", "curvis_last_error", "curvis_abi_version",
+    "curvis_ctx_device_count", "curvis_orientation", "curvis_camera_init", "curvis_metric_validate",
+    "curvis_set_background", "curvis_render_image", "curvis_render_rows", "curvis_render_rows_device",
+    "curvis_measure_fma_peak",
+)
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcurvis_b200.so")
+_lib = None
+
+
+class CurvisError(RuntimeError):
+    """A non-zero curvis_status; ``code`` holds it (the reference panics or returns Err(String))."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"curvis status {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+def load_library() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `make -C curvis_b200/csrc` (or __graft_entry__.build()). "
+            "curvis_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    dp, vp = C.POINTER(C.c_double), C.c_void_p
+    lib.curvis_ctx_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    lib.curvis_ctx_destroy.argtypes = [vp]
+    lib.curvis_ctx_destroy.restype = None
+    lib.curvis_last_error.argtypes = [vp]
+    lib.curvis_last_error.restype = C.c_char_p
+    lib.curvis_abi_version.argtypes = []
+    lib.curvis_ctx_device_count.argtypes = [vp]
+    lib.curvis_orientation.argtypes = [dp, dp, dp, dp, dp]
+    lib.curvis_camera_init.argtypes = [C.POINTER(CurvisCamera), dp, dp, dp, C.c_double, C.c_double, C.c_uint32, C.c_uint32]
+    lib.curvis_metric_validate.argtypes = [C.POINTER(CurvisMetric)]
+    lib.curvis_set_background.argtypes = [vp, C.c_int, vp, C.c_uint32, C.c_uint32, dp]
+    lib.curvis_render_image.argtypes = [vp, C.POINTER(CurvisMetric), C.POINTER(CurvisCamera), C.POINTER(CurvisSim), vp, C.POINTER(CurvisStats)]
+    lib.curvis_render_rows.argtypes = [vp, C.POINTER(CurvisMetric), C.POINTER(CurvisCamera), C.POINTER(CurvisSim),
+                                       C.c_uint32, C.c_uint32, vp, vp, C.POINTER(CurvisStats)]
+    lib.curvis_render_rows_device.argtypes = [vp, C.POINTER(CurvisMetric), C.POINTER(CurvisCamera), C.POINTER(CurvisSim),
+                                              C.c_uint32, C.c_uint32, vp, vp, vp, C.POINTER(CurvisStats)]
+    lib.curvis_measure_fma_peak.argtypes = [vp, dp, dp]
+    for name in EXPORTED_SYMBOLS:
+        fn = getattr(lib, name)
+        if name not in ("curvis_ctx_destroy", "curvis_last_error"):
+            fn.restype = C.c_int
+    if lib.curvis_abi_version() != ABI_VERSION:
+        raise ImportError(f"libcurvis_b200.so ABI {lib.curvis_abi_version()} != expected {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(code: int, ctx=None) -> None:
+    if code != OK:
+        msg = load_library().curvis_last_error(ctx)
+        raise CurvisError(code, msg.decode("utf-8", "replace") if msg else "")
+
+
+def dvec(values, n):
+    arr = (C.c_double * n)(*[float(v) for v in values])
+    return arr

@@ -1,0 +1,366 @@
+// curvis_abi.cu — implementation of include/curvis_gpu.h: contexts, background residency,
+// frame launches (single tile, device-resident tile, whole frame row-tiled over the
+// context's devices).  The boundary replaces RelativisticSystem::render_image
+// (reference src/systems.rs:307-330); there is no CPU compute path in this library.
+#include <cuda_runtime.h>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+#include "../../include/curvis_gpu.h"
+#include "frame_params.h"
+#include "host_error.h"
+#include "launch.h"
+
+namespace curvis {
+
+static thread_local std::string g_thread_error;
+int set_thread_error(int code, const char* msg) { g_thread_error = msg ? msg : ""; return code; }
+const char* thread_error() { return g_thread_error.c_str(); }
+
+struct DeviceState {
+    int ordinal = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    // resident scene
+    uint32_t* bg_texels[2] = {nullptr, nullptr};
+    uint32_t bg_w[2] = {0, 0}, bg_h[2] = {0, 0};
+    // per-launch scratch
+    DeviceCounters* d_counters = nullptr;
+    DeviceCounters* h_counters = nullptr;  // pinned
+    uint8_t* d_out = nullptr; size_t d_out_cap = 0;
+    uint8_t* h_out = nullptr; size_t h_out_cap = 0;  // pinned staging
+    curvis_ray_record* d_records = nullptr; size_t d_records_cap = 0;
+    // tile of the frame in flight
+    uint32_t row_begin = 0, row_end = 0;
+};
+
+}  // namespace curvis
+
+struct curvis_ctx {
+    std::vector<curvis::DeviceState> devs;
+    double bg_inv_rot[2][9];
+    bool bg_set[2] = {false, false};
+    std::string err;
+};
+
+namespace curvis {
+
+static int fail(curvis_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    g_thread_error = msg;
+    return code;
+}
+
+static int cuda_fail(curvis_ctx* ctx, cudaError_t e, const char* what) {
+    std::string msg = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    return fail(ctx, e == cudaErrorMemoryAllocation ? CURVIS_ERR_OUT_OF_MEMORY : CURVIS_ERR_CUDA, msg);
+}
+
+#define CURVIS_CUDA(ctx, expr)                                         \
+    do {                                                               \
+        cudaError_t _e = (expr);                                       \
+        if (_e != cudaSuccess) return curvis::cuda_fail((ctx), _e, #expr); \
+    } while (0)
+
+static int validate_frame(curvis_ctx* ctx, const curvis_metric* metric, const curvis_camera* cam, const curvis_sim* sim,
+                          uint32_t row_begin, uint32_t row_end) {
+    if (!ctx) return fail(nullptr, CURVIS_ERR_INVALID_ARGUMENT, "null context");
+    if (!metric || !cam || !sim) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "null metric/camera/sim");
+    int rc = curvis_metric_validate(metric);
+    if (rc != CURVIS_OK) return fail(ctx, rc, thread_error());
+    if (cam->resolution_width == 0 || cam->resolution_height == 0)
+        return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "resolution_width and resolution_height must be greater than 0");
+    if (row_begin > row_end || row_end > cam->resolution_height)
+        return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "row range outside the frame");
+    if (sim->precision != CURVIS_PRECISION_F64)
+        return fail(ctx, CURVIS_ERR_UNSUPPORTED, "only CURVIS_PRECISION_F64 is implemented in this build");
+    if (sim->sampling != CURVIS_SAMPLING_NEAREST)
+        return fail(ctx, CURVIS_ERR_UNSUPPORTED, "only CURVIS_SAMPLING_NEAREST is implemented in this build");
+    if (!ctx->bg_set[0] || !ctx->bg_set[1])
+        return fail(ctx, CURVIS_ERR_NO_BACKGROUND, "both backgrounds must be set before rendering");
+    // escape_photon panics when the photon starts beyond the radius (systems.rs:122-124);
+    // every ray starts at the camera, so the check is per frame.  NaN compares false, as in Rust.
+    if (std::fabs(cam->position[1]) > sim->max_radius)
+        return fail(ctx, CURVIS_ERR_CAMERA_OUTSIDE_RADIUS, "Photon already beyond the maximum radius. Cannot evaluate escape.");
+    return CURVIS_OK;
+}
+
+static void fill_params(const curvis_ctx* ctx, const DeviceState& d, const curvis_metric* metric, const curvis_camera* cam,
+                        const curvis_sim* sim, uint32_t row_begin, uint32_t row_end, uint8_t* d_out,
+                        curvis_ray_record* d_records, FrameParams& p) {
+    std::memset(&p, 0, sizeof p);
+    p.rho = metric->rho; p.m = metric->m; p.a = metric->a;
+    std::memcpy(p.cam_pos, cam->position, sizeof p.cam_pos);
+    std::memcpy(p.cam_to_world, cam->cam_to_world, sizeof p.cam_to_world);
+    p.focal_length = cam->focal_length; p.sensor_width = cam->sensor_width; p.sensor_height = cam->sensor_height;
+    p.width = cam->resolution_width; p.height = cam->resolution_height;
+    p.max_iterations = sim->max_iterations; p.sampling = (uint32_t)sim->sampling;
+    p.max_radius = sim->max_radius; p.delta = sim->delta;
+    p.row_begin = row_begin; p.row_end = row_end;
+    for (int s = 0; s < 2; ++s) {
+        p.bg[s].texels = d.bg_texels[s];
+        p.bg[s].width = d.bg_w[s]; p.bg[s].height = d.bg_h[s];
+        std::memcpy(p.bg[s].inv_rot, ctx->bg_inv_rot[s], sizeof p.bg[s].inv_rot);
+    }
+    p.out_rgb8 = d_out; p.records = d_records; p.counters = d.d_counters;
+}
+
+// Enqueue one tile on `stream` of device d: zero counters, kernel bracketed by events.
+static int enqueue_tile(curvis_ctx* ctx, DeviceState& d, const curvis_metric* metric, const curvis_camera* cam,
+                        const curvis_sim* sim, uint32_t row_begin, uint32_t row_end, uint8_t* d_out,
+                        curvis_ray_record* d_records, cudaStream_t stream) {
+    FrameParams p;
+    fill_params(ctx, d, metric, cam, sim, row_begin, row_end, d_out, d_records, p);
+    CURVIS_CUDA(ctx, cudaMemsetAsync(d.d_counters, 0, sizeof(DeviceCounters), stream));
+    CURVIS_CUDA(ctx, cudaEventRecord(d.ev_begin, stream));
+    if (row_end > row_begin) CURVIS_CUDA(ctx, launch_render_f64(p, metric->kind, d.sm_count, stream));
+    CURVIS_CUDA(ctx, cudaEventRecord(d.ev_end, stream));
+    return CURVIS_OK;
+}
+
+static void add_counters(const DeviceCounters& c, uint64_t n_rays, curvis_stats* s) {
+    s->total_steps += c.total_steps; s->n_rays += n_rays;
+    s->n_positive += c.n_positive; s->n_negative += c.n_negative; s->n_not_escaped += c.n_not_escaped;
+    s->n_clamped += c.n_clamped; s->n_big_theta += c.n_big_theta;
+}
+
+static int ensure_capacity(curvis_ctx* ctx, DeviceState& d, size_t out_bytes, size_t n_records, bool staging) {
+    if (out_bytes > d.d_out_cap) {
+        if (d.d_out) cudaFree(d.d_out);
+        d.d_out = nullptr; d.d_out_cap = 0;
+        CURVIS_CUDA(ctx, cudaMalloc(&d.d_out, out_bytes));
+        d.d_out_cap = out_bytes;
+    }
+    if (staging && out_bytes > d.h_out_cap) {
+        if (d.h_out) cudaFreeHost(d.h_out);
+        d.h_out = nullptr; d.h_out_cap = 0;
+        CURVIS_CUDA(ctx, cudaMallocHost(&d.h_out, out_bytes));
+        d.h_out_cap = out_bytes;
+    }
+    if (n_records > d.d_records_cap) {
+        if (d.d_records) cudaFree(d.d_records);
+        d.d_records = nullptr; d.d_records_cap = 0;
+        CURVIS_CUDA(ctx, cudaMalloc(&d.d_records, n_records * sizeof(curvis_ray_record)));
+        d.d_records_cap = n_records;
+    }
+    return CURVIS_OK;
+}
+
+static void release_device(DeviceState& d) {
+    if (d.ordinal < 0) return;
+    cudaSetDevice(d.ordinal);
+    for (int s = 0; s < 2; ++s) if (d.bg_texels[s]) cudaFree(d.bg_texels[s]);
+    if (d.d_counters) cudaFree(d.d_counters);
+    if (d.h_counters) cudaFreeHost(d.h_counters);
+    if (d.d_out) cudaFree(d.d_out);
+    if (d.h_out) cudaFreeHost(d.h_out);
+    if (d.d_records) cudaFree(d.d_records);
+    if (d.ev_begin) cudaEventDestroy(d.ev_begin);
+    if (d.ev_end) cudaEventDestroy(d.ev_end);
+    if (d.stream) cudaStreamDestroy(d.stream);
+    d = DeviceState();
+}
+
+}  // namespace curvis
+
+using namespace curvis;
+
+extern "C" int curvis_abi_version(void) { return CURVIS_ABI_VERSION; }
+
+extern "C" const char* curvis_last_error(const curvis_ctx* ctx) { return ctx ? ctx->err.c_str() : thread_error(); }
+
+extern "C" int curvis_ctx_device_count(const curvis_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+
+extern "C" int curvis_ctx_create(const int* devices, int n_devices, curvis_ctx** out) {
+    if (!out) return fail(nullptr, CURVIS_ERR_INVALID_ARGUMENT, "curvis_ctx_create: null out");
+    *out = nullptr;
+    int visible = 0;
+    cudaError_t e = cudaGetDeviceCount(&visible);
+    if (e != cudaSuccess || visible == 0) {
+        cudaGetLastError();
+        return fail(nullptr, CURVIS_ERR_NO_DEVICE,
+                    "no CUDA device visible (libcurvis_b200 has no CPU fallback; it needs an sm_100 GPU)");
+    }
+    std::vector<int> ords;
+    if (devices && n_devices > 0) ords.assign(devices, devices + n_devices);
+    else for (int i = 0; i < visible; ++i) ords.push_back(i);
+    curvis_ctx* ctx = new (std::nothrow) curvis_ctx();
+    if (!ctx) return fail(nullptr, CURVIS_ERR_OUT_OF_MEMORY, "out of host memory");
+    for (int s = 0; s < 2; ++s) {
+        const double ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        std::memcpy(ctx->bg_inv_rot[s], ident, sizeof ident);
+    }
+    ctx->devs.resize(ords.size());
+    for (size_t i = 0; i < ords.size(); ++i) {
+        DeviceState& d = ctx->devs[i];
+        const int ord = ords[i];
+        int rc = CURVIS_OK;
+        cudaDeviceProp prop;
+        if (ord < 0 || ord >= visible) rc = fail(nullptr, CURVIS_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+        else if ((e = cudaSetDevice(ord)) != cudaSuccess) rc = cuda_fail(nullptr, e, "cudaSetDevice");
+        else if ((e = cudaGetDeviceProperties(&prop, ord)) != cudaSuccess) rc = cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+        else if (prop.major != 10) rc = fail(nullptr, CURVIS_ERR_NO_DEVICE, "device is not sm_100 (this library ships sm_100a code only)");
+        else {
+            d.ordinal = ord;
+            d.sm_count = prop.multiProcessorCount;
+            if ((e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking)) != cudaSuccess) rc = cuda_fail(nullptr, e, "cudaStreamCreate");
+            else if ((e = cudaEventCreate(&d.ev_begin)) != cudaSuccess) rc = cuda_fail(nullptr, e, "cudaEventCreate");
+            else if ((e = cudaEventCreate(&d.ev_end)) != cudaSuccess) rc = cuda_fail(nullptr, e, "cudaEventCreate");
+            else if ((e = cudaMalloc(&d.d_counters, sizeof(DeviceCounters))) != cudaSuccess) rc = cuda_fail(nullptr, e, "cudaMalloc(counters)");
+            else if ((e = cudaMallocHost(&d.h_counters, sizeof(DeviceCounters))) != cudaSuccess) rc = cuda_fail(nullptr, e, "cudaMallocHost(counters)");
+        }
+        if (rc != CURVIS_OK) {
+            curvis_ctx_destroy(ctx);
+            return rc;
+        }
+    }
+    *out = ctx;
+    return CURVIS_OK;
+}
+
+extern "C" void curvis_ctx_destroy(curvis_ctx* ctx) {
+    if (!ctx) return;
+    for (auto& d : ctx->devs) release_device(d);
+    delete ctx;
+}
+
+extern "C" int curvis_set_background(curvis_ctx* ctx, int side, const uint8_t* rgba8,
+                                     uint32_t width, uint32_t height, const double inv_rot[9]) {
+    if (!ctx) return fail(nullptr, CURVIS_ERR_INVALID_ARGUMENT, "null context");
+    if (side == 0 || !rgba8 || width == 0 || height == 0)
+        return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "curvis_set_background: side must be +-1, image non-empty");
+    const int s = side > 0 ? 0 : 1;
+    const size_t bytes = (size_t)width * height * 4;
+    for (auto& d : ctx->devs) {
+        CURVIS_CUDA(ctx, cudaSetDevice(d.ordinal));
+        if (d.bg_texels[s]) { cudaFree(d.bg_texels[s]); d.bg_texels[s] = nullptr; }
+        CURVIS_CUDA(ctx, cudaMalloc(&d.bg_texels[s], bytes));
+        CURVIS_CUDA(ctx, cudaMemcpyAsync(d.bg_texels[s], rgba8, bytes, cudaMemcpyHostToDevice, d.stream));
+        d.bg_w[s] = width; d.bg_h[s] = height;
+    }
+    for (auto& d : ctx->devs) {
+        CURVIS_CUDA(ctx, cudaSetDevice(d.ordinal));
+        CURVIS_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    }
+    const double ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    std::memcpy(ctx->bg_inv_rot[s], inv_rot ? inv_rot : ident, sizeof ident);
+    ctx->bg_set[s] = true;
+    return CURVIS_OK;
+}
+
+extern "C" int curvis_render_rows_device(curvis_ctx* ctx, const curvis_metric* metric,
+                                         const curvis_camera* camera, const curvis_sim* sim,
+                                         uint32_t row_begin, uint32_t row_end,
+                                         void* d_out_rgb8_rows, void* d_records,
+                                         void* stream, curvis_stats* stats) {
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = validate_frame(ctx, metric, camera, sim, row_begin, row_end);
+    if (rc != CURVIS_OK) return rc;
+    if (!d_out_rgb8_rows && row_end > row_begin) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "null device output");
+    DeviceState& d = ctx->devs[0];
+    cudaStream_t st = (cudaStream_t)stream;
+    CURVIS_CUDA(ctx, cudaSetDevice(d.ordinal));
+    rc = enqueue_tile(ctx, d, metric, camera, sim, row_begin, row_end, (uint8_t*)d_out_rgb8_rows,
+                      (curvis_ray_record*)d_records, st);
+    if (rc != CURVIS_OK) return rc;
+    if (stats) {
+        CURVIS_CUDA(ctx, cudaMemcpyAsync(d.h_counters, d.d_counters, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, st));
+        CURVIS_CUDA(ctx, cudaStreamSynchronize(st));
+        std::memset(stats, 0, sizeof *stats);
+        add_counters(*d.h_counters, (uint64_t)(row_end - row_begin) * camera->resolution_width, stats);
+        float ms = 0.f;
+        CURVIS_CUDA(ctx, cudaEventElapsedTime(&ms, d.ev_begin, d.ev_end));
+        stats->kernel_ms = ms;
+        stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return CURVIS_OK;
+}
+
+extern "C" int curvis_render_rows(curvis_ctx* ctx, const curvis_metric* metric,
+                                  const curvis_camera* camera, const curvis_sim* sim,
+                                  uint32_t row_begin, uint32_t row_end,
+                                  uint8_t* out_rgb8_rows, curvis_ray_record* records,
+                                  curvis_stats* stats) {
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = validate_frame(ctx, metric, camera, sim, row_begin, row_end);
+    if (rc != CURVIS_OK) return rc;
+    const size_t n_rays = (size_t)(row_end - row_begin) * camera->resolution_width;
+    if (n_rays && !out_rgb8_rows) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "null output buffer");
+    DeviceState& d = ctx->devs[0];
+    CURVIS_CUDA(ctx, cudaSetDevice(d.ordinal));
+    rc = ensure_capacity(ctx, d, n_rays * 3 + 1, records ? n_rays : 0, true);
+    if (rc != CURVIS_OK) return rc;
+    rc = enqueue_tile(ctx, d, metric, camera, sim, row_begin, row_end, d.d_out, records ? d.d_records : nullptr, d.stream);
+    if (rc != CURVIS_OK) return rc;
+    if (n_rays) CURVIS_CUDA(ctx, cudaMemcpyAsync(d.h_out, d.d_out, n_rays * 3, cudaMemcpyDeviceToHost, d.stream));
+    if (records && n_rays)
+        CURVIS_CUDA(ctx, cudaMemcpyAsync(records, d.d_records, n_rays * sizeof(curvis_ray_record), cudaMemcpyDeviceToHost, d.stream));
+    CURVIS_CUDA(ctx, cudaMemcpyAsync(d.h_counters, d.d_counters, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, d.stream));
+    CURVIS_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    if (n_rays) std::memcpy(out_rgb8_rows, d.h_out, n_rays * 3);
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+        add_counters(*d.h_counters, n_rays, stats);
+        float ms = 0.f;
+        CURVIS_CUDA(ctx, cudaEventElapsedTime(&ms, d.ev_begin, d.ev_end));
+        stats->kernel_ms = ms;
+        stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return CURVIS_OK;
+}
+
+extern "C" int curvis_render_image(curvis_ctx* ctx, const curvis_metric* metric,
+                                   const curvis_camera* camera, const curvis_sim* sim,
+                                   uint8_t* out_rgb8, curvis_stats* stats) {
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = validate_frame(ctx, metric, camera, sim, 0, camera ? camera->resolution_height : 0);
+    if (rc != CURVIS_OK) return rc;
+    if (!out_rgb8) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "null output buffer");
+    const uint32_t W = camera->resolution_width, H = camera->resolution_height;
+    const size_t n = ctx->devs.size();
+    // Row tiles: device g renders rows [g*H/n, (g+1)*H/n) — every pixel is independent
+    // (systems.rs:316-326 carries no state between iterations), so no exchange is needed:
+    // each device copies its tile straight into its slice of the host frame.
+    for (size_t g = 0; g < n; ++g) {
+        DeviceState& d = ctx->devs[g];
+        d.row_begin = (uint32_t)((uint64_t)H * g / n);
+        d.row_end = (uint32_t)((uint64_t)H * (g + 1) / n);
+        const size_t bytes = (size_t)(d.row_end - d.row_begin) * W * 3;
+        CURVIS_CUDA(ctx, cudaSetDevice(d.ordinal));
+        rc = ensure_capacity(ctx, d, bytes + 1, 0, true);
+        if (rc != CURVIS_OK) return rc;
+        rc = enqueue_tile(ctx, d, metric, camera, sim, d.row_begin, d.row_end, d.d_out, nullptr, d.stream);
+        if (rc != CURVIS_OK) return rc;
+        if (bytes) CURVIS_CUDA(ctx, cudaMemcpyAsync(d.h_out, d.d_out, bytes, cudaMemcpyDeviceToHost, d.stream));
+        CURVIS_CUDA(ctx, cudaMemcpyAsync(d.h_counters, d.d_counters, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, d.stream));
+    }
+    if (stats) std::memset(stats, 0, sizeof *stats);
+    for (size_t g = 0; g < n; ++g) {
+        DeviceState& d = ctx->devs[g];
+        const size_t bytes = (size_t)(d.row_end - d.row_begin) * W * 3;
+        CURVIS_CUDA(ctx, cudaSetDevice(d.ordinal));
+        CURVIS_CUDA(ctx, cudaStreamSynchronize(d.stream));
+        if (bytes) std::memcpy(out_rgb8 + (size_t)d.row_begin * W * 3, d.h_out, bytes);
+        if (stats) {
+            add_counters(*d.h_counters, (uint64_t)(d.row_end - d.row_begin) * W, stats);
+            float ms = 0.f;
+            CURVIS_CUDA(ctx, cudaEventElapsedTime(&ms, d.ev_begin, d.ev_end));
+            if (ms > stats->kernel_ms) stats->kernel_ms = ms;
+        }
+    }
+    if (stats) stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return CURVIS_OK;
+}
+
+extern "C" int curvis_measure_fma_peak(curvis_ctx* ctx, double* fp64_tflops, double* fp32_tflops) {
+    if (!ctx || !fp64_tflops || !fp32_tflops) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "null argument");
+    DeviceState& d = ctx->devs[0];
+    CURVIS_CUDA(ctx, cudaSetDevice(d.ordinal));
+    CURVIS_CUDA(ctx, measure_fma_peak(d.sm_count, d.stream, fp64_tflops, fp32_tflops));
+    return CURVIS_OK;
+}

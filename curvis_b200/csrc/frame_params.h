@@ -1,0 +1,51 @@
+// frame_params.h — the one kernel argument of the render kernels: everything
+// RelativisticSystem::render_image reads from `self` and its three arguments
+// (reference src/systems.rs:68-73, :307-312), flattened to plain data so it travels in the
+// kernel parameter space (constant bank, uniform loads) with no per-launch H2D copy.
+#pragma once
+#include <stdint.h>
+#include "../../include/curvis_gpu.h"
+
+namespace curvis {
+
+// Device-side counters of one launch (one 128-byte line; zeroed before each launch).
+struct DeviceCounters {
+    unsigned long long next_ray;      // work queue: next ray index of the tile to hand out
+    unsigned long long total_steps;   // curvis_stats.total_steps
+    unsigned long long n_positive;
+    unsigned long long n_negative;
+    unsigned long long n_not_escaped;
+    unsigned long long n_clamped;
+    unsigned long long n_big_theta;
+    unsigned long long _pad[9];
+};
+
+struct Background {
+    const uint32_t* texels;  // RGBA8 packed little-endian (R in the low byte), row-major
+    uint32_t width, height;
+    double inv_rot[9];       // image orientation inverse, row-major (images.rs:132-142)
+};
+
+struct FrameParams {
+    // metric parameters (metrics.rs:399-401, :431-435)
+    double rho, m, a;
+    // camera (cameras.rs:30-43)
+    double cam_pos[4];
+    double cam_to_world[9];
+    double focal_length, sensor_width, sensor_height;
+    uint32_t width, height;
+    // render_image arguments (systems.rs:309-311)
+    uint32_t max_iterations;
+    uint32_t sampling;
+    double max_radius, delta;
+    // tile of the frame this launch renders: rows [row_begin, row_end)
+    uint32_t row_begin, row_end;
+    // scene (systems.rs:70-71): [0] = background_positive, [1] = background_negative
+    Background bg[2];
+    // outputs: RGB8 rows of the tile (packed, row-major), optional per-ray records, counters
+    uint8_t* out_rgb8;
+    curvis_ray_record* records;
+    DeviceCounters* counters;
+};
+
+}  // namespace curvis

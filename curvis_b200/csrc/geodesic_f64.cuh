@@ -1,0 +1,178 @@
+// geodesic_f64.cuh — device-side fp64 restatement of the per-ray work of
+// RelativisticSystem::render_image (reference src/systems.rs:307-330), in the reference's
+// operation order.  This translation unit MUST be compiled with -fmad=false: Rust never
+// contracts a*b+c, so a contracted FMA here would change the low bit of the Euler update and
+// break bit parity with the reference.  IEEE double +,-,*,/ and sqrt are correctly rounded on
+// sm_100a, so with contraction off every line below is bit-identical to the CPU evaluation;
+// the only operations that can differ from the reference's platform libm are the
+// transcendentals, isolated behind the Trig / shape-function policies.
+#pragma once
+#include <cuda_runtime.h>
+#include "frame_params.h"
+
+namespace curvis {
+
+#define CURVIS_PI 3.14159265358979323846264338327950288  // std::f64::consts::PI
+
+// ---------------------------------------------------------------- photon state
+// Position (t, l, theta, phi) + covariant momentum (p_t, p_l, p_theta, p_phi)
+// (vectors.rs:135-139).  t is never read, p_t and p_phi never change (their derivatives are
+// the literals 0.0, metrics.rs:259-264; x + 0.0*delta == x exactly), so a ray is five live
+// doubles plus two per-ray constants.
+struct Ray {
+    double l, th, ph;    // x(1), x(2), x(3)
+    double pl, pth;      // p(1), p(2)
+    double pph, pph2;    // p(3) and p(3).powi(2) (same operands every step -> hoisted bit-safely)
+};
+
+// ---------------------------------------------------------------- trig policies
+struct TrigCuda {  // CUDA math library (<= 2 ulp; not bit-identical to glibc)
+    static __device__ __forceinline__ void sincos(double x, double& s, double& c) { ::sincos(x, &s, &c); }
+    static __device__ __forceinline__ double sin(double x) { return ::sin(x); }
+};
+
+// ---------------------------------------------------------------- shape functions r(l)
+// Each returns r(l), r_squared(l), r_derivative(l) exactly as the reference's three trait
+// methods would (the reference re-evaluates them several times per step with identical
+// arguments; evaluating once is bit-safe).
+struct ShapeEllis {  // metrics.rs:417-421
+    static constexpr int kind = CURVIS_METRIC_ELLIS;
+    static __device__ __forceinline__ void eval(const FrameParams& p, double l, double& r, double& r2, double& rp) {
+        r2 = p.rho * p.rho + l * l;  // :419 (and the radicand of :418)
+        r = sqrt(r2);                // :418
+        rp = l / r;                  // :420
+    }
+};
+
+struct ShapeInterstellar {  // metrics.rs:461-485
+    static constexpr int kind = CURVIS_METRIC_INTERSTELLAR;
+    static __device__ __forceinline__ void eval(const FrameParams& p, double l, double& r, double& r2, double& rp) {
+        const double al = fabs(l);
+        if (al > p.a) {
+            const double x = 2.0 * (al - p.a) / (CURVIS_PI * p.m);            // :461
+            const double at = atan(x);
+            r = p.rho + p.m * (x * at - log(1.0 + x * x) / 2.0);               // :467-468
+            const double sg = (l != l) ? l : copysign(1.0, l);                 // f64::signum
+            rp = (2.0 / CURVIS_PI) * sg * at;                                  // :479-480
+        } else {
+            r = p.rho;   // :470
+            rp = 0.0;    // :482
+        }
+        r2 = r * r;      // :474
+    }
+};
+
+struct ShapeFlat {  // metrics.rs:501-505
+    static constexpr int kind = CURVIS_METRIC_FLAT;
+    static __device__ __forceinline__ void eval(const FrameParams&, double l, double& r, double& r2, double& rp) {
+        r = l; r2 = l * l; rp = 1.0;
+    }
+};
+
+// ---------------------------------------------------------------- nalgebra-order helpers
+__device__ __forceinline__ double norm3(double x, double y, double z) { return sqrt((x * x + y * y) + z * z); }
+
+__device__ __forceinline__ void mat3_mul(const double* m, double x, double y, double z, double& ox, double& oy, double& oz) {
+    ox = (m[0] * x + m[1] * y) + m[2] * z;
+    oy = (m[3] * x + m[4] * y) + m[5] * z;
+    oz = (m[6] * x + m[7] * y) + m[8] * z;
+}
+
+// f64::rem_euclid
+__device__ __forceinline__ double rem_euclid(double x, double rhs) {
+    const double r = fmod(x, rhs);
+    return (r < 0.0) ? r + fabs(rhs) : r;
+}
+
+// normalize_theta_phi, algebra.rs:106-116
+__device__ __forceinline__ void normalize_theta_phi(double& th, double& ph) {
+    if (th < 0.0) { th = fabs(th); ph = ph + CURVIS_PI; }
+    ph = rem_euclid(ph, 2.0 * CURVIS_PI);
+}
+
+// ---------------------------------------------------------------- ray generation
+// camera_pixels_x_y_to_photon (systems.rs:531-534): outward_vector_on_camera_space
+// (cameras.rs:150-164), camera_to_world rotation (:169-172), new_photon (metrics.rs:301-334).
+template <class Shape, class Trig>
+__device__ __forceinline__ void new_photon_for_pixel(const FrameParams& p, uint32_t px, uint32_t py, Ray& q) {
+    const double res_x = (double)p.width, res_y = (double)p.height;
+    const double h = 0.5 - ((double)py / res_y);
+    const double w = ((double)px / res_x) - 0.5;
+    double vx = p.focal_length * 1.0;
+    double vy = -p.sensor_width * w;
+    double vz = p.sensor_height * h;
+    double n = norm3(vx, vy, vz);
+    vx = vx / n; vy = vy / n; vz = vz / n;                       // cameras.rs:163
+    double dx, dy, dz;
+    mat3_mul(p.cam_to_world, vx, vy, vz, dx, dy, dz);            // cameras.rs:171
+    n = norm3(dx, dy, dz);
+    dx = dx / n; dy = dy / n; dz = dz / n;                       // metrics.rs:320
+    double r, r2, rp;
+    Shape::eval(p, p.cam_pos[1], r, r2, rp);
+    q.l = p.cam_pos[1]; q.th = p.cam_pos[2]; q.ph = p.cam_pos[3];
+    q.pl = dx;                                                   // :328
+    q.pth = dy * r;                                              // :329
+    q.pph = dz * r * Trig::sin(p.cam_pos[2]);                    // :330
+    q.pph2 = q.pph * q.pph;
+}
+
+// ---------------------------------------------------------------- one explicit Euler step
+// update_relativistic_object (metrics.rs:283-297) = object_position_diff_contr (:223-244) +
+// object_momentum_diff_cov (:247-270), evaluated at the old state, then x += dx*delta,
+// p += dp*delta.
+template <class Shape, class Trig>
+__device__ __forceinline__ void euler_step(const FrameParams& p, Ray& q) {
+    double s, c;
+    Trig::sincos(q.th, s, c);
+    double r, r2, rp;
+    Shape::eval(p, q.l, r, r2, rp);
+    const double s2 = s * s;                                  // sin().powi(2)
+    const double g22c = 1.0 / r2;                             // :90 over :61-63
+    const double g33c = 1.0 / (r2 * s2);                      // :93 over :66-68
+    const double dl = q.pl;                                   // :238  p_l * 1
+    const double dth = q.pth * g22c;                          // :239
+    const double dph = q.pph * g33c;                          // :240
+    const double b2 = q.pth * q.pth + q.pph2 / s2;            // :257
+    const double dpl = (b2 * rp) / ((r * r) * r);             // :261
+    const double dpth = q.pph2 * (c / (r2 * (s2 * s)));       // :262
+    q.l = q.l + dl * p.delta;                                 // :295
+    q.th = q.th + dth * p.delta;
+    q.ph = q.ph + dph * p.delta;
+    q.pl = q.pl + dpl * p.delta;                              // :296
+    q.pth = q.pth + dpth * p.delta;
+}
+
+// ---------------------------------------------------------------- escaped photon -> texel
+// photon_escape_to_pixel (systems.rs:540-561): relativistic_vector_to_direction
+// (metrics.rs:339-349 incl. the frame_field_22 on the phi component, :347), then
+// SphericalImage::get_pixel_from_vector3 (images.rs:171-174 -> :151-167 -> algebra.rs:128-134
+// -> images.rs:115-121).  Returns true when the reference's get_pixel would have indexed out
+// of bounds (images.rs:107-111 panic); the index is clamped instead.
+template <class Shape, class Trig>
+__device__ __forceinline__ bool escaped_texel(const FrameParams& p, const Ray& q, const Background& bg,
+                                              uint32_t& tx, uint32_t& ty) {
+    const double s = Trig::sin(q.th);
+    double r, r2, rp;
+    Shape::eval(p, q.l, r, r2, rp);
+    const double v1 = q.pl;                                   // p_l * g11_contr (= 1)
+    const double v2 = q.pth * (1.0 / r2);
+    const double v3 = q.pph * (1.0 / (r2 * (s * s)));
+    const double dx = v1, dy = v2 * r, dz = v3 * r;           // metrics.rs:345-347
+    double wx, wy, wz;
+    mat3_mul(bg.inv_rot, dx, dy, dz, wx, wy, wz);             // images.rs:139-141
+    const double rn = norm3(wx, wy, wz);
+    double th = acos(wz / rn);                                // algebra.rs:130
+    double ph = atan2(wy, wx);                                // :131
+    normalize_theta_phi(th, ph);                              // :133
+    normalize_theta_phi(th, ph);                              // images.rs:116
+    const double fy = (th / CURVIS_PI) * (double)bg.height;                                   // :118
+    const double fx = rem_euclid(0.5 - ph / (2.0 * CURVIS_PI), 1.0) * (double)bg.width;       // :119
+    ty = __double2uint_rz(fy);  // Rust `as u32`: truncate, saturate, NaN -> 0
+    tx = __double2uint_rz(fx);
+    bool clamped = false;
+    if (tx >= bg.width) { tx = bg.width - 1; clamped = true; }
+    if (ty >= bg.height) { ty = bg.height - 1; clamped = true; }
+    return clamped;
+}
+
+}  // namespace curvis

@@ -1,0 +1,132 @@
+"""Host mirror of reference src/systems.rs ``RelativisticSystem``: the scene (metric, two
+backgrounds, camera) and its ``render_image(max_iterations, max_radius, delta)`` entry point
+(src/systems.rs:307-330), executed by the sm_100a kernels of libcurvis_b200.so through the C
+ABI of include/curvis_gpu.h.  Nothing here computes a pixel on the CPU."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _abi
+from .cameras import Camera
+from .images import SphericalImage
+
+
+class Context:
+    """Owner of a ``curvis_ctx``: the CUDA devices a frame is row-tiled over."""
+
+    def __init__(self, devices: Optional[Sequence[int]] = None):
+        lib = _abi.load_library()
+        self._lib = lib
+        self._ptr = C.c_void_p()
+        if devices:
+            arr = (C.c_int * len(devices))(*devices)
+            _abi.check(lib.curvis_ctx_create(arr, len(devices), C.byref(self._ptr)))
+        else:
+            _abi.check(lib.curvis_ctx_create(None, 0, C.byref(self._ptr)))
+
+    @property
+    def ptr(self):
+        return self._ptr
+
+    def device_count(self) -> int:
+        return int(self._lib.curvis_ctx_device_count(self._ptr))
+
+    def close(self):
+        if self._ptr:
+            self._lib.curvis_ctx_destroy(self._ptr)
+            self._ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def measure_fma_peak(self):
+        f64, f32 = C.c_double(), C.c_double()
+        _abi.check(self._lib.curvis_measure_fma_peak(self._ptr, C.byref(f64), C.byref(f32)), self._ptr)
+        return f64.value, f32.value
+
+
+class RelativisticSystem:
+    """``RelativisticSystem::new(metric, background_positive, background_negative, camera)``
+    (src/systems.rs:283-285).  The backgrounds are uploaded to every device of the context once,
+    here — like the reference, which decodes them once per system (src/rendering.rs:36-39)."""
+
+    def __init__(self, metric, background_positive: SphericalImage, background_negative: SphericalImage,
+                 camera: Camera, context: Optional[Context] = None, devices: Optional[Sequence[int]] = None):
+        self.metric = metric
+        self.background_positive = background_positive
+        self.background_negative = background_negative
+        self.camera = camera
+        self.context = context if context is not None else Context(devices)
+        self._lib = _abi.load_library()
+        self.last_stats: Optional[dict] = None
+        self._upload(+1, background_positive)
+        self._upload(-1, background_negative)
+
+    def _upload(self, side: int, image: SphericalImage) -> None:
+        inv = np.ascontiguousarray(image.orientation().inverse_rotation_matrix(), dtype=np.float64)
+        _abi.check(self._lib.curvis_set_background(
+            self.context.ptr, side, image.rgba8.ctypes.data_as(C.c_void_p), image.width_pixels, image.height_pixels,
+            inv.ctypes.data_as(C.POINTER(C.c_double))), self.context.ptr)
+
+    @staticmethod
+    def _sim(max_iterations, max_radius, delta, precision=_abi.PRECISION_F64, sampling=_abi.SAMPLING_NEAREST):
+        if max_iterations < 0 or max_iterations > 0xFFFFFFFF:
+            raise _abi.CurvisError(_abi.ERR_INVALID_ARGUMENT, "max_iterations must fit u32")
+        return _abi.CurvisSim(max_iterations=int(max_iterations), max_radius=float(max_radius), delta=float(delta),
+                              precision=precision, sampling=sampling)
+
+    def render_image(self, max_iterations: int, max_radius: float, delta: float, **options) -> np.ndarray:
+        """The whole frame, row-tiled over the context's devices; returns uint8 (H, W, 3) —
+        the layout of the ``DynamicImage::ImageRgb8`` the reference returns."""
+        cam = self.camera.as_c()
+        out = np.empty((cam.resolution_height, cam.resolution_width, 3), dtype=np.uint8)
+        sim = self._sim(max_iterations, max_radius, delta, **options)
+        stats = _abi.CurvisStats()
+        m = self.metric.as_c()
+        _abi.check(self._lib.curvis_render_image(self.context.ptr, C.byref(m), C.byref(cam), C.byref(sim),
+                                                 out.ctypes.data_as(C.c_void_p), C.byref(stats)), self.context.ptr)
+        self.last_stats = stats.as_dict()
+        return out
+
+    def render_rows(self, max_iterations: int, max_radius: float, delta: float, row_begin: int, row_end: int,
+                    with_records: bool = False, **options):
+        """Rows [row_begin, row_end) on the context's first device (one rank's tile)."""
+        cam = self.camera.as_c()
+        n_rows = max(0, row_end - row_begin)
+        out = np.empty((n_rows, cam.resolution_width, 3), dtype=np.uint8)
+        rec = np.zeros((n_rows, cam.resolution_width), dtype=_abi.RAY_RECORD_DTYPE) if with_records else None
+        sim = self._sim(max_iterations, max_radius, delta, **options)
+        stats = _abi.CurvisStats()
+        m = self.metric.as_c()
+        _abi.check(self._lib.curvis_render_rows(
+            self.context.ptr, C.byref(m), C.byref(cam), C.byref(sim), int(row_begin), int(row_end),
+            out.ctypes.data_as(C.c_void_p), rec.ctypes.data_as(C.c_void_p) if rec is not None else None,
+            C.byref(stats)), self.context.ptr)
+        self.last_stats = stats.as_dict()
+        return (out, rec) if with_records else out
+
+    def render_rows_device(self, max_iterations: int, max_radius: float, delta: float, row_begin: int, row_end: int,
+                           out_ptr: int, stream_ptr: int = 0, records_ptr: int = 0, want_stats: bool = False,
+                           **options):
+        """Device-resident tile: ``out_ptr`` is a device pointer ((row_end-row_begin)*W*3 bytes)
+        on the context's first device, ``stream_ptr`` a cudaStream_t.  Asynchronous unless
+        ``want_stats``."""
+        cam = self.camera.as_c()
+        sim = self._sim(max_iterations, max_radius, delta, **options)
+        stats = _abi.CurvisStats() if want_stats else None
+        m = self.metric.as_c()
+        _abi.check(self._lib.curvis_render_rows_device(
+            self.context.ptr, C.byref(m), C.byref(cam), C.byref(sim), int(row_begin), int(row_end),
+            C.c_void_p(out_ptr), C.c_void_p(records_ptr) if records_ptr else None,
+            C.c_void_p(stream_ptr) if stream_ptr else None, C.byref(stats) if stats is not None else None),
+            self.context.ptr)
+        if stats is not None:
+            self.last_stats = stats.as_dict()
+            return self.last_stats
+        return None

@@ -1,0 +1,215 @@
+/*
+ * curvis_gpu.h — C ABI of libcurvis_b200.so, the B200 (sm_100a) replacement for the
+ * per-pixel null-geodesic renderer of fragarriss/CurVis.
+ *
+ * The reference has no FFI seam today (it is one single-threaded Rust crate).  The
+ * narrowest seam on the hot path is
+ *
+ *     RelativisticSystem::render_image(&self, max_iterations: u32, max_radius: f64,
+ *                                      delta: f64) -> image::DynamicImage
+ *                                                          (src/systems.rs:307-330)
+ *
+ * with  self = { metric, background_positive, background_negative, camera }
+ *                                                          (src/systems.rs:68-73).
+ *
+ * Everything render_image reads crosses this boundary as plain-old-data (doubles,
+ * fixed-width integers, raw pointers + sizes); every struct below can be mirrored by a
+ * Rust `#[repr(C)]` struct field for field (INTEGRATION.md shows the binding).
+ * No torch / C++ types appear in any signature.  No entry point aborts or unwinds:
+ * each returns a curvis_status and leaves a message for curvis_last_error().
+ *
+ * Threading: one context is used by one host thread at a time; distinct contexts may
+ * be used concurrently.  A context keeps no caller pointer after a call returns.
+ */
+#ifndef CURVIS_GPU_H
+#define CURVIS_GPU_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CURVIS_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------
+ * The reference panics (src/systems.rs:122-124, src/algebra.rs:19-21, src/cameras.rs:
+ * 94-105, src/metrics.rs:407-409 / 446-456, image index out of bounds) or bubbles a
+ * Result<(), String> (src/rendering.rs:85).  Across the C ABI each becomes a code. */
+typedef enum curvis_status {
+    CURVIS_OK = 0,
+    CURVIS_ERR_INVALID_ARGUMENT = 1,      /* null pointer, zero resolution, bad enum, bad row range */
+    CURVIS_ERR_CAMERA_OUTSIDE_RADIUS = 2, /* |l_camera| > max_radius   (systems.rs:122-124 panic)   */
+    CURVIS_ERR_PARALLEL_VECTORS = 3,      /* forward x up == 0         (algebra.rs:19-21 panic)     */
+    CURVIS_ERR_INVALID_METRIC = 4,        /* rho/m/a <= 0              (metrics.rs:407-409,446-456) */
+    CURVIS_ERR_NO_BACKGROUND = 5,         /* render before both backgrounds were set                */
+    CURVIS_ERR_CUDA = 6,                  /* a CUDA runtime call failed; see curvis_last_error      */
+    CURVIS_ERR_OUT_OF_MEMORY = 7,
+    CURVIS_ERR_NO_DEVICE = 8,             /* no sm_100 device visible: there is NO CPU fallback     */
+    CURVIS_ERR_UNSUPPORTED = 9            /* e.g. a sim option this build does not implement        */
+} curvis_status;
+
+/* ---- metric: closed enum + parameters ----------------------------------------------
+ * Replaces the generic `M: DiagonalSphericalMetric` (src/metrics.rs:40-44).  Kernels are
+ * template-instantiated per kind; arbitrary user metrics cannot cross the ABI. */
+typedef enum curvis_metric_kind {
+    CURVIS_METRIC_ELLIS = 0,        /* EllisMetric{rho}             src/metrics.rs:399-421 */
+    CURVIS_METRIC_INTERSTELLAR = 1, /* InterstellarMetric{m,a,rho}  src/metrics.rs:431-487 */
+    CURVIS_METRIC_FLAT = 2          /* FlatSphericalMetric{}        src/metrics.rs:492-505 */
+} curvis_metric_kind;
+
+typedef struct curvis_metric {
+    int32_t kind;  /* curvis_metric_kind */
+    int32_t _pad;
+    double rho;    /* Ellis, Interstellar */
+    double m;      /* Interstellar        */
+    double a;      /* Interstellar        */
+} curvis_metric;
+
+/* ---- camera --------------------------------------------------------------------------
+ * The fields Camera (src/cameras.rs:30-43) holds after Camera::new ran.  Fill it with
+ * curvis_camera_init() (which restates Camera::new + Orientation::new) or, from a Rust
+ * host, copy the values nalgebra already computed. */
+typedef struct curvis_camera {
+    double position[4];      /* (t, l, theta, phi), contravariant   cameras.rs:31           */
+    double cam_to_world[9];  /* row-major 3x3                        cameras.rs:42           */
+    double focal_length;     /*                                      cameras.rs:35           */
+    double sensor_width;     /*                                      cameras.rs:36, :107-110 */
+    double sensor_height;    /*                                      cameras.rs:37           */
+    uint32_t resolution_width;
+    uint32_t resolution_height;
+} curvis_camera;
+
+/* ---- simulation settings -------------------------------------------------------------
+ * The three arguments of render_image (systems.rs:307-312) plus opt-in extensions.  All
+ * extension fields are 0 in parity mode. */
+typedef enum curvis_precision {
+    CURVIS_PRECISION_F64 = 0, /* reference arithmetic: IEEE double, reference operation order */
+    CURVIS_PRECISION_F32 = 1  /* extension: fp32 state (not bit-comparable)    */
+} curvis_precision;
+
+typedef enum curvis_sampling {
+    CURVIS_SAMPLING_NEAREST = 0, /* images.rs:115-121: truncating nearest texel, u8 copy */
+    CURVIS_SAMPLING_BILINEAR = 1 /* extension: fp32 2x2 tap (wrap in x, clamp in y)       */
+} curvis_sampling;
+
+typedef struct curvis_sim {
+    uint32_t max_iterations; /* systems.rs:309 */
+    uint32_t _pad;
+    double max_radius;       /* systems.rs:310 */
+    double delta;            /* systems.rs:311 */
+    int32_t precision;       /* curvis_precision */
+    int32_t sampling;        /* curvis_sampling  */
+} curvis_sim;
+
+/* ---- per-frame counters (the reference has none) ----------------- */
+typedef struct curvis_stats {
+    uint64_t total_steps;   /* sum over rays of Euler steps executed (early exit counted) */
+    uint64_t n_rays;
+    uint64_t n_positive;    /* PhotonEscape::PositiveSpace  systems.rs:129-131 */
+    uint64_t n_negative;    /* PhotonEscape::NegativeSpace  systems.rs:132-134 */
+    uint64_t n_not_escaped; /* PhotonEscape::NotEscaped     systems.rs:137     */
+    uint64_t n_clamped;     /* texel index the reference would have panicked on (images.rs:107-111) */
+    uint64_t n_big_theta;   /* rays whose |theta| left the fast range-reduction domain */
+    double kernel_ms;       /* device time of the render kernel(s), CUDA events, max over devices */
+    double total_ms;        /* host wall time of the call, copies included */
+} curvis_stats;
+
+/* ---- per-ray record (debug / parity; optional) ---------------------------------------
+ * Final photon state as escape_photon left it (systems.rs:115-139) and the texel chosen by
+ * images.rs:115-121.  side: +1 PositiveSpace, -1 NegativeSpace, 0 NotEscaped. */
+typedef struct curvis_ray_record {
+    double l, theta, phi, p_l, p_theta, p_phi;
+    uint32_t steps;
+    int32_t side;
+    uint32_t texel_x, texel_y;
+} curvis_ray_record;
+
+typedef struct curvis_ctx curvis_ctx;
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+
+/* Opens `n_devices` CUDA devices (ordinals in `devices`; NULL/0 = every visible device).
+ * A frame is row-tiled over the context's devices.  Fails with CURVIS_ERR_NO_DEVICE when no
+ * CUDA device is present — the library never computes on the CPU. */
+int curvis_ctx_create(const int* devices, int n_devices, curvis_ctx** out);
+void curvis_ctx_destroy(curvis_ctx* ctx);
+
+/* Message of the last failing call on `ctx` (or of the last failing ctx-less call when
+ * ctx == NULL).  Valid until the next call on the same context/thread. */
+const char* curvis_last_error(const curvis_ctx* ctx);
+int curvis_abi_version(void);
+int curvis_ctx_device_count(const curvis_ctx* ctx);
+
+/* ---- host-side setup helpers (pure CPU, no device needed) ----------------------------- */
+
+/* Orientation::new (src/algebra.rs:16-38) + rotation_matrix_from_forward_up_pairs
+ * (:64-74): rotation taking (x, z) to (forward, orthogonalised up).  rot / inv_rot are
+ * row-major 3x3; any output may be NULL. */
+int curvis_orientation(const double forward[3], const double up[3],
+                       double rot[9], double inv_rot[9], double up_orthogonal[3]);
+
+/* Camera::new (src/cameras.rs:79-122). */
+int curvis_camera_init(curvis_camera* cam, const double position[4],
+                       const double forward[3], const double up[3],
+                       double focal_length, double sensor_diagonal,
+                       uint32_t resolution_width, uint32_t resolution_height);
+
+/* EllisMetric::new / InterstellarMetric::new / FlatSphericalMetric::new parameter checks
+ * (src/metrics.rs:404-414, :441-459, :496-498). */
+int curvis_metric_validate(const curvis_metric* metric);
+
+/* ---- scene --------------------------------------------------------------------------- */
+
+/* SphericalImage::new (src/images.rs:71-89): side > 0 = background_positive, side < 0 =
+ * background_negative (systems.rs:70-71).  `rgba8` is what DynamicImage::get_pixel would
+ * return for every texel (images.rs:107-111), row-major, 4 bytes per texel; it is copied
+ * to every device of the context.  `inv_rot` = the image orientation's inverse rotation
+ * (images.rs:132-142), row-major; NULL = identity (images are always loaded with
+ * forward/up = None, rendering.rs:36-39). */
+int curvis_set_background(curvis_ctx* ctx, int side, const uint8_t* rgba8,
+                          uint32_t width, uint32_t height, const double inv_rot[9]);
+
+/* ---- the hot path -------------------------------------------------------------------- */
+
+/* RelativisticSystem::render_image (src/systems.rs:307-330).  Renders the whole frame,
+ * row-tiled over the context's devices, into the HOST buffer `out_rgb8`
+ * (W*H*3 bytes, row-major: out[(y*W + x)*3 + c], the layout of DynamicImage::ImageRgb8).
+ * `stats` may be NULL. */
+int curvis_render_image(curvis_ctx* ctx, const curvis_metric* metric,
+                        const curvis_camera* camera, const curvis_sim* sim,
+                        uint8_t* out_rgb8, curvis_stats* stats);
+
+/* Rows [row_begin, row_end) of the same frame on the context's FIRST device, into host
+ * buffers holding only those rows.  `records` (nullable) receives one curvis_ray_record per
+ * pixel of the tile, row-major.  This is the unit a multi-process host (one rank per GPU)
+ * calls before its own all-gather. */
+int curvis_render_rows(curvis_ctx* ctx, const curvis_metric* metric,
+                       const curvis_camera* camera, const curvis_sim* sim,
+                       uint32_t row_begin, uint32_t row_end,
+                       uint8_t* out_rgb8_rows, curvis_ray_record* records,
+                       curvis_stats* stats);
+
+/* Same tile, device-resident: `d_out_rgb8_rows` is a DEVICE pointer on the context's first
+ * device ((row_end-row_begin)*W*3 bytes), `d_records` a nullable device pointer, `stream` a
+ * cudaStream_t passed as void* (NULL = the legacy default stream).  The launch is
+ * asynchronous on `stream`; when `stats` is non-NULL the call synchronises the stream and
+ * fills it.  Used to keep the frame in HBM for an NCCL all-gather or a following kernel. */
+int curvis_render_rows_device(curvis_ctx* ctx, const curvis_metric* metric,
+                              const curvis_camera* camera, const curvis_sim* sim,
+                              uint32_t row_begin, uint32_t row_end,
+                              void* d_out_rgb8_rows, void* d_records,
+                              void* stream, curvis_stats* stats);
+
+/* ---- measurement helper -------------------------------------------------------------- */
+
+/* Runs an FMA-only micro-kernel on the context's first device and returns the achieved
+ * fp64 and fp32 FMA rates in TFLOP/s (2 flop per FMA).  bench.py uses it as the measured
+ * compute-roofline denominator (MEASURED_PEAKS.json has no fp64/fp32 ALU entry). */
+int curvis_measure_fma_peak(curvis_ctx* ctx, double* fp64_tflops, double* fp32_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CURVIS_GPU_H */

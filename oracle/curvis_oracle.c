@@ -1,0 +1,457 @@
+/*
+ * curvis_oracle.c — CPU restatement (fp64, reference operation order) of CurVis's
+ * per-pixel null-geodesic renderer.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This file is the parity oracle and the CPU baseline.  Only tests/, bench.py's
+ * cpu_baseline / --impl reference legs and __graft_entry__.smoke() may load it; the
+ * product (curvis_b200/, libcurvis_b200.so) never links, imports or calls it.
+ *
+ * PINNING STATUS.  The reference is Rust and no cargo/rustc exists in this image, so the
+ * reference itself cannot be run here.  What IS pinned (tests/test_oracle_kat.py):
+ *   - every known-answer test the reference holds on this path: src/algebra.rs:143-309
+ *     (camera basis exact, 13 theta/phi KATs, vec3<->theta/phi round trip),
+ *     src/metrics.rs:515-541 (new_photon <-> direction round trip), and the disabled
+ *     angle-convention KATs of src/images.rs:353-398.
+ *   What is NOT pinned by any reference test or fixture: escape_photon, the Euler step
+ *   values, render_image and the texel mapping — for those rows the status is
+ *   "PARITY UNPINNED": this restatement, reviewed line by line against the cited
+ *   reference lines, is the oracle (plus SURVEY.md section 8c's independent probe
+ *   values, which a separate numpy restatement produced).
+ *
+ * Bit-faithfulness rules (why this should equal a Linux/glibc build of the reference):
+ *   Rust never contracts a*b+c to an FMA and f64::{sin,cos,acos,atan,atan2,ln,sqrt}
+ *   resolve to the platform libm.  So: build with -ffp-contract=off, no -ffast-math,
+ *   call glibc libm, keep the reference's association order.  powi(2) = x*x,
+ *   powi(3) = (x*x)*x, powi(-1) = 1.0/x.
+ *
+ * Third-party arithmetic that is NOT under /root/reference (restated from the published
+ * behaviour of the pinned versions, Cargo.lock:623-624 nalgebra 0.33.0):
+ *   Vector3::norm      = sqrt((x*x + y*y) + z*z)
+ *   Vector3::normalize = v / norm (three divisions)
+ *   Vector3::cross     = (ay*bz - az*by, az*bx - ax*bz, ax*by - ay*bx)
+ *   Rotation3::face_towards(dir, up): z' = dir.normalize(); x' = up.cross(z').normalize();
+ *                       y' = z'.cross(x').normalize(); columns (x', y', z')
+ *   Rotation3::inverse = transpose;  R*S and R*v accumulate k = 0,1,2 left to right.
+ * These agree with the reference's own exact-equality tests (algebra.rs:143-176, :200-209).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include <stdatomic.h>
+#include "../include/curvis_gpu.h"
+
+#define ORACLE_PI 3.14159265358979323846264338327950288 /* std::f64::consts::PI */
+
+/* ------------------------------------------------------------------ nalgebra restatements */
+
+static double v3_norm(const double v[3]) { return sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]); }
+
+static void v3_normalize(const double v[3], double o[3]) {
+    double n = v3_norm(v);
+    o[0] = v[0] / n; o[1] = v[1] / n; o[2] = v[2] / n;
+}
+
+static void v3_cross(const double a[3], const double b[3], double o[3]) {
+    double x = a[1] * b[2] - a[2] * b[1];
+    double y = a[2] * b[0] - a[0] * b[2];
+    double z = a[0] * b[1] - a[1] * b[0];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+
+/* row-major 3x3 times vector, k accumulated left to right (nalgebra gemv/axcpy order) */
+static void m3_mul_v(const double m[9], const double v[3], double o[3]) {
+    for (int i = 0; i < 3; ++i)
+        o[i] = (m[3 * i + 0] * v[0] + m[3 * i + 1] * v[1]) + m[3 * i + 2] * v[2];
+}
+
+static void m3_mul_m(const double a[9], const double b[9], double o[9]) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            o[3 * i + j] = (a[3 * i + 0] * b[0 + j] + a[3 * i + 1] * b[3 + j]) + a[3 * i + 2] * b[6 + j];
+}
+
+static void m3_transpose(const double a[9], double o[9]) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) o[3 * j + i] = a[3 * i + j];
+}
+
+/* nalgebra 0.33 Rotation3::face_towards(dir, up) */
+static void face_towards(const double dir[3], const double up[3], double m[9]) {
+    double z[3], x[3], y[3], t[3];
+    v3_normalize(dir, z);
+    v3_cross(up, z, t); v3_normalize(t, x);
+    v3_cross(z, x, t); v3_normalize(t, y);
+    for (int i = 0; i < 3; ++i) { m[3 * i + 0] = x[i]; m[3 * i + 1] = y[i]; m[3 * i + 2] = z[i]; }
+}
+
+/* ------------------------------------------------------------------ algebra.rs */
+
+/* Orientation::new, src/algebra.rs:16-38 with rotation_matrix_from_forward_up_pairs :64-74.
+ * Returns 1 when the reference would panic (:19-21). */
+int oracle_orientation(const double forward[3], const double up[3],
+                       double rot[9], double inv_rot[9], double up_orth[3]) {
+    double c[3];
+    v3_cross(forward, up, c);
+    if (v3_norm(c) == 0.0) return 1; /* "Forward and up vectors must not be parallel" */
+    const double ex[3] = {1.0, 0.0, 0.0}, ez[3] = {0.0, 0.0, 1.0};
+    double r1[9], r2[9], r1t[9], r[9], rt[9];
+    face_towards(ex, ez, r1);       /* :71 */
+    face_towards(forward, up, r2);  /* :72 */
+    m3_transpose(r1, r1t);
+    m3_mul_m(r2, r1t, r);           /* :73 rotation2*rotation1.inverse() */
+    m3_transpose(r, rt);            /* :27 */
+    if (rot) memcpy(rot, r, sizeof r);
+    if (inv_rot) memcpy(inv_rot, rt, sizeof rt);
+    if (up_orth) m3_mul_v(r, ez, up_orth); /* :30 */
+    return 0;
+}
+
+/* f64::rem_euclid (Rust core): r = self % rhs; if r < 0 { r + rhs.abs() } else { r } */
+static double rem_euclid(double x, double rhs) {
+    double r = fmod(x, rhs);
+    return (r < 0.0) ? r + fabs(rhs) : r;
+}
+
+/* normalize_theta_phi, src/algebra.rs:106-116 */
+void oracle_normalize_theta_phi(double theta, double phi, double* theta_o, double* phi_o) {
+    if (theta < 0.0) { theta = fabs(theta); phi = phi + ORACLE_PI; }
+    *theta_o = theta;
+    *phi_o = rem_euclid(phi, 2.0 * ORACLE_PI);
+}
+
+/* vector3_from_theta_phi, src/algebra.rs:118-126 */
+void oracle_vector3_from_theta_phi(double theta, double phi, double o[3]) {
+    oracle_normalize_theta_phi(theta, phi, &theta, &phi);
+    o[0] = sin(theta) * cos(phi);
+    o[1] = sin(theta) * sin(phi);
+    o[2] = cos(theta);
+}
+
+/* theta_phi_from_vector3, src/algebra.rs:128-134 */
+void oracle_theta_phi_from_vector3(const double v[3], double* theta_o, double* phi_o) {
+    double r = v3_norm(v);
+    double theta = acos(v[2] / r);
+    double phi = atan2(v[1], v[0]);
+    oracle_normalize_theta_phi(theta, phi, theta_o, phi_o);
+}
+
+/* ------------------------------------------------------------------ cameras.rs */
+
+/* Camera::new, src/cameras.rs:79-122.  1 = parallel forward/up, 2 = argument check failed. */
+int oracle_camera_init(curvis_camera* cam, const double position[4], const double forward[3],
+                       const double up[3], double focal_length, double sensor_diagonal,
+                       uint32_t w, uint32_t h) {
+    if (focal_length <= 0.0 || sensor_diagonal <= 0.0 || w == 0 || h == 0) return 2; /* :94-102 */
+    if (oracle_orientation(forward, up, cam->cam_to_world, NULL, NULL)) return 1;    /* :104-105 */
+    double aspect = (double)w / (double)h;                                           /* :107 */
+    double aspect2 = aspect * aspect;                                                /* :108 */
+    cam->sensor_height = sqrt((sensor_diagonal * sensor_diagonal) / (aspect2 + 1.0));/* :109 */
+    cam->sensor_width = aspect * cam->sensor_height;                                 /* :110 */
+    memcpy(cam->position, position, 4 * sizeof(double));
+    cam->focal_length = focal_length;
+    cam->resolution_width = w;
+    cam->resolution_height = h;
+    return 0;
+}
+
+/* outward_vector_on_camera_space, src/cameras.rs:150-164 */
+void oracle_outward_vector_on_camera_space(const curvis_camera* cam, uint32_t px, uint32_t py, double o[3]) {
+    double res_x = (double)cam->resolution_width, res_y = (double)cam->resolution_height;
+    double h = 0.5 - ((double)py / res_y);
+    double w = ((double)px / res_x) - 0.5;
+    double v[3];
+    v[0] = cam->focal_length * 1.0;
+    v[1] = -cam->sensor_width * w;
+    v[2] = cam->sensor_height * h;
+    v3_normalize(v, o);
+}
+
+/* outward_vector_on_world_space_from_x_y, src/cameras.rs:169-172 */
+void oracle_outward_vector_on_world_space(const curvis_camera* cam, uint32_t px, uint32_t py, double o[3]) {
+    double v[3];
+    oracle_outward_vector_on_camera_space(cam, px, py, v);
+    m3_mul_v(cam->cam_to_world, v, o);
+}
+
+/* ------------------------------------------------------------------ metrics.rs */
+
+/* r, r_squared, r_derivative: Ellis src/metrics.rs:417-421, Interstellar :461-485, Flat :501-505 */
+static double metric_r(const curvis_metric* g, double l) {
+    switch (g->kind) {
+    case CURVIS_METRIC_ELLIS: return sqrt(g->rho * g->rho + l * l);
+    case CURVIS_METRIC_INTERSTELLAR:
+        if (fabs(l) > g->a) {
+            double x = 2.0 * (fabs(l) - g->a) / (ORACLE_PI * g->m);
+            return g->rho + g->m * (x * atan(x) - log(1.0 + x * x) / 2.0);
+        }
+        return g->rho;
+    default: return l;
+    }
+}
+
+static double metric_r_squared(const curvis_metric* g, double l) {
+    switch (g->kind) {
+    case CURVIS_METRIC_ELLIS: return g->rho * g->rho + l * l;
+    case CURVIS_METRIC_INTERSTELLAR: { double r = metric_r(g, l); return r * r; }
+    default: return l * l;
+    }
+}
+
+/* f64::signum: 1.0 for +0.0 and positives, -1.0 for -0.0 and negatives, NaN for NaN */
+static double f64_signum(double x) { return isnan(x) ? x : copysign(1.0, x); }
+
+static double metric_r_derivative(const curvis_metric* g, double l) {
+    switch (g->kind) {
+    case CURVIS_METRIC_ELLIS: return l / metric_r(g, l);
+    case CURVIS_METRIC_INTERSTELLAR:
+        if (fabs(l) > g->a) {
+            double x = 2.0 * (fabs(l) - g->a) / (ORACLE_PI * g->m);
+            return (2.0 / ORACLE_PI) * f64_signum(l) * atan(x);
+        }
+        return 0.0;
+    default: return 1.0;
+    }
+}
+
+/* photon = position x[4] (contravariant) + momentum p[4] (covariant) */
+typedef struct oracle_photon { double x[4]; double p[4]; } oracle_photon;
+
+/* new_photon, src/metrics.rs:301-334 */
+void oracle_new_photon(const curvis_metric* g, const double position[4], const double direction[3], oracle_photon* ph) {
+    double d[3];
+    v3_normalize(direction, d); /* :320 */
+    memcpy(ph->x, position, 4 * sizeof(double));
+    ph->p[0] = 1.0;
+    ph->p[1] = d[0];
+    ph->p[2] = d[1] * metric_r(g, position[1]);
+    ph->p[3] = d[2] * metric_r(g, position[1]) * sin(position[2]);
+}
+
+/* update_relativistic_object, src/metrics.rs:283-297 (momentum already covariant, so the
+ * branch at :286-288 is not taken), with object_position_diff_contr :223-244 and
+ * object_momentum_diff_cov :247-270. */
+void oracle_step(const curvis_metric* g, oracle_photon* ph, double delta) {
+    const double l = ph->x[1], th = ph->x[2];
+    /* contravariant metric components, :84-93 on top of :49-68 */
+    double g00c = 1.0 / -1.0;
+    double g11c = 1.0 / 1.0;
+    double g22c = 1.0 / metric_r_squared(g, l);
+    double s = sin(th);
+    double g33c = 1.0 / (metric_r_squared(g, l) * (s * s));
+    double dx0 = ph->p[0] * g00c, dx1 = ph->p[1] * g11c, dx2 = ph->p[2] * g22c, dx3 = ph->p[3] * g33c; /* :237-240 */
+    /* :257 */
+    double b2 = ph->p[2] * ph->p[2] + (ph->p[3] * ph->p[3]) / (s * s);
+    double r = metric_r(g, l);
+    double dp1 = b2 * metric_r_derivative(g, l) / ((r * r) * r);                        /* :261 */
+    double dp2 = (ph->p[3] * ph->p[3]) * (cos(th) / (metric_r_squared(g, l) * ((s * s) * s))); /* :262 */
+    /* :295-296 */
+    ph->x[0] = ph->x[0] + dx0 * delta; ph->x[1] = ph->x[1] + dx1 * delta;
+    ph->x[2] = ph->x[2] + dx2 * delta; ph->x[3] = ph->x[3] + dx3 * delta;
+    ph->p[0] = ph->p[0] + 0.0 * delta; ph->p[1] = ph->p[1] + dp1 * delta;
+    ph->p[2] = ph->p[2] + dp2 * delta; ph->p[3] = ph->p[3] + 0.0 * delta;
+}
+
+/* escape_photon, src/systems.rs:115-139.  Returns side (+1/-1/0); -2 = the panic at :122-124. */
+int oracle_escape_photon(const curvis_metric* g, oracle_photon* ph, double delta,
+                         uint32_t max_iterations, double max_radius, uint32_t* steps) {
+    *steps = 0;
+    if (fabs(ph->x[1]) > max_radius) return -2;
+    for (uint32_t i = 0; i < max_iterations; ++i) {
+        oracle_step(g, ph, delta);
+        *steps = i + 1;
+        if (ph->x[1] > max_radius) return 1;
+        else if (ph->x[1] < -max_radius) return -1;
+    }
+    return 0;
+}
+
+/* relativistic_vector_to_direction for a covariant vector, src/metrics.rs:339-349 via
+ * to_contravariant :190-203.  Note :347 multiplies the phi component by frame_field_22. */
+void oracle_relativistic_vector_to_direction(const curvis_metric* g, const double p[4], const double x[4], double o[3]) {
+    double s = sin(x[2]);
+    double v1 = p[1] * (1.0 / 1.0);
+    double v2 = p[2] * (1.0 / metric_r_squared(g, x[1]));
+    double v3 = p[3] * (1.0 / (metric_r_squared(g, x[1]) * (s * s)));
+    o[0] = v1 * 1.0;
+    o[1] = v2 * metric_r(g, x[1]);
+    o[2] = v3 * metric_r(g, x[1]);
+}
+
+/* squared_norm / dot_product, src/metrics.rs:355-383 (tests only) */
+double oracle_squared_norm_cov(const curvis_metric* g, const double p_cov[4], const double x[4]) {
+    double s = sin(x[2]);
+    double gii[4] = {-1.0, 1.0, metric_r_squared(g, x[1]), metric_r_squared(g, x[1]) * (s * s)};
+    double result = 0.0;
+    for (int i = 0; i < 4; ++i) {
+        double vc = p_cov[i] * (1.0 / gii[i]);
+        result += vc * vc * gii[i];
+    }
+    return result;
+}
+
+/* ------------------------------------------------------------------ images.rs */
+
+/* Rust `f64 as u32`: saturating, NaN -> 0 */
+static uint32_t f64_as_u32(double v) {
+    if (!(v == v)) return 0;
+    if (v <= 0.0) return 0;
+    if (v >= 4294967295.0) return 4294967295u;
+    return (uint32_t)v;
+}
+
+/* theta_phi_of_image_from_vector3 src/images.rs:151-167 + pixel_indexes_x_y_from_theta_phi_of_image
+ * :115-121.  inv_rot: image orientation inverse (identity by default). */
+void oracle_texel_from_vector3(const double inv_rot[9], const double v_world[3], uint32_t bg_w, uint32_t bg_h,
+                               uint32_t* x_o, uint32_t* y_o, double* theta_o, double* phi_o) {
+    double w[3], theta, phi;
+    m3_mul_v(inv_rot, v_world, w);                 /* images.rs:139-141 */
+    oracle_theta_phi_from_vector3(w, &theta, &phi);/* :166 */
+    if (theta_o) *theta_o = theta;
+    if (phi_o) *phi_o = phi;
+    oracle_normalize_theta_phi(theta, phi, &theta, &phi); /* :116 */
+    *y_o = f64_as_u32((theta / ORACLE_PI) * (double)bg_h);                               /* :118 */
+    *x_o = f64_as_u32(rem_euclid(0.5 - phi / (2.0 * ORACLE_PI), 1.0) * (double)bg_w);   /* :119 */
+}
+
+/* ------------------------------------------------------------------ systems.rs */
+
+typedef struct oracle_background { const uint8_t* rgba8; uint32_t w, h; double inv_rot[9]; } oracle_background;
+
+/* One pixel of render_image (src/systems.rs:321-324): camera_pixels_x_y_to_photon :531-534,
+ * escape_photon, photon_escape_to_pixel :540-561.  rec may be NULL.  Returns the side, or -2
+ * on the :122-124 panic.  *clamped is set when the reference's get_pixel would index out of
+ * bounds (images.rs:107-111 panic); the texel is then clamped like the GPU does. */
+static int oracle_pixel(const curvis_metric* g, const curvis_camera* cam, const curvis_sim* sim,
+                        const oracle_background* pos, const oracle_background* neg,
+                        uint32_t px, uint32_t py, uint8_t rgb[3], curvis_ray_record* rec, int* clamped) {
+    double dir[3];
+    oracle_photon ph;
+    uint32_t steps;
+    oracle_outward_vector_on_world_space(cam, px, py, dir);
+    oracle_new_photon(g, cam->position, dir, &ph);
+    int side = oracle_escape_photon(g, &ph, sim->delta, sim->max_iterations, sim->max_radius, &steps);
+    if (side == -2) return -2;
+    uint32_t tx = 0, ty = 0;
+    *clamped = 0;
+    if (side == 0) {
+        rgb[0] = rgb[1] = rgb[2] = 0; /* :556-558 */
+    } else {
+        const oracle_background* bg = side > 0 ? pos : neg;
+        double d[3];
+        oracle_relativistic_vector_to_direction(g, ph.p, ph.x, d);
+        oracle_texel_from_vector3(bg->inv_rot, d, bg->w, bg->h, &tx, &ty, NULL, NULL);
+        if (tx >= bg->w) { tx = bg->w - 1; *clamped = 1; }
+        if (ty >= bg->h) { ty = bg->h - 1; *clamped = 1; }
+        const uint8_t* t = bg->rgba8 + ((size_t)ty * bg->w + tx) * 4;
+        rgb[0] = t[0]; rgb[1] = t[1]; rgb[2] = t[2]; /* put_pixel on ImageRgb8 drops alpha, :324 */
+    }
+    if (rec) {
+        rec->l = ph.x[1]; rec->theta = ph.x[2]; rec->phi = ph.x[3];
+        rec->p_l = ph.p[1]; rec->p_theta = ph.p[2]; rec->p_phi = ph.p[3];
+        rec->steps = steps; rec->side = side; rec->texel_x = tx; rec->texel_y = ty;
+    }
+    return side;
+}
+
+/* render_image, src/systems.rs:307-330, restricted to rows [row_begin,row_end) taken every
+ * `row_stride` rows (stride 1 = the tile; >1 = the bounded CPU-baseline sample).  Outputs hold
+ * only the visited rows, packed.  n_threads > 1 splits the columns over pthreads (parity data
+ * only — the reference is single-threaded).  The reference's loop is x outer / y inner
+ * (:316-320); pixels are independent so the visiting order does not change any value. */
+typedef struct oracle_job {
+    const curvis_metric* g; const curvis_camera* cam; const curvis_sim* sim;
+    const oracle_background *pos, *neg;
+    uint32_t row_begin, row_stride; int64_t n_rows;
+    uint8_t* out_rgb8; curvis_ray_record* records;
+    atomic_long next_col;
+    uint64_t tot, np, nn, n0, nc, nr; /* per-worker copies are summed by the caller */
+} oracle_job;
+
+typedef struct oracle_worker { oracle_job* job; uint64_t tot, np, nn, n0, nc, nr; } oracle_worker;
+
+static void* oracle_worker_main(void* arg) {
+    oracle_worker* wk = (oracle_worker*)arg;
+    oracle_job* jb = wk->job;
+    const int64_t W = (int64_t)jb->cam->resolution_width;
+    for (;;) {
+        int64_t i = atomic_fetch_add(&jb->next_col, 1);
+        if (i >= W) break;
+        for (int64_t jr = 0; jr < jb->n_rows; ++jr) {
+            uint32_t j = jb->row_begin + (uint32_t)jr * jb->row_stride;
+            uint8_t rgb[3] = {0, 0, 0};
+            curvis_ray_record rec;
+            int clamped = 0;
+            int side = oracle_pixel(jb->g, jb->cam, jb->sim, jb->pos, jb->neg, (uint32_t)i, j, rgb, &rec, &clamped);
+            size_t o = (size_t)jr * (size_t)W + (size_t)i;
+            if (jb->out_rgb8) { jb->out_rgb8[o * 3 + 0] = rgb[0]; jb->out_rgb8[o * 3 + 1] = rgb[1]; jb->out_rgb8[o * 3 + 2] = rgb[2]; }
+            if (jb->records) jb->records[o] = rec;
+            wk->tot += rec.steps; wk->nr += 1; wk->nc += (uint64_t)clamped;
+            if (side > 0) wk->np += 1; else if (side < 0) wk->nn += 1; else wk->n0 += 1;
+        }
+    }
+    return NULL;
+}
+
+int oracle_render_rows(const curvis_metric* g, const curvis_camera* cam, const curvis_sim* sim,
+                       const uint8_t* bg_pos, uint32_t pos_w, uint32_t pos_h, const double* pos_inv_rot,
+                       const uint8_t* bg_neg, uint32_t neg_w, uint32_t neg_h, const double* neg_inv_rot,
+                       uint32_t row_begin, uint32_t row_end, uint32_t row_stride,
+                       uint8_t* out_rgb8, curvis_ray_record* records, curvis_stats* stats, int n_threads) {
+    static const double ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    oracle_background pos = {bg_pos, pos_w, pos_h, {0}}, neg = {bg_neg, neg_w, neg_h, {0}};
+    memcpy(pos.inv_rot, pos_inv_rot ? pos_inv_rot : ident, sizeof ident);
+    memcpy(neg.inv_rot, neg_inv_rot ? neg_inv_rot : ident, sizeof ident);
+    if (row_stride == 0) row_stride = 1;
+    if (fabs(cam->position[1]) > sim->max_radius) return CURVIS_ERR_CAMERA_OUTSIDE_RADIUS; /* systems.rs:122-124 */
+    oracle_job jb;
+    memset(&jb, 0, sizeof jb);
+    jb.g = g; jb.cam = cam; jb.sim = sim; jb.pos = &pos; jb.neg = &neg;
+    jb.row_begin = row_begin; jb.row_stride = row_stride;
+    jb.n_rows = row_end > row_begin ? (int64_t)((row_end - row_begin + row_stride - 1) / row_stride) : 0;
+    jb.out_rgb8 = out_rgb8; jb.records = records;
+    atomic_init(&jb.next_col, 0);
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 256) n_threads = 256;
+    oracle_worker wk[256];
+    pthread_t th[256];
+    memset(wk, 0, sizeof(oracle_worker) * (size_t)n_threads);
+    for (int t = 0; t < n_threads; ++t) wk[t].job = &jb;
+    if (n_threads == 1) {
+        oracle_worker_main(&wk[0]);
+    } else {
+        for (int t = 0; t < n_threads; ++t) pthread_create(&th[t], NULL, oracle_worker_main, &wk[t]);
+        for (int t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
+    }
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        for (int t = 0; t < n_threads; ++t) {
+            stats->total_steps += wk[t].tot; stats->n_rays += wk[t].nr; stats->n_positive += wk[t].np;
+            stats->n_negative += wk[t].nn; stats->n_not_escaped += wk[t].n0; stats->n_clamped += wk[t].nc;
+        }
+    }
+    return CURVIS_OK;
+}
+
+/* Trajectory of a single pixel's photon for the first n steps (debug/tests):
+ * out[k*8 + 0..3] = x after step k, out[k*8 + 4..7] = p after step k. */
+void oracle_trajectory(const curvis_metric* g, const double position[4], const double direction[3],
+                       double delta, uint32_t n, double* out) {
+    oracle_photon ph;
+    oracle_new_photon(g, position, direction, &ph);
+    for (uint32_t k = 0; k < n; ++k) {
+        oracle_step(g, &ph, delta);
+        memcpy(out + (size_t)k * 8, ph.x, 4 * sizeof(double));
+        memcpy(out + (size_t)k * 8 + 4, ph.p, 4 * sizeof(double));
+    }
+}
+
+int oracle_metric_validate(const curvis_metric* g) {
+    switch (g->kind) {
+    case CURVIS_METRIC_ELLIS: return g->rho > 0.0 ? 0 : CURVIS_ERR_INVALID_METRIC;
+    case CURVIS_METRIC_INTERSTELLAR: return (g->m > 0.0 && g->a > 0.0 && g->rho > 0.0) ? 0 : CURVIS_ERR_INVALID_METRIC;
+    case CURVIS_METRIC_FLAT: return 0;
+    default: return CURVIS_ERR_INVALID_ARGUMENT;
+    }
+}

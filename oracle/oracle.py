@@ -1,0 +1,190 @@
+"""ctypes wrapper of oracle/libcurvis_oracle.so — the CPU restatement of the reference's
+``render_image`` path (oracle/curvis_oracle.c).  TEST INFRASTRUCTURE: imported only by tests/,
+bench.py's cpu_baseline / --impl reference legs and __graft_entry__.smoke().  It shares the
+plain-data struct layouts of include/curvis_gpu.h (via curvis_b200._abi) and nothing else with
+the product."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from curvis_b200 import _abi
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_DIR, "libcurvis_oracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_DIR, "curvis_oracle.c")
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _DIR, "-s"] + (["-B"] if force else []))
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB_PATH)
+        dp, vp = C.POINTER(C.c_double), C.c_void_p
+        L.oracle_orientation.argtypes = [dp, dp, dp, dp, dp]
+        L.oracle_camera_init.argtypes = [C.POINTER(_abi.CurvisCamera), dp, dp, dp, C.c_double, C.c_double, C.c_uint32, C.c_uint32]
+        L.oracle_normalize_theta_phi.argtypes = [C.c_double, C.c_double, dp, dp]
+        L.oracle_normalize_theta_phi.restype = None
+        L.oracle_vector3_from_theta_phi.argtypes = [C.c_double, C.c_double, dp]
+        L.oracle_vector3_from_theta_phi.restype = None
+        L.oracle_theta_phi_from_vector3.argtypes = [dp, dp, dp]
+        L.oracle_theta_phi_from_vector3.restype = None
+        L.oracle_outward_vector_on_camera_space.argtypes = [C.POINTER(_abi.CurvisCamera), C.c_uint32, C.c_uint32, dp]
+        L.oracle_outward_vector_on_camera_space.restype = None
+        L.oracle_outward_vector_on_world_space.argtypes = [C.POINTER(_abi.CurvisCamera), C.c_uint32, C.c_uint32, dp]
+        L.oracle_outward_vector_on_world_space.restype = None
+        L.oracle_new_photon.argtypes = [C.POINTER(_abi.CurvisMetric), dp, dp, dp]
+        L.oracle_new_photon.restype = None
+        L.oracle_step.argtypes = [C.POINTER(_abi.CurvisMetric), dp, C.c_double]
+        L.oracle_step.restype = None
+        L.oracle_escape_photon.argtypes = [C.POINTER(_abi.CurvisMetric), dp, C.c_double, C.c_uint32, C.c_double, C.POINTER(C.c_uint32)]
+        L.oracle_relativistic_vector_to_direction.argtypes = [C.POINTER(_abi.CurvisMetric), dp, dp, dp]
+        L.oracle_relativistic_vector_to_direction.restype = None
+        L.oracle_squared_norm_cov.argtypes = [C.POINTER(_abi.CurvisMetric), dp, dp]
+        L.oracle_squared_norm_cov.restype = C.c_double
+        L.oracle_texel_from_vector3.argtypes = [dp, dp, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), dp, dp]
+        L.oracle_texel_from_vector3.restype = None
+        L.oracle_render_rows.argtypes = [
+            C.POINTER(_abi.CurvisMetric), C.POINTER(_abi.CurvisCamera), C.POINTER(_abi.CurvisSim),
+            vp, C.c_uint32, C.c_uint32, dp, vp, C.c_uint32, C.c_uint32, dp,
+            C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, C.POINTER(_abi.CurvisStats), C.c_int]
+        L.oracle_trajectory.argtypes = [C.POINTER(_abi.CurvisMetric), dp, dp, C.c_double, C.c_uint32, dp]
+        L.oracle_trajectory.restype = None
+        L.oracle_metric_validate.argtypes = [C.POINTER(_abi.CurvisMetric)]
+        _lib = L
+    return _lib
+
+
+def _d(values, n):
+    return (C.c_double * n)(*[float(v) for v in values])
+
+
+def metric(kind: str, rho=1.0, m=0.1, a=1e-4) -> _abi.CurvisMetric:
+    k = {"ellis": _abi.METRIC_ELLIS, "interstellar": _abi.METRIC_INTERSTELLAR, "flat": _abi.METRIC_FLAT}[kind.lower()]
+    return _abi.CurvisMetric(kind=k, rho=rho, m=m, a=a)
+
+
+def orientation(forward, up):
+    rot, inv, upo = (C.c_double * 9)(), (C.c_double * 9)(), (C.c_double * 3)()
+    rc = lib().oracle_orientation(_d(forward, 3), _d(up, 3), rot, inv, upo)
+    if rc:
+        raise ValueError("Forward and up vectors must not be parallel")
+    return np.array(rot).reshape(3, 3), np.array(inv).reshape(3, 3), np.array(upo)
+
+
+def camera(position, forward, up, focal_length, diagonal, width, height) -> _abi.CurvisCamera:
+    cam = _abi.CurvisCamera()
+    rc = lib().oracle_camera_init(C.byref(cam), _d(position, 4), _d(forward, 3), _d(up, 3), focal_length, diagonal, width, height)
+    if rc:
+        raise ValueError(f"oracle_camera_init failed ({rc})")
+    return cam
+
+
+def sim(max_iterations, max_radius, delta) -> _abi.CurvisSim:
+    return _abi.CurvisSim(max_iterations=max_iterations, max_radius=max_radius, delta=delta, precision=0, sampling=0)
+
+
+def normalize_theta_phi(theta, phi):
+    t, p = C.c_double(), C.c_double()
+    lib().oracle_normalize_theta_phi(theta, phi, C.byref(t), C.byref(p))
+    return t.value, p.value
+
+
+def vector3_from_theta_phi(theta, phi):
+    o = (C.c_double * 3)()
+    lib().oracle_vector3_from_theta_phi(theta, phi, o)
+    return np.array(o)
+
+
+def theta_phi_from_vector3(v):
+    t, p = C.c_double(), C.c_double()
+    lib().oracle_theta_phi_from_vector3(_d(v, 3), C.byref(t), C.byref(p))
+    return t.value, p.value
+
+
+def outward_vector(cam, px, py, world=True):
+    o = (C.c_double * 3)()
+    fn = lib().oracle_outward_vector_on_world_space if world else lib().oracle_outward_vector_on_camera_space
+    fn(C.byref(cam), px, py, o)
+    return np.array(o)
+
+
+def new_photon(g, position, direction):
+    ph = (C.c_double * 8)()
+    lib().oracle_new_photon(C.byref(g), _d(position, 4), _d(direction, 3), ph)
+    a = np.array(ph)
+    return a[:4].copy(), a[4:].copy()
+
+
+def step(g, x, p, delta):
+    ph = _d(list(x) + list(p), 8)
+    lib().oracle_step(C.byref(g), ph, delta)
+    a = np.array(ph)
+    return a[:4].copy(), a[4:].copy()
+
+
+def escape_photon(g, x, p, delta, max_iterations, max_radius):
+    ph = _d(list(x) + list(p), 8)
+    steps = C.c_uint32()
+    side = lib().oracle_escape_photon(C.byref(g), ph, delta, max_iterations, max_radius, C.byref(steps))
+    a = np.array(ph)
+    return side, steps.value, a[:4].copy(), a[4:].copy()
+
+
+def direction(g, p, x):
+    o = (C.c_double * 3)()
+    lib().oracle_relativistic_vector_to_direction(C.byref(g), _d(p, 4), _d(x, 4), o)
+    return np.array(o)
+
+
+def squared_norm_cov(g, p, x):
+    return lib().oracle_squared_norm_cov(C.byref(g), _d(p, 4), _d(x, 4))
+
+
+def texel_from_vector3(v, bg_w, bg_h, inv_rot=None):
+    x, y, t, p = C.c_uint32(), C.c_uint32(), C.c_double(), C.c_double()
+    inv = _d(np.asarray(inv_rot if inv_rot is not None else np.eye(3)).reshape(-1), 9)
+    lib().oracle_texel_from_vector3(inv, _d(v, 3), bg_w, bg_h, C.byref(x), C.byref(y), C.byref(t), C.byref(p))
+    return x.value, y.value, t.value, p.value
+
+
+def trajectory(g, position, direction_, delta, n):
+    out = np.zeros((n, 8), dtype=np.float64)
+    lib().oracle_trajectory(C.byref(g), _d(position, 4), _d(direction_, 3), delta, n, out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out
+
+
+def render_rows(g, cam, s, bg_pos, bg_neg, row_begin=0, row_end=None, row_stride=1, threads=1,
+                pos_inv_rot=None, neg_inv_rot=None, with_records=True):
+    """Returns (rgb8 (rows, W, 3), records (rows, W) structured, stats dict)."""
+    W, H = cam.resolution_width, cam.resolution_height
+    if row_end is None:
+        row_end = H
+    n_rows = 0 if row_end <= row_begin else (row_end - row_begin + row_stride - 1) // row_stride
+    bg_pos = np.ascontiguousarray(bg_pos, dtype=np.uint8)
+    bg_neg = np.ascontiguousarray(bg_neg, dtype=np.uint8)
+    out = np.zeros((n_rows, W, 3), dtype=np.uint8)
+    rec = np.zeros((n_rows, W), dtype=_abi.RAY_RECORD_DTYPE) if with_records else None
+    st = _abi.CurvisStats()
+    dp = C.POINTER(C.c_double)
+    pi = np.ascontiguousarray(pos_inv_rot, dtype=np.float64).ctypes.data_as(dp) if pos_inv_rot is not None else None
+    ni = np.ascontiguousarray(neg_inv_rot, dtype=np.float64).ctypes.data_as(dp) if neg_inv_rot is not None else None
+    rc = lib().oracle_render_rows(
+        C.byref(g), C.byref(cam), C.byref(s),
+        bg_pos.ctypes.data_as(C.c_void_p), bg_pos.shape[1], bg_pos.shape[0], pi,
+        bg_neg.ctypes.data_as(C.c_void_p), bg_neg.shape[1], bg_neg.shape[0], ni,
+        row_begin, row_end, row_stride, out.ctypes.data_as(C.c_void_p),
+        rec.ctypes.data_as(C.c_void_p) if rec is not None else None, C.byref(st), threads)
+    if rc:
+        raise RuntimeError(f"oracle_render_rows status {rc}")
+    return out, rec, st.as_dict()
