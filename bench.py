@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py — ray-steps/s of the per-pixel null-geodesic renderer (reference
+RelativisticSystem::render_image, src/systems.rs:307-330) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json `metric`: "ray-steps/sec and frames/sec at 3840x2160 Ellis"): the
+Ellis rho=1 wormhole at 3840x2160 with the reference's default camera and simulation settings
+(settings/defaults/*.toml: l=5, forward -x, diag 43, focal 15; escape_radius 100, max
+iterations 40000, step 0.05), two synthetic decodable 8192x4096 RGBA8 backgrounds.
+
+One "step" = one pass of the hot path over one batch: at N GPUs the batch is N frames of that
+4K scene (frame f of a synthetic camera path), EACH frame row-tiled over the N ranks (rank g
+renders rows [g*H/N, (g+1)*H/N)) and its tiles all-gathered over NCCL so every rank holds every
+complete frame.  Per-GPU work is one frame's worth of rays whatever N is -> "scaling": "weak".
+At N=1 there is no collective.
+
+Printed (rank 0, ONE JSON line): see the task contract; `value` = ray-steps/s with the scene
+resident in HBM (CUDA events, max over ranks); `e2e` = the same through the host-buffer C-ABI
+call curvis_render_image / curvis_render_rows (per-frame parameters in, RGB8 frame out to
+host); `roofline` against the live-measured fp64 FMA peak; `cpu_baseline` = the oracle port on
+one host core (the reference is single-threaded, README.md:110) on a bounded row sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W4K, H4K = 3840, 2160
+BG_W, BG_H = 8192, 4096
+FLOP_PER_STEP = {"ellis": 33, "interstellar": 43}   # SURVEY.md 8a canonical count after CSE
+METRIC_NAME = "ray_steps_per_sec"
+UNIT = "ray-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--width", type=int, default=W4K)
+    ap.add_argument("--height", type=int, default=H4K)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, n):
+    return {
+        "workload": f"Ellis rho=1 wormhole, {args.width}x{args.height}, default camera (l=5, fwd -x, diag 43, focal 15), "
+                    f"escape_radius 100 / max_iterations 40000 / step 0.05 (forward Euler, early exit), nearest u8 lookup in "
+                    f"two {BG_W}x{BG_H} RGBA8 backgrounds",
+        "frames_per_step": n,
+        "parallelism": "single GPU" if n == 1 else f"{n} frames/step, each row-tiled over {n} ranks + NCCL all-gather of row tiles",
+        "l2": "256 MiB device buffer rewritten between steps inside the timed region (L2 flush); the kernel is ALU-bound",
+    }
+
+
+# ----------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU with NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.05):
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {}
+        for n in dir(nv):
+            if n.startswith("nvmlClocksThrottleReason") and isinstance(getattr(nv, n), int):
+                names[getattr(nv, n)] = n[len("nvmlClocksThrottleReason"):]
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for bit, name in names.items():
+                    if bit and (mask & bit) and name not in ("None", "All", "GpuIdle", "ApplicationsClocksSetting"):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------------- reference arm
+def oracle_sample(args, rows_per_step: int, threads: int):
+    """Times the oracle port on a bounded sample: `rows_per_step` rows of the frame, spread
+    evenly over its height."""
+    from curvis_b200 import scenes
+    from oracle import oracle as O
+
+    bp = scenes.decodable_background(BG_W, BG_H)
+    bn = scenes.decodable_background(BG_W, BG_H, negative=True)
+    cam = O.camera(scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP,
+                   scenes.DEFAULT_FOCAL_LENGTH, scenes.DEFAULT_DIAGONAL, args.width, args.height)
+    g = O.metric("ellis", rho=1.0)
+    s = O.sim(scenes.DEFAULT_MAX_ITERATIONS, scenes.DEFAULT_ESCAPE_RADIUS, scenes.DEFAULT_STEP)
+    stride = max(1, args.height // rows_per_step)
+    first = stride // 2
+
+    def one():
+        t0 = time.perf_counter()
+        _, _, st = O.render_rows(g, cam, s, bp, bn, row_begin=first, row_end=args.height, row_stride=stride,
+                                 threads=threads, with_records=False)
+        return time.perf_counter() - t0, st
+
+    return one, f"rows {first}::{stride} of the {args.width}x{args.height} frame ({len(range(first, args.height, stride))} rows)"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # The reference (pure Rust, no cargo in the image) cannot be built here: the arm is the
+    # oracle port, on ONE thread because the reference's render_image is single-threaded
+    # (README.md:110, src/systems.rs:316-326 is a plain nested loop).
+    one, sample = oracle_sample(args, rows_per_step=4, threads=1)
+    for _ in range(args.warmup):
+        one()
+    t_total, steps_total = 0.0, 0
+    for _ in range(args.steps):
+        dt, st = one()
+        t_total += dt
+        steps_total += st["total_steps"]
+    value = steps_total / t_total
+    ncpu = os.cpu_count() or 1
+    one_mt, _ = oracle_sample(args, rows_per_step=4 * min(ncpu, 64), threads=ncpu)
+    dt, st = one_mt()
+    line = {
+        "impl": "reference", "metric": METRIC_NAME, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_total / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": dict(workload_config(args, 1), sample_per_step=sample),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores": ncpu,
+                         "note": "reference is single-threaded; all-core figure of the same port in cpu_all_cores"},
+        "cpu_all_cores": {"value": st["total_steps"] / dt, "unit": UNIT, "cores": ncpu},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import curvis_b200 as cv
+    from curvis_b200 import _abi, scenes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: curvis_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n = world
+    Wd, Ht = args.width, args.height
+    if Ht % n:
+        raise SystemExit(f"height {Ht} not divisible by {n} ranks")
+    rows = Ht // n
+    row_begin, row_end = rank * rows, (rank + 1) * rows
+
+    lib = _abi.load_library()
+    ctx = cv.Context([local])
+    bp = scenes.decodable_background(BG_W, BG_H)
+    bn = scenes.decodable_background(BG_W, BG_H, negative=True)
+    t_up0 = time.perf_counter()
+    system = cv.RelativisticSystem(
+        cv.EllisMetric(1.0), cv.SphericalImage(bp), cv.SphericalImage(bn),
+        cv.Camera(scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP,
+                  scenes.DEFAULT_FOCAL_LENGTH, scenes.DEFAULT_DIAGONAL, Wd, Ht), context=ctx)
+    background_upload_ms = (time.perf_counter() - t_up0) * 1e3
+    sim = (scenes.DEFAULT_MAX_ITERATIONS, scenes.DEFAULT_ESCAPE_RADIUS, scenes.DEFAULT_STEP)
+
+    stream = torch.cuda.current_stream()
+    frames = [torch.empty(Ht * Wd * 3, dtype=torch.uint8, device=dev) for _ in range(n)]   # complete frames
+    tile = torch.empty(rows * Wd * 3, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def device_step():
+        """One step of the resident path: n frames, this rank's row tile of each, all-gather."""
+        flush.fill_(1)
+        for f in range(n):
+            if n == 1:
+                system.render_rows_device(*sim, row_begin, row_end, frames[f].data_ptr(), stream.cuda_stream)
+            else:
+                system.render_rows_device(*sim, row_begin, row_end, tile.data_ptr(), stream.cuda_stream)
+                dist.all_gather_into_tensor(frames[f], tile)
+
+    # steps of one tile (deterministic) -> steps per job-step
+    st = system.render_rows_device(*sim, row_begin, row_end, tile.data_ptr() if n > 1 else frames[0].data_ptr(),
+                                   stream.cuda_stream, want_stats=True)
+    tile_steps = torch.tensor([st["total_steps"]], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(tile_steps)
+    frame_steps = int(tile_steps.item())          # Euler steps of one whole frame
+    steps_per_job_step = frame_steps * n
+
+    for _ in range(args.warmup):
+        device_step()
+    torch.cuda.synchronize()
+    barrier()
+    launches0 = lib.curvis_kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            device_step()
+        e1.record()
+        torch.cuda.synchronize()
+    barrier()
+    launches = lib.curvis_kernel_launch_count() - launches0
+    elapsed_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    launches_t = torch.tensor([launches], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(launches_t)
+    elapsed_ms = float(elapsed_ms.item())
+    value = steps_per_job_step * args.steps / (elapsed_ms * 1e-3)
+
+    # kernel-only duration of the dominant kernel (events recorded by the library around it)
+    kernel_ms = []
+    for _ in range(3):
+        s2 = system.render_rows_device(*sim, row_begin, row_end, tile.data_ptr() if n > 1 else frames[0].data_ptr(),
+                                       stream.cuda_stream, want_stats=True)
+        kernel_ms.append(s2["kernel_ms"])
+    kernel_ms = sum(kernel_ms) / len(kernel_ms)
+    tile_steps_local = st["total_steps"]
+
+    # ---- e2e through the host-buffer C-ABI call (per-frame parameters in, RGB8 out to host)
+    host_frames = [torch.empty(Ht * Wd * 3, dtype=torch.uint8).pin_memory() for _ in range(n)] if (n > 1 and rank == 0) else None
+    param_bytes = (C_sizeof(_abi.CurvisMetric) + C_sizeof(_abi.CurvisCamera) + C_sizeof(_abi.CurvisSim))
+
+    def e2e_step():
+        if n == 1:
+            system.render_image(*sim)                      # curvis_render_image: kernel + D2H + copy to caller buffer
+        else:
+            for f in range(n):
+                system.render_rows_device(*sim, row_begin, row_end, tile.data_ptr(), stream.cuda_stream)
+                dist.all_gather_into_tensor(frames[f], tile)
+                if rank == 0:
+                    host_frames[f].copy_(frames[f], non_blocking=True)
+            torch.cuda.synchronize()
+
+    e2e_step()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = steps_per_job_step * args.steps / float(e2e_s.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- cold e2e at N=1: re-upload both backgrounds every frame as well
+    e2e_cold = None
+    if n == 1:
+        t0 = time.perf_counter()
+        reps = max(2, min(args.steps, 3))
+        for _ in range(reps):
+            system._upload(+1, system.background_positive)
+            system._upload(-1, system.background_negative)
+            system.render_image(*sim)
+        dt = time.perf_counter() - t0
+        e2e_cold = {"value": frame_steps * reps / dt, "unit": UNIT,
+                    "h2d_bytes_per_step": 2 * BG_W * BG_H * 4 + param_bytes, "d2h_bytes_per_step": Wd * Ht * 3,
+                    "note": "both backgrounds re-uploaded from pageable host memory every frame"}
+
+    fp64_peak, fp32_peak = ctx.measure_fma_peak()
+    flop = FLOP_PER_STEP["ellis"]
+    kernel_rate = tile_steps_local / (kernel_ms * 1e-3)       # this rank's kernel, steps/s
+    achieved_tf = kernel_rate * flop / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    alg_bytes_per_ray = 4 + 3                                  # one RGBA8 texel read + 3 B written
+    tile_rays = rows * Wd
+    hbm_achieved = tile_rays * alg_bytes_per_ray / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "latest_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {
+        "bound": "fp64_alu (no dense contraction and ~1e3 flop/B: neither hbm nor tensor; DESIGN.md section 5)",
+        "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
+        "traffic": traffic,
+        "peak_source": "live DFMA micro-kernel on this GPU (curvis_measure_fma_peak); MEASURED_PEAKS.json has no fp64 entry",
+        "flop_per_ray_step": flop, "kernel": "render_rows_f64<ShapeEllis>", "kernel_ms": kernel_ms,
+        "kernel_ray_steps_per_s": kernel_rate,
+        "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
+                "algorithmic_bytes_per_ray": alg_bytes_per_ray},
+        "fp32_fma_peak_tflops": fp32_peak,
+    }
+
+    cpu_baseline = None
+    if n == 1 and not args.no_cpu_baseline:
+        one, sample = oracle_sample(args, rows_per_step=24, threads=1)
+        dt, cst = one()
+        cpu_baseline = {"value": cst["total_steps"] / dt, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                        "seconds": dt, "host_cores": os.cpu_count()}
+
+    line = {
+        "metric": METRIC_NAME, "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args, n),
+        "frames_per_sec": n * args.steps / (elapsed_ms * 1e-3), "rays_per_sec": n * Wd * Ht * args.steps / (elapsed_ms * 1e-3),
+        "ray_steps_per_frame": frame_steps,
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": param_bytes * n,
+                "d2h_bytes_per_step": Wd * Ht * 3 * n,
+                "note": "backgrounds are part of the scene (`&self`, uploaded once: %.1f ms); per-frame input = metric+camera+sim structs" % background_upload_ms},
+        "e2e_cold": e2e_cold,
+        "gpu_launches": int(launches_t.item()),
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def C_sizeof(t):
+    import ctypes
+    return ctypes.sizeof(t)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -92,7 +92,7 @@ EXPORTED_SYMBOLS = (
     "curvis_ctx_create", "curvis_ctx_destroy", "curvis_last_error", "curvis_abi_version",
     "curvis_ctx_device_count", "curvis_orientation", "curvis_camera_init", "curvis_metric_validate",
     "curvis_set_background", "curvis_render_image", "curvis_render_rows", "curvis_render_rows_device",
-    "curvis_measure_fma_peak",
+    "curvis_measure_fma_peak", "curvis_kernel_launch_count",
 )
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcurvis_b200.so")
@@ -138,8 +138,10 @@ def load_library() -> C.CDLL:
     lib.curvis_measure_fma_peak.argtypes = [vp, dp, dp]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
-        if name not in ("curvis_ctx_destroy", "curvis_last_error"):
+        if name not in ("curvis_ctx_destroy", "curvis_last_error", "curvis_kernel_launch_count"):
             fn.restype = C.c_int
+    lib.curvis_kernel_launch_count.argtypes = []
+    lib.curvis_kernel_launch_count.restype = C.c_uint64
     if lib.curvis_abi_version() != ABI_VERSION:
         raise ImportError(f"libcurvis_b200.so ABI {lib.curvis_abi_version()} != expected {ABI_VERSION}")
     _lib = lib

@@ -3,6 +3,7 @@
 // context's devices).  The boundary replaces RelativisticSystem::render_image
 // (reference src/systems.rs:307-330); there is no CPU compute path in this library.
 #include <cuda_runtime.h>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -18,6 +19,7 @@
 namespace curvis {
 
 static thread_local std::string g_thread_error;
+static std::atomic<uint64_t> g_kernel_launches{0};
 int set_thread_error(int code, const char* msg) { g_thread_error = msg ? msg : ""; return code; }
 const char* thread_error() { return g_thread_error.c_str(); }
 
@@ -118,7 +120,10 @@ static int enqueue_tile(curvis_ctx* ctx, DeviceState& d, const curvis_metric* me
     fill_params(ctx, d, metric, cam, sim, row_begin, row_end, d_out, d_records, p);
     CURVIS_CUDA(ctx, cudaMemsetAsync(d.d_counters, 0, sizeof(DeviceCounters), stream));
     CURVIS_CUDA(ctx, cudaEventRecord(d.ev_begin, stream));
-    if (row_end > row_begin) CURVIS_CUDA(ctx, launch_render_f64(p, metric->kind, d.sm_count, stream));
+    if (row_end > row_begin) {
+        CURVIS_CUDA(ctx, launch_render_f64(p, metric->kind, d.sm_count, stream));
+        g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+    }
     CURVIS_CUDA(ctx, cudaEventRecord(d.ev_end, stream));
     return CURVIS_OK;
 }
@@ -171,6 +176,8 @@ static void release_device(DeviceState& d) {
 using namespace curvis;
 
 extern "C" int curvis_abi_version(void) { return CURVIS_ABI_VERSION; }
+
+extern "C" uint64_t curvis_kernel_launch_count(void) { return g_kernel_launches.load(std::memory_order_relaxed); }
 
 extern "C" const char* curvis_last_error(const curvis_ctx* ctx) { return ctx ? ctx->err.c_str() : thread_error(); }
 

@@ -202,7 +202,11 @@ int curvis_render_rows_device(curvis_ctx* ctx, const curvis_metric* metric,
                               void* d_out_rgb8_rows, void* d_records,
                               void* stream, curvis_stats* stats);
 
-/* ---- measurement helper -------------------------------------------------------------- */
+/* ---- measurement helpers ------------------------------------------------------------- */
+
+/* Number of render-kernel launches this process has issued so far (all contexts).  bench.py
+ * reads it on both sides of the timed region to report `gpu_launches`. */
+uint64_t curvis_kernel_launch_count(void);
 
 /* Runs an FMA-only micro-kernel on the context's first device and returns the achieved
  * fp64 and fp32 FMA rates in TFLOP/s (2 flop per FMA).  bench.py uses it as the measured

@@ -1,0 +1,147 @@
+"""CPU-only checks of the C-ABI library: it loads, exports every symbol include/curvis_gpu.h
+declares, its host-side setup helpers equal the oracle bit for bit, its error behaviour mirrors
+the reference's panics, and it refuses to run without a GPU (no CPU fallback)."""
+import ctypes as C
+import math
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "curvis_gpu.h")
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(curvis_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from curvis_b200 import _abi
+    names = declared_functions()
+    assert len(names) >= 13
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _abi.LIB_PATH], text=True)
+    exported = set(re.findall(r"\bT (curvis_[a-z0-9_]+)", out))
+    assert set(names) <= exported, f"missing: {set(names) - exported}"
+    assert set(names) == set(_abi.EXPORTED_SYMBOLS)
+    for n in names:
+        getattr(lib, n)
+    assert lib.curvis_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    from curvis_b200 import _abi
+    assert C.sizeof(_abi.CurvisMetric) == 32
+    assert C.sizeof(_abi.CurvisCamera) == 4 * 8 + 9 * 8 + 3 * 8 + 8
+    assert C.sizeof(_abi.CurvisSim) == 32
+    assert C.sizeof(_abi.CurvisStats) == 9 * 8
+    assert C.sizeof(_abi.CurvisRayRecord) == 64 == np.dtype(_abi.RAY_RECORD_DTYPE).itemsize
+
+
+def test_library_embeds_sm100a_kernels(lib):
+    from curvis_b200 import _abi
+    out = subprocess.check_output(["cuobjdump", "-lelf", _abi.LIB_PATH], text=True)
+    assert "sm_100a" in out
+
+
+def test_orientation_and_camera_equal_oracle_bitwise(lib, oracle):
+    import curvis_b200 as cv
+    rng = np.random.default_rng(7)
+    cases = [((1, 0, 0), (0, 0, 1)), ((-1, 0, 0), (0, 0, 1)), ((1, 1, 0), (-1, -1, 1)), ((1, 0, 1), (1, 1, 1))]
+    cases += [(tuple(rng.uniform(-1, 1, 3)), tuple(rng.uniform(-1, 1, 3))) for _ in range(50)]
+    for f, u in cases:
+        o = cv.Orientation(f, u)
+        rot, inv, up = oracle.orientation(f, u)
+        assert o.rotation_matrix().tobytes() == rot.tobytes()
+        assert o.inverse_rotation_matrix().tobytes() == inv.tobytes()
+        assert o.up().tobytes() == up.tobytes()
+        cam = cv.Camera((0, 5, 1.0, 0.5), f, u, 15.0, 43.0, 1920, 1080).as_c()
+        ocam = oracle.camera((0, 5, 1.0, 0.5), f, u, 15.0, 43.0, 1920, 1080)
+        assert bytes(cam) == bytes(ocam)
+
+
+def test_reference_orientation_kats_through_the_abi(lib):     # algebra.rs:143-209 via the product
+    import curvis_b200 as cv
+    assert (cv.Orientation((1, 0, 0), (0, 0, 1)).rotation_matrix() == np.eye(3)).all()
+    assert cv.Orientation((1, 0, 0), (1, 0, 1)).up().tolist() == [0, 0, 1]
+    assert cv.Orientation((1, 1, 0), (-1, -1, 1)).up().tolist() == [0, 0, 1]
+    assert cv.Orientation((1, 0, 1), (1, 1, 1)).up().tolist() == [0, 1, 0]
+    assert cv.Orientation((1, 1, 0), (-1, -1, 1)).forward().tolist() == [1, 1, 0]   # forward kept as given
+
+
+def test_error_behaviour_mirrors_reference_panics(lib):
+    import curvis_b200 as cv
+    from curvis_b200 import _abi
+    with pytest.raises(cv.CurvisError) as e:                   # algebra.rs:19-21
+        cv.Orientation((1, 0, 0), (-2, 0, 0))
+    assert e.value.code == _abi.ERR_PARALLEL_VECTORS and "parallel" in e.value.message
+    for bad in (dict(focal_length=0.0), dict(sensor_diagonal=-1.0), dict(resolution_width=0)):   # cameras.rs:94-102
+        kw = dict(focal_length=15.0, sensor_diagonal=43.0, resolution_width=16, resolution_height=9)
+        kw.update(bad)
+        with pytest.raises(cv.CurvisError) as e:
+            cv.Camera((0, 5, 1, 0), (-1, 0, 0), (0, 0, 1), **kw)
+        assert e.value.code == _abi.ERR_INVALID_ARGUMENT
+    with pytest.raises(cv.CurvisError) as e:                   # metrics.rs:407-409
+        cv.EllisMetric(0.0)
+    assert e.value.code == _abi.ERR_INVALID_METRIC and "rho" in e.value.message
+    for m, a, rho in ((0, 1, 1), (1, -1, 1), (1, 1, 0)):        # metrics.rs:443-456
+        with pytest.raises(cv.CurvisError):
+            cv.InterstellarMetric(m, a, rho)
+    cv.InterstellarMetric(0.1, 1e-4, 1.0)
+    cv.FlatSphericalMetric()
+
+
+def test_null_arguments_do_not_crash(lib):
+    from curvis_b200 import _abi
+    assert lib.curvis_orientation(None, None, None, None, None) == _abi.ERR_INVALID_ARGUMENT
+    assert lib.curvis_camera_init(None, None, None, None, 1.0, 1.0, 1, 1) == _abi.ERR_INVALID_ARGUMENT
+    assert lib.curvis_metric_validate(None) == _abi.ERR_INVALID_ARGUMENT
+    assert lib.curvis_ctx_create(None, 0, None) == _abi.ERR_INVALID_ARGUMENT
+    assert lib.curvis_set_background(None, 1, None, 1, 1, None) == _abi.ERR_INVALID_ARGUMENT
+    assert lib.curvis_render_image(None, None, None, None, None, None) == _abi.ERR_INVALID_ARGUMENT
+    assert lib.curvis_ctx_device_count(None) == 0
+    lib.curvis_ctx_destroy(None)
+    assert isinstance(lib.curvis_last_error(None), bytes)
+
+
+def test_no_cpu_fallback_without_a_gpu(lib):
+    """Without a CUDA device the product refuses to run: no CPU path exists behind the ABI."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    import curvis_b200 as cv
+    from curvis_b200 import _abi
+    with pytest.raises(cv.CurvisError) as e:
+        cv.Context()
+    assert e.value.code == _abi.ERR_NO_DEVICE
+    assert "no CPU fallback" in e.value.message
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under curvis_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "curvis_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "build" in dirpath.split(os.sep):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "curvis_oracle" not in text and "liboracle" not in text, f
+
+
+def test_spherical_image_conversions(lib):
+    import curvis_b200 as cv
+    rgb = np.arange(2 * 3 * 3, dtype=np.uint8).reshape(2, 3, 3)
+    img = cv.SphericalImage(rgb)
+    assert img.rgba8.shape == (2, 3, 4) and (img.rgba8[..., 3] == 255).all() and (img.rgba8[..., :3] == rgb).all()
+    assert img.dimensions() == (3, 2)
+    assert (img.orientation().inverse_rotation_matrix() == np.eye(3)).all()
+    luma = cv.SphericalImage(np.full((2, 2), 9, np.uint8))
+    assert (luma.rgba8[..., :3] == 9).all()
+    with pytest.raises(TypeError):
+        cv.SphericalImage(np.zeros((2, 2, 3), np.float32))

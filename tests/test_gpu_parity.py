@@ -1,0 +1,221 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the golden fixtures.
+Run on the GPU box:  python -m pytest tests -m gpu
+
+Bar (fp64 parity mode): RGB8, escape side, step count and texel index are integer/byte results
+and must be IDENTICAL to the oracle for every pixel.  The final photon state is floating point:
+CUDA's sin/cos (<= 2 ulp) are not bit-identical to glibc's, so it is compared with a tolerance
+stated in each test; the end DIRECTION must agree within 1e-5 rad (BASELINE.json north_star).
+"""
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+END_DIRECTION_TOL_RAD = 1e-5      # BASELINE.json north_star
+STATE_RTOL = 1e-9                 # final (l, theta, phi, p_l, p_theta): Euler amplifies 1-ulp trig differences
+
+
+def _system(cv, metric, cam_args, bp, bn, ctx, bg_orient=(None, None)):
+    cam = cv.Camera(*cam_args)
+    return cv.RelativisticSystem(metric, cv.SphericalImage(bp, *bg_orient), cv.SphericalImage(bn), cam, context=ctx)
+
+
+def _direction(rec):
+    """Local tangent-frame direction of the escaped photon (metrics.rs:339-349) from a record,
+    for Ellis-like use only as an ANGLE between two nearly equal states."""
+    return np.stack([rec["p_l"], rec["p_theta"], rec["p_phi"]], axis=-1)
+
+
+def _assert_parity(frame, rec, ref_frame, ref_rec, name):
+    assert frame.shape == ref_frame.shape
+    diff_px = int((frame != ref_frame).any(axis=2).sum())
+    assert diff_px == 0, f"{name}: {diff_px} pixels differ in RGB"
+    for f in ("side", "steps", "texel_x", "texel_y"):
+        bad = int((rec[f] != ref_rec[f]).sum())
+        assert bad == 0, f"{name}: {bad} rays differ in {f}"
+    assert rec["p_phi"].tobytes() == ref_rec["p_phi"].tobytes(), f"{name}: p_phi (conserved, no trig in it) must be bit-exact"
+    esc = ref_rec["side"] != 0
+    finite = esc & np.isfinite(ref_rec["l"]) & np.isfinite(ref_rec["theta"])
+    for f in ("l", "p_l"):
+        np.testing.assert_allclose(rec[f][finite], ref_rec[f][finite], rtol=STATE_RTOL, atol=1e-9, err_msg=f"{name}: {f}")
+    # end direction (momentum) within 1e-5 rad
+    a, b = _direction(rec)[finite], _direction(ref_rec)[finite]
+    if a.size:
+        cosang = (a * b).sum(-1) / (np.linalg.norm(a, axis=-1) * np.linalg.norm(b, axis=-1))
+        ang = np.arccos(np.clip(cosang, -1.0, 1.0))
+        # arccos of 1-eps is ~1e-8 noise; compare through the cross-product-free bound
+        assert float(np.nanmax(ang)) <= END_DIRECTION_TOL_RAD, f"{name}: end direction differs by {np.nanmax(ang)} rad"
+
+
+@pytest.mark.parametrize("name", ["ellis_c1a_64x36", "ellis_defaults_48x27", "interstellar_defaults_48x27",
+                                  "flat_40x30", "ellis_tilted_33x17"])
+def test_golden_and_oracle_parity(gpu_ctx, oracle, name):
+    import curvis_b200 as cv
+    import make_golden
+    from curvis_b200 import scenes
+    kind, mk, W, H, sim, pos, fwd, up, _ = make_golden.CASES[name]
+    g, ocam, s, bp, bn = make_golden.scene(name)
+    metric = {"ellis": lambda: cv.EllisMetric(mk.get("rho", 1.0)), "interstellar": lambda: cv.InterstellarMetric(0.1, 1e-4, 1.0),
+              "flat": cv.FlatSphericalMetric}[kind]()
+    sysm = _system(cv, metric, (pos, fwd, up, scenes.DEFAULT_FOCAL_LENGTH, scenes.DEFAULT_DIAGONAL, W, H), bp, bn, gpu_ctx)
+    frame, rec = sysm.render_rows(*sim, 0, H, with_records=True)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    _assert_parity(frame, rec, gold["rgb"], gold["rec"], name + " vs golden")
+    st = sysm.last_stats
+    assert st["total_steps"] == int(gold["total_steps"])
+    assert [st["n_positive"], st["n_negative"], st["n_not_escaped"], st["n_clamped"]] == gold["counts"].tolist()
+    ref_frame, ref_rec, ref_st = oracle.render_rows(g, ocam, s, bp, bn, threads=os.cpu_count() or 1)
+    _assert_parity(frame, rec, ref_frame, ref_rec, name + " vs live oracle")
+    full = sysm.render_image(*sim)                       # whole-frame entry point = tile entry point
+    assert (full == frame).all()
+
+
+@pytest.mark.parametrize("kind,sim", [("ellis", (200, 10.0, 0.1)), ("ellis", (40000, 100.0, 0.05)),
+                                      ("interstellar", (40000, 100.0, 0.05))])
+def test_baseline_config_256x144(gpu_ctx, oracle, kind, sim):
+    """BASELINE.json configs[0] (C1a/C1b) and the Interstellar default frame: every pixel."""
+    import curvis_b200 as cv
+    from curvis_b200 import scenes
+    W, H = 256, 144
+    bp, bn = scenes.decodable_background(4096, 2048), scenes.decodable_background(4096, 2048, True)
+    metric = cv.EllisMetric(1.0) if kind == "ellis" else cv.InterstellarMetric(0.1, 1e-4, 1.0)
+    cam_args = (scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP, 15.0, 43.0, W, H)
+    sysm = _system(cv, metric, cam_args, bp, bn, gpu_ctx)
+    frame, rec = sysm.render_rows(*sim, 0, H, with_records=True)
+    ocam = oracle.camera(*cam_args)
+    ref_frame, ref_rec, ref_st = oracle.render_rows(oracle.metric(kind), ocam, oracle.sim(*sim), bp, bn, threads=os.cpu_count() or 1)
+    _assert_parity(frame, rec, ref_frame, ref_rec, f"{kind} {sim}")
+    assert sysm.last_stats["total_steps"] == ref_st["total_steps"]
+    if kind == "ellis" and sim[0] == 40000:
+        assert ref_st["total_steps"] == 72225185
+
+
+def test_oriented_background_and_ragged_sizes(gpu_ctx, oracle):
+    """Non-identity image orientation (images.rs:132-142), widths that are not a multiple of the
+    warp size, a 1x1 frame, and an empty tile."""
+    import curvis_b200 as cv
+    bp, bn = __import__("curvis_b200").scenes.noise_background(301, 157, 5), __import__("curvis_b200").scenes.noise_background(64, 32, 6)
+    fwd_img, up_img = (0.2, 1.0, 0.1), (0.0, 0.3, 1.0)
+    _, inv, _ = oracle.orientation(fwd_img, up_img)
+    for (W, H) in [(37, 5), (1, 1), (3, 64), (130, 3)]:
+        cam_args = ((0.0, 4.0, 1.3, -0.7), (-1.0, 0.1, 0.05), (0.0, 0.0, 1.0), 12.0, 40.0, W, H)
+        sysm = _system(cv, cv.EllisMetric(1.5), cam_args, bp, bn, gpu_ctx, bg_orient=(fwd_img, up_img))
+        frame, rec = sysm.render_rows(3000, 50.0, 0.05, 0, H, with_records=True)
+        ocam = oracle.camera(*cam_args)
+        ref_frame, ref_rec, _ = oracle.render_rows(oracle.metric("ellis", rho=1.5), ocam, oracle.sim(3000, 50.0, 0.05), bp, bn,
+                                                   pos_inv_rot=inv)
+        _assert_parity(frame, rec, ref_frame, ref_rec, f"oriented {W}x{H}")
+        empty = sysm.render_rows(3000, 50.0, 0.05, H, H)
+        assert empty.shape == (0, W, 3) and sysm.last_stats["n_rays"] == 0 and sysm.last_stats["total_steps"] == 0
+
+
+def test_not_escaped_and_zero_iterations(gpu_ctx, oracle):
+    """NotEscaped rays are black (systems.rs:556-558) and count max_iterations steps;
+    max_iterations = 0 renders an all-black frame with zero steps."""
+    import curvis_b200 as cv
+    from curvis_b200 import scenes
+    bp, bn = scenes.noise_background(128, 64, 1), scenes.noise_background(128, 64, 2)
+    cam_args = (scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP, 15.0, 43.0, 40, 24)
+    sysm = _system(cv, cv.EllisMetric(1.0), cam_args, bp, bn, gpu_ctx)
+    frame = sysm.render_image(100, 100.0, 0.05)          # 100 steps of 0.05 cannot reach |l| > 100
+    assert (frame == 0).all()
+    st = sysm.last_stats
+    assert st["n_not_escaped"] == 40 * 24 and st["total_steps"] == 100 * 40 * 24
+    frame = sysm.render_image(0, 100.0, 0.05)
+    assert (frame == 0).all() and sysm.last_stats["total_steps"] == 0 and sysm.last_stats["n_not_escaped"] == 40 * 24
+    # mixed: some rays escape, some do not (C1a has 12 NotEscaped rays at 256x144)
+    ocam = oracle.camera(*cam_args)
+    frame, rec = sysm.render_rows(140, 10.0, 0.1, 0, 24, with_records=True)
+    ref_frame, ref_rec, ref_st = oracle.render_rows(oracle.metric("ellis"), ocam, oracle.sim(140, 10.0, 0.1), bp, bn)
+    assert ref_st["n_not_escaped"] > 0 and ref_st["n_positive"] > 0
+    _assert_parity(frame, rec, ref_frame, ref_rec, "mixed escape")
+
+
+def test_error_codes_on_device(gpu_ctx):
+    import curvis_b200 as cv
+    from curvis_b200 import _abi, scenes
+    bp = scenes.noise_background(64, 32, 1)
+    cam = cv.Camera((0.0, 150.0, 1.0, 0.0), (-1, 0, 0), (0, 0, 1), 15.0, 43.0, 16, 9)
+    sysm = cv.RelativisticSystem(cv.EllisMetric(1.0), cv.SphericalImage(bp), cv.SphericalImage(bp), cam, context=gpu_ctx)
+    with pytest.raises(cv.CurvisError) as e:             # systems.rs:122-124
+        sysm.render_image(10, 100.0, 0.05)
+    assert e.value.code == _abi.ERR_CAMERA_OUTSIDE_RADIUS and "beyond the maximum radius" in e.value.message
+    with pytest.raises(cv.CurvisError) as e:
+        sysm.render_rows(10, 200.0, 0.05, 5, 20)
+    assert e.value.code == _abi.ERR_INVALID_ARGUMENT
+    fresh = cv.Context([0])
+    import ctypes as C
+    lib = _abi.load_library()
+    m, c, s = cv.EllisMetric(1.0).as_c(), cam.as_c(), _abi.CurvisSim(max_iterations=1, max_radius=200.0, delta=0.1)
+    out = np.zeros(16 * 9 * 3, np.uint8)
+    rc = lib.curvis_render_image(fresh.ptr, C.byref(m), C.byref(c), C.byref(s), out.ctypes.data_as(C.c_void_p), None)
+    assert rc == _abi.ERR_NO_BACKGROUND
+
+
+def test_full_size_properties_4k(gpu_ctx, oracle):
+    """BASELINE metric config (Ellis 3840x2160, defaults) through size-independent properties:
+    row tiles == whole frame, run-to-run determinism, counters consistent with per-ray records,
+    every pixel's colour decodes to the texel its record names, escape invariants — plus a
+    strided sample of rows compared with the oracle pixel for pixel."""
+    import curvis_b200 as cv
+    from curvis_b200 import scenes
+    from curvis_b200.distributed import row_tile
+    W, H = 3840, 2160
+    sim = (40000, 100.0, 0.05)
+    bp, bn = scenes.decodable_background(4096, 2048), scenes.decodable_background(4096, 2048, True)
+    cam_args = (scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP, 15.0, 43.0, W, H)
+    sysm = _system(cv, cv.EllisMetric(1.0), cam_args, bp, bn, gpu_ctx)
+    full = sysm.render_image(*sim)
+    st_full = dict(sysm.last_stats)
+    assert (sysm.render_image(*sim) == full).all()                      # deterministic
+    tiles, steps = [], 0
+    for r in range(8):                                                 # the 8-rank partition
+        b, e = row_tile(H, r, 8)
+        tiles.append(sysm.render_rows(*sim, b, e))
+        steps += sysm.last_stats["total_steps"]
+    assert (np.concatenate(tiles, axis=0) == full).all() and steps == st_full["total_steps"]
+    assert st_full["n_positive"] + st_full["n_negative"] + st_full["n_not_escaped"] == W * H
+    # records of a band + decode the colours back to texel indices
+    b, e = 1000, 1100
+    band, rec = sysm.render_rows(*sim, b, e, with_records=True)
+    assert (band == full[b:e]).all()
+    assert int(rec["steps"].sum()) == sysm.last_stats["total_steps"]
+    pos, neg = rec["side"] > 0, rec["side"] < 0
+    assert (rec["l"][pos] > 100.0).all() and (rec["l"][neg] < -100.0).all() and (rec["steps"] <= 40000).all()
+    for mask, inv in ((pos, 0), (neg, 255)):
+        r8, g8, b8 = (band[..., 0][mask] ^ inv), (band[..., 1][mask] ^ inv), band[..., 2][mask]
+        assert ((rec["texel_x"][mask] & 255) == r8).all() and ((rec["texel_y"][mask] & 255) == g8).all()
+        assert ((((rec["texel_x"][mask] >> 8) & 15) << 4 | ((rec["texel_y"][mask] >> 8) & 15)) == b8).all()
+    # strided oracle rows
+    ocam = oracle.camera(*cam_args)
+    ref, _, _ = oracle.render_rows(oracle.metric("ellis"), ocam, oracle.sim(*sim), bp, bn, row_begin=7, row_end=H, row_stride=269,
+                                   threads=os.cpu_count() or 1, with_records=False)
+    assert (ref == full[7:H:269]).all()
+
+
+def test_device_resident_tile_on_a_torch_stream(gpu_ctx, oracle):
+    """curvis_render_rows_device: output stays in HBM (a torch tensor), launched on torch's stream."""
+    import torch
+    import curvis_b200 as cv
+    from curvis_b200 import scenes
+    W, H = 96, 54
+    bp, bn = scenes.noise_background(256, 128, 3), scenes.noise_background(256, 128, 4)
+    cam_args = (scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP, 15.0, 43.0, W, H)
+    sysm = _system(cv, cv.EllisMetric(1.0), cam_args, bp, bn, gpu_ctx)
+    out = torch.zeros(20 * W * 3, dtype=torch.uint8, device="cuda:0")
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        st = sysm.render_rows_device(200, 10.0, 0.1, 10, 30, out.data_ptr(), side.cuda_stream, want_stats=True)
+    side.synchronize()
+    ocam = oracle.camera(*cam_args)
+    ref, _, ref_st = oracle.render_rows(oracle.metric("ellis"), ocam, oracle.sim(200, 10.0, 0.1), bp, bn, row_begin=10, row_end=30,
+                                        with_records=False)
+    assert (out.cpu().numpy().reshape(20, W, 3) == ref).all() and st["total_steps"] == ref_st["total_steps"]
+    assert st["kernel_ms"] > 0

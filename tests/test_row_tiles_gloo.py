@@ -1,0 +1,65 @@
+"""world_size-2 (and 3, ragged) gloo test of the multi-rank host logic on CPU: every rank
+renders its row tile, the tiles are all-gathered, and every rank ends with the frame a single
+process renders.  The tile renderer here is the oracle (there is no GPU in this container);
+the -m gpu suite repeats the equality with the CUDA kernel (test_gpu_parity.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, W, H, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from curvis_b200 import scenes
+        from curvis_b200.distributed import all_gather_frame, row_tile
+        from oracle import oracle as O
+        cam = O.camera(scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP, 15.0, 43.0, W, H)
+        bp, bn = scenes.noise_background(256, 128, 1), scenes.noise_background(256, 128, 2)
+        g, s = O.metric("ellis"), O.sim(200, 10.0, 0.1)
+        b, e = row_tile(H, rank, world)
+        tile, _, st = O.render_rows(g, cam, s, bp, bn, row_begin=b, row_end=e, with_records=False)
+        frame = torch.empty(H * W * 3, dtype=torch.uint8)
+        all_gather_frame(torch.from_numpy(tile.reshape(-1)), frame, H, W)
+        steps = torch.tensor([st["total_steps"]], dtype=torch.int64)
+        dist.all_reduce(steps)
+        full, _, fst = O.render_rows(g, cam, s, bp, bn, with_records=False)
+        ok = bool((frame.numpy().reshape(H, W, 3) == full).all()) and int(steps.item()) == fst["total_steps"]
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,W,H", [(2, 32, 18), (3, 16, 10)])
+def test_row_tiles_all_gather_equals_single_process(built, world, W, H):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 500) + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, W, H, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(results) == [(r, True) for r in range(world)]
+
+
+def test_row_tile_partition():
+    from curvis_b200.distributed import row_tile
+    for H in (1, 7, 144, 2160, 4320):
+        for world in (1, 2, 3, 4, 8):
+            tiles = [row_tile(H, r, world) for r in range(world)]
+            assert tiles[0][0] == 0 and tiles[-1][1] == H
+            assert all(tiles[i][1] == tiles[i + 1][0] for i in range(world - 1))
+    with pytest.raises(ValueError):
+        row_tile(10, 2, 2)
