@@ -348,7 +348,7 @@ def run_b200(args):
         "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
         "traffic": traffic,
         "peak_source": "live DFMA micro-kernel on this GPU (curvis_measure_fma_peak); MEASURED_PEAKS.json has no fp64 entry",
-        "flop_per_ray_step": flop, "kernel": "render_rows_f64<ShapeEllis>", "kernel_ms": kernel_ms,
+        "flop_per_ray_step": flop, "kernel": "render_rows_f64_lean<ShapeEllis>", "kernel_ms": kernel_ms,
         "kernel_ray_steps_per_s": kernel_rate,
         "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",

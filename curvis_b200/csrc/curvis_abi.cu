@@ -47,6 +47,7 @@ struct curvis_ctx {
     std::vector<curvis::DeviceState> devs;
     double bg_inv_rot[2][9];
     bool bg_set[2] = {false, false};
+    curvis::LaunchTuning tuning;
     std::string err;
 };
 
@@ -99,6 +100,9 @@ static void fill_params(const curvis_ctx* ctx, const DeviceState& d, const curvi
     p.rho = metric->rho; p.m = metric->m; p.a = metric->a;
     std::memcpy(p.cam_pos, cam->position, sizeof p.cam_pos);
     std::memcpy(p.cam_to_world, cam->cam_to_world, sizeof p.cam_to_world);
+    p.cam_r = host_shape_r(*metric, cam->position[1]);
+    p.cam_sin_theta = host_sin(cam->position[2]);
+    p.window = (uint32_t)(ctx->tuning.window > 0 ? ctx->tuning.window : 32);
     p.focal_length = cam->focal_length; p.sensor_width = cam->sensor_width; p.sensor_height = cam->sensor_height;
     p.width = cam->resolution_width; p.height = cam->resolution_height;
     p.max_iterations = sim->max_iterations; p.sampling = (uint32_t)sim->sampling;
@@ -121,7 +125,7 @@ static int enqueue_tile(curvis_ctx* ctx, DeviceState& d, const curvis_metric* me
     CURVIS_CUDA(ctx, cudaMemsetAsync(d.d_counters, 0, sizeof(DeviceCounters), stream));
     CURVIS_CUDA(ctx, cudaEventRecord(d.ev_begin, stream));
     if (row_end > row_begin) {
-        CURVIS_CUDA(ctx, launch_render_f64(p, metric->kind, d.sm_count, stream));
+        CURVIS_CUDA(ctx, launch_render_f64(p, metric->kind, ctx->tuning, d.sm_count, stream));
         g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
     }
     CURVIS_CUDA(ctx, cudaEventRecord(d.ev_end, stream));
@@ -370,4 +374,34 @@ extern "C" int curvis_measure_fma_peak(curvis_ctx* ctx, double* fp64_tflops, dou
     CURVIS_CUDA(ctx, cudaSetDevice(d.ordinal));
     CURVIS_CUDA(ctx, measure_fma_peak(d.sm_count, d.stream, fp64_tflops, fp32_tflops));
     return CURVIS_OK;
+}
+
+extern "C" int curvis_ctx_set_option(curvis_ctx* ctx, const char* key, int64_t value) {
+    if (!ctx || !key) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "null argument");
+    const std::string k(key);
+    if (k == "kernel_variant" && value >= 0 && value <= 3) ctx->tuning.kernel_variant = (int)value;
+    else if (k == "blocks_per_sm" && value >= 0 && value <= 32) ctx->tuning.blocks_per_sm = (int)value;
+    else if (k == "window" && value >= 1 && value <= 4096) ctx->tuning.window = (int)value;
+    else return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "unknown option or value out of range: " + k);
+    return CURVIS_OK;
+}
+
+extern "C" int curvis_debug_eval(curvis_ctx* ctx, int op, const double* a, const double* b, double* out, size_t n) {
+    if (!ctx || !a || !out) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "null argument");
+    DeviceState& d = ctx->devs[0];
+    CURVIS_CUDA(ctx, cudaSetDevice(d.ordinal));
+    double *da = nullptr, *db = nullptr, *dout = nullptr;
+    const size_t bytes = n * sizeof(double);
+    int rc = CURVIS_OK;
+    cudaError_t e = cudaSuccess;
+    if ((e = cudaMalloc(&da, bytes ? bytes : 8)) == cudaSuccess && (e = cudaMalloc(&dout, bytes ? bytes : 8)) == cudaSuccess &&
+        (!b || (e = cudaMalloc(&db, bytes ? bytes : 8)) == cudaSuccess) &&
+        (e = cudaMemcpyAsync(da, a, bytes, cudaMemcpyHostToDevice, d.stream)) == cudaSuccess &&
+        (!b || (e = cudaMemcpyAsync(db, b, bytes, cudaMemcpyHostToDevice, d.stream)) == cudaSuccess) &&
+        (e = launch_debug_eval(op, da, db, dout, n, d.stream)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, d.stream)) == cudaSuccess)
+        e = cudaStreamSynchronize(d.stream);
+    if (e != cudaSuccess) rc = cuda_fail(ctx, e, "curvis_debug_eval");
+    cudaFree(da); cudaFree(db); cudaFree(dout);
+    return rc;
 }

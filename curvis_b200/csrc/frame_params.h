@@ -32,6 +32,9 @@ struct FrameParams {
     // camera (cameras.rs:30-43)
     double cam_pos[4];
     double cam_to_world[9];
+    // r(l_camera) and sin(theta_camera): per-frame uniforms of new_photon (metrics.rs:329-330),
+    // evaluated once on the host with the platform libm like the reference does per ray
+    double cam_r, cam_sin_theta;
     double focal_length, sensor_width, sensor_height;
     uint32_t width, height;
     // render_image arguments (systems.rs:309-311)
@@ -40,6 +43,9 @@ struct FrameParams {
     double max_radius, delta;
     // tile of the frame this launch renders: rows [row_begin, row_end)
     uint32_t row_begin, row_end;
+    // steps between two refill points of a warp (render_f64.cu), tuning knob
+    uint32_t window;
+    uint32_t _pad0;
     // scene (systems.rs:70-71): [0] = background_positive, [1] = background_negative
     Background bg[2];
     // outputs: RGB8 rows of the tile (packed, row-major), optional per-ray records, counters

@@ -9,6 +9,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "frame_params.h"
+#include "ieee_f64.cuh"
+#include "trig_f64.cuh"
 
 namespace curvis {
 
@@ -42,6 +44,14 @@ struct ShapeEllis {  // metrics.rs:417-421
         r = sqrt(r2);                // :418
         rp = l / r;                  // :420
     }
+    // Same values through the unguarded correctly-rounded sequences (ieee_f64.cuh); only
+    // called when step_operands_safe() holds.
+    static __device__ __forceinline__ void eval_fast(const FrameParams& p, double l, double& r, double& r2, double& rp) {
+        r2 = p.rho * p.rho + l * l;
+        r = sqrt_rn_unguarded(r2);
+        rp = div_rn_unguarded(l, r);
+    }
+    static __device__ __forceinline__ bool params_safe(const FrameParams& p) { return exponent_in(p.rho, -100, 100); }
 };
 
 struct ShapeInterstellar {  // metrics.rs:461-485
@@ -60,6 +70,14 @@ struct ShapeInterstellar {  // metrics.rs:461-485
         }
         r2 = r * r;      // :474
     }
+    // atan/log dominate this metric; the generic evaluation is kept (its one division has a
+    // uniform divisor) and only the step's six divisions take the unguarded path.
+    static __device__ __forceinline__ void eval_fast(const FrameParams& p, double l, double& r, double& r2, double& rp) {
+        eval(p, l, r, r2, rp);
+    }
+    static __device__ __forceinline__ bool params_safe(const FrameParams& p) {
+        return exponent_in(p.rho, -100, 100) && exponent_in(p.m, -100, 100) && exponent_in(p.a, -100, 100);
+    }
 };
 
 struct ShapeFlat {  // metrics.rs:501-505
@@ -67,6 +85,10 @@ struct ShapeFlat {  // metrics.rs:501-505
     static __device__ __forceinline__ void eval(const FrameParams&, double l, double& r, double& r2, double& rp) {
         r = l; r2 = l * l; rp = 1.0;
     }
+    static __device__ __forceinline__ void eval_fast(const FrameParams& p, double l, double& r, double& r2, double& rp) {
+        eval(p, l, r, r2, rp);
+    }
+    static __device__ __forceinline__ bool params_safe(const FrameParams&) { return true; }
 };
 
 // ---------------------------------------------------------------- nalgebra-order helpers
@@ -93,7 +115,6 @@ __device__ __forceinline__ void normalize_theta_phi(double& th, double& ph) {
 // ---------------------------------------------------------------- ray generation
 // camera_pixels_x_y_to_photon (systems.rs:531-534): outward_vector_on_camera_space
 // (cameras.rs:150-164), camera_to_world rotation (:169-172), new_photon (metrics.rs:301-334).
-template <class Shape, class Trig>
 __device__ __forceinline__ void new_photon_for_pixel(const FrameParams& p, uint32_t px, uint32_t py, Ray& q) {
     const double res_x = (double)p.width, res_y = (double)p.height;
     const double h = 0.5 - ((double)py / res_y);
@@ -107,12 +128,10 @@ __device__ __forceinline__ void new_photon_for_pixel(const FrameParams& p, uint3
     mat3_mul(p.cam_to_world, vx, vy, vz, dx, dy, dz);            // cameras.rs:171
     n = norm3(dx, dy, dz);
     dx = dx / n; dy = dy / n; dz = dz / n;                       // metrics.rs:320
-    double r, r2, rp;
-    Shape::eval(p, p.cam_pos[1], r, r2, rp);
     q.l = p.cam_pos[1]; q.th = p.cam_pos[2]; q.ph = p.cam_pos[3];
     q.pl = dx;                                                   // :328
-    q.pth = dy * r;                                              // :329
-    q.pph = dz * r * Trig::sin(p.cam_pos[2]);                    // :330
+    q.pth = dy * p.cam_r;                                        // :329  direction[1] * r(l)
+    q.pph = dz * p.cam_r * p.cam_sin_theta;                      // :330  direction[2] * r(l) * sin(theta)
     q.pph2 = q.pph * q.pph;
 }
 
@@ -139,6 +158,97 @@ __device__ __forceinline__ void euler_step(const FrameParams& p, Ray& q) {
     q.th = q.th + dth * p.delta;
     q.ph = q.ph + dph * p.delta;
     q.pl = q.pl + dpl * p.delta;                              // :296
+    q.pth = q.pth + dpth * p.delta;
+}
+
+// ---------------------------------------------------------------- the same step, tuned
+// Identical arithmetic (every rounding of the reference sequence is kept; IEEE division and
+// sqrt are correctly rounded either way), but the six divisions and the square root run the
+// unguarded Newton-Raphson sequences of ieee_f64.cuh behind ONE merged operand-range check
+// instead of one guard + branch each.  `ray_safe` carries the per-ray part of the check
+// (p_phi^2 and the frame parameters, constant along a ray).  Outside the window — rays grazing
+// the coordinate poles (sin theta -> 0), NaN/Inf states — the plain operators are used.
+__device__ __forceinline__ bool ray_operands_safe(const Ray& q) { return exponent_in(q.pph2, -200, 200); }
+
+template <class Shape, class Trig>
+__device__ __forceinline__ void euler_step_tuned(const FrameParams& p, Ray& q, bool ray_safe) {
+    double s, c;
+    Trig::sincos(q.th, s, c);
+    double dl, dth, dph, dpl, dpth;
+    const bool safe = ray_safe && exponent_in(s, -60, 1) && exponent_in(q.l, -100, 100) && (fabs(q.pth) < 0x1p100);
+    if (safe) {
+        double r, r2, rp;
+        Shape::eval_fast(p, q.l, r, r2, rp);
+        const double s2 = s * s;
+        const double g22c = rcp_rn_unguarded(r2);
+        const double g33c = rcp_rn_unguarded(r2 * s2);
+        dl = q.pl;
+        dth = q.pth * g22c;
+        dph = q.pph * g33c;
+        const double b2 = q.pth * q.pth + div_rn_unguarded(q.pph2, s2);
+        dpl = div_rn_unguarded(b2 * rp, (r * r) * r);
+        dpth = q.pph2 * div_rn_unguarded(c, r2 * (s2 * s));
+    } else {
+        double r, r2, rp;
+        Shape::eval(p, q.l, r, r2, rp);
+        const double s2 = s * s;
+        const double g22c = 1.0 / r2;
+        const double g33c = 1.0 / (r2 * s2);
+        dl = q.pl;
+        dth = q.pth * g22c;
+        dph = q.pph * g33c;
+        const double b2 = q.pth * q.pth + q.pph2 / s2;
+        dpl = (b2 * rp) / ((r * r) * r);
+        dpth = q.pph2 * (c / (r2 * (s2 * s)));
+    }
+    q.l = q.l + dl * p.delta;
+    q.th = q.th + dth * p.delta;
+    q.ph = q.ph + dph * p.delta;
+    q.pl = q.pl + dpl * p.delta;
+    q.pth = q.pth + dpth * p.delta;
+}
+
+// ---------------------------------------------------------------- the lean step (default kernel)
+// euler_step_tuned with the operand check done entirely on the integer pipe (high-word
+// exponent compares) BEFORE the trigonometry, so the common case runs sincos_fast + the
+// unguarded sequences with two predictable branches and no fp64 compare.  On sm_100a an fp64
+// instruction holds the scheduler's dispatch port for two cycles, so every fp64 op removed is
+// worth two integer ops (profiles/r01_f64_v2_ncu_summary.txt).  Arithmetic is unchanged.
+template <class Shape>
+__device__ __forceinline__ void euler_step_lean(const FrameParams& p, Ray& q, bool ray_safe) {
+    const bool pre = ray_safe && (abs_hi(q.th) < pow2_hi(30)) && ((abs_hi(q.l) - pow2_hi(-100)) < (pow2_hi(100) - pow2_hi(-100))) &&
+                     (abs_hi(q.pth) < pow2_hi(100));
+    double s, c;
+    if (pre) sincos_fast(q.th, s, c);
+    else TrigFast::sincos(q.th, s, c);
+    double dth, dph, dpl, dpth;
+    if (pre && abs_hi(s) >= pow2_hi(-60)) {
+        double r, r2, rp;
+        Shape::eval_fast(p, q.l, r, r2, rp);
+        const double s2 = s * s;
+        const double g22c = rcp_rn_unguarded(r2);
+        const double g33c = rcp_rn_unguarded(r2 * s2);
+        dth = q.pth * g22c;
+        dph = q.pph * g33c;
+        const double b2 = q.pth * q.pth + div_rn_unguarded(q.pph2, s2);
+        dpl = div_rn_unguarded(b2 * rp, (r * r) * r);
+        dpth = q.pph2 * div_rn_unguarded(c, r2 * (s2 * s));
+    } else {
+        double r, r2, rp;
+        Shape::eval(p, q.l, r, r2, rp);
+        const double s2 = s * s;
+        const double g22c = 1.0 / r2;
+        const double g33c = 1.0 / (r2 * s2);
+        dth = q.pth * g22c;
+        dph = q.pph * g33c;
+        const double b2 = q.pth * q.pth + q.pph2 / s2;
+        dpl = (b2 * rp) / ((r * r) * r);
+        dpth = q.pph2 * (c / (r2 * (s2 * s)));
+    }
+    q.l = q.l + q.pl * p.delta;
+    q.th = q.th + dth * p.delta;
+    q.ph = q.ph + dph * p.delta;
+    q.pl = q.pl + dpl * p.delta;
     q.pth = q.pth + dpth * p.delta;
 }
 

@@ -10,6 +10,7 @@
 #include <cstring>
 #include "../../include/curvis_gpu.h"
 #include "host_error.h"
+#include "launch_host.h"
 
 namespace {
 
@@ -50,6 +51,27 @@ Mat3 face_towards(const Vec3& dir, const Vec3& up) {
 }
 
 }  // namespace
+
+namespace curvis {
+
+// r(l) of the three metrics, reference operation order (metrics.rs:417-418, :465-472, :502).
+double host_shape_r(const curvis_metric& g, double l) {
+    const double pi = 3.14159265358979323846264338327950288;
+    switch (g.kind) {
+    case CURVIS_METRIC_ELLIS: return std::sqrt(g.rho * g.rho + l * l);
+    case CURVIS_METRIC_INTERSTELLAR:
+        if (std::fabs(l) > g.a) {
+            const double x = 2.0 * (std::fabs(l) - g.a) / (pi * g.m);
+            return g.rho + g.m * (x * std::atan(x) - std::log(1.0 + x * x) / 2.0);
+        }
+        return g.rho;
+    default: return l;
+    }
+}
+
+double host_sin(double x) { return std::sin(x); }
+
+}  // namespace curvis
 
 extern "C" int curvis_orientation(const double forward[3], const double up[3],
                                   double rot[9], double inv_rot[9], double up_orthogonal[3]) {

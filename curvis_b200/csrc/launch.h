@@ -2,11 +2,25 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "frame_params.h"
+#include "launch_host.h"
 
 namespace curvis {
 
+// Tuning knobs of a context (curvis_ctx_set_option).
+struct LaunchTuning {
+    int kernel_variant = 3;  // 0 plain operators + CUDA sincos (round-1 v0); 1 unguarded IEEE sequences + CUDA sincos;
+                             // 2 + in-kernel sincos; 3 (default) lean loop: integer-pipe guards, gated escape test
+    int blocks_per_sm = 0;   // 0 = occupancy maximum
+    int window = 32;         // Euler steps between two refill points of a warp
+};
+
 // fp64 parity kernel (render_f64.cu, compiled with -fmad=false).
-cudaError_t launch_render_f64(const FrameParams& p, int metric_kind, int sm_count, cudaStream_t stream);
+cudaError_t launch_render_f64(const FrameParams& p, int metric_kind, const LaunchTuning& t, int sm_count, cudaStream_t stream);
+
+// Elementwise evaluation of one device math primitive (test hook, curvis_debug_eval).
+cudaError_t launch_debug_eval(int op, const double* a, const double* b, double* out, size_t n, cudaStream_t stream);
+
+
 
 // FMA-only micro-kernels used as the measured compute-roofline denominator (peak_kernels.cu).
 cudaError_t measure_fma_peak(int sm_count, cudaStream_t stream, double* fp64_tflops, double* fp32_tflops);

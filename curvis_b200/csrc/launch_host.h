@@ -1,0 +1,7 @@
+// launch_host.h — host-only declarations shared by host_setup.cpp (g++) and curvis_abi.cu.
+#pragma once
+#include "../../include/curvis_gpu.h"
+namespace curvis {
+double host_shape_r(const curvis_metric& metric, double l);
+double host_sin(double x);
+}

@@ -16,10 +16,11 @@
 namespace curvis {
 
 constexpr int kBlock = 128;
-constexpr int kWindow = 16;
 constexpr unsigned kFull = 0xffffffffu;
 
-template <class Shape, class Trig>
+// TUNED = true: euler_step_tuned (unguarded IEEE sequences behind one merged range check);
+// TUNED = false: euler_step (plain operators) — kept as the A/B baseline and safety net.
+template <class Shape, class Trig, bool TUNED>
 __global__ void __launch_bounds__(kBlock) render_rows_f64(const __grid_constant__ FrameParams p) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -29,6 +30,8 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64(const __grid_constant_
     bool live = false;      // this lane is integrating a ray
     bool pending = false;   // this lane finished a ray whose epilogue has not run yet
     bool drained = false;   // the queue is empty (warp-uniform)
+    bool ray_safe = false;  // per-ray part of the tuned step's operand check
+    const bool frame_safe = Shape::params_safe(p);
     int side = 0;
     uint32_t steps = 0;
     unsigned long long ray = 0;
@@ -39,7 +42,6 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64(const __grid_constant_
     for (;;) {
         // ---- epilogue of the lanes that finished during the last window
         if (pending) {
-            const uint32_t px = (uint32_t)(ray % p.width);
             uint32_t rgba = 0, tx = 0, ty = 0;
             if (side != 0) {
                 const Background& bg = p.bg[side > 0 ? 0 : 1];
@@ -60,7 +62,6 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64(const __grid_constant_
                 rec.steps = steps; rec.side = side; rec.texel_x = tx; rec.texel_y = ty;
                 p.records[ray] = rec;
             }
-            (void)px;
             acc_steps += steps;
             pending = false;
         }
@@ -79,7 +80,8 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64(const __grid_constant_
                         ray = idx;
                         const uint32_t px = (uint32_t)(idx % p.width);
                         const uint32_t py = p.row_begin + (uint32_t)(idx / p.width);
-                        new_photon_for_pixel<Shape, Trig>(p, px, py, q);
+                        new_photon_for_pixel(p, px, py, q);
+                        ray_safe = frame_safe && ray_operands_safe(q);
                         steps = 0;
                         side = 0;
                         if (p.max_iterations == 0) pending = true;  // loop of systems.rs:126 runs zero times
@@ -93,9 +95,10 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64(const __grid_constant_
 
         // ---- WINDOW Euler steps (escape_photon's loop body, systems.rs:126-135)
 #pragma unroll 1
-        for (int k = 0; k < kWindow; ++k) {
+        for (uint32_t k = 0; k < p.window; ++k) {
             if (live) {
-                euler_step<Shape, Trig>(p, q);
+                if (TUNED) euler_step_tuned<Shape, Trig>(p, q, ray_safe);
+                else euler_step<Shape, Trig>(p, q);
                 ++steps;
                 if (q.l > p.max_radius) { side = 1; live = false; pending = true; }          // :129-131
                 else if (q.l < -p.max_radius) { side = -1; live = false; pending = true; }   // :132-134
@@ -121,29 +124,196 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64(const __grid_constant_
     }
 }
 
-template <class Shape, class Trig>
-static cudaError_t launch_one(const FrameParams& p, int sm_count, cudaStream_t stream) {
-    static int blocks_per_sm = 0;  // per instantiation; same for every sm_100 device
-    if (blocks_per_sm == 0) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_rows_f64<Shape, Trig>, kBlock, 0);
-        if (e != cudaSuccess) return e;
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
+// ---------------------------------------------------------------- default kernel (variant 2)
+// Same execution model as render_rows_f64, leaner loop state: a down-counter instead of
+// steps/max compare, the escape side decided in the epilogue from the final l, and the
+// per-step escape test gated by an integer compare of |l|'s high word against the radius's
+// (the fp64 compares only run within 2^-20 of the radius, or for NaN).
+template <class Shape>
+__global__ void __launch_bounds__(kBlock) render_rows_f64_lean(const __grid_constant__ FrameParams p) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned long long tile_rays = (unsigned long long)(p.row_end - p.row_begin) * p.width;
+    const double R = p.max_radius;
+    // |l| > R needs abs_hi(l) >= hi(R) when R >= 0; for negative or NaN R the gate is open.
+    const unsigned gate = (R >= 0.0) ? abs_hi(R) : 0u;
+    const bool frame_safe = Shape::params_safe(p);
+
+    Ray q;
+    int state = 0;            // 0 idle, 1 integrating, 2 finished (epilogue pending)
+    bool drained = false;     // the queue is empty (warp-uniform)
+    bool ray_safe = false;
+    uint32_t remaining = 0;   // steps left before NotEscaped
+    unsigned long long ray = 0;
+
+    unsigned long long acc_steps = 0;
+    unsigned acc_pos = 0, acc_neg = 0, acc_none = 0, acc_clamped = 0;
+
+    for (;;) {
+        if (state == 2) {
+            const uint32_t steps = p.max_iterations - remaining;
+            const int side = (q.l > R) ? 1 : ((q.l < -R) ? -1 : 0);   // systems.rs:129-134 on the final state
+            uint32_t rgba = 0, tx = 0, ty = 0;
+            if (side != 0) {
+                const Background& bg = p.bg[side > 0 ? 0 : 1];
+                if (escaped_texel<Shape, TrigFast>(p, q, bg, tx, ty)) ++acc_clamped;
+                rgba = __ldg(bg.texels + (size_t)ty * bg.width + tx);
+                if (side > 0) ++acc_pos; else ++acc_neg;
+            } else {
+                ++acc_none;
+            }
+            uint8_t* o = p.out_rgb8 + ray * 3ull;
+            o[0] = (uint8_t)(rgba & 0xffu);
+            o[1] = (uint8_t)((rgba >> 8) & 0xffu);
+            o[2] = (uint8_t)((rgba >> 16) & 0xffu);
+            if (p.records) {
+                curvis_ray_record rec;
+                rec.l = q.l; rec.theta = q.th; rec.phi = q.ph;
+                rec.p_l = q.pl; rec.p_theta = q.pth; rec.p_phi = q.pph;
+                rec.steps = steps; rec.side = side; rec.texel_x = tx; rec.texel_y = ty;
+                p.records[ray] = rec;
+            }
+            acc_steps += steps;
+            state = 0;
+        }
+
+        const unsigned idle = __ballot_sync(kFull, state == 0);
+        if (idle) {
+            if (!drained) {
+                const int leader = __ffs(idle) - 1;
+                unsigned long long base = 0;
+                if ((int)lane == leader) base = atomicAdd(&p.counters->next_ray, (unsigned long long)__popc(idle));
+                base = __shfl_sync(kFull, base, leader);
+                if (state == 0) {
+                    const unsigned long long idx = base + (unsigned long long)__popc(idle & lt_mask);
+                    if (idx < tile_rays) {
+                        ray = idx;
+                        new_photon_for_pixel(p, (uint32_t)(idx % p.width), p.row_begin + (uint32_t)(idx / p.width), q);
+                        ray_safe = frame_safe && ray_operands_safe(q);
+                        remaining = p.max_iterations;
+                        state = (remaining == 0) ? 2 : 1;   // the loop of systems.rs:126 may run zero times
+                    }
+                }
+                if (base + (unsigned long long)__popc(idle) >= tile_rays) drained = true;
+            }
+            if (__ballot_sync(kFull, state != 0) == 0u) break;
+        }
+
+#pragma unroll 1
+        for (uint32_t k = 0; k < p.window; ++k) {
+            if (state == 1) {
+                euler_step_lean<Shape>(p, q, ray_safe);
+                --remaining;
+                bool done = (remaining == 0);                                   // systems.rs:137
+                if (abs_hi(q.l) >= gate) done = done || (q.l > R) || (q.l < -R);  // :129-134
+                if (done) state = 2;
+            }
+        }
     }
+
+    for (int o = 16; o > 0; o >>= 1) {
+        acc_steps += __shfl_down_sync(kFull, acc_steps, o);
+        acc_pos += __shfl_down_sync(kFull, acc_pos, o);
+        acc_neg += __shfl_down_sync(kFull, acc_neg, o);
+        acc_none += __shfl_down_sync(kFull, acc_none, o);
+        acc_clamped += __shfl_down_sync(kFull, acc_clamped, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&p.counters->total_steps, acc_steps);
+        if (acc_pos) atomicAdd(&p.counters->n_positive, (unsigned long long)acc_pos);
+        if (acc_neg) atomicAdd(&p.counters->n_negative, (unsigned long long)acc_neg);
+        if (acc_none) atomicAdd(&p.counters->n_not_escaped, (unsigned long long)acc_none);
+        if (acc_clamped) atomicAdd(&p.counters->n_clamped, (unsigned long long)acc_clamped);
+    }
+}
+
+template <class Kernel>
+static cudaError_t launch_persistent(Kernel kernel, int& blocks_per_sm_auto, const FrameParams& p, int sm_count,
+                                     int blocks_per_sm_override, cudaStream_t stream) {
+    if (blocks_per_sm_auto == 0) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm_auto, kernel, kBlock, 0);
+        if (e != cudaSuccess) return e;
+        if (blocks_per_sm_auto < 1) blocks_per_sm_auto = 1;
+    }
+    int blocks_per_sm = blocks_per_sm_auto;
+    if (blocks_per_sm_override > 0 && blocks_per_sm_override < blocks_per_sm) blocks_per_sm = blocks_per_sm_override;
     const unsigned long long tile_rays = (unsigned long long)(p.row_end - p.row_begin) * p.width;
     unsigned long long want = (tile_rays + kBlock - 1) / kBlock;
     unsigned long long cap = (unsigned long long)sm_count * (unsigned long long)blocks_per_sm;
     const unsigned grid = (unsigned)(want < cap ? (want ? want : 1) : cap);
-    render_rows_f64<Shape, Trig><<<grid, kBlock, 0, stream>>>(p);
+    kernel<<<grid, kBlock, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
-cudaError_t launch_render_f64(const FrameParams& p, int metric_kind, int sm_count, cudaStream_t stream) {
+template <class Shape>
+static cudaError_t launch_lean(const FrameParams& p, int sm_count, int blocks_per_sm_override, cudaStream_t stream) {
+    static int blocks_per_sm_auto = 0;
+    return launch_persistent(render_rows_f64_lean<Shape>, blocks_per_sm_auto, p, sm_count, blocks_per_sm_override, stream);
+}
+
+template <class Shape, class Trig, bool TUNED>
+static cudaError_t launch_one(const FrameParams& p, int sm_count, int blocks_per_sm_override, cudaStream_t stream) {
+    static int blocks_per_sm_auto = 0;  // per instantiation; same for every sm_100 device
+    if (blocks_per_sm_auto == 0) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm_auto, render_rows_f64<Shape, Trig, TUNED>, kBlock, 0);
+        if (e != cudaSuccess) return e;
+        if (blocks_per_sm_auto < 1) blocks_per_sm_auto = 1;
+    }
+    int blocks_per_sm = blocks_per_sm_auto;
+    if (blocks_per_sm_override > 0 && blocks_per_sm_override < blocks_per_sm) blocks_per_sm = blocks_per_sm_override;
+    const unsigned long long tile_rays = (unsigned long long)(p.row_end - p.row_begin) * p.width;
+    unsigned long long want = (tile_rays + kBlock - 1) / kBlock;
+    unsigned long long cap = (unsigned long long)sm_count * (unsigned long long)blocks_per_sm;
+    const unsigned grid = (unsigned)(want < cap ? (want ? want : 1) : cap);
+    render_rows_f64<Shape, Trig, TUNED><<<grid, kBlock, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+template <class Shape>
+static cudaError_t launch_variant(const FrameParams& p, const LaunchTuning& t, int sm_count, cudaStream_t stream) {
+    switch (t.kernel_variant) {
+    case 0: return launch_one<Shape, TrigCuda, false>(p, sm_count, t.blocks_per_sm, stream);   // round-1 v0
+    case 1: return launch_one<Shape, TrigCuda, true>(p, sm_count, t.blocks_per_sm, stream);
+    case 2: return launch_one<Shape, TrigFast, true>(p, sm_count, t.blocks_per_sm, stream);
+    default: return launch_lean<Shape>(p, sm_count, t.blocks_per_sm, stream);                  // default (3)
+    }
+}
+
+cudaError_t launch_render_f64(const FrameParams& p, int metric_kind, const LaunchTuning& t, int sm_count, cudaStream_t stream) {
     switch (metric_kind) {
-    case CURVIS_METRIC_ELLIS: return launch_one<ShapeEllis, TrigCuda>(p, sm_count, stream);
-    case CURVIS_METRIC_INTERSTELLAR: return launch_one<ShapeInterstellar, TrigCuda>(p, sm_count, stream);
-    case CURVIS_METRIC_FLAT: return launch_one<ShapeFlat, TrigCuda>(p, sm_count, stream);
+    case CURVIS_METRIC_ELLIS: return launch_variant<ShapeEllis>(p, t, sm_count, stream);
+    case CURVIS_METRIC_INTERSTELLAR: return launch_variant<ShapeInterstellar>(p, t, sm_count, stream);
+    case CURVIS_METRIC_FLAT: return launch_variant<ShapeFlat>(p, t, sm_count, stream);
     default: return cudaErrorInvalidValue;
     }
+}
+
+// ---------------------------------------------------------------- op-level test hook
+__global__ void debug_eval_kernel(int op, const double* a, const double* b, double* out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = a[i], y = b ? b[i] : 0.0;
+    double r = 0.0, s, c;
+    switch (op) {
+    case 0: r = rcp_rn_unguarded(x); break;
+    case 1: r = div_rn_unguarded(x, y); break;
+    case 2: r = sqrt_rn_unguarded(x); break;
+    case 3: sincos_fast(x, s, c); r = s; break;
+    case 4: sincos_fast(x, s, c); r = c; break;
+    case 5: TrigFast::sincos(x, s, c); r = s; break;
+    case 6: TrigFast::sincos(x, s, c); r = c; break;
+    case 7: r = x / y; break;
+    case 8: r = sqrt(x); break;
+    case 9: r = 1.0 / x; break;
+    default: break;
+    }
+    out[i] = r;
+}
+
+cudaError_t launch_debug_eval(int op, const double* a, const double* b, double* out, size_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    debug_eval_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(op, a, b, out, n);
+    return cudaGetLastError();
 }
 
 }  // namespace curvis

@@ -1,0 +1,71 @@
+// trig_f64.cuh — sin/cos for the Euler step, fp64, ~1 ulp (same class as the CUDA math
+// library's sincos: <= 2 ulp).  Written out here because the library version costs ~35
+// non-fp64 instructions per call in constant materialisation and guards (UMOV/IMAD.MOV/BRA,
+// see profiles/r01_f64_v0_ncu_summary.txt); here the coefficients come straight from the
+// constant bank as FMA operands and the large-argument guard is part of the step's single
+// merged check.  Coefficients: tools/gen_trig_coeffs.py (Remez on [0,(1.02*pi/4)^2]).
+//
+// The reference calls the platform libm (glibc) here; no GPU implementation is bit-identical
+// to it (glibc's own result depends on the CPU's FMA support), so the parity bar for the
+// photon STATE is a tolerance while RGB / steps / texels must be identical.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace curvis {
+
+__device__ __constant__ double kSinPoly[6] = {
+    -0.16666666666666663, 0.00833333333333043, -0.00019841269835988552,
+    2.7557315710929657e-06, -2.5051051817332214e-08, 1.5912475864762696e-10};
+__device__ __constant__ double kCosPoly[6] = {
+    0.041666666666666664, -0.0013888888888887072, 2.4801587298283765e-05,
+    -2.755731702664308e-07, 2.0876096187138334e-09, -1.1379094621237813e-11};
+
+constexpr double kTwoOverPi = 0.6366197723675814;
+constexpr double kPio2Hi = 1.5707963267948966;
+constexpr double kPio2Mid = 6.123233995736766e-17;
+constexpr double kPio2Lo = -1.4973849048591698e-33;
+constexpr double kRoundMagic = 6755399441055744.0;   // 1.5 * 2^52: adding it rounds to an integer in the low word
+constexpr double kTrigFastLimit = 1073741824.0;      // 2^30: beyond it fall back to ::sincos (Payne-Hanek)
+
+// sin and cos of x for |x| < kTrigFastLimit (caller guarantees it; NaN/Inf excluded).
+__device__ __forceinline__ void sincos_fast(double x, double& s, double& c) {
+    const double t = fma(x, kTwoOverPi, kRoundMagic);
+    const int k = __double2loint(t);                  // nearest integer to x*2/pi
+    const double q = t - kRoundMagic;
+    double r = fma(-q, kPio2Hi, x);
+    r = fma(-q, kPio2Mid, r);
+    r = fma(-q, kPio2Lo, r);
+    const double u = r * r;
+    double sp = fma(u, kSinPoly[5], kSinPoly[4]);
+    double cp = fma(u, kCosPoly[5], kCosPoly[4]);
+    sp = fma(u, sp, kSinPoly[3]);
+    cp = fma(u, cp, kCosPoly[3]);
+    sp = fma(u, sp, kSinPoly[2]);
+    cp = fma(u, cp, kCosPoly[2]);
+    sp = fma(u, sp, kSinPoly[1]);
+    cp = fma(u, cp, kCosPoly[1]);
+    sp = fma(u, sp, kSinPoly[0]);
+    cp = fma(u, cp, kCosPoly[0]);
+    const double sr = fma(r * u, sp, r);              // sin(r)
+    const double cr = fma(u * u, cp, fma(u, -0.5, 1.0));  // cos(r)
+    // quadrant: sin(x) = [sr, cr, -sr, -cr][k&3], cos(x) = [cr, -sr, -cr, sr][k&3]
+    const double a = (k & 1) ? cr : sr;
+    const double b = (k & 1) ? sr : cr;
+    // sign flips on the integer pipe (bit 1 of k, resp. k+1, moved onto the sign bit)
+    s = __hiloint2double(__double2hiint(a) ^ ((k & 2) << 30), __double2loint(a));
+    c = __hiloint2double(__double2hiint(b) ^ (((k + 1) & 2) << 30), __double2loint(b));
+}
+
+struct TrigFast {
+    static __device__ __forceinline__ void sincos(double x, double& s, double& c) {
+        if (fabs(x) < kTrigFastLimit) sincos_fast(x, s, c);
+        else ::sincos(x, &s, &c);
+    }
+    static __device__ __forceinline__ double sin(double x) {
+        double s, c;
+        sincos(x, s, c);
+        return s;
+    }
+};
+
+}  // namespace curvis

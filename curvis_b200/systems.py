@@ -45,6 +45,23 @@ class Context:
         except Exception:
             pass
 
+    def set_option(self, key: str, value: int) -> None:
+        """curvis_ctx_set_option: tuning knobs ("kernel_variant", "blocks_per_sm", "window")."""
+        _abi.check(self._lib.curvis_ctx_set_option(self._ptr, key.encode(), int(value)), self._ptr)
+
+    def debug_eval(self, op: int, a, b=None):
+        """curvis_debug_eval: one device math primitive evaluated elementwise (test hook)."""
+        import numpy as np
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        out = np.empty_like(a)
+        dp = C.POINTER(C.c_double)
+        bp = None
+        if b is not None:
+            b = np.ascontiguousarray(b, dtype=np.float64)
+            bp = b.ctypes.data_as(dp)
+        _abi.check(self._lib.curvis_debug_eval(self._ptr, op, a.ctypes.data_as(dp), bp, out.ctypes.data_as(dp), a.size), self._ptr)
+        return out
+
     def measure_fma_peak(self):
         f64, f32 = C.c_double(), C.c_double()
         _abi.check(self._lib.curvis_measure_fma_peak(self._ptr, C.byref(f64), C.byref(f32)), self._ptr)

@@ -213,6 +213,22 @@ uint64_t curvis_kernel_launch_count(void);
  * compute-roofline denominator (MEASURED_PEAKS.json has no fp64/fp32 ALU entry). */
 int curvis_measure_fma_peak(curvis_ctx* ctx, double* fp64_tflops, double* fp32_tflops);
 
+/* ---- tuning and test hooks ------------------------------------------------------------ */
+
+/* Tuning knobs of a context; results never depend on them (tests/test_gpu_parity.py).
+ *   "kernel_variant": 0 plain `/`, sqrt and CUDA sincos; 1 unguarded IEEE sequences + CUDA
+ *                     sincos; 2 unguarded IEEE sequences + in-kernel sincos; 3 (default) the same
+ *                     arithmetic in the lean loop (integer-pipe guards, gated escape test)
+ *   "blocks_per_sm":  resident CTAs per SM of the persistent grid (0 = occupancy maximum)
+ *   "window":         Euler steps between two refill points of a warp (default 32)        */
+int curvis_ctx_set_option(curvis_ctx* ctx, const char* key, int64_t value);
+
+/* Op-level test hook: out[i] = op(a[i], b[i]) evaluated on the device (host pointers).
+ *   0 rcp_rn_unguarded(a)  1 div_rn_unguarded(a,b)  2 sqrt_rn_unguarded(a)
+ *   3 / 4 sin / cos of the in-kernel sincos fast path   5 / 6 the same with its large-argument fallback
+ *   7 a/b   8 sqrt(a)   9 1/a   (the compiler's IEEE operators, for reference)              */
+int curvis_debug_eval(curvis_ctx* ctx, int op, const double* a, const double* b, double* out, size_t n);
+
 #ifdef __cplusplus
 }
 #endif
