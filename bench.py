@@ -60,7 +60,7 @@ def workload_config(args, n):
                     f"escape_radius 100 / max_iterations 40000 / step 0.05 (forward Euler, early exit), nearest u8 lookup in "
                     f"two {BG_W}x{BG_H} RGBA8 backgrounds",
         "frames_per_step": n,
-        "parallelism": "single GPU" if n == 1 else f"{n} frames/step, each row-tiled over {n} ranks + NCCL all-gather of row tiles",
+        "parallelism": "single GPU" if n == 1 else f"{n} frames/step (camera path), each row-tiled over {n} ranks: one batched launch per rank + one NCCL all-gather of row tiles per frame",
         "l2": "256 MiB device buffer rewritten between steps inside the timed region (L2 flush); the kernel is ALU-bound",
     }
 
@@ -220,31 +220,36 @@ def run_b200(args):
 
     stream = torch.cuda.current_stream()
     frames = [torch.empty(Ht * Wd * 3, dtype=torch.uint8, device=dev) for _ in range(n)]   # complete frames
-    tile = torch.empty(rows * Wd * 3, dtype=torch.uint8, device=dev)
+    tiles = torch.empty(n * rows * Wd * 3, dtype=torch.uint8, device=dev)                  # this rank's tile of each frame
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    # synthetic camera path: frame f sits 0.02*f further out along l (a dolly move), same orientation
+    cameras = [cv.Camera((0.0, scenes.DEFAULT_CAMERA_POSITION[1] + 0.02 * f, scenes.DEFAULT_CAMERA_POSITION[2], 0.0),
+                         scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP, scenes.DEFAULT_FOCAL_LENGTH, scenes.DEFAULT_DIAGONAL, Wd, Ht)
+               for f in range(n)]
+    tile_bytes = rows * Wd * 3
 
     def barrier():
         if world > 1:
             dist.barrier()
 
-    def device_step():
-        """One step of the resident path: n frames, this rank's row tile of each, all-gather."""
+    def device_step(want_stats=False):
+        """One step of the resident path: n frames; this rank's row tile of every frame in ONE
+        batched launch (curvis_render_frames_device), then one all-gather per frame."""
         flush.fill_(1)
+        if n == 1:
+            return system.render_rows_device(*sim, row_begin, row_end, frames[0].data_ptr(), stream.cuda_stream, want_stats=want_stats)
+        st = system.render_frames_device(cameras, *sim, row_begin, row_end, tiles.data_ptr(), stream.cuda_stream, want_stats=want_stats)
         for f in range(n):
-            if n == 1:
-                system.render_rows_device(*sim, row_begin, row_end, frames[f].data_ptr(), stream.cuda_stream)
-            else:
-                system.render_rows_device(*sim, row_begin, row_end, tile.data_ptr(), stream.cuda_stream)
-                dist.all_gather_into_tensor(frames[f], tile)
+            dist.all_gather_into_tensor(frames[f], tiles[f * tile_bytes:(f + 1) * tile_bytes])
+        return st
 
-    # steps of one tile (deterministic) -> steps per job-step
-    st = system.render_rows_device(*sim, row_begin, row_end, tile.data_ptr() if n > 1 else frames[0].data_ptr(),
-                                   stream.cuda_stream, want_stats=True)
-    tile_steps = torch.tensor([st["total_steps"]], dtype=torch.int64, device=dev)
+    # steps of this rank's share of one job-step (deterministic) -> total over ranks
+    st = device_step(want_stats=True)
+    share = torch.tensor([st["total_steps"]], dtype=torch.int64, device=dev)
     if world > 1:
-        dist.all_reduce(tile_steps)
-    frame_steps = int(tile_steps.item())          # Euler steps of one whole frame
-    steps_per_job_step = frame_steps * n
+        dist.all_reduce(share)
+    steps_per_job_step = int(share.item())        # Euler steps of the n frames of one step
+    frame_steps = steps_per_job_step // n
 
     for _ in range(args.warmup):
         device_step()
@@ -272,8 +277,7 @@ def run_b200(args):
     # kernel-only duration of the dominant kernel (events recorded by the library around it)
     kernel_ms = []
     for _ in range(3):
-        s2 = system.render_rows_device(*sim, row_begin, row_end, tile.data_ptr() if n > 1 else frames[0].data_ptr(),
-                                       stream.cuda_stream, want_stats=True)
+        s2 = device_step(want_stats=True)
         kernel_ms.append(s2["kernel_ms"])
     kernel_ms = sum(kernel_ms) / len(kernel_ms)
     tile_steps_local = st["total_steps"]
@@ -286,9 +290,9 @@ def run_b200(args):
         if n == 1:
             system.render_image(*sim)                      # curvis_render_image: kernel + D2H + copy to caller buffer
         else:
+            system.render_frames_device(cameras, *sim, row_begin, row_end, tiles.data_ptr(), stream.cuda_stream)
             for f in range(n):
-                system.render_rows_device(*sim, row_begin, row_end, tile.data_ptr(), stream.cuda_stream)
-                dist.all_gather_into_tensor(frames[f], tile)
+                dist.all_gather_into_tensor(frames[f], tiles[f * tile_bytes:(f + 1) * tile_bytes])
                 if rank == 0:
                     host_frames[f].copy_(frames[f], non_blocking=True)
             torch.cuda.synchronize()
@@ -336,7 +340,7 @@ def run_b200(args):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     alg_bytes_per_ray = 4 + 3                                  # one RGBA8 texel read + 3 B written
-    tile_rays = rows * Wd
+    tile_rays = rows * Wd * n
     hbm_achieved = tile_rays * alg_bytes_per_ray / (kernel_ms * 1e-3) / 1e9
     traffic = None
     try:

@@ -37,6 +37,7 @@ struct DeviceState {
     uint8_t* d_out = nullptr; size_t d_out_cap = 0;
     uint8_t* h_out = nullptr; size_t h_out_cap = 0;  // pinned staging
     curvis_ray_record* d_records = nullptr; size_t d_records_cap = 0;
+    CameraBlock* d_cameras = nullptr; size_t d_cameras_cap = 0;   // batched launches
     // tile of the frame in flight
     uint32_t row_begin = 0, row_end = 0;
 };
@@ -93,17 +94,22 @@ static int validate_frame(curvis_ctx* ctx, const curvis_metric* metric, const cu
     return CURVIS_OK;
 }
 
+static void fill_camera(const curvis_metric* metric, const curvis_camera* cam, CameraBlock& c) {
+    std::memcpy(c.cam_pos, cam->position, sizeof c.cam_pos);
+    std::memcpy(c.cam_to_world, cam->cam_to_world, sizeof c.cam_to_world);
+    c.cam_r = host_shape_r(*metric, cam->position[1]);
+    c.cam_sin_theta = host_sin(cam->position[2]);
+    c.focal_length = cam->focal_length; c.sensor_width = cam->sensor_width; c.sensor_height = cam->sensor_height;
+}
+
 static void fill_params(const curvis_ctx* ctx, const DeviceState& d, const curvis_metric* metric, const curvis_camera* cam,
                         const curvis_sim* sim, uint32_t row_begin, uint32_t row_end, uint8_t* d_out,
                         curvis_ray_record* d_records, FrameParams& p) {
     std::memset(&p, 0, sizeof p);
     p.rho = metric->rho; p.m = metric->m; p.a = metric->a;
-    std::memcpy(p.cam_pos, cam->position, sizeof p.cam_pos);
-    std::memcpy(p.cam_to_world, cam->cam_to_world, sizeof p.cam_to_world);
-    p.cam_r = host_shape_r(*metric, cam->position[1]);
-    p.cam_sin_theta = host_sin(cam->position[2]);
+    fill_camera(metric, cam, p.cam);
+    p.cameras = nullptr; p.n_frames = 1;
     p.window = (uint32_t)(ctx->tuning.window > 0 ? ctx->tuning.window : 32);
-    p.focal_length = cam->focal_length; p.sensor_width = cam->sensor_width; p.sensor_height = cam->sensor_height;
     p.width = cam->resolution_width; p.height = cam->resolution_height;
     p.max_iterations = sim->max_iterations; p.sampling = (uint32_t)sim->sampling;
     p.max_radius = sim->max_radius; p.delta = sim->delta;
@@ -169,6 +175,7 @@ static void release_device(DeviceState& d) {
     if (d.d_out) cudaFree(d.d_out);
     if (d.h_out) cudaFreeHost(d.h_out);
     if (d.d_records) cudaFree(d.d_records);
+    if (d.d_cameras) cudaFree(d.d_cameras);
     if (d.ev_begin) cudaEventDestroy(d.ev_begin);
     if (d.ev_end) cudaEventDestroy(d.ev_end);
     if (d.stream) cudaStreamDestroy(d.stream);
@@ -284,6 +291,56 @@ extern "C" int curvis_render_rows_device(curvis_ctx* ctx, const curvis_metric* m
         CURVIS_CUDA(ctx, cudaStreamSynchronize(st));
         std::memset(stats, 0, sizeof *stats);
         add_counters(*d.h_counters, (uint64_t)(row_end - row_begin) * camera->resolution_width, stats);
+        float ms = 0.f;
+        CURVIS_CUDA(ctx, cudaEventElapsedTime(&ms, d.ev_begin, d.ev_end));
+        stats->kernel_ms = ms;
+        stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return CURVIS_OK;
+}
+
+extern "C" int curvis_render_frames_device(curvis_ctx* ctx, const curvis_metric* metric,
+                                           const curvis_camera* cameras, uint32_t n_frames, const curvis_sim* sim,
+                                           uint32_t row_begin, uint32_t row_end,
+                                           void* d_out_rgb8_tiles, void* stream, curvis_stats* stats) {
+    const auto t0 = std::chrono::steady_clock::now();
+    if (!ctx) return fail(nullptr, CURVIS_ERR_INVALID_ARGUMENT, "null context");
+    if (!cameras || n_frames == 0) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "no cameras");
+    for (uint32_t f = 0; f < n_frames; ++f) {
+        int rc = validate_frame(ctx, metric, &cameras[f], sim, row_begin, row_end);
+        if (rc != CURVIS_OK) return rc;
+        if (cameras[f].resolution_width != cameras[0].resolution_width || cameras[f].resolution_height != cameras[0].resolution_height)
+            return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "all frames of a batch must share one resolution");
+    }
+    if (!d_out_rgb8_tiles && row_end > row_begin) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "null device output");
+    DeviceState& d = ctx->devs[0];
+    cudaStream_t st = (cudaStream_t)stream;
+    CURVIS_CUDA(ctx, cudaSetDevice(d.ordinal));
+    if (n_frames > d.d_cameras_cap) {
+        if (d.d_cameras) cudaFree(d.d_cameras);
+        d.d_cameras = nullptr; d.d_cameras_cap = 0;
+        CURVIS_CUDA(ctx, cudaMalloc(&d.d_cameras, (size_t)n_frames * sizeof(CameraBlock)));
+        d.d_cameras_cap = n_frames;
+    }
+    std::vector<CameraBlock> blocks(n_frames);
+    for (uint32_t f = 0; f < n_frames; ++f) fill_camera(metric, &cameras[f], blocks[f]);
+    // pageable source: the driver stages it before returning, so `blocks` may die at scope exit
+    CURVIS_CUDA(ctx, cudaMemcpyAsync(d.d_cameras, blocks.data(), (size_t)n_frames * sizeof(CameraBlock), cudaMemcpyHostToDevice, st));
+    FrameParams p;
+    fill_params(ctx, d, metric, &cameras[0], sim, row_begin, row_end, (uint8_t*)d_out_rgb8_tiles, nullptr, p);
+    p.cameras = d.d_cameras; p.n_frames = n_frames;
+    CURVIS_CUDA(ctx, cudaMemsetAsync(d.d_counters, 0, sizeof(DeviceCounters), st));
+    CURVIS_CUDA(ctx, cudaEventRecord(d.ev_begin, st));
+    if (row_end > row_begin) {
+        CURVIS_CUDA(ctx, launch_render_f64(p, metric->kind, ctx->tuning, d.sm_count, st));
+        g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    CURVIS_CUDA(ctx, cudaEventRecord(d.ev_end, st));
+    if (stats) {
+        CURVIS_CUDA(ctx, cudaMemcpyAsync(d.h_counters, d.d_counters, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, st));
+        CURVIS_CUDA(ctx, cudaStreamSynchronize(st));
+        std::memset(stats, 0, sizeof *stats);
+        add_counters(*d.h_counters, (uint64_t)(row_end - row_begin) * cameras[0].resolution_width * n_frames, stats);
         float ms = 0.f;
         CURVIS_CUDA(ctx, cudaEventElapsedTime(&ms, d.ev_begin, d.ev_end));
         stats->kernel_ms = ms;

@@ -26,16 +26,26 @@ struct Background {
     double inv_rot[9];       // image orientation inverse, row-major (images.rs:132-142)
 };
 
-struct FrameParams {
-    // metric parameters (metrics.rs:399-401, :431-435)
-    double rho, m, a;
-    // camera (cameras.rs:30-43)
+// Per-frame camera block (cameras.rs:30-43 after Camera::new, plus two per-frame uniforms).
+struct CameraBlock {
     double cam_pos[4];
     double cam_to_world[9];
     // r(l_camera) and sin(theta_camera): per-frame uniforms of new_photon (metrics.rs:329-330),
     // evaluated once on the host with the platform libm like the reference does per ray
     double cam_r, cam_sin_theta;
     double focal_length, sensor_width, sensor_height;
+};
+
+struct FrameParams {
+    // metric parameters (metrics.rs:399-401, :431-435)
+    double rho, m, a;
+    // camera of the frame (n_frames == 1), in the constant bank
+    CameraBlock cam;
+    // batched launch (video): n_frames cameras in device memory, one tile of each frame per launch;
+    // ray index = frame * tile_rays + pixel-in-tile, output tiles frame-major
+    const CameraBlock* cameras;
+    uint32_t n_frames;
+    uint32_t _pad1;
     uint32_t width, height;
     // render_image arguments (systems.rs:309-311)
     uint32_t max_iterations;

@@ -115,24 +115,35 @@ __device__ __forceinline__ void normalize_theta_phi(double& th, double& ph) {
 // ---------------------------------------------------------------- ray generation
 // camera_pixels_x_y_to_photon (systems.rs:531-534): outward_vector_on_camera_space
 // (cameras.rs:150-164), camera_to_world rotation (:169-172), new_photon (metrics.rs:301-334).
-__device__ __forceinline__ void new_photon_for_pixel(const FrameParams& p, uint32_t px, uint32_t py, Ray& q) {
-    const double res_x = (double)p.width, res_y = (double)p.height;
+__device__ __forceinline__ void new_photon_from_camera(const CameraBlock& cam, uint32_t width, uint32_t height,
+                                                       uint32_t px, uint32_t py, Ray& q) {
+    const double res_x = (double)width, res_y = (double)height;
     const double h = 0.5 - ((double)py / res_y);
     const double w = ((double)px / res_x) - 0.5;
-    double vx = p.focal_length * 1.0;
-    double vy = -p.sensor_width * w;
-    double vz = p.sensor_height * h;
+    double vx = cam.focal_length * 1.0;
+    double vy = -cam.sensor_width * w;
+    double vz = cam.sensor_height * h;
     double n = norm3(vx, vy, vz);
     vx = vx / n; vy = vy / n; vz = vz / n;                       // cameras.rs:163
     double dx, dy, dz;
-    mat3_mul(p.cam_to_world, vx, vy, vz, dx, dy, dz);            // cameras.rs:171
+    mat3_mul(cam.cam_to_world, vx, vy, vz, dx, dy, dz);          // cameras.rs:171
     n = norm3(dx, dy, dz);
     dx = dx / n; dy = dy / n; dz = dz / n;                       // metrics.rs:320
-    q.l = p.cam_pos[1]; q.th = p.cam_pos[2]; q.ph = p.cam_pos[3];
+    q.l = cam.cam_pos[1]; q.th = cam.cam_pos[2]; q.ph = cam.cam_pos[3];
     q.pl = dx;                                                   // :328
-    q.pth = dy * p.cam_r;                                        // :329  direction[1] * r(l)
-    q.pph = dz * p.cam_r * p.cam_sin_theta;                      // :330  direction[2] * r(l) * sin(theta)
+    q.pth = dy * cam.cam_r;                                      // :329  direction[1] * r(l)
+    q.pph = dz * cam.cam_r * cam.cam_sin_theta;                  // :330  direction[2] * r(l) * sin(theta)
     q.pph2 = q.pph * q.pph;
+}
+
+// Ray `idx` of a launch: frame = idx / tile_rays (batched launches), pixel = idx % tile_rays.
+__device__ __forceinline__ void new_photon_for_ray(const FrameParams& p, unsigned long long idx, unsigned long long tile_rays, Ray& q) {
+    if (p.n_frames <= 1) {
+        new_photon_from_camera(p.cam, p.width, p.height, (uint32_t)(idx % p.width), p.row_begin + (uint32_t)(idx / p.width), q);
+    } else {
+        const unsigned long long f = idx / tile_rays, r = idx % tile_rays;
+        new_photon_from_camera(p.cameras[f], p.width, p.height, (uint32_t)(r % p.width), p.row_begin + (uint32_t)(r / p.width), q);
+    }
 }
 
 // ---------------------------------------------------------------- one explicit Euler step

@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64(const __grid_constant_
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned long long tile_rays = (unsigned long long)(p.row_end - p.row_begin) * p.width;
+    const unsigned long long launch_rays = tile_rays * (p.n_frames ? p.n_frames : 1u);
 
     Ray q;
     bool live = false;      // this lane is integrating a ray
@@ -76,11 +77,9 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64(const __grid_constant_
                 base = __shfl_sync(kFull, base, leader);
                 if (!live) {
                     const unsigned long long idx = base + (unsigned long long)__popc(idle & lt_mask);
-                    if (idx < tile_rays) {
+                    if (idx < launch_rays) {
                         ray = idx;
-                        const uint32_t px = (uint32_t)(idx % p.width);
-                        const uint32_t py = p.row_begin + (uint32_t)(idx / p.width);
-                        new_photon_for_pixel(p, px, py, q);
+                        new_photon_for_ray(p, idx, tile_rays, q);
                         ray_safe = frame_safe && ray_operands_safe(q);
                         steps = 0;
                         side = 0;
@@ -88,7 +87,7 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64(const __grid_constant_
                         else live = true;
                     }
                 }
-                if (base + (unsigned long long)__popc(idle) >= tile_rays) drained = true;
+                if (base + (unsigned long long)__popc(idle) >= launch_rays) drained = true;
             }
             if (__ballot_sync(kFull, live || pending) == 0u) break;
         }
@@ -134,6 +133,7 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64_lean(const __grid_cons
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned long long tile_rays = (unsigned long long)(p.row_end - p.row_begin) * p.width;
+    const unsigned long long launch_rays = tile_rays * (p.n_frames ? p.n_frames : 1u);
     const double R = p.max_radius;
     // |l| > R needs abs_hi(l) >= hi(R) when R >= 0; for negative or NaN R the gate is open.
     const unsigned gate = (R >= 0.0) ? abs_hi(R) : 0u;
@@ -186,15 +186,15 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64_lean(const __grid_cons
                 base = __shfl_sync(kFull, base, leader);
                 if (state == 0) {
                     const unsigned long long idx = base + (unsigned long long)__popc(idle & lt_mask);
-                    if (idx < tile_rays) {
+                    if (idx < launch_rays) {
                         ray = idx;
-                        new_photon_for_pixel(p, (uint32_t)(idx % p.width), p.row_begin + (uint32_t)(idx / p.width), q);
+                        new_photon_for_ray(p, idx, tile_rays, q);
                         ray_safe = frame_safe && ray_operands_safe(q);
                         remaining = p.max_iterations;
                         state = (remaining == 0) ? 2 : 1;   // the loop of systems.rs:126 may run zero times
                     }
                 }
-                if (base + (unsigned long long)__popc(idle) >= tile_rays) drained = true;
+                if (base + (unsigned long long)__popc(idle) >= launch_rays) drained = true;
             }
             if (__ballot_sync(kFull, state != 0) == 0u) break;
         }
@@ -237,7 +237,7 @@ static cudaError_t launch_persistent(Kernel kernel, int& blocks_per_sm_auto, con
     }
     int blocks_per_sm = blocks_per_sm_auto;
     if (blocks_per_sm_override > 0 && blocks_per_sm_override < blocks_per_sm) blocks_per_sm = blocks_per_sm_override;
-    const unsigned long long tile_rays = (unsigned long long)(p.row_end - p.row_begin) * p.width;
+    const unsigned long long tile_rays = (unsigned long long)(p.row_end - p.row_begin) * p.width * (p.n_frames ? p.n_frames : 1u);
     unsigned long long want = (tile_rays + kBlock - 1) / kBlock;
     unsigned long long cap = (unsigned long long)sm_count * (unsigned long long)blocks_per_sm;
     const unsigned grid = (unsigned)(want < cap ? (want ? want : 1) : cap);
@@ -254,19 +254,7 @@ static cudaError_t launch_lean(const FrameParams& p, int sm_count, int blocks_pe
 template <class Shape, class Trig, bool TUNED>
 static cudaError_t launch_one(const FrameParams& p, int sm_count, int blocks_per_sm_override, cudaStream_t stream) {
     static int blocks_per_sm_auto = 0;  // per instantiation; same for every sm_100 device
-    if (blocks_per_sm_auto == 0) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm_auto, render_rows_f64<Shape, Trig, TUNED>, kBlock, 0);
-        if (e != cudaSuccess) return e;
-        if (blocks_per_sm_auto < 1) blocks_per_sm_auto = 1;
-    }
-    int blocks_per_sm = blocks_per_sm_auto;
-    if (blocks_per_sm_override > 0 && blocks_per_sm_override < blocks_per_sm) blocks_per_sm = blocks_per_sm_override;
-    const unsigned long long tile_rays = (unsigned long long)(p.row_end - p.row_begin) * p.width;
-    unsigned long long want = (tile_rays + kBlock - 1) / kBlock;
-    unsigned long long cap = (unsigned long long)sm_count * (unsigned long long)blocks_per_sm;
-    const unsigned grid = (unsigned)(want < cap ? (want ? want : 1) : cap);
-    render_rows_f64<Shape, Trig, TUNED><<<grid, kBlock, 0, stream>>>(p);
-    return cudaGetLastError();
+    return launch_persistent(render_rows_f64<Shape, Trig, TUNED>, blocks_per_sm_auto, p, sm_count, blocks_per_sm_override, stream);
 }
 
 template <class Shape>

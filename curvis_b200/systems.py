@@ -147,3 +147,20 @@ class RelativisticSystem:
             self.last_stats = stats.as_dict()
             return self.last_stats
         return None
+
+    def render_frames_device(self, cameras, max_iterations: int, max_radius: float, delta: float, row_begin: int, row_end: int,
+                             out_ptr: int, stream_ptr: int = 0, want_stats: bool = False, **options):
+        """Batched video form (curvis_render_frames_device): rows [row_begin,row_end) of one frame
+        per camera in ONE launch; ``out_ptr`` receives len(cameras) tiles, frame-major."""
+        arr = (_abi.CurvisCamera * len(cameras))(*[c.as_c() if hasattr(c, "as_c") else c for c in cameras])
+        sim = self._sim(max_iterations, max_radius, delta, **options)
+        stats = _abi.CurvisStats() if want_stats else None
+        m = self.metric.as_c()
+        _abi.check(self._lib.curvis_render_frames_device(
+            self.context.ptr, C.byref(m), arr, len(cameras), C.byref(sim), int(row_begin), int(row_end),
+            C.c_void_p(out_ptr), C.c_void_p(stream_ptr) if stream_ptr else None,
+            C.byref(stats) if stats is not None else None), self.context.ptr)
+        if stats is not None:
+            self.last_stats = stats.as_dict()
+            return self.last_stats
+        return None

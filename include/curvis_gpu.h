@@ -202,6 +202,16 @@ int curvis_render_rows_device(curvis_ctx* ctx, const curvis_metric* metric,
                               void* d_out_rgb8_rows, void* d_records,
                               void* stream, curvis_stats* stats);
 
+/* Batched form for video (VideoRenderingSystem::render, src/rendering.rs:291-316: one
+ * render per frame after update_camera): rows [row_begin,row_end) of `n_frames` frames —
+ * one camera per frame, same resolution, same metric/sim/backgrounds — in ONE launch over a
+ * single work queue.  Output: n_frames tiles, frame-major ((row_end-row_begin)*W*3 bytes each)
+ * at the device pointer `d_out_rgb8_tiles`.  Asynchronous on `stream` unless `stats` != NULL. */
+int curvis_render_frames_device(curvis_ctx* ctx, const curvis_metric* metric,
+                                const curvis_camera* cameras, uint32_t n_frames, const curvis_sim* sim,
+                                uint32_t row_begin, uint32_t row_end,
+                                void* d_out_rgb8_tiles, void* stream, curvis_stats* stats);
+
 /* ---- measurement helpers ------------------------------------------------------------- */
 
 /* Number of render-kernel launches this process has issued so far (all contexts).  bench.py

@@ -219,3 +219,29 @@ def test_device_resident_tile_on_a_torch_stream(gpu_ctx, oracle):
                                         with_records=False)
     assert (out.cpu().numpy().reshape(20, W, 3) == ref).all() and st["total_steps"] == ref_st["total_steps"]
     assert st["kernel_ms"] > 0
+
+
+def test_batched_frames_equal_single_frames(gpu_ctx, oracle):
+    """curvis_render_frames_device (video batch, one launch) == one curvis_render_rows per camera."""
+    import torch
+    import curvis_b200 as cv
+    from curvis_b200 import scenes
+    W, H = 80, 45
+    bp, bn = scenes.noise_background(256, 128, 8), scenes.noise_background(256, 128, 9)
+    cams = [cv.Camera((0.0, 5.0 + 0.3 * f, 1.4 + 0.05 * f, 0.2 * f), (-1.0, 0.1 * f, 0.0), (0.0, 0.0, 1.0), 15.0, 43.0, W, H) for f in range(4)]
+    sysm = cv.RelativisticSystem(cv.EllisMetric(1.0), cv.SphericalImage(bp), cv.SphericalImage(bn), cams[0], context=gpu_ctx)
+    b, e = 9, 36
+    out = torch.zeros(len(cams) * (e - b) * W * 3, dtype=torch.uint8, device="cuda:0")
+    st = sysm.render_frames_device(cams, 3000, 60.0, 0.05, b, e, out.data_ptr(), torch.cuda.current_stream().cuda_stream, want_stats=True)
+    got = out.cpu().numpy().reshape(len(cams), e - b, W, 3)
+    steps = 0
+    for f, cam in enumerate(cams):
+        sysm.camera = cam
+        single = sysm.render_rows(3000, 60.0, 0.05, b, e)
+        steps += sysm.last_stats["total_steps"]
+        assert (got[f] == single).all(), f
+        ocam = oracle.camera(cam.position(), (-1.0, 0.1 * f, 0.0), (0.0, 0.0, 1.0), 15.0, 43.0, W, H)
+        ref, _, _ = oracle.render_rows(oracle.metric("ellis"), ocam, oracle.sim(3000, 60.0, 0.05), bp, bn, row_begin=b, row_end=e,
+                                       with_records=False)
+        assert (got[f] == ref).all(), f
+    assert st["total_steps"] == steps and st["n_rays"] == len(cams) * (e - b) * W
