@@ -81,8 +81,8 @@ static int validate_frame(curvis_ctx* ctx, const curvis_metric* metric, const cu
         return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "resolution_width and resolution_height must be greater than 0");
     if (row_begin > row_end || row_end > cam->resolution_height)
         return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "row range outside the frame");
-    if (sim->precision != CURVIS_PRECISION_F64)
-        return fail(ctx, CURVIS_ERR_UNSUPPORTED, "only CURVIS_PRECISION_F64 is implemented in this build");
+    if (sim->precision != CURVIS_PRECISION_F64 && sim->precision != CURVIS_PRECISION_F32)
+        return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "unknown precision");
     if (sim->sampling != CURVIS_SAMPLING_NEAREST)
         return fail(ctx, CURVIS_ERR_UNSUPPORTED, "only CURVIS_SAMPLING_NEAREST is implemented in this build");
     if (!ctx->bg_set[0] || !ctx->bg_set[1])
@@ -92,6 +92,13 @@ static int validate_frame(curvis_ctx* ctx, const curvis_metric* metric, const cu
     if (std::fabs(cam->position[1]) > sim->max_radius)
         return fail(ctx, CURVIS_ERR_CAMERA_OUTSIDE_RADIUS, "Photon already beyond the maximum radius. Cannot evaluate escape.");
     return CURVIS_OK;
+}
+
+static cudaError_t launch_render(const FrameParams& p, const curvis_metric* metric, const curvis_sim* sim,
+                                 const LaunchTuning& t, int sm_count, cudaStream_t stream) {
+    g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+    if (sim->precision == CURVIS_PRECISION_F32) return launch_render_f32(p, metric->kind, t, sm_count, stream);
+    return launch_render_f64(p, metric->kind, t, sm_count, stream);
 }
 
 static void fill_camera(const curvis_metric* metric, const curvis_camera* cam, CameraBlock& c) {
@@ -114,6 +121,12 @@ static void fill_params(const curvis_ctx* ctx, const DeviceState& d, const curvi
     p.max_iterations = sim->max_iterations; p.sampling = (uint32_t)sim->sampling;
     p.max_radius = sim->max_radius; p.delta = sim->delta;
     p.row_begin = row_begin; p.row_end = row_end;
+    p.f_rho = (float)metric->rho; p.f_rho2 = (float)(metric->rho * metric->rho);
+    p.f_m = (float)metric->m; p.f_a = (float)metric->a;
+    p.f_xscale = (float)(2.0 / (3.14159265358979323846 * metric->m));
+    p.f_delta = (float)sim->delta;
+    // below this |l| no escape test is needed in the fp32 kernel (4 steps of slack at |p_l| <= ~1.3)
+    p.f_near_radius = (float)(std::fabs(sim->max_radius) - 6.0 * std::fabs(sim->delta) - 1e-3 * std::fabs(sim->max_radius));
     for (int s = 0; s < 2; ++s) {
         p.bg[s].texels = d.bg_texels[s];
         p.bg[s].width = d.bg_w[s]; p.bg[s].height = d.bg_h[s];
@@ -130,10 +143,7 @@ static int enqueue_tile(curvis_ctx* ctx, DeviceState& d, const curvis_metric* me
     fill_params(ctx, d, metric, cam, sim, row_begin, row_end, d_out, d_records, p);
     CURVIS_CUDA(ctx, cudaMemsetAsync(d.d_counters, 0, sizeof(DeviceCounters), stream));
     CURVIS_CUDA(ctx, cudaEventRecord(d.ev_begin, stream));
-    if (row_end > row_begin) {
-        CURVIS_CUDA(ctx, launch_render_f64(p, metric->kind, ctx->tuning, d.sm_count, stream));
-        g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
-    }
+    if (row_end > row_begin) CURVIS_CUDA(ctx, launch_render(p, metric, sim, ctx->tuning, d.sm_count, stream));
     CURVIS_CUDA(ctx, cudaEventRecord(d.ev_end, stream));
     return CURVIS_OK;
 }
@@ -331,10 +341,7 @@ extern "C" int curvis_render_frames_device(curvis_ctx* ctx, const curvis_metric*
     p.cameras = d.d_cameras; p.n_frames = n_frames;
     CURVIS_CUDA(ctx, cudaMemsetAsync(d.d_counters, 0, sizeof(DeviceCounters), st));
     CURVIS_CUDA(ctx, cudaEventRecord(d.ev_begin, st));
-    if (row_end > row_begin) {
-        CURVIS_CUDA(ctx, launch_render_f64(p, metric->kind, ctx->tuning, d.sm_count, st));
-        g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
-    }
+    if (row_end > row_begin) CURVIS_CUDA(ctx, launch_render(p, metric, sim, ctx->tuning, d.sm_count, st));
     CURVIS_CUDA(ctx, cudaEventRecord(d.ev_end, st));
     if (stats) {
         CURVIS_CUDA(ctx, cudaMemcpyAsync(d.h_counters, d.d_counters, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, st));

@@ -17,6 +17,9 @@ struct LaunchTuning {
 // fp64 parity kernel (render_f64.cu, compiled with -fmad=false).
 cudaError_t launch_render_f64(const FrameParams& p, int metric_kind, const LaunchTuning& t, int sm_count, cudaStream_t stream);
 
+// fp32 fast mode, CURVIS_PRECISION_F32 (render_f32.cu) — extension, not the parity path.
+cudaError_t launch_render_f32(const FrameParams& p, int metric_kind, const LaunchTuning& t, int sm_count, cudaStream_t stream);
+
 // Elementwise evaluation of one device math primitive (test hook, curvis_debug_eval).
 cudaError_t launch_debug_eval(int op, const double* a, const double* b, double* out, size_t n, cudaStream_t stream);
 

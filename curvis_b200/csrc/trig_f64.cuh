@@ -13,10 +13,10 @@
 
 namespace curvis {
 
-__device__ __constant__ double kSinPoly[6] = {
+static __device__ __constant__ double kSinPoly[6] = {
     -0.16666666666666663, 0.00833333333333043, -0.00019841269835988552,
     2.7557315710929657e-06, -2.5051051817332214e-08, 1.5912475864762696e-10};
-__device__ __constant__ double kCosPoly[6] = {
+static __device__ __constant__ double kCosPoly[6] = {
     0.041666666666666664, -0.0013888888888887072, 2.4801587298283765e-05,
     -2.755731702664308e-07, 2.0876096187138334e-09, -1.1379094621237813e-11};
 
