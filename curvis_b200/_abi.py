@@ -73,6 +73,19 @@ class CurvisStats(C.Structure):
         return {name: getattr(self, name) for name, _ in self._fields_}
 
 
+class CurvisSamplingSettings(C.Structure):
+    _fields_ = [("alphas_num", C.c_uint32), ("max_iterations_sampling", C.c_uint32),
+                ("threshold_1", C.c_double), ("threshold_2", C.c_double)]
+
+
+class CurvisEfficientInfo(C.Structure):
+    _fields_ = [("table_points", C.c_uint32), ("table_passes", C.c_uint32), ("table_evaluations", C.c_uint64),
+                ("table_steps", C.c_uint64), ("table_ms", C.c_double), ("pixels_ms", C.c_double)]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
 class CurvisRayRecord(C.Structure):
     _fields_ = [
         ("l", C.c_double), ("theta", C.c_double), ("phi", C.c_double),
@@ -93,7 +106,7 @@ EXPORTED_SYMBOLS = (
     "curvis_ctx_device_count", "curvis_orientation", "curvis_camera_init", "curvis_metric_validate",
     "curvis_set_background", "curvis_render_image", "curvis_render_rows", "curvis_render_rows_device",
     "curvis_measure_fma_peak", "curvis_kernel_launch_count", "curvis_ctx_set_option", "curvis_debug_eval",
-    "curvis_render_frames_device",
+    "curvis_render_frames_device", "curvis_render_image_efficient",
 )
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcurvis_b200.so")
@@ -138,6 +151,9 @@ def load_library() -> C.CDLL:
                                               C.c_uint32, C.c_uint32, vp, vp, vp, C.POINTER(CurvisStats)]
     lib.curvis_render_frames_device.argtypes = [vp, C.POINTER(CurvisMetric), C.POINTER(CurvisCamera), C.c_uint32, C.POINTER(CurvisSim),
                                                 C.c_uint32, C.c_uint32, vp, vp, C.POINTER(CurvisStats)]
+    lib.curvis_render_image_efficient.argtypes = [vp, C.POINTER(CurvisMetric), C.POINTER(CurvisCamera), C.POINTER(CurvisSim),
+                                                  C.POINTER(CurvisSamplingSettings), vp, dp, C.POINTER(CurvisStats),
+                                                  C.POINTER(CurvisEfficientInfo)]
     lib.curvis_measure_fma_peak.argtypes = [vp, dp, dp]
     lib.curvis_ctx_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     lib.curvis_debug_eval.argtypes = [vp, C.c_int, dp, dp, dp, C.c_size_t]

@@ -15,6 +15,8 @@
 #include "frame_params.h"
 #include "host_error.h"
 #include "launch.h"
+#include "efficient.h"
+#include "efficient_params.h"
 
 namespace curvis {
 
@@ -468,4 +470,121 @@ extern "C" int curvis_debug_eval(curvis_ctx* ctx, int op, const double* a, const
     if (e != cudaSuccess) rc = cuda_fail(ctx, e, "curvis_debug_eval");
     cudaFree(da); cudaFree(db); cudaFree(dout);
     return rc;
+}
+
+extern "C" int curvis_render_image_efficient(curvis_ctx* ctx, const curvis_metric* metric, const curvis_camera* camera,
+                                             const curvis_sim* sim, const curvis_sampling_settings* sampling,
+                                             uint8_t* out_rgb8, double* dbg, curvis_stats* stats, curvis_efficient_info* info) {
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = validate_frame(ctx, metric, camera, sim, 0, camera ? camera->resolution_height : 0);
+    if (rc != CURVIS_OK) return rc;
+    if (!sampling || !out_rgb8) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "null sampling settings / output buffer");
+    if (sampling->alphas_num < 3) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "alphas_num must be at least 3");
+    if (sim->precision != CURVIS_PRECISION_F64) return fail(ctx, CURVIS_ERR_UNSUPPORTED, "the table-based renderer is fp64 only");
+    DeviceState& d = ctx->devs[0];
+    CURVIS_CUDA(ctx, cudaSetDevice(d.ordinal));
+    const uint32_t W = camera->resolution_width, H = camera->resolution_height;
+
+    // ---- step 3 of the reference (systems.rs:437-486): the escape-angle table
+    curvis_camera eq = *camera;                       // compute_escape_angle starts at (0, l, pi/2, 0), systems.rs:224-227
+    eq.position[0] = 0.0; eq.position[2] = 3.14159265358979323846264338327950288 / 2.0; eq.position[3] = 0.0;
+    double* d_dirs = nullptr; size_t d_dirs_cap = 0;
+    uint64_t launches = 0;
+    int cuda_rc = CURVIS_OK;
+    auto integrate = [&](const double* dirs, size_t n, curvis_ray_record* out) -> int {
+        if (n > d_dirs_cap) {
+            if (d_dirs) cudaFree(d_dirs);
+            d_dirs = nullptr; d_dirs_cap = 0;
+            cudaError_t e = cudaMalloc(&d_dirs, n * 3 * sizeof(double));
+            if (e != cudaSuccess) return cuda_rc = cuda_fail(ctx, e, "cudaMalloc(ray directions)");
+            d_dirs_cap = n;
+        }
+        int r = ensure_capacity(ctx, d, 1, n, false);
+        if (r != CURVIS_OK) return cuda_rc = r;
+        cudaError_t e = cudaMemcpyAsync(d_dirs, dirs, n * 3 * sizeof(double), cudaMemcpyHostToDevice, d.stream);
+        if (e != cudaSuccess) return cuda_rc = cuda_fail(ctx, e, "cudaMemcpyAsync(ray directions)");
+        FrameParams p;
+        eq.resolution_width = (uint32_t)n; eq.resolution_height = 1;
+        fill_params(ctx, d, metric, &eq, sim, 0, 1, nullptr, d.d_records, p);
+        p.ray_dirs = d_dirs;
+        if ((e = cudaMemsetAsync(d.d_counters, 0, sizeof(DeviceCounters), d.stream)) != cudaSuccess ||
+            (e = launch_render(p, metric, sim, ctx->tuning, d.sm_count, d.stream)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(out, d.d_records, n * sizeof(curvis_ray_record), cudaMemcpyDeviceToHost, d.stream)) != cudaSuccess ||
+            (e = cudaStreamSynchronize(d.stream)) != cudaSuccess)
+            return cuda_rc = cuda_fail(ctx, e, "escape-angle table launch");
+        ++launches;
+        return CURVIS_OK;
+    };
+    EscapeTable table;
+    std::string err;
+    rc = build_escape_table(*metric, camera->position[1], sampling->alphas_num, sampling->max_iterations_sampling,
+                            sampling->threshold_1, sampling->threshold_2, integrate, table, err);
+    if (d_dirs) cudaFree(d_dirs);
+    if (rc != CURVIS_OK) return cuda_rc != CURVIS_OK ? cuda_rc : fail(ctx, rc, err);
+    const double table_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+
+    // ---- steps 1, 2, 4, 5 (systems.rs:388-433, :489-523): one thread per pixel
+    EfficientParams ep;
+    std::memset(&ep, 0, sizeof ep);
+    fill_camera(metric, camera, ep.cam);
+    ep.width = W; ep.height = H; ep.row_begin = 0; ep.row_end = H;
+    host_vector3_from_theta_phi(camera->position[2], camera->position[3], ep.cam_pos_bg);
+    const double ex[3] = {1.0, 0.0, 0.0};
+    if (!host_rotation_from_two_vectors(ex, ep.cam_pos_bg, ep.rot_bg))              // systems.rs:409 panics here
+        return fail(ctx, CURVIS_ERR_PARALLEL_VECTORS, "v1 and v2 must not be parallel");
+    const size_t n_pts = table.alphas.size(), n_seg = table.m_e.size();
+    const size_t table_doubles = n_pts + 4 * n_seg;
+    std::vector<double> packed;
+    packed.reserve(table_doubles);
+    packed.insert(packed.end(), table.alphas.begin(), table.alphas.end());
+    packed.insert(packed.end(), table.m_e.begin(), table.m_e.end());
+    packed.insert(packed.end(), table.c_e.begin(), table.c_e.end());
+    packed.insert(packed.end(), table.m_s.begin(), table.m_s.end());
+    packed.insert(packed.end(), table.c_s.begin(), table.c_s.end());
+    double* d_table = nullptr;
+    double* d_dbg = nullptr;
+    const size_t px = (size_t)W * H;
+    auto cleanup = [&]() { if (d_table) cudaFree(d_table); if (d_dbg) cudaFree(d_dbg); };
+    cudaError_t e = cudaMalloc(&d_table, (table_doubles ? table_doubles : 1) * sizeof(double));
+    if (e == cudaSuccess && dbg) e = cudaMalloc(&d_dbg, px * 3 * sizeof(double));
+    if (e != cudaSuccess) { cleanup(); return cuda_fail(ctx, e, "cudaMalloc(table)"); }
+    rc = ensure_capacity(ctx, d, px * 3 + 1, 0, true);
+    if (rc != CURVIS_OK) { cleanup(); return rc; }
+    ep.alphas = d_table; ep.m_e = d_table + n_pts; ep.c_e = ep.m_e + n_seg; ep.m_s = ep.c_e + n_seg; ep.c_s = ep.m_s + n_seg;
+    ep.n_points = (uint32_t)n_pts; ep.n_segments = (uint32_t)n_seg;
+    for (int s = 0; s < 2; ++s) {
+        ep.bg[s].texels = d.bg_texels[s]; ep.bg[s].width = d.bg_w[s]; ep.bg[s].height = d.bg_h[s];
+        std::memcpy(ep.bg[s].inv_rot, ctx->bg_inv_rot[s], sizeof ep.bg[s].inv_rot);
+    }
+    ep.out_rgb8 = d.d_out; ep.dbg = d_dbg; ep.counters = d.d_counters;
+    if ((e = cudaMemcpyAsync(d_table, packed.data(), table_doubles * sizeof(double), cudaMemcpyHostToDevice, d.stream)) != cudaSuccess ||
+        (e = cudaMemsetAsync(d.d_counters, 0, sizeof(DeviceCounters), d.stream)) != cudaSuccess ||
+        (e = cudaEventRecord(d.ev_begin, d.stream)) != cudaSuccess ||
+        (e = launch_efficient_pixels(ep, d.sm_count, d.stream)) != cudaSuccess ||
+        (e = cudaEventRecord(d.ev_end, d.stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(d.h_out, d.d_out, px * 3, cudaMemcpyDeviceToHost, d.stream)) != cudaSuccess ||
+        (dbg && (e = cudaMemcpyAsync(dbg, d_dbg, px * 3 * sizeof(double), cudaMemcpyDeviceToHost, d.stream)) != cudaSuccess) ||
+        (e = cudaMemcpyAsync(d.h_counters, d.d_counters, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, d.stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(d.stream)) != cudaSuccess) {
+        cleanup();
+        return cuda_fail(ctx, e, "per-pixel pass");
+    }
+    g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+    std::memcpy(out_rgb8, d.h_out, px * 3);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, d.ev_begin, d.ev_end);
+    cleanup();
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+        add_counters(*d.h_counters, px, stats);
+        stats->total_steps = table.steps;
+        stats->kernel_ms = ms;
+        stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    if (info) {
+        info->table_points = (uint32_t)n_pts; info->table_passes = table.passes;
+        info->table_evaluations = table.evaluations; info->table_steps = table.steps;
+        info->table_ms = table_ms; info->pixels_ms = ms;
+    }
+    return CURVIS_OK;
 }

@@ -46,6 +46,10 @@ struct FrameParams {
     const CameraBlock* cameras;
     uint32_t n_frames;
     uint32_t _pad1;
+    // explicit-ray launch (the escape-angle table of render_image_efficient): when non-null, ray i
+    // starts at cam.cam_pos with tangent-space direction ray_dirs[3i..3i+2] instead of a camera
+    // pixel; width = number of rays, one row; only `records` is written
+    const double* ray_dirs;
     uint32_t width, height;
     // render_image arguments (systems.rs:309-311)
     uint32_t max_iterations;

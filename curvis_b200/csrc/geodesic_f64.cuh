@@ -115,19 +115,9 @@ __device__ __forceinline__ void normalize_theta_phi(double& th, double& ph) {
 // ---------------------------------------------------------------- ray generation
 // camera_pixels_x_y_to_photon (systems.rs:531-534): outward_vector_on_camera_space
 // (cameras.rs:150-164), camera_to_world rotation (:169-172), new_photon (metrics.rs:301-334).
-__device__ __forceinline__ void new_photon_from_camera(const CameraBlock& cam, uint32_t width, uint32_t height,
-                                                       uint32_t px, uint32_t py, Ray& q) {
-    const double res_x = (double)width, res_y = (double)height;
-    const double h = 0.5 - ((double)py / res_y);
-    const double w = ((double)px / res_x) - 0.5;
-    double vx = cam.focal_length * 1.0;
-    double vy = -cam.sensor_width * w;
-    double vz = cam.sensor_height * h;
-    double n = norm3(vx, vy, vz);
-    vx = vx / n; vy = vy / n; vz = vz / n;                       // cameras.rs:163
-    double dx, dy, dz;
-    mat3_mul(cam.cam_to_world, vx, vy, vz, dx, dy, dz);          // cameras.rs:171
-    n = norm3(dx, dy, dz);
+// Metric::new_photon (metrics.rs:301-334) at the camera position for a tangent-space direction.
+__device__ __forceinline__ void new_photon_from_direction(const CameraBlock& cam, double dx, double dy, double dz, Ray& q) {
+    const double n = norm3(dx, dy, dz);
     dx = dx / n; dy = dy / n; dz = dz / n;                       // metrics.rs:320
     q.l = cam.cam_pos[1]; q.th = cam.cam_pos[2]; q.ph = cam.cam_pos[3];
     q.pl = dx;                                                   // :328
@@ -136,9 +126,33 @@ __device__ __forceinline__ void new_photon_from_camera(const CameraBlock& cam, u
     q.pph2 = q.pph * q.pph;
 }
 
+// Camera::outward_vector_on_world_space_from_x_y (cameras.rs:150-172): unit vector in camera
+// space, rotated to the tangent space at the camera (NOT re-normalised).
+__device__ __forceinline__ void outward_vector_on_world_space(const CameraBlock& cam, uint32_t width, uint32_t height,
+                                                              uint32_t px, uint32_t py, double& dx, double& dy, double& dz) {
+    const double res_x = (double)width, res_y = (double)height;
+    const double h = 0.5 - ((double)py / res_y);
+    const double w = ((double)px / res_x) - 0.5;
+    double vx = cam.focal_length * 1.0;
+    double vy = -cam.sensor_width * w;
+    double vz = cam.sensor_height * h;
+    const double n = norm3(vx, vy, vz);
+    vx = vx / n; vy = vy / n; vz = vz / n;                       // cameras.rs:163
+    mat3_mul(cam.cam_to_world, vx, vy, vz, dx, dy, dz);          // cameras.rs:171
+}
+
+__device__ __forceinline__ void new_photon_from_camera(const CameraBlock& cam, uint32_t width, uint32_t height,
+                                                       uint32_t px, uint32_t py, Ray& q) {
+    double dx, dy, dz;
+    outward_vector_on_world_space(cam, width, height, px, py, dx, dy, dz);
+    new_photon_from_direction(cam, dx, dy, dz, q);
+}
+
 // Ray `idx` of a launch: frame = idx / tile_rays (batched launches), pixel = idx % tile_rays.
 __device__ __forceinline__ void new_photon_for_ray(const FrameParams& p, unsigned long long idx, unsigned long long tile_rays, Ray& q) {
-    if (p.n_frames <= 1) {
+    if (p.ray_dirs) {
+        new_photon_from_direction(p.cam, p.ray_dirs[3 * idx], p.ray_dirs[3 * idx + 1], p.ray_dirs[3 * idx + 2], q);
+    } else if (p.n_frames <= 1) {
         new_photon_from_camera(p.cam, p.width, p.height, (uint32_t)(idx % p.width), p.row_begin + (uint32_t)(idx / p.width), q);
     } else {
         const unsigned long long f = idx / tile_rays, r = idx % tile_rays;
@@ -269,6 +283,9 @@ __device__ __forceinline__ void euler_step_lean(const FrameParams& p, Ray& q, bo
 // SphericalImage::get_pixel_from_vector3 (images.rs:171-174 -> :151-167 -> algebra.rs:128-134
 // -> images.rs:115-121).  Returns true when the reference's get_pixel would have indexed out
 // of bounds (images.rs:107-111 panic); the index is clamped instead.
+__device__ __forceinline__ bool texel_from_direction(const Background& bg, double dx, double dy, double dz,
+                                                     uint32_t& tx, uint32_t& ty);
+
 template <class Shape, class Trig>
 __device__ __forceinline__ bool escaped_texel(const FrameParams& p, const Ray& q, const Background& bg,
                                               uint32_t& tx, uint32_t& ty) {
@@ -279,6 +296,12 @@ __device__ __forceinline__ bool escaped_texel(const FrameParams& p, const Ray& q
     const double v2 = q.pth * (1.0 / r2);
     const double v3 = q.pph * (1.0 / (r2 * (s * s)));
     const double dx = v1, dy = v2 * r, dz = v3 * r;           // metrics.rs:345-347
+    return texel_from_direction(bg, dx, dy, dz, tx, ty);
+}
+
+// SphericalImage::get_pixel_from_vector3 (images.rs:171-174): texel index of a direction.
+__device__ __forceinline__ bool texel_from_direction(const Background& bg, double dx, double dy, double dz,
+                                                     uint32_t& tx, uint32_t& ty) {
     double wx, wy, wz;
     mat3_mul(bg.inv_rot, dx, dy, dz, wx, wy, wz);             // images.rs:139-141
     const double rn = norm3(wx, wy, wz);

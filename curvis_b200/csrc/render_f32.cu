@@ -150,18 +150,18 @@ __global__ void __launch_bounds__(kBlock32) render_rows_f32(const __grid_constan
             const uint32_t steps = p.max_iterations - remaining;
             const int side = (q.l > R) ? 1 : ((q.l < -R) ? -1 : 0);
             uint32_t rgba = 0, tx = 0, ty = 0;
-            if (side != 0) {
-                const Background& bg = p.bg[side > 0 ? 0 : 1];
-                if (escaped_texel<Shape64, TrigFast>(p, q, bg, tx, ty)) ++acc_clamped;
-                rgba = __ldg(bg.texels + (size_t)ty * bg.width + tx);
-                if (side > 0) ++acc_pos; else ++acc_neg;
-            } else {
-                ++acc_none;
+            if (side > 0) ++acc_pos; else if (side < 0) ++acc_neg; else ++acc_none;   // none: black, systems.rs:556-558
+            if (p.out_rgb8) {
+                if (side != 0) {
+                    const Background& bg = p.bg[side > 0 ? 0 : 1];
+                    if (escaped_texel<Shape64, TrigFast>(p, q, bg, tx, ty)) ++acc_clamped;
+                    rgba = __ldg(bg.texels + (size_t)ty * bg.width + tx);
+                }
+                uint8_t* o = p.out_rgb8 + ray * 3ull;  // put_pixel on ImageRgb8 drops alpha (systems.rs:324)
+                o[0] = (uint8_t)(rgba & 0xffu);
+                o[1] = (uint8_t)((rgba >> 8) & 0xffu);
+                o[2] = (uint8_t)((rgba >> 16) & 0xffu);
             }
-            uint8_t* o = p.out_rgb8 + ray * 3ull;
-            o[0] = (uint8_t)(rgba & 0xffu);
-            o[1] = (uint8_t)((rgba >> 8) & 0xffu);
-            o[2] = (uint8_t)((rgba >> 16) & 0xffu);
             if (p.records) {
                 curvis_ray_record rec;
                 rec.l = q.l; rec.theta = q.th; rec.phi = q.ph;

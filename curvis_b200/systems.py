@@ -164,3 +164,25 @@ class RelativisticSystem:
             self.last_stats = stats.as_dict()
             return self.last_stats
         return None
+
+    def render_image_efficient(self, max_iterations_propagation: int, max_radius: float, delta: float, alpha_nums: int,
+                               max_iterations_sampling: int, sampling_convergence_threshold_1: float,
+                               sampling_convergence_threshold_2: float, debug: bool = False):
+        """``render_image_efficient`` (src/systems.rs:333-527), same argument order: the
+        table-based renderer the ``curvis`` binary uses.  Returns uint8 (H, W, 3); with
+        ``debug`` also a float64 (H, W, 3) array of (alpha, escape angle, escape space)."""
+        cam = self.camera.as_c()
+        out = np.empty((cam.resolution_height, cam.resolution_width, 3), dtype=np.uint8)
+        dbg = np.empty((cam.resolution_height, cam.resolution_width, 3), dtype=np.float64) if debug else None
+        sim = self._sim(max_iterations_propagation, max_radius, delta)
+        smp = _abi.CurvisSamplingSettings(alphas_num=int(alpha_nums), max_iterations_sampling=int(max_iterations_sampling),
+                                          threshold_1=float(sampling_convergence_threshold_1),
+                                          threshold_2=float(sampling_convergence_threshold_2))
+        stats, info = _abi.CurvisStats(), _abi.CurvisEfficientInfo()
+        m = self.metric.as_c()
+        _abi.check(self._lib.curvis_render_image_efficient(
+            self.context.ptr, C.byref(m), C.byref(cam), C.byref(sim), C.byref(smp), out.ctypes.data_as(C.c_void_p),
+            dbg.ctypes.data_as(C.POINTER(C.c_double)) if dbg is not None else None, C.byref(stats), C.byref(info)), self.context.ptr)
+        self.last_stats = stats.as_dict()
+        self.last_efficient_info = info.as_dict()
+        return (out, dbg) if debug else out

@@ -212,6 +212,35 @@ int curvis_render_frames_device(curvis_ctx* ctx, const curvis_metric* metric,
                                 uint32_t row_begin, uint32_t row_end,
                                 void* d_out_rgb8_tiles, void* stream, curvis_stats* stats);
 
+/* ---- the table-based renderer (what `curvis image` / `curvis video` run) -------------------
+ * RelativisticSystem::render_image_efficient (src/systems.rs:333-527): an adaptive sampler
+ * (src/sampling.rs) tabulates alpha -> (escape angle, escape space) from a few hundred
+ * equatorial photon integrations, then every pixel interpolates the table and rotates the
+ * camera-position direction.  Arguments mirror the reference's (systems.rs:333-342); the
+ * photon integrations and the per-pixel pass run on the context's first device. */
+typedef struct curvis_sampling_settings {
+    uint32_t alphas_num;              /* systems.rs:338  (settings key sampling_initial_nums)          */
+    uint32_t max_iterations_sampling; /* systems.rs:339  (main.rs:46-47 passes sampling_initial_nums)  */
+    double threshold_1;               /* systems.rs:340  sampling_convergence_threshold_1               */
+    double threshold_2;               /* systems.rs:341  sampling_convergence_threshold_2               */
+} curvis_sampling_settings;
+
+typedef struct curvis_efficient_info {
+    uint32_t table_points;       /* points the sampler kept                              */
+    uint32_t table_passes;       /* refinement passes = device launches after the first  */
+    uint64_t table_evaluations;  /* photons integrated                                   */
+    uint64_t table_steps;        /* Euler steps of those photons                         */
+    double table_ms;             /* host wall time of the sampler (launches included)    */
+    double pixels_ms;            /* device time of the per-pixel pass                    */
+} curvis_efficient_info;
+
+/* `dbg` (nullable, host, 3 doubles per pixel): alpha, interpolated escape angle, escape space.
+ * stats->total_steps counts the table's Euler steps; n_positive/negative/not_escaped classify
+ * PIXELS (not_escaped = black, including the reference's seam artefact, README.md:108). */
+int curvis_render_image_efficient(curvis_ctx* ctx, const curvis_metric* metric, const curvis_camera* camera,
+                                  const curvis_sim* sim, const curvis_sampling_settings* sampling,
+                                  uint8_t* out_rgb8, double* dbg, curvis_stats* stats, curvis_efficient_info* info);
+
 /* ---- measurement helpers ------------------------------------------------------------- */
 
 /* Number of render-kernel launches this process has issued so far (all contexts).  bench.py

@@ -455,3 +455,277 @@ int oracle_metric_validate(const curvis_metric* g) {
     default: return CURVIS_ERR_INVALID_ARGUMENT;
     }
 }
+
+
+/* =====================================================================================
+ * "Next" row f1: RelativisticSystem::render_image_efficient,
+ * src/systems.rs:333-527 — what `curvis image` / `curvis video` actually run — with its
+ * helpers compute_escape_angle (:203-261), escaped_photon_to_world_direction (:144-187),
+ * sampling::doubly_sample_function (src/sampling.rs:46-245) and interp::interp_slice
+ * (interp 1.0.3, Cargo.lock:474-475; not under /root/reference: restated from its published
+ * behaviour — per-segment slope m = dy/dx (0 when dx == 0), intercept c = y - x*m, segment index
+ * = index of the last x strictly below xp (0 if none) clamped to len-2, value m*xp + c, so it
+ * extrapolates linearly beyond both ends).
+ * PARITY UNPINNED: the reference holds no test or fixture for any of these.
+ *
+ * nalgebra 0.33.0 pieces restated here: Rotation3::rotation_between (axis = a^ x b^, identity
+ * when |axis| <= f64::EPSILON and a^.b^ >= 0, None -> the reference's unwrap panics when
+ * antiparallel), Rotation3::from_axis_angle (Rodrigues matrix; identity when angle == 0),
+ * Unit::new_normalize (v / |v|, no zero check).
+ * ===================================================================================== */
+
+/* Rotation3::from_axis_angle(axis (unit), angle) */
+static void rot_from_axis_angle(const double u[3], double angle, double m[9]) {
+    if (!(angle != 0.0)) { /* simd_ne(angle, 0) false -> identity (NaN != 0 is true and falls through) */
+        m[0] = 1; m[1] = 0; m[2] = 0; m[3] = 0; m[4] = 1; m[5] = 0; m[6] = 0; m[7] = 0; m[8] = 1;
+        return;
+    }
+    const double ux = u[0], uy = u[1], uz = u[2];
+    const double sqx = ux * ux, sqy = uy * uy, sqz = uz * uz;
+    const double sn = sin(angle), cs = cos(angle);
+    const double omc = 1.0 - cs;
+    m[0] = sqx + (1.0 - sqx) * cs;
+    m[1] = ux * uy * omc - uz * sn;
+    m[2] = ux * uz * omc + uy * sn;
+    m[3] = ux * uy * omc + uz * sn;
+    m[4] = sqy + (1.0 - sqy) * cs;
+    m[5] = uy * uz * omc - ux * sn;
+    m[6] = ux * uz * omc - uy * sn;
+    m[7] = uy * uz * omc + ux * sn;
+    m[8] = sqz + (1.0 - sqz) * cs;
+}
+
+static double v3_dot(const double a[3], const double b[3]) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+
+/* algebra::rotation_from_two_vectors, src/algebra.rs:92-101.  Returns 1 where the reference
+ * panics (:95-97 parallel, or rotation_between -> None on antiparallel inputs). */
+int oracle_rotation_from_two_vectors(const double v1[3], const double v2[3], double m[9]) {
+    double c[3];
+    v3_cross(v1, v2, c);
+    if (v3_norm(c) == 0.0) return 1;
+    /* Rotation3::rotation_between(v1, v2) */
+    double na[3], nb[3];
+    const double n1 = v3_norm(v1), n2 = v3_norm(v2);
+    if (n1 > 0.0 && n2 > 0.0) { /* try_normalize(0) */
+        for (int i = 0; i < 3; ++i) { na[i] = v1[i] / n1; nb[i] = v2[i] / n2; }
+        v3_cross(na, nb, c);
+        const double cn = v3_norm(c);
+        if (cn > 2.220446049250313e-16) { /* Unit::try_new(c, default_epsilon) */
+            double axis[3] = {c[0] / cn, c[1] / cn, c[2] / cn};
+            rot_from_axis_angle(axis, acos(v3_dot(na, nb)) * 1.0, m);
+            return 0;
+        }
+        if (v3_dot(na, nb) < 0.0) return 1; /* None.unwrap() */
+    }
+    m[0] = 1; m[1] = 0; m[2] = 0; m[3] = 0; m[4] = 1; m[5] = 0; m[6] = 0; m[7] = 0; m[8] = 1;
+    return 0;
+}
+
+/* rotation_matrix_from_theta_phi, src/algebra.rs:82-90 (tests only in the reference: the KAT at
+ * :237-257 pins the handedness of the axis-angle matrix above).  Rotation3::new(v) =
+ * from_scaled_axis: axis = v/|v|, angle = |v|, identity for the zero vector. */
+void oracle_rotation_matrix_from_theta_phi(double theta, double phi, double m[9]) {
+    oracle_normalize_theta_phi(theta, phi, &theta, &phi);
+    double r1[9], r2[9];
+    const double a1 = theta - ORACLE_PI / 2.0;
+    if (fabs(a1) > 0.0) { const double ax[3] = {0.0 / fabs(a1), a1 / fabs(a1), 0.0 / fabs(a1)}; rot_from_axis_angle(ax, fabs(a1), r1); }
+    else { const double z[3] = {0, 0, 0}; rot_from_axis_angle(z, 0.0, r1); }
+    if (fabs(phi) > 0.0) { const double ax[3] = {0.0 / fabs(phi), 0.0 / fabs(phi), phi / fabs(phi)}; rot_from_axis_angle(ax, fabs(phi), r2); }
+    else { const double z[3] = {0, 0, 0}; rot_from_axis_angle(z, 0.0, r2); }
+    m3_mul_m(r2, r1, m);
+}
+
+/* compute_escape_angle, src/systems.rs:203-261 via escaped_photon_to_world_direction :144-187.
+ * Returns the side (+1/-1/0 NotEscaped); -2/-3 where the reference panics. */
+int oracle_compute_escape_angle(const curvis_metric* g, double l, double alpha, double delta,
+                                uint32_t max_iterations, double max_radius, double* angle, uint32_t* steps_out) {
+    const double direction_world[3] = {cos(alpha), 0.0, sin(alpha)};              /* :221 */
+    const double position[4] = {0.0, l, ORACLE_PI / 2.0, 0.0};                    /* :224-227 */
+    oracle_photon ph;
+    uint32_t steps = 0;
+    oracle_new_photon(g, position, direction_world, &ph);                         /* :230 */
+    const int side = oracle_escape_photon(g, &ph, delta, max_iterations, max_radius, &steps);   /* :233 */
+    if (steps_out) *steps_out = steps;
+    if (side == -2) return -2;
+    if (side == 0) { *angle = NAN; return 0; }                                    /* :238-244 */
+    double tangent[3], world_position[3], rot[9], wd[3];
+    oracle_relativistic_vector_to_direction(g, ph.p, ph.x, tangent);              /* :170-171 */
+    oracle_vector3_from_theta_phi(ph.x[2], ph.x[3], world_position);              /* :176 */
+    const double ex[3] = {1.0, 0.0, 0.0};
+    if (oracle_rotation_from_two_vectors(ex, world_position, rot)) return -3;     /* :178-181 */
+    m3_mul_v(rot, tangent, wd);                                                   /* :183 */
+    const double n = v3_norm(wd);                                                 /* :246 normalize_mut */
+    wd[0] = wd[0] / n; wd[1] = wd[1] / n; wd[2] = wd[2] / n;
+    const double vx = (wd[0] * 1.0 + wd[1] * 0.0) + wd[2] * 0.0;                  /* :248 dot with x */
+    const double vy = (wd[0] * 0.0 + wd[1] * 1.0) + wd[2] * 0.0;                  /* :249 dot with y */
+    *angle = (vy >= 0.0) ? acos(vx) : 2.0 * ORACLE_PI - acos(vx);                 /* :251 */
+    return side;
+}
+
+/* ---- sampling.rs ---- */
+typedef struct bipoint { double a, e, s; } bipoint;
+typedef struct bivec { bipoint* v; size_t n, cap; } bivec;
+static void bv_push(bivec* b, bipoint p) {
+    if (b->n == b->cap) { b->cap = b->cap ? b->cap * 2 : 256; b->v = (bipoint*)realloc(b->v, b->cap * sizeof(bipoint)); }
+    b->v[b->n++] = p;
+}
+static void bv_clean(bivec* b) { /* clean_bipoints, sampling.rs:21-32 */
+    size_t k = 0;
+    for (size_t i = 0; i < b->n; ++i)
+        if (isfinite(b->v[i].a) && isfinite(b->v[i].e) && isfinite(b->v[i].s)) b->v[k++] = b->v[i];
+    b->n = k;
+}
+
+typedef struct escape_fn { const curvis_metric* g; double l, delta, max_radius; uint32_t max_iterations; uint64_t evals, steps; int panicked; } escape_fn;
+static bipoint eval_escape(escape_fn* f, double alpha) { /* the closure at systems.rs:472-485 */
+    double angle = NAN; uint32_t steps = 0;
+    const int side = oracle_compute_escape_angle(f->g, f->l, alpha, f->delta, f->max_iterations, f->max_radius, &angle, &steps);
+    f->evals += 1; f->steps += steps;
+    bipoint p; p.a = alpha;
+    if (side == 1) { p.e = angle; p.s = 1.0; }
+    else if (side == -1) { p.e = angle; p.s = -1.0; }
+    else { if (side < 0) f->panicked = 1; p.e = NAN; p.s = NAN; }
+    return p;
+}
+
+/* evaluate_convergence_scores, sampling.rs:198-245 */
+static void convergence_scores(const bipoint* b1, const bipoint* b2, const bipoint* b3, double* s1, double* s2) {
+    *s1 = fabs(((b1->a * b2->e + b2->a * b3->e) + b3->a * b1->e) - ((b1->e * b2->a + b2->e * b3->a) + b3->e * b1->a));
+    *s2 = fabs(((b1->a * b2->s + b2->a * b3->s) + b3->a * b1->s) - ((b1->s * b2->a + b2->s * b3->a) + b3->s * b1->a));
+}
+
+/* doubly_sample_function, sampling.rs:46-124 (+ compute_uniform_range :129-140, evaluate_denser_bipoints
+ * :144-195).  Outputs are malloc'd (free with oracle_free).  Returns 0, or 1 where the reference panics. */
+int oracle_sample_escape_angles(const curvis_metric* g, double l, double delta, uint32_t max_iterations, double max_radius,
+                                double a_min, double a_max, uint32_t initial_points_number, uint32_t max_sampling_iterations,
+                                double thr1, double thr2, double** alphas, double** escapes, double** signs, uint32_t* n_out,
+                                uint64_t* n_evals, uint64_t* n_steps, uint32_t* n_passes) {
+    escape_fn f = {g, l, delta, max_radius, max_iterations, 0, 0, 0};
+    bivec cur = {NULL, 0, 0};
+    const double step = (a_max - a_min) / ((double)(initial_points_number - 1));   /* :135 */
+    for (uint32_t i = 0; i < initial_points_number; ++i) bv_push(&cur, eval_escape(&f, a_min + (double)i * step));
+    bv_clean(&cur);
+    uint32_t iteration = 0, passes = 0;
+    int rc = 0;
+    while (iteration < max_sampling_iterations) {                                  /* :90 */
+        const size_t previous = cur.n;
+        bivec nxt = {NULL, 0, 0};
+        bv_clean(&cur);
+        if (cur.n < 3) { rc = 1; free(nxt.v); break; }                             /* :158-160 panic */
+        size_t i = 0;
+        while (i < cur.n - 2) {                                                    /* :163 */
+            const bipoint *b1 = &cur.v[i], *b2 = &cur.v[(i + 1) % cur.n], *b3 = &cur.v[(i + 2) % cur.n];
+            double s1, s2;
+            convergence_scores(b1, b2, b3, &s1, &s2);
+            if (!(s1 > thr1 || s2 > thr2)) { bv_push(&nxt, *b1); i += 1; continue; }
+            const double na1 = (b1->a + b2->a) / 2.0, na2 = (b2->a + b3->a) / 2.0;
+            const bipoint n1 = eval_escape(&f, na1), n2 = eval_escape(&f, na2);
+            bv_push(&nxt, *b1); bv_push(&nxt, n1); bv_push(&nxt, *b2); bv_push(&nxt, n2);
+            i += 2;
+        }
+        bv_clean(&nxt);
+        free(cur.v); cur = nxt; passes += 1;
+        if (cur.n < previous) break;                                               /* :97-102 */
+        if (cur.n == previous) break;                                              /* :105-107 */
+        iteration += 1;
+    }
+    *alphas = (double*)malloc((cur.n ? cur.n : 1) * sizeof(double));
+    *escapes = (double*)malloc((cur.n ? cur.n : 1) * sizeof(double));
+    *signs = (double*)malloc((cur.n ? cur.n : 1) * sizeof(double));
+    for (size_t i = 0; i < cur.n; ++i) { (*alphas)[i] = cur.v[i].a; (*escapes)[i] = cur.v[i].e; (*signs)[i] = cur.v[i].s; }
+    *n_out = (uint32_t)cur.n;
+    if (n_evals) *n_evals = f.evals;
+    if (n_steps) *n_steps = f.steps;
+    if (n_passes) *n_passes = passes;
+    free(cur.v);
+    return rc || f.panicked;
+}
+
+void oracle_free(void* p) { free(p); }
+
+/* interp::interp_slice(x, y, xp) of interp 1.0.3 */
+void oracle_interp_slice(const double* x, const double* y, uint32_t n, const double* xp, size_t n_xp, double* out) {
+    if (n == 0) { for (size_t k = 0; k < n_xp; ++k) out[k] = 0.0; return; }
+    if (n == 1) { for (size_t k = 0; k < n_xp; ++k) out[k] = y[0]; return; }
+    double* m = (double*)malloc((n - 1) * sizeof(double));
+    double* c = (double*)malloc((n - 1) * sizeof(double));
+    for (uint32_t i = 0; i + 1 < n; ++i) {
+        const double dx = x[i + 1] - x[i], dy = y[i + 1] - y[i];
+        m[i] = (dx == 0.0) ? 0.0 : dy / dx;
+        c[i] = y[i] - x[i] * m[i];
+    }
+    for (size_t k = 0; k < n_xp; ++k) {
+        size_t cnt = 0;                      /* prev_index: last i with x[i] < xp over the leading run */
+        while (cnt < n && x[cnt] < xp[k]) ++cnt;
+        size_t i = cnt ? cnt - 1 : 0;
+        if (i > (size_t)n - 2) i = (size_t)n - 2;
+        out[k] = m[i] * xp[k] + c[i];
+    }
+    free(m); free(c);
+}
+
+/* render_image_efficient, src/systems.rs:333-527.  `rows` restricts the output to rows
+ * [row_begin,row_end) (every pixel is independent after the table is built).  Optional debug
+ * outputs per pixel: alpha, interpolated escape angle and space.  Returns a curvis_status. */
+int oracle_render_image_efficient(const curvis_metric* g, const curvis_camera* cam, const curvis_sim* sim,
+                                  uint32_t alpha_nums, uint32_t max_iterations_sampling, double thr1, double thr2,
+                                  const uint8_t* bg_pos, uint32_t pos_w, uint32_t pos_h, const double* pos_inv_rot,
+                                  const uint8_t* bg_neg, uint32_t neg_w, uint32_t neg_h, const double* neg_inv_rot,
+                                  uint32_t row_begin, uint32_t row_end, uint8_t* out_rgb8,
+                                  double* dbg_alpha, double* dbg_angle, double* dbg_space,
+                                  uint32_t* table_points, uint64_t* table_evals, uint64_t* table_steps) {
+    static const double ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    oracle_background pos = {bg_pos, pos_w, pos_h, {0}}, neg = {bg_neg, neg_w, neg_h, {0}};
+    memcpy(pos.inv_rot, pos_inv_rot ? pos_inv_rot : ident, sizeof ident);
+    memcpy(neg.inv_rot, neg_inv_rot ? neg_inv_rot : ident, sizeof ident);
+    const uint32_t W = cam->resolution_width;
+    double cam_pos_bg[3], rot_bg[9];
+    oracle_vector3_from_theta_phi(cam->position[2], cam->position[3], cam_pos_bg);            /* :392-396 */
+    const double ex[3] = {1.0, 0.0, 0.0};
+    if (oracle_rotation_from_two_vectors(ex, cam_pos_bg, rot_bg)) return CURVIS_ERR_PARALLEL_VECTORS;   /* :411 */
+    /* Step 3: the table (:437-486) */
+    double *ta = NULL, *te = NULL, *ts = NULL; uint32_t tn = 0;
+    if (oracle_sample_escape_angles(g, cam->position[1], sim->delta, sim->max_iterations, sim->max_radius,
+                                    -0.1 * ORACLE_PI, 1.1 * ORACLE_PI, alpha_nums, max_iterations_sampling, thr1, thr2,
+                                    &ta, &te, &ts, &tn, table_evals, table_steps, NULL)) {
+        free(ta); free(te); free(ts);
+        return CURVIS_ERR_CAMERA_OUTSIDE_RADIUS;
+    }
+    if (table_points) *table_points = tn;
+    const size_t n_rows = row_end > row_begin ? row_end - row_begin : 0;
+    for (uint32_t j = row_begin; j < row_end; ++j) {
+        for (uint32_t i = 0; i < W; ++i) {
+            double tangent[3], bgdir[3], axis[3];
+            oracle_outward_vector_on_world_space(cam, i, j, tangent);                          /* :408 */
+            m3_mul_v(rot_bg, tangent, bgdir);                                                  /* :409 */
+            v3_cross(cam_pos_bg, bgdir, axis);                                                 /* :412-414 */
+            const double alpha = acos((tangent[0] * 1.0 + tangent[1] * 0.0) + tangent[2] * 0.0);   /* :428-431 */
+            double angle, space;
+            oracle_interp_slice(ta, te, tn, &alpha, 1, &angle);                                /* :489 */
+            oracle_interp_slice(ta, ts, tn, &alpha, 1, &space);                                /* :491 */
+            const double an = v3_norm(axis);                                                   /* Unit::new_normalize */
+            const double unit[3] = {axis[0] / an, axis[1] / an, axis[2] / an};
+            double rot[9], fin[3];
+            rot_from_axis_angle(unit, angle, rot);                                             /* :502 */
+            m3_mul_v(rot, cam_pos_bg, fin);                                                    /* :503 */
+            uint8_t rgb[3] = {0, 0, 0};
+            const oracle_background* bg = (space == 1.0) ? &pos : ((space == -1.0) ? &neg : NULL);   /* :514-518 */
+            if (bg) {
+                uint32_t tx, ty;
+                oracle_texel_from_vector3(bg->inv_rot, fin, bg->w, bg->h, &tx, &ty, NULL, NULL);
+                if (tx >= bg->w) tx = bg->w - 1;
+                if (ty >= bg->h) ty = bg->h - 1;
+                const uint8_t* t = bg->rgba8 + ((size_t)ty * bg->w + tx) * 4;
+                rgb[0] = t[0]; rgb[1] = t[1]; rgb[2] = t[2];
+            }
+            const size_t o = (size_t)(j - row_begin) * W + i;
+            if (out_rgb8) { out_rgb8[o * 3] = rgb[0]; out_rgb8[o * 3 + 1] = rgb[1]; out_rgb8[o * 3 + 2] = rgb[2]; }
+            if (dbg_alpha) dbg_alpha[o] = alpha;
+            if (dbg_angle) dbg_angle[o] = angle;
+            if (dbg_space) dbg_space[o] = space;
+        }
+    }
+    (void)n_rows;
+    free(ta); free(te); free(ts);
+    return CURVIS_OK;
+}

@@ -61,6 +61,25 @@ def lib() -> C.CDLL:
         L.oracle_trajectory.argtypes = [C.POINTER(_abi.CurvisMetric), dp, dp, C.c_double, C.c_uint32, dp]
         L.oracle_trajectory.restype = None
         L.oracle_metric_validate.argtypes = [C.POINTER(_abi.CurvisMetric)]
+        L.oracle_rotation_from_two_vectors.argtypes = [dp, dp, dp]
+        L.oracle_rotation_matrix_from_theta_phi.argtypes = [C.c_double, C.c_double, dp]
+        L.oracle_rotation_matrix_from_theta_phi.restype = None
+        L.oracle_compute_escape_angle.argtypes = [C.POINTER(_abi.CurvisMetric), C.c_double, C.c_double, C.c_double, C.c_uint32, C.c_double,
+                                                  dp, C.POINTER(C.c_uint32)]
+        pdp = C.POINTER(dp)
+        L.oracle_sample_escape_angles.argtypes = [C.POINTER(_abi.CurvisMetric), C.c_double, C.c_double, C.c_uint32, C.c_double,
+                                                  C.c_double, C.c_double, C.c_uint32, C.c_uint32, C.c_double, C.c_double,
+                                                  pdp, pdp, pdp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                                  C.POINTER(C.c_uint32)]
+        L.oracle_free.argtypes = [vp]
+        L.oracle_free.restype = None
+        L.oracle_interp_slice.argtypes = [dp, dp, C.c_uint32, dp, C.c_size_t, dp]
+        L.oracle_interp_slice.restype = None
+        L.oracle_render_image_efficient.argtypes = [
+            C.POINTER(_abi.CurvisMetric), C.POINTER(_abi.CurvisCamera), C.POINTER(_abi.CurvisSim),
+            C.c_uint32, C.c_uint32, C.c_double, C.c_double,
+            vp, C.c_uint32, C.c_uint32, dp, vp, C.c_uint32, C.c_uint32, dp,
+            C.c_uint32, C.c_uint32, vp, dp, dp, dp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
 
@@ -188,3 +207,76 @@ def render_rows(g, cam, s, bg_pos, bg_neg, row_begin=0, row_end=None, row_stride
     if rc:
         raise RuntimeError(f"oracle_render_rows status {rc}")
     return out, rec, st.as_dict()
+
+
+def rotation_from_two_vectors(v1, v2):
+    m = (C.c_double * 9)()
+    if lib().oracle_rotation_from_two_vectors(_d(v1, 3), _d(v2, 3), m):
+        raise ValueError("v1 and v2 must not be parallel")
+    return np.array(m).reshape(3, 3)
+
+
+def rotation_matrix_from_theta_phi(theta, phi):
+    m = (C.c_double * 9)()
+    lib().oracle_rotation_matrix_from_theta_phi(theta, phi, m)
+    return np.array(m).reshape(3, 3)
+
+
+def compute_escape_angle(g, l, alpha, delta, max_iterations, max_radius):
+    """(side, angle, steps): side +1/-1, 0 NotEscaped (angle NaN)."""
+    a, st = C.c_double(), C.c_uint32()
+    side = lib().oracle_compute_escape_angle(C.byref(g), l, alpha, delta, max_iterations, max_radius, C.byref(a), C.byref(st))
+    return side, a.value, st.value
+
+
+def sample_escape_angles(g, l, delta, max_iterations, max_radius, a_min=-0.1 * np.pi, a_max=1.1 * np.pi, initial_points=100,
+                         max_sampling_iterations=100, thr1=1e-5, thr2=1e-5):
+    """doubly_sample_function over compute_escape_angle: (alphas, escapes, signs, info)."""
+    dp = C.POINTER(C.c_double)
+    pa, pe, ps = dp(), dp(), dp()
+    n, ev, stp, passes = C.c_uint32(), C.c_uint64(), C.c_uint64(), C.c_uint32()
+    rc = lib().oracle_sample_escape_angles(C.byref(g), l, delta, max_iterations, max_radius, a_min, a_max, initial_points,
+                                           max_sampling_iterations, thr1, thr2, C.byref(pa), C.byref(pe), C.byref(ps), C.byref(n),
+                                           C.byref(ev), C.byref(stp), C.byref(passes))
+    out = tuple(np.ctypeslib.as_array(p, shape=(max(n.value, 1),))[: n.value].copy() for p in (pa, pe, ps))
+    for p in (pa, pe, ps):
+        lib().oracle_free(p)
+    if rc:
+        raise RuntimeError("the reference would panic while sampling")
+    return out + (dict(points=n.value, evaluations=ev.value, steps=stp.value, passes=passes.value),)
+
+
+def interp_slice(x, y, xp):
+    x = np.ascontiguousarray(x, dtype=np.float64); y = np.ascontiguousarray(y, dtype=np.float64)
+    xp = np.ascontiguousarray(xp, dtype=np.float64)
+    out = np.empty_like(xp)
+    dp = C.POINTER(C.c_double)
+    lib().oracle_interp_slice(x.ctypes.data_as(dp), y.ctypes.data_as(dp), min(len(x), len(y)), xp.ctypes.data_as(dp), xp.size,
+                              out.ctypes.data_as(dp))
+    return out
+
+
+def render_image_efficient(g, cam, s, bg_pos, bg_neg, alpha_nums=100, max_iterations_sampling=100, thr1=1e-5, thr2=1e-5,
+                           row_begin=0, row_end=None, pos_inv_rot=None, neg_inv_rot=None, debug=False):
+    """render_image_efficient restated: (rgb8 (rows, W, 3), info[, alpha, angle, space])."""
+    W, H = cam.resolution_width, cam.resolution_height
+    if row_end is None:
+        row_end = H
+    rows = max(0, row_end - row_begin)
+    bg_pos = np.ascontiguousarray(bg_pos, dtype=np.uint8); bg_neg = np.ascontiguousarray(bg_neg, dtype=np.uint8)
+    out = np.zeros((rows, W, 3), dtype=np.uint8)
+    dp = C.POINTER(C.c_double)
+    dbg = [np.zeros((rows, W)) for _ in range(3)] if debug else [None] * 3
+    pi = np.ascontiguousarray(pos_inv_rot, dtype=np.float64).ctypes.data_as(dp) if pos_inv_rot is not None else None
+    ni = np.ascontiguousarray(neg_inv_rot, dtype=np.float64).ctypes.data_as(dp) if neg_inv_rot is not None else None
+    tp, te, ts = C.c_uint32(), C.c_uint64(), C.c_uint64()
+    rc = lib().oracle_render_image_efficient(
+        C.byref(g), C.byref(cam), C.byref(s), alpha_nums, max_iterations_sampling, thr1, thr2,
+        bg_pos.ctypes.data_as(C.c_void_p), bg_pos.shape[1], bg_pos.shape[0], pi,
+        bg_neg.ctypes.data_as(C.c_void_p), bg_neg.shape[1], bg_neg.shape[0], ni,
+        row_begin, row_end, out.ctypes.data_as(C.c_void_p),
+        *[d.ctypes.data_as(dp) if d is not None else None for d in dbg], C.byref(tp), C.byref(te), C.byref(ts))
+    if rc:
+        raise RuntimeError(f"oracle_render_image_efficient status {rc}")
+    info = dict(table_points=tp.value, table_evaluations=te.value, table_steps=ts.value)
+    return (out, info, *dbg) if debug else (out, info)
