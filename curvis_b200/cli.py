@@ -1,0 +1,96 @@
+"""``python -m curvis_b200 image|video|custom`` — the command tree of reference src/cli.rs:35-122
+and src/main.rs:135-235: positionals ``background_image_1 background_image_2 [output_folder]``,
+options ``-i/--image-settings``, ``-v/--video-settings``, ``-m/--metric-settings``,
+``-c/--camera-settings``, ``-s/--simulation-settings`` (TOML files; missing -> defaults).
+Extensions (absent from the reference): ``--renderer``, ``--devices``, ``--frames``,
+``--corrected-interpolation``."""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+
+from . import settings as S
+from .rendering import (ImageRenderingSettings, ImageRenderingSystem, VideoRenderingSettings, VideoRenderingSystem,
+                        instantiate_metric)
+from .systems import Context
+
+
+def _common(sub):
+    sub.add_argument("background_image_1")
+    sub.add_argument("background_image_2")
+    sub.add_argument("output_folder", nargs="?", default=None)
+    sub.add_argument("-m", "--metric-settings", dest="metric_settings")
+    sub.add_argument("-c", "--camera-settings", dest="camera_settings")
+    sub.add_argument("-s", "--simulation-settings", dest="simulation_settings")
+    sub.add_argument("--renderer", choices=["efficient", "per_pixel"], default="efficient",
+                     help="efficient = render_image_efficient (the reference binary's choice); per_pixel = render_image")
+    sub.add_argument("--devices", default=None, help="comma-separated CUDA ordinals (default: all visible)")
+
+
+def get_cli() -> argparse.ArgumentParser:
+    ap = argparse.ArgumentParser(prog="curvis", description="Ray tracing of wormhole space-times on B200 GPUs")
+    subs = ap.add_subparsers(dest="command")
+    img = subs.add_parser("image")
+    _common(img)
+    img.add_argument("-i", "--image-settings", dest="image_settings")
+    vid = subs.add_parser("video")
+    _common(vid)
+    vid.add_argument("-v", "--video-settings", dest="video_settings")
+    vid.add_argument("--frames", type=int, default=None, help="render only the first N frames")
+    vid.add_argument("--corrected-interpolation", action="store_true")
+    subs.add_parser("custom")
+    return ap
+
+
+def _existing(path: str) -> str:
+    if not os.path.exists(path):
+        raise S.SettingsError(f"File {path!r} not found.")        # cli.rs:156-161
+    return path
+
+
+def _load(cls, path):
+    return cls.default() if path is None else cls.from_toml_file(_existing(path))
+
+
+def _output_folder(path):
+    if path is None:
+        return os.getcwd()                                         # cli.rs:196-203
+    _existing(path)
+    if not os.path.isdir(path):
+        raise S.SettingsError(f"{path!r} is not a folder.")
+    return path
+
+
+def main(argv=None) -> int:
+    args = get_cli().parse_args(argv)
+    try:
+        if args.command is None:
+            print("Subcommand not found", file=sys.stderr)
+            return 1
+        if args.command == "custom":
+            raise S.SettingsError("The custom subcommand is a placeholder in the reference (src/custom.rs:4-8).")
+        bg1, bg2 = _existing(args.background_image_1), _existing(args.background_image_2)
+        out = _output_folder(args.output_folder)
+        metric = instantiate_metric(S.metric_settings_from_file(args.metric_settings))
+        camera, simulation = _load(S.CameraSettings, args.camera_settings), _load(S.SimulationSettings, args.simulation_settings)
+        ctx = Context([int(d) for d in args.devices.split(",")] if args.devices else None)
+        if args.command == "image":
+            image = _load(S.ImageSettings, args.image_settings)
+            settings = ImageRenderingSettings.from_settings(bg1, bg2, out, image, camera, simulation)
+            path = ImageRenderingSystem(metric, settings, context=ctx, renderer=args.renderer).render()
+            print(f"Saved {path}")
+        else:
+            video = _load(S.VideoSettings, args.video_settings)
+            settings = VideoRenderingSettings.from_settings(bg1, bg2, out, video, camera, simulation)
+            system = VideoRenderingSystem(metric, settings, context=ctx, renderer=args.renderer,
+                                          corrected_interpolation=args.corrected_interpolation)
+            print(f"Frames in {system.render(max_frames=args.frames)}")
+        return 0
+    except Exception as e:                                          # main.rs:219-227: print the error, exit 1
+        print(f"Error: {e}", file=sys.stderr)
+        return 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

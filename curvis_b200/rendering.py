@@ -1,0 +1,200 @@
+"""Host driver: the image and video rendering systems of reference src/rendering.rs, on top of
+the GPU renderers.  Like the reference, ``render()`` calls the table-based renderer
+(``render_image_efficient``, src/rendering.rs:97 and :299) by default; ``renderer="per_pixel"``
+selects the per-pixel integrator ``render_image`` (src/systems.rs:307-330) instead.  File names
+follow the reference: ``<out>/<image_name>.png`` and ``<out>/tmp/frame_{index}.png``."""
+from __future__ import annotations
+
+import os
+import shutil
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+
+from .cameras import Camera
+from .images import SphericalImage
+from .interpolation import Interpolator
+from .metrics import EllisMetric, InterstellarMetric
+from .settings import (CameraSettings, EllisMetricSettings, ImageSettings, InterstellarMetricSettings, SimulationSettings,
+                       VideoSettings)
+from .systems import Context, RelativisticSystem
+
+
+def load_image(path: str) -> np.ndarray:
+    """images.rs:7-11 + what DynamicImage::get_pixel yields (:107-111): RGBA8 texels."""
+    from PIL import Image
+    with Image.open(path) as im:
+        return np.ascontiguousarray(np.asarray(im.convert("RGBA"), dtype=np.uint8))
+
+
+def save_image(rgb8: np.ndarray, path: str) -> None:
+    """images.rs:13-15: the frame is an RGB8 image saved as PNG."""
+    from PIL import Image
+    Image.fromarray(rgb8, mode="RGB").save(path)
+
+
+def load_image_as_spherical_image(path: str, forward=None, up=None) -> SphericalImage:   # images.rs:186-193
+    return SphericalImage(load_image(path), forward, up)
+
+
+def instantiate_metric(metric_settings):                         # main.rs:114-132
+    if isinstance(metric_settings, InterstellarMetricSettings):
+        return InterstellarMetric(metric_settings.m, metric_settings.a, metric_settings.rho)
+    return EllisMetric(metric_settings.rho)
+
+
+@dataclass
+class ImageRenderingSettings:                                    # rendering.rs:148-167, filled like main.rs:54-111
+    resolution_x: int
+    resolution_y: int
+    camera_diagonal: float
+    camera_focal_length: float
+    camera_position: tuple
+    camera_forward: tuple
+    camera_up: tuple
+    path_to_background_image_1: str
+    path_to_background_image_2: str
+    path_to_output_folder: str
+    output_image_name: str
+    escape_radius: float
+    max_iterations_propagation: int
+    ray_integration_step: float
+    alphas_num: int
+    max_iterations_sampling: int
+    sampling_convergence_threshold_1: float
+    sampling_convergence_threshold_2: float
+
+    @classmethod
+    def from_settings(cls, bg1, bg2, out, image: ImageSettings, camera: CameraSettings, simulation: SimulationSettings):
+        for s in (image, camera, simulation):
+            s.normalize()
+            s.validate()
+        return cls(camera.resolution_x, camera.resolution_y, camera.diagonal, camera.focal_length,
+                   (image.t, image.l, image.theta, image.phi), (image.forward_x, image.forward_y, image.forward_z),
+                   (image.up_x, image.up_y, image.up_z), bg1, bg2, out, image.image_name,
+                   simulation.escape_radius, simulation.ray_integration_max_itarations, simulation.ray_integration_step,
+                   simulation.sampling_initial_nums,
+                   simulation.sampling_initial_nums,      # main.rs:106-107 feeds sampling_initial_nums into BOTH fields
+                   simulation.sampling_convergence_threshold_1, simulation.sampling_convergence_threshold_2)
+
+
+@dataclass
+class VideoRenderingSettings:                                    # rendering.rs:355-374, filled like main.rs:14-51
+    frame_rate: float
+    resolution_x: int
+    resolution_y: int
+    camera_diagonal: float
+    camera_focal_length: float
+    filepath_to_camera_path: str
+    filepath_to_background_image_1: str
+    filepath_to_background_image_2: str
+    filepath_to_output_folder: str
+    output_video_name: str
+    escape_radius: float
+    max_iterations_propagation: int
+    ray_integration_step: float
+    alphas_num: int
+    max_iterations_sampling: int
+    sampling_convergence_threshold_1: float
+    sampling_convergence_threshold_2: float
+
+    @classmethod
+    def from_settings(cls, bg1, bg2, out, video: VideoSettings, camera: CameraSettings, simulation: SimulationSettings):
+        for s in (video, camera, simulation):
+            s.normalize()
+            s.validate()
+        return cls(video.frame_rate, camera.resolution_x, camera.resolution_y, camera.diagonal, camera.focal_length,
+                   video.filepath_to_camera_path, bg1, bg2, out, video.video_name,
+                   simulation.escape_radius, simulation.ray_integration_max_itarations, simulation.ray_integration_step,
+                   simulation.sampling_initial_nums, simulation.sampling_initial_nums,
+                   simulation.sampling_convergence_threshold_1, simulation.sampling_convergence_threshold_2)
+
+
+class ImageRenderingSystem:
+    """rendering.rs:20-117."""
+
+    def __init__(self, metric, settings: ImageRenderingSettings, context: Optional[Context] = None, renderer: str = "efficient"):
+        self.image_rendering_settings = settings
+        self.renderer = renderer
+        image_1 = load_image_as_spherical_image(settings.path_to_background_image_1)
+        image_2 = load_image_as_spherical_image(settings.path_to_background_image_2)
+        camera = Camera(settings.camera_position, settings.camera_forward, settings.camera_up, settings.camera_focal_length,
+                        settings.camera_diagonal, settings.resolution_x, settings.resolution_y)
+        self.relativistic_system = RelativisticSystem(metric, image_1, image_2, camera, context=context)
+
+    def render_frame(self) -> np.ndarray:
+        s = self.image_rendering_settings
+        if self.renderer == "per_pixel":
+            return self.relativistic_system.render_image(s.max_iterations_propagation, s.escape_radius, s.ray_integration_step)
+        return self.relativistic_system.render_image_efficient(
+            s.max_iterations_propagation, s.escape_radius, s.ray_integration_step, s.alphas_num, s.max_iterations_sampling,
+            s.sampling_convergence_threshold_1, s.sampling_convergence_threshold_2)
+
+    def render(self) -> str:
+        s = self.image_rendering_settings
+        if not os.path.exists(s.path_to_output_folder):            # rendering.rs:89-95
+            os.mkdir(s.path_to_output_folder)
+        frame = self.render_frame()
+        path = os.path.join(s.path_to_output_folder, s.output_image_name) + ".png"   # :108
+        save_image(frame, path)
+        return path
+
+
+class VideoRenderingSystem:
+    """rendering.rs:170-327."""
+
+    def __init__(self, metric, settings: VideoRenderingSettings, context: Optional[Context] = None, renderer: str = "efficient",
+                 corrected_interpolation: bool = False):
+        self.video_rendering_settings = settings
+        self.renderer = renderer
+        self.interpolator = Interpolator.from_file(settings.filepath_to_camera_path, corrected=corrected_interpolation)
+        image_1 = load_image_as_spherical_image(settings.filepath_to_background_image_1)
+        image_2 = load_image_as_spherical_image(settings.filepath_to_background_image_2)
+        t0 = self.interpolator.min_time()
+        camera = Camera(self.interpolator.camera_position(t0), self.interpolator.camera_forward(t0), self.interpolator.camera_up(t0),
+                        settings.camera_focal_length, settings.camera_diagonal, settings.resolution_x, settings.resolution_y)
+        self.relativistic_system = RelativisticSystem(metric, image_1, image_2, camera, context=context)
+
+    def times_of_frames(self) -> List[float]:                      # rendering.rs:224-238
+        min_time, max_time = self.interpolator.min_time(), self.interpolator.max_time()
+        delta_time = 1.0 / self.video_rendering_settings.frame_rate
+        times, t = [], min_time
+        while t < max_time:
+            times.append(t)
+            t += delta_time
+        return times
+
+    def update_camera(self, t: float) -> None:                     # rendering.rs:242-253
+        cam = self.relativistic_system.camera
+        cam.update_position(self.interpolator.camera_position(t))
+        cam.update_orientation(self.interpolator.camera_forward(t), self.interpolator.camera_up(t))
+
+    def render_frame(self) -> np.ndarray:
+        s = self.video_rendering_settings
+        if self.renderer == "per_pixel":
+            return self.relativistic_system.render_image(s.max_iterations_propagation, s.escape_radius, s.ray_integration_step)
+        return self.relativistic_system.render_image_efficient(
+            s.max_iterations_propagation, s.escape_radius, s.ray_integration_step, s.alphas_num, s.max_iterations_sampling,
+            s.sampling_convergence_threshold_1,
+            s.sampling_convergence_threshold_1)                     # rendering.rs:305-306 passes threshold_1 twice
+
+    def render(self, max_frames: Optional[int] = None, verbose: bool = True) -> str:
+        s = self.video_rendering_settings
+        times = self.times_of_frames()
+        if max_frames is not None:
+            times = times[:max_frames]
+        if not os.path.exists(s.filepath_to_output_folder):        # rendering.rs:266-274
+            os.mkdir(s.filepath_to_output_folder)
+        tmp_folder = os.path.join(s.filepath_to_output_folder, "tmp")
+        if os.path.exists(tmp_folder):                              # :277-282
+            shutil.rmtree(tmp_folder)
+        os.mkdir(tmp_folder)
+        if verbose:
+            print(f"Rendering {len(times)} frames...")
+        for index, t in enumerate(times):
+            if verbose:
+                print(f"Rendering frame {index + 1}/{len(times)}...")
+            self.update_camera(t)                                   # may raise on the last frame, like the reference panics
+            save_image(self.render_frame(), os.path.join(tmp_folder, f"frame_{index}.png"))
+        return tmp_folder
