@@ -245,3 +245,26 @@ def test_batched_frames_equal_single_frames(gpu_ctx, oracle):
                                        with_records=False)
         assert (got[f] == ref).all(), f
     assert st["total_steps"] == steps and st["n_rays"] == len(cams) * (e - b) * W
+
+
+def test_in_process_multi_device_frame(oracle):
+    """curvis_render_image on a context with every visible device: the frame is row-tiled over
+    them inside one call and equals the single-device frame (needs >= 2 GPUs to mean anything)."""
+    import torch
+    import curvis_b200 as cv
+    from curvis_b200 import scenes
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    W, H = 320, 181                                           # 181 rows: ragged split
+    bp, bn = scenes.noise_background(512, 256, 31), scenes.noise_background(512, 256, 32)
+    cam = cv.Camera(scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP, 15.0, 43.0, W, H)
+    multi = cv.RelativisticSystem(cv.EllisMetric(1.0), cv.SphericalImage(bp), cv.SphericalImage(bn), cam, context=cv.Context())
+    assert multi.context.device_count() == n
+    single = cv.RelativisticSystem(cv.EllisMetric(1.0), cv.SphericalImage(bp), cv.SphericalImage(bn), cam, context=cv.Context([n - 1]))
+    a = multi.render_image(40000, 100.0, 0.05)
+    b = single.render_image(40000, 100.0, 0.05)
+    assert (a == b).all() and multi.last_stats["total_steps"] == single.last_stats["total_steps"]
+    ref, _, _ = oracle.render_rows(oracle.metric("ellis"), oracle.camera(scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD,
+                                   scenes.DEFAULT_UP, 15.0, 43.0, W, H), oracle.sim(40000, 100.0, 0.05), bp, bn, threads=os.cpu_count() or 1)
+    assert (a == ref).all()
