@@ -106,7 +106,7 @@ EXPORTED_SYMBOLS = (
     "curvis_ctx_device_count", "curvis_orientation", "curvis_camera_init", "curvis_metric_validate",
     "curvis_set_background", "curvis_render_image", "curvis_render_rows", "curvis_render_rows_device",
     "curvis_measure_fma_peak", "curvis_kernel_launch_count", "curvis_ctx_set_option", "curvis_debug_eval",
-    "curvis_render_frames_device", "curvis_render_image_efficient",
+    "curvis_render_frames_device", "curvis_render_image_efficient", "curvis_render_rows_rgba32f", "curvis_debug_bilinear",
 )
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcurvis_b200.so")
@@ -154,6 +154,9 @@ def load_library() -> C.CDLL:
     lib.curvis_render_image_efficient.argtypes = [vp, C.POINTER(CurvisMetric), C.POINTER(CurvisCamera), C.POINTER(CurvisSim),
                                                   C.POINTER(CurvisSamplingSettings), vp, dp, C.POINTER(CurvisStats),
                                                   C.POINTER(CurvisEfficientInfo)]
+    lib.curvis_render_rows_rgba32f.argtypes = [vp, C.POINTER(CurvisMetric), C.POINTER(CurvisCamera), C.POINTER(CurvisSim),
+                                               C.c_uint32, C.c_uint32, vp, C.POINTER(CurvisStats)]
+    lib.curvis_debug_bilinear.argtypes = [vp, C.c_int, dp, dp, vp, C.c_size_t]
     lib.curvis_measure_fma_peak.argtypes = [vp, dp, dp]
     lib.curvis_ctx_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     lib.curvis_debug_eval.argtypes = [vp, C.c_int, dp, dp, dp, C.c_size_t]

@@ -32,6 +32,7 @@ struct DeviceState {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     // resident scene
     uint32_t* bg_texels[2] = {nullptr, nullptr};
+    float4* bg_texels_f4[2] = {nullptr, nullptr};   // staged on first CURVIS_SAMPLING_BILINEAR use
     uint32_t bg_w[2] = {0, 0}, bg_h[2] = {0, 0};
     // per-launch scratch
     DeviceCounters* d_counters = nullptr;
@@ -85,8 +86,8 @@ static int validate_frame(curvis_ctx* ctx, const curvis_metric* metric, const cu
         return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "row range outside the frame");
     if (sim->precision != CURVIS_PRECISION_F64 && sim->precision != CURVIS_PRECISION_F32)
         return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "unknown precision");
-    if (sim->sampling != CURVIS_SAMPLING_NEAREST)
-        return fail(ctx, CURVIS_ERR_UNSUPPORTED, "only CURVIS_SAMPLING_NEAREST is implemented in this build");
+    if (sim->sampling != CURVIS_SAMPLING_NEAREST && sim->sampling != CURVIS_SAMPLING_BILINEAR)
+        return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "unknown sampling mode");
     if (!ctx->bg_set[0] || !ctx->bg_set[1])
         return fail(ctx, CURVIS_ERR_NO_BACKGROUND, "both backgrounds must be set before rendering");
     // escape_photon panics when the photon starts beyond the radius (systems.rs:122-124);
@@ -131,18 +132,35 @@ static void fill_params(const curvis_ctx* ctx, const DeviceState& d, const curvi
     p.f_near_radius = (float)(std::fabs(sim->max_radius) - 6.0 * std::fabs(sim->delta) - 1e-3 * std::fabs(sim->max_radius));
     for (int s = 0; s < 2; ++s) {
         p.bg[s].texels = d.bg_texels[s];
+        p.bg[s].texels_f4 = d.bg_texels_f4[s];
         p.bg[s].width = d.bg_w[s]; p.bg[s].height = d.bg_h[s];
         std::memcpy(p.bg[s].inv_rot, ctx->bg_inv_rot[s], sizeof p.bg[s].inv_rot);
     }
-    p.out_rgb8 = d_out; p.records = d_records; p.counters = d.d_counters;
+    p.out_rgb8 = d_out; p.out_rgba32f = nullptr; p.records = d_records; p.counters = d.d_counters;
+}
+
+// CURVIS_SAMPLING_BILINEAR reads the backgrounds as float4 (one 128-bit load per tap): staged once
+// per background and device, on first use, by a conversion kernel (stream-ordered on `stream`).
+static int ensure_float_backgrounds(curvis_ctx* ctx, DeviceState& d, const curvis_sim* sim, cudaStream_t stream) {
+    if (sim->sampling != CURVIS_SAMPLING_BILINEAR) return CURVIS_OK;
+    for (int s = 0; s < 2; ++s) {
+        if (d.bg_texels_f4[s]) continue;
+        const size_t n = (size_t)d.bg_w[s] * d.bg_h[s];
+        CURVIS_CUDA(ctx, cudaMalloc(&d.bg_texels_f4[s], n * sizeof(float4)));
+        CURVIS_CUDA(ctx, launch_texels_to_float4(d.bg_texels[s], d.bg_texels_f4[s], n, stream));
+    }
+    return CURVIS_OK;
 }
 
 // Enqueue one tile on `stream` of device d: zero counters, kernel bracketed by events.
 static int enqueue_tile(curvis_ctx* ctx, DeviceState& d, const curvis_metric* metric, const curvis_camera* cam,
                         const curvis_sim* sim, uint32_t row_begin, uint32_t row_end, uint8_t* d_out,
-                        curvis_ray_record* d_records, cudaStream_t stream) {
+                        curvis_ray_record* d_records, cudaStream_t stream, float4* d_out_f32 = nullptr) {
+    int frc = ensure_float_backgrounds(ctx, d, sim, stream);
+    if (frc != CURVIS_OK) return frc;
     FrameParams p;
     fill_params(ctx, d, metric, cam, sim, row_begin, row_end, d_out, d_records, p);
+    p.out_rgba32f = d_out_f32;
     CURVIS_CUDA(ctx, cudaMemsetAsync(d.d_counters, 0, sizeof(DeviceCounters), stream));
     CURVIS_CUDA(ctx, cudaEventRecord(d.ev_begin, stream));
     if (row_end > row_begin) CURVIS_CUDA(ctx, launch_render(p, metric, sim, ctx->tuning, d.sm_count, stream));
@@ -182,6 +200,7 @@ static void release_device(DeviceState& d) {
     if (d.ordinal < 0) return;
     cudaSetDevice(d.ordinal);
     for (int s = 0; s < 2; ++s) if (d.bg_texels[s]) cudaFree(d.bg_texels[s]);
+    for (int s = 0; s < 2; ++s) if (d.bg_texels_f4[s]) cudaFree(d.bg_texels_f4[s]);
     if (d.d_counters) cudaFree(d.d_counters);
     if (d.h_counters) cudaFreeHost(d.h_counters);
     if (d.d_out) cudaFree(d.d_out);
@@ -269,6 +288,7 @@ extern "C" int curvis_set_background(curvis_ctx* ctx, int side, const uint8_t* r
     for (auto& d : ctx->devs) {
         CURVIS_CUDA(ctx, cudaSetDevice(d.ordinal));
         if (d.bg_texels[s]) { cudaFree(d.bg_texels[s]); d.bg_texels[s] = nullptr; }
+        if (d.bg_texels_f4[s]) { cudaFree(d.bg_texels_f4[s]); d.bg_texels_f4[s] = nullptr; }
         CURVIS_CUDA(ctx, cudaMalloc(&d.bg_texels[s], bytes));
         CURVIS_CUDA(ctx, cudaMemcpyAsync(d.bg_texels[s], rgba8, bytes, cudaMemcpyHostToDevice, d.stream));
         d.bg_w[s] = width; d.bg_h[s] = height;
@@ -333,6 +353,10 @@ extern "C" int curvis_render_frames_device(curvis_ctx* ctx, const curvis_metric*
         d.d_cameras = nullptr; d.d_cameras_cap = 0;
         CURVIS_CUDA(ctx, cudaMalloc(&d.d_cameras, (size_t)n_frames * sizeof(CameraBlock)));
         d.d_cameras_cap = n_frames;
+    }
+    {
+        int frc = ensure_float_backgrounds(ctx, d, sim, st);
+        if (frc != CURVIS_OK) return frc;
     }
     std::vector<CameraBlock> blocks(n_frames);
     for (uint32_t f = 0; f < n_frames; ++f) fill_camera(metric, &cameras[f], blocks[f]);
@@ -586,5 +610,63 @@ extern "C" int curvis_render_image_efficient(curvis_ctx* ctx, const curvis_metri
         info->table_evaluations = table.evaluations; info->table_steps = table.steps;
         info->table_ms = table_ms; info->pixels_ms = ms;
     }
+    return CURVIS_OK;
+}
+
+extern "C" int curvis_render_rows_rgba32f(curvis_ctx* ctx, const curvis_metric* metric, const curvis_camera* camera,
+                                          const curvis_sim* sim, uint32_t row_begin, uint32_t row_end,
+                                          float* out_rgba32f_rows, curvis_stats* stats) {
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = validate_frame(ctx, metric, camera, sim, row_begin, row_end);
+    if (rc != CURVIS_OK) return rc;
+    const size_t n_rays = (size_t)(row_end - row_begin) * camera->resolution_width;
+    if (n_rays && !out_rgba32f_rows) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "null output buffer");
+    DeviceState& d = ctx->devs[0];
+    CURVIS_CUDA(ctx, cudaSetDevice(d.ordinal));
+    float4* d_f32 = nullptr;
+    CURVIS_CUDA(ctx, cudaMalloc(&d_f32, (n_rays ? n_rays : 1) * sizeof(float4)));
+    rc = enqueue_tile(ctx, d, metric, camera, sim, row_begin, row_end, nullptr, nullptr, d.stream, d_f32);
+    cudaError_t e = cudaSuccess;
+    if (rc == CURVIS_OK && n_rays) e = cudaMemcpyAsync(out_rgba32f_rows, d_f32, n_rays * sizeof(float4), cudaMemcpyDeviceToHost, d.stream);
+    if (rc == CURVIS_OK && e == cudaSuccess) e = cudaMemcpyAsync(d.h_counters, d.d_counters, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, d.stream);
+    if (rc == CURVIS_OK && e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+    cudaFree(d_f32);
+    if (rc != CURVIS_OK) return rc;
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "curvis_render_rows_rgba32f");
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+        add_counters(*d.h_counters, n_rays, stats);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, d.ev_begin, d.ev_end);
+        stats->kernel_ms = ms;
+        stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return CURVIS_OK;
+}
+
+extern "C" int curvis_debug_bilinear(curvis_ctx* ctx, int side, const double* fx, const double* fy, float* out_rgba32f, size_t n) {
+    if (!ctx || !fx || !fy || !out_rgba32f || side == 0) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "null argument");
+    const int s = side > 0 ? 0 : 1;
+    if (!ctx->bg_set[s]) return fail(ctx, CURVIS_ERR_NO_BACKGROUND, "background not set");
+    DeviceState& d = ctx->devs[0];
+    CURVIS_CUDA(ctx, cudaSetDevice(d.ordinal));
+    curvis_sim bil; std::memset(&bil, 0, sizeof bil); bil.sampling = CURVIS_SAMPLING_BILINEAR;
+    int rc = ensure_float_backgrounds(ctx, d, &bil, d.stream);
+    if (rc != CURVIS_OK) return rc;
+    double *dx = nullptr, *dy = nullptr; float4* dout = nullptr;
+    cudaError_t e = cudaSuccess;
+    const size_t nb = (n ? n : 1);
+    Background bg;
+    bg.texels = d.bg_texels[s]; bg.texels_f4 = d.bg_texels_f4[s]; bg.width = d.bg_w[s]; bg.height = d.bg_h[s];
+    std::memcpy(bg.inv_rot, ctx->bg_inv_rot[s], sizeof bg.inv_rot);
+    if ((e = cudaMalloc(&dx, nb * 8)) == cudaSuccess && (e = cudaMalloc(&dy, nb * 8)) == cudaSuccess &&
+        (e = cudaMalloc(&dout, nb * sizeof(float4))) == cudaSuccess &&
+        (e = cudaMemcpyAsync(dx, fx, n * 8, cudaMemcpyHostToDevice, d.stream)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(dy, fy, n * 8, cudaMemcpyHostToDevice, d.stream)) == cudaSuccess &&
+        (e = launch_debug_bilinear(bg, dx, dy, dout, n, d.stream)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(out_rgba32f, dout, n * sizeof(float4), cudaMemcpyDeviceToHost, d.stream)) == cudaSuccess)
+        e = cudaStreamSynchronize(d.stream);
+    cudaFree(dx); cudaFree(dy); cudaFree(dout);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "curvis_debug_bilinear");
     return CURVIS_OK;
 }

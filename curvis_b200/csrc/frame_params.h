@@ -4,6 +4,7 @@
 // kernel parameter space (constant bank, uniform loads) with no per-launch H2D copy.
 #pragma once
 #include <stdint.h>
+#include <vector_types.h>
 #include "../../include/curvis_gpu.h"
 
 namespace curvis {
@@ -22,6 +23,7 @@ struct DeviceCounters {
 
 struct Background {
     const uint32_t* texels;  // RGBA8 packed little-endian (R in the low byte), row-major
+    const float4* texels_f4; // the same texels as float4 (0..255), staged on first bilinear use
     uint32_t width, height;
     double inv_rot[9];       // image orientation inverse, row-major (images.rs:132-142)
 };
@@ -66,6 +68,7 @@ struct FrameParams {
     Background bg[2];
     // outputs: RGB8 rows of the tile (packed, row-major), optional per-ray records, counters
     uint8_t* out_rgb8;
+    float4* out_rgba32f;     // optional: the unrounded colour of every ray (RGBA, 0..255 scale)
     curvis_ray_record* records;
     DeviceCounters* counters;
 };

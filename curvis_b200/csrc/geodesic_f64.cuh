@@ -277,31 +277,11 @@ __device__ __forceinline__ void euler_step_lean(const FrameParams& p, Ray& q, bo
     q.pth = q.pth + dpth * p.delta;
 }
 
-// ---------------------------------------------------------------- escaped photon -> texel
-// photon_escape_to_pixel (systems.rs:540-561): relativistic_vector_to_direction
-// (metrics.rs:339-349 incl. the frame_field_22 on the phi component, :347), then
-// SphericalImage::get_pixel_from_vector3 (images.rs:171-174 -> :151-167 -> algebra.rs:128-134
-// -> images.rs:115-121).  Returns true when the reference's get_pixel would have indexed out
-// of bounds (images.rs:107-111 panic); the index is clamped instead.
-__device__ __forceinline__ bool texel_from_direction(const Background& bg, double dx, double dy, double dz,
-                                                     uint32_t& tx, uint32_t& ty);
-
-template <class Shape, class Trig>
-__device__ __forceinline__ bool escaped_texel(const FrameParams& p, const Ray& q, const Background& bg,
-                                              uint32_t& tx, uint32_t& ty) {
-    const double s = Trig::sin(q.th);
-    double r, r2, rp;
-    Shape::eval(p, q.l, r, r2, rp);
-    const double v1 = q.pl;                                   // p_l * g11_contr (= 1)
-    const double v2 = q.pth * (1.0 / r2);
-    const double v3 = q.pph * (1.0 / (r2 * (s * s)));
-    const double dx = v1, dy = v2 * r, dz = v3 * r;           // metrics.rs:345-347
-    return texel_from_direction(bg, dx, dy, dz, tx, ty);
-}
-
-// SphericalImage::get_pixel_from_vector3 (images.rs:171-174): texel index of a direction.
-__device__ __forceinline__ bool texel_from_direction(const Background& bg, double dx, double dy, double dz,
-                                                     uint32_t& tx, uint32_t& ty) {
+// ---------------------------------------------------------------- direction -> texel
+// Continuous equirectangular coordinates of a direction: theta_phi_of_image_from_vector3
+// (images.rs:151-167) then the two expressions inside pixel_indexes_x_y_from_theta_phi_of_image
+// (:115-121) before their truncating casts.
+__device__ __forceinline__ void image_coordinates(const Background& bg, double dx, double dy, double dz, double& fx, double& fy) {
     double wx, wy, wz;
     mat3_mul(bg.inv_rot, dx, dy, dz, wx, wy, wz);             // images.rs:139-141
     const double rn = norm3(wx, wy, wz);
@@ -309,14 +289,127 @@ __device__ __forceinline__ bool texel_from_direction(const Background& bg, doubl
     double ph = atan2(wy, wx);                                // :131
     normalize_theta_phi(th, ph);                              // :133
     normalize_theta_phi(th, ph);                              // images.rs:116
-    const double fy = (th / CURVIS_PI) * (double)bg.height;                                   // :118
-    const double fx = rem_euclid(0.5 - ph / (2.0 * CURVIS_PI), 1.0) * (double)bg.width;       // :119
+    fy = (th / CURVIS_PI) * (double)bg.height;                                   // :118
+    fx = rem_euclid(0.5 - ph / (2.0 * CURVIS_PI), 1.0) * (double)bg.width;       // :119
+}
+
+// The truncating casts of images.rs:118-119 + the bounds the reference's get_pixel panics on.
+__device__ __forceinline__ bool nearest_texel(const Background& bg, double fx, double fy, uint32_t& tx, uint32_t& ty) {
     ty = __double2uint_rz(fy);  // Rust `as u32`: truncate, saturate, NaN -> 0
     tx = __double2uint_rz(fx);
     bool clamped = false;
     if (tx >= bg.width) { tx = bg.width - 1; clamped = true; }
     if (ty >= bg.height) { ty = bg.height - 1; clamped = true; }
     return clamped;
+}
+
+// SphericalImage::get_pixel_from_vector3 (images.rs:171-174): texel index of a direction.
+__device__ __forceinline__ bool texel_from_direction(const Background& bg, double dx, double dy, double dz,
+                                                     uint32_t& tx, uint32_t& ty) {
+    double fx, fy;
+    image_coordinates(bg, dx, dy, dz, fx, fy);
+    return nearest_texel(bg, fx, fy, tx, ty);
+}
+
+// ---------------------------------------------------------------- bilinear tap (extension)
+// CURVIS_SAMPLING_BILINEAR — the reference only has the nearest lookup above.  Texel centres sit
+// at integer + 0.5; wrap in x, clamp in y.  The integer parts are split off in fp64 (fp32 holds
+// only ~10 fractional bits at x ~ 8192), the three lerps run in fp32 with fmaf on RGBA texels
+// staged as float4 (one 128-bit load per tap).  tests/test_gpu_bilinear.py: bit-identical to the
+// oracle's fp32 restatement when fed the same coordinates.
+__device__ __forceinline__ float4 bilinear_tap(const Background& bg, double fx, double fy) {
+    const double ux = fx - 0.5, uy = fy - 0.5;
+    const double x0d = floor(ux), y0d = floor(uy);
+    float wx = (float)(ux - x0d), wy = (float)(uy - y0d);
+    long long x0 = (x0d == x0d) ? (long long)x0d : 0ll, y0 = (y0d == y0d) ? (long long)y0d : 0ll;   // NaN -> 0 like `as`
+    if (!(wx == wx)) wx = 0.f;
+    if (!(wy == wy)) wy = 0.f;
+    const long long W = (long long)bg.width, H = (long long)bg.height;
+    x0 = ((x0 % W) + W) % W;
+    const long long x1 = (x0 + 1) % W;
+    long long y1 = y0 + 1;
+    y0 = y0 < 0 ? 0 : (y0 > H - 1 ? H - 1 : y0);
+    y1 = y1 < 0 ? 0 : (y1 > H - 1 ? H - 1 : y1);
+    const float4 t00 = __ldg(bg.texels_f4 + y0 * W + x0), t10 = __ldg(bg.texels_f4 + y0 * W + x1);
+    const float4 t01 = __ldg(bg.texels_f4 + y1 * W + x0), t11 = __ldg(bg.texels_f4 + y1 * W + x1);
+    float4 o;
+    const float tx_ = fmaf(wx, t10.x - t00.x, t00.x), bx = fmaf(wx, t11.x - t01.x, t01.x); o.x = fmaf(wy, bx - tx_, tx_);
+    const float ty_ = fmaf(wx, t10.y - t00.y, t00.y), by = fmaf(wx, t11.y - t01.y, t01.y); o.y = fmaf(wy, by - ty_, ty_);
+    const float tz_ = fmaf(wx, t10.z - t00.z, t00.z), bz = fmaf(wx, t11.z - t01.z, t01.z); o.z = fmaf(wy, bz - tz_, tz_);
+    const float tw_ = fmaf(wx, t10.w - t00.w, t00.w), bw = fmaf(wx, t11.w - t01.w, t01.w); o.w = fmaf(wy, bw - tw_, tw_);
+    return o;
+}
+
+__device__ __forceinline__ uint32_t quantize_channel(float v) {   // round to nearest even, clamp to u8; NaN -> 0
+    v = rintf(v);
+    return (v >= 255.f) ? 255u : ((v > 0.f) ? (uint32_t)v : 0u);
+}
+
+// ---------------------------------------------------------------- ray epilogue (all per-ray kernels)
+// photon_escape_to_pixel + put_pixel (systems.rs:540-561, :324) for one finished ray, plus the
+// optional outputs: fp32 RGBA (the unrounded tap) and the per-ray record.
+struct RayTally { unsigned pos = 0, neg = 0, none = 0, clamped = 0; unsigned long long steps = 0; };
+
+template <class Shape, class Trig>
+__device__ __forceinline__ void finish_ray(const FrameParams& p, const Ray& q, int side, uint32_t steps,
+                                           unsigned long long ray, RayTally& tally) {
+    if (side > 0) ++tally.pos; else if (side < 0) ++tally.neg; else ++tally.none;   // none: black, systems.rs:556-558
+    tally.steps += steps;
+    uint32_t tx = 0, ty = 0;
+    if (p.out_rgb8 || p.out_rgba32f) {
+        uint32_t rgba = 0;
+        float4 tap = make_float4(0.f, 0.f, 0.f, 255.f);        // Rgba([0, 0, 0, 255])
+        if (side != 0) {
+            const Background& bg = p.bg[side > 0 ? 0 : 1];
+            // relativistic_vector_to_direction (metrics.rs:339-349), covariant momentum
+            const double s = Trig::sin(q.th);
+            double r, r2, rp;
+            Shape::eval(p, q.l, r, r2, rp);
+            const double v2 = q.pth * (1.0 / r2);
+            const double v3 = q.pph * (1.0 / (r2 * (s * s)));
+            double fx, fy;
+            image_coordinates(bg, q.pl, v2 * r, v3 * r, fx, fy);                    // :345-347 (frame_field_22 twice)
+            if (nearest_texel(bg, fx, fy, tx, ty)) ++tally.clamped;
+            if (p.sampling == CURVIS_SAMPLING_BILINEAR) {
+                tap = bilinear_tap(bg, fx, fy);
+                rgba = quantize_channel(tap.x) | (quantize_channel(tap.y) << 8) | (quantize_channel(tap.z) << 16);
+            } else {
+                rgba = __ldg(bg.texels + (size_t)ty * bg.width + tx);
+                tap = make_float4((float)(rgba & 0xffu), (float)((rgba >> 8) & 0xffu), (float)((rgba >> 16) & 0xffu), (float)(rgba >> 24));
+            }
+        }
+        if (p.out_rgb8) {
+            uint8_t* o = p.out_rgb8 + ray * 3ull;                                   // put_pixel on ImageRgb8 drops alpha (:324)
+            o[0] = (uint8_t)(rgba & 0xffu);
+            o[1] = (uint8_t)((rgba >> 8) & 0xffu);
+            o[2] = (uint8_t)((rgba >> 16) & 0xffu);
+        }
+        if (p.out_rgba32f) p.out_rgba32f[ray] = tap;
+    }
+    if (p.records) {
+        curvis_ray_record rec;
+        rec.l = q.l; rec.theta = q.th; rec.phi = q.ph;
+        rec.p_l = q.pl; rec.p_theta = q.pth; rec.p_phi = q.pph;
+        rec.steps = steps; rec.side = side; rec.texel_x = tx; rec.texel_y = ty;
+        p.records[ray] = rec;
+    }
+}
+
+__device__ __forceinline__ void flush_tally(const FrameParams& p, RayTally t, unsigned lane) {
+    for (int o = 16; o > 0; o >>= 1) {
+        t.steps += __shfl_down_sync(0xffffffffu, t.steps, o);
+        t.pos += __shfl_down_sync(0xffffffffu, t.pos, o);
+        t.neg += __shfl_down_sync(0xffffffffu, t.neg, o);
+        t.none += __shfl_down_sync(0xffffffffu, t.none, o);
+        t.clamped += __shfl_down_sync(0xffffffffu, t.clamped, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&p.counters->total_steps, t.steps);
+        if (t.pos) atomicAdd(&p.counters->n_positive, (unsigned long long)t.pos);
+        if (t.neg) atomicAdd(&p.counters->n_negative, (unsigned long long)t.neg);
+        if (t.none) atomicAdd(&p.counters->n_not_escaped, (unsigned long long)t.none);
+        if (t.clamped) atomicAdd(&p.counters->n_clamped, (unsigned long long)t.clamped);
+    }
 }
 
 }  // namespace curvis

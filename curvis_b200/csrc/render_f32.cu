@@ -138,8 +138,7 @@ __global__ void __launch_bounds__(kBlock32) render_rows_f32(const __grid_constan
     bool drained = false;
     uint32_t remaining = 0;
     unsigned long long ray = 0;
-    unsigned long long acc_steps = 0;
-    unsigned acc_pos = 0, acc_neg = 0, acc_none = 0, acc_clamped = 0;
+    RayTally tally;
 
     for (;;) {
         if (state == 2) {
@@ -147,29 +146,8 @@ __global__ void __launch_bounds__(kBlock32) render_rows_f32(const __grid_constan
             Ray q;
             q.l = l.value(); q.th = th.value(); q.ph = ph.value(); q.pl = pl.value(); q.pth = pth.value();
             q.pph = pph_exact; q.pph2 = pph_exact * pph_exact;
-            const uint32_t steps = p.max_iterations - remaining;
             const int side = (q.l > R) ? 1 : ((q.l < -R) ? -1 : 0);
-            uint32_t rgba = 0, tx = 0, ty = 0;
-            if (side > 0) ++acc_pos; else if (side < 0) ++acc_neg; else ++acc_none;   // none: black, systems.rs:556-558
-            if (p.out_rgb8) {
-                if (side != 0) {
-                    const Background& bg = p.bg[side > 0 ? 0 : 1];
-                    if (escaped_texel<Shape64, TrigFast>(p, q, bg, tx, ty)) ++acc_clamped;
-                    rgba = __ldg(bg.texels + (size_t)ty * bg.width + tx);
-                }
-                uint8_t* o = p.out_rgb8 + ray * 3ull;  // put_pixel on ImageRgb8 drops alpha (systems.rs:324)
-                o[0] = (uint8_t)(rgba & 0xffu);
-                o[1] = (uint8_t)((rgba >> 8) & 0xffu);
-                o[2] = (uint8_t)((rgba >> 16) & 0xffu);
-            }
-            if (p.records) {
-                curvis_ray_record rec;
-                rec.l = q.l; rec.theta = q.th; rec.phi = q.ph;
-                rec.p_l = q.pl; rec.p_theta = q.pth; rec.p_phi = q.pph;
-                rec.steps = steps; rec.side = side; rec.texel_x = tx; rec.texel_y = ty;
-                p.records[ray] = rec;
-            }
-            acc_steps += steps;
+            finish_ray<Shape64, TrigFast>(p, q, side, p.max_iterations - remaining, ray, tally);
             state = 0;
         }
 
@@ -226,20 +204,7 @@ __global__ void __launch_bounds__(kBlock32) render_rows_f32(const __grid_constan
         }
     }
 
-    for (int o = 16; o > 0; o >>= 1) {
-        acc_steps += __shfl_down_sync(kFull32, acc_steps, o);
-        acc_pos += __shfl_down_sync(kFull32, acc_pos, o);
-        acc_neg += __shfl_down_sync(kFull32, acc_neg, o);
-        acc_none += __shfl_down_sync(kFull32, acc_none, o);
-        acc_clamped += __shfl_down_sync(kFull32, acc_clamped, o);
-    }
-    if (lane == 0) {
-        atomicAdd(&p.counters->total_steps, acc_steps);
-        if (acc_pos) atomicAdd(&p.counters->n_positive, (unsigned long long)acc_pos);
-        if (acc_neg) atomicAdd(&p.counters->n_negative, (unsigned long long)acc_neg);
-        if (acc_none) atomicAdd(&p.counters->n_not_escaped, (unsigned long long)acc_none);
-        if (acc_clamped) atomicAdd(&p.counters->n_clamped, (unsigned long long)acc_clamped);
-    }
+    flush_tally(p, tally, lane);
 }
 
 template <class Shape32>

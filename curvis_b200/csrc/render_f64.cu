@@ -37,33 +37,12 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64(const __grid_constant_
     uint32_t steps = 0;
     unsigned long long ray = 0;
 
-    unsigned long long acc_steps = 0;
-    unsigned acc_pos = 0, acc_neg = 0, acc_none = 0, acc_clamped = 0;
+    RayTally tally;
 
     for (;;) {
         // ---- epilogue of the lanes that finished during the last window
         if (pending) {
-            uint32_t rgba = 0, tx = 0, ty = 0;
-            if (side > 0) ++acc_pos; else if (side < 0) ++acc_neg; else ++acc_none;   // none: black, systems.rs:556-558
-            if (p.out_rgb8) {
-                if (side != 0) {
-                    const Background& bg = p.bg[side > 0 ? 0 : 1];
-                    if (escaped_texel<Shape, Trig>(p, q, bg, tx, ty)) ++acc_clamped;
-                    rgba = __ldg(bg.texels + (size_t)ty * bg.width + tx);
-                }
-                uint8_t* o = p.out_rgb8 + ray * 3ull;  // put_pixel on ImageRgb8 drops alpha (systems.rs:324)
-                o[0] = (uint8_t)(rgba & 0xffu);
-                o[1] = (uint8_t)((rgba >> 8) & 0xffu);
-                o[2] = (uint8_t)((rgba >> 16) & 0xffu);
-            }
-            if (p.records) {
-                curvis_ray_record rec;
-                rec.l = q.l; rec.theta = q.th; rec.phi = q.ph;
-                rec.p_l = q.pl; rec.p_theta = q.pth; rec.p_phi = q.pph;
-                rec.steps = steps; rec.side = side; rec.texel_x = tx; rec.texel_y = ty;
-                p.records[ray] = rec;
-            }
-            acc_steps += steps;
+            finish_ray<Shape, Trig>(p, q, side, steps, ray, tally);
             pending = false;
         }
 
@@ -106,21 +85,7 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64(const __grid_constant_
         }
     }
 
-    // ---- per-warp reduction of the counters, one atomic per counter per warp
-    for (int o = 16; o > 0; o >>= 1) {
-        acc_steps += __shfl_down_sync(kFull, acc_steps, o);
-        acc_pos += __shfl_down_sync(kFull, acc_pos, o);
-        acc_neg += __shfl_down_sync(kFull, acc_neg, o);
-        acc_none += __shfl_down_sync(kFull, acc_none, o);
-        acc_clamped += __shfl_down_sync(kFull, acc_clamped, o);
-    }
-    if (lane == 0) {
-        atomicAdd(&p.counters->total_steps, acc_steps);
-        if (acc_pos) atomicAdd(&p.counters->n_positive, (unsigned long long)acc_pos);
-        if (acc_neg) atomicAdd(&p.counters->n_negative, (unsigned long long)acc_neg);
-        if (acc_none) atomicAdd(&p.counters->n_not_escaped, (unsigned long long)acc_none);
-        if (acc_clamped) atomicAdd(&p.counters->n_clamped, (unsigned long long)acc_clamped);
-    }
+    flush_tally(p, tally, lane);   // per-warp reduction of the counters, one atomic per counter per warp
 }
 
 // ---------------------------------------------------------------- default kernel (variant 2)
@@ -146,34 +111,12 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64_lean(const __grid_cons
     uint32_t remaining = 0;   // steps left before NotEscaped
     unsigned long long ray = 0;
 
-    unsigned long long acc_steps = 0;
-    unsigned acc_pos = 0, acc_neg = 0, acc_none = 0, acc_clamped = 0;
+    RayTally tally;
 
     for (;;) {
         if (state == 2) {
-            const uint32_t steps = p.max_iterations - remaining;
             const int side = (q.l > R) ? 1 : ((q.l < -R) ? -1 : 0);   // systems.rs:129-134 on the final state
-            uint32_t rgba = 0, tx = 0, ty = 0;
-            if (side > 0) ++acc_pos; else if (side < 0) ++acc_neg; else ++acc_none;   // none: black, systems.rs:556-558
-            if (p.out_rgb8) {
-                if (side != 0) {
-                    const Background& bg = p.bg[side > 0 ? 0 : 1];
-                    if (escaped_texel<Shape, TrigFast>(p, q, bg, tx, ty)) ++acc_clamped;
-                    rgba = __ldg(bg.texels + (size_t)ty * bg.width + tx);
-                }
-                uint8_t* o = p.out_rgb8 + ray * 3ull;  // put_pixel on ImageRgb8 drops alpha (systems.rs:324)
-                o[0] = (uint8_t)(rgba & 0xffu);
-                o[1] = (uint8_t)((rgba >> 8) & 0xffu);
-                o[2] = (uint8_t)((rgba >> 16) & 0xffu);
-            }
-            if (p.records) {
-                curvis_ray_record rec;
-                rec.l = q.l; rec.theta = q.th; rec.phi = q.ph;
-                rec.p_l = q.pl; rec.p_theta = q.pth; rec.p_phi = q.pph;
-                rec.steps = steps; rec.side = side; rec.texel_x = tx; rec.texel_y = ty;
-                p.records[ray] = rec;
-            }
-            acc_steps += steps;
+            finish_ray<Shape, TrigFast>(p, q, side, p.max_iterations - remaining, ray, tally);
             state = 0;
         }
 
@@ -211,20 +154,7 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64_lean(const __grid_cons
         }
     }
 
-    for (int o = 16; o > 0; o >>= 1) {
-        acc_steps += __shfl_down_sync(kFull, acc_steps, o);
-        acc_pos += __shfl_down_sync(kFull, acc_pos, o);
-        acc_neg += __shfl_down_sync(kFull, acc_neg, o);
-        acc_none += __shfl_down_sync(kFull, acc_none, o);
-        acc_clamped += __shfl_down_sync(kFull, acc_clamped, o);
-    }
-    if (lane == 0) {
-        atomicAdd(&p.counters->total_steps, acc_steps);
-        if (acc_pos) atomicAdd(&p.counters->n_positive, (unsigned long long)acc_pos);
-        if (acc_neg) atomicAdd(&p.counters->n_negative, (unsigned long long)acc_neg);
-        if (acc_none) atomicAdd(&p.counters->n_not_escaped, (unsigned long long)acc_none);
-        if (acc_clamped) atomicAdd(&p.counters->n_clamped, (unsigned long long)acc_clamped);
-    }
+    flush_tally(p, tally, lane);
 }
 
 template <class Kernel>
@@ -296,6 +226,30 @@ __global__ void debug_eval_kernel(int op, const double* a, const double* b, doub
     default: break;
     }
     out[i] = r;
+}
+
+__global__ void texels_to_float4_kernel(const uint32_t* texels, float4* out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t t = texels[i];
+        out[i] = make_float4((float)(t & 0xffu), (float)((t >> 8) & 0xffu), (float)((t >> 16) & 0xffu), (float)(t >> 24));
+    }
+}
+
+cudaError_t launch_texels_to_float4(const uint32_t* texels, float4* out, size_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    texels_to_float4_kernel<<<148 * 8, 256, 0, stream>>>(texels, out, n);
+    return cudaGetLastError();
+}
+
+__global__ void debug_bilinear_kernel(const Background bg, const double* fx, const double* fy, float4* out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = bilinear_tap(bg, fx[i], fy[i]);
+}
+
+cudaError_t launch_debug_bilinear(const Background& bg, const double* fx, const double* fy, float4* out, size_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    debug_bilinear_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(bg, fx, fy, out, n);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_debug_eval(int op, const double* a, const double* b, double* out, size_t n, cudaStream_t stream) {

@@ -186,3 +186,25 @@ class RelativisticSystem:
         self.last_stats = stats.as_dict()
         self.last_efficient_info = info.as_dict()
         return (out, dbg) if debug else out
+
+    def render_rows_rgba32f(self, max_iterations: int, max_radius: float, delta: float, row_begin: int, row_end: int, **options):
+        """Unrounded colours (curvis_render_rows_rgba32f): float32 (rows, W, 4) on the 0..255 scale."""
+        cam = self.camera.as_c()
+        out = np.empty((max(0, row_end - row_begin), cam.resolution_width, 4), dtype=np.float32)
+        sim = self._sim(max_iterations, max_radius, delta, **options)
+        stats = _abi.CurvisStats()
+        m = self.metric.as_c()
+        _abi.check(self._lib.curvis_render_rows_rgba32f(self.context.ptr, C.byref(m), C.byref(cam), C.byref(sim), int(row_begin),
+                                                        int(row_end), out.ctypes.data_as(C.c_void_p), C.byref(stats)), self.context.ptr)
+        self.last_stats = stats.as_dict()
+        return out
+
+    def debug_bilinear(self, side: int, fx, fy):
+        """curvis_debug_bilinear: the fp32 tap at explicit continuous texel coordinates."""
+        fx = np.ascontiguousarray(fx, dtype=np.float64)
+        fy = np.ascontiguousarray(fy, dtype=np.float64)
+        out = np.empty(fx.shape + (4,), dtype=np.float32)
+        dp = C.POINTER(C.c_double)
+        _abi.check(self._lib.curvis_debug_bilinear(self.context.ptr, side, fx.ctypes.data_as(dp), fy.ctypes.data_as(dp),
+                                                   out.ctypes.data_as(C.c_void_p), fx.size), self.context.ptr)
+        return out

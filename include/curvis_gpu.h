@@ -91,7 +91,7 @@ typedef enum curvis_precision {
 
 typedef enum curvis_sampling {
     CURVIS_SAMPLING_NEAREST = 0, /* images.rs:115-121: truncating nearest texel, u8 copy */
-    CURVIS_SAMPLING_BILINEAR = 1 /* extension: fp32 2x2 tap (wrap in x, clamp in y)       */
+    CURVIS_SAMPLING_BILINEAR = 1 /* extension: fp32 2x2 tap on float4 texels (wrap in x, clamp in y), rounded to u8 */
 } curvis_sampling;
 
 typedef struct curvis_sim {
@@ -202,6 +202,13 @@ int curvis_render_rows_device(curvis_ctx* ctx, const curvis_metric* metric,
                               void* d_out_rgb8_rows, void* d_records,
                               void* stream, curvis_stats* stats);
 
+/* The same tile as unrounded colours: 4 floats (R, G, B, A on the 0..255 scale) per pixel into a
+ * HOST buffer.  With CURVIS_SAMPLING_NEAREST these are the texel's bytes as floats; with
+ * CURVIS_SAMPLING_BILINEAR (extension) the fp32 2x2 tap before quantisation. */
+int curvis_render_rows_rgba32f(curvis_ctx* ctx, const curvis_metric* metric, const curvis_camera* camera,
+                               const curvis_sim* sim, uint32_t row_begin, uint32_t row_end,
+                               float* out_rgba32f_rows, curvis_stats* stats);
+
 /* Batched form for video (VideoRenderingSystem::render, src/rendering.rs:291-316: one
  * render per frame after update_camera): rows [row_begin,row_end) of `n_frames` frames —
  * one camera per frame, same resolution, same metric/sim/backgrounds — in ONE launch over a
@@ -267,6 +274,11 @@ int curvis_ctx_set_option(curvis_ctx* ctx, const char* key, int64_t value);
  *   3 / 4 sin / cos of the in-kernel sincos fast path   5 / 6 the same with its large-argument fallback
  *   7 a/b   8 sqrt(a)   9 1/a   (the compiler's IEEE operators, for reference)              */
 int curvis_debug_eval(curvis_ctx* ctx, int op, const double* a, const double* b, double* out, size_t n);
+
+/* Test hook of CURVIS_SAMPLING_BILINEAR: the fp32 tap of background `side` at explicit continuous
+ * texel coordinates (fx in [0,W), fy in [0,H]; texel centres at integer + 0.5; wrap in x, clamp in
+ * y) — 4 floats per point into `out_rgba32f`.  Host pointers. */
+int curvis_debug_bilinear(curvis_ctx* ctx, int side, const double* fx, const double* fy, float* out_rgba32f, size_t n);
 
 #ifdef __cplusplus
 }

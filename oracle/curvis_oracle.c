@@ -303,16 +303,58 @@ static uint32_t f64_as_u32(double v) {
 
 /* theta_phi_of_image_from_vector3 src/images.rs:151-167 + pixel_indexes_x_y_from_theta_phi_of_image
  * :115-121.  inv_rot: image orientation inverse (identity by default). */
+void oracle_texel_from_vector3_ex(const double inv_rot[9], const double v_world[3], uint32_t bg_w, uint32_t bg_h,
+                                  uint32_t* x_o, uint32_t* y_o, double* theta_o, double* phi_o, double* fx_o, double* fy_o);
+
 void oracle_texel_from_vector3(const double inv_rot[9], const double v_world[3], uint32_t bg_w, uint32_t bg_h,
                                uint32_t* x_o, uint32_t* y_o, double* theta_o, double* phi_o) {
+    oracle_texel_from_vector3_ex(inv_rot, v_world, bg_w, bg_h, x_o, y_o, theta_o, phi_o, NULL, NULL);
+}
+
+void oracle_texel_from_vector3_ex(const double inv_rot[9], const double v_world[3], uint32_t bg_w, uint32_t bg_h,
+                                  uint32_t* x_o, uint32_t* y_o, double* theta_o, double* phi_o, double* fx_o, double* fy_o) {
     double w[3], theta, phi;
     m3_mul_v(inv_rot, v_world, w);                 /* images.rs:139-141 */
     oracle_theta_phi_from_vector3(w, &theta, &phi);/* :166 */
     if (theta_o) *theta_o = theta;
     if (phi_o) *phi_o = phi;
     oracle_normalize_theta_phi(theta, phi, &theta, &phi); /* :116 */
-    *y_o = f64_as_u32((theta / ORACLE_PI) * (double)bg_h);                               /* :118 */
-    *x_o = f64_as_u32(rem_euclid(0.5 - phi / (2.0 * ORACLE_PI), 1.0) * (double)bg_w);   /* :119 */
+    const double fy = (theta / ORACLE_PI) * (double)bg_h;                               /* :118 */
+    const double fx = rem_euclid(0.5 - phi / (2.0 * ORACLE_PI), 1.0) * (double)bg_w;   /* :119 */
+    *y_o = f64_as_u32(fy);
+    *x_o = f64_as_u32(fx);
+    if (fx_o) *fx_o = fx;
+    if (fy_o) *fy_o = fy;
+}
+
+/* Extension CURVIS_SAMPLING_BILINEAR (no reference counterpart; this fp32 restatement IS its
+ * oracle): texel centres at integer + 0.5, wrap in x, clamp in y; integer parts split off in
+ * fp64, three fmaf lerps per channel in fp32 on texels converted to float (0..255). */
+void oracle_bilinear_tap(const uint8_t* rgba8, uint32_t bg_w, uint32_t bg_h, double fx, double fy, float out[4]) {
+    const double ux = fx - 0.5, uy = fy - 0.5;
+    const double x0d = floor(ux), y0d = floor(uy);
+    float wx = (float)(ux - x0d), wy = (float)(uy - y0d);
+    long long x0 = (x0d == x0d) ? (long long)x0d : 0ll, y0 = (y0d == y0d) ? (long long)y0d : 0ll;
+    if (!(wx == wx)) wx = 0.f;
+    if (!(wy == wy)) wy = 0.f;
+    const long long W = (long long)bg_w, H = (long long)bg_h;
+    x0 = ((x0 % W) + W) % W;
+    const long long x1 = (x0 + 1) % W;
+    long long y1 = y0 + 1;
+    y0 = y0 < 0 ? 0 : (y0 > H - 1 ? H - 1 : y0);
+    y1 = y1 < 0 ? 0 : (y1 > H - 1 ? H - 1 : y1);
+    const uint8_t *t00 = rgba8 + (y0 * W + x0) * 4, *t10 = rgba8 + (y0 * W + x1) * 4;
+    const uint8_t *t01 = rgba8 + (y1 * W + x0) * 4, *t11 = rgba8 + (y1 * W + x1) * 4;
+    for (int c = 0; c < 4; ++c) {
+        const float a = (float)t00[c], b = (float)t10[c], d = (float)t01[c], e = (float)t11[c];
+        const float top = fmaf(wx, b - a, a), bot = fmaf(wx, e - d, d);
+        out[c] = fmaf(wy, bot - top, top);
+    }
+}
+
+static uint8_t quantize_channel(float v) { /* round to nearest even, clamp; NaN -> 0 */
+    v = rintf(v);
+    return (v >= 255.f) ? 255 : ((v > 0.f) ? (uint8_t)v : 0);
 }
 
 /* ------------------------------------------------------------------ systems.rs */
@@ -325,7 +367,7 @@ typedef struct oracle_background { const uint8_t* rgba8; uint32_t w, h; double i
  * bounds (images.rs:107-111 panic); the texel is then clamped like the GPU does. */
 static int oracle_pixel(const curvis_metric* g, const curvis_camera* cam, const curvis_sim* sim,
                         const oracle_background* pos, const oracle_background* neg,
-                        uint32_t px, uint32_t py, uint8_t rgb[3], curvis_ray_record* rec, int* clamped) {
+                        uint32_t px, uint32_t py, uint8_t rgb[3], curvis_ray_record* rec, int* clamped, float rgba32f[4]) {
     double dir[3];
     oracle_photon ph;
     uint32_t steps;
@@ -335,18 +377,26 @@ static int oracle_pixel(const curvis_metric* g, const curvis_camera* cam, const 
     if (side == -2) return -2;
     uint32_t tx = 0, ty = 0;
     *clamped = 0;
+    float tap[4] = {0.f, 0.f, 0.f, 255.f};
     if (side == 0) {
         rgb[0] = rgb[1] = rgb[2] = 0; /* :556-558 */
     } else {
         const oracle_background* bg = side > 0 ? pos : neg;
-        double d[3];
+        double d[3], fx, fy;
         oracle_relativistic_vector_to_direction(g, ph.p, ph.x, d);
-        oracle_texel_from_vector3(bg->inv_rot, d, bg->w, bg->h, &tx, &ty, NULL, NULL);
+        oracle_texel_from_vector3_ex(bg->inv_rot, d, bg->w, bg->h, &tx, &ty, NULL, NULL, &fx, &fy);
         if (tx >= bg->w) { tx = bg->w - 1; *clamped = 1; }
         if (ty >= bg->h) { ty = bg->h - 1; *clamped = 1; }
-        const uint8_t* t = bg->rgba8 + ((size_t)ty * bg->w + tx) * 4;
-        rgb[0] = t[0]; rgb[1] = t[1]; rgb[2] = t[2]; /* put_pixel on ImageRgb8 drops alpha, :324 */
+        if (sim->sampling == CURVIS_SAMPLING_BILINEAR) {
+            oracle_bilinear_tap(bg->rgba8, bg->w, bg->h, fx, fy, tap);
+            rgb[0] = quantize_channel(tap[0]); rgb[1] = quantize_channel(tap[1]); rgb[2] = quantize_channel(tap[2]);
+        } else {
+            const uint8_t* t = bg->rgba8 + ((size_t)ty * bg->w + tx) * 4;
+            rgb[0] = t[0]; rgb[1] = t[1]; rgb[2] = t[2]; /* put_pixel on ImageRgb8 drops alpha, :324 */
+            tap[0] = (float)t[0]; tap[1] = (float)t[1]; tap[2] = (float)t[2]; tap[3] = (float)t[3];
+        }
     }
+    if (rgba32f) memcpy(rgba32f, tap, sizeof tap);
     if (rec) {
         rec->l = ph.x[1]; rec->theta = ph.x[2]; rec->phi = ph.x[3];
         rec->p_l = ph.p[1]; rec->p_theta = ph.p[2]; rec->p_phi = ph.p[3];
@@ -364,7 +414,7 @@ typedef struct oracle_job {
     const curvis_metric* g; const curvis_camera* cam; const curvis_sim* sim;
     const oracle_background *pos, *neg;
     uint32_t row_begin, row_stride; int64_t n_rows;
-    uint8_t* out_rgb8; curvis_ray_record* records;
+    uint8_t* out_rgb8; curvis_ray_record* records; float* out_rgba32f;
     atomic_long next_col;
     uint64_t tot, np, nn, n0, nc, nr; /* per-worker copies are summed by the caller */
 } oracle_job;
@@ -383,8 +433,10 @@ static void* oracle_worker_main(void* arg) {
             uint8_t rgb[3] = {0, 0, 0};
             curvis_ray_record rec;
             int clamped = 0;
-            int side = oracle_pixel(jb->g, jb->cam, jb->sim, jb->pos, jb->neg, (uint32_t)i, j, rgb, &rec, &clamped);
+            float tap[4] = {0.f, 0.f, 0.f, 0.f};
+            int side = oracle_pixel(jb->g, jb->cam, jb->sim, jb->pos, jb->neg, (uint32_t)i, j, rgb, &rec, &clamped, tap);
             size_t o = (size_t)jr * (size_t)W + (size_t)i;
+            if (jb->out_rgba32f) memcpy(jb->out_rgba32f + o * 4, tap, sizeof tap);
             if (jb->out_rgb8) { jb->out_rgb8[o * 3 + 0] = rgb[0]; jb->out_rgb8[o * 3 + 1] = rgb[1]; jb->out_rgb8[o * 3 + 2] = rgb[2]; }
             if (jb->records) jb->records[o] = rec;
             wk->tot += rec.steps; wk->nr += 1; wk->nc += (uint64_t)clamped;
@@ -394,11 +446,26 @@ static void* oracle_worker_main(void* arg) {
     return NULL;
 }
 
+int oracle_render_rows_ex(const curvis_metric* g, const curvis_camera* cam, const curvis_sim* sim,
+                          const uint8_t* bg_pos, uint32_t pos_w, uint32_t pos_h, const double* pos_inv_rot,
+                          const uint8_t* bg_neg, uint32_t neg_w, uint32_t neg_h, const double* neg_inv_rot,
+                          uint32_t row_begin, uint32_t row_end, uint32_t row_stride,
+                          uint8_t* out_rgb8, curvis_ray_record* records, curvis_stats* stats, int n_threads, float* out_rgba32f);
+
 int oracle_render_rows(const curvis_metric* g, const curvis_camera* cam, const curvis_sim* sim,
                        const uint8_t* bg_pos, uint32_t pos_w, uint32_t pos_h, const double* pos_inv_rot,
                        const uint8_t* bg_neg, uint32_t neg_w, uint32_t neg_h, const double* neg_inv_rot,
                        uint32_t row_begin, uint32_t row_end, uint32_t row_stride,
                        uint8_t* out_rgb8, curvis_ray_record* records, curvis_stats* stats, int n_threads) {
+    return oracle_render_rows_ex(g, cam, sim, bg_pos, pos_w, pos_h, pos_inv_rot, bg_neg, neg_w, neg_h, neg_inv_rot,
+                                 row_begin, row_end, row_stride, out_rgb8, records, stats, n_threads, NULL);
+}
+
+int oracle_render_rows_ex(const curvis_metric* g, const curvis_camera* cam, const curvis_sim* sim,
+                          const uint8_t* bg_pos, uint32_t pos_w, uint32_t pos_h, const double* pos_inv_rot,
+                          const uint8_t* bg_neg, uint32_t neg_w, uint32_t neg_h, const double* neg_inv_rot,
+                          uint32_t row_begin, uint32_t row_end, uint32_t row_stride,
+                          uint8_t* out_rgb8, curvis_ray_record* records, curvis_stats* stats, int n_threads, float* out_rgba32f) {
     static const double ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     oracle_background pos = {bg_pos, pos_w, pos_h, {0}}, neg = {bg_neg, neg_w, neg_h, {0}};
     memcpy(pos.inv_rot, pos_inv_rot ? pos_inv_rot : ident, sizeof ident);
@@ -410,7 +477,7 @@ int oracle_render_rows(const curvis_metric* g, const curvis_camera* cam, const c
     jb.g = g; jb.cam = cam; jb.sim = sim; jb.pos = &pos; jb.neg = &neg;
     jb.row_begin = row_begin; jb.row_stride = row_stride;
     jb.n_rows = row_end > row_begin ? (int64_t)((row_end - row_begin + row_stride - 1) / row_stride) : 0;
-    jb.out_rgb8 = out_rgb8; jb.records = records;
+    jb.out_rgb8 = out_rgb8; jb.records = records; jb.out_rgba32f = out_rgba32f;
     atomic_init(&jb.next_col, 0);
     if (n_threads < 1) n_threads = 1;
     if (n_threads > 256) n_threads = 256;

@@ -58,6 +58,9 @@ def lib() -> C.CDLL:
             C.POINTER(_abi.CurvisMetric), C.POINTER(_abi.CurvisCamera), C.POINTER(_abi.CurvisSim),
             vp, C.c_uint32, C.c_uint32, dp, vp, C.c_uint32, C.c_uint32, dp,
             C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, C.POINTER(_abi.CurvisStats), C.c_int]
+        L.oracle_render_rows_ex.argtypes = L.oracle_render_rows.argtypes + [vp]
+        L.oracle_bilinear_tap.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.POINTER(C.c_float)]
+        L.oracle_bilinear_tap.restype = None
         L.oracle_trajectory.argtypes = [C.POINTER(_abi.CurvisMetric), dp, dp, C.c_double, C.c_uint32, dp]
         L.oracle_trajectory.restype = None
         L.oracle_metric_validate.argtypes = [C.POINTER(_abi.CurvisMetric)]
@@ -109,8 +112,21 @@ def camera(position, forward, up, focal_length, diagonal, width, height) -> _abi
     return cam
 
 
-def sim(max_iterations, max_radius, delta) -> _abi.CurvisSim:
-    return _abi.CurvisSim(max_iterations=max_iterations, max_radius=max_radius, delta=delta, precision=0, sampling=0)
+def sim(max_iterations, max_radius, delta, sampling=0) -> _abi.CurvisSim:
+    return _abi.CurvisSim(max_iterations=max_iterations, max_radius=max_radius, delta=delta, precision=0, sampling=sampling)
+
+
+def bilinear_tap(bg_rgba8, fx, fy):
+    """The fp32 bilinear tap (extension) at continuous texel coordinates: float32 (..., 4)."""
+    bg = np.ascontiguousarray(bg_rgba8, dtype=np.uint8)
+    fx = np.asarray(fx, dtype=np.float64); fy = np.asarray(fy, dtype=np.float64)
+    out = np.empty(fx.shape + (4,), dtype=np.float32)
+    flat = out.reshape(-1, 4)
+    o = (C.c_float * 4)()
+    for k, (x, y) in enumerate(zip(fx.reshape(-1), fy.reshape(-1))):
+        lib().oracle_bilinear_tap(bg.ctypes.data_as(C.c_void_p), bg.shape[1], bg.shape[0], float(x), float(y), o)
+        flat[k] = o[:]
+    return out
 
 
 def normalize_theta_phi(theta, phi):
@@ -184,8 +200,9 @@ def trajectory(g, position, direction_, delta, n):
 
 
 def render_rows(g, cam, s, bg_pos, bg_neg, row_begin=0, row_end=None, row_stride=1, threads=1,
-                pos_inv_rot=None, neg_inv_rot=None, with_records=True):
-    """Returns (rgb8 (rows, W, 3), records (rows, W) structured, stats dict)."""
+                pos_inv_rot=None, neg_inv_rot=None, with_records=True, rgba32f=None):
+    """Returns (rgb8 (rows, W, 3), records (rows, W) structured, stats dict).  ``rgba32f``: an
+    optional float32 (rows, W, 4) array that receives the unrounded colours."""
     W, H = cam.resolution_width, cam.resolution_height
     if row_end is None:
         row_end = H
@@ -198,12 +215,13 @@ def render_rows(g, cam, s, bg_pos, bg_neg, row_begin=0, row_end=None, row_stride
     dp = C.POINTER(C.c_double)
     pi = np.ascontiguousarray(pos_inv_rot, dtype=np.float64).ctypes.data_as(dp) if pos_inv_rot is not None else None
     ni = np.ascontiguousarray(neg_inv_rot, dtype=np.float64).ctypes.data_as(dp) if neg_inv_rot is not None else None
-    rc = lib().oracle_render_rows(
+    rc = lib().oracle_render_rows_ex(
         C.byref(g), C.byref(cam), C.byref(s),
         bg_pos.ctypes.data_as(C.c_void_p), bg_pos.shape[1], bg_pos.shape[0], pi,
         bg_neg.ctypes.data_as(C.c_void_p), bg_neg.shape[1], bg_neg.shape[0], ni,
         row_begin, row_end, row_stride, out.ctypes.data_as(C.c_void_p),
-        rec.ctypes.data_as(C.c_void_p) if rec is not None else None, C.byref(st), threads)
+        rec.ctypes.data_as(C.c_void_p) if rec is not None else None, C.byref(st), threads,
+        rgba32f.ctypes.data_as(C.c_void_p) if rgba32f is not None else None)
     if rc:
         raise RuntimeError(f"oracle_render_rows status {rc}")
     return out, rec, st.as_dict()
