@@ -10,7 +10,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # curvis_status
 OK = 0
@@ -27,6 +27,7 @@ ERR_UNSUPPORTED = 9
 METRIC_ELLIS, METRIC_INTERSTELLAR, METRIC_FLAT = 0, 1, 2
 PRECISION_F64, PRECISION_F32 = 0, 1
 SAMPLING_NEAREST, SAMPLING_BILINEAR = 0, 1
+INTEGRATOR_EULER, INTEGRATOR_RK4 = 0, 1
 
 
 class CurvisMetric(C.Structure):
@@ -53,6 +54,8 @@ class CurvisSim(C.Structure):
         ("delta", C.c_double),
         ("precision", C.c_int32),
         ("sampling", C.c_int32),
+        ("integrator", C.c_int32),
+        ("_pad2", C.c_int32),
     ]
 
 

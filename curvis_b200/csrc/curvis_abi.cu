@@ -41,6 +41,7 @@ struct DeviceState {
     uint8_t* h_out = nullptr; size_t h_out_cap = 0;  // pinned staging
     curvis_ray_record* d_records = nullptr; size_t d_records_cap = 0;
     CameraBlock* d_cameras = nullptr; size_t d_cameras_cap = 0;   // batched launches
+    cudaEvent_t chunk_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // pipelined read-back
     // tile of the frame in flight
     uint32_t row_begin = 0, row_end = 0;
 };
@@ -88,6 +89,10 @@ static int validate_frame(curvis_ctx* ctx, const curvis_metric* metric, const cu
         return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "unknown precision");
     if (sim->sampling != CURVIS_SAMPLING_NEAREST && sim->sampling != CURVIS_SAMPLING_BILINEAR)
         return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "unknown sampling mode");
+    if (sim->integrator != CURVIS_INTEGRATOR_EULER && sim->integrator != CURVIS_INTEGRATOR_RK4)
+        return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "unknown integrator");
+    if (sim->integrator == CURVIS_INTEGRATOR_RK4 && sim->precision != CURVIS_PRECISION_F64)
+        return fail(ctx, CURVIS_ERR_UNSUPPORTED, "the RK4 extension is implemented for CURVIS_PRECISION_F64 only");
     if (!ctx->bg_set[0] || !ctx->bg_set[1])
         return fail(ctx, CURVIS_ERR_NO_BACKGROUND, "both backgrounds must be set before rendering");
     // escape_photon panics when the photon starts beyond the radius (systems.rs:122-124);
@@ -122,6 +127,7 @@ static void fill_params(const curvis_ctx* ctx, const DeviceState& d, const curvi
     p.window = (uint32_t)(ctx->tuning.window > 0 ? ctx->tuning.window : 32);
     p.width = cam->resolution_width; p.height = cam->resolution_height;
     p.max_iterations = sim->max_iterations; p.sampling = (uint32_t)sim->sampling;
+    p.integrator = (uint32_t)sim->integrator;
     p.max_radius = sim->max_radius; p.delta = sim->delta;
     p.row_begin = row_begin; p.row_end = row_end;
     p.f_rho = (float)metric->rho; p.f_rho2 = (float)(metric->rho * metric->rho);
@@ -196,6 +202,32 @@ static int ensure_capacity(curvis_ctx* ctx, DeviceState& d, size_t out_bytes, si
     return CURVIS_OK;
 }
 
+// Frame read-back: D2H into the pinned staging buffer in up to 8 chunks, each followed by an
+// event, so the host's copy of chunk k into the caller's (pageable) frame overlaps the DMA of
+// chunk k+1.  enqueue_readback only enqueues; finish_readback blocks chunk by chunk.
+static int enqueue_readback(curvis_ctx* ctx, DeviceState& d, size_t bytes) {
+    const size_t chunks = bytes >= (8u << 20) ? 8 : 1;
+    const size_t step = ((bytes + chunks - 1) / chunks + 255) & ~size_t(255);
+    for (size_t k = 0, off = 0; k < chunks && off < bytes; ++k, off += step) {
+        const size_t len = off + step <= bytes ? step : bytes - off;
+        if (!d.chunk_done[k]) CURVIS_CUDA(ctx, cudaEventCreateWithFlags(&d.chunk_done[k], cudaEventDisableTiming));
+        CURVIS_CUDA(ctx, cudaMemcpyAsync(d.h_out + off, d.d_out + off, len, cudaMemcpyDeviceToHost, d.stream));
+        CURVIS_CUDA(ctx, cudaEventRecord(d.chunk_done[k], d.stream));
+    }
+    return CURVIS_OK;
+}
+
+static int finish_readback(curvis_ctx* ctx, DeviceState& d, uint8_t* dst, size_t bytes) {
+    const size_t chunks = bytes >= (8u << 20) ? 8 : 1;
+    const size_t step = ((bytes + chunks - 1) / chunks + 255) & ~size_t(255);
+    for (size_t k = 0, off = 0; k < chunks && off < bytes; ++k, off += step) {
+        const size_t len = off + step <= bytes ? step : bytes - off;
+        CURVIS_CUDA(ctx, cudaEventSynchronize(d.chunk_done[k]));
+        std::memcpy(dst + off, d.h_out + off, len);
+    }
+    return CURVIS_OK;
+}
+
 static void release_device(DeviceState& d) {
     if (d.ordinal < 0) return;
     cudaSetDevice(d.ordinal);
@@ -207,6 +239,7 @@ static void release_device(DeviceState& d) {
     if (d.h_out) cudaFreeHost(d.h_out);
     if (d.d_records) cudaFree(d.d_records);
     if (d.d_cameras) cudaFree(d.d_cameras);
+    for (auto& ev : d.chunk_done) if (ev) cudaEventDestroy(ev);
     if (d.ev_begin) cudaEventDestroy(d.ev_begin);
     if (d.ev_end) cudaEventDestroy(d.ev_end);
     if (d.stream) cudaStreamDestroy(d.stream);
@@ -398,12 +431,12 @@ extern "C" int curvis_render_rows(curvis_ctx* ctx, const curvis_metric* metric,
     if (rc != CURVIS_OK) return rc;
     rc = enqueue_tile(ctx, d, metric, camera, sim, row_begin, row_end, d.d_out, records ? d.d_records : nullptr, d.stream);
     if (rc != CURVIS_OK) return rc;
-    if (n_rays) CURVIS_CUDA(ctx, cudaMemcpyAsync(d.h_out, d.d_out, n_rays * 3, cudaMemcpyDeviceToHost, d.stream));
+    if (n_rays) { rc = enqueue_readback(ctx, d, n_rays * 3); if (rc != CURVIS_OK) return rc; }
     if (records && n_rays)
         CURVIS_CUDA(ctx, cudaMemcpyAsync(records, d.d_records, n_rays * sizeof(curvis_ray_record), cudaMemcpyDeviceToHost, d.stream));
     CURVIS_CUDA(ctx, cudaMemcpyAsync(d.h_counters, d.d_counters, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, d.stream));
+    if (n_rays) { rc = finish_readback(ctx, d, out_rgb8_rows, n_rays * 3); if (rc != CURVIS_OK) return rc; }
     CURVIS_CUDA(ctx, cudaStreamSynchronize(d.stream));
-    if (n_rays) std::memcpy(out_rgb8_rows, d.h_out, n_rays * 3);
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
         add_counters(*d.h_counters, n_rays, stats);
@@ -437,16 +470,16 @@ extern "C" int curvis_render_image(curvis_ctx* ctx, const curvis_metric* metric,
         if (rc != CURVIS_OK) return rc;
         rc = enqueue_tile(ctx, d, metric, camera, sim, d.row_begin, d.row_end, d.d_out, nullptr, d.stream);
         if (rc != CURVIS_OK) return rc;
-        if (bytes) CURVIS_CUDA(ctx, cudaMemcpyAsync(d.h_out, d.d_out, bytes, cudaMemcpyDeviceToHost, d.stream));
         CURVIS_CUDA(ctx, cudaMemcpyAsync(d.h_counters, d.d_counters, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, d.stream));
+        if (bytes) { rc = enqueue_readback(ctx, d, bytes); if (rc != CURVIS_OK) return rc; }
     }
     if (stats) std::memset(stats, 0, sizeof *stats);
     for (size_t g = 0; g < n; ++g) {
         DeviceState& d = ctx->devs[g];
         const size_t bytes = (size_t)(d.row_end - d.row_begin) * W * 3;
         CURVIS_CUDA(ctx, cudaSetDevice(d.ordinal));
+        if (bytes) { rc = finish_readback(ctx, d, out_rgb8 + (size_t)d.row_begin * W * 3, bytes); if (rc != CURVIS_OK) return rc; }
         CURVIS_CUDA(ctx, cudaStreamSynchronize(d.stream));
-        if (bytes) std::memcpy(out_rgb8 + (size_t)d.row_begin * W * 3, d.h_out, bytes);
         if (stats) {
             add_counters(*d.h_counters, (uint64_t)(d.row_end - d.row_begin) * W, stats);
             float ms = 0.f;

@@ -61,7 +61,7 @@ struct FrameParams {
     uint32_t row_begin, row_end;
     // steps between two refill points of a warp (render_f64.cu), tuning knob
     uint32_t window;
-    uint32_t _pad0;
+    uint32_t integrator;   // curvis_integrator
     // fp32 copies of the uniforms for CURVIS_PRECISION_F32 (render_f32.cu), rounded once on the host
     float f_rho, f_rho2, f_m, f_a, f_xscale, f_delta, f_near_radius, _pad2;
     // scene (systems.rs:70-71): [0] = background_positive, [1] = background_negative

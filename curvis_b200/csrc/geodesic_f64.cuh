@@ -239,42 +239,73 @@ __device__ __forceinline__ void euler_step_tuned(const FrameParams& p, Ray& q, b
 // unguarded sequences with two predictable branches and no fp64 compare.  On sm_100a an fp64
 // instruction holds the scheduler's dispatch port for two cycles, so every fp64 op removed is
 // worth two integer ops (profiles/r01_f64_v2_ncu_summary.txt).  Arithmetic is unchanged.
+// Right-hand side of the geodesic equations at a state (metrics.rs:223-270), lean form.
 template <class Shape>
-__device__ __forceinline__ void euler_step_lean(const FrameParams& p, Ray& q, bool ray_safe) {
-    const bool pre = ray_safe && (abs_hi(q.th) < pow2_hi(30)) && ((abs_hi(q.l) - pow2_hi(-100)) < (pow2_hi(100) - pow2_hi(-100))) &&
-                     (abs_hi(q.pth) < pow2_hi(100));
+__device__ __forceinline__ void rhs_lean(const FrameParams& p, bool ray_safe, double l, double th, double pth, double pph, double pph2,
+                                         double& dth, double& dph, double& dpl, double& dpth) {
+    const bool pre = ray_safe && (abs_hi(th) < pow2_hi(30)) && ((abs_hi(l) - pow2_hi(-100)) < (pow2_hi(100) - pow2_hi(-100))) &&
+                     (abs_hi(pth) < pow2_hi(100));
     double s, c;
-    if (pre) sincos_fast(q.th, s, c);
-    else TrigFast::sincos(q.th, s, c);
-    double dth, dph, dpl, dpth;
+    if (pre) sincos_fast(th, s, c);
+    else TrigFast::sincos(th, s, c);
     if (pre && abs_hi(s) >= pow2_hi(-60)) {
         double r, r2, rp;
-        Shape::eval_fast(p, q.l, r, r2, rp);
+        Shape::eval_fast(p, l, r, r2, rp);
         const double s2 = s * s;
         const double g22c = rcp_rn_unguarded(r2);
         const double g33c = rcp_rn_unguarded(r2 * s2);
-        dth = q.pth * g22c;
-        dph = q.pph * g33c;
-        const double b2 = q.pth * q.pth + div_rn_unguarded(q.pph2, s2);
+        dth = pth * g22c;
+        dph = pph * g33c;
+        const double b2 = pth * pth + div_rn_unguarded(pph2, s2);
         dpl = div_rn_unguarded(b2 * rp, (r * r) * r);
-        dpth = q.pph2 * div_rn_unguarded(c, r2 * (s2 * s));
+        dpth = pph2 * div_rn_unguarded(c, r2 * (s2 * s));
     } else {
         double r, r2, rp;
-        Shape::eval(p, q.l, r, r2, rp);
+        Shape::eval(p, l, r, r2, rp);
         const double s2 = s * s;
         const double g22c = 1.0 / r2;
         const double g33c = 1.0 / (r2 * s2);
-        dth = q.pth * g22c;
-        dph = q.pph * g33c;
-        const double b2 = q.pth * q.pth + q.pph2 / s2;
+        dth = pth * g22c;
+        dph = pph * g33c;
+        const double b2 = pth * pth + pph2 / s2;
         dpl = (b2 * rp) / ((r * r) * r);
-        dpth = q.pph2 * (c / (r2 * (s2 * s)));
+        dpth = pph2 * (c / (r2 * (s2 * s)));
     }
-    q.l = q.l + q.pl * p.delta;
+}
+
+template <class Shape>
+__device__ __forceinline__ void euler_step_lean(const FrameParams& p, Ray& q, bool ray_safe) {
+    double dth, dph, dpl, dpth;
+    rhs_lean<Shape>(p, ray_safe, q.l, q.th, q.pth, q.pph, q.pph2, dth, dph, dpl, dpth);
+    q.l = q.l + q.pl * p.delta;                               // metrics.rs:295 (dl = p_l * 1)
     q.th = q.th + dth * p.delta;
     q.ph = q.ph + dph * p.delta;
-    q.pl = q.pl + dpl * p.delta;
+    q.pl = q.pl + dpl * p.delta;                              // :296
     q.pth = q.pth + dpth * p.delta;
+}
+
+// CURVIS_INTEGRATOR_RK4 (extension; the reference only has the Euler step above): classical
+// Runge-Kutta on the same right-hand side.  Operation order (shared with the oracle's
+// oracle_step_rk4 so the two agree bit for bit up to the transcendentals):
+//   h2 = delta*0.5, d6 = delta/6;  y2 = y + h2*k1;  y3 = y + h2*k2;  y4 = y + delta*k3;
+//   y += d6 * (((k1 + 2*k2) + 2*k3) + k4)
+template <class Shape>
+__device__ __forceinline__ void rk4_step_lean(const FrameParams& p, Ray& q, bool ray_safe) {
+    const double h2 = p.delta * 0.5, d6 = p.delta / 6.0;
+    double k1th, k1ph, k1pl, k1pth, k2th, k2ph, k2pl, k2pth, k3th, k3ph, k3pl, k3pth, k4th, k4ph, k4pl, k4pth;
+    const double k1l = q.pl;
+    rhs_lean<Shape>(p, ray_safe, q.l, q.th, q.pth, q.pph, q.pph2, k1th, k1ph, k1pl, k1pth);
+    const double k2l = q.pl + h2 * k1pl;
+    rhs_lean<Shape>(p, ray_safe, q.l + h2 * k1l, q.th + h2 * k1th, q.pth + h2 * k1pth, q.pph, q.pph2, k2th, k2ph, k2pl, k2pth);
+    const double k3l = q.pl + h2 * k2pl;
+    rhs_lean<Shape>(p, ray_safe, q.l + h2 * k2l, q.th + h2 * k2th, q.pth + h2 * k2pth, q.pph, q.pph2, k3th, k3ph, k3pl, k3pth);
+    const double k4l = q.pl + p.delta * k3pl;
+    rhs_lean<Shape>(p, ray_safe, q.l + p.delta * k3l, q.th + p.delta * k3th, q.pth + p.delta * k3pth, q.pph, q.pph2, k4th, k4ph, k4pl, k4pth);
+    q.l = q.l + d6 * (((k1l + 2.0 * k2l) + 2.0 * k3l) + k4l);
+    q.th = q.th + d6 * (((k1th + 2.0 * k2th) + 2.0 * k3th) + k4th);
+    q.ph = q.ph + d6 * (((k1ph + 2.0 * k2ph) + 2.0 * k3ph) + k4ph);
+    q.pl = q.pl + d6 * (((k1pl + 2.0 * k2pl) + 2.0 * k3pl) + k4pl);
+    q.pth = q.pth + d6 * (((k1pth + 2.0 * k2pth) + 2.0 * k3pth) + k4pth);
 }
 
 // ---------------------------------------------------------------- direction -> texel

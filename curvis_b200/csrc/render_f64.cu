@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64(const __grid_constant_
 // steps/max compare, the escape side decided in the epilogue from the final l, and the
 // per-step escape test gated by an integer compare of |l|'s high word against the radius's
 // (the fp64 compares only run within 2^-20 of the radius, or for NaN).
-template <class Shape>
+template <class Shape, bool RK4>
 __global__ void __launch_bounds__(kBlock) render_rows_f64_lean(const __grid_constant__ FrameParams p) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64_lean(const __grid_cons
 #pragma unroll 1
         for (uint32_t k = 0; k < p.window; ++k) {
             if (state == 1) {
-                euler_step_lean<Shape>(p, q, ray_safe);
+                if (RK4) rk4_step_lean<Shape>(p, q, ray_safe);
+                else euler_step_lean<Shape>(p, q, ray_safe);
                 --remaining;
                 bool done = (remaining == 0);                                   // systems.rs:137
                 if (abs_hi(q.l) >= gate) done = done || (q.l > R) || (q.l < -R);  // :129-134
@@ -177,8 +178,10 @@ static cudaError_t launch_persistent(Kernel kernel, int& blocks_per_sm_auto, con
 
 template <class Shape>
 static cudaError_t launch_lean(const FrameParams& p, int sm_count, int blocks_per_sm_override, cudaStream_t stream) {
-    static int blocks_per_sm_auto = 0;
-    return launch_persistent(render_rows_f64_lean<Shape>, blocks_per_sm_auto, p, sm_count, blocks_per_sm_override, stream);
+    static int blocks_per_sm_euler = 0, blocks_per_sm_rk4 = 0;
+    if (p.integrator == CURVIS_INTEGRATOR_RK4)
+        return launch_persistent(render_rows_f64_lean<Shape, true>, blocks_per_sm_rk4, p, sm_count, blocks_per_sm_override, stream);
+    return launch_persistent(render_rows_f64_lean<Shape, false>, blocks_per_sm_euler, p, sm_count, blocks_per_sm_override, stream);
 }
 
 template <class Shape, class Trig, bool TUNED>
@@ -189,6 +192,7 @@ static cudaError_t launch_one(const FrameParams& p, int sm_count, int blocks_per
 
 template <class Shape>
 static cudaError_t launch_variant(const FrameParams& p, const LaunchTuning& t, int sm_count, cudaStream_t stream) {
+    if (p.integrator == CURVIS_INTEGRATOR_RK4) return launch_lean<Shape>(p, sm_count, t.blocks_per_sm, stream);   // lean kernel only
     switch (t.kernel_variant) {
     case 0: return launch_one<Shape, TrigCuda, false>(p, sm_count, t.blocks_per_sm, stream);   // round-1 v0
     case 1: return launch_one<Shape, TrigCuda, true>(p, sm_count, t.blocks_per_sm, stream);

@@ -92,11 +92,12 @@ class RelativisticSystem:
             inv.ctypes.data_as(C.POINTER(C.c_double))), self.context.ptr)
 
     @staticmethod
-    def _sim(max_iterations, max_radius, delta, precision=_abi.PRECISION_F64, sampling=_abi.SAMPLING_NEAREST):
+    def _sim(max_iterations, max_radius, delta, precision=_abi.PRECISION_F64, sampling=_abi.SAMPLING_NEAREST,
+             integrator=_abi.INTEGRATOR_EULER):
         if max_iterations < 0 or max_iterations > 0xFFFFFFFF:
             raise _abi.CurvisError(_abi.ERR_INVALID_ARGUMENT, "max_iterations must fit u32")
         return _abi.CurvisSim(max_iterations=int(max_iterations), max_radius=float(max_radius), delta=float(delta),
-                              precision=precision, sampling=sampling)
+                              precision=precision, sampling=sampling, integrator=integrator)
 
     def render_image(self, max_iterations: int, max_radius: float, delta: float, **options) -> np.ndarray:
         """The whole frame, row-tiled over the context's devices; returns uint8 (H, W, 3) —

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CURVIS_ABI_VERSION 1
+#define CURVIS_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------------------
  * The reference panics (src/systems.rs:122-124, src/algebra.rs:19-21, src/cameras.rs:
@@ -94,13 +94,21 @@ typedef enum curvis_sampling {
     CURVIS_SAMPLING_BILINEAR = 1 /* extension: fp32 2x2 tap on float4 texels (wrap in x, clamp in y), rounded to u8 */
 } curvis_sampling;
 
+typedef enum curvis_integrator {
+    CURVIS_INTEGRATOR_EULER = 0, /* update_relativistic_object, metrics.rs:283-297: explicit Euler (the reference's only stepper) */
+    CURVIS_INTEGRATOR_RK4 = 1    /* extension: classical 4th-order Runge-Kutta on the same right-hand side; one
+                                    "iteration" = one RK4 step, escape test after every step */
+} curvis_integrator;
+
 typedef struct curvis_sim {
     uint32_t max_iterations; /* systems.rs:309 */
     uint32_t _pad;
     double max_radius;       /* systems.rs:310 */
     double delta;            /* systems.rs:311 */
-    int32_t precision;       /* curvis_precision */
-    int32_t sampling;        /* curvis_sampling  */
+    int32_t precision;       /* curvis_precision  */
+    int32_t sampling;        /* curvis_sampling   */
+    int32_t integrator;      /* curvis_integrator */
+    int32_t _pad2;
 } curvis_sim;
 
 /* ---- per-frame counters (the reference has none) ----------------- */

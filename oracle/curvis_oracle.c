@@ -229,37 +229,71 @@ void oracle_new_photon(const curvis_metric* g, const double position[4], const d
     ph->p[3] = d[2] * metric_r(g, position[1]) * sin(position[2]);
 }
 
-/* update_relativistic_object, src/metrics.rs:283-297 (momentum already covariant, so the
- * branch at :286-288 is not taken), with object_position_diff_contr :223-244 and
- * object_momentum_diff_cov :247-270. */
-void oracle_step(const curvis_metric* g, oracle_photon* ph, double delta) {
-    const double l = ph->x[1], th = ph->x[2];
+/* object_position_diff_contr (src/metrics.rs:223-244) and object_momentum_diff_cov (:247-270) for a
+ * covariant momentum: dx[i] = p[i] * g^{ii}(x), dp = (0, b^2 r'/r^3, p_phi^2 cos/(r^2 sin^3), 0). */
+static void oracle_rhs(const curvis_metric* g, const double x[4], const double p[4], double dx[4], double dp[4]) {
+    const double l = x[1], th = x[2];
     /* contravariant metric components, :84-93 on top of :49-68 */
     double g00c = 1.0 / -1.0;
     double g11c = 1.0 / 1.0;
     double g22c = 1.0 / metric_r_squared(g, l);
     double s = sin(th);
     double g33c = 1.0 / (metric_r_squared(g, l) * (s * s));
-    double dx0 = ph->p[0] * g00c, dx1 = ph->p[1] * g11c, dx2 = ph->p[2] * g22c, dx3 = ph->p[3] * g33c; /* :237-240 */
-    /* :257 */
-    double b2 = ph->p[2] * ph->p[2] + (ph->p[3] * ph->p[3]) / (s * s);
+    dx[0] = p[0] * g00c; dx[1] = p[1] * g11c; dx[2] = p[2] * g22c; dx[3] = p[3] * g33c;          /* :237-240 */
+    double b2 = p[2] * p[2] + (p[3] * p[3]) / (s * s);                                         /* :257 */
     double r = metric_r(g, l);
-    double dp1 = b2 * metric_r_derivative(g, l) / ((r * r) * r);                        /* :261 */
-    double dp2 = (ph->p[3] * ph->p[3]) * (cos(th) / (metric_r_squared(g, l) * ((s * s) * s))); /* :262 */
-    /* :295-296 */
-    ph->x[0] = ph->x[0] + dx0 * delta; ph->x[1] = ph->x[1] + dx1 * delta;
-    ph->x[2] = ph->x[2] + dx2 * delta; ph->x[3] = ph->x[3] + dx3 * delta;
-    ph->p[0] = ph->p[0] + 0.0 * delta; ph->p[1] = ph->p[1] + dp1 * delta;
-    ph->p[2] = ph->p[2] + dp2 * delta; ph->p[3] = ph->p[3] + 0.0 * delta;
+    dp[0] = 0.0;
+    dp[1] = b2 * metric_r_derivative(g, l) / ((r * r) * r);                                    /* :261 */
+    dp[2] = (p[3] * p[3]) * (cos(th) / (metric_r_squared(g, l) * ((s * s) * s)));               /* :262 */
+    dp[3] = 0.0;
+}
+
+/* update_relativistic_object, src/metrics.rs:283-297 (momentum already covariant, so the
+ * branch at :286-288 is not taken): both derivatives at the OLD state, then x += dx*delta,
+ * p += dp*delta (:295-296). */
+void oracle_step(const curvis_metric* g, oracle_photon* ph, double delta) {
+    double dx[4], dp[4];
+    oracle_rhs(g, ph->x, ph->p, dx, dp);
+    for (int i = 0; i < 4; ++i) ph->x[i] = ph->x[i] + dx[i] * delta;
+    for (int i = 0; i < 4; ++i) ph->p[i] = ph->p[i] + dp[i] * delta;
+}
+
+/* Extension CURVIS_INTEGRATOR_RK4 (no reference counterpart; this restatement IS its oracle):
+ * classical Runge-Kutta on oracle_rhs.  Operation order shared with the device code:
+ *   h2 = delta*0.5, d6 = delta/6;  y2 = y + h2*k1;  y3 = y + h2*k2;  y4 = y + delta*k3;
+ *   y += d6 * (((k1 + 2*k2) + 2*k3) + k4)                                                   */
+void oracle_step_rk4(const curvis_metric* g, oracle_photon* ph, double delta) {
+    const double h2 = delta * 0.5, d6 = delta / 6.0;
+    double k1x[4], k1p[4], k2x[4], k2p[4], k3x[4], k3p[4], k4x[4], k4p[4], x[4], p[4];
+    oracle_rhs(g, ph->x, ph->p, k1x, k1p);
+    for (int i = 0; i < 4; ++i) { x[i] = ph->x[i] + h2 * k1x[i]; p[i] = ph->p[i] + h2 * k1p[i]; }
+    oracle_rhs(g, x, p, k2x, k2p);
+    for (int i = 0; i < 4; ++i) { x[i] = ph->x[i] + h2 * k2x[i]; p[i] = ph->p[i] + h2 * k2p[i]; }
+    oracle_rhs(g, x, p, k3x, k3p);
+    for (int i = 0; i < 4; ++i) { x[i] = ph->x[i] + delta * k3x[i]; p[i] = ph->p[i] + delta * k3p[i]; }
+    oracle_rhs(g, x, p, k4x, k4p);
+    for (int i = 0; i < 4; ++i) {
+        ph->x[i] = ph->x[i] + d6 * (((k1x[i] + 2.0 * k2x[i]) + 2.0 * k3x[i]) + k4x[i]);
+        ph->p[i] = ph->p[i] + d6 * (((k1p[i] + 2.0 * k2p[i]) + 2.0 * k3p[i]) + k4p[i]);
+    }
 }
 
 /* escape_photon, src/systems.rs:115-139.  Returns side (+1/-1/0); -2 = the panic at :122-124. */
+int oracle_escape_photon_ex(const curvis_metric* g, oracle_photon* ph, double delta,
+                            uint32_t max_iterations, double max_radius, uint32_t* steps, int integrator);
+
 int oracle_escape_photon(const curvis_metric* g, oracle_photon* ph, double delta,
                          uint32_t max_iterations, double max_radius, uint32_t* steps) {
+    return oracle_escape_photon_ex(g, ph, delta, max_iterations, max_radius, steps, CURVIS_INTEGRATOR_EULER);
+}
+
+int oracle_escape_photon_ex(const curvis_metric* g, oracle_photon* ph, double delta,
+                            uint32_t max_iterations, double max_radius, uint32_t* steps, int integrator) {
     *steps = 0;
     if (fabs(ph->x[1]) > max_radius) return -2;
     for (uint32_t i = 0; i < max_iterations; ++i) {
-        oracle_step(g, ph, delta);
+        if (integrator == CURVIS_INTEGRATOR_RK4) oracle_step_rk4(g, ph, delta);
+        else oracle_step(g, ph, delta);
         *steps = i + 1;
         if (ph->x[1] > max_radius) return 1;
         else if (ph->x[1] < -max_radius) return -1;
@@ -373,7 +407,7 @@ static int oracle_pixel(const curvis_metric* g, const curvis_camera* cam, const 
     uint32_t steps;
     oracle_outward_vector_on_world_space(cam, px, py, dir);
     oracle_new_photon(g, cam->position, dir, &ph);
-    int side = oracle_escape_photon(g, &ph, sim->delta, sim->max_iterations, sim->max_radius, &steps);
+    int side = oracle_escape_photon_ex(g, &ph, sim->delta, sim->max_iterations, sim->max_radius, &steps, sim->integrator);
     if (side == -2) return -2;
     uint32_t tx = 0, ty = 0;
     *clamped = 0;

@@ -47,6 +47,8 @@ def lib() -> C.CDLL:
         L.oracle_new_photon.restype = None
         L.oracle_step.argtypes = [C.POINTER(_abi.CurvisMetric), dp, C.c_double]
         L.oracle_step.restype = None
+        L.oracle_step_rk4.argtypes = [C.POINTER(_abi.CurvisMetric), dp, C.c_double]
+        L.oracle_step_rk4.restype = None
         L.oracle_escape_photon.argtypes = [C.POINTER(_abi.CurvisMetric), dp, C.c_double, C.c_uint32, C.c_double, C.POINTER(C.c_uint32)]
         L.oracle_relativistic_vector_to_direction.argtypes = [C.POINTER(_abi.CurvisMetric), dp, dp, dp]
         L.oracle_relativistic_vector_to_direction.restype = None
@@ -112,8 +114,9 @@ def camera(position, forward, up, focal_length, diagonal, width, height) -> _abi
     return cam
 
 
-def sim(max_iterations, max_radius, delta, sampling=0) -> _abi.CurvisSim:
-    return _abi.CurvisSim(max_iterations=max_iterations, max_radius=max_radius, delta=delta, precision=0, sampling=sampling)
+def sim(max_iterations, max_radius, delta, sampling=0, integrator=0) -> _abi.CurvisSim:
+    return _abi.CurvisSim(max_iterations=max_iterations, max_radius=max_radius, delta=delta, precision=0, sampling=sampling,
+                          integrator=integrator)
 
 
 def bilinear_tap(bg_rgba8, fx, fy):
@@ -161,9 +164,9 @@ def new_photon(g, position, direction):
     return a[:4].copy(), a[4:].copy()
 
 
-def step(g, x, p, delta):
+def step(g, x, p, delta, rk4=False):
     ph = _d(list(x) + list(p), 8)
-    lib().oracle_step(C.byref(g), ph, delta)
+    (lib().oracle_step_rk4 if rk4 else lib().oracle_step)(C.byref(g), ph, delta)
     a = np.array(ph)
     return a[:4].copy(), a[4:].copy()
 

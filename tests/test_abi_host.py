@@ -30,14 +30,14 @@ def test_library_exports_every_declared_symbol(lib):
     assert set(names) == set(_abi.EXPORTED_SYMBOLS)
     for n in names:
         getattr(lib, n)
-    assert lib.curvis_abi_version() == 1
+    assert lib.curvis_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
     from curvis_b200 import _abi
     assert C.sizeof(_abi.CurvisMetric) == 32
     assert C.sizeof(_abi.CurvisCamera) == 4 * 8 + 9 * 8 + 3 * 8 + 8
-    assert C.sizeof(_abi.CurvisSim) == 32
+    assert C.sizeof(_abi.CurvisSim) == 40
     assert C.sizeof(_abi.CurvisStats) == 9 * 8
     assert C.sizeof(_abi.CurvisRayRecord) == 64 == np.dtype(_abi.RAY_RECORD_DTYPE).itemsize
 
