@@ -286,9 +286,11 @@ def run_b200(args):
     host_frames = [torch.empty(Ht * Wd * 3, dtype=torch.uint8).pin_memory() for _ in range(n)] if (n > 1 and rank == 0) else None
     param_bytes = (C_sizeof(_abi.CurvisMetric) + C_sizeof(_abi.CurvisCamera) + C_sizeof(_abi.CurvisSim))
 
+    host_frame = np.empty((Ht, Wd, 3), dtype=np.uint8)      # the caller's (pageable) frame buffer, reused every step
+
     def e2e_step():
         if n == 1:
-            system.render_image(*sim)                      # curvis_render_image: kernel + D2H + copy to caller buffer
+            system.render_image(*sim, out=host_frame)      # curvis_render_image: kernel + D2H + copy to caller buffer
         else:
             system.render_frames_device(cameras, *sim, row_begin, row_end, tiles.data_ptr(), stream.cuda_stream)
             for f in range(n):
@@ -348,7 +350,9 @@ def run_b200(args):
     except Exception:
         pass
     roofline = {
-        "bound": "fp64_alu (no dense contraction and ~1e3 flop/B: neither hbm nor tensor; DESIGN.md section 5)",
+        "bound": "fp64_alu",
+        "bound_note": "per-ray ODE: ~1e4 flop/B and no dense contraction, so neither hbm nor tensor bounds it (DESIGN.md section 5); "
+                      "the hbm figure is reported below for completeness",
         "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
         "traffic": traffic,
         "peak_source": "live DFMA micro-kernel on this GPU (curvis_measure_fma_peak); MEASURED_PEAKS.json has no fp64 entry",
@@ -389,7 +393,7 @@ def run_b200(args):
 
     cpu_baseline = None
     if n == 1 and not args.no_cpu_baseline:
-        one, sample = oracle_sample(args, rows_per_step=24, threads=1)
+        one, sample = oracle_sample(args, rows_per_step=60, threads=1)
         dt, cst = one()
         cpu_baseline = {"value": cst["total_steps"] / dt, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
                         "seconds": dt, "host_cores": os.cpu_count()}

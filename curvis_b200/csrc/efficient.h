@@ -19,7 +19,8 @@ struct EscapeTable {
     std::vector<double> alphas, escapes, signs;       // the sampler's output (systems.rs:458-486)
     std::vector<double> m_e, c_e, m_s, c_s;           // interp_slice segments: value = m[i]*x + c[i]
     uint64_t evaluations = 0, steps = 0;
-    uint32_t passes = 0;
+    uint32_t passes = 0;              // device launches (speculative look-ahead merges refinement passes)
+    uint32_t refinement_passes = 0;   // passes of the sampler's loop (sampling.rs:90-112)
 };
 
 // Integrates n photons leaving the camera position with the given tangent-space directions

@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(kBlock32) render_rows_f32(const __grid_constan
             if (__ballot_sync(kFull32, state != 0) == 0u) break;
         }
 
-#pragma unroll 1
+#pragma unroll 2
         for (uint32_t k = 0; k < p.window; ++k) {
             if (state == 1) {
                 // ---- one forward-Euler step, fp32 right-hand side (metrics.rs:223-270 regrouped)
@@ -185,17 +185,19 @@ __global__ void __launch_bounds__(kBlock32) render_rows_f32(const __grid_constan
                 float inv_r2, force;
                 shape.eval(p, l.s, inv_r2, force);
                 const float inv_s2 = rcp_fast(s * s);
+                const float ir2d = inv_r2 * delta;                   // delta folded into the shared factors
                 const float w = pph2 * inv_s2;                       // p_phi^2 / sin^2
-                const float dth = pth.s * inv_r2;                    // :239
-                const float dph = pph * (inv_r2 * inv_s2);           // :240
                 const float b2 = fmaf(pth.s, pth.s, w);              // :257
-                const float dpl = b2 * force;                        // :261
-                const float dpth = (w * inv_s2) * (c * s) * inv_r2;  // :262  p_phi^2 cos / (r^2 sin^3)
-                l.add(pl.s * delta);                                 // :295 (old p_l)
-                th.add(dth * delta);
-                ph.add(dph * delta);
-                pl.add(dpl * delta);                                 // :296
-                pth.add(dpth * delta);
+                const float inc_l = pl.s * delta;                    // :295 (old p_l)
+                const float inc_th = pth.s * ir2d;                   // :239
+                const float inc_ph = pph * (ir2d * inv_s2);          // :240
+                const float inc_pl = b2 * (force * delta);           // :261
+                const float inc_pth = (w * inv_s2) * (c * s) * ir2d; // :262  p_phi^2 cos / (r^2 sin^3)
+                l.add(inc_l);
+                th.add(inc_th);
+                ph.add(inc_ph);
+                pl.add(inc_pl);                                      // :296
+                pth.add(inc_pth);
                 --remaining;
                 bool done = (remaining == 0);
                 if (!(fabsf(l.s) < near_radius)) done = done || escaped_exact(l.s, l.c, R);  // near the radius, or NaN

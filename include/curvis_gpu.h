@@ -242,7 +242,7 @@ typedef struct curvis_sampling_settings {
 
 typedef struct curvis_efficient_info {
     uint32_t table_points;       /* points the sampler kept                              */
-    uint32_t table_passes;       /* refinement passes = device launches after the first  */
+    uint32_t table_passes;       /* device launches of the sampler (look-ahead merges passes) */
     uint64_t table_evaluations;  /* photons integrated                                   */
     uint64_t table_steps;        /* Euler steps of those photons                         */
     double table_ms;             /* host wall time of the sampler (launches included)    */
