@@ -28,10 +28,11 @@ def load_image(path: str) -> np.ndarray:
         return np.ascontiguousarray(np.asarray(im.convert("RGBA"), dtype=np.uint8))
 
 
-def save_image(rgb8: np.ndarray, path: str) -> None:
-    """images.rs:13-15: the frame is an RGB8 image saved as PNG."""
+def save_image(rgb8: np.ndarray, path: str, compress_level: int = 6) -> None:
+    """images.rs:13-15: the frame is an RGB8 image saved as PNG (lossless: the pixels are what
+    matters, not the deflate level)."""
     from PIL import Image
-    Image.fromarray(rgb8, mode="RGB").save(path)
+    Image.fromarray(rgb8, mode="RGB").save(path, compress_level=compress_level)
 
 
 def load_image_as_spherical_image(path: str, forward=None, up=None) -> SphericalImage:   # images.rs:186-193
@@ -179,7 +180,12 @@ class VideoRenderingSystem:
             s.sampling_convergence_threshold_1,
             s.sampling_convergence_threshold_1)                     # rendering.rs:305-306 passes threshold_1 twice
 
-    def render(self, max_frames: Optional[int] = None, verbose: bool = True) -> str:
+    def render(self, max_frames: Optional[int] = None, verbose: bool = True, encoder_threads: int = 8) -> str:
+        """The frame loop of rendering.rs:258-327.  Rendering a 4K frame takes milliseconds on
+        the GPU while its PNG encode takes a sizeable fraction of a second on one core, so frames
+        are handed to a pool of encoder threads (zlib releases the GIL) and the loop only waits
+        when ``2 * encoder_threads`` frames are in flight."""
+        from concurrent.futures import ThreadPoolExecutor
         s = self.video_rendering_settings
         times = self.times_of_frames()
         if max_frames is not None:
@@ -192,9 +198,18 @@ class VideoRenderingSystem:
         os.mkdir(tmp_folder)
         if verbose:
             print(f"Rendering {len(times)} frames...")
-        for index, t in enumerate(times):
-            if verbose:
-                print(f"Rendering frame {index + 1}/{len(times)}...")
-            self.update_camera(t)                                   # may raise on the last frame, like the reference panics
-            save_image(self.render_frame(), os.path.join(tmp_folder, f"frame_{index}.png"))
+        pending = []
+        with ThreadPoolExecutor(max_workers=max(1, encoder_threads)) as pool:
+            try:
+                for index, t in enumerate(times):
+                    if verbose:
+                        print(f"Rendering frame {index + 1}/{len(times)}...")
+                    self.update_camera(t)                           # may raise on the last frame, like the reference panics
+                    frame = self.render_frame()
+                    pending.append(pool.submit(save_image, frame, os.path.join(tmp_folder, f"frame_{index}.png"), 3))
+                    while len(pending) > 2 * max(1, encoder_threads):
+                        pending.pop(0).result()
+            finally:
+                for f in pending:
+                    f.result()
         return tmp_folder

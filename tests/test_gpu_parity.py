@@ -268,3 +268,24 @@ def test_in_process_multi_device_frame(oracle):
     ref, _, _ = oracle.render_rows(oracle.metric("ellis"), oracle.camera(scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD,
                                    scenes.DEFAULT_UP, 15.0, 43.0, W, H), oracle.sim(40000, 100.0, 0.05), bp, bn, threads=os.cpu_count() or 1)
     assert (a == ref).all()
+
+
+def test_negative_delta_and_unusual_parameters(gpu_ctx, oracle):
+    """A negative step ("evolving the object back in time", metrics.rs:279-280), a camera on the
+    negative side, a large throat, a tiny escape radius: same identity bar."""
+    import curvis_b200 as cv
+    from curvis_b200 import scenes
+    bp, bn = scenes.noise_background(333, 111, 51), scenes.noise_background(333, 111, 52)
+    cases = [
+        ("ellis", dict(rho=2.0), ((0.0, -6.0, 1.1, 0.4), (1.0, 0.1, 0.2), (0.0, 0.0, 1.0), 20.0, 43.0, 48, 32), (3000, 40.0, -0.05)),
+        ("ellis", dict(rho=0.05), ((0.0, 0.5, 2.0, 5.0), (-1.0, 0.0, 0.3), (0.0, 1.0, 0.0), 35.0, 43.0, 40, 40), (5000, 3.0, 0.001)),
+        ("interstellar", dict(m=1.5, a=0.5, rho=3.0), ((0.0, 8.0, 1.0, -1.0), (-1.0, -0.2, 0.0), (0.0, 0.0, 1.0), 15.0, 43.0, 50, 30), (4000, 60.0, 0.03)),
+    ]
+    for kind, mk, cam_args, sim in cases:
+        metric = cv.EllisMetric(mk["rho"]) if kind == "ellis" else cv.InterstellarMetric(mk["m"], mk["a"], mk["rho"])
+        sysm = _system(cv, metric, cam_args, bp, bn, gpu_ctx)
+        H = cam_args[6]
+        frame, rec = sysm.render_rows(*sim, 0, H, with_records=True)
+        ref, rrec, rst = oracle.render_rows(oracle.metric(kind, **mk), oracle.camera(*cam_args), oracle.sim(*sim), bp, bn)
+        _assert_parity(frame, rec, ref, rrec, f"{kind} {mk} {sim}")
+        assert sysm.last_stats["total_steps"] == rst["total_steps"]
