@@ -220,7 +220,13 @@ def run_b200(args):
 
     stream = torch.cuda.current_stream()
     frames = [torch.empty(Ht * Wd * 3, dtype=torch.uint8, device=dev) for _ in range(n)]   # complete frames
-    tiles = torch.empty(n * rows * Wd * 3, dtype=torch.uint8, device=dev)                  # this rank's tile of each frame
+    # this rank's tile of each frame; double-buffered so the all-gathers of step k (comm stream)
+    # overlap the render kernel of step k+1 (compute stream)
+    tiles_buf = [torch.empty(n * rows * Wd * 3, dtype=torch.uint8, device=dev) for _ in range(2)]
+    tiles = tiles_buf[0]
+    comm_stream = torch.cuda.Stream(device=dev) if n > 1 else None
+    tiles_free = [torch.cuda.Event(), torch.cuda.Event()]      # recorded on the comm stream after a buffer was gathered
+    step_index = [0]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     # synthetic camera path: frame f sits 0.02*f further out along l (a dolly move), same orientation
     cameras = [cv.Camera((0.0, scenes.DEFAULT_CAMERA_POSITION[1] + 0.02 * f, scenes.DEFAULT_CAMERA_POSITION[2], 0.0),
@@ -238,9 +244,18 @@ def run_b200(args):
         flush.fill_(1)
         if n == 1:
             return system.render_rows_device(*sim, row_begin, row_end, frames[0].data_ptr(), stream.cuda_stream, want_stats=want_stats)
-        st = system.render_frames_device(cameras, *sim, row_begin, row_end, tiles.data_ptr(), stream.cuda_stream, want_stats=want_stats)
-        for f in range(n):
-            dist.all_gather_into_tensor(frames[f], tiles[f * tile_bytes:(f + 1) * tile_bytes])
+        buf = step_index[0] & 1
+        step_index[0] += 1
+        cur = tiles_buf[buf]
+        stream.wait_event(tiles_free[buf])          # the gather that last read this buffer has finished
+        st = system.render_frames_device(cameras, *sim, row_begin, row_end, cur.data_ptr(), stream.cuda_stream, want_stats=want_stats)
+        rendered = torch.cuda.Event()
+        rendered.record(stream)
+        with torch.cuda.stream(comm_stream):
+            comm_stream.wait_event(rendered)
+            for f in range(n):
+                dist.all_gather_into_tensor(frames[f], cur[f * tile_bytes:(f + 1) * tile_bytes])
+            tiles_free[buf].record(comm_stream)
         return st
 
     # steps of this rank's share of one job-step (deterministic) -> total over ranks
@@ -262,6 +277,8 @@ def run_b200(args):
         e0.record()
         for _ in range(args.steps):
             device_step()
+        if comm_stream is not None:
+            stream.wait_stream(comm_stream)        # the last step's all-gathers are inside the timed region
         e1.record()
         torch.cuda.synchronize()
     barrier()
@@ -344,9 +361,20 @@ def run_b200(args):
     alg_bytes_per_ray = 4 + 3                                  # one RGBA8 texel read + 3 B written
     tile_rays = rows * Wd * n
     hbm_achieved = tile_rays * alg_bytes_per_ray / (kernel_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, fp64_pipe = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "latest_traffic.json"))).get("dram_bytes_per_launch")
+        prof = json.load(open(os.path.join(ROOT, "profiles", "latest_traffic.json")))
+        traffic = prof.get("dram_bytes_per_launch")
+        ipw = prof.get("fp64_warp_instructions_per_warp_step")
+        if ipw:
+            # instruction-level view: fp64-pipe warp-instructions issued per second vs one per two
+            # cycles per scheduler (4 per SM) at the SM clock sampled during the timed region
+            sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+            mhz = clocks.summary().get("sm_mhz") or 1965
+            issued = kernel_rate / 32.0 * ipw
+            peak_issue = sm_count * 4 * mhz * 1e6 / 2.0
+            fp64_pipe = {"fp64_warp_instr_per_s": issued, "peak_warp_instr_per_s": peak_issue, "frac": issued / peak_issue,
+                         "fp64_warp_instr_per_warp_step": ipw, "source": prof.get("source")}
     except Exception:
         pass
     roofline = {
@@ -354,7 +382,7 @@ def run_b200(args):
         "bound_note": "per-ray ODE: ~1e4 flop/B and no dense contraction, so neither hbm nor tensor bounds it (DESIGN.md section 5); "
                       "the hbm figure is reported below for completeness",
         "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
-        "traffic": traffic,
+        "traffic": traffic, "fp64_pipe": fp64_pipe,
         "peak_source": "live DFMA micro-kernel on this GPU (curvis_measure_fma_peak); MEASURED_PEAKS.json has no fp64 entry",
         "flop_per_ray_step": flop, "kernel": "render_rows_f64_lean<ShapeEllis>", "kernel_ms": kernel_ms,
         "kernel_ray_steps_per_s": kernel_rate,

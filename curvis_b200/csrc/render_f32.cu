@@ -200,7 +200,10 @@ __global__ void __launch_bounds__(kBlock32) render_rows_f32(const __grid_constan
                 pth.add(inc_pth);
                 --remaining;
                 bool done = (remaining == 0);
-                if (!(fabsf(l.s) < near_radius)) done = done || escaped_exact(l.s, l.c, R);  // near the radius, or NaN
+                if (!(fabsf(l.s) < near_radius)) {                  // near the radius, or NaN
+                    done = done || escaped_exact(l.s, l.c, R);
+                    if (l.s != l.s) { remaining = 0; done = true; }   // NaN never escapes: NotEscaped with all iterations counted
+                }
                 if (done) state = 2;
             }
         }

@@ -149,7 +149,13 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64_lean(const __grid_cons
                 else euler_step_lean<Shape>(p, q, ray_safe);
                 --remaining;
                 bool done = (remaining == 0);                                   // systems.rs:137
-                if (abs_hi(q.l) >= gate) done = done || (q.l > R) || (q.l < -R);  // :129-134
+                if (abs_hi(q.l) >= gate) {
+                    done = done || (q.l > R) || (q.l < -R);                     // :129-134
+                    // A NaN l never compares true and never recovers (l += NaN): the reference would
+                    // spin through all remaining iterations and return NotEscaped.  Same result, same
+                    // step count, without the spinning.
+                    if (q.l != q.l) { remaining = 0; done = true; }
+                }
                 if (done) state = 2;
             }
         }
