@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--width", type=int, default=W4K)
     ap.add_argument("--height", type=int, default=H4K)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="f64_fast", choices=["f64_fast", "f64"],
+                    help="f64_fast (default): fp64, right-hand side regrouped around one reciprocal per step "
+                         "(CURVIS_PRECISION_F64_FAST); f64: one rounding per reference operation (CURVIS_PRECISION_F64)")
     return ap.parse_args()
 
 
@@ -60,6 +63,10 @@ def workload_config(args, n):
                     f"escape_radius 100 / max_iterations 40000 / step 0.05 (forward Euler, early exit), nearest u8 lookup in "
                     f"two {BG_W}x{BG_H} RGBA8 backgrounds",
         "frames_per_step": n,
+        "precision": {"f64_fast": "CURVIS_PRECISION_F64_FAST: fp64, same Euler scheme, right-hand side regrouped around one "
+                                  "reciprocal per step (each operation <= 1 ulp; frame checked against the operation-for-operation "
+                                  "kernel in `parity_check`)",
+                      "f64": "CURVIS_PRECISION_F64: fp64, one rounding per reference operation"}[args.precision],
         "parallelism": "single GPU" if n == 1 else f"{n} frames/step (camera path), each row-tiled over {n} ranks: one batched launch per rank + one NCCL all-gather of row tiles per frame",
         "l2": "256 MiB device buffer rewritten between steps inside the timed region (L2 flush); the kernel is ALU-bound",
     }
@@ -217,6 +224,8 @@ def run_b200(args):
                   scenes.DEFAULT_FOCAL_LENGTH, scenes.DEFAULT_DIAGONAL, Wd, Ht), context=ctx)
     background_upload_ms = (time.perf_counter() - t_up0) * 1e3
     sim = (scenes.DEFAULT_MAX_ITERATIONS, scenes.DEFAULT_ESCAPE_RADIUS, scenes.DEFAULT_STEP)
+    PREC = {"f64_fast": _abi.PRECISION_F64_FAST, "f64": _abi.PRECISION_F64}[args.precision]
+    KERNEL = {"f64_fast": "render_rows_f64_fast<FastEllis>", "f64": "render_rows_f64_lean<ShapeEllis>"}[args.precision]
 
     stream = torch.cuda.current_stream()
     frames = [torch.empty(Ht * Wd * 3, dtype=torch.uint8, device=dev) for _ in range(n)]   # complete frames
@@ -243,12 +252,14 @@ def run_b200(args):
         batched launch (curvis_render_frames_device), then one all-gather per frame."""
         flush.fill_(1)
         if n == 1:
-            return system.render_rows_device(*sim, row_begin, row_end, frames[0].data_ptr(), stream.cuda_stream, want_stats=want_stats)
+            return system.render_rows_device(*sim, row_begin, row_end, frames[0].data_ptr(), stream.cuda_stream, want_stats=want_stats,
+                                             precision=PREC)
         buf = step_index[0] & 1
         step_index[0] += 1
         cur = tiles_buf[buf]
         stream.wait_event(tiles_free[buf])          # the gather that last read this buffer has finished
-        st = system.render_frames_device(cameras, *sim, row_begin, row_end, cur.data_ptr(), stream.cuda_stream, want_stats=want_stats)
+        st = system.render_frames_device(cameras, *sim, row_begin, row_end, cur.data_ptr(), stream.cuda_stream, want_stats=want_stats,
+                                         precision=PREC)
         rendered = torch.cuda.Event()
         rendered.record(stream)
         with torch.cuda.stream(comm_stream):
@@ -307,9 +318,9 @@ def run_b200(args):
 
     def e2e_step():
         if n == 1:
-            system.render_image(*sim, out=host_frame)      # curvis_render_image: kernel + D2H + copy to caller buffer
+            system.render_image(*sim, out=host_frame, precision=PREC)   # curvis_render_image: kernel + D2H + copy to caller buffer
         else:
-            system.render_frames_device(cameras, *sim, row_begin, row_end, tiles.data_ptr(), stream.cuda_stream)
+            system.render_frames_device(cameras, *sim, row_begin, row_end, tiles.data_ptr(), stream.cuda_stream, precision=PREC)
             for f in range(n):
                 dist.all_gather_into_tensor(frames[f], tiles[f * tile_bytes:(f + 1) * tile_bytes])
                 if rank == 0:
@@ -342,7 +353,7 @@ def run_b200(args):
         for _ in range(reps):
             system._upload(+1, system.background_positive)
             system._upload(-1, system.background_negative)
-            system.render_image(*sim)
+            system.render_image(*sim, out=host_frame, precision=PREC)
         dt = time.perf_counter() - t0
         e2e_cold = {"value": frame_steps * reps / dt, "unit": UNIT,
                     "h2d_bytes_per_step": 2 * BG_W * BG_H * 4 + param_bytes, "d2h_bytes_per_step": Wd * Ht * 3,
@@ -363,7 +374,7 @@ def run_b200(args):
     hbm_achieved = tile_rays * alg_bytes_per_ray / (kernel_ms * 1e-3) / 1e9
     traffic, fp64_pipe = None, None
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "latest_traffic.json")))
+        prof = json.load(open(os.path.join(ROOT, "profiles", "latest_traffic.json")))[KERNEL]
         traffic = prof.get("dram_bytes_per_launch")
         ipw = prof.get("fp64_warp_instructions_per_warp_step")
         if ipw:
@@ -384,7 +395,7 @@ def run_b200(args):
         "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
         "traffic": traffic, "fp64_pipe": fp64_pipe,
         "peak_source": "live DFMA micro-kernel on this GPU (curvis_measure_fma_peak); MEASURED_PEAKS.json has no fp64 entry",
-        "flop_per_ray_step": flop, "kernel": "render_rows_f64_lean<ShapeEllis>", "kernel_ms": kernel_ms,
+        "flop_per_ray_step": flop, "kernel": KERNEL, "kernel_ms": kernel_ms,
         "kernel_ray_steps_per_s": kernel_rate,
         "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
@@ -392,7 +403,29 @@ def run_b200(args):
         "fp32_fma_peak_tflops": fp32_peak,
     }
 
-    # ---- opt-in fast mode (CURVIS_PRECISION_F32), reported next to the parity numbers, never instead of them
+    # ---- the operation-for-operation kernel (CURVIS_PRECISION_F64) next to the headline, and the headline
+    # frame checked against it pixel for pixel (it equals the CPU oracle on all 8,294,400 pixels of this
+    # frame, profiles/r01_parity_full_4k_ellis.json)
+    strict_mode, parity_check = None, None
+    if n == 1:
+        sms = []
+        for _ in range(3):
+            s4 = system.render_rows_device(*sim, row_begin, row_end, frames[0].data_ptr(), stream.cuda_stream, want_stats=True,
+                                           precision=_abi.PRECISION_F64)
+            sms.append(s4["kernel_ms"])
+        strict_frame = frames[0].clone()
+        s5 = system.render_rows_device(*sim, row_begin, row_end, frames[0].data_ptr(), stream.cuda_stream, want_stats=True, precision=PREC)
+        differing = int((strict_frame.view(-1, 3) != frames[0].view(-1, 3)).any(dim=1).sum().item())
+        strict_mode = {"precision": "CURVIS_PRECISION_F64: one rounding per reference operation (six correctly rounded divisions, "
+                                    "one square root, sincos per step)",
+                       "kernel": "render_rows_f64_lean<ShapeEllis>", "value": s4["total_steps"] / (min(sms) * 1e-3), "unit": UNIT,
+                       "kernel_ms": min(sms), "frac_of_fp64_fma_peak": s4["total_steps"] / (min(sms) * 1e-3) * flop / 1e12 / fp64_peak}
+        parity_check = {"against": "render_rows_f64_lean<ShapeEllis> (CURVIS_PRECISION_F64), same frame, every pixel",
+                        "pixels": Wd * Ht, "differing_pixels": differing,
+                        "total_steps_equal": bool(s4["total_steps"] == s5["total_steps"]),
+                        "escape_counters_equal": all(s4[k] == s5[k] for k in ("n_positive", "n_negative", "n_not_escaped", "n_clamped"))}
+
+    # ---- opt-in fp32 mode (CURVIS_PRECISION_F32), reported next to the headline, never instead of it
     fast_mode = None
     if n == 1:
         fms = []
@@ -407,7 +440,7 @@ def run_b200(args):
                           BG_W - np.abs(r64["texel_x"].astype(np.int64) - r32["texel_x"].astype(np.int64))) <= 1) & \
               (np.abs(r64["texel_y"].astype(np.int64) - r32["texel_y"].astype(np.int64)) <= 1)
         fast_mode = {
-            "precision": "f32 right-hand side + Kahan-compensated state (extension, off by default)",
+            "precision": "CURVIS_PRECISION_F32: f32 right-hand side + Kahan-compensated state (extension, off by default)",
             "value": s3["total_steps"] / (min(fms) * 1e-3), "unit": UNIT, "kernel_ms": min(fms),
             "fp32_fma_peak_tflops": fp32_peak, "frac_of_fp32_peak": s3["total_steps"] / (min(fms) * 1e-3) * flop / 1e12 / fp32_peak,
             "deviation_vs_parity_kernel": {
@@ -440,7 +473,9 @@ def run_b200(args):
         "gpu_launches": int(launches_t.item()),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
-        "fast_mode": fast_mode,
+        "strict_mode": strict_mode,
+        "parity_check": parity_check,
+        "f32_mode": fast_mode,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

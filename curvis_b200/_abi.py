@@ -25,7 +25,7 @@ ERR_NO_DEVICE = 8
 ERR_UNSUPPORTED = 9
 
 METRIC_ELLIS, METRIC_INTERSTELLAR, METRIC_FLAT = 0, 1, 2
-PRECISION_F64, PRECISION_F32 = 0, 1
+PRECISION_F64, PRECISION_F32, PRECISION_F64_FAST = 0, 1, 2
 SAMPLING_NEAREST, SAMPLING_BILINEAR = 0, 1
 INTEGRATOR_EULER, INTEGRATOR_RK4 = 0, 1
 

@@ -85,7 +85,8 @@ static int validate_frame(curvis_ctx* ctx, const curvis_metric* metric, const cu
         return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "resolution_width and resolution_height must be greater than 0");
     if (row_begin > row_end || row_end > cam->resolution_height)
         return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "row range outside the frame");
-    if (sim->precision != CURVIS_PRECISION_F64 && sim->precision != CURVIS_PRECISION_F32)
+    if (sim->precision != CURVIS_PRECISION_F64 && sim->precision != CURVIS_PRECISION_F32 &&
+        sim->precision != CURVIS_PRECISION_F64_FAST)
         return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "unknown precision");
     if (sim->sampling != CURVIS_SAMPLING_NEAREST && sim->sampling != CURVIS_SAMPLING_BILINEAR)
         return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "unknown sampling mode");
@@ -106,6 +107,7 @@ static cudaError_t launch_render(const FrameParams& p, const curvis_metric* metr
                                  const LaunchTuning& t, int sm_count, cudaStream_t stream) {
     g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
     if (sim->precision == CURVIS_PRECISION_F32) return launch_render_f32(p, metric->kind, t, sm_count, stream);
+    if (sim->precision == CURVIS_PRECISION_F64_FAST) return launch_render_f64_fast(p, metric->kind, t, sm_count, stream);
     return launch_render_f64(p, metric->kind, t, sm_count, stream);
 }
 
@@ -134,6 +136,8 @@ static void fill_params(const curvis_ctx* ctx, const DeviceState& d, const curvi
     p.f_m = (float)metric->m; p.f_a = (float)metric->a;
     p.f_xscale = (float)(2.0 / (3.14159265358979323846 * metric->m));
     p.f_delta = (float)sim->delta;
+    p.d_rho2 = metric->rho * metric->rho;
+    p.d_xscale = 2.0 / (3.14159265358979323846 * metric->m);
     // below this |l| no escape test is needed in the fp32 kernel (4 steps of slack at |p_l| <= ~1.3)
     p.f_near_radius = (float)(std::fabs(sim->max_radius) - 6.0 * std::fabs(sim->delta) - 1e-3 * std::fabs(sim->max_radius));
     for (int s = 0; s < 2; ++s) {

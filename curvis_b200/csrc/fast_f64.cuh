@@ -1,0 +1,71 @@
+// fast_f64.cuh — arithmetic primitives of CURVIS_PRECISION_F64_FAST (render_f64_fast.cu): a
+// <= 1 ulp reciprocal without the correction step, and sin^2 / sin*cos from one range reduction.
+// Shared with the op-level test hook (curvis_debug_eval ops 10-12, render_f64.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "ieee_f64.cuh"
+#include "trig_f64.cuh"
+
+namespace curvis {
+
+// 1/d to <= 1 ulp for d in the safe window: seed (~2^-20) + one cubic Newton step.
+__device__ __forceinline__ double rcp_1ulp(double d) {
+    const double y = rcp_seed(d);
+    double e = fma(-d, y, 1.0);
+    e = fma(e, e, e);
+    return fma(y, e, y);
+}
+
+// An fp64 instruction takes at most ONE uniform (constant-bank) operand, so the constants that
+// meet another constant in the same FMA — 2/pi with the rounding magic, the leading coefficient
+// of each polynomial — must sit in vector registers.  Left to itself ptxas re-loads them (LDC)
+// every step; read through ld.global they stay in registers for the whole kernel.  The remaining
+// constants come from the constant bank into uniform registers once per window.
+static __device__ __constant__ double kReduce[2] = {1.5707963267948966, 6.123233995736766e-17};   // pi/2 hi, mid
+static __device__ double kPinned[3] = {0.6366197723675814, 1.5912475864762696e-10, -1.1379094621237813e-11};   // 2/pi, kSinPoly[5], kCosPoly[5]
+
+struct TrigRegs {
+    double two_over_pi, sin5, cos5;
+    __device__ __forceinline__ void load() {
+        asm volatile("ld.global.f64 %0, [%1];" : "=d"(two_over_pi) : "l"(kPinned));
+        asm volatile("ld.global.f64 %0, [%1];" : "=d"(sin5) : "l"(kPinned + 1));
+        asm volatile("ld.global.f64 %0, [%1];" : "=d"(cos5) : "l"(kPinned + 2));
+    }
+};
+
+// sin^2(x) and sin(x)cos(x) for |x| < 2^30.  With x = k*pi/2 + r, |r| <= pi/4:
+//   sin^2 x = (k odd) ? cos^2 r : sin^2 r,   sin x cos x = (-1)^k sin r cos r.
+// Two-term Cody-Waite reduction (|k| is small: theta stays within a few multiples of pi).
+__device__ __forceinline__ void sin2_sincos(const TrigRegs& tr, double x, double& s2, double& cs) {
+    const double t = fma(x, tr.two_over_pi, kRoundMagic);
+    const int k = __double2loint(t);
+    const double q = t - kRoundMagic;
+    double r = fma(-q, kReduce[0], x);
+    r = fma(-q, kReduce[1], r);
+    const double u = r * r;
+    double sp = fma(u, tr.sin5, kSinPoly[4]);
+    double cp = fma(u, tr.cos5, kCosPoly[4]);
+    sp = fma(u, sp, kSinPoly[3]);
+    cp = fma(u, cp, kCosPoly[3]);
+    sp = fma(u, sp, kSinPoly[2]);
+    cp = fma(u, cp, kCosPoly[2]);
+    sp = fma(u, sp, kSinPoly[1]);
+    cp = fma(u, cp, kCosPoly[1]);
+    sp = fma(u, sp, kSinPoly[0]);
+    cp = fma(u, cp, kCosPoly[0]);
+    const double sr = fma(r * u, sp, r);                    // sin r
+    const double cr = fma(u, fma(u, cp, -0.5), 1.0);        // cos r
+    const double a = (k & 1) ? cr : sr;
+    s2 = a * a;
+    const double m = sr * cr;
+    cs = __hiloint2double(__double2hiint(m) ^ (k << 31), __double2loint(m));
+}
+
+// d >= 0 by construction (a product of squares and a positive radius), so the high word is
+// its own magnitude key: finite, normal and in [2^-300, 2^300) <=> one unsigned compare.
+// NaN (either sign) and Inf fall outside.
+__device__ __forceinline__ bool in_window_nonneg(double d) {
+    return ((unsigned)__double2hiint(d) - pow2_hi(-300)) < (pow2_hi(300) - pow2_hi(-300));
+}
+
+}  // namespace curvis

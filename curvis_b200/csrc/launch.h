@@ -20,6 +20,9 @@ cudaError_t launch_render_f64(const FrameParams& p, int metric_kind, const Launc
 // fp32 fast mode, CURVIS_PRECISION_F32 (render_f32.cu) — extension, not the parity path.
 cudaError_t launch_render_f32(const FrameParams& p, int metric_kind, const LaunchTuning& t, int sm_count, cudaStream_t stream);
 
+// fp64 with a regrouped right-hand side, CURVIS_PRECISION_F64_FAST (render_f64_fast.cu) — extension.
+cudaError_t launch_render_f64_fast(const FrameParams& p, int metric_kind, const LaunchTuning& t, int sm_count, cudaStream_t stream);
+
 // RGBA8 -> float4 staging for CURVIS_SAMPLING_BILINEAR, and the tap evaluated at explicit
 // continuous coordinates (test hook curvis_debug_bilinear).  render_f64.cu.
 cudaError_t launch_texels_to_float4(const uint32_t* texels, float4* out, size_t n, cudaStream_t stream);

@@ -11,6 +11,7 @@
 // (<1 % of a ~2000-step ray) instead of waiting for the slowest lane of the warp, and a ray
 // that runs to max_iterations (NotEscaped, 40000 steps at defaults) costs one lane, not 32.
 #include "geodesic_f64.cuh"
+#include "fast_f64.cuh"
 #include "launch.h"
 
 namespace curvis {
@@ -233,6 +234,8 @@ __global__ void debug_eval_kernel(int op, const double* a, const double* b, doub
     case 7: r = x / y; break;
     case 8: r = sqrt(x); break;
     case 9: r = 1.0 / x; break;
+    case 10: r = rcp_1ulp(x); break;
+    case 11: case 12: { TrigRegs tr; tr.load(); sin2_sincos(tr, x, s, c); r = (op == 11) ? s : c; break; }
     default: break;
     }
     out[i] = r;

@@ -86,7 +86,10 @@ typedef struct curvis_camera {
  * extension fields are 0 in parity mode. */
 typedef enum curvis_precision {
     CURVIS_PRECISION_F64 = 0, /* reference arithmetic: IEEE double, reference operation order */
-    CURVIS_PRECISION_F32 = 1  /* extension: fp32 state (not bit-comparable)    */
+    CURVIS_PRECISION_F32 = 1, /* extension: fp32 state (not bit-comparable)    */
+    CURVIS_PRECISION_F64_FAST = 2 /* extension: fp64 with the right-hand side regrouped around ONE reciprocal per step
+                                     and fused multiply-adds; every operation <= 1 ulp, rounding points differ from
+                                     the reference's (state agrees to ~1e-13 relative)    */
 } curvis_precision;
 
 typedef enum curvis_sampling {
@@ -280,7 +283,8 @@ int curvis_ctx_set_option(curvis_ctx* ctx, const char* key, int64_t value);
 /* Op-level test hook: out[i] = op(a[i], b[i]) evaluated on the device (host pointers).
  *   0 rcp_rn_unguarded(a)  1 div_rn_unguarded(a,b)  2 sqrt_rn_unguarded(a)
  *   3 / 4 sin / cos of the in-kernel sincos fast path   5 / 6 the same with its large-argument fallback
- *   7 a/b   8 sqrt(a)   9 1/a   (the compiler's IEEE operators, for reference)              */
+ *   7 a/b   8 sqrt(a)   9 1/a   (the compiler's IEEE operators, for reference)
+ *   10 the <= 1 ulp reciprocal of CURVIS_PRECISION_F64_FAST   11 / 12 its sin^2(a) / sin(a)cos(a)   */
 int curvis_debug_eval(curvis_ctx* ctx, int op, const double* a, const double* b, double* out, size_t n);
 
 /* Test hook of CURVIS_SAMPLING_BILINEAR: the fp32 tap of background `side` at explicit continuous

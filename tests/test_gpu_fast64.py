@@ -1,0 +1,180 @@
+"""CURVIS_PRECISION_F64_FAST — fp64 with the right-hand side regrouped around one reciprocal per
+step (render_f64_fast.cu).  It has no operation-for-operation counterpart in the reference, so
+its bar is stated here, against the same oracle as the parity kernel:
+
+* integer / byte results (RGB8, escape side, step count, texel index, counters): identical to the
+  oracle on >= 99.999 % of rays of every tested frame (measured: every ray of every frame below,
+  and all but 1 of 8.3 M pixels of the full Interstellar 4K frame);
+* floating-point state: final l and p_l within rtol 1e-9 on >= 99.9 % of escaped rays (the rest are
+  the chaotic rays that graze a coordinate pole, where 1 ulp is amplified without bound), end
+  direction within 1e-5 rad (BASELINE.json north_star) on >= 99.99 %;
+* exotic cases (NaN rays of the Flat metric, NotEscaped, zero iterations, negative delta): exactly
+  the parity kernel's output — such rays take the parity step.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+MAX_DIFFERING_FRACTION = 1e-5
+END_DIRECTION_TOL_RAD = 1e-5
+
+
+def _ulps(got, want_ld):
+    want = want_ld.astype(np.float64)
+    return np.abs((got.astype(np.longdouble) - want_ld) / np.spacing(np.abs(want)).astype(np.longdouble)).astype(np.float64)
+
+
+def test_primitives_accuracy(gpu_ctx):
+    """The reciprocal without the correction step is <= 1 ulp (and correctly rounded on > 99 % of
+    operands); sin^2 and sin*cos from one reduction are within 4 ulp."""
+    rng = np.random.default_rng(20251017)
+    x = np.exp(rng.uniform(-200, 200, 2_000_000)) * rng.choice([-1.0, 1.0], 2_000_000)
+    got = gpu_ctx.debug_eval(10, x)
+    e = _ulps(got, 1.0 / x.astype(np.longdouble))
+    assert e.max() <= 1.0 and (got == 1.0 / x).mean() > 0.99
+    th = np.concatenate([rng.uniform(-7, 7, 2_000_000), np.pi + rng.uniform(-1e-3, 1e-3, 50_000), rng.uniform(-1e-6, 1e-6, 50_000),
+                         rng.uniform(-1e4, 1e4, 100_000)])
+    thl = th.astype(np.longdouble)
+    assert _ulps(gpu_ctx.debug_eval(11, th), np.sin(thl) ** 2).max() <= 4.0
+    # sin*cos = sin(2 theta)/2 has zeros at multiples of pi/2, where the relative error of any
+    # finite-precision reduction is unbounded: absolute bound there, relative elsewhere
+    cs, want = gpu_ctx.debug_eval(12, th), np.sin(thl) * np.cos(thl)
+    away = np.abs(want) > 1e-3
+    assert _ulps(cs[away], want[away]).max() <= 4.0
+    assert np.abs(cs[~away] - want[~away].astype(np.float64)).max() <= 1e-18 + 4e-16 * np.abs(th[~away]).max()
+
+
+def _compare_with_oracle(frame, rec, ref_frame, ref_rec, name):
+    n = ref_rec.size
+    bad = ((frame != ref_frame).any(axis=2) | (rec["side"] != ref_rec["side"]) | (rec["steps"] != ref_rec["steps"]) |
+           (rec["texel_x"] != ref_rec["texel_x"]) | (rec["texel_y"] != ref_rec["texel_y"]))
+    n_bad = int(bad.sum())
+    assert n_bad <= max(0, int(MAX_DIFFERING_FRACTION * n)), f"{name}: {n_bad} of {n} rays differ from the oracle"
+    assert rec["p_phi"].tobytes() == ref_rec["p_phi"].tobytes(), f"{name}: p_phi is conserved and never recomputed"
+    ok = (ref_rec["side"] != 0) & ~bad & np.isfinite(ref_rec["l"]) & np.isfinite(ref_rec["theta"])
+    if ok.any():
+        for f in ("l", "p_l"):
+            rel = np.abs(rec[f][ok] - ref_rec[f][ok]) / np.maximum(np.abs(ref_rec[f][ok]), 1e-300)
+            assert (rel <= 1e-9).mean() >= 0.999, f"{name}: {f} deviates (p99.9 = {np.percentile(rel, 99.9)})"
+        a = np.stack([rec["p_l"], rec["p_theta"], rec["p_phi"]], -1)[ok]
+        b = np.stack([ref_rec["p_l"], ref_rec["p_theta"], ref_rec["p_phi"]], -1)[ok]
+        ang = np.arctan2(np.linalg.norm(np.cross(a, b), axis=-1), (a * b).sum(-1))
+        assert (ang <= END_DIRECTION_TOL_RAD).mean() >= 0.9999, f"{name}: end direction"
+    return n_bad
+
+
+@pytest.mark.parametrize("name", ["ellis_c1a_64x36", "ellis_defaults_48x27", "interstellar_defaults_48x27",
+                                  "flat_40x30", "ellis_tilted_33x17"])
+def test_golden_scenes(gpu_ctx, oracle, name):
+    """The golden fixtures of the parity kernel, rendered in fast mode."""
+    import curvis_b200 as cv
+    import make_golden
+    from curvis_b200 import _abi, scenes
+    kind, mk, W, H, sim, pos, fwd, up, _ = make_golden.CASES[name]
+    _, _, _, bp, bn = make_golden.scene(name)
+    metric = {"ellis": lambda: cv.EllisMetric(mk.get("rho", 1.0)), "interstellar": lambda: cv.InterstellarMetric(0.1, 1e-4, 1.0),
+              "flat": cv.FlatSphericalMetric}[kind]()
+    cam = cv.Camera(pos, fwd, up, scenes.DEFAULT_FOCAL_LENGTH, scenes.DEFAULT_DIAGONAL, W, H)
+    sysm = cv.RelativisticSystem(metric, cv.SphericalImage(bp), cv.SphericalImage(bn), cam, context=gpu_ctx)
+    frame, rec = sysm.render_rows(*sim, 0, H, with_records=True, precision=_abi.PRECISION_F64_FAST)
+    st = sysm.last_stats
+    gold = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    n_bad = _compare_with_oracle(frame, rec, gold["rgb"], gold["rec"], name)
+    if n_bad == 0:
+        assert st["total_steps"] == int(gold["total_steps"])
+        assert [st["n_positive"], st["n_negative"], st["n_not_escaped"], st["n_clamped"]] == gold["counts"].tolist()
+    assert (sysm.render_image(*sim, precision=_abi.PRECISION_F64_FAST) == frame).all()
+
+
+@pytest.mark.parametrize("kind,sim", [("ellis", (200, 10.0, 0.1)), ("ellis", (40000, 100.0, 0.05)),
+                                      ("interstellar", (40000, 100.0, 0.05))])
+def test_baseline_config_256x144(gpu_ctx, oracle, kind, sim):
+    """BASELINE.json configs[0] (C1a / C1b) and the Interstellar default frame against the live oracle."""
+    import curvis_b200 as cv
+    from curvis_b200 import _abi, scenes
+    W, H = 256, 144
+    bp, bn = scenes.decodable_background(4096, 2048), scenes.decodable_background(4096, 2048, True)
+    metric = cv.EllisMetric(1.0) if kind == "ellis" else cv.InterstellarMetric(0.1, 1e-4, 1.0)
+    cam_args = (scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP, 15.0, 43.0, W, H)
+    sysm = cv.RelativisticSystem(metric, cv.SphericalImage(bp), cv.SphericalImage(bn), cv.Camera(*cam_args), context=gpu_ctx)
+    frame, rec = sysm.render_rows(*sim, 0, H, with_records=True, precision=_abi.PRECISION_F64_FAST)
+    ref_frame, ref_rec, ref_st = oracle.render_rows(oracle.metric(kind), oracle.camera(*cam_args), oracle.sim(*sim), bp, bn,
+                                                    threads=os.cpu_count() or 1)
+    n_bad = _compare_with_oracle(frame, rec, ref_frame, ref_rec, f"{kind} {sim}")
+    assert abs(sysm.last_stats["total_steps"] - ref_st["total_steps"]) <= n_bad * sim[0]
+
+
+def test_exotic_rays_match_the_parity_kernel(gpu_ctx):
+    """NaN rays (Flat metric through l = 0), NotEscaped, zero iterations, negative step, a camera on
+    the polar axis: rays outside the fast step's operand window take the parity step, so the frames
+    and the per-ray integers equal the parity kernel's."""
+    import curvis_b200 as cv
+    from curvis_b200 import _abi, scenes
+    bp, bn = scenes.noise_background(128, 64, 1), scenes.noise_background(128, 64, 2)
+    cases = [
+        (cv.FlatSphericalMetric(), (scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP, 15.0, 43.0, 40, 30), (4000, 100.0, 0.05)),
+        (cv.EllisMetric(1.0), (scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP, 15.0, 43.0, 40, 24), (100, 100.0, 0.05)),
+        (cv.EllisMetric(1.0), (scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP, 15.0, 43.0, 40, 24), (0, 100.0, 0.05)),
+        (cv.EllisMetric(1.0), (scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP, 15.0, 43.0, 40, 24), (140, 10.0, 0.1)),
+        (cv.EllisMetric(1.0), (scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP, 15.0, 43.0, 40, 24), (3000, 100.0, -0.05)),
+        (cv.EllisMetric(2.0), ((0.0, 3.0, 1e-9, 0.3), (-1.0, 0.2, 0.1), (0.0, 0.0, 1.0), 15.0, 43.0, 31, 17), (3000, 50.0, 0.05)),
+        (cv.InterstellarMetric(0.1, 1e-4, 1.0), ((0.0, 0.00005, 1.2, 0.3), (-1.0, 0.2, 0.1), (0.0, 0.0, 1.0), 15.0, 43.0, 31, 17), (3000, 50.0, 0.05)),
+    ]
+    for metric, cam_args, sim in cases:
+        H = cam_args[-1]
+        sysm = cv.RelativisticSystem(metric, cv.SphericalImage(bp), cv.SphericalImage(bn), cv.Camera(*cam_args), context=gpu_ctx)
+        f0, r0 = sysm.render_rows(*sim, 0, H, with_records=True)
+        s0 = dict(sysm.last_stats)
+        f1, r1 = sysm.render_rows(*sim, 0, H, with_records=True, precision=_abi.PRECISION_F64_FAST)
+        s1 = sysm.last_stats
+        name = f"{type(metric).__name__} {sim}"
+        assert (f0 == f1).all(), name
+        for f in ("side", "steps", "texel_x", "texel_y"):
+            assert (r0[f] == r1[f]).all(), (name, f)
+        for k in ("total_steps", "n_positive", "n_negative", "n_not_escaped", "n_clamped"):
+            assert s0[k] == s1[k], (name, k)
+
+
+def test_full_4k_frame_against_the_parity_kernel(gpu_ctx, oracle):
+    """BASELINE metric config (Ellis 3840x2160 defaults): the fast frame against the parity kernel's
+    (itself identical to the oracle on all 8,294,400 pixels, profiles/r01_parity_full_4k_ellis.json),
+    row tiles == whole frame, determinism, and strided rows against the oracle directly."""
+    import curvis_b200 as cv
+    from curvis_b200 import _abi, scenes
+    from curvis_b200.distributed import row_tile
+    W, H = 3840, 2160
+    sim = (40000, 100.0, 0.05)
+    bp, bn = scenes.decodable_background(4096, 2048), scenes.decodable_background(4096, 2048, True)
+    cam_args = (scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP, 15.0, 43.0, W, H)
+    sysm = cv.RelativisticSystem(cv.EllisMetric(1.0), cv.SphericalImage(bp), cv.SphericalImage(bn), cv.Camera(*cam_args), context=gpu_ctx)
+    strict = sysm.render_image(*sim).copy()
+    st_strict = dict(sysm.last_stats)
+    fast = sysm.render_image(*sim, precision=_abi.PRECISION_F64_FAST).copy()
+    st_fast = dict(sysm.last_stats)
+    differing = int((strict != fast).any(axis=2).sum())
+    assert differing <= int(MAX_DIFFERING_FRACTION * W * H), differing
+    assert abs(st_fast["total_steps"] - st_strict["total_steps"]) <= differing * sim[0]
+    assert (sysm.render_image(*sim, precision=_abi.PRECISION_F64_FAST) == fast).all()      # deterministic
+    tiles = [sysm.render_rows(*sim, *row_tile(H, r, 8), precision=_abi.PRECISION_F64_FAST) for r in range(8)]
+    assert (np.concatenate(tiles, axis=0) == fast).all()
+    ref, _, _ = oracle.render_rows(oracle.metric("ellis"), oracle.camera(*cam_args), oracle.sim(*sim), bp, bn, row_begin=11, row_end=H,
+                                   row_stride=271, threads=os.cpu_count() or 1, with_records=False)
+    assert int((ref != fast[11:H:271]).any(axis=2).sum()) <= 1
+
+
+def test_fast64_rejects_rk4(gpu_ctx):
+    import curvis_b200 as cv
+    from curvis_b200 import _abi, scenes
+    bp = scenes.noise_background(64, 32, 1)
+    cam = cv.Camera(scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP, 15.0, 43.0, 16, 9)
+    sysm = cv.RelativisticSystem(cv.EllisMetric(1.0), cv.SphericalImage(bp), cv.SphericalImage(bp), cam, context=gpu_ctx)
+    with pytest.raises(cv.CurvisError) as e:
+        sysm.render_image(10, 100.0, 0.05, precision=_abi.PRECISION_F64_FAST, integrator=_abi.INTEGRATOR_RK4)
+    assert e.value.code == _abi.ERR_UNSUPPORTED

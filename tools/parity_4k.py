@@ -19,9 +19,13 @@ out = dict(kind=kind, W=W, H=H, sim=sim, oracle_seconds=t_cpu, oracle_threads=os
 ctx = cv.Context([0])
 metric = cv.EllisMetric(1.0) if kind == "ellis" else cv.InterstellarMetric(0.1, 1e-4, 1.0)
 sysm = cv.RelativisticSystem(metric, cv.SphericalImage(bp), cv.SphericalImage(bn), cv.Camera(*cam_args), context=ctx)
-for variant in (0, 3):
-    ctx.set_option("kernel_variant", variant)
-    frame = sysm.render_image(*sim)
+from curvis_b200 import _abi
+for variant in (0, 3, "f64_fast"):
+    if variant == "f64_fast":      # CURVIS_PRECISION_F64_FAST (render_f64_fast.cu)
+        frame = sysm.render_image(*sim, precision=_abi.PRECISION_F64_FAST)
+    else:
+        ctx.set_option("kernel_variant", variant)
+        frame = sysm.render_image(*sim)
     st = sysm.last_stats
     diff = (frame != ref).any(axis=2)
     ys, xs = np.nonzero(diff)
