@@ -509,6 +509,7 @@ extern "C" int curvis_ctx_set_option(curvis_ctx* ctx, const char* key, int64_t v
     if (k == "kernel_variant" && value >= 0 && value <= 3) ctx->tuning.kernel_variant = (int)value;
     else if (k == "blocks_per_sm" && value >= 0 && value <= 32) ctx->tuning.blocks_per_sm = (int)value;
     else if (k == "window" && value >= 1 && value <= 4096) ctx->tuning.window = (int)value;
+    else if (k == "fast_variant" && value >= 0 && value <= 1) ctx->tuning.fast_variant = (int)value;
     else return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "unknown option or value out of range: " + k);
     return CURVIS_OK;
 }

@@ -12,6 +12,8 @@ struct LaunchTuning {
                              // 2 + in-kernel sincos; 3 (default) lean loop: integer-pipe guards, gated escape test
     int blocks_per_sm = 0;   // 0 = occupancy maximum
     int window = 32;         // Euler steps between two refill points of a warp
+    int fast_variant = 1;    // CURVIS_PRECISION_F64_FAST: 0 sin/cos from theta every step; 1 (default) (sin, cos) carried and
+                             // rotated by the step's small dtheta, re-derived from theta once per window
 };
 
 // fp64 parity kernel (render_f64.cu, compiled with -fmad=false).

@@ -109,6 +109,35 @@ __device__ __forceinline__ bool fast_step(const FrameParams& p, const TrigRegs& 
     return true;
 }
 
+// The same step with (sin theta, cos theta) carried as state (fast_f64.cuh: rotate_sincos): the
+// pair is rotated by the step's dtheta unconditionally; the caller re-derives it from theta when
+// |dtheta| >= 2^-4 (`dth` is returned for that test).  Returns false, leaving the state untouched,
+// when an operand is outside the safe window.
+template <class Fast>
+__device__ __forceinline__ bool fast_step_rot(const FrameParams& p, const RotRegs& rr, Ray& q, double& s, double& c, double& dth) {
+    const double s2 = s * s, cs = s * c;
+    double w, u, v, ud, fd;
+    if (!Fast::factors(p, q.l, s2, w, u, v, ud, fd)) return false;
+    dth = q.pth * ud;                                       // :239 times delta
+    const double pv = q.pph2 * v;                           // p_phi^2 / sin^2
+    const double b2 = fma(q.pth, q.pth, pv);                // metrics.rs:257
+    const double wd = w * p.delta;
+    q.l = fma(q.pl, p.delta, q.l);                          // :238, :295
+    q.th = q.th + dth;
+    q.ph = fma(q.pph, wd, q.ph);                            // :240
+    q.pl = fma(b2, fd, q.pl);                               // :261, :296
+    q.pth = fma(pv * cs, wd, q.pth);                        // :262
+    rotate_sincos(rr, dth, s, c);
+    return true;
+}
+
+// (sin, cos)(theta) for the rare re-derivation inside the loop; out of line, by value.
+__device__ __noinline__ double2 sincos_pair(double th) {
+    double s, c;
+    sincos_fast(th, s, c);
+    return make_double2(s, c);
+}
+
 // Parity steps for a lane whose operands left the safe window: plain operators, reference
 // arithmetic (euler_step_lean with the guards off).  Out of line so that the hot loop keeps its
 // registers and uniform constants to itself; rays that come here graze a coordinate pole or
@@ -132,7 +161,7 @@ __device__ __noinline__ SlowResult parity_steps(const FrameParams& p, Ray q, uin
     return r;
 }
 
-template <class Fast>
+template <class Fast, int Variant>
 __global__ void __launch_bounds__(kBlockFast) render_rows_f64_fast(const __grid_constant__ FrameParams p) {
     using Shape64 = typename Fast::Shape64;
     const unsigned lane = threadIdx.x & 31u;
@@ -144,7 +173,9 @@ __global__ void __launch_bounds__(kBlockFast) render_rows_f64_fast(const __grid_
     const unsigned gate = (R >= 0.0) ? abs_hi(R) : 0u;
 
     TrigRegs tr;
-    tr.load();
+    RotRegs rr;
+    if (Variant == 0) tr.load();
+    else rr.load();
     Ray q;
     int state = 0;            // 0 idle, 1 integrating, 2 finished (epilogue pending)
     bool drained = false;
@@ -189,12 +220,31 @@ __global__ void __launch_bounds__(kBlockFast) render_rows_f64_fast(const __grid_
             bool stop = false;
             // huge angles (outside the reduction's range) and non-finite p_theta / p_phi^2 take parity steps
             bool slow = !(abs_hi(q.th) < pow2_hi(30) && abs_hi(q.pth) < pow2_hi(200) && abs_hi(q.pph2) < pow2_hi(200));
-            if (!slow) {
+            if (!slow && Variant == 0) {
                 do {
                     if (!fast_step<Fast>(p, tr, q)) { slow = true; break; }
                     ++k;
                     if (abs_hi(q.l) >= gate) {                                   // within 2^-20 of the radius, or NaN
                         if ((q.l > R) || (q.l < -R) || (q.l != q.l)) { stop = true; break; }   // :129-134
+                    }
+                } while (k < n);
+            }
+            if (!slow && Variant == 1) {
+                double sn, cn, dth;
+                sincos_fast(q.th, sn, cn);                                       // once per window, then rotated
+                do {
+                    if (!fast_step_rot<Fast>(p, rr, q, sn, cn, dth)) { slow = true; break; }
+                    ++k;
+                    // one rarely-taken branch for both per-step tests: near the escape radius (or NaN), and
+                    // a dtheta too large for the rotation (or NaN)
+                    const bool big = abs_hi(dth) >= pow2_hi(-4);
+                    if (big || abs_hi(q.l) >= gate) {
+                        if ((q.l > R) || (q.l < -R) || (q.l != q.l)) { stop = true; break; }   // :129-134
+                        if (big) {
+                            if (abs_hi(q.th) >= pow2_hi(30)) { slow = (k < n); break; }
+                            const double2 sc = sincos_pair(q.th);
+                            sn = sc.x; cn = sc.y;
+                        }
                     }
                 } while (k < n);
             }
@@ -216,11 +266,11 @@ __global__ void __launch_bounds__(kBlockFast) render_rows_f64_fast(const __grid_
     flush_tally(p, tally, lane);
 }
 
-template <class Fast>
-cudaError_t launch_fast(const FrameParams& p, int sm_count, int blocks_per_sm_override, cudaStream_t stream) {
+template <class Fast, int Variant>
+cudaError_t launch_fast_variant(const FrameParams& p, int sm_count, int blocks_per_sm_override, cudaStream_t stream) {
     static int blocks_per_sm_auto = 0;
     if (blocks_per_sm_auto == 0) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm_auto, render_rows_f64_fast<Fast>, kBlockFast, 0);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm_auto, render_rows_f64_fast<Fast, Variant>, kBlockFast, 0);
         if (e != cudaSuccess) return e;
         if (blocks_per_sm_auto < 1) blocks_per_sm_auto = 1;
     }
@@ -230,17 +280,23 @@ cudaError_t launch_fast(const FrameParams& p, int sm_count, int blocks_per_sm_ov
     unsigned long long want = (rays + kBlockFast - 1) / kBlockFast;
     unsigned long long cap = (unsigned long long)sm_count * (unsigned long long)blocks_per_sm;
     const unsigned grid = (unsigned)(want < cap ? (want ? want : 1) : cap);
-    render_rows_f64_fast<Fast><<<grid, kBlockFast, 0, stream>>>(p);
+    render_rows_f64_fast<Fast, Variant><<<grid, kBlockFast, 0, stream>>>(p);
     return cudaGetLastError();
+}
+
+template <class Fast>
+cudaError_t launch_fast(const FrameParams& p, const LaunchTuning& t, int sm_count, cudaStream_t stream) {
+    if (t.fast_variant == 0) return launch_fast_variant<Fast, 0>(p, sm_count, t.blocks_per_sm, stream);   // trigonometry from theta every step
+    return launch_fast_variant<Fast, 1>(p, sm_count, t.blocks_per_sm, stream);                            // default: rotated (sin, cos)
 }
 
 }  // namespace
 
 cudaError_t launch_render_f64_fast(const FrameParams& p, int metric_kind, const LaunchTuning& t, int sm_count, cudaStream_t stream) {
     switch (metric_kind) {
-    case CURVIS_METRIC_ELLIS: return launch_fast<FastEllis>(p, sm_count, t.blocks_per_sm, stream);
-    case CURVIS_METRIC_INTERSTELLAR: return launch_fast<FastInterstellar>(p, sm_count, t.blocks_per_sm, stream);
-    case CURVIS_METRIC_FLAT: return launch_fast<FastFlat>(p, sm_count, t.blocks_per_sm, stream);
+    case CURVIS_METRIC_ELLIS: return launch_fast<FastEllis>(p, t, sm_count, stream);
+    case CURVIS_METRIC_INTERSTELLAR: return launch_fast<FastInterstellar>(p, t, sm_count, stream);
+    case CURVIS_METRIC_FLAT: return launch_fast<FastFlat>(p, t, sm_count, stream);
     default: return cudaErrorInvalidValue;
     }
 }

@@ -61,14 +61,15 @@ def show(name, coef):
         d = float(c)
         print(f"    {d!r},   // {d.hex()}")
 
-sc = remez_polish(S, cheb_fit(S, 5, 0, U), 0, U)
-cc = remez_polish(C, cheb_fit(C, 5, 0, U), 0, U)
-show("S(u): sin(r) = r + r*u*S(u), ascending powers of u", sc)
-show("C(u): cos(r) = 1 - u/2 + u*u*C(u), ascending powers of u", cc)
-errS = max(abs(S(U * k / 2000) - sum(mp.mpf(float(c)) * (U * k / 2000) ** j for j, c in enumerate(sc))) * (U * k / 2000) for k in range(2001))
-errC = max(abs(C(U * k / 2000) - sum(mp.mpf(float(c)) * (U * k / 2000) ** j for j, c in enumerate(cc))) * (U * k / 2000) ** 2 for k in range(2001))
-print("// max approximation error relative to r (sin):", mp.nstr(errS, 5), " absolute (cos):", mp.nstr(errC, 5))
-p = mp.pi / 2
-c1 = float(p); c2 = float(p - mp.mpf(c1)); c3 = float(p - mp.mpf(c1) - mp.mpf(c2))
-print("// pi/2 split:", repr(c1), repr(c2), repr(c3))
-print("// 2/pi:", repr(float(2 / mp.pi)))
+if __name__ == "__main__":
+    sc = remez_polish(S, cheb_fit(S, 5, 0, U), 0, U)
+    cc = remez_polish(C, cheb_fit(C, 5, 0, U), 0, U)
+    show("S(u): sin(r) = r + r*u*S(u), ascending powers of u", sc)
+    show("C(u): cos(r) = 1 - u/2 + u*u*C(u), ascending powers of u", cc)
+    errS = max(abs(S(U * k / 2000) - sum(mp.mpf(float(c)) * (U * k / 2000) ** j for j, c in enumerate(sc))) * (U * k / 2000) for k in range(2001))
+    errC = max(abs(C(U * k / 2000) - sum(mp.mpf(float(c)) * (U * k / 2000) ** j for j, c in enumerate(cc))) * (U * k / 2000) ** 2 for k in range(2001))
+    print("// max approximation error relative to r (sin):", mp.nstr(errS, 5), " absolute (cos):", mp.nstr(errC, 5))
+    p = mp.pi / 2
+    c1 = float(p); c2 = float(p - mp.mpf(c1)); c3 = float(p - mp.mpf(c1) - mp.mpf(c2))
+    print("// pi/2 split:", repr(c1), repr(c2), repr(c3))
+    print("// 2/pi:", repr(float(2 / mp.pi)))
