@@ -17,6 +17,7 @@
 #include "launch.h"
 #include "efficient.h"
 #include "efficient_params.h"
+#include "shape_table.h"
 
 namespace curvis {
 
@@ -41,6 +42,7 @@ struct DeviceState {
     uint8_t* h_out = nullptr; size_t h_out_cap = 0;  // pinned staging
     curvis_ray_record* d_records = nullptr; size_t d_records_cap = 0;
     CameraBlock* d_cameras = nullptr; size_t d_cameras_cap = 0;   // batched launches
+    double2* d_shape_tab = nullptr;   // Interstellar shape-function table (shape_table.h), uploaded at context creation
     cudaEvent_t chunk_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // pipelined read-back
     // tile of the frame in flight
     uint32_t row_begin = 0, row_end = 0;
@@ -126,7 +128,9 @@ static void fill_params(const curvis_ctx* ctx, const DeviceState& d, const curvi
     p.rho = metric->rho; p.m = metric->m; p.a = metric->a;
     fill_camera(metric, cam, p.cam);
     p.cameras = nullptr; p.n_frames = 1;
-    p.window = (uint32_t)(ctx->tuning.window > 0 ? ctx->tuning.window : 32);
+    // auto: 32 steps between refill points; 64 for CURVIS_PRECISION_F64_FAST, whose per-window work (sin/cos
+    // re-derived from theta) is larger and whose steps are shorter (tools/window_sweep.py)
+    p.window = (uint32_t)(ctx->tuning.window > 0 ? ctx->tuning.window : (sim->precision == CURVIS_PRECISION_F64_FAST ? 64 : 32));
     p.width = cam->resolution_width; p.height = cam->resolution_height;
     p.max_iterations = sim->max_iterations; p.sampling = (uint32_t)sim->sampling;
     p.integrator = (uint32_t)sim->integrator;
@@ -138,6 +142,7 @@ static void fill_params(const curvis_ctx* ctx, const DeviceState& d, const curvi
     p.f_delta = (float)sim->delta;
     p.d_rho2 = metric->rho * metric->rho;
     p.d_xscale = 2.0 / (3.14159265358979323846 * metric->m);
+    p.shape_tab = d.d_shape_tab;
     // below this |l| no escape test is needed in the fp32 kernel (4 steps of slack at |p_l| <= ~1.3)
     p.f_near_radius = (float)(std::fabs(sim->max_radius) - 6.0 * std::fabs(sim->delta) - 1e-3 * std::fabs(sim->max_radius));
     for (int s = 0; s < 2; ++s) {
@@ -243,6 +248,7 @@ static void release_device(DeviceState& d) {
     if (d.h_out) cudaFreeHost(d.h_out);
     if (d.d_records) cudaFree(d.d_records);
     if (d.d_cameras) cudaFree(d.d_cameras);
+    if (d.d_shape_tab) cudaFree(d.d_shape_tab);
     for (auto& ev : d.chunk_done) if (ev) cudaEventDestroy(ev);
     if (d.ev_begin) cudaEventDestroy(d.ev_begin);
     if (d.ev_end) cudaEventDestroy(d.ev_end);
@@ -282,6 +288,8 @@ extern "C" int curvis_ctx_create(const int* devices, int n_devices, curvis_ctx**
         std::memcpy(ctx->bg_inv_rot[s], ident, sizeof ident);
     }
     ctx->devs.resize(ords.size());
+    std::vector<double> shape_tab(kShapeTabIntervals * kShapeTabDoubles);
+    build_interstellar_shape_table(shape_tab.data());
     for (size_t i = 0; i < ords.size(); ++i) {
         DeviceState& d = ctx->devs[i];
         const int ord = ords[i];
@@ -299,6 +307,9 @@ extern "C" int curvis_ctx_create(const int* devices, int n_devices, curvis_ctx**
             else if ((e = cudaEventCreate(&d.ev_end)) != cudaSuccess) rc = cuda_fail(nullptr, e, "cudaEventCreate");
             else if ((e = cudaMalloc(&d.d_counters, sizeof(DeviceCounters))) != cudaSuccess) rc = cuda_fail(nullptr, e, "cudaMalloc(counters)");
             else if ((e = cudaMallocHost(&d.h_counters, sizeof(DeviceCounters))) != cudaSuccess) rc = cuda_fail(nullptr, e, "cudaMallocHost(counters)");
+            else if ((e = cudaMalloc(&d.d_shape_tab, shape_tab.size() * sizeof(double))) != cudaSuccess) rc = cuda_fail(nullptr, e, "cudaMalloc(shape table)");
+            else if ((e = cudaMemcpy(d.d_shape_tab, shape_tab.data(), shape_tab.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess)
+                rc = cuda_fail(nullptr, e, "cudaMemcpy(shape table)");
         }
         if (rc != CURVIS_OK) {
             curvis_ctx_destroy(ctx);
@@ -508,7 +519,7 @@ extern "C" int curvis_ctx_set_option(curvis_ctx* ctx, const char* key, int64_t v
     const std::string k(key);
     if (k == "kernel_variant" && value >= 0 && value <= 3) ctx->tuning.kernel_variant = (int)value;
     else if (k == "blocks_per_sm" && value >= 0 && value <= 32) ctx->tuning.blocks_per_sm = (int)value;
-    else if (k == "window" && value >= 1 && value <= 4096) ctx->tuning.window = (int)value;
+    else if (k == "window" && value >= 0 && value <= 4096) ctx->tuning.window = (int)value;
     else if (k == "fast_variant" && value >= 0 && value <= 1) ctx->tuning.fast_variant = (int)value;
     else return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "unknown option or value out of range: " + k);
     return CURVIS_OK;
@@ -526,7 +537,8 @@ extern "C" int curvis_debug_eval(curvis_ctx* ctx, int op, const double* a, const
         (!b || (e = cudaMalloc(&db, bytes ? bytes : 8)) == cudaSuccess) &&
         (e = cudaMemcpyAsync(da, a, bytes, cudaMemcpyHostToDevice, d.stream)) == cudaSuccess &&
         (!b || (e = cudaMemcpyAsync(db, b, bytes, cudaMemcpyHostToDevice, d.stream)) == cudaSuccess) &&
-        (e = launch_debug_eval(op, da, db, dout, n, d.stream)) == cudaSuccess &&
+        (e = (op == 13 || op == 14) ? launch_debug_shape(d.d_shape_tab, op - 13, da, dout, n, d.stream)
+                                    : launch_debug_eval(op, da, db, dout, n, d.stream)) == cudaSuccess &&
         (e = cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, d.stream)) == cudaSuccess)
         e = cudaStreamSynchronize(d.stream);
     if (e != cudaSuccess) rc = cuda_fail(ctx, e, "curvis_debug_eval");

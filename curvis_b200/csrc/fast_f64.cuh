@@ -64,23 +64,23 @@ __device__ __forceinline__ void sin2_sincos(const TrigRegs& tr, double x, double
 // ---- incremental trigonometry (fast_variant 1, the default of render_f64_fast.cu)
 // theta changes by d = delta * p_theta / r^2 per step, and |d| < 2^-10 on 87 % of all steps of the
 // 4K Ellis frame (< 2^-4 on 99.99 %).  Instead of a full range reduction + two degree-5 polynomials
-// per step, (sin theta, cos theta) are carried along and rotated by the small angle:
-//     sin(theta + d) = sin theta + (sin theta (cos d - 1) + cos theta sin d)
-//     cos(theta + d) = cos theta + (cos theta (cos d - 1) - sin theta sin d)
-// with sin d = d + d v S(v), cos d - 1 = v C(v), v = d*d; S (degree 2) and C (degree 3) are Remez fits
-// on |d| < 2^-4 (tools/gen_rot_coeffs.py: error 2.0e-17 relative to d, resp. 3.3e-21 absolute).
-// 13 fp64 instructions instead of 21.  The pair is re-derived from theta itself (sincos_fast) at the
-// start of every window of steps and after any step with |d| >= 2^-4, so its rounding drift is
-// bounded by one window (32 steps * ~1.5e-16) instead of growing along the ray.
+// per step, (sin theta, cos theta) are carried along and rotated by the small angle, in the
+// three-shear form of a rotation (every update in place, no temporaries):
+//     c -= t s;   s += sd c;   c -= t s;        t = tan(d/2),  sd = sin d
+// with sin d = d (1 + v S(v)) and tan(d/2) = d (1/2 + v T(v)), v = d*d; S and T are degree-2 Remez
+// fits on |d| < 2^-4 (tools/gen_rot_coeffs.py: error 2.0e-17 resp. 3.1e-16 relative to d, i.e.
+// <= 2e-17 absolute).  12 fp64 instructions instead of 21.  The pair is re-derived from theta itself
+// (sincos_fast) at the start of every window of steps and after any step with |d| >= 2^-4, so its
+// rounding drift is bounded by one window (64 steps * ~1.5e-16) instead of growing along the ray.
 static __device__ __constant__ double kRotSin[2] = {-0.16666666666666152, 0.008333333309682096};
-static __device__ __constant__ double kRotCos[3] = {-0.5, 0.04166666666666256, -0.0013888888836330506};
-static __device__ double kRotPinned[2] = {-0.00019839655223880117, 2.479943447760353e-05};   // S2, C3 (see kPinned)
+static __device__ __constant__ double kRotTan[2] = {0.04166666666674629, 0.00416666629980884};
+static __device__ double kRotPinned[2] = {-0.00019839655223880117, 0.0004218773803051587};   // S2, T2 (see kPinned)
 
 struct RotRegs {
-    double sin2, cos3;
+    double sin2, tan2;                    // leading coefficients: vector registers (see kPinned)
     __device__ __forceinline__ void load() {
         asm volatile("ld.global.f64 %0, [%1];" : "=d"(sin2) : "l"(kRotPinned));
-        asm volatile("ld.global.f64 %0, [%1];" : "=d"(cos3) : "l"(kRotPinned + 1));
+        asm volatile("ld.global.f64 %0, [%1];" : "=d"(tan2) : "l"(kRotPinned + 1));
     }
 };
 
@@ -88,16 +88,14 @@ struct RotRegs {
 __device__ __forceinline__ void rotate_sincos(const RotRegs& rr, double d, double& s, double& c) {
     const double v = d * d;
     double sp = fma(v, rr.sin2, kRotSin[1]);
-    double cp = fma(v, rr.cos3, kRotCos[2]);
+    double tp = fma(v, rr.tan2, kRotTan[1]);
     sp = fma(v, sp, kRotSin[0]);
-    cp = fma(v, cp, kRotCos[1]);
-    cp = fma(v, cp, kRotCos[0]);
-    const double sd = fma(d * v, sp, d);      // sin d
-    const double cm = v * cp;                 // cos d - 1
-    const double s1 = fma(c, sd, fma(s, cm, s));
-    const double c1 = fma(-s, sd, fma(c, cm, c));
-    s = s1;
-    c = c1;
+    tp = fma(v, tp, kRotTan[0]);
+    const double sd = d * fma(v, sp, 1.0);    // sin d
+    const double t = d * fma(v, tp, 0.5);     // tan(d/2)
+    c = fma(-t, s, c);
+    s = fma(sd, c, s);
+    c = fma(-t, s, c);
 }
 
 // d >= 0 by construction (a product of squares and a positive radius), so the high word is

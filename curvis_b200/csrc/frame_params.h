@@ -66,6 +66,8 @@ struct FrameParams {
     float f_rho, f_rho2, f_m, f_a, f_xscale, f_delta, f_near_radius, _pad2;
     // fp64 uniforms of CURVIS_PRECISION_F64_FAST (render_f64_fast.cu): rho^2 and 2/(pi*m)
     double d_rho2, d_xscale;
+    // Interstellar shape-function table of CURVIS_PRECISION_F64_FAST (shape_table.h), resident per device
+    const double2* shape_tab;
     // scene (systems.rs:70-71): [0] = background_positive, [1] = background_negative
     Background bg[2];
     // outputs: RGB8 rows of the tile (packed, row-major), optional per-ray records, counters

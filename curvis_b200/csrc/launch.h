@@ -11,7 +11,7 @@ struct LaunchTuning {
     int kernel_variant = 3;  // 0 plain operators + CUDA sincos (round-1 v0); 1 unguarded IEEE sequences + CUDA sincos;
                              // 2 + in-kernel sincos; 3 (default) lean loop: integer-pipe guards, gated escape test
     int blocks_per_sm = 0;   // 0 = occupancy maximum
-    int window = 32;         // Euler steps between two refill points of a warp
+    int window = 0;          // Euler steps between two refill points of a warp; 0 = auto (32; 64 in F64_FAST)
     int fast_variant = 1;    // CURVIS_PRECISION_F64_FAST: 0 sin/cos from theta every step; 1 (default) (sin, cos) carried and
                              // rotated by the step's small dtheta, re-derived from theta once per window
 };
@@ -34,6 +34,10 @@ cudaError_t launch_debug_bilinear(const Background& bg, const double* fx, const 
 cudaError_t launch_debug_eval(int op, const double* a, const double* b, double* out, size_t n, cudaStream_t stream);
 
 
+
+// F(x) (which = 0) / G(x) (which = 1) of the Interstellar shape-function table as the fast kernel
+// evaluates them (test hook, curvis_debug_eval ops 13 / 14).  render_f64_fast.cu.
+cudaError_t launch_debug_shape(const double2* tab, int which, const double* x, double* out, size_t n, cudaStream_t stream);
 
 // FMA-only micro-kernels used as the measured compute-roofline denominator (peak_kernels.cu).
 cudaError_t measure_fma_peak(int sm_count, cudaStream_t stream, double* fp64_tflops, double* fp32_tflops);

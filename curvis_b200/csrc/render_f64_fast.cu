@@ -29,6 +29,7 @@
 #include "geodesic_f64.cuh"
 #include "fast_f64.cuh"
 #include "launch.h"
+#include "shape_table.h"
 
 namespace curvis {
 
@@ -53,6 +54,20 @@ struct FastEllis {   // metrics.rs:417-421 : r^2 = rho^2 + l^2, r' = l/r  =>  r'
         fd = l * (u * ud);
         return true;
     }
+    // The same quantities split around the reciprocal (fast_variant 1): prepare() returns the
+    // divisor d = r^2 sin^2, finish() turns y0 = 1/d into w, u, v and f = r'/r^3 (no delta: the
+    // momenta are pre-scaled, see fast_window_scaled).
+    struct Pre { double r2; };
+    static __device__ __forceinline__ double prepare(const FrameParams& p, double l, double s2, Pre& pre) {
+        pre.r2 = fma(l, l, p.d_rho2);
+        return pre.r2 * s2;
+    }
+    static __device__ __forceinline__ void finish(const Pre& pre, double y0, double l, double s2, double& w, double& u, double& v, double& f) {
+        w = y0;
+        u = w * s2;
+        v = w * pre.r2;
+        f = l * (u * u);
+    }
 };
 
 // r(l) > 0 and r'(l) given: one reciprocal of r*sin^2 yields 1/r and 1/sin^2.
@@ -69,6 +84,41 @@ __device__ __forceinline__ bool factors_from_r(const FrameParams& p, double r, d
     return true;
 }
 
+struct PreFromR { double r, rp; };
+__device__ __forceinline__ void finish_from_r(const PreFromR& pre, double y0, double s2, double& w, double& u, double& v, double& f) {
+    const double y = y0 * s2;      // 1/r
+    v = y0 * pre.r;                // 1/sin^2
+    u = y * y;
+    w = u * v;
+    f = pre.rp * (y * u);          // r'/r^3
+}
+
+// F(x) = x atan x - ln(1+x^2)/2 and G(x) = atan x for x > 0 from the piecewise degree-5 table
+// (shape_table.h): interval index = a shift of x's high word, t = x - midpoint (exact), two Horner
+// chains on coefficients fetched with six 128-bit loads (neighbouring rays sit in the same or the
+// next interval, so the loads are L1 hits).  Outside [2^-10, 2^16): the library functions.
+__device__ __noinline__ double2 shape_fg_library(double x) {   // x outside the table: rare, out of line
+    const double G = atan(x);
+    return make_double2(fma(x, G, -0.5 * log(fma(x, x, 1.0))), G);
+}
+
+__device__ __forceinline__ void shape_fg(const FrameParams& p, double x, double& F, double& G) {
+    const unsigned hi = (unsigned)__double2hiint(x);
+    const unsigned idx = (hi >> kShapeTabShift) - kShapeTabBase;
+    if (idx < (unsigned)kShapeTabIntervals) {
+        const double c = __hiloint2double((int)((hi & ~((1u << kShapeTabShift) - 1u)) | (1u << (kShapeTabShift - 1))), 0);
+        const double t = x - c;
+        const double2* e = p.shape_tab + (size_t)idx * (kShapeTabDoubles / 2);
+        const double2 a01 = __ldg(e), a23 = __ldg(e + 1), a45 = __ldg(e + 2);
+        const double2 b01 = __ldg(e + 3), b23 = __ldg(e + 4), b45 = __ldg(e + 5);
+        F = fma(t, fma(t, fma(t, fma(t, fma(t, a45.y, a45.x), a23.y), a23.x), a01.y), a01.x);
+        G = fma(t, fma(t, fma(t, fma(t, fma(t, b45.y, b45.x), b23.y), b23.x), b01.y), b01.x);
+    } else {
+        const double2 fg = shape_fg_library(x);
+        F = fg.x; G = fg.y;
+    }
+}
+
 struct FastInterstellar {   // metrics.rs:461-485 with the uniform divisor pi*m folded into d_xscale
     using Shape64 = ShapeInterstellar;
     static __device__ __forceinline__ bool factors(const FrameParams& p, double l, double s2, double& w, double& u, double& v, double& ud, double& fd) {
@@ -76,11 +126,28 @@ struct FastInterstellar {   // metrics.rs:461-485 with the uniform divisor pi*m 
         double r = p.rho, rp = 0.0;
         if (al > p.a) {
             const double x = (al - p.a) * p.d_xscale;
-            const double at = atan(x);
-            r = fma(p.m, fma(x, at, -0.5 * log(fma(x, x, 1.0))), p.rho);
-            rp = copysign((2.0 / CURVIS_PI) * at, l);
+            double F, G;
+            shape_fg(p, x, F, G);
+            r = fma(p.m, F, p.rho);
+            rp = copysign((2.0 / CURVIS_PI) * G, l);
         }
         return factors_from_r(p, r, rp, s2, w, u, v, ud, fd);
+    }
+    using Pre = PreFromR;
+    static __device__ __forceinline__ double prepare(const FrameParams& p, double l, double s2, Pre& pre) {
+        const double al = fabs(l);
+        pre.r = p.rho; pre.rp = 0.0;
+        if (al > p.a) {
+            const double x = (al - p.a) * p.d_xscale;
+            double F, G;
+            shape_fg(p, x, F, G);
+            pre.r = fma(p.m, F, p.rho);
+            pre.rp = copysign((2.0 / CURVIS_PI) * G, l);
+        }
+        return pre.r * s2;
+    }
+    static __device__ __forceinline__ void finish(const Pre& pre, double y0, double, double s2, double& w, double& u, double& v, double& f) {
+        finish_from_r(pre, y0, s2, w, u, v, f);
     }
 };
 
@@ -88,6 +155,14 @@ struct FastFlat {   // metrics.rs:501-505: r = l, r' = 1 (r may be negative: tak
     using Shape64 = ShapeFlat;
     static __device__ __forceinline__ bool factors(const FrameParams& p, double l, double s2, double& w, double& u, double& v, double& ud, double& fd) {
         return factors_from_r(p, l, 1.0, s2, w, u, v, ud, fd);
+    }
+    using Pre = PreFromR;
+    static __device__ __forceinline__ double prepare(const FrameParams&, double l, double s2, Pre& pre) {
+        pre.r = l; pre.rp = 1.0;
+        return l * s2;
+    }
+    static __device__ __forceinline__ void finish(const Pre& pre, double y0, double, double s2, double& w, double& u, double& v, double& f) {
+        finish_from_r(pre, y0, s2, w, u, v, f);
     }
 };
 
@@ -109,33 +184,58 @@ __device__ __forceinline__ bool fast_step(const FrameParams& p, const TrigRegs& 
     return true;
 }
 
-// The same step with (sin theta, cos theta) carried as state (fast_f64.cuh: rotate_sincos): the
-// pair is rotated by the step's dtheta unconditionally; the caller re-derives it from theta when
-// |dtheta| >= 2^-4 (`dth` is returned for that test).  Returns false, leaving the state untouched,
-// when an operand is outside the safe window.
+// fast_variant 1 (default): up to n steps of one window with
+//   * (sin theta, cos theta) carried along and rotated by the step's dtheta (fast_f64.cuh), re-derived
+//     from theta at the start of the window and after a step with |dtheta| >= 2^-4;
+//   * the momenta pre-scaled by delta, P = delta * p (the caller keeps q.pl, q.pth, q.pph, q.pph2 in
+//     that form).  The geodesic equations are homogeneous in the momenta — this is the same Euler
+//     iteration with the affine parameter rescaled to unit steps — and delta disappears from the loop:
+//         l += P_l;  theta += P_theta u;  phi += P_phi w;
+//         P_l += (P_theta^2 + P_phi^2 v) r'/r^3;  P_theta += P_phi^2 v (sin cos) w
+//     (u = 1/r^2, v = 1/sin^2, w = u v): 33 fp64 instructions per Ellis step instead of 41;
+//   * ONE exit branch per step: the four rarely-true conditions (step budget used up, |l| within reach
+//     of the escape radius or NaN, |dtheta| too large for the rotation, next divisor outside the safe
+//     window) are OR-ed on the integer pipe and sorted out after the loop.
+// Returns the number of steps taken; `stop` = the ray left the radius (systems.rs:129-134), `slow` =
+// the remaining steps of the window need the parity step.
 template <class Fast>
-__device__ __forceinline__ bool fast_step_rot(const FrameParams& p, const RotRegs& rr, Ray& q, double& s, double& c, double& dth) {
-    const double s2 = s * s, cs = s * c;
-    double w, u, v, ud, fd;
-    if (!Fast::factors(p, q.l, s2, w, u, v, ud, fd)) return false;
-    dth = q.pth * ud;                                       // :239 times delta
-    const double pv = q.pph2 * v;                           // p_phi^2 / sin^2
-    const double b2 = fma(q.pth, q.pth, pv);                // metrics.rs:257
-    const double wd = w * p.delta;
-    q.l = fma(q.pl, p.delta, q.l);                          // :238, :295
-    q.th = q.th + dth;
-    q.ph = fma(q.pph, wd, q.ph);                            // :240
-    q.pl = fma(b2, fd, q.pl);                               // :261, :296
-    q.pth = fma(pv * cs, wd, q.pth);                        // :262
-    rotate_sincos(rr, dth, s, c);
-    return true;
-}
-
-// (sin, cos)(theta) for the rare re-derivation inside the loop; out of line, by value.
-__device__ __noinline__ double2 sincos_pair(double th) {
-    double s, c;
-    sincos_fast(th, s, c);
-    return make_double2(s, c);
+__device__ __forceinline__ uint32_t fast_window_scaled(const FrameParams& p, const RotRegs& rr, Ray& q, uint32_t n, unsigned gate,
+                                                       double R, bool& stop, bool& slow) {
+    uint32_t k = 0;
+    for (;;) {
+        if (abs_hi(q.th) >= pow2_hi(30)) { slow = true; return k; }
+        double sn, cn;
+        sincos_fast(q.th, sn, cn);
+        typename Fast::Pre pre;
+        double s2 = sn * sn;
+        double d = Fast::prepare(p, q.l, s2, pre);
+        if (!in_window_nonneg(d)) { slow = true; return k; }
+        double dth;
+        for (;;) {
+            double w, u, v, f;
+            Fast::finish(pre, rcp_1ulp(d), q.l, s2, w, u, v, f);
+            const double cs = sn * cn;
+            dth = q.pth * u;                                    // metrics.rs:239
+            const double pv = q.pph2 * v;                       // p_phi^2 / sin^2
+            const double b2 = fma(q.pth, q.pth, pv);            // :257
+            q.l = q.l + q.pl;                                   // :238, :295
+            q.th = q.th + dth;
+            q.ph = fma(q.pph, w, q.ph);                         // :240
+            q.pl = fma(b2, f, q.pl);                            // :261, :296
+            q.pth = fma(pv * cs, w, q.pth);                     // :262
+            rotate_sincos(rr, dth, sn, cn);
+            ++k;
+            s2 = sn * sn;
+            d = Fast::prepare(p, q.l, s2, pre);
+            if ((k >= n) | (abs_hi(q.l) >= gate) | (abs_hi(dth) >= pow2_hi(-4)) | !in_window_nonneg(d)) break;
+        }
+        if (abs_hi(q.l) >= gate) {
+            if ((q.l > R) || (q.l < -R) || (q.l != q.l)) { stop = true; return k; }       // systems.rs:129-134
+        }
+        if (k >= n) return k;
+        if (!(abs_hi(dth) >= pow2_hi(-4)) && !in_window_nonneg(d)) { slow = true; return k; }
+        // |dtheta| too large for the rotation (or a false alarm of the radius gate): re-derive (sin, cos) and go on
+    }
 }
 
 // Parity steps for a lane whose operands left the safe window: plain operators, reference
@@ -159,6 +259,21 @@ __device__ __noinline__ SlowResult parity_steps(const FrameParams& p, Ray q, uin
     SlowResult r;
     r.l = q.l; r.th = q.th; r.ph = q.ph; r.pl = q.pl; r.pth = q.pth; r.steps = k; r.stop = stop;
     return r;
+}
+
+// The photon of fast_variant 1 (momenta scaled by delta) in the reference's units, for the parity
+// steps and the epilogue.  p_phi is conserved, so it is regenerated from the ray index rather than
+// divided back (bit-exact, and it spares the hot loop two registers); a ray that has not moved is
+// regenerated whole.
+__device__ __noinline__ Ray unscaled_ray(const FrameParams& p, const Ray& q, unsigned long long ray, unsigned long long tile_rays, bool untouched) {
+    Ray o;
+    new_photon_for_ray(p, ray, tile_rays, o);
+    if (!untouched) {
+        o.l = q.l; o.th = q.th; o.ph = q.ph;
+        o.pl = q.pl / p.delta;
+        o.pth = q.pth / p.delta;
+    }
+    return o;
 }
 
 template <class Fast, int Variant>
@@ -186,7 +301,12 @@ __global__ void __launch_bounds__(kBlockFast) render_rows_f64_fast(const __grid_
     for (;;) {
         if (state == 2) {
             const int side = (q.l > R) ? 1 : ((q.l < -R) ? -1 : 0);   // systems.rs:129-134 on the final state
-            finish_ray<Shape64, TrigFast>(p, q, side, p.max_iterations - remaining, ray, tally);
+            if (Variant == 1) {
+                const Ray qe = unscaled_ray(p, q, ray, tile_rays, remaining == p.max_iterations);
+                finish_ray<Shape64, TrigFast>(p, qe, side, p.max_iterations - remaining, ray, tally);
+            } else {
+                finish_ray<Shape64, TrigFast>(p, q, side, p.max_iterations - remaining, ray, tally);
+            }
             state = 0;
         }
 
@@ -202,6 +322,10 @@ __global__ void __launch_bounds__(kBlockFast) render_rows_f64_fast(const __grid_
                     if (idx < launch_rays) {
                         ray = idx;
                         new_photon_for_ray(p, idx, tile_rays, q);
+                        if (Variant == 1) {            // momenta pre-scaled by delta (fast_window_scaled)
+                            q.pl = q.pl * p.delta; q.pth = q.pth * p.delta; q.pph = q.pph * p.delta;
+                            q.pph2 = q.pph * q.pph;
+                        }
                         remaining = p.max_iterations;
                         state = (remaining == 0) ? 2 : 1;
                     }
@@ -229,28 +353,11 @@ __global__ void __launch_bounds__(kBlockFast) render_rows_f64_fast(const __grid_
                     }
                 } while (k < n);
             }
-            if (!slow && Variant == 1) {
-                double sn, cn, dth;
-                sincos_fast(q.th, sn, cn);                                       // once per window, then rotated
-                do {
-                    if (!fast_step_rot<Fast>(p, rr, q, sn, cn, dth)) { slow = true; break; }
-                    ++k;
-                    // one rarely-taken branch for both per-step tests: near the escape radius (or NaN), and
-                    // a dtheta too large for the rotation (or NaN)
-                    const bool big = abs_hi(dth) >= pow2_hi(-4);
-                    if (big || abs_hi(q.l) >= gate) {
-                        if ((q.l > R) || (q.l < -R) || (q.l != q.l)) { stop = true; break; }   // :129-134
-                        if (big) {
-                            if (abs_hi(q.th) >= pow2_hi(30)) { slow = (k < n); break; }
-                            const double2 sc = sincos_pair(q.th);
-                            sn = sc.x; cn = sc.y;
-                        }
-                    }
-                } while (k < n);
-            }
+            if (!slow && Variant == 1) k = fast_window_scaled<Fast>(p, rr, q, n, gate, R, stop, slow);
             if (slow) {
-                const SlowResult sr = parity_steps<Shape64>(p, q, n - k, gate);
+                const SlowResult sr = parity_steps<Shape64>(p, Variant == 1 ? unscaled_ray(p, q, ray, tile_rays, false) : q, n - k, gate);
                 q.l = sr.l; q.th = sr.th; q.ph = sr.ph; q.pl = sr.pl; q.pth = sr.pth;
+                if (Variant == 1) { q.pl = q.pl * p.delta; q.pth = q.pth * p.delta; }
                 k += sr.steps;
                 stop = sr.stop;
             }
@@ -286,11 +393,29 @@ cudaError_t launch_fast_variant(const FrameParams& p, int sm_count, int blocks_p
 
 template <class Fast>
 cudaError_t launch_fast(const FrameParams& p, const LaunchTuning& t, int sm_count, cudaStream_t stream) {
-    if (t.fast_variant == 0) return launch_fast_variant<Fast, 0>(p, sm_count, t.blocks_per_sm, stream);   // trigonometry from theta every step
+    // variant 1 scales the momenta by delta: it needs a finite, non-zero step of ordinary magnitude
+    const double ad = p.delta < 0.0 ? -p.delta : p.delta;
+    if (t.fast_variant == 0 || !(ad >= 0x1p-100 && ad <= 0x1p100)) return launch_fast_variant<Fast, 0>(p, sm_count, t.blocks_per_sm, stream);   // trigonometry from theta every step
     return launch_fast_variant<Fast, 1>(p, sm_count, t.blocks_per_sm, stream);                            // default: rotated (sin, cos)
 }
 
 }  // namespace
+
+__global__ void debug_shape_kernel(const double2* tab, int which, const double* x, double* out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    FrameParams p;
+    p.shape_tab = tab;
+    double F, G;
+    shape_fg(p, x[i], F, G);
+    out[i] = which ? G : F;
+}
+
+cudaError_t launch_debug_shape(const double2* tab, int which, const double* x, double* out, size_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    debug_shape_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(tab, which, x, out, n);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_render_f64_fast(const FrameParams& p, int metric_kind, const LaunchTuning& t, int sm_count, cudaStream_t stream) {
     switch (metric_kind) {

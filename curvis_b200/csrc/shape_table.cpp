@@ -1,0 +1,95 @@
+// shape_table.cpp — host-side generation of the table described in shape_table.h (x87 long double:
+// 64-bit significand, glibc atanl / log1pl).
+#include "shape_table.h"
+#include <cmath>
+
+namespace curvis {
+
+namespace {
+
+constexpr int N = kShapeTabDegree + 1;
+const long double kPiL = 3.14159265358979323846264338327950288L;
+
+long double shape_f(long double x) { return x * atanl(x) - 0.5L * log1pl(x * x); }
+long double shape_g(long double x) { return atanl(x); }
+
+// Monomial coefficients (in tau = t / w, |tau| <= 1) of the degree-(N-1) interpolant of f through
+// the N Chebyshev nodes of [c - w, c + w]: Chebyshev coefficients by the discrete cosine sums,
+// then the T_j -> monomial recurrence.
+void fit(long double (*f)(long double), long double c, long double w, long double mono[N]) {
+    long double fv[N], cj[N];
+    for (int k = 0; k < N; ++k) fv[k] = f(c + w * cosl(kPiL * (2 * k + 1) / (2 * N)));
+    for (int j = 0; j < N; ++j) {
+        long double s = 0.0L;
+        for (int k = 0; k < N; ++k) s += fv[k] * cosl(j * kPiL * (2 * k + 1) / (2 * N));
+        cj[j] = s * 2.0L / N;
+    }
+    cj[0] *= 0.5L;
+    long double T[N][N] = {};
+    T[0][0] = 1.0L;
+    if (N > 1) T[1][1] = 1.0L;
+    for (int j = 2; j < N; ++j)
+        for (int k = 0; k < N; ++k) T[j][k] = (k > 0 ? 2.0L * T[j - 1][k - 1] : 0.0L) - T[j - 2][k];
+    for (int k = 0; k < N; ++k) {
+        long double s = 0.0L;
+        for (int j = 0; j < N; ++j) s += cj[j] * T[j][k];
+        mono[k] = s;
+    }
+}
+
+}  // namespace
+
+void build_interstellar_shape_table(double* out) {
+    const int per_binade = 1 << kShapeTabK;
+    size_t idx = 0;
+    for (int e = kShapeTabEmin; e < kShapeTabEmax; ++e) {
+        const long double x0 = ldexpl(1.0L, e);
+        const long double w = ldexpl(1.0L, e - kShapeTabK - 1);        // half width: a power of two
+        for (int j = 0; j < per_binade; ++j, ++idx) {
+            const long double c = x0 + (2 * j + 1) * w;
+            long double mf[N], mg[N];
+            fit(shape_f, c, w, mf);
+            fit(shape_g, c, w, mg);
+            double* o = out + idx * kShapeTabDoubles;
+            for (int k = 0; k < N; ++k) {                              // tau^k = t^k / w^k, exact scaling
+                o[k] = (double)ldexpl(mf[k], -k * (e - kShapeTabK - 1));
+                o[N + k] = (double)ldexpl(mg[k], -k * (e - kShapeTabK - 1));
+            }
+        }
+    }
+}
+
+}  // namespace curvis
+
+// Test hook (include/curvis_gpu.h): the host-built table evaluated on the host exactly as the kernel
+// evaluates it (index from the high word, exact t, two fma Horner chains).  No GPU involved; it lets
+// the CPU test-suite check the generator.  Returns 0 when x is outside the table's range.
+extern "C" int curvis_debug_shape_table_host(const double* x, double* f, double* g, size_t n) {
+    using namespace curvis;
+    static double* table = nullptr;
+    if (!table) {
+        double* t = new double[kShapeTabIntervals * kShapeTabDoubles];
+        build_interstellar_shape_table(t);
+        table = t;
+    }
+    int all = 1;
+    for (size_t i = 0; i < n; ++i) {
+        unsigned long long bits;
+        __builtin_memcpy(&bits, &x[i], 8);
+        const unsigned hi = (unsigned)(bits >> 32);
+        const unsigned idx = (hi >> kShapeTabShift) - kShapeTabBase;
+        if (idx >= (unsigned)kShapeTabIntervals) { f[i] = g[i] = NAN; all = 0; continue; }
+        const unsigned long long cbits = (unsigned long long)((hi & ~((1u << kShapeTabShift) - 1u)) | (1u << (kShapeTabShift - 1))) << 32;
+        double c;
+        __builtin_memcpy(&c, &cbits, 8);
+        const double t = x[i] - c;
+        const double* a = table + (size_t)idx * kShapeTabDoubles;
+        double F = a[kShapeTabDegree], G = a[kShapeTabDoubles - 1];
+        for (int k = kShapeTabDegree - 1; k >= 0; --k) {
+            F = fma(t, F, a[k]);
+            G = fma(t, G, a[kShapeTabDegree + 1 + k]);
+        }
+        f[i] = F; g[i] = G;
+    }
+    return all;
+}

@@ -277,15 +277,26 @@ int curvis_measure_fma_peak(curvis_ctx* ctx, double* fp64_tflops, double* fp32_t
  *                     sincos; 2 unguarded IEEE sequences + in-kernel sincos; 3 (default) the same
  *                     arithmetic in the lean loop (integer-pipe guards, gated escape test)
  *   "blocks_per_sm":  resident CTAs per SM of the persistent grid (0 = occupancy maximum)
- *   "window":         Euler steps between two refill points of a warp (default 32)        */
+ *   "window":         Euler steps between two refill points of a warp (0 = default: 32, and 64 for
+ *                     CURVIS_PRECISION_F64_FAST)
+ *   "fast_variant":   CURVIS_PRECISION_F64_FAST only: 0 sin/cos from theta every step; 1 (default)
+ *                     (sin theta, cos theta) carried along and rotated by the step's small dtheta,
+ *                     re-derived from theta once per window (results agree to ~1e-13, same frames) */
 int curvis_ctx_set_option(curvis_ctx* ctx, const char* key, int64_t value);
 
 /* Op-level test hook: out[i] = op(a[i], b[i]) evaluated on the device (host pointers).
  *   0 rcp_rn_unguarded(a)  1 div_rn_unguarded(a,b)  2 sqrt_rn_unguarded(a)
  *   3 / 4 sin / cos of the in-kernel sincos fast path   5 / 6 the same with its large-argument fallback
  *   7 a/b   8 sqrt(a)   9 1/a   (the compiler's IEEE operators, for reference)
- *   10 the <= 1 ulp reciprocal of CURVIS_PRECISION_F64_FAST   11 / 12 its sin^2(a) / sin(a)cos(a)   */
+ *   10 the <= 1 ulp reciprocal of CURVIS_PRECISION_F64_FAST   11 / 12 its sin^2(a) / sin(a)cos(a)
+ *   13 / 14 its Interstellar shape functions a atan a - ln(1 + a^2)/2 and atan a (table, a > 0)   */
 int curvis_debug_eval(curvis_ctx* ctx, int op, const double* a, const double* b, double* out, size_t n);
+
+/* Test hook, host only (no GPU needed): the piecewise-polynomial table of the Interstellar shape
+ * functions that CURVIS_PRECISION_F64_FAST uploads to every device (csrc/shape_table.h), evaluated on
+ * the host with the kernel's arithmetic: f[i] = x atan x - ln(1 + x^2)/2, g[i] = atan x.  Returns 1
+ * when every x[i] lay inside the table's range [2^-10, 2^16), else 0 (those entries are NaN). */
+int curvis_debug_shape_table_host(const double* x, double* f, double* g, size_t n);
 
 /* Test hook of CURVIS_SAMPLING_BILINEAR: the fp32 tap of background `side` at explicit continuous
  * texel coordinates (fx in [0,W), fy in [0,H]; texel centres at integer + 0.5; wrap in x, clamp in

@@ -145,3 +145,32 @@ def test_spherical_image_conversions(lib):
     assert (luma.rgba8[..., :3] == 9).all()
     with pytest.raises(TypeError):
         cv.SphericalImage(np.zeros((2, 2, 3), np.float32))
+
+
+def test_interstellar_shape_table_host(lib):
+    """The piecewise degree-5 table of F(x) = x atan x - ln(1+x^2)/2 and G(x) = atan x that
+    CURVIS_PRECISION_F64_FAST uploads (csrc/shape_table.h; replaces the atan + ln of
+    InterstellarMetric::r / r_derivative, reference src/metrics.rs:461-485), evaluated on the host
+    with the kernel's arithmetic, against x87 long double: <= 2 ulp, i.e. the class of a libm."""
+    import ctypes as C
+    import numpy as np
+    rng = np.random.default_rng(20251017)
+    edges = np.ldexp(1.0, np.arange(-10, 17))
+    x = np.concatenate([np.exp(rng.uniform(np.log(2.0 ** -10), np.log(2.0 ** 16), 400_000)),
+                        edges[:-1], np.nextafter(edges[1:], 0.0), np.nextafter(edges[:-1], np.inf),
+                        np.ldexp(1.0 + np.arange(128) / 128.0, 3), np.nextafter(np.ldexp(1.0 + np.arange(1, 129) / 128.0, 3), 0.0)])
+    f, g = np.empty_like(x), np.empty_like(x)
+    dp = C.POINTER(C.c_double)
+    assert lib.curvis_debug_shape_table_host(x.ctypes.data_as(dp), f.ctypes.data_as(dp), g.ctypes.data_as(dp), x.size) == 1
+    xl = x.astype(np.longdouble)
+    want_f, want_g = xl * np.arctan(xl) - np.log1p(xl * xl) / 2, np.arctan(xl)
+
+    def ulps(got, want):
+        return np.abs((got.astype(np.longdouble) - want) / np.spacing(np.abs(want.astype(np.float64))).astype(np.longdouble)).astype(np.float64)
+
+    assert ulps(f, want_f).max() <= 2.0
+    assert ulps(g, want_g).max() <= 2.0
+    out = np.array([0.0, 2.0 ** -11, 2.0 ** 16, np.inf, np.nan, -1.0])
+    fo, go = np.empty_like(out), np.empty_like(out)
+    assert lib.curvis_debug_shape_table_host(out.ctypes.data_as(dp), fo.ctypes.data_as(dp), go.ctypes.data_as(dp), out.size) == 0
+    assert np.isnan(fo).all() and np.isnan(go).all()

@@ -51,6 +51,57 @@ def test_primitives_accuracy(gpu_ctx):
     assert np.abs(cs[~away] - want[~away].astype(np.float64)).max() <= 1e-18 + 4e-16 * np.abs(th[~away]).max()
 
 
+def test_interstellar_shape_table_on_device(gpu_ctx):
+    """F(x) = x atan x - ln(1+x^2)/2 and G(x) = atan x as the fast kernel evaluates them (table inside
+    [2^-10, 2^16), library functions outside): <= 2 ulp inside, <= 6 ulp of the composition outside;
+    bit-identical to the host evaluation of the same table."""
+    import ctypes as C
+    from curvis_b200 import _abi
+    rng = np.random.default_rng(7)
+    x = np.concatenate([np.exp(rng.uniform(np.log(2.0 ** -10), np.log(2.0 ** 16), 1_000_000)), np.ldexp(1.0, np.arange(-10, 16))])
+    xl = x.astype(np.longdouble)
+    f, g = gpu_ctx.debug_eval(13, x), gpu_ctx.debug_eval(14, x)
+    assert _ulps(f, xl * np.arctan(xl) - np.log1p(xl * xl) / 2).max() <= 2.0
+    assert _ulps(g, np.arctan(xl)).max() <= 2.0
+    hf, hg = np.empty_like(x), np.empty_like(x)
+    dp = C.POINTER(C.c_double)
+    assert _abi.load_library().curvis_debug_shape_table_host(x.ctypes.data_as(dp), hf.ctypes.data_as(dp), hg.ctypes.data_as(dp), x.size) == 1
+    assert f.tobytes() == hf.tobytes() and g.tobytes() == hg.tobytes()
+    # outside the table: the reference's own expression x atan x - ln(1 + x*x)/2 through the library
+    # functions.  For tiny x its 1 + x*x rounds, so the bar there is absolute (r = rho + m F only
+    # sees F's absolute error); for huge x it is relative.
+    tiny, huge = np.exp(rng.uniform(np.log(1e-6), np.log(2.0 ** -10), 10_000)), np.exp(rng.uniform(np.log(2.0 ** 16), np.log(1e12), 10_000))
+    tl, hl = tiny.astype(np.longdouble), huge.astype(np.longdouble)
+    assert np.abs(gpu_ctx.debug_eval(13, tiny).astype(np.longdouble) - (tl * np.arctan(tl) - np.log1p(tl * tl) / 2)).max() <= 2.3e-16
+    assert _ulps(gpu_ctx.debug_eval(13, huge), hl * np.arctan(hl) - np.log1p(hl * hl) / 2).max() <= 6.0
+    assert _ulps(gpu_ctx.debug_eval(14, np.concatenate([tiny, huge])), np.arctan(np.concatenate([tl, hl]))).max() <= 2.0
+
+
+def test_fast_variants_render_the_same_frames(gpu_ctx):
+    """ctx option "fast_variant": (sin theta, cos theta) rotated by the step's dtheta (1, default)
+    against sin/cos from theta every step (0) — same RGB8, sides, step counts and texels."""
+    import curvis_b200 as cv
+    from curvis_b200 import _abi, scenes
+    bp, bn = scenes.decodable_background(4096, 2048), scenes.decodable_background(4096, 2048, True)
+    cases = [(cv.EllisMetric(1.0), (40000, 100.0, 0.05)), (cv.InterstellarMetric(0.1, 1e-4, 1.0), (40000, 100.0, 0.05)),
+             (cv.FlatSphericalMetric(), (4000, 100.0, 0.05)), (cv.EllisMetric(1.0), (200, 10.0, 0.1))]
+    W, H = 320, 180
+    cam = cv.Camera(scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP, 15.0, 43.0, W, H)
+    try:
+        for metric, sim in cases:
+            sysm = cv.RelativisticSystem(metric, cv.SphericalImage(bp), cv.SphericalImage(bn), cam, context=gpu_ctx)
+            out = {}
+            for variant in (0, 1):
+                gpu_ctx.set_option("fast_variant", variant)
+                out[variant] = sysm.render_rows(*sim, 0, H, with_records=True, precision=_abi.PRECISION_F64_FAST)
+            (f0, r0), (f1, r1) = out[0], out[1]
+            bad = (f0 != f1).any(axis=2) | (r0["side"] != r1["side"]) | (r0["steps"] != r1["steps"]) | \
+                  (r0["texel_x"] != r1["texel_x"]) | (r0["texel_y"] != r1["texel_y"])
+            assert int(bad.sum()) <= int(MAX_DIFFERING_FRACTION * W * H), (type(metric).__name__, sim, int(bad.sum()))
+    finally:
+        gpu_ctx.set_option("fast_variant", 1)
+
+
 def _compare_with_oracle(frame, rec, ref_frame, ref_rec, name):
     n = ref_rec.size
     bad = ((frame != ref_frame).any(axis=2) | (rec["side"] != ref_rec["side"]) | (rec["steps"] != ref_rec["steps"]) |

@@ -34,7 +34,7 @@ for kind in kinds:
                 differing_pixels=int(len(xs)), first=[(int(a), int(b)) for a, b in zip(xs[:8], ys[:8])],
                 total_steps_equal=bool(st["total_steps"] == ref_stats["total_steps"]),
                 counters_equal=all(st[k] == ref_stats[k] for k in ("n_positive", "n_negative", "n_not_escaped", "n_clamped")))
-    ctx.set_option("window", 32)
+    ctx.set_option("window", 0)
     ctx.set_option("fast_variant", 1)
     print(json.dumps(res), flush=True)
     out.append(res)
