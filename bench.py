@@ -64,8 +64,9 @@ def workload_config(args, n):
                     f"two {BG_W}x{BG_H} RGBA8 backgrounds",
         "frames_per_step": n,
         "precision": {"f64_fast": "CURVIS_PRECISION_F64_FAST: fp64, same Euler scheme, right-hand side regrouped around one "
-                                  "reciprocal per step (each operation <= 1 ulp; frame checked against the operation-for-operation "
-                                  "kernel in `parity_check`)",
+                                  "reciprocal per step, momenta pre-scaled by the step, (sin, cos) of theta carried and rotated by the "
+                                  "step's dtheta (each operation <= 1 ulp; frame checked against the operation-for-operation kernel in "
+                                  "`parity_check`)",
                       "f64": "CURVIS_PRECISION_F64: fp64, one rounding per reference operation"}[args.precision],
         "parallelism": "single GPU" if n == 1 else f"{n} frames/step (camera path), each row-tiled over {n} ranks: one batched launch per rank + one NCCL all-gather of row tiles per frame",
         "l2": "256 MiB device buffer rewritten between steps inside the timed region (L2 flush); the kernel is ALU-bound",
@@ -225,7 +226,7 @@ def run_b200(args):
     background_upload_ms = (time.perf_counter() - t_up0) * 1e3
     sim = (scenes.DEFAULT_MAX_ITERATIONS, scenes.DEFAULT_ESCAPE_RADIUS, scenes.DEFAULT_STEP)
     PREC = {"f64_fast": _abi.PRECISION_F64_FAST, "f64": _abi.PRECISION_F64}[args.precision]
-    KERNEL = {"f64_fast": "render_rows_f64_fast<FastEllis>", "f64": "render_rows_f64_lean<ShapeEllis>"}[args.precision]
+    KERNEL = {"f64_fast": "render_rows_f64_fast<FastEllis, 1>", "f64": "render_rows_f64_lean<ShapeEllis>"}[args.precision]
 
     stream = torch.cuda.current_stream()
     frames = [torch.empty(Ht * Wd * 3, dtype=torch.uint8, device=dev) for _ in range(n)]   # complete frames
