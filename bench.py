@@ -312,7 +312,9 @@ def run_b200(args):
     tile_steps_local = st["total_steps"]
 
     # ---- e2e through the host-buffer C-ABI call (per-frame parameters in, RGB8 out to host)
-    host_frames = [torch.empty(Ht * Wd * 3, dtype=torch.uint8).pin_memory() for _ in range(n)] if (n > 1 and rank == 0) else None
+    # N > 1: rank r owns frame r of the step's batch (the frame it would encode / write): it copies that one
+    # complete frame to its pinned host buffer, so the step's N read-backs run on N PCIe links in parallel
+    host_frames = [torch.empty(Ht * Wd * 3, dtype=torch.uint8).pin_memory()] if n > 1 else None
     param_bytes = (C_sizeof(_abi.CurvisMetric) + C_sizeof(_abi.CurvisCamera) + C_sizeof(_abi.CurvisSim))
 
     # the caller's frame buffer, reused every step and registered once with curvis_host_register (page-locked, as
@@ -329,8 +331,8 @@ def run_b200(args):
             system.render_frames_device(cameras, *sim, row_begin, row_end, tiles.data_ptr(), stream.cuda_stream, precision=PREC)
             for f in range(n):
                 dist.all_gather_into_tensor(frames[f], tiles[f * tile_bytes:(f + 1) * tile_bytes])
-                if rank == 0:
-                    host_frames[f].copy_(frames[f], non_blocking=True)
+                if f == rank:
+                    host_frames[0].copy_(frames[f], non_blocking=True)
             torch.cuda.synchronize()
 
     e2e_step()
@@ -488,7 +490,7 @@ def run_b200(args):
                 "d2h_bytes_per_step": Wd * Ht * 3 * n,
                 "note": ("backgrounds are part of the scene (`&self`, uploaded once: %.1f ms); per-frame input = metric+camera+sim structs; " % background_upload_ms) +
                         ("the RGB8 frame lands in a caller buffer registered once with curvis_host_register (the kernel stores into it over PCIe)"
-                         if n == 1 else "every rank renders its tiles, NCCL all-gathers them, rank 0 copies the complete frames to pinned host memory")},
+                         if n == 1 else "every rank renders its tiles of the N frames, NCCL all-gathers them, rank r copies complete frame r to its pinned host buffer")},
         "e2e_pageable": e2e_pageable,
         "e2e_cold": e2e_cold,
         "gpu_launches": int(launches_t.item()),
