@@ -2,7 +2,7 @@
 and src/main.rs:135-235: positionals ``background_image_1 background_image_2 [output_folder]``,
 options ``-i/--image-settings``, ``-v/--video-settings``, ``-m/--metric-settings``,
 ``-c/--camera-settings``, ``-s/--simulation-settings`` (TOML files; missing -> defaults).
-Extensions (absent from the reference): ``--renderer``, ``--devices``, ``--frames``,
+Extensions (absent from the reference): ``--renderer``, ``--precision``, ``--devices``, ``--frames``,
 ``--corrected-interpolation``."""
 from __future__ import annotations
 
@@ -25,6 +25,9 @@ def _common(sub):
     sub.add_argument("-s", "--simulation-settings", dest="simulation_settings")
     sub.add_argument("--renderer", choices=["efficient", "per_pixel"], default="efficient",
                      help="efficient = render_image_efficient (the reference binary's choice); per_pixel = render_image")
+    sub.add_argument("--precision", choices=["f64", "f64_fast", "f32"], default="f64",
+                     help="per_pixel renderer only: f64 = one rounding per reference operation; f64_fast = the same fp64 Euler "
+                          "iteration regrouped for the GPU (3x faster, same frames); f32 = fp32 right-hand side")
     sub.add_argument("--devices", default=None, help="comma-separated CUDA ordinals (default: all visible)")
 
 
@@ -78,13 +81,13 @@ def main(argv=None) -> int:
         if args.command == "image":
             image = _load(S.ImageSettings, args.image_settings)
             settings = ImageRenderingSettings.from_settings(bg1, bg2, out, image, camera, simulation)
-            path = ImageRenderingSystem(metric, settings, context=ctx, renderer=args.renderer).render()
+            path = ImageRenderingSystem(metric, settings, context=ctx, renderer=args.renderer, precision=args.precision).render()
             print(f"Saved {path}")
         else:
             video = _load(S.VideoSettings, args.video_settings)
             settings = VideoRenderingSettings.from_settings(bg1, bg2, out, video, camera, simulation)
             system = VideoRenderingSystem(metric, settings, context=ctx, renderer=args.renderer,
-                                          corrected_interpolation=args.corrected_interpolation)
+                                          corrected_interpolation=args.corrected_interpolation, precision=args.precision)
             print(f"Frames in {system.render(max_frames=args.frames)}")
         return 0
     except Exception as e:                                          # main.rs:219-227: print the error, exit 1

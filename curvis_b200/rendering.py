@@ -18,6 +18,7 @@ from .interpolation import Interpolator
 from .metrics import EllisMetric, InterstellarMetric
 from .settings import (CameraSettings, EllisMetricSettings, ImageSettings, InterstellarMetricSettings, SimulationSettings,
                        VideoSettings)
+from . import _abi
 from .systems import Context, RelativisticSystem
 
 
@@ -112,12 +113,18 @@ class VideoRenderingSettings:                                    # rendering.rs:
                    simulation.sampling_convergence_threshold_1, simulation.sampling_convergence_threshold_2)
 
 
+# per-pixel renderer only (extension): curvis_sim.precision of include/curvis_gpu.h
+PRECISIONS = {"f64": _abi.PRECISION_F64, "f64_fast": _abi.PRECISION_F64_FAST, "f32": _abi.PRECISION_F32}
+
+
 class ImageRenderingSystem:
     """rendering.rs:20-117."""
 
-    def __init__(self, metric, settings: ImageRenderingSettings, context: Optional[Context] = None, renderer: str = "efficient"):
+    def __init__(self, metric, settings: ImageRenderingSettings, context: Optional[Context] = None, renderer: str = "efficient",
+                 precision: str = "f64"):
         self.image_rendering_settings = settings
         self.renderer = renderer
+        self.precision = PRECISIONS[precision]
         image_1 = load_image_as_spherical_image(settings.path_to_background_image_1)
         image_2 = load_image_as_spherical_image(settings.path_to_background_image_2)
         camera = Camera(settings.camera_position, settings.camera_forward, settings.camera_up, settings.camera_focal_length,
@@ -127,7 +134,8 @@ class ImageRenderingSystem:
     def render_frame(self) -> np.ndarray:
         s = self.image_rendering_settings
         if self.renderer == "per_pixel":
-            return self.relativistic_system.render_image(s.max_iterations_propagation, s.escape_radius, s.ray_integration_step)
+            return self.relativistic_system.render_image(s.max_iterations_propagation, s.escape_radius, s.ray_integration_step,
+                                                         precision=self.precision)
         return self.relativistic_system.render_image_efficient(
             s.max_iterations_propagation, s.escape_radius, s.ray_integration_step, s.alphas_num, s.max_iterations_sampling,
             s.sampling_convergence_threshold_1, s.sampling_convergence_threshold_2)
@@ -146,9 +154,10 @@ class VideoRenderingSystem:
     """rendering.rs:170-327."""
 
     def __init__(self, metric, settings: VideoRenderingSettings, context: Optional[Context] = None, renderer: str = "efficient",
-                 corrected_interpolation: bool = False):
+                 corrected_interpolation: bool = False, precision: str = "f64"):
         self.video_rendering_settings = settings
         self.renderer = renderer
+        self.precision = PRECISIONS[precision]
         self.interpolator = Interpolator.from_file(settings.filepath_to_camera_path, corrected=corrected_interpolation)
         image_1 = load_image_as_spherical_image(settings.filepath_to_background_image_1)
         image_2 = load_image_as_spherical_image(settings.filepath_to_background_image_2)
@@ -174,7 +183,8 @@ class VideoRenderingSystem:
     def render_frame(self) -> np.ndarray:
         s = self.video_rendering_settings
         if self.renderer == "per_pixel":
-            return self.relativistic_system.render_image(s.max_iterations_propagation, s.escape_radius, s.ray_integration_step)
+            return self.relativistic_system.render_image(s.max_iterations_propagation, s.escape_radius, s.ray_integration_step,
+                                                         precision=self.precision)
         return self.relativistic_system.render_image_efficient(
             s.max_iterations_propagation, s.escape_radius, s.ray_integration_step, s.alphas_num, s.max_iterations_sampling,
             s.sampling_convergence_threshold_1,

@@ -1,0 +1,24 @@
+"""Small frames through every per-ray kernel (for compute-sanitizer memcheck / racecheck on the GPU box):
+the three precisions x three metrics, records on, a registered host frame (zero-copy stores), batched frames."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import curvis_b200 as cv
+from curvis_b200 import scenes, _abi
+
+ctx = cv.Context([0])
+bp, bn = scenes.decodable_background(256, 128), scenes.decodable_background(256, 128, True)
+W, H = 96, 54
+cam = cv.Camera(scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP, 15.0, 43.0, W, H)
+out = np.empty((H, W, 3), dtype=np.uint8)
+ctx.register_host_buffer(out)
+for metric, sim in ((cv.EllisMetric(1.0), (300, 12.0, 0.1)), (cv.InterstellarMetric(0.1, 1e-4, 1.0), (300, 12.0, 0.1)),
+                    (cv.FlatSphericalMetric(), (400, 12.0, 0.1))):
+    sysm = cv.RelativisticSystem(metric, cv.SphericalImage(bp), cv.SphericalImage(bn), cam, context=ctx)
+    for prec in (_abi.PRECISION_F64, _abi.PRECISION_F64_FAST, _abi.PRECISION_F32):
+        sysm.render_image(*sim, precision=prec, out=out)
+        frame, rec = sysm.render_rows(*sim, 3, 41, with_records=True, precision=prec)
+        assert (frame == out[3:41]).all()
+        print(type(metric).__name__, prec, sysm.last_stats["total_steps"], flush=True)
+ctx.unregister_host_buffer(out)
+print("ok")
