@@ -3,18 +3,25 @@
 // Same ODE, same forward-Euler scheme, same execution model as render_f64.cu (persistent grid,
 // one ray per lane, windowed ballot refill), but the right-hand side of
 // update_relativistic_object (reference src/metrics.rs:223-270) is evaluated in fp32 and
-// algebraically regrouped for the hardware:
-//   * Ellis needs only two reciprocals per step (1/r^2 and 1/sin^2 theta, MUFU.RCP): r'/r^3 = l/r^4,
-//     cos/(r^2 sin^3) = cos*sin/(r^2 sin^4); no square root, no division;
-//   * sin/cos: Cody-Waite reduction + degree-9/8 minimax polynomials (tools/gen_trig_coeffs_f32.py);
-//   * the five state variables (l, theta, phi, p_l, p_theta) are accumulated with Kahan
+// regrouped like CURVIS_PRECISION_F64_FAST (render_f64_fast.cu):
+//   * ONE MUFU.RCP per step, w = 1/(r^2 sin^2 theta); 1/r^2 = w sin^2, 1/sin^2 = w r^2; Ellis needs no
+//     square root (r'/r^3 = l/r^4);
+//   * momenta pre-scaled by delta (P = delta p — the same Euler iteration with the affine parameter
+//     rescaled to unit steps), so delta leaves the loop;
+//   * (sin theta, cos theta) carried along and rotated by the step's dtheta in the three-shear form
+//     (c -= t s; s += sd c; c -= t s with sd = sin dtheta, t = tan(dtheta/2), two-term series for
+//     |dtheta| < 2^-4), re-derived from the compensated theta at the start of every window (32
+//     steps) and after a larger dtheta, so the rotation's fp32 rounding never accumulates along the ray;
+//   * the five state variables (l, theta, phi, P_l, P_theta) are accumulated with Kahan
 //     compensation (sum + carry in fp32), so 2000 increments of ~0.05 do not random-walk the
 //     low bits of l ~ 100 — this is what keeps the step count and the end direction close to
 //     the fp64 path;
+//   * one exit branch per step (step budget, |l| near the radius or NaN, |dtheta| >= 2^-4), sorted
+//     out after the loop; the exact escape test runs in fp64 on the compensated l;
 //   * ray generation and the escaped-photon epilogue (direction, acos/atan2, texel index) reuse
 //     the fp64 code of geodesic_f64.cuh: they run once per ray.
 // An fp32 instruction issues every cycle per scheduler where an fp64 one holds the dispatch port
-// for two or more (profiles/r01_microbench_fp64_pipe.txt), hence the ~4x.
+// for two or more (profiles/r01_microbench_fp64_pipe.txt).
 //
 // Results are NOT bit-comparable with the reference: tests/test_gpu_fast_mode.py states the
 // tolerance (escape side identical, end direction within 1e-5 rad on >= 99 % of rays, texel equal
@@ -54,69 +61,150 @@ __device__ __noinline__ bool escaped_exact(float ls, float lc, double R) {
     return (lv > R) || (lv < -R);
 }
 
-// sin/cos for |x| < 2^16 (fast path), otherwise the library.
+// sin/cos for |x| < 2^16 (the caller guarantees it; larger or non-finite angles go to sincos_library).
 __device__ __forceinline__ void sincos_f32(float x, float& s, float& c) {
-    if (fabsf(x) < 65536.0f) {
-        const float t = fmaf(x, 0.63661975f, 12582912.0f);   // 1.5*2^23: integer in the low mantissa bits
-        const int k = __float_as_int(t);
-        const float q = t - 12582912.0f;
-        float r = fmaf(-q, 1.5707963705062866f, x);
-        r = fmaf(-q, -4.371138828673793e-08f, r);
-        r = fmaf(-q, -1.7151245100058819e-15f, r);
-        const float u = r * r;
-        float sp = fmaf(u, 2.723765874179662e-06f, -0.0001983999100048095f);
-        float cp = fmaf(u, 2.4537857825635e-05f, -0.001388825592584908f);
-        sp = fmaf(u, sp, 0.008333331905305386f);
-        cp = fmaf(u, cp, 0.0416666641831398f);
-        sp = fmaf(u, sp, -0.1666666716337204f);
-        const float sr = fmaf(r * u, sp, r);
-        const float cr = fmaf(u * u, cp, fmaf(u, -0.5f, 1.0f));
-        const float a = (k & 1) ? cr : sr;
-        const float b = (k & 1) ? sr : cr;
-        s = __int_as_float(__float_as_int(a) ^ ((k & 2) << 30));
-        c = __int_as_float(__float_as_int(b) ^ (((k + 1) & 2) << 30));
-    } else {
-        sincosf(x, &s, &c);
-    }
+    const float t = fmaf(x, 0.63661975f, 12582912.0f);   // 1.5*2^23: integer in the low mantissa bits
+    const int k = __float_as_int(t);
+    const float q = t - 12582912.0f;
+    float r = fmaf(-q, 1.5707963705062866f, x);
+    r = fmaf(-q, -4.371138828673793e-08f, r);
+    r = fmaf(-q, -1.7151245100058819e-15f, r);
+    const float u = r * r;
+    float sp = fmaf(u, 2.723765874179662e-06f, -0.0001983999100048095f);
+    float cp = fmaf(u, 2.4537857825635e-05f, -0.001388825592584908f);
+    sp = fmaf(u, sp, 0.008333331905305386f);
+    cp = fmaf(u, cp, 0.0416666641831398f);
+    sp = fmaf(u, sp, -0.1666666716337204f);
+    const float sr = fmaf(r * u, sp, r);
+    const float cr = fmaf(u * u, cp, fmaf(u, -0.5f, 1.0f));
+    const float a = (k & 1) ? cr : sr;
+    const float b = (k & 1) ? sr : cr;
+    s = __int_as_float(__float_as_int(a) ^ ((k & 2) << 30));
+    c = __int_as_float(__float_as_int(b) ^ (((k + 1) & 2) << 30));
 }
 
-// Shape functions in fp32: 1/r^2 and the radial-force coefficient r'(l)/r(l)^3.
-struct Shape32Ellis {
+// Large or non-finite angles: the library (Payne-Hanek), out of line.
+__device__ __noinline__ float2 sincos_library(float x) {
+    float s, c;
+    sincosf(x, &s, &c);
+    return make_float2(s, c);
+}
+
+// Shape policies, split around the reciprocal like render_f64_fast.cu: prepare() returns the divisor
+// d (r^2 sin^2 for Ellis, r sin^2 otherwise), finish() turns y0 = 1/d into w = 1/(r^2 sin^2),
+// u = 1/r^2, v = 1/sin^2 and f = r'(l)/r(l)^3.
+struct Shape32Ellis {   // metrics.rs:417-421
     using Shape64 = ShapeEllis;
-    __device__ __forceinline__ void init(const FrameParams&) {}
-    __device__ __forceinline__ void eval(const FrameParams& p, float l, float& inv_r2, float& force) const {
-        inv_r2 = rcp_fast(fmaf(l, l, p.f_rho2));
-        force = l * (inv_r2 * inv_r2);   // (l/r) / r^3
+    struct Pre { float r2; };
+    static __device__ __forceinline__ float prepare(const FrameParams& p, float l, float s2, Pre& pre) {
+        pre.r2 = fmaf(l, l, p.f_rho2);
+        return pre.r2 * s2;
+    }
+    static __device__ __forceinline__ void finish(const Pre& pre, float y0, float l, float s2, float& w, float& u, float& v, float& f) {
+        w = y0;
+        u = w * s2;
+        v = w * pre.r2;
+        f = l * (u * u);             // (l/r) / r^3
     }
 };
 
-struct Shape32Interstellar {
+struct Pre32FromR { float r, rp; };
+__device__ __forceinline__ void finish32_from_r(const Pre32FromR& pre, float y0, float s2, float& w, float& u, float& v, float& f) {
+    const float y = y0 * s2;         // 1/r
+    v = y0 * pre.r;                  // 1/sin^2
+    u = y * y;
+    w = u * v;
+    f = pre.rp * (y * u);            // r'/r^3
+}
+
+struct Shape32Interstellar {   // metrics.rs:461-485
     using Shape64 = ShapeInterstellar;
-    __device__ __forceinline__ void init(const FrameParams&) {}
-    __device__ __forceinline__ void eval(const FrameParams& p, float l, float& inv_r2, float& force) const {
+    using Pre = Pre32FromR;
+    static __device__ __forceinline__ float prepare(const FrameParams& p, float l, float s2, Pre& pre) {
         const float al = fabsf(l);
-        float r = p.f_rho, rp = 0.0f;
+        pre.r = p.f_rho; pre.rp = 0.0f;
         if (al > p.f_a) {
             const float x = (al - p.f_a) * p.f_xscale;
             const float at = atanf(x);
-            r = fmaf(p.f_m, fmaf(x, at, -0.5f * __logf(fmaf(x, x, 1.0f))), p.f_rho);
-            rp = copysignf(0.63661975f * at, l);
+            pre.r = fmaf(p.f_m, fmaf(x, at, -0.5f * __logf(fmaf(x, x, 1.0f))), p.f_rho);
+            pre.rp = copysignf(0.63661975f * at, l);
         }
-        const float inv_r = rcp_fast(r);
-        inv_r2 = inv_r * inv_r;
-        force = rp * (inv_r2 * inv_r);
+        return pre.r * s2;
+    }
+    static __device__ __forceinline__ void finish(const Pre& pre, float y0, float, float s2, float& w, float& u, float& v, float& f) {
+        finish32_from_r(pre, y0, s2, w, u, v, f);
     }
 };
 
-struct Shape32Flat {
+struct Shape32Flat {   // metrics.rs:501-505
     using Shape64 = ShapeFlat;
-    __device__ __forceinline__ void init(const FrameParams&) {}
-    __device__ __forceinline__ void eval(const FrameParams&, float l, float& inv_r2, float& force) const {
-        const float inv_r = rcp_fast(l);
-        inv_r2 = inv_r * inv_r;
-        force = inv_r2 * inv_r;
+    using Pre = Pre32FromR;
+    static __device__ __forceinline__ float prepare(const FrameParams&, float l, float s2, Pre& pre) {
+        pre.r = l; pre.rp = 1.0f;
+        return l * s2;
+    }
+    static __device__ __forceinline__ void finish(const Pre& pre, float y0, float, float s2, float& w, float& u, float& v, float& f) {
+        finish32_from_r(pre, y0, s2, w, u, v, f);
     }
 };
+
+// Compensated state of one ray; momenta scaled by delta (see the file header).
+struct Ray32 {
+    Kahan l, th, ph, pl, pth;
+    float pph, pph2;
+};
+
+// Up to n steps of one window.  Returns the number of steps taken; `stop` = the ray left the radius
+// (systems.rs:129-134, tested in fp64 on the compensated l) or its l became NaN.
+template <class Shape32>
+__device__ __forceinline__ uint32_t window_f32(const FrameParams& p, Ray32& q, uint32_t n, float near_radius, double R, bool& stop) {
+    uint32_t k = 0;
+    for (;;) {
+        // (sin, cos) of the compensated angle
+        float sn, cn;
+        if (fabsf(q.th.s) < 65536.0f) sincos_f32(q.th.s, sn, cn);
+        else { const float2 sc = sincos_library(q.th.s); sn = sc.x; cn = sc.y; }
+        { const float s0 = sn; sn = fmaf(-cn, q.th.c, sn); cn = fmaf(s0, q.th.c, cn); }      // theta = th.s - th.c
+        typename Shape32::Pre pre;
+        float s2 = sn * sn;
+        float d = Shape32::prepare(p, q.l.s, s2, pre);
+        float dth;
+        // one step; true = leave the loop (one of the rarely-true conditions holds)
+        auto step = [&]() -> bool {
+            float w, u, v, f;
+            Shape32::finish(pre, rcp_fast(d), q.l.s, s2, w, u, v, f);
+            const float cs = sn * cn;
+            dth = q.pth.s * u;                                  // metrics.rs:239 (times delta)
+            const float pv = q.pph2 * v;                        // p_phi^2 / sin^2
+            const float b2 = fmaf(q.pth.s, q.pth.s, pv);        // :257
+            q.l.add(q.pl.s);                                    // :238, :295 (old p_l)
+            q.th.add(dth);
+            q.ph.add(q.pph * w);                                // :240
+            q.pl.add(b2 * f);                                   // :261, :296
+            q.pth.add((pv * cs) * w);                           // :262  p_phi^2 cos / (r^2 sin^3)
+            // rotate (sin, cos) by dth: three shears, sd = sin dth, t = tan(dth/2)
+            const float v2 = dth * dth;
+            const float sd = dth * fmaf(v2, fmaf(v2, 0.0083333333f, -0.16666667f), 1.0f);
+            const float t = dth * fmaf(v2, fmaf(v2, 0.0041666667f, 0.041666667f), 0.5f);
+            cn = fmaf(-t, sn, cn);
+            sn = fmaf(sd, cn, sn);
+            cn = fmaf(-t, sn, cn);
+            ++k;
+            s2 = sn * sn;
+            d = Shape32::prepare(p, q.l.s, s2, pre);
+            return (k >= n) | !(fabsf(q.l.s) < near_radius) | !(fabsf(dth) < 0.0625f);
+        };
+        for (;;) {               // unrolled by two: the Kahan sums alternate registers instead of copying them
+            if (step()) break;
+            if (step()) break;
+        }
+        if (!(fabsf(q.l.s) < near_radius)) {                    // near the radius, or NaN
+            if (q.l.s != q.l.s || escaped_exact(q.l.s, q.l.c, R)) { stop = true; return k; }
+        }
+        if (k >= n) return k;
+        // |dtheta| too large for the rotation (or NaN), or a false alarm near the radius: re-derive (sin, cos) and go on
+    }
+}
 
 template <class Shape32>
 __global__ void __launch_bounds__(kBlock32) render_rows_f32(const __grid_constant__ FrameParams p) {
@@ -126,14 +214,10 @@ __global__ void __launch_bounds__(kBlock32) render_rows_f32(const __grid_constan
     const unsigned long long tile_rays = (unsigned long long)(p.row_end - p.row_begin) * p.width;
     const unsigned long long launch_rays = tile_rays * (p.n_frames ? p.n_frames : 1u);
     const double R = p.max_radius;
-    const float delta = p.f_delta;
     const float near_radius = p.f_near_radius;   // below it no escape test is needed
-    Shape32 shape;
-    shape.init(p);
 
-    Kahan l, th, ph, pl, pth;
-    float pph = 0.f, pph2 = 0.f;
-    double pph_exact = 0.0;
+    Ray32 q;
+    q.pph = 0.f; q.pph2 = 0.f;
     int state = 0;
     bool drained = false;
     uint32_t remaining = 0;
@@ -142,12 +226,16 @@ __global__ void __launch_bounds__(kBlock32) render_rows_f32(const __grid_constan
 
     for (;;) {
         if (state == 2) {
-            // epilogue in fp64 on the compensated state: same code path as the parity kernel
-            Ray q;
-            q.l = l.value(); q.th = th.value(); q.ph = ph.value(); q.pl = pl.value(); q.pth = pth.value();
-            q.pph = pph_exact; q.pph2 = pph_exact * pph_exact;
-            const int side = (q.l > R) ? 1 : ((q.l < -R) ? -1 : 0);
-            finish_ray<Shape64, TrigFast>(p, q, side, p.max_iterations - remaining, ray, tally);
+            // epilogue in fp64 on the compensated state: same code path as the parity kernel.  p_phi is
+            // conserved: it is regenerated from the ray index (exact) instead of un-scaled.
+            Ray e;
+            new_photon_for_ray(p, ray, tile_rays, e);
+            if (remaining != p.max_iterations && p.delta != 0.0) {   // (a zero step never moves the photon)
+                e.l = q.l.value(); e.th = q.th.value(); e.ph = q.ph.value();
+                e.pl = q.pl.value() / p.delta; e.pth = q.pth.value() / p.delta;
+            }
+            const int side = (e.l > R) ? 1 : ((e.l < -R) ? -1 : 0);
+            finish_ray<Shape64, TrigFast>(p, e, side, p.max_iterations - remaining, ray, tally);
             state = 0;
         }
 
@@ -162,11 +250,12 @@ __global__ void __launch_bounds__(kBlock32) render_rows_f32(const __grid_constan
                     const unsigned long long idx = base + (unsigned long long)__popc(idle & lt_mask);
                     if (idx < launch_rays) {
                         ray = idx;
-                        Ray q;
-                        new_photon_for_ray(p, idx, tile_rays, q);   // fp64 ray generation (once per ray)
-                        l.set(q.l); th.set(q.th); ph.set(q.ph); pl.set(q.pl); pth.set(q.pth);
-                        pph_exact = q.pph;
-                        pph = (float)q.pph; pph2 = (float)q.pph2;
+                        Ray e;
+                        new_photon_for_ray(p, idx, tile_rays, e);   // fp64 ray generation (once per ray)
+                        q.l.set(e.l); q.th.set(e.th); q.ph.set(e.ph);
+                        q.pl.set(e.pl * p.delta); q.pth.set(e.pth * p.delta);
+                        const double pphd = e.pph * p.delta;
+                        q.pph = (float)pphd; q.pph2 = (float)(pphd * pphd);
                         remaining = p.max_iterations;
                         state = (remaining == 0) ? 2 : 1;
                     }
@@ -176,37 +265,15 @@ __global__ void __launch_bounds__(kBlock32) render_rows_f32(const __grid_constan
             if (__ballot_sync(kFull32, state != 0) == 0u) break;
         }
 
-#pragma unroll 2
-        for (uint32_t k = 0; k < p.window; ++k) {
-            if (state == 1) {
-                // ---- one forward-Euler step, fp32 right-hand side (metrics.rs:223-270 regrouped)
-                float s, c;
-                sincos_f32(th.s, s, c);
-                float inv_r2, force;
-                shape.eval(p, l.s, inv_r2, force);
-                const float inv_s2 = rcp_fast(s * s);
-                const float ir2d = inv_r2 * delta;                   // delta folded into the shared factors
-                const float w = pph2 * inv_s2;                       // p_phi^2 / sin^2
-                const float b2 = fmaf(pth.s, pth.s, w);              // :257
-                const float inc_l = pl.s * delta;                    // :295 (old p_l)
-                const float inc_th = pth.s * ir2d;                   // :239
-                const float inc_ph = pph * (ir2d * inv_s2);          // :240
-                const float inc_pl = b2 * (force * delta);           // :261
-                const float inc_pth = (w * inv_s2) * (c * s) * ir2d; // :262  p_phi^2 cos / (r^2 sin^3)
-                l.add(inc_l);
-                th.add(inc_th);
-                ph.add(inc_ph);
-                pl.add(inc_pl);                                      // :296
-                pth.add(inc_pth);
-                --remaining;
-                bool done = (remaining == 0);
-                if (!(fabsf(l.s) < near_radius)) {                  // near the radius, or NaN
-                    done = done || escaped_exact(l.s, l.c, R);
-                    if (l.s != l.s) { remaining = 0; done = true; }   // NaN never escapes: NotEscaped with all iterations counted
-                }
-                if (done) state = 2;
-            }
+        if (state == 1) {
+            bool stop = false;
+            const uint32_t k = window_f32<Shape32>(p, q, min(p.window, remaining), near_radius, R, stop);
+            remaining -= k;
+            // a NaN l never escapes: NotEscaped with all iterations counted (as the reference would, after spinning)
+            if (q.l.s != q.l.s) remaining = 0;
+            if (stop || remaining == 0) state = 2;
         }
+        __syncwarp();
     }
 
     flush_tally(p, tally, lane);
