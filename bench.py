@@ -248,10 +248,19 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
 
-    def device_step(want_stats=False):
+    # Overlapping the all-gathers of step k with the render kernel of step k+1 does not pay here: the render
+    # kernel is persistent and saturates every scheduler, and NCCL CTAs that become co-resident with it are
+    # starved by the warp scheduler (DESIGN.md sections 5-6) — measured at N=2: one step in four stalls 8-9 ms.
+    # Default: the gathers run between two renders on the compute stream (N x ~0.1 ms per step); the frame
+    # read-back of the e2e path is a DMA and does overlap.  CURVIS_BENCH_OVERLAP=1 restores the overlapped form.
+    overlap = os.environ.get("CURVIS_BENCH_OVERLAP", "0") == "1"
+    copied = [torch.cuda.Event()]                 # recorded on the comm (copy) stream after this rank's frame has been read back
+
+    def device_step(want_stats=False, readback=False):
         """One step of the resident path: n frames; this rank's row tile of every frame in ONE
-        batched launch (curvis_render_frames_device), then one all-gather per frame."""
-        flush.fill_(1)
+        batched launch (curvis_render_frames_device), then one all-gather per frame; with `readback`
+        (the e2e path) rank r also copies complete frame r to its pinned host buffer."""
+        flush.fill_(1)                                # L2 flush between steps
         if n == 1:
             return system.render_rows_device(*sim, row_begin, row_end, frames[0].data_ptr(), stream.cuda_stream, want_stats=want_stats,
                                              precision=PREC)
@@ -261,13 +270,30 @@ def run_b200(args):
         stream.wait_event(tiles_free[buf])          # the gather that last read this buffer has finished
         st = system.render_frames_device(cameras, *sim, row_begin, row_end, cur.data_ptr(), stream.cuda_stream, want_stats=want_stats,
                                          precision=PREC)
-        rendered = torch.cuda.Event()
-        rendered.record(stream)
-        with torch.cuda.stream(comm_stream):
-            comm_stream.wait_event(rendered)
+        if overlap:
+            rendered = torch.cuda.Event()
+            rendered.record(stream)
+            with torch.cuda.stream(comm_stream):
+                comm_stream.wait_event(rendered)
+                for f in range(n):
+                    dist.all_gather_into_tensor(frames[f], cur[f * tile_bytes:(f + 1) * tile_bytes])
+                    if readback and f == rank:
+                        host_frames[0].copy_(frames[f], non_blocking=True)
+                tiles_free[buf].record(comm_stream)
+            return st
+        stream.wait_event(copied[0])                # the previous step's read-back of frames[rank] has finished
+        with dist._coalescing_manager():            # the n all-gathers as ONE NCCL group (one launch)
             for f in range(n):
                 dist.all_gather_into_tensor(frames[f], cur[f * tile_bytes:(f + 1) * tile_bytes])
-            tiles_free[buf].record(comm_stream)
+        tiles_free[buf].record(stream)
+        if readback:
+            gathered = torch.cuda.Event()
+            gathered.record(stream)
+            with torch.cuda.stream(comm_stream):
+                comm_stream.wait_event(gathered)
+                host_frames[0].copy_(frames[rank], non_blocking=True)
+                copied[0] = torch.cuda.Event()
+                copied[0].record(comm_stream)
         return st
 
     # steps of this rank's share of one job-step (deterministic) -> total over ranks
@@ -326,24 +352,28 @@ def run_b200(args):
 
     def e2e_step():
         if n == 1:
-            system.render_image(*sim, out=host_frame, precision=PREC)   # curvis_render_image: kernel + D2H + copy to caller buffer
+            system.render_image(*sim, out=host_frame, precision=PREC)   # curvis_render_image into the registered caller frame
         else:
-            system.render_frames_device(cameras, *sim, row_begin, row_end, tiles.data_ptr(), stream.cuda_stream, precision=PREC)
-            for f in range(n):
-                dist.all_gather_into_tensor(frames[f], tiles[f * tile_bytes:(f + 1) * tile_bytes])
-                if f == rank:
-                    host_frames[0].copy_(frames[f], non_blocking=True)
-            torch.cuda.synchronize()
+            device_step(readback=True)            # the resident step + the read-back (a DMA) of this rank's frame under the next render
 
     e2e_step()
     torch.cuda.synchronize()
     barrier()
+    trace_events = [] if os.environ.get("CURVIS_BENCH_TRACE") else None
     t0 = time.perf_counter()
     for _ in range(args.steps):
         e2e_step()
+        if trace_events is not None:
+            ev = torch.cuda.Event(enable_timing=True); ev.record(stream); trace_events.append((ev, time.perf_counter() - t0))
+    t_enq = time.perf_counter() - t0
     torch.cuda.synchronize()
+    t_sync = time.perf_counter() - t0
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if trace_events is not None:
+        print(f"[trace rank {rank}] enqueue done {t_enq * 1e3:.2f} ms, synchronized {t_sync * 1e3:.2f} ms, after barrier {float(e2e_s.item()) * 1e3:.2f} ms; "
+              f"render-end gaps (ms): {[round(trace_events[i][0].elapsed_time(trace_events[i + 1][0]), 2) for i in range(len(trace_events) - 1)]}; "
+              f"host enqueue times (ms): {[round(t * 1e3, 1) for _, t in trace_events]}", file=sys.stderr, flush=True)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = steps_per_job_step * args.steps / float(e2e_s.item())
