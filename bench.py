@@ -51,6 +51,10 @@ def parse():
     ap.add_argument("--width", type=int, default=W4K)
     ap.add_argument("--height", type=int, default=H4K)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="peers", choices=["peers", "nccl"],
+                    help="N > 1: peers (default) = the render kernel stores every pixel into the complete frames of all ranks over "
+                         "NVLink (fused render + all-gather, curvis_render_frames_peers) and a 4-byte all-reduce is the step barrier; "
+                         "nccl = tiles rendered locally, then one coalesced NCCL all-gather per step")
     ap.add_argument("--precision", default="f64_fast", choices=["f64_fast", "f64"],
                     help="f64_fast (default): fp64, right-hand side regrouped around one reciprocal per step "
                          "(CURVIS_PRECISION_F64_FAST); f64: one rounding per reference operation (CURVIS_PRECISION_F64)")
@@ -68,7 +72,12 @@ def workload_config(args, n):
                                   "step's dtheta (each operation <= 1 ulp; frame checked against the operation-for-operation kernel in "
                                   "`parity_check`)",
                       "f64": "CURVIS_PRECISION_F64: fp64, one rounding per reference operation"}[args.precision],
-        "parallelism": "single GPU" if n == 1 else f"{n} frames/step (camera path), each row-tiled over {n} ranks: one batched launch per rank + one NCCL all-gather of row tiles per frame",
+        "parallelism": "single GPU" if n == 1 else (
+            f"{n} frames/step (camera path), each row-tiled over {n} ranks: one batched launch per rank whose epilogue stores every pixel into "
+            f"the complete frames of all {n} ranks over NVLink peer memory (fused render + all-gather), then a 4-byte NCCL all-reduce as the step barrier"
+            if args.gather == "peers" else
+            f"{n} frames/step (camera path), each row-tiled over {n} ranks: one batched launch per rank + the {n} NCCL all-gathers of row tiles "
+            f"(one NCCL group) between two renders"),
         "l2": "256 MiB device buffer rewritten between steps inside the timed region (L2 flush); the kernel is ALU-bound",
     }
 
@@ -256,10 +265,51 @@ def run_b200(args):
     overlap = os.environ.get("CURVIS_BENCH_OVERLAP", "0") == "1"
     copied = [torch.cuda.Event()]                 # recorded on the comm (copy) stream after this rank's frame has been read back
 
+    # ---- fused render + all-gather (--gather peers): every rank owns two buffers of n complete frames (steps alternate
+    # between them), exported to its peers through CUDA IPC; the render kernel of every rank stores each pixel into all n
+    # buffers of the step's set — its own and, over NVLink, its peers'.  No collective moves pixels; a 4-byte all-reduce
+    # after the launch tells a rank that its peers' kernels have ended.
+    frame_bytes = Ht * Wd * 3
+    peers_mode = n > 1 and args.gather == "peers"
+    peer_sets, my_frames, token = [], [], None
+    if peers_mode:
+        for s_ in range(2):
+            mine = cv.PeerBuffer.create(ctx, n * frame_bytes)
+            handles = [None] * n
+            dist.all_gather_object(handles, mine.handle)
+            peer_sets.append([mine if r == rank else cv.PeerBuffer.open(ctx, handles[r], n * frame_bytes) for r in range(n)])
+            my_frames.append(mine.as_tensor(local))
+        token = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def peers_step(want_stats=False, readback=False):
+        flush.fill_(1)                                # L2 flush between steps
+        k = step_index[0]
+        step_index[0] += 1
+        cur = peer_sets[k & 1]
+        st = system.render_frames_peers(cameras, *sim, row_begin, row_end, [b.ptr for b in cur], stream.cuda_stream,
+                                        want_stats=want_stats, precision=PREC)
+        # this rank's read-back of step k-1 (which read set (k-1)&1) must have finished before the barrier of step k lets
+        # anybody launch step k+1 into that set
+        stream.wait_event(copied[0])
+        dist.all_reduce(token)                        # step barrier: every rank's kernel of step k has ended
+        frames[:] = [my_frames[k & 1][f * frame_bytes:(f + 1) * frame_bytes] for f in range(n)]
+        if readback:
+            gathered = torch.cuda.Event()
+            gathered.record(stream)
+            with torch.cuda.stream(comm_stream):
+                comm_stream.wait_event(gathered)
+                host_frames[0].copy_(frames[rank], non_blocking=True)
+                copied[0] = torch.cuda.Event()
+                copied[0].record(comm_stream)
+        return st
+
     def device_step(want_stats=False, readback=False):
         """One step of the resident path: n frames; this rank's row tile of every frame in ONE
-        batched launch (curvis_render_frames_device), then one all-gather per frame; with `readback`
-        (the e2e path) rank r also copies complete frame r to its pinned host buffer."""
+        batched launch, gathered so that every rank holds every complete frame (fused peer stores, or
+        NCCL all-gathers with --gather nccl); with `readback` (the e2e path) rank r also copies
+        complete frame r to its pinned host buffer."""
+        if peers_mode:
+            return peers_step(want_stats, readback)
         flush.fill_(1)                                # L2 flush between steps
         if n == 1:
             return system.render_rows_device(*sim, row_begin, row_end, frames[0].data_ptr(), stream.cuda_stream, want_stats=want_stats,
@@ -308,6 +358,18 @@ def run_b200(args):
         device_step()
     torch.cuda.synchronize()
     barrier()
+    # N > 1: the gathered frame r on rank r against the same frame rendered whole on this rank alone
+    gather_check = None
+    if n > 1:
+        whole = torch.empty(frame_bytes, dtype=torch.uint8, device=dev)
+        keep_camera, system.camera = system.camera, cameras[rank]
+        system.render_rows_device(*sim, 0, Ht, whole.data_ptr(), stream.cuda_stream, want_stats=True, precision=PREC)
+        system.camera = keep_camera
+        bad = (whole.view(-1, 3) != frames[rank].view(-1, 3)).any(dim=1).sum().to(torch.int64).reshape(1)
+        dist.all_reduce(bad)
+        gather_check = {"what": "complete frame r as gathered on rank r vs. the same frame rendered whole on rank r alone, all ranks",
+                        "pixels": n * Wd * Ht, "differing_pixels": int(bad.item())}
+        del whole
     launches0 = lib.curvis_kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
@@ -520,7 +582,9 @@ def run_b200(args):
                 "d2h_bytes_per_step": Wd * Ht * 3 * n,
                 "note": ("backgrounds are part of the scene (`&self`, uploaded once: %.1f ms); per-frame input = metric+camera+sim structs; " % background_upload_ms) +
                         ("the RGB8 frame lands in a caller buffer registered once with curvis_host_register (the kernel stores into it over PCIe)"
-                         if n == 1 else "every rank renders its tiles of the N frames, NCCL all-gathers them, rank r copies complete frame r to its pinned host buffer")},
+                         if n == 1 else "every rank renders its tiles of the N frames into all ranks' frame buffers, rank r copies complete frame r to its pinned host buffer (DMA under the next render)")},
+        "gather": (args.gather if n > 1 else None),
+        "gather_check": gather_check,
         "e2e_pageable": e2e_pageable,
         "e2e_cold": e2e_cold,
         "gpu_launches": int(launches_t.item()),

@@ -7,4 +7,4 @@ from .algebra import Orientation  # noqa: F401
 from .cameras import Camera  # noqa: F401
 from .images import SphericalImage  # noqa: F401
 from .metrics import EllisMetric, FlatSphericalMetric, InterstellarMetric  # noqa: F401
-from .systems import Context, RelativisticSystem  # noqa: F401
+from .systems import Context, PeerBuffer, RelativisticSystem  # noqa: F401

@@ -103,6 +103,9 @@ RAY_RECORD_DTYPE = [
     ("steps", "<u4"), ("side", "<i4"), ("texel_x", "<u4"), ("texel_y", "<u4"),
 ]
 
+MAX_PEERS = 8               # CURVIS_MAX_PEERS
+IPC_HANDLE_BYTES = 64       # CURVIS_IPC_HANDLE_BYTES
+
 # Every symbol include/curvis_gpu.h declares (tests assert the .so exports exactly these).
 EXPORTED_SYMBOLS = (
     "curvis_ctx_create", "curvis_ctx_destroy", "curvis_last_error", "curvis_abi_version",
@@ -111,6 +114,8 @@ EXPORTED_SYMBOLS = (
     "curvis_measure_fma_peak", "curvis_kernel_launch_count", "curvis_ctx_set_option", "curvis_debug_eval",
     "curvis_render_frames_device", "curvis_render_image_efficient", "curvis_render_rows_rgba32f", "curvis_debug_bilinear",
     "curvis_debug_shape_table_host", "curvis_host_register", "curvis_host_unregister",
+    "curvis_peer_buffer_create", "curvis_peer_buffer_open", "curvis_peer_buffer_close", "curvis_peer_buffer_destroy",
+    "curvis_render_frames_peers",
 )
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcurvis_b200.so")
@@ -164,6 +169,12 @@ def load_library() -> C.CDLL:
     lib.curvis_measure_fma_peak.argtypes = [vp, dp, dp]
     lib.curvis_ctx_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     lib.curvis_debug_eval.argtypes = [vp, C.c_int, dp, dp, dp, C.c_size_t]
+    lib.curvis_peer_buffer_create.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.c_char_p]
+    lib.curvis_peer_buffer_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    lib.curvis_peer_buffer_close.argtypes = [vp, vp]
+    lib.curvis_peer_buffer_destroy.argtypes = [vp, vp]
+    lib.curvis_render_frames_peers.argtypes = [vp, C.POINTER(CurvisMetric), C.POINTER(CurvisCamera), C.c_uint32, C.POINTER(CurvisSim),
+                                               C.c_uint32, C.c_uint32, C.POINTER(vp), C.c_uint32, vp, C.POINTER(CurvisStats)]
     lib.curvis_host_register.argtypes = [vp, vp, C.c_size_t]
     lib.curvis_host_unregister.argtypes = [vp, vp]
     lib.curvis_debug_shape_table_host.argtypes = [dp, dp, dp, C.c_size_t]

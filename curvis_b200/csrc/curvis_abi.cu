@@ -394,10 +394,10 @@ extern "C" int curvis_render_rows_device(curvis_ctx* ctx, const curvis_metric* m
     return CURVIS_OK;
 }
 
-extern "C" int curvis_render_frames_device(curvis_ctx* ctx, const curvis_metric* metric,
-                                           const curvis_camera* cameras, uint32_t n_frames, const curvis_sim* sim,
-                                           uint32_t row_begin, uint32_t row_end,
-                                           void* d_out_rgb8_tiles, void* stream, curvis_stats* stats) {
+static int render_frames_impl(curvis_ctx* ctx, const curvis_metric* metric,
+                              const curvis_camera* cameras, uint32_t n_frames, const curvis_sim* sim,
+                              uint32_t row_begin, uint32_t row_end,
+                              void* d_out_rgb8_tiles, void* const* d_peer_frames, uint32_t n_peers, void* stream, curvis_stats* stats) {
     const auto t0 = std::chrono::steady_clock::now();
     if (!ctx) return fail(nullptr, CURVIS_ERR_INVALID_ARGUMENT, "null context");
     if (!cameras || n_frames == 0) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "no cameras");
@@ -407,7 +407,10 @@ extern "C" int curvis_render_frames_device(curvis_ctx* ctx, const curvis_metric*
         if (cameras[f].resolution_width != cameras[0].resolution_width || cameras[f].resolution_height != cameras[0].resolution_height)
             return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "all frames of a batch must share one resolution");
     }
-    if (!d_out_rgb8_tiles && row_end > row_begin) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "null device output");
+    if (!d_out_rgb8_tiles && n_peers == 0 && row_end > row_begin) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "null device output");
+    if (n_peers > CURVIS_MAX_PEERS) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "more than CURVIS_MAX_PEERS peer buffers");
+    for (uint32_t i = 0; i < n_peers; ++i)
+        if (!d_peer_frames || !d_peer_frames[i]) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "null peer frame buffer");
     DeviceState& d = ctx->devs[0];
     cudaStream_t st = (cudaStream_t)stream;
     CURVIS_CUDA(ctx, cudaSetDevice(d.ordinal));
@@ -428,6 +431,8 @@ extern "C" int curvis_render_frames_device(curvis_ctx* ctx, const curvis_metric*
     FrameParams p;
     fill_params(ctx, d, metric, &cameras[0], sim, row_begin, row_end, (uint8_t*)d_out_rgb8_tiles, nullptr, p);
     p.cameras = d.d_cameras; p.n_frames = n_frames;
+    p.n_peers = n_peers;
+    for (uint32_t i = 0; i < n_peers; ++i) p.out_peers[i] = (uint8_t*)d_peer_frames[i];
     CURVIS_CUDA(ctx, cudaMemsetAsync(d.d_counters, 0, sizeof(DeviceCounters), st));
     CURVIS_CUDA(ctx, cudaEventRecord(d.ev_begin, st));
     if (row_end > row_begin) CURVIS_CUDA(ctx, launch_render(p, metric, sim, ctx->tuning, d.sm_count, st));
@@ -442,6 +447,57 @@ extern "C" int curvis_render_frames_device(curvis_ctx* ctx, const curvis_metric*
         stats->kernel_ms = ms;
         stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
+    return CURVIS_OK;
+}
+
+extern "C" int curvis_render_frames_device(curvis_ctx* ctx, const curvis_metric* metric,
+                                           const curvis_camera* cameras, uint32_t n_frames, const curvis_sim* sim,
+                                           uint32_t row_begin, uint32_t row_end,
+                                           void* d_out_rgb8_tiles, void* stream, curvis_stats* stats) {
+    return render_frames_impl(ctx, metric, cameras, n_frames, sim, row_begin, row_end, d_out_rgb8_tiles, nullptr, 0, stream, stats);
+}
+
+extern "C" int curvis_render_frames_peers(curvis_ctx* ctx, const curvis_metric* metric, const curvis_camera* cameras, uint32_t n_frames,
+                                          const curvis_sim* sim, uint32_t row_begin, uint32_t row_end,
+                                          void* const* d_frames, uint32_t n_peers, void* stream, curvis_stats* stats) {
+    if (n_peers == 0) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "curvis_render_frames_peers: no peer buffers");
+    return render_frames_impl(ctx, metric, cameras, n_frames, sim, row_begin, row_end, nullptr, d_frames, n_peers, stream, stats);
+}
+
+extern "C" int curvis_peer_buffer_create(curvis_ctx* ctx, size_t bytes, void** d_ptr, uint8_t ipc_handle[CURVIS_IPC_HANDLE_BYTES]) {
+    if (!ctx || !d_ptr || !ipc_handle || bytes == 0) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "curvis_peer_buffer_create: null argument or zero size");
+    static_assert(sizeof(cudaIpcMemHandle_t) == CURVIS_IPC_HANDLE_BYTES, "IPC handle size");
+    CURVIS_CUDA(ctx, cudaSetDevice(ctx->devs[0].ordinal));
+    void* ptr = nullptr;
+    CURVIS_CUDA(ctx, cudaMalloc(&ptr, bytes));
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, ptr);
+    if (e != cudaSuccess) { cudaFree(ptr); return cuda_fail(ctx, e, "cudaIpcGetMemHandle"); }
+    std::memcpy(ipc_handle, &h, sizeof h);
+    *d_ptr = ptr;
+    return CURVIS_OK;
+}
+
+extern "C" int curvis_peer_buffer_open(curvis_ctx* ctx, const uint8_t ipc_handle[CURVIS_IPC_HANDLE_BYTES], void** d_ptr) {
+    if (!ctx || !d_ptr || !ipc_handle) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "curvis_peer_buffer_open: null argument");
+    CURVIS_CUDA(ctx, cudaSetDevice(ctx->devs[0].ordinal));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, ipc_handle, sizeof h);
+    CURVIS_CUDA(ctx, cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return CURVIS_OK;
+}
+
+extern "C" int curvis_peer_buffer_close(curvis_ctx* ctx, void* d_ptr) {
+    if (!ctx || !d_ptr) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "curvis_peer_buffer_close: null argument");
+    CURVIS_CUDA(ctx, cudaSetDevice(ctx->devs[0].ordinal));
+    CURVIS_CUDA(ctx, cudaIpcCloseMemHandle(d_ptr));
+    return CURVIS_OK;
+}
+
+extern "C" int curvis_peer_buffer_destroy(curvis_ctx* ctx, void* d_ptr) {
+    if (!ctx || !d_ptr) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "curvis_peer_buffer_destroy: null argument");
+    CURVIS_CUDA(ctx, cudaSetDevice(ctx->devs[0].ordinal));
+    CURVIS_CUDA(ctx, cudaFree(d_ptr));
     return CURVIS_OK;
 }
 

@@ -70,6 +70,11 @@ struct FrameParams {
     const double2* shape_tab;
     // scene (systems.rs:70-71): [0] = background_positive, [1] = background_negative
     Background bg[2];
+    // Fused render + all-gather (curvis_render_frames_peers): n_peers > 0 = every finished ray stores its RGB8
+    // into the COMPLETE frames of all peers (own device + peer devices mapped over NVLink), frame f at byte
+    // offset f*W*H*3, so the row tiles are "gathered" by the render kernel itself and no collective moves pixels
+    uint8_t* out_peers[CURVIS_MAX_PEERS];
+    uint32_t n_peers, _pad3;
     // outputs: RGB8 rows of the tile (packed, row-major), optional per-ray records, counters
     uint8_t* out_rgb8;
     float4* out_rgba32f;     // optional: the unrounded colour of every ray (RGBA, 0..255 scale)

@@ -387,7 +387,7 @@ __device__ __forceinline__ void finish_ray(const FrameParams& p, const Ray& q, i
     if (side > 0) ++tally.pos; else if (side < 0) ++tally.neg; else ++tally.none;   // none: black, systems.rs:556-558
     tally.steps += steps;
     uint32_t tx = 0, ty = 0;
-    if (p.out_rgb8 || p.out_rgba32f) {
+    if (p.out_rgb8 || p.out_rgba32f || p.n_peers) {
         uint32_t rgba = 0;
         float4 tap = make_float4(0.f, 0.f, 0.f, 255.f);        // Rgba([0, 0, 0, 255])
         if (side != 0) {
@@ -416,6 +416,18 @@ __device__ __forceinline__ void finish_ray(const FrameParams& p, const Ray& q, i
             o[2] = (uint8_t)((rgba >> 16) & 0xffu);
         }
         if (p.out_rgba32f) p.out_rgba32f[ray] = tap;
+        if (p.n_peers) {
+            // fused all-gather: this pixel into the complete frame of every peer (frame_params.h)
+            const unsigned long long tile_rays = (unsigned long long)(p.row_end - p.row_begin) * p.width;
+            const unsigned long long f = ray / tile_rays, in_tile = ray - f * tile_rays;
+            const size_t off = (((size_t)f * p.height + p.row_begin) * p.width + in_tile) * 3;
+            for (uint32_t i = 0; i < p.n_peers; ++i) {
+                uint8_t* o = p.out_peers[i] + off;
+                o[0] = (uint8_t)(rgba & 0xffu);
+                o[1] = (uint8_t)((rgba >> 8) & 0xffu);
+                o[2] = (uint8_t)((rgba >> 16) & 0xffu);
+            }
+        }
     }
     if (p.records) {
         curvis_ray_record rec;

@@ -80,6 +80,43 @@ class Context:
         return f64.value, f32.value
 
 
+class PeerBuffer:
+    """A device buffer other ranks' GPUs write into (curvis_peer_buffer_*): ``PeerBuffer.create`` allocates it on
+    the context's first device and exposes ``handle`` (64 bytes, CUDA IPC) to send to the peers;
+    ``PeerBuffer.open`` maps a peer's buffer from its handle.  ``ptr`` is the device pointer;
+    ``as_tensor()`` views it as a torch uint8 tensor (no copy)."""
+
+    def __init__(self, context: "Context", ptr: int, nbytes: int, handle: Optional[bytes], owned: bool):
+        self.context, self.ptr, self.nbytes, self.handle, self._owned = context, ptr, nbytes, handle, owned
+
+    @classmethod
+    def create(cls, context: "Context", nbytes: int) -> "PeerBuffer":
+        ptr, handle = C.c_void_p(), C.create_string_buffer(_abi.IPC_HANDLE_BYTES)
+        _abi.check(context._lib.curvis_peer_buffer_create(context.ptr, int(nbytes), C.byref(ptr), handle), context.ptr)
+        return cls(context, ptr.value, int(nbytes), handle.raw, True)
+
+    @classmethod
+    def open(cls, context: "Context", handle: bytes, nbytes: int) -> "PeerBuffer":
+        ptr = C.c_void_p()
+        _abi.check(context._lib.curvis_peer_buffer_open(context.ptr, C.create_string_buffer(handle, _abi.IPC_HANDLE_BYTES), C.byref(ptr)), context.ptr)
+        return cls(context, ptr.value, int(nbytes), None, False)
+
+    def as_tensor(self, device_index: int = 0):
+        import torch
+
+        class _Raw:
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 3}
+        return torch.as_tensor(raw, device=torch.device("cuda", device_index))
+
+    def close(self) -> None:
+        if self.ptr:
+            fn = self.context._lib.curvis_peer_buffer_destroy if self._owned else self.context._lib.curvis_peer_buffer_close
+            _abi.check(fn(self.context.ptr, C.c_void_p(self.ptr)), self.context.ptr)
+            self.ptr = 0
+
+
 class RelativisticSystem:
     """``RelativisticSystem::new(metric, background_positive, background_negative, camera)``
     (src/systems.rs:283-285).  The backgrounds are uploaded to every device of the context once,
@@ -183,6 +220,25 @@ class RelativisticSystem:
             self.context.ptr, C.byref(m), arr, len(cameras), C.byref(sim), int(row_begin), int(row_end),
             C.c_void_p(out_ptr), C.c_void_p(stream_ptr) if stream_ptr else None,
             C.byref(stats) if stats is not None else None), self.context.ptr)
+        if stats is not None:
+            self.last_stats = stats.as_dict()
+            return self.last_stats
+        return None
+
+    def render_frames_peers(self, cameras, max_iterations: int, max_radius: float, delta: float, row_begin: int, row_end: int,
+                            frame_ptrs, stream_ptr: int = 0, want_stats: bool = False, **options):
+        """Fused render + all-gather (curvis_render_frames_peers): rows [row_begin,row_end) of one frame per
+        camera in ONE launch, every pixel stored into the complete-frames buffer of every peer
+        (``frame_ptrs``: device pointers — this rank's PeerBuffer and the opened ones of its peers)."""
+        arr = (_abi.CurvisCamera * len(cameras))(*[c.as_c() if hasattr(c, "as_c") else c for c in cameras])
+        ptrs = (C.c_void_p * len(frame_ptrs))(*[C.c_void_p(int(x)) for x in frame_ptrs])
+        sim = self._sim(max_iterations, max_radius, delta, **options)
+        stats = _abi.CurvisStats() if want_stats else None
+        m = self.metric.as_c()
+        _abi.check(self._lib.curvis_render_frames_peers(
+            self.context.ptr, C.byref(m), arr, len(cameras), C.byref(sim), int(row_begin), int(row_end),
+            ptrs, len(frame_ptrs), C.c_void_p(stream_ptr) if stream_ptr else None, C.byref(stats) if stats is not None else None),
+            self.context.ptr)
         if stats is not None:
             self.last_stats = stats.as_dict()
             return self.last_stats

@@ -182,6 +182,30 @@ int curvis_metric_validate(const curvis_metric* metric);
 int curvis_set_background(curvis_ctx* ctx, int side, const uint8_t* rgba8,
                           uint32_t width, uint32_t height, const double inv_rot[9]);
 
+/* ---- fused render + all-gather over NVLink peer memory (one rank per GPU) -------------------
+ * curvis_render_frames_device leaves this rank's row tiles on its own device and the host program
+ * all-gathers them (NCCL).  The fused form needs no collective for the pixels: every rank owns one
+ * device buffer holding the COMPLETE frames of a step (n_frames * W*H*3 bytes, frame-major), exports
+ * it to its peers (CUDA IPC), and the render kernel of every rank stores each finished ray's RGB8
+ * straight into all of them — its own and, over NVLink, its peers'.  After the launch a rank only
+ * has to learn that its peers' kernels have ended (any barrier on the stream, e.g. a 4-byte
+ * all-reduce) before it reads its buffer.
+ *   curvis_peer_buffer_create  cudaMalloc on the context's first device + the 64-byte IPC handle to send to the peers
+ *   curvis_peer_buffer_open    maps a peer's buffer from its handle (another process on the same node)
+ *   curvis_peer_buffer_close   unmaps an opened buffer;  curvis_peer_buffer_destroy frees a created one
+ *   curvis_render_frames_peers rows [row_begin,row_end) of n_frames frames in ONE launch, stored into
+ *                              d_frames[0..n_peers) (device pointers valid on this device: own buffer and
+ *                              opened peers; n_peers <= CURVIS_MAX_PEERS).  Asynchronous on `stream` unless stats. */
+#define CURVIS_MAX_PEERS 8
+#define CURVIS_IPC_HANDLE_BYTES 64
+int curvis_peer_buffer_create(curvis_ctx* ctx, size_t bytes, void** d_ptr, uint8_t ipc_handle[CURVIS_IPC_HANDLE_BYTES]);
+int curvis_peer_buffer_open(curvis_ctx* ctx, const uint8_t ipc_handle[CURVIS_IPC_HANDLE_BYTES], void** d_ptr);
+int curvis_peer_buffer_close(curvis_ctx* ctx, void* d_ptr);
+int curvis_peer_buffer_destroy(curvis_ctx* ctx, void* d_ptr);
+int curvis_render_frames_peers(curvis_ctx* ctx, const curvis_metric* metric, const curvis_camera* cameras, uint32_t n_frames,
+                               const curvis_sim* sim, uint32_t row_begin, uint32_t row_end,
+                               void* const* d_frames, uint32_t n_peers, void* stream, curvis_stats* stats);
+
 /* Optional: page-locks a caller-owned host buffer that will be passed as `out_rgb8` to
  * curvis_render_image / curvis_render_rows again and again (the frame buffer of a video loop; the
  * reference allocates a fresh DynamicImage per frame, systems.rs:314, a binding would keep one).

@@ -326,3 +326,41 @@ def test_registered_host_frame(gpu_ctx):
         gpu_ctx.unregister_host_buffer(buf)
     sysm.render_image(*sim, out=buf[0])
     assert (buf[0] == plain).all()
+
+
+def test_fused_render_and_gather_into_peer_buffers(gpu_ctx):
+    """curvis_render_frames_peers: the kernel stores every pixel into the complete-frames buffer of every
+    peer, so after all row tiles have been rendered each buffer holds every complete frame — no collective.
+    One device here: two buffers stand for two ranks; "rank" g renders rows [g*H/2, (g+1)*H/2) of both
+    frames into both buffers.  The result equals curvis_render_image of each frame, for every precision."""
+    import torch
+    import curvis_b200 as cv
+    from curvis_b200 import _abi, scenes
+    bp, bn = scenes.decodable_background(1024, 512), scenes.decodable_background(1024, 512, True)
+    W, H, sim = 160, 90, (300, 12.0, 0.1)
+    cams = [cv.Camera((0.0, 5.0 + 0.3 * f, 1.4, 0.2 * f), scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP, 15.0, 43.0, W, H) for f in range(2)]
+    sysm = cv.RelativisticSystem(cv.EllisMetric(1.0), cv.SphericalImage(bp), cv.SphericalImage(bn), cams[0], context=gpu_ctx)
+    bufs = [cv.PeerBuffer.create(gpu_ctx, 2 * W * H * 3) for _ in range(2)]
+    try:
+        assert all(len(b.handle) == _abi.IPC_HANDLE_BYTES for b in bufs)
+        for prec in (_abi.PRECISION_F64, _abi.PRECISION_F64_FAST, _abi.PRECISION_F32):
+            want = []
+            for cam in cams:
+                one = cv.RelativisticSystem(cv.EllisMetric(1.0), cv.SphericalImage(bp), cv.SphericalImage(bn), cam, context=gpu_ctx)
+                want.append(one.render_image(*sim, precision=prec).copy())
+            for b in bufs:
+                b.as_tensor().fill_(7)
+            total = 0
+            for g, (r0, r1) in enumerate(((0, 41), (41, H))):                   # ragged tiles
+                st = sysm.render_frames_peers(cams, *sim, r0, r1, [b.ptr for b in bufs], want_stats=True, precision=prec)
+                total += st["n_rays"]
+            assert total == 2 * W * H
+            torch.cuda.synchronize()
+            for b in bufs:
+                got = b.as_tensor().cpu().numpy().reshape(2, H, W, 3)
+                assert (got[0] == want[0]).all() and (got[1] == want[1]).all(), prec
+        with pytest.raises(cv.CurvisError):
+            sysm.render_frames_peers(cams, *sim, 0, H, [b.ptr for b in bufs] * 5)    # more than CURVIS_MAX_PEERS
+    finally:
+        for b in bufs:
+            b.close()
