@@ -174,7 +174,7 @@ def load_library() -> C.CDLL:
     lib.curvis_peer_buffer_close.argtypes = [vp, vp]
     lib.curvis_peer_buffer_destroy.argtypes = [vp, vp]
     lib.curvis_render_frames_peers.argtypes = [vp, C.POINTER(CurvisMetric), C.POINTER(CurvisCamera), C.c_uint32, C.POINTER(CurvisSim),
-                                               C.c_uint32, C.c_uint32, C.POINTER(vp), C.c_uint32, vp, C.POINTER(CurvisStats)]
+                                               C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp), C.c_uint32, vp, C.POINTER(CurvisStats)]
     lib.curvis_host_register.argtypes = [vp, vp, C.c_size_t]
     lib.curvis_host_unregister.argtypes = [vp, vp]
     lib.curvis_debug_shape_table_host.argtypes = [dp, dp, dp, C.c_size_t]

@@ -143,7 +143,7 @@ static void fill_params(const curvis_ctx* ctx, const DeviceState& d, const curvi
     p.max_iterations = sim->max_iterations; p.sampling = (uint32_t)sim->sampling;
     p.integrator = (uint32_t)sim->integrator;
     p.max_radius = sim->max_radius; p.delta = sim->delta;
-    p.row_begin = row_begin; p.row_end = row_end;
+    p.row_begin = row_begin; p.row_end = row_end; p.row_stride = 1;
     p.f_rho = (float)metric->rho; p.f_rho2 = (float)(metric->rho * metric->rho);
     p.f_m = (float)metric->m; p.f_a = (float)metric->a;
     p.f_xscale = (float)(2.0 / (3.14159265358979323846 * metric->m));
@@ -397,7 +397,8 @@ extern "C" int curvis_render_rows_device(curvis_ctx* ctx, const curvis_metric* m
 static int render_frames_impl(curvis_ctx* ctx, const curvis_metric* metric,
                               const curvis_camera* cameras, uint32_t n_frames, const curvis_sim* sim,
                               uint32_t row_begin, uint32_t row_end,
-                              void* d_out_rgb8_tiles, void* const* d_peer_frames, uint32_t n_peers, void* stream, curvis_stats* stats) {
+                              void* d_out_rgb8_tiles, void* const* d_peer_frames, uint32_t n_peers, uint32_t row_stride, void* stream,
+                              curvis_stats* stats) {
     const auto t0 = std::chrono::steady_clock::now();
     if (!ctx) return fail(nullptr, CURVIS_ERR_INVALID_ARGUMENT, "null context");
     if (!cameras || n_frames == 0) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "no cameras");
@@ -433,6 +434,10 @@ static int render_frames_impl(curvis_ctx* ctx, const curvis_metric* metric,
     p.cameras = d.d_cameras; p.n_frames = n_frames;
     p.n_peers = n_peers;
     for (uint32_t i = 0; i < n_peers; ++i) p.out_peers[i] = (uint8_t*)d_peer_frames[i];
+    // strided rows: the kernels index a tile of n_rows rows; p.row_end - p.row_begin is that count
+    const uint32_t n_rows = (row_end - row_begin + row_stride - 1) / row_stride;
+    p.row_stride = row_stride;
+    p.row_end = row_begin + n_rows;
     CURVIS_CUDA(ctx, cudaMemsetAsync(d.d_counters, 0, sizeof(DeviceCounters), st));
     CURVIS_CUDA(ctx, cudaEventRecord(d.ev_begin, st));
     if (row_end > row_begin) CURVIS_CUDA(ctx, launch_render(p, metric, sim, ctx->tuning, d.sm_count, st));
@@ -441,7 +446,7 @@ static int render_frames_impl(curvis_ctx* ctx, const curvis_metric* metric,
         CURVIS_CUDA(ctx, cudaMemcpyAsync(d.h_counters, d.d_counters, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, st));
         CURVIS_CUDA(ctx, cudaStreamSynchronize(st));
         std::memset(stats, 0, sizeof *stats);
-        add_counters(*d.h_counters, (uint64_t)(row_end - row_begin) * cameras[0].resolution_width * n_frames, stats);
+        add_counters(*d.h_counters, (uint64_t)n_rows * cameras[0].resolution_width * n_frames, stats);
         float ms = 0.f;
         CURVIS_CUDA(ctx, cudaEventElapsedTime(&ms, d.ev_begin, d.ev_end));
         stats->kernel_ms = ms;
@@ -454,14 +459,15 @@ extern "C" int curvis_render_frames_device(curvis_ctx* ctx, const curvis_metric*
                                            const curvis_camera* cameras, uint32_t n_frames, const curvis_sim* sim,
                                            uint32_t row_begin, uint32_t row_end,
                                            void* d_out_rgb8_tiles, void* stream, curvis_stats* stats) {
-    return render_frames_impl(ctx, metric, cameras, n_frames, sim, row_begin, row_end, d_out_rgb8_tiles, nullptr, 0, stream, stats);
+    return render_frames_impl(ctx, metric, cameras, n_frames, sim, row_begin, row_end, d_out_rgb8_tiles, nullptr, 0, 1, stream, stats);
 }
 
 extern "C" int curvis_render_frames_peers(curvis_ctx* ctx, const curvis_metric* metric, const curvis_camera* cameras, uint32_t n_frames,
-                                          const curvis_sim* sim, uint32_t row_begin, uint32_t row_end,
+                                          const curvis_sim* sim, uint32_t row_begin, uint32_t row_end, uint32_t row_stride,
                                           void* const* d_frames, uint32_t n_peers, void* stream, curvis_stats* stats) {
     if (n_peers == 0) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "curvis_render_frames_peers: no peer buffers");
-    return render_frames_impl(ctx, metric, cameras, n_frames, sim, row_begin, row_end, nullptr, d_frames, n_peers, stream, stats);
+    if (row_stride == 0) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "curvis_render_frames_peers: row_stride must be at least 1");
+    return render_frames_impl(ctx, metric, cameras, n_frames, sim, row_begin, row_end, nullptr, d_frames, n_peers, row_stride, stream, stats);
 }
 
 extern "C" int curvis_peer_buffer_create(curvis_ctx* ctx, size_t bytes, void** d_ptr, uint8_t ipc_handle[CURVIS_IPC_HANDLE_BYTES]) {

@@ -74,7 +74,9 @@ struct FrameParams {
     // into the COMPLETE frames of all peers (own device + peer devices mapped over NVLink), frame f at byte
     // offset f*W*H*3, so the row tiles are "gathered" by the render kernel itself and no collective moves pixels
     uint8_t* out_peers[CURVIS_MAX_PEERS];
-    uint32_t n_peers, _pad3;
+    // row_stride > 1 (peers launches only): the launch renders rows row_begin + k*row_stride, k in [0, row_end - row_begin)
+    // — interleaved row ownership, which gives every rank statistically the same work
+    uint32_t n_peers, row_stride;
     // outputs: RGB8 rows of the tile (packed, row-major), optional per-ray records, counters
     uint8_t* out_rgb8;
     float4* out_rgba32f;     // optional: the unrounded colour of every ray (RGBA, 0..255 scale)

@@ -153,10 +153,10 @@ __device__ __forceinline__ void new_photon_for_ray(const FrameParams& p, unsigne
     if (p.ray_dirs) {
         new_photon_from_direction(p.cam, p.ray_dirs[3 * idx], p.ray_dirs[3 * idx + 1], p.ray_dirs[3 * idx + 2], q);
     } else if (p.n_frames <= 1) {
-        new_photon_from_camera(p.cam, p.width, p.height, (uint32_t)(idx % p.width), p.row_begin + (uint32_t)(idx / p.width), q);
+        new_photon_from_camera(p.cam, p.width, p.height, (uint32_t)(idx % p.width), p.row_begin + (uint32_t)(idx / p.width) * p.row_stride, q);
     } else {
         const unsigned long long f = idx / tile_rays, r = idx % tile_rays;
-        new_photon_from_camera(p.cameras[f], p.width, p.height, (uint32_t)(r % p.width), p.row_begin + (uint32_t)(r / p.width), q);
+        new_photon_from_camera(p.cameras[f], p.width, p.height, (uint32_t)(r % p.width), p.row_begin + (uint32_t)(r / p.width) * p.row_stride, q);
     }
 }
 
@@ -420,7 +420,8 @@ __device__ __forceinline__ void finish_ray(const FrameParams& p, const Ray& q, i
             // fused all-gather: this pixel into the complete frame of every peer (frame_params.h)
             const unsigned long long tile_rays = (unsigned long long)(p.row_end - p.row_begin) * p.width;
             const unsigned long long f = ray / tile_rays, in_tile = ray - f * tile_rays;
-            const size_t off = (((size_t)f * p.height + p.row_begin) * p.width + in_tile) * 3;
+            const unsigned long long k = in_tile / p.width, px = in_tile - k * p.width;
+            const size_t off = (((size_t)f * p.height + p.row_begin + (size_t)k * p.row_stride) * p.width + px) * 3;
             for (uint32_t i = 0; i < p.n_peers; ++i) {
                 uint8_t* o = p.out_peers[i] + off;
                 o[0] = (uint8_t)(rgba & 0xffu);

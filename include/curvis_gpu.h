@@ -193,9 +193,12 @@ int curvis_set_background(curvis_ctx* ctx, int side, const uint8_t* rgba8,
  *   curvis_peer_buffer_create  cudaMalloc on the context's first device + the 64-byte IPC handle to send to the peers
  *   curvis_peer_buffer_open    maps a peer's buffer from its handle (another process on the same node)
  *   curvis_peer_buffer_close   unmaps an opened buffer;  curvis_peer_buffer_destroy frees a created one
- *   curvis_render_frames_peers rows [row_begin,row_end) of n_frames frames in ONE launch, stored into
- *                              d_frames[0..n_peers) (device pointers valid on this device: own buffer and
- *                              opened peers; n_peers <= CURVIS_MAX_PEERS).  Asynchronous on `stream` unless stats. */
+ *   curvis_render_frames_peers rows row_begin, row_begin + row_stride, ... (< row_end) of n_frames frames in ONE
+ *                              launch, stored into d_frames[0..n_peers) (device pointers valid on this device:
+ *                              own buffer and opened peers; n_peers <= CURVIS_MAX_PEERS).  row_stride = 1: a
+ *                              contiguous tile; rank g of N with (row_begin, row_stride) = (g, N): interleaved rows,
+ *                              which gives every rank the same mix of short and long rays (the pixels land in place
+ *                              either way).  Asynchronous on `stream` unless stats. */
 #define CURVIS_MAX_PEERS 8
 #define CURVIS_IPC_HANDLE_BYTES 64
 int curvis_peer_buffer_create(curvis_ctx* ctx, size_t bytes, void** d_ptr, uint8_t ipc_handle[CURVIS_IPC_HANDLE_BYTES]);
@@ -203,7 +206,7 @@ int curvis_peer_buffer_open(curvis_ctx* ctx, const uint8_t ipc_handle[CURVIS_IPC
 int curvis_peer_buffer_close(curvis_ctx* ctx, void* d_ptr);
 int curvis_peer_buffer_destroy(curvis_ctx* ctx, void* d_ptr);
 int curvis_render_frames_peers(curvis_ctx* ctx, const curvis_metric* metric, const curvis_camera* cameras, uint32_t n_frames,
-                               const curvis_sim* sim, uint32_t row_begin, uint32_t row_end,
+                               const curvis_sim* sim, uint32_t row_begin, uint32_t row_end, uint32_t row_stride,
                                void* const* d_frames, uint32_t n_peers, void* stream, curvis_stats* stats);
 
 /* Optional: page-locks a caller-owned host buffer that will be passed as `out_rgb8` to

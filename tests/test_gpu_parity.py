@@ -350,15 +350,19 @@ def test_fused_render_and_gather_into_peer_buffers(gpu_ctx):
                 want.append(one.render_image(*sim, precision=prec).copy())
             for b in bufs:
                 b.as_tensor().fill_(7)
-            total = 0
-            for g, (r0, r1) in enumerate(((0, 41), (41, H))):                   # ragged tiles
-                st = sysm.render_frames_peers(cams, *sim, r0, r1, [b.ptr for b in bufs], want_stats=True, precision=prec)
-                total += st["n_rays"]
-            assert total == 2 * W * H
-            torch.cuda.synchronize()
-            for b in bufs:
-                got = b.as_tensor().cpu().numpy().reshape(2, H, W, 3)
-                assert (got[0] == want[0]).all() and (got[1] == want[1]).all(), prec
+            # contiguous ragged tiles, then interleaved rows (rank g of 3 renders rows g, g+3, ...)
+            for tiles in (((0, 41, 1), (41, H, 1)), ((0, H, 3), (1, H, 3), (2, H, 3))):
+                for b in bufs:
+                    b.as_tensor().fill_(7)
+                total = 0
+                for r0, r1, stride in tiles:
+                    st = sysm.render_frames_peers(cams, *sim, r0, r1, [b.ptr for b in bufs], want_stats=True, row_stride=stride, precision=prec)
+                    total += st["n_rays"]
+                assert total == 2 * W * H
+                torch.cuda.synchronize()
+                for b in bufs:
+                    got = b.as_tensor().cpu().numpy().reshape(2, H, W, 3)
+                    assert (got[0] == want[0]).all() and (got[1] == want[1]).all(), (prec, tiles)
         with pytest.raises(cv.CurvisError):
             sysm.render_frames_peers(cams, *sim, 0, H, [b.ptr for b in bufs] * 5)    # more than CURVIS_MAX_PEERS
     finally:
