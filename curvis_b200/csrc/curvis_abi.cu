@@ -136,9 +136,16 @@ static void fill_params(const curvis_ctx* ctx, const DeviceState& d, const curvi
     p.rho = metric->rho; p.m = metric->m; p.a = metric->a;
     fill_camera(metric, cam, p.cam);
     p.cameras = nullptr; p.n_frames = 1;
-    // auto: 32 steps between refill points; 64 for CURVIS_PRECISION_F64_FAST, whose per-window work (sin/cos
-    // re-derived from theta) is larger and whose steps are shorter (tools/window_sweep.py)
-    p.window = (uint32_t)(ctx->tuning.window > 0 ? ctx->tuning.window : (sim->precision == CURVIS_PRECISION_F64_FAST ? 64 : 32));
+    // auto: 32 steps between refill points.  CURVIS_PRECISION_F64_FAST has more per-window work (sin/cos re-derived
+    // from theta) and shorter steps, so its window grows with the expected ray length (R + |l_camera|) / |delta| — a
+    // photon moves ~delta per step — as length/16 clamped to [32, 128]: 128 at the default settings (2100 steps per
+    // ray), 32 for a 150-step frame (tools/window_sweep.py: 4K Ellis 38.4 / 37.2 / 36.7 / 36.5 ms at 32 / 64 / 128 / 256)
+    uint32_t auto_window = 32;
+    if (sim->precision == CURVIS_PRECISION_F64_FAST) {
+        const double expected_steps = (std::fabs(sim->max_radius) + std::fabs(cam->position[1])) / std::fabs(sim->delta);
+        auto_window = expected_steps >= 2048.0 ? 128u : (expected_steps >= 512.0 ? (uint32_t)(expected_steps / 16.0) : 32u);   // NaN -> 32
+    }
+    p.window = (uint32_t)(ctx->tuning.window > 0 ? ctx->tuning.window : auto_window);
     p.width = cam->resolution_width; p.height = cam->resolution_height;
     p.max_iterations = sim->max_iterations; p.sampling = (uint32_t)sim->sampling;
     p.integrator = (uint32_t)sim->integrator;

@@ -11,7 +11,7 @@ struct LaunchTuning {
     int kernel_variant = 3;  // 0 plain operators + CUDA sincos (round-1 v0); 1 unguarded IEEE sequences + CUDA sincos;
                              // 2 + in-kernel sincos; 3 (default) lean loop: integer-pipe guards, gated escape test
     int blocks_per_sm = 0;   // 0 = occupancy maximum
-    int window = 0;          // Euler steps between two refill points of a warp; 0 = auto (32; 64 in F64_FAST)
+    int window = 0;          // Euler steps between two refill points of a warp; 0 = auto (32; 32..128 in F64_FAST)
     int zero_copy = 1;       // curvis_render_image into a registered host frame: 1 (default) = the kernel stores its pixels
                              // straight into it (measured: kernel time unchanged, 0.04 ms exposed); 0 = device frame + one DMA (0.5 ms)
     int fast_variant = 1;    // CURVIS_PRECISION_F64_FAST: 0 sin/cos from theta every step; 1 (default) (sin, cos) carried and

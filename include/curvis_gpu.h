@@ -314,8 +314,8 @@ int curvis_measure_fma_peak(curvis_ctx* ctx, double* fp64_tflops, double* fp32_t
  *                     sincos; 2 unguarded IEEE sequences + in-kernel sincos; 3 (default) the same
  *                     arithmetic in the lean loop (integer-pipe guards, gated escape test)
  *   "blocks_per_sm":  resident CTAs per SM of the persistent grid (0 = occupancy maximum)
- *   "window":         Euler steps between two refill points of a warp (0 = default: 32, and 64 for
- *                     CURVIS_PRECISION_F64_FAST)
+ *   "window":         Euler steps between two refill points of a warp (0 = default: 32; for
+ *                     CURVIS_PRECISION_F64_FAST 32..128, growing with the expected ray length)
  *   "zero_copy":      curvis_render_image into a buffer registered with curvis_host_register: 1 (default)
  *                     = the kernel stores its pixels straight into the mapped host frame (no device
  *                     frame, no copy; 3 bytes per ray over PCIe do not slow the kernel); 0 = device

@@ -20,7 +20,7 @@ for kind in kinds:
     ref_stats = dict(sysm.last_stats)
     res = dict(kind=kind, f64_kernel_ms=ref_stats["kernel_ms"], total_steps=ref_stats["total_steps"])
     for variant in (0, 1):
-        for window in (32, 64):
+        for window in ((32, 64) if variant == 0 else (0, 64, 128, 256)):
             ctx.set_option("fast_variant", variant)
             ctx.set_option("window", window)
             ms = []

@@ -10,8 +10,8 @@ kind = sys.argv[1] if len(sys.argv) > 1 else "ellis"
 metric = cv.EllisMetric(1.0) if kind == "ellis" else cv.InterstellarMetric(0.1, 1e-4, 1.0)
 sysm = cv.RelativisticSystem(metric, cv.SphericalImage(bp), cv.SphericalImage(bn), cam, context=ctx)
 sim = (40000, 100.0, 0.05)
-for bps in (0, 5, 4):
-    for window in (16, 32, 48, 64, 96, 128, 256):
+for bps in (0, 5):
+    for window in (32, 64, 96, 128, 192, 256):
         ctx.set_option("window", window); ctx.set_option("blocks_per_sm", bps)
         ms = []
         for _ in range(3):
