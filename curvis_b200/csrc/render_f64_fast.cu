@@ -202,14 +202,17 @@ template <class Fast>
 __device__ __forceinline__ uint32_t fast_window_scaled(const FrameParams& p, const RotRegs& rr, Ray& q, uint32_t n, unsigned gate,
                                                        double R, bool& stop, bool& slow) {
     uint32_t k = 0;
+    // phi += P_phi * w every step (:240): the w's are summed (a two-operand DADD issues faster than a DFMA with three
+    // distinct registers) and folded into phi once, when the window is left
+    double wsum = 0.0;
     for (;;) {
-        if (abs_hi(q.th) >= pow2_hi(30)) { slow = true; return k; }
+        if (abs_hi(q.th) >= pow2_hi(30)) { slow = true; break; }
         double sn, cn;
         sincos_fast(q.th, sn, cn);
         typename Fast::Pre pre;
         double s2 = sn * sn;
         double d = Fast::prepare(p, q.l, s2, pre);
-        if (!in_window_nonneg(d)) { slow = true; return k; }
+        if (!in_window_nonneg(d)) { slow = true; break; }
         double dth;
         for (;;) {
             double w, u, v, f;
@@ -220,7 +223,7 @@ __device__ __forceinline__ uint32_t fast_window_scaled(const FrameParams& p, con
             const double b2 = fma(q.pth, q.pth, pv);            // :257
             q.l = q.l + q.pl;                                   // :238, :295
             q.th = q.th + dth;
-            q.ph = fma(q.pph, w, q.ph);                         // :240
+            wsum = wsum + w;                                    // :240, folded below
             q.pl = fma(b2, f, q.pl);                            // :261, :296
             q.pth = fma(pv * cs, w, q.pth);                     // :262
             rotate_sincos(rr, dth, sn, cn);
@@ -230,12 +233,14 @@ __device__ __forceinline__ uint32_t fast_window_scaled(const FrameParams& p, con
             if ((k >= n) | (abs_hi(q.l) >= gate) | (abs_hi(dth) >= pow2_hi(-4)) | !in_window_nonneg(d)) break;
         }
         if (abs_hi(q.l) >= gate) {
-            if ((q.l > R) || (q.l < -R) || (q.l != q.l)) { stop = true; return k; }       // systems.rs:129-134
+            if ((q.l > R) || (q.l < -R) || (q.l != q.l)) { stop = true; break; }          // systems.rs:129-134
         }
-        if (k >= n) return k;
-        if (!(abs_hi(dth) >= pow2_hi(-4)) && !in_window_nonneg(d)) { slow = true; return k; }
+        if (k >= n) break;
+        if (!(abs_hi(dth) >= pow2_hi(-4)) && !in_window_nonneg(d)) { slow = true; break; }
         // |dtheta| too large for the rotation (or a false alarm of the radius gate): re-derive (sin, cos) and go on
     }
+    q.ph = fma(q.pph, wsum, q.ph);
+    return k;
 }
 
 // Parity steps for a lane whose operands left the safe window: plain operators, reference
