@@ -43,6 +43,7 @@ struct DeviceState {
     curvis_ray_record* d_records = nullptr; size_t d_records_cap = 0;
     CameraBlock* d_cameras = nullptr; size_t d_cameras_cap = 0;   // batched launches
     double2* d_shape_tab = nullptr;   // Interstellar shape-function table (shape_table.h), uploaded at context creation
+    float4* d_shape_tab32 = nullptr;  // its fp32 edition
     cudaEvent_t chunk_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // pipelined read-back
     // tile of the frame in flight
     uint32_t row_begin = 0, row_end = 0;
@@ -158,6 +159,7 @@ static void fill_params(const curvis_ctx* ctx, const DeviceState& d, const curvi
     p.d_rho2 = metric->rho * metric->rho;
     p.d_xscale = 2.0 / (3.14159265358979323846 * metric->m);
     p.shape_tab = d.d_shape_tab;
+    p.shape_tab32 = d.d_shape_tab32;
     // below this |l| no escape test is needed in the fp32 kernel (4 steps of slack at |p_l| <= ~1.3)
     p.f_near_radius = (float)(std::fabs(sim->max_radius) - 6.0 * std::fabs(sim->delta) - 1e-3 * std::fabs(sim->max_radius));
     for (int s = 0; s < 2; ++s) {
@@ -270,6 +272,7 @@ static void release_device(DeviceState& d) {
     if (d.d_records) cudaFree(d.d_records);
     if (d.d_cameras) cudaFree(d.d_cameras);
     if (d.d_shape_tab) cudaFree(d.d_shape_tab);
+    if (d.d_shape_tab32) cudaFree(d.d_shape_tab32);
     for (auto& ev : d.chunk_done) if (ev) cudaEventDestroy(ev);
     if (d.ev_begin) cudaEventDestroy(d.ev_begin);
     if (d.ev_end) cudaEventDestroy(d.ev_end);
@@ -311,6 +314,8 @@ extern "C" int curvis_ctx_create(const int* devices, int n_devices, curvis_ctx**
     ctx->devs.resize(ords.size());
     std::vector<double> shape_tab(kShapeTabIntervals * kShapeTabDoubles);
     build_interstellar_shape_table(shape_tab.data());
+    std::vector<float> shape_tab32(kShapeTab32Intervals * kShapeTab32Floats);
+    build_interstellar_shape_table_f32(shape_tab32.data());
     for (size_t i = 0; i < ords.size(); ++i) {
         DeviceState& d = ctx->devs[i];
         const int ord = ords[i];
@@ -331,6 +336,9 @@ extern "C" int curvis_ctx_create(const int* devices, int n_devices, curvis_ctx**
             else if ((e = cudaMalloc(&d.d_shape_tab, shape_tab.size() * sizeof(double))) != cudaSuccess) rc = cuda_fail(nullptr, e, "cudaMalloc(shape table)");
             else if ((e = cudaMemcpy(d.d_shape_tab, shape_tab.data(), shape_tab.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess)
                 rc = cuda_fail(nullptr, e, "cudaMemcpy(shape table)");
+            else if ((e = cudaMalloc(&d.d_shape_tab32, shape_tab32.size() * sizeof(float))) != cudaSuccess) rc = cuda_fail(nullptr, e, "cudaMalloc(shape table f32)");
+            else if ((e = cudaMemcpy(d.d_shape_tab32, shape_tab32.data(), shape_tab32.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess)
+                rc = cuda_fail(nullptr, e, "cudaMemcpy(shape table f32)");
         }
         if (rc != CURVIS_OK) {
             curvis_ctx_destroy(ctx);
@@ -649,8 +657,9 @@ extern "C" int curvis_debug_eval(curvis_ctx* ctx, int op, const double* a, const
         (!b || (e = cudaMalloc(&db, bytes ? bytes : 8)) == cudaSuccess) &&
         (e = cudaMemcpyAsync(da, a, bytes, cudaMemcpyHostToDevice, d.stream)) == cudaSuccess &&
         (!b || (e = cudaMemcpyAsync(db, b, bytes, cudaMemcpyHostToDevice, d.stream)) == cudaSuccess) &&
-        (e = (op == 13 || op == 14) ? launch_debug_shape(d.d_shape_tab, op - 13, da, dout, n, d.stream)
-                                    : launch_debug_eval(op, da, db, dout, n, d.stream)) == cudaSuccess &&
+        (e = (op == 13 || op == 14)   ? launch_debug_shape(d.d_shape_tab, op - 13, da, dout, n, d.stream)
+             : (op == 15 || op == 16) ? launch_debug_shape32(d.d_shape_tab32, op - 15, da, dout, n, d.stream)
+                                      : launch_debug_eval(op, da, db, dout, n, d.stream)) == cudaSuccess &&
         (e = cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, d.stream)) == cudaSuccess)
         e = cudaStreamSynchronize(d.stream);
     if (e != cudaSuccess) rc = cuda_fail(ctx, e, "curvis_debug_eval");

@@ -68,6 +68,7 @@ struct FrameParams {
     double d_rho2, d_xscale;
     // Interstellar shape-function table of CURVIS_PRECISION_F64_FAST (shape_table.h), resident per device
     const double2* shape_tab;
+    const float4* shape_tab32;   // the fp32 edition for CURVIS_PRECISION_F32
     // scene (systems.rs:70-71): [0] = background_positive, [1] = background_negative
     Background bg[2];
     // Fused render + all-gather (curvis_render_frames_peers): n_peers > 0 = every finished ray stores its RGB8

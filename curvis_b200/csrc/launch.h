@@ -40,6 +40,8 @@ cudaError_t launch_debug_eval(int op, const double* a, const double* b, double* 
 // F(x) (which = 0) / G(x) (which = 1) of the Interstellar shape-function table as the fast kernel
 // evaluates them (test hook, curvis_debug_eval ops 13 / 14).  render_f64_fast.cu.
 cudaError_t launch_debug_shape(const double2* tab, int which, const double* x, double* out, size_t n, cudaStream_t stream);
+// The same for the fp32 table of CURVIS_PRECISION_F32 (ops 15 / 16; x is rounded to float first).  render_f32.cu.
+cudaError_t launch_debug_shape32(const float4* tab, int which, const double* x, double* out, size_t n, cudaStream_t stream);
 
 // FMA-only micro-kernels used as the measured compute-roofline denominator (peak_kernels.cu).
 cudaError_t measure_fma_peak(int sm_count, cudaStream_t stream, double* fp64_tflops, double* fp32_tflops);

@@ -28,6 +28,7 @@
 // or adjacent) and bench.py reports the measured deviation next to the throughput.
 #include "geodesic_f64.cuh"
 #include "launch.h"
+#include "shape_table.h"
 
 namespace curvis {
 
@@ -117,6 +118,28 @@ __device__ __forceinline__ void finish32_from_r(const Pre32FromR& pre, float y0,
     f = pre.rp * (y * u);            // r'/r^3
 }
 
+// F(x) = x atan x - ln(1+x^2)/2 and G(x) = atan x, x > 0 (shape_table.h): inside [2^-10, 2^16) two degree-3
+// polynomials in t = x - interval midpoint, coefficients from two 128-bit loads; outside, the library.
+__device__ __noinline__ float2 shape32_library(float x) {
+    const float G = atanf(x);
+    return make_float2(fmaf(x, G, -0.5f * log1pf(x * x)), G);
+}
+
+__device__ __forceinline__ void shape32_fg(const float4* tab, float x, float& F, float& G) {
+    const unsigned bits = (unsigned)__float_as_int(x);
+    const unsigned idx = (bits >> kShapeTab32Shift) - kShapeTab32Base;
+    if (idx < (unsigned)kShapeTab32Intervals) {
+        const float c = __int_as_float((int)((bits & ~((1u << kShapeTab32Shift) - 1u)) | (1u << (kShapeTab32Shift - 1))));
+        const float t = x - c;
+        const float4 a = __ldg(tab + 2 * idx), b = __ldg(tab + 2 * idx + 1);
+        F = fmaf(t, fmaf(t, fmaf(t, a.w, a.z), a.y), a.x);
+        G = fmaf(t, fmaf(t, fmaf(t, b.w, b.z), b.y), b.x);
+    } else {
+        const float2 fg = shape32_library(x);
+        F = fg.x; G = fg.y;
+    }
+}
+
 struct Shape32Interstellar {   // metrics.rs:461-485
     using Shape64 = ShapeInterstellar;
     using Pre = Pre32FromR;
@@ -125,9 +148,10 @@ struct Shape32Interstellar {   // metrics.rs:461-485
         pre.r = p.f_rho; pre.rp = 0.0f;
         if (al > p.f_a) {
             const float x = (al - p.f_a) * p.f_xscale;
-            const float at = atanf(x);
-            pre.r = fmaf(p.f_m, fmaf(x, at, -0.5f * __logf(fmaf(x, x, 1.0f))), p.f_rho);
-            pre.rp = copysignf(0.63661975f * at, l);
+            float F, G;
+            shape32_fg(p.shape_tab32, x, F, G);
+            pre.r = fmaf(p.f_m, F, p.f_rho);
+            pre.rp = copysignf(0.63661975f * G, l);
         }
         return pre.r * s2;
     }
@@ -298,6 +322,20 @@ cudaError_t launch32(const FrameParams& p, int sm_count, int blocks_per_sm_overr
 }
 
 }  // namespace
+
+__global__ void debug_shape32_kernel(const float4* tab, int which, const double* x, double* out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float F, G;
+    shape32_fg(tab, (float)x[i], F, G);
+    out[i] = (double)(which ? G : F);
+}
+
+cudaError_t launch_debug_shape32(const float4* tab, int which, const double* x, double* out, size_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    debug_shape32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(tab, which, x, out, n);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_render_f32(const FrameParams& p, int metric_kind, const LaunchTuning& t, int sm_count, cudaStream_t stream) {
     switch (metric_kind) {

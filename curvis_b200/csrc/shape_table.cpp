@@ -7,7 +7,6 @@ namespace curvis {
 
 namespace {
 
-constexpr int N = kShapeTabDegree + 1;
 const long double kPiL = 3.14159265358979323846264338327950288L;
 
 long double shape_f(long double x) { return x * atanl(x) - 0.5L * log1pl(x * x); }
@@ -16,6 +15,7 @@ long double shape_g(long double x) { return atanl(x); }
 // Monomial coefficients (in tau = t / w, |tau| <= 1) of the degree-(N-1) interpolant of f through
 // the N Chebyshev nodes of [c - w, c + w]: Chebyshev coefficients by the discrete cosine sums,
 // then the T_j -> monomial recurrence.
+template <int N>
 void fit(long double (*f)(long double), long double c, long double w, long double mono[N]) {
     long double fv[N], cj[N];
     for (int k = 0; k < N; ++k) fv[k] = f(c + w * cosl(kPiL * (2 * k + 1) / (2 * N)));
@@ -37,27 +37,34 @@ void fit(long double (*f)(long double), long double c, long double w, long doubl
     }
 }
 
-}  // namespace
-
-void build_interstellar_shape_table(double* out) {
-    const int per_binade = 1 << kShapeTabK;
+// One table: `per_binade_log2` intervals per binade, degree N-1, N coefficients of F then N of G per interval.
+template <int N, class Real>
+void build(Real* out, int per_binade_log2) {
+    const int per_binade = 1 << per_binade_log2;
     size_t idx = 0;
     for (int e = kShapeTabEmin; e < kShapeTabEmax; ++e) {
         const long double x0 = ldexpl(1.0L, e);
-        const long double w = ldexpl(1.0L, e - kShapeTabK - 1);        // half width: a power of two
+        const int wexp = e - per_binade_log2 - 1;
+        const long double w = ldexpl(1.0L, wexp);                      // half width: a power of two
         for (int j = 0; j < per_binade; ++j, ++idx) {
             const long double c = x0 + (2 * j + 1) * w;
             long double mf[N], mg[N];
-            fit(shape_f, c, w, mf);
-            fit(shape_g, c, w, mg);
-            double* o = out + idx * kShapeTabDoubles;
+            fit<N>(shape_f, c, w, mf);
+            fit<N>(shape_g, c, w, mg);
+            Real* o = out + idx * 2 * N;
             for (int k = 0; k < N; ++k) {                              // tau^k = t^k / w^k, exact scaling
-                o[k] = (double)ldexpl(mf[k], -k * (e - kShapeTabK - 1));
-                o[N + k] = (double)ldexpl(mg[k], -k * (e - kShapeTabK - 1));
+                o[k] = (Real)ldexpl(mf[k], -k * wexp);
+                o[N + k] = (Real)ldexpl(mg[k], -k * wexp);
             }
         }
     }
 }
+
+}  // namespace
+
+void build_interstellar_shape_table(double* out) { build<kShapeTabDegree + 1, double>(out, kShapeTabK); }
+
+void build_interstellar_shape_table_f32(float* out) { build<kShapeTab32Degree + 1, float>(out, kShapeTab32K); }
 
 }  // namespace curvis
 

@@ -30,4 +30,15 @@ constexpr unsigned kShapeTabBase = (unsigned)(1023 + kShapeTabEmin) << kShapeTab
 // Fills out[kShapeTabIntervals * kShapeTabDoubles]; pure host arithmetic.
 void build_interstellar_shape_table(double* out);
 
+// The fp32 edition for CURVIS_PRECISION_F32 (render_f32.cu): 2^4 intervals per binade of the same range,
+// degree-3 polynomials, 8 floats per interval (F a0..a3, then G b0..b3): two 128-bit loads and six FFMA
+// replace atanf + logf.  Relative error ~1e-7 (the fp32 rounding floor).
+constexpr int kShapeTab32K = 4;
+constexpr int kShapeTab32Degree = 3;
+constexpr int kShapeTab32Floats = 2 * (kShapeTab32Degree + 1);
+constexpr size_t kShapeTab32Intervals = (size_t)(kShapeTabEmax - kShapeTabEmin) << kShapeTab32K;
+constexpr unsigned kShapeTab32Shift = 23 - kShapeTab32K;      // float bits below the interval index
+constexpr unsigned kShapeTab32Base = (unsigned)(127 + kShapeTabEmin) << kShapeTab32K;
+void build_interstellar_shape_table_f32(float* out);
+
 }  // namespace curvis

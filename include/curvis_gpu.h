@@ -330,7 +330,8 @@ int curvis_ctx_set_option(curvis_ctx* ctx, const char* key, int64_t value);
  *   3 / 4 sin / cos of the in-kernel sincos fast path   5 / 6 the same with its large-argument fallback
  *   7 a/b   8 sqrt(a)   9 1/a   (the compiler's IEEE operators, for reference)
  *   10 the <= 1 ulp reciprocal of CURVIS_PRECISION_F64_FAST   11 / 12 its sin^2(a) / sin(a)cos(a)
- *   13 / 14 its Interstellar shape functions a atan a - ln(1 + a^2)/2 and atan a (table, a > 0)   */
+ *   13 / 14 its Interstellar shape functions a atan a - ln(1 + a^2)/2 and atan a (table, a > 0)
+ *   15 / 16 the same two functions as CURVIS_PRECISION_F32 evaluates them (fp32 table; a is rounded to float)   */
 int curvis_debug_eval(curvis_ctx* ctx, int op, const double* a, const double* b, double* out, size_t n);
 
 /* Test hook, host only (no GPU needed): the piecewise-polynomial table of the Interstellar shape

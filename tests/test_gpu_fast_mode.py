@@ -69,3 +69,25 @@ def test_fast_mode_other_metrics_and_edges(gpu_ctx):
     assert (frame == 0).all() and sysm.last_stats["n_not_escaped"] == 192 * 108
     with pytest.raises(cv.CurvisError):
         sysm.render_image(10, 100.0, 0.05, precision=7)
+
+
+def test_fp32_shape_table(gpu_ctx):
+    """The fp32 edition of the Interstellar shape-function table (csrc/shape_table.h: 16 intervals per binade,
+    degree 3): F(x) = x atan x - ln(1+x^2)/2 and G(x) = atan x within 4 fp32 ulp inside [2^-10, 2^16), and the
+    library composition outside it (absolute bar for tiny x, as in the fp64 test)."""
+    rng = np.random.default_rng(11)
+    x = np.exp(rng.uniform(np.log(2.0 ** -10), np.log(2.0 ** 16), 500_000)).astype(np.float32).astype(np.float64)
+    xl = x.astype(np.longdouble)
+    want_f, want_g = xl * np.arctan(xl) - np.log1p(xl * xl) / 2, np.arctan(xl)
+
+    def ulps32(got, want):
+        return np.abs((got.astype(np.longdouble) - want) / np.spacing(np.abs(want.astype(np.float32))).astype(np.longdouble)).astype(np.float64)
+
+    assert ulps32(gpu_ctx.debug_eval(15, x), want_f).max() <= 4.0
+    assert ulps32(gpu_ctx.debug_eval(16, x), want_g).max() <= 4.0
+    tiny = np.exp(rng.uniform(np.log(1e-5), np.log(2.0 ** -10), 5_000)).astype(np.float32).astype(np.float64)
+    huge = np.exp(rng.uniform(np.log(2.0 ** 16), np.log(1e9), 5_000)).astype(np.float32).astype(np.float64)
+    tl, hl = tiny.astype(np.longdouble), huge.astype(np.longdouble)
+    assert np.abs(gpu_ctx.debug_eval(15, tiny).astype(np.longdouble) - (tl * np.arctan(tl) - np.log1p(tl * tl) / 2)).max() <= 2e-7
+    assert ulps32(gpu_ctx.debug_eval(15, huge), hl * np.arctan(hl) - np.log1p(hl * hl) / 2).max() <= 8.0
+    assert ulps32(gpu_ctx.debug_eval(16, np.concatenate([tiny, huge])), np.arctan(np.concatenate([tl, hl]))).max() <= 4.0
