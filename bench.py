@@ -442,6 +442,18 @@ def run_b200(args):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = steps_per_job_step * args.steps / float(e2e_s.item())
 
+    if peers_mode:                                  # unmap the peers' buffers, then (after everybody has) free this rank's
+        torch.cuda.synchronize()
+        frames[:] = []
+        my_frames[:] = []
+        for bufs in peer_sets:
+            for r, b in enumerate(bufs):
+                if r != rank:
+                    b.close()
+        barrier()
+        for bufs in peer_sets:
+            bufs[rank].close()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
