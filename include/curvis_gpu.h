@@ -31,7 +31,9 @@
 extern "C" {
 #endif
 
-#define CURVIS_ABI_VERSION 2
+/* 2: curvis_sim.integrator;  3: CURVIS_PRECISION_F64_FAST, curvis_host_register/unregister, curvis_peer_buffer_*,
+ *    curvis_render_frames_peers, curvis_debug_shape_table_host (additions only: struct layouts are those of version 2) */
+#define CURVIS_ABI_VERSION 3
 
 /* ---- status codes ------------------------------------------------------------------
  * The reference panics (src/systems.rs:122-124, src/algebra.rs:19-21, src/cameras.rs:

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert set(names) == set(_abi.EXPORTED_SYMBOLS)
     for n in names:
         getattr(lib, n)
-    assert lib.curvis_abi_version() == 2
+    assert lib.curvis_abi_version() == _abi.ABI_VERSION == 3
 
 
 def test_struct_layouts_match_header():
