@@ -203,6 +203,7 @@ def run_b200(args):
 
     import curvis_b200 as cv
     from curvis_b200 import _abi, scenes
+    from curvis_b200.distributed import interleaved_rows
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -288,8 +289,9 @@ def run_b200(args):
         cur = peer_sets[k & 1]
         # interleaved rows: rank g renders rows g, g+n, g+2n, ... of every frame — the same mix of short (sky) and
         # long (throat-grazing) rays on every rank; a contiguous tile of central rows holds ~3 % more steps than the mean
-        st = system.render_frames_peers(cameras, *sim, rank, Ht, [b.ptr for b in cur], stream.cuda_stream,
-                                        want_stats=want_stats, row_stride=n, precision=PREC)
+        r0, r1, stride = interleaved_rows(Ht, rank, n)
+        st = system.render_frames_peers(cameras, *sim, r0, r1, [b.ptr for b in cur], stream.cuda_stream,
+                                        want_stats=want_stats, row_stride=stride, precision=PREC)
         # this rank's read-back of step k-1 (which read set (k-1)&1) must have finished before the barrier of step k lets
         # anybody launch step k+1 into that set
         stream.wait_event(copied[0])

@@ -17,6 +17,45 @@ def row_tile(height: int, rank: int, world: int) -> Tuple[int, int]:
     return height * rank // world, height * (rank + 1) // world
 
 
+def interleaved_rows(height: int, rank: int, world: int) -> Tuple[int, int, int]:
+    """(row_begin, row_end, row_stride) of rank ``rank`` under interleaved ownership — rows rank, rank+world, ... —
+    the arguments of curvis_render_frames_peers.  Every rank gets the same mix of short (sky) and long
+    (throat-grazing) rays; a contiguous tile of central rows holds ~3 % more Euler steps than the mean."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("rank/world out of range")
+    return rank, height, world
+
+
+def frame_offset(frame: int, row: int, height: int, width: int) -> int:
+    """Byte offset of row ``row`` of frame ``frame`` in a buffer of complete RGB8 frames (frame-major) — where
+    curvis_render_frames_peers stores it in every peer's buffer (csrc/geodesic_f64.cuh: finish_ray)."""
+    return (frame * height + row) * width * 3
+
+
+def all_gather_interleaved(rows, frame, height: int, width: int, group=None):
+    """The CPU stand-in for the fused peer stores: every rank contributes its interleaved rows (flat uint8
+    tensor, its rows in order) and ends with the complete frame, each row at frame_offset(0, row, ...)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    biggest = ((height + world - 1) // world) * width * 3
+    padded = torch.zeros(biggest, dtype=rows.dtype, device=rows.device)
+    padded[: rows.numel()] = rows
+    parts = [torch.empty(biggest, dtype=rows.dtype, device=rows.device) for _ in range(world)]
+    if world == 1:
+        parts[0].copy_(padded)
+    else:
+        dist.all_gather(parts, padded, group=group)
+    row_bytes = width * 3
+    for r in range(world):
+        b, e, stride = interleaved_rows(height, r, world)
+        for k, row in enumerate(range(b, e, stride)):
+            off = frame_offset(0, row, height, width)
+            frame[off: off + row_bytes] = parts[r][k * row_bytes: (k + 1) * row_bytes]
+    return frame
+
+
 def all_gather_frame(tile, frame, height: int, width: int, group=None):
     """Gathers every rank's RGB8 row tile (flat uint8 tensor, rows*width*3) into ``frame``
     (flat uint8 tensor, height*width*3) on every rank.  Equal tiles use one

@@ -1,6 +1,6 @@
 """world_size-2 (and 3, ragged) gloo test of the multi-rank host logic on CPU: every rank
-renders its row tile, the tiles are all-gathered, and every rank ends with the frame a single
-process renders.  The tile renderer here is the oracle (there is no GPU in this container);
+renders its row tile (contiguous, and interleaved as the fused peer-store path does), the rows are
+gathered, and every rank ends with the frame a single process renders.  The tile renderer here is the oracle (there is no GPU in this container);
 the -m gpu suite repeats the equality with the CUDA kernel (test_gpu_parity.py)."""
 import os
 import sys
@@ -34,6 +34,15 @@ def _worker(rank, world, port, W, H, q):
         dist.all_reduce(steps)
         full, _, fst = O.render_rows(g, cam, s, bp, bn, with_records=False)
         ok = bool((frame.numpy().reshape(H, W, 3) == full).all()) and int(steps.item()) == fst["total_steps"]
+        # interleaved ownership (what the fused peer-store path of bench.py uses): rows rank, rank+world, ...
+        from curvis_b200.distributed import all_gather_interleaved, interleaved_rows
+        b, e, stride = interleaved_rows(H, rank, world)
+        mine, _, st2 = O.render_rows(g, cam, s, bp, bn, row_begin=b, row_end=e, row_stride=stride, with_records=False)
+        frame2 = torch.zeros(H * W * 3, dtype=torch.uint8)
+        all_gather_interleaved(torch.from_numpy(mine.reshape(-1)), frame2, H, W)
+        steps2 = torch.tensor([st2["total_steps"]], dtype=torch.int64)
+        dist.all_reduce(steps2)
+        ok = ok and bool((frame2.numpy().reshape(H, W, 3) == full).all()) and int(steps2.item()) == fst["total_steps"]
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()
@@ -63,3 +72,15 @@ def test_row_tile_partition():
             assert all(tiles[i][1] == tiles[i + 1][0] for i in range(world - 1))
     with pytest.raises(ValueError):
         row_tile(10, 2, 2)
+
+
+def test_interleaved_rows_partition():
+    from curvis_b200.distributed import frame_offset, interleaved_rows
+    for H in (1, 7, 144, 2160):
+        for world in (1, 2, 3, 8):
+            owned = [list(range(*interleaved_rows(H, r, world))) for r in range(world)]
+            assert sorted(sum(owned, [])) == list(range(H))
+            assert max(len(o) for o in owned) - min(len(o) for o in owned) <= 1
+    assert frame_offset(0, 0, 2160, 3840) == 0 and frame_offset(2, 5, 2160, 3840) == (2 * 2160 + 5) * 3840 * 3
+    with pytest.raises(ValueError):
+        interleaved_rows(10, 3, 3)
