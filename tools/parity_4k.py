@@ -20,9 +20,11 @@ ctx = cv.Context([0])
 metric = cv.EllisMetric(1.0) if kind == "ellis" else cv.InterstellarMetric(0.1, 1e-4, 1.0)
 sysm = cv.RelativisticSystem(metric, cv.SphericalImage(bp), cv.SphericalImage(bn), cv.Camera(*cam_args), context=ctx)
 from curvis_b200 import _abi
-for variant in (0, 3, "f64_fast"):
+for variant in (0, 3, "f64_fast", "f32"):
     if variant == "f64_fast":      # CURVIS_PRECISION_F64_FAST (render_f64_fast.cu)
         frame = sysm.render_image(*sim, precision=_abi.PRECISION_F64_FAST)
+    elif variant == "f32":         # CURVIS_PRECISION_F32 (render_f32.cu): a tolerance mode, reported for scale
+        frame = sysm.render_image(*sim, precision=_abi.PRECISION_F32)
     else:
         ctx.set_option("kernel_variant", variant)
         frame = sysm.render_image(*sim)
