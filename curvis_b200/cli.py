@@ -26,8 +26,8 @@ def _common(sub):
     sub.add_argument("--renderer", choices=["efficient", "per_pixel"], default="efficient",
                      help="efficient = render_image_efficient (the reference binary's choice); per_pixel = render_image")
     sub.add_argument("--precision", choices=["f64", "f64_fast", "f32"], default="f64",
-                     help="per_pixel renderer only: f64 = one rounding per reference operation; f64_fast = the same fp64 Euler "
-                          "iteration regrouped for the GPU (3x faster, same frames); f32 = fp32 right-hand side")
+                     help="f64 = one rounding per reference operation; f64_fast = the same fp64 Euler iteration regrouped for the "
+                          "GPU (3x faster, same frames); f32 = fp32 right-hand side (per_pixel renderer only)")
     sub.add_argument("--devices", default=None, help="comma-separated CUDA ordinals (default: all visible)")
 
 

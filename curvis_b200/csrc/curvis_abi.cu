@@ -675,7 +675,10 @@ extern "C" int curvis_render_image_efficient(curvis_ctx* ctx, const curvis_metri
     if (rc != CURVIS_OK) return rc;
     if (!sampling || !out_rgb8) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "null sampling settings / output buffer");
     if (sampling->alphas_num < 3) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "alphas_num must be at least 3");
-    if (sim->precision != CURVIS_PRECISION_F64) return fail(ctx, CURVIS_ERR_UNSUPPORTED, "the table-based renderer is fp64 only");
+    // F64: the table equals the CPU's bit for bit; F64_FAST: its photons are integrated by the regrouped kernel, whose
+    // dependency chain per step is ~5x shorter — the table passes are latency-bound — at ~1e-13 relative in the table
+    if (sim->precision != CURVIS_PRECISION_F64 && sim->precision != CURVIS_PRECISION_F64_FAST)
+        return fail(ctx, CURVIS_ERR_UNSUPPORTED, "the table-based renderer is fp64 only (CURVIS_PRECISION_F64 or _F64_FAST)");
     DeviceState& d = ctx->devs[0];
     CURVIS_CUDA(ctx, cudaSetDevice(d.ordinal));
     const uint32_t W = camera->resolution_width, H = camera->resolution_height;
@@ -743,7 +746,8 @@ extern "C" int curvis_render_image_efficient(curvis_ctx* ctx, const curvis_metri
     cudaError_t e = cudaMalloc(&d_table, (table_doubles ? table_doubles : 1) * sizeof(double));
     if (e == cudaSuccess && dbg) e = cudaMalloc(&d_dbg, px * 3 * sizeof(double));
     if (e != cudaSuccess) { cleanup(); return cuda_fail(ctx, e, "cudaMalloc(table)"); }
-    rc = ensure_capacity(ctx, d, px * 3 + 1, 0, true);
+    const bool direct = ctx->is_registered(out_rgb8, px * 3);     // registered caller frame: one DMA, no staging copy
+    rc = ensure_capacity(ctx, d, px * 3 + 1, 0, !direct);
     if (rc != CURVIS_OK) { cleanup(); return rc; }
     ep.alphas = d_table; ep.m_e = d_table + n_pts; ep.c_e = ep.m_e + n_seg; ep.m_s = ep.c_e + n_seg; ep.c_s = ep.m_s + n_seg;
     ep.n_points = (uint32_t)n_pts; ep.n_segments = (uint32_t)n_seg;
@@ -757,7 +761,7 @@ extern "C" int curvis_render_image_efficient(curvis_ctx* ctx, const curvis_metri
         (e = cudaEventRecord(d.ev_begin, d.stream)) != cudaSuccess ||
         (e = launch_efficient_pixels(ep, d.sm_count, d.stream)) != cudaSuccess ||
         (e = cudaEventRecord(d.ev_end, d.stream)) != cudaSuccess ||
-        (e = cudaMemcpyAsync(d.h_out, d.d_out, px * 3, cudaMemcpyDeviceToHost, d.stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(direct ? out_rgb8 : d.h_out, d.d_out, px * 3, cudaMemcpyDeviceToHost, d.stream)) != cudaSuccess ||
         (dbg && (e = cudaMemcpyAsync(dbg, d_dbg, px * 3 * sizeof(double), cudaMemcpyDeviceToHost, d.stream)) != cudaSuccess) ||
         (e = cudaMemcpyAsync(d.h_counters, d.d_counters, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, d.stream)) != cudaSuccess ||
         (e = cudaStreamSynchronize(d.stream)) != cudaSuccess) {
@@ -765,7 +769,7 @@ extern "C" int curvis_render_image_efficient(curvis_ctx* ctx, const curvis_metri
         return cuda_fail(ctx, e, "per-pixel pass");
     }
     g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
-    std::memcpy(out_rgb8, d.h_out, px * 3);
+    if (!direct) std::memcpy(out_rgb8, d.h_out, px * 3);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, d.ev_begin, d.ev_end);
     cleanup();

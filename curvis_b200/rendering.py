@@ -113,7 +113,7 @@ class VideoRenderingSettings:                                    # rendering.rs:
                    simulation.sampling_convergence_threshold_1, simulation.sampling_convergence_threshold_2)
 
 
-# per-pixel renderer only (extension): curvis_sim.precision of include/curvis_gpu.h
+# extension: curvis_sim.precision of include/curvis_gpu.h (the table-based renderer accepts f64 and f64_fast)
 PRECISIONS = {"f64": _abi.PRECISION_F64, "f64_fast": _abi.PRECISION_F64_FAST, "f32": _abi.PRECISION_F32}
 
 
@@ -138,7 +138,7 @@ class ImageRenderingSystem:
                                                          precision=self.precision)
         return self.relativistic_system.render_image_efficient(
             s.max_iterations_propagation, s.escape_radius, s.ray_integration_step, s.alphas_num, s.max_iterations_sampling,
-            s.sampling_convergence_threshold_1, s.sampling_convergence_threshold_2)
+            s.sampling_convergence_threshold_1, s.sampling_convergence_threshold_2, precision=self.precision)
 
     def render(self) -> str:
         s = self.image_rendering_settings
@@ -188,7 +188,8 @@ class VideoRenderingSystem:
         return self.relativistic_system.render_image_efficient(
             s.max_iterations_propagation, s.escape_radius, s.ray_integration_step, s.alphas_num, s.max_iterations_sampling,
             s.sampling_convergence_threshold_1,
-            s.sampling_convergence_threshold_1)                     # rendering.rs:305-306 passes threshold_1 twice
+            s.sampling_convergence_threshold_1,                     # rendering.rs:305-306 passes threshold_1 twice
+            precision=self.precision)
 
     def render(self, max_frames: Optional[int] = None, verbose: bool = True, encoder_threads: int = 8) -> str:
         """The frame loop of rendering.rs:258-327.  Rendering a 4K frame takes milliseconds on

@@ -246,14 +246,18 @@ class RelativisticSystem:
 
     def render_image_efficient(self, max_iterations_propagation: int, max_radius: float, delta: float, alpha_nums: int,
                                max_iterations_sampling: int, sampling_convergence_threshold_1: float,
-                               sampling_convergence_threshold_2: float, debug: bool = False):
+                               sampling_convergence_threshold_2: float, debug: bool = False, out=None, **options):
         """``render_image_efficient`` (src/systems.rs:333-527), same argument order: the
         table-based renderer the ``curvis`` binary uses.  Returns uint8 (H, W, 3); with
-        ``debug`` also a float64 (H, W, 3) array of (alpha, escape angle, escape space)."""
+        ``debug`` also a float64 (H, W, 3) array of (alpha, escape angle, escape space).
+        ``out``: a caller frame (e.g. one registered with Context.register_host_buffer)."""
         cam = self.camera.as_c()
-        out = np.empty((cam.resolution_height, cam.resolution_width, 3), dtype=np.uint8)
+        if out is None:
+            out = np.empty((cam.resolution_height, cam.resolution_width, 3), dtype=np.uint8)
+        elif out.dtype != np.uint8 or out.shape != (cam.resolution_height, cam.resolution_width, 3) or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous uint8 array of shape (H, W, 3)")
         dbg = np.empty((cam.resolution_height, cam.resolution_width, 3), dtype=np.float64) if debug else None
-        sim = self._sim(max_iterations_propagation, max_radius, delta)
+        sim = self._sim(max_iterations_propagation, max_radius, delta, **options)
         smp = _abi.CurvisSamplingSettings(alphas_num=int(alpha_nums), max_iterations_sampling=int(max_iterations_sampling),
                                           threshold_1=float(sampling_convergence_threshold_1),
                                           threshold_2=float(sampling_convergence_threshold_2))

@@ -51,6 +51,23 @@ def test_efficient_tilted_camera_and_errors(gpu_ctx, oracle):
     ref, _ = oracle.render_image_efficient(oracle.metric("ellis", rho=1.5), oracle.camera(*cam_args), oracle.sim(40000, 100.0, 0.05), bp, bn,
                                            50, 50, 1e-4, 1e-4)
     assert (frame == ref).all(axis=2).mean() >= 0.9995
+    # the table integrated by the regrouped fp64 kernel (precision = F64_FAST): same sampler decisions, same frame
+    info = dict(sysm.last_efficient_info)
+    fast = sysm.render_image_efficient(40000, 100.0, 0.05, 50, 50, 1e-4, 1e-4, precision=_abi.PRECISION_F64_FAST)
+    assert sysm.last_efficient_info["table_points"] == info["table_points"]
+    assert sysm.last_efficient_info["table_evaluations"] == info["table_evaluations"]
+    assert (fast == frame).all(axis=2).mean() >= 0.9999
+    with pytest.raises(cv.CurvisError) as e32:
+        sysm.render_image_efficient(40000, 100.0, 0.05, 50, 50, 1e-4, 1e-4, precision=_abi.PRECISION_F32)
+    assert e32.value.code == _abi.ERR_UNSUPPORTED
+    # into a registered caller frame (one DMA, no staging copy): the same bytes
+    buf = np.zeros((80, 120, 3), dtype=np.uint8)
+    gpu_ctx.register_host_buffer(buf)
+    try:
+        sysm.render_image_efficient(40000, 100.0, 0.05, 50, 50, 1e-4, 1e-4, out=buf)
+        assert (buf == frame).all()
+    finally:
+        gpu_ctx.unregister_host_buffer(buf)
     with pytest.raises(cv.CurvisError) as e:                    # camera outside the escape radius (systems.rs:122-124)
         sysm.render_image_efficient(100, 2.0, 0.05, 50, 50, 1e-4, 1e-4)
     assert e.value.code == _abi.ERR_CAMERA_OUTSIDE_RADIUS
