@@ -1,5 +1,5 @@
 """Small frames through every per-ray kernel (for compute-sanitizer memcheck / racecheck on the GPU box):
-the three precisions x three metrics, records on, a registered host frame (zero-copy stores), batched frames."""
+the three precisions x three metrics, records on, a registered host frame (zero-copy stores), the fused peer-store launch, the table-based renderer."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -20,5 +20,19 @@ for metric, sim in ((cv.EllisMetric(1.0), (300, 12.0, 0.1)), (cv.InterstellarMet
         frame, rec = sysm.render_rows(*sim, 3, 41, with_records=True, precision=prec)
         assert (frame == out[3:41]).all()
         print(type(metric).__name__, prec, sysm.last_stats["total_steps"], flush=True)
+# fused render + gather into two peer buffers (interleaved rows), and the table-based renderer into the registered frame
+import torch
+bufs = [cv.PeerBuffer.create(ctx, 2 * W * H * 3) for _ in range(2)]
+cams = [cam, cv.Camera((0.0, 5.5, 1.4, 0.2), scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP, 15.0, 43.0, W, H)]
+sysm = cv.RelativisticSystem(cv.EllisMetric(1.0), cv.SphericalImage(bp), cv.SphericalImage(bn), cam, context=ctx)
+for prec in (_abi.PRECISION_F64, _abi.PRECISION_F64_FAST, _abi.PRECISION_F32):
+    for g in range(3):
+        sysm.render_frames_peers(cams, 300, 12.0, 0.1, g, H, [b.ptr for b in bufs], want_stats=True, row_stride=3, precision=prec)
+torch.cuda.synchronize()
+assert (bufs[0].as_tensor() == bufs[1].as_tensor()).all()
+for b in bufs:
+    b.close()
+for prec in (_abi.PRECISION_F64, _abi.PRECISION_F64_FAST):
+    sysm.render_image_efficient(2000, 30.0, 0.05, 30, 30, 1e-4, 1e-4, out=out, precision=prec)
 ctx.unregister_host_buffer(out)
 print("ok")
