@@ -38,6 +38,16 @@ def test_cli_image_both_renderers(tmp_path, oracle):
     got = np.asarray(Image.open(out / "output_image.png"))
     ref, _, _ = oracle.render_rows(oracle.metric("ellis"), ocam, oracle.sim(40000, 100.0, 0.05), bp, bn, threads=os.cpu_count() or 1)
     assert (got == ref).all()
+    # --precision (extension): the regrouped fp64 kernel renders the same frame with both renderers; fp32 is
+    # per-pixel only
+    assert main(["image", p1, p2, str(out), "-c", str(cam), "--renderer", "per_pixel", "--precision", "f64_fast"]) == 0
+    assert (np.asarray(Image.open(out / "output_image.png")) == ref).all(axis=2).mean() >= 0.9999
+    assert main(["image", p1, p2, str(out), "-c", str(cam), "--precision", "f64_fast"]) == 0
+    eff, _ = oracle.render_image_efficient(oracle.metric("ellis"), ocam, oracle.sim(40000, 100.0, 0.05), bp, bn, 100, 100, 1e-5, 1e-5)
+    assert (np.asarray(Image.open(out / "output_image.png")) == eff).all(axis=2).mean() >= 0.9999
+    assert main(["image", p1, p2, str(out), "-c", str(cam), "--renderer", "per_pixel", "--precision", "f32"]) == 0
+    assert (np.asarray(Image.open(out / "output_image.png")) == ref).all(axis=2).mean() >= 0.99
+    assert main(["image", p1, p2, str(out), "-c", str(cam), "--precision", "f32"]) == 1        # the table-based renderer is fp64 only
 
 
 def test_cli_video_frames(tmp_path, oracle):
