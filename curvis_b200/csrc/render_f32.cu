@@ -118,11 +118,13 @@ __device__ __forceinline__ void finish32_from_r(const Pre32FromR& pre, float y0,
     f = pre.rp * (y * u);            // r'/r^3
 }
 
-// F(x) = x atan x - ln(1+x^2)/2 and G(x) = atan x, x > 0 (shape_table.h): inside [2^-10, 2^16) two degree-3
-// polynomials in t = x - interval midpoint, coefficients from two 128-bit loads; outside, the library.
+// F(x) = x atan x - ln(1+x^2)/2 and G(x) = (2/pi) atan x, x > 0 (shape_table.h): inside [2^-10, 2^16) two degree-3
+// polynomials in t = x - interval midpoint, coefficients from two 128-bit loads; outside, the library; x <= 0 (the
+// plateau |l| <= a) and NaN give F = G = 0, i.e. r = rho, r' = 0.
 __device__ __noinline__ float2 shape32_library(float x) {
-    const float G = atanf(x);
-    return make_float2(fmaf(x, G, -0.5f * log1pf(x * x)), G);
+    if (!(x > 0.0f)) return make_float2(0.0f, 0.0f);
+    const float at = atanf(x);
+    return make_float2(fmaf(x, at, -0.5f * log1pf(x * x)), 0.63661975f * at);
 }
 
 __device__ __forceinline__ void shape32_fg(const float4* tab, float x, float& F, float& G) {
@@ -144,15 +146,11 @@ struct Shape32Interstellar {   // metrics.rs:461-485
     using Shape64 = ShapeInterstellar;
     using Pre = Pre32FromR;
     static __device__ __forceinline__ float prepare(const FrameParams& p, float l, float s2, Pre& pre) {
-        const float al = fabsf(l);
-        pre.r = p.f_rho; pre.rp = 0.0f;
-        if (al > p.f_a) {
-            const float x = (al - p.f_a) * p.f_xscale;
-            float F, G;
-            shape32_fg(p.shape_tab32, x, F, G);
-            pre.r = fmaf(p.f_m, F, p.f_rho);
-            pre.rp = copysignf(0.63661975f * G, l);
-        }
+        const float x = (fabsf(l) - p.f_a) * p.f_xscale;      // <= 0 on the plateau: F = G = 0 from the library branch
+        float F, G;
+        shape32_fg(p.shape_tab32, x, F, G);
+        pre.r = fmaf(p.f_m, F, p.f_rho);
+        pre.rp = copysignf(G, l);
         return pre.r * s2;
     }
     static __device__ __forceinline__ void finish(const Pre& pre, float y0, float, float s2, float& w, float& u, float& v, float& f) {

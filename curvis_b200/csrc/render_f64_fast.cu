@@ -93,13 +93,15 @@ __device__ __forceinline__ void finish_from_r(const PreFromR& pre, double y0, do
     f = pre.rp * (y * u);          // r'/r^3
 }
 
-// F(x) = x atan x - ln(1+x^2)/2 and G(x) = atan x for x > 0 from the piecewise degree-5 table
+// F(x) = x atan x - ln(1+x^2)/2 and G(x) = (2/pi) atan x for x > 0 from the piecewise degree-5 table
 // (shape_table.h): interval index = a shift of x's high word, t = x - midpoint (exact), two Horner
 // chains on coefficients fetched with six 128-bit loads (neighbouring rays sit in the same or the
-// next interval, so the loads are L1 hits).  Outside [2^-10, 2^16): the library functions.
+// next interval, so the loads are L1 hits).  Outside [2^-10, 2^16): the library functions; x <= 0 (the
+// plateau |l| <= a of the throat, metrics.rs:470 / :482) and NaN give F = G = 0, i.e. r = rho, r' = 0.
 __device__ __noinline__ double2 shape_fg_library(double x) {   // x outside the table: rare, out of line
-    const double G = atan(x);
-    return make_double2(fma(x, G, -0.5 * log(fma(x, x, 1.0))), G);
+    if (!(x > 0.0)) return make_double2(0.0, 0.0);
+    const double at = atan(x);
+    return make_double2(fma(x, at, -0.5 * log(fma(x, x, 1.0))), (2.0 / CURVIS_PI) * at);
 }
 
 __device__ __forceinline__ void shape_fg(const FrameParams& p, double x, double& F, double& G) {
@@ -121,29 +123,23 @@ __device__ __forceinline__ void shape_fg(const FrameParams& p, double x, double&
 
 struct FastInterstellar {   // metrics.rs:461-485 with the uniform divisor pi*m folded into d_xscale
     using Shape64 = ShapeInterstellar;
+    // One path for the whole l axis: x <= 0 on the plateau |l| <= a fails the table's range test and comes back as
+    // F = G = 0 from the library branch (a ray spends at most a step or two there), so the step carries no branch on l.
+    static __device__ __forceinline__ void shape(const FrameParams& p, double l, double& r, double& rp) {
+        const double x = (fabs(l) - p.a) * p.d_xscale;
+        double F, G;
+        shape_fg(p, x, F, G);
+        r = fma(p.m, F, p.rho);
+        rp = copysign(G, l);
+    }
     static __device__ __forceinline__ bool factors(const FrameParams& p, double l, double s2, double& w, double& u, double& v, double& ud, double& fd) {
-        const double al = fabs(l);
-        double r = p.rho, rp = 0.0;
-        if (al > p.a) {
-            const double x = (al - p.a) * p.d_xscale;
-            double F, G;
-            shape_fg(p, x, F, G);
-            r = fma(p.m, F, p.rho);
-            rp = copysign((2.0 / CURVIS_PI) * G, l);
-        }
+        double r, rp;
+        shape(p, l, r, rp);
         return factors_from_r(p, r, rp, s2, w, u, v, ud, fd);
     }
     using Pre = PreFromR;
     static __device__ __forceinline__ double prepare(const FrameParams& p, double l, double s2, Pre& pre) {
-        const double al = fabs(l);
-        pre.r = p.rho; pre.rp = 0.0;
-        if (al > p.a) {
-            const double x = (al - p.a) * p.d_xscale;
-            double F, G;
-            shape_fg(p, x, F, G);
-            pre.r = fma(p.m, F, p.rho);
-            pre.rp = copysign((2.0 / CURVIS_PI) * G, l);
-        }
+        shape(p, l, pre.r, pre.rp);
         return pre.r * s2;
     }
     static __device__ __forceinline__ void finish(const Pre& pre, double y0, double, double s2, double& w, double& u, double& v, double& f) {

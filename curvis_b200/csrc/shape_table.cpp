@@ -10,7 +10,7 @@ namespace {
 const long double kPiL = 3.14159265358979323846264338327950288L;
 
 long double shape_f(long double x) { return x * atanl(x) - 0.5L * log1pl(x * x); }
-long double shape_g(long double x) { return atanl(x); }
+long double shape_g(long double x) { return (2.0L / kPiL) * atanl(x); }
 
 // Monomial coefficients (in tau = t / w, |tau| <= 1) of the degree-(N-1) interpolant of f through
 // the N Chebyshev nodes of [c - w, c + w]: Chebyshev coefficients by the discrete cosine sums,

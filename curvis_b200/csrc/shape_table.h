@@ -3,7 +3,7 @@
 //
 // InterstellarMetric::r / r_derivative (reference src/metrics.rs:461-485) need, per Euler step,
 //     F(x) = x atan x - ln(1 + x^2)/2      (r  = rho + m F)
-//     G(x) = atan x = F'(x)                (r' = sign(l) 2/pi G),     x = 2(|l| - a)/(pi m) > 0,
+//     G(x) = (2/pi) atan x = (2/pi) F'(x)  (r' = sign(l) G),          x = 2(|l| - a)/(pi m) > 0,
 // two library transcendentals worth ~80 fp64-pipe instructions — two thirds of that metric's step.
 // Both are parameter-free functions of x, so ONE table serves every metric setting:
 // x in [2^kShapeTabEmin, 2^kShapeTabEmax) is cut into 2^kShapeTabK equal intervals per binade (the

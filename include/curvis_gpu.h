@@ -336,13 +336,13 @@ int curvis_ctx_set_option(curvis_ctx* ctx, const char* key, int64_t value);
  *   3 / 4 sin / cos of the in-kernel sincos fast path   5 / 6 the same with its large-argument fallback
  *   7 a/b   8 sqrt(a)   9 1/a   (the compiler's IEEE operators, for reference)
  *   10 the <= 1 ulp reciprocal of CURVIS_PRECISION_F64_FAST   11 / 12 its sin^2(a) / sin(a)cos(a)
- *   13 / 14 its Interstellar shape functions a atan a - ln(1 + a^2)/2 and atan a (table, a > 0)
+ *   13 / 14 its Interstellar shape functions a atan a - ln(1 + a^2)/2 and (2/pi) atan a (table; 0 for a <= 0)
  *   15 / 16 the same two functions as CURVIS_PRECISION_F32 evaluates them (fp32 table; a is rounded to float)   */
 int curvis_debug_eval(curvis_ctx* ctx, int op, const double* a, const double* b, double* out, size_t n);
 
 /* Test hook, host only (no GPU needed): the piecewise-polynomial table of the Interstellar shape
  * functions that CURVIS_PRECISION_F64_FAST uploads to every device (csrc/shape_table.h), evaluated on
- * the host with the kernel's arithmetic: f[i] = x atan x - ln(1 + x^2)/2, g[i] = atan x.  Returns 1
+ * the host with the kernel's arithmetic: f[i] = x atan x - ln(1 + x^2)/2, g[i] = (2/pi) atan x.  Returns 1
  * when every x[i] lay inside the table's range [2^-10, 2^16), else 0 (those entries are NaN). */
 int curvis_debug_shape_table_host(const double* x, double* f, double* g, size_t n);
 

@@ -148,7 +148,7 @@ def test_spherical_image_conversions(lib):
 
 
 def test_interstellar_shape_table_host(lib):
-    """The piecewise degree-5 table of F(x) = x atan x - ln(1+x^2)/2 and G(x) = atan x that
+    """The piecewise degree-5 table of F(x) = x atan x - ln(1+x^2)/2 and G(x) = (2/pi) atan x that
     CURVIS_PRECISION_F64_FAST uploads (csrc/shape_table.h; replaces the atan + ln of
     InterstellarMetric::r / r_derivative, reference src/metrics.rs:461-485), evaluated on the host
     with the kernel's arithmetic, against x87 long double: <= 2 ulp, i.e. the class of a libm."""
@@ -163,7 +163,8 @@ def test_interstellar_shape_table_host(lib):
     dp = C.POINTER(C.c_double)
     assert lib.curvis_debug_shape_table_host(x.ctypes.data_as(dp), f.ctypes.data_as(dp), g.ctypes.data_as(dp), x.size) == 1
     xl = x.astype(np.longdouble)
-    want_f, want_g = xl * np.arctan(xl) - np.log1p(xl * xl) / 2, np.arctan(xl)
+    TWO_OVER_PI = np.longdouble(2) / (4 * np.arctan(np.longdouble(1)))      # in x87 long double
+    want_f, want_g = xl * np.arctan(xl) - np.log1p(xl * xl) / 2, TWO_OVER_PI * np.arctan(xl)
 
     def ulps(got, want):
         return np.abs((got.astype(np.longdouble) - want) / np.spacing(np.abs(want.astype(np.float64))).astype(np.longdouble)).astype(np.float64)
