@@ -10,7 +10,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # curvis_status
 OK = 0
@@ -27,7 +27,9 @@ ERR_UNSUPPORTED = 9
 METRIC_ELLIS, METRIC_INTERSTELLAR, METRIC_FLAT = 0, 1, 2
 PRECISION_F64, PRECISION_F32, PRECISION_F64_FAST = 0, 1, 2
 SAMPLING_NEAREST, SAMPLING_BILINEAR = 0, 1
-INTEGRATOR_EULER, INTEGRATOR_RK4 = 0, 1
+INTEGRATOR_EULER, INTEGRATOR_RK4, INTEGRATOR_EULER_ADAPTIVE = 0, 1, 2
+FRAME_LOCAL, FRAME_WORLD, FRAME_WORLD_QUIRK = 0, 1, 2
+COORDINATES_SPHERICAL, COORDINATES_CARTESIAN = 0, 1
 
 
 class CurvisMetric(C.Structure):
@@ -49,13 +51,15 @@ class CurvisCamera(C.Structure):
 class CurvisSim(C.Structure):
     _fields_ = [
         ("max_iterations", C.c_uint32),
-        ("_pad", C.c_uint32),
+        ("frame", C.c_int32),
         ("max_radius", C.c_double),
         ("delta", C.c_double),
         ("precision", C.c_int32),
         ("sampling", C.c_int32),
         ("integrator", C.c_int32),
-        ("_pad2", C.c_int32),
+        ("coordinates", C.c_int32),
+        ("step_tolerance", C.c_double),
+        ("_reserved", C.c_double),
     ]
 
 
@@ -67,7 +71,7 @@ class CurvisStats(C.Structure):
         ("n_negative", C.c_uint64),
         ("n_not_escaped", C.c_uint64),
         ("n_clamped", C.c_uint64),
-        ("n_big_theta", C.c_uint64),
+        ("n_reintegrated", C.c_uint64),
         ("kernel_ms", C.c_double),
         ("total_ms", C.c_double),
     ]
@@ -94,13 +98,15 @@ class CurvisRayRecord(C.Structure):
         ("l", C.c_double), ("theta", C.c_double), ("phi", C.c_double),
         ("p_l", C.c_double), ("p_theta", C.c_double), ("p_phi", C.c_double),
         ("steps", C.c_uint32), ("side", C.c_int32), ("texel_x", C.c_uint32), ("texel_y", C.c_uint32),
+        ("min_abs_sin_theta", C.c_double), ("stiffness", C.c_double),
     ]
 
 
-# numpy view of curvis_ray_record (same layout, 64 bytes)
+# numpy view of curvis_ray_record (same layout, 80 bytes)
 RAY_RECORD_DTYPE = [
     ("l", "<f8"), ("theta", "<f8"), ("phi", "<f8"), ("p_l", "<f8"), ("p_theta", "<f8"), ("p_phi", "<f8"),
     ("steps", "<u4"), ("side", "<i4"), ("texel_x", "<u4"), ("texel_y", "<u4"),
+    ("min_abs_sin_theta", "<f8"), ("stiffness", "<f8"),
 ]
 
 MAX_PEERS = 8               # CURVIS_MAX_PEERS

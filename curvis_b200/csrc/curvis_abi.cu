@@ -45,6 +45,11 @@ struct DeviceState {
     double2* d_shape_tab = nullptr;   // Interstellar shape-function table (shape_table.h), uploaded at context creation
     float4* d_shape_tab32 = nullptr;  // its fp32 edition
     cudaEvent_t chunk_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // pipelined read-back
+    // CURVIS_PRECISION_F64_FAST: indices of the rays inside the guard band, re-integrated by the parity kernel
+    unsigned long long* d_redo = nullptr; size_t d_redo_cap = 0;
+    // the per-launch scratch above (counters, cameras, redo list, events) is shared by every launch of the context: a
+    // launch on a stream other than the previous one's first waits for the previous launch (launch_fence)
+    cudaStream_t last_stream = nullptr; bool launched = false;
     // tile of the frame in flight
     uint32_t row_begin = 0, row_end = 0;
 };
@@ -101,10 +106,20 @@ static int validate_frame(curvis_ctx* ctx, const curvis_metric* metric, const cu
         return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "unknown precision");
     if (sim->sampling != CURVIS_SAMPLING_NEAREST && sim->sampling != CURVIS_SAMPLING_BILINEAR)
         return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "unknown sampling mode");
-    if (sim->integrator != CURVIS_INTEGRATOR_EULER && sim->integrator != CURVIS_INTEGRATOR_RK4)
+    if (sim->integrator != CURVIS_INTEGRATOR_EULER && sim->integrator != CURVIS_INTEGRATOR_RK4 &&
+        sim->integrator != CURVIS_INTEGRATOR_EULER_ADAPTIVE)
         return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "unknown integrator");
-    if (sim->integrator == CURVIS_INTEGRATOR_RK4 && sim->precision != CURVIS_PRECISION_F64)
-        return fail(ctx, CURVIS_ERR_UNSUPPORTED, "the RK4 extension is implemented for CURVIS_PRECISION_F64 only");
+    if (sim->integrator != CURVIS_INTEGRATOR_EULER && sim->precision != CURVIS_PRECISION_F64)
+        return fail(ctx, CURVIS_ERR_UNSUPPORTED, "the RK4 and adaptive-step extensions are implemented for CURVIS_PRECISION_F64 only");
+    if (sim->integrator == CURVIS_INTEGRATOR_EULER_ADAPTIVE && !(sim->step_tolerance > 0.0))
+        return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "CURVIS_INTEGRATOR_EULER_ADAPTIVE needs step_tolerance > 0");
+    if (sim->frame != CURVIS_FRAME_LOCAL && sim->frame != CURVIS_FRAME_WORLD && sim->frame != CURVIS_FRAME_WORLD_QUIRK)
+        return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "unknown frame");
+    if (sim->coordinates != CURVIS_COORDINATES_SPHERICAL && sim->coordinates != CURVIS_COORDINATES_CARTESIAN)
+        return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "unknown coordinates");
+    if (sim->coordinates == CURVIS_COORDINATES_CARTESIAN &&
+        (sim->precision != CURVIS_PRECISION_F64 || sim->integrator != CURVIS_INTEGRATOR_EULER))
+        return fail(ctx, CURVIS_ERR_UNSUPPORTED, "CURVIS_COORDINATES_CARTESIAN is implemented for CURVIS_PRECISION_F64 with the Euler integrator");
     if (!ctx->bg_set[0] || !ctx->bg_set[1])
         return fail(ctx, CURVIS_ERR_NO_BACKGROUND, "both backgrounds must be set before rendering");
     // escape_photon panics when the photon starts beyond the radius (systems.rs:122-124);
@@ -117,9 +132,44 @@ static int validate_frame(curvis_ctx* ctx, const curvis_metric* metric, const cu
 static cudaError_t launch_render(const FrameParams& p, const curvis_metric* metric, const curvis_sim* sim,
                                  const LaunchTuning& t, int sm_count, cudaStream_t stream) {
     g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+    if (sim->coordinates == CURVIS_COORDINATES_CARTESIAN) return launch_render_cart(p, metric->kind, t, sm_count, stream);
     if (sim->precision == CURVIS_PRECISION_F32) return launch_render_f32(p, metric->kind, t, sm_count, stream);
-    if (sim->precision == CURVIS_PRECISION_F64_FAST) return launch_render_f64_fast(p, metric->kind, t, sm_count, stream);
+    if (sim->precision == CURVIS_PRECISION_F64_FAST) {
+        cudaError_t e = launch_render_f64_fast(p, metric->kind, t, sm_count, stream);
+        if (e != cudaSuccess || !p.redo_list) return e;
+        // second launch: the parity kernel over the rays the fast kernel left in its guard band (list mode; the list's
+        // length stays on the device)
+        FrameParams r = p;
+        r.ray_list = p.redo_list;
+        r.ray_list_count = &p.counters->n_reintegrated;
+        r.redo_list = nullptr;
+        r.window = 32;
+        g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+        return launch_render_f64(r, metric->kind, t, sm_count, stream);
+    }
     return launch_render_f64(p, metric->kind, t, sm_count, stream);
+}
+
+// Every launch of a context shares its per-device scratch (counters with the work-queue cursor, the camera block, the redo
+// list, the timing events).  Launches on one stream are ordered by the stream; a launch on a DIFFERENT stream than the
+// previous one waits for the previous launch to finish before it touches the scratch.
+static cudaError_t launch_fence(DeviceState& d, cudaStream_t stream) {
+    cudaError_t e = cudaSuccess;
+    if (d.launched && d.last_stream != stream) e = cudaStreamWaitEvent(stream, d.ev_end, 0);
+    d.last_stream = stream; d.launched = true;
+    return e;
+}
+
+// The redo list of CURVIS_PRECISION_F64_FAST: one slot per ray of the launch (8 bytes each; a 4K frame: 66 MB), grown on demand.
+static int ensure_redo(curvis_ctx* ctx, DeviceState& d, const curvis_sim* sim, size_t rays) {
+    if (sim->precision != CURVIS_PRECISION_F64_FAST || !ctx->tuning.guard || ctx->tuning.fast_variant != 1) return CURVIS_OK;
+    if (rays > d.d_redo_cap) {
+        if (d.d_redo) cudaFree(d.d_redo);
+        d.d_redo = nullptr; d.d_redo_cap = 0;
+        CURVIS_CUDA(ctx, cudaMalloc(&d.d_redo, rays * sizeof(unsigned long long)));
+        d.d_redo_cap = rays;
+    }
+    return CURVIS_OK;
 }
 
 static void fill_camera(const curvis_metric* metric, const curvis_camera* cam, CameraBlock& c) {
@@ -127,6 +177,7 @@ static void fill_camera(const curvis_metric* metric, const curvis_camera* cam, C
     std::memcpy(c.cam_to_world, cam->cam_to_world, sizeof c.cam_to_world);
     c.cam_r = host_shape_r(*metric, cam->position[1]);
     c.cam_sin_theta = host_sin(cam->position[2]);
+    host_camera_basis(cam->position[2], cam->position[3], c.cam_n, c.cam_eth, c.cam_eph);
     c.focal_length = cam->focal_length; c.sensor_width = cam->sensor_width; c.sensor_height = cam->sensor_height;
 }
 
@@ -169,6 +220,11 @@ static void fill_params(const curvis_ctx* ctx, const DeviceState& d, const curvi
         std::memcpy(p.bg[s].inv_rot, ctx->bg_inv_rot[s], sizeof p.bg[s].inv_rot);
     }
     p.out_rgb8 = d_out; p.out_rgba32f = nullptr; p.records = d_records; p.counters = d.d_counters;
+    p.frame = (uint32_t)sim->frame; p.coordinates = (uint32_t)sim->coordinates; p.step_tolerance = sim->step_tolerance;
+    const bool guard = sim->precision == CURVIS_PRECISION_F64_FAST && ctx->tuning.guard && ctx->tuning.fast_variant == 1;
+    p.redo_list = guard ? d.d_redo : nullptr;
+    p.redo_capacity = guard ? d.d_redo_cap : 0;
+    p.guard_rel = ctx->tuning.guard_rel;
 }
 
 // CURVIS_SAMPLING_BILINEAR reads the backgrounds as float4 (one 128-bit load per tap): staged once
@@ -188,7 +244,10 @@ static int ensure_float_backgrounds(curvis_ctx* ctx, DeviceState& d, const curvi
 static int enqueue_tile(curvis_ctx* ctx, DeviceState& d, const curvis_metric* metric, const curvis_camera* cam,
                         const curvis_sim* sim, uint32_t row_begin, uint32_t row_end, uint8_t* d_out,
                         curvis_ray_record* d_records, cudaStream_t stream, float4* d_out_f32 = nullptr) {
+    CURVIS_CUDA(ctx, launch_fence(d, stream));
     int frc = ensure_float_backgrounds(ctx, d, sim, stream);
+    if (frc != CURVIS_OK) return frc;
+    frc = ensure_redo(ctx, d, sim, (size_t)(row_end - row_begin) * cam->resolution_width);
     if (frc != CURVIS_OK) return frc;
     FrameParams p;
     fill_params(ctx, d, metric, cam, sim, row_begin, row_end, d_out, d_records, p);
@@ -203,7 +262,7 @@ static int enqueue_tile(curvis_ctx* ctx, DeviceState& d, const curvis_metric* me
 static void add_counters(const DeviceCounters& c, uint64_t n_rays, curvis_stats* s) {
     s->total_steps += c.total_steps; s->n_rays += n_rays;
     s->n_positive += c.n_positive; s->n_negative += c.n_negative; s->n_not_escaped += c.n_not_escaped;
-    s->n_clamped += c.n_clamped; s->n_big_theta += c.n_big_theta;
+    s->n_clamped += c.n_clamped; s->n_reintegrated += c.n_reintegrated;
 }
 
 static int ensure_capacity(curvis_ctx* ctx, DeviceState& d, size_t out_bytes, size_t n_records, bool staging) {
@@ -273,6 +332,7 @@ static void release_device(DeviceState& d) {
     if (d.d_cameras) cudaFree(d.d_cameras);
     if (d.d_shape_tab) cudaFree(d.d_shape_tab);
     if (d.d_shape_tab32) cudaFree(d.d_shape_tab32);
+    if (d.d_redo) cudaFree(d.d_redo);
     for (auto& ev : d.chunk_done) if (ev) cudaEventDestroy(ev);
     if (d.ev_begin) cudaEventDestroy(d.ev_begin);
     if (d.ev_end) cudaEventDestroy(d.ev_end);
@@ -430,6 +490,7 @@ static int render_frames_impl(curvis_ctx* ctx, const curvis_metric* metric,
     DeviceState& d = ctx->devs[0];
     cudaStream_t st = (cudaStream_t)stream;
     CURVIS_CUDA(ctx, cudaSetDevice(d.ordinal));
+    CURVIS_CUDA(ctx, launch_fence(d, st));
     if (n_frames > d.d_cameras_cap) {
         if (d.d_cameras) cudaFree(d.d_cameras);
         d.d_cameras = nullptr; d.d_cameras_cap = 0;
@@ -439,6 +500,11 @@ static int render_frames_impl(curvis_ctx* ctx, const curvis_metric* metric,
     {
         int frc = ensure_float_backgrounds(ctx, d, sim, st);
         if (frc != CURVIS_OK) return frc;
+    }
+    {
+        const uint32_t rows_launch = (row_end - row_begin + row_stride - 1) / row_stride;
+        int rrc = ensure_redo(ctx, d, sim, (size_t)rows_launch * cameras[0].resolution_width * n_frames);
+        if (rrc != CURVIS_OK) return rrc;
     }
     std::vector<CameraBlock> blocks(n_frames);
     for (uint32_t f = 0; f < n_frames; ++f) fill_camera(metric, &cameras[f], blocks[f]);
@@ -641,6 +707,9 @@ extern "C" int curvis_ctx_set_option(curvis_ctx* ctx, const char* key, int64_t v
     else if (k == "window" && value >= 0 && value <= 4096) ctx->tuning.window = (int)value;
     else if (k == "fast_variant" && value >= 0 && value <= 1) ctx->tuning.fast_variant = (int)value;
     else if (k == "zero_copy" && value >= 0 && value <= 1) ctx->tuning.zero_copy = (int)value;
+    else if (k == "guard" && value >= 0 && value <= 1) ctx->tuning.guard = (int)value;
+    else if (k == "fast_regs" && (value == 96 || value == 128)) ctx->tuning.fast_regs = (int)value;
+    else if (k == "guard_rel_e15" && value >= 1 && value <= 1000000000000ll) ctx->tuning.guard_rel = (double)value * 1e-15;
     else return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "unknown option or value out of range: " + k);
     return CURVIS_OK;
 }
@@ -699,6 +768,8 @@ extern "C" int curvis_render_image_efficient(curvis_ctx* ctx, const curvis_metri
         }
         int r = ensure_capacity(ctx, d, 1, n, false);
         if (r != CURVIS_OK) return cuda_rc = r;
+        if ((r = ensure_redo(ctx, d, sim, n)) != CURVIS_OK) return cuda_rc = r;
+        if (launch_fence(d, d.stream) != cudaSuccess) return cuda_rc = fail(ctx, CURVIS_ERR_CUDA, "launch fence");
         cudaError_t e = cudaMemcpyAsync(d_dirs, dirs, n * 3 * sizeof(double), cudaMemcpyHostToDevice, d.stream);
         if (e != cudaSuccess) return cuda_rc = cuda_fail(ctx, e, "cudaMemcpyAsync(ray directions)");
         FrameParams p;

@@ -17,8 +17,9 @@ struct DeviceCounters {
     unsigned long long n_negative;
     unsigned long long n_not_escaped;
     unsigned long long n_clamped;
-    unsigned long long n_big_theta;
-    unsigned long long _pad[9];
+    unsigned long long n_reintegrated; // CURVIS_PRECISION_F64_FAST: rays pushed onto the re-integration list (= its length)
+    unsigned long long redo_next;      // work queue of the re-integration launch
+    unsigned long long _pad[8];
 };
 
 struct Background {
@@ -36,6 +37,9 @@ struct CameraBlock {
     // evaluated once on the host with the platform libm like the reference does per ray
     double cam_r, cam_sin_theta;
     double focal_length, sensor_width, sensor_height;
+    // CURVIS_COORDINATES_CARTESIAN: unit position vector of the camera and the unit vectors of increasing theta / phi
+    // there (host libm, once per frame)
+    double cam_n[3], cam_eth[3], cam_eph[3];
 };
 
 struct FrameParams {
@@ -78,6 +82,19 @@ struct FrameParams {
     // row_stride > 1 (peers launches only): the launch renders rows row_begin + k*row_stride, k in [0, row_end - row_begin)
     // — interleaved row ownership, which gives every rank statistically the same work
     uint32_t n_peers, row_stride;
+    // curvis_sim extensions (all 0 in parity mode): curvis_frame, curvis_coordinates, adaptive-step tolerance
+    uint32_t frame, coordinates;
+    double step_tolerance;
+    // CURVIS_PRECISION_F64_FAST guard band (render_f64_fast.cu: guard_ok): a finished ray whose escape step or texel lies
+    // closer to a decision boundary than the band is not written; its index goes to redo_list (capacity redo_capacity,
+    // length counters->n_reintegrated) and the parity kernel re-integrates the list in a second launch (ray_list mode)
+    unsigned long long* redo_list;
+    unsigned long long redo_capacity;
+    double guard_rel;        // relative state error budget of an unamplified ray (units of 1.0)
+    // list mode (the second launch): ray i of the launch is ray ray_list[i] of the tile; the launch holds
+    // *ray_list_count rays (device-resident count: the host never learns it before launching)
+    const unsigned long long* ray_list;
+    const unsigned long long* ray_list_count;
     // outputs: RGB8 rows of the tile (packed, row-major), optional per-ray records, counters
     uint8_t* out_rgb8;
     float4* out_rgba32f;     // optional: the unrounded colour of every ray (RGBA, 0..255 scale)

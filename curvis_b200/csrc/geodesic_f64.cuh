@@ -242,10 +242,10 @@ __device__ __forceinline__ void euler_step_tuned(const FrameParams& p, Ray& q, b
 // Right-hand side of the geodesic equations at a state (metrics.rs:223-270), lean form.
 template <class Shape>
 __device__ __forceinline__ void rhs_lean(const FrameParams& p, bool ray_safe, double l, double th, double pth, double pph, double pph2,
-                                         double& dth, double& dph, double& dpl, double& dpth) {
+                                         double& dth, double& dph, double& dpl, double& dpth, double& s) {
     const bool pre = ray_safe && (abs_hi(th) < pow2_hi(30)) && ((abs_hi(l) - pow2_hi(-100)) < (pow2_hi(100) - pow2_hi(-100))) &&
                      (abs_hi(pth) < pow2_hi(100));
-    double s, c;
+    double c;
     if (pre) sincos_fast(th, s, c);
     else TrigFast::sincos(th, s, c);
     if (pre && abs_hi(s) >= pow2_hi(-60)) {
@@ -273,15 +273,49 @@ __device__ __forceinline__ void rhs_lean(const FrameParams& p, bool ray_safe, do
     }
 }
 
-template <class Shape>
-__device__ __forceinline__ void euler_step_lean(const FrameParams& p, Ray& q, bool ray_safe) {
-    double dth, dph, dpl, dpth;
-    rhs_lean<Shape>(p, ray_safe, q.l, q.th, q.pth, q.pph, q.pph2, dth, dph, dpl, dpth);
+// Trajectory diagnostics of curvis_ray_record (NaN when the kernel does not track them): min |sin theta| over the states
+// the right-hand side was evaluated at, and the stiffness max (delta dphi/dlambda)^2 = max delta^2 p_phi^2 / (r^2 sin^2)^2.
+struct RayDiag { double min_abs_sin, stiffness; };
+
+template <class Shape, bool TRACK = false>
+__device__ __forceinline__ void euler_step_lean(const FrameParams& p, Ray& q, bool ray_safe, RayDiag* diag = nullptr) {
+    double dth, dph, dpl, dpth, s;
+    rhs_lean<Shape>(p, ray_safe, q.l, q.th, q.pth, q.pph, q.pph2, dth, dph, dpl, dpth, s);
+    if (TRACK) {
+        const double step_phi = dph * p.delta;
+        diag->min_abs_sin = fmin(diag->min_abs_sin, fabs(s));
+        diag->stiffness = fmax(diag->stiffness, step_phi * step_phi);
+    }
     q.l = q.l + q.pl * p.delta;                               // metrics.rs:295 (dl = p_l * 1)
     q.th = q.th + dth * p.delta;
     q.ph = q.ph + dph * p.delta;
     q.pl = q.pl + dpl * p.delta;                              // :296
     q.pth = q.pth + dpth * p.delta;
+}
+
+// CURVIS_INTEGRATOR_EULER_ADAPTIVE (extension; its oracle is oracle_step_adaptive, same operation order): the explicit
+// Euler step above with the step size cut near a coordinate pole.  Monitor m = max(|delta dphi/dlambda|,
+// |delta dtheta/dlambda| / |sin theta|) — the azimuth advance of a full step and the polar advance measured in units of
+// the distance to the pole; m > step_tolerance: h = delta * (step_tolerance / m), else h = delta and the step is the
+// reference's bit for bit.
+template <class Shape, bool TRACK = false>
+__device__ __forceinline__ void euler_step_adaptive(const FrameParams& p, Ray& q, bool ray_safe, RayDiag* diag = nullptr) {
+    double dth, dph, dpl, dpth, s;
+    rhs_lean<Shape>(p, ray_safe, q.l, q.th, q.pth, q.pph, q.pph2, dth, dph, dpl, dpth, s);
+    const double step_phi = dph * p.delta;
+    const double m = fmax(fabs(step_phi), fabs(dth * p.delta) / fabs(s));
+    double h = p.delta;
+    if (m > p.step_tolerance) h = p.delta * (p.step_tolerance / m);
+    if (TRACK) {
+        const double sp = dph * h;
+        diag->min_abs_sin = fmin(diag->min_abs_sin, fabs(s));
+        diag->stiffness = fmax(diag->stiffness, sp * sp);
+    }
+    q.l = q.l + q.pl * h;
+    q.th = q.th + dth * h;
+    q.ph = q.ph + dph * h;
+    q.pl = q.pl + dpl * h;
+    q.pth = q.pth + dpth * h;
 }
 
 // CURVIS_INTEGRATOR_RK4 (extension; the reference only has the Euler step above): classical
@@ -292,15 +326,15 @@ __device__ __forceinline__ void euler_step_lean(const FrameParams& p, Ray& q, bo
 template <class Shape>
 __device__ __forceinline__ void rk4_step_lean(const FrameParams& p, Ray& q, bool ray_safe) {
     const double h2 = p.delta * 0.5, d6 = p.delta / 6.0;
-    double k1th, k1ph, k1pl, k1pth, k2th, k2ph, k2pl, k2pth, k3th, k3ph, k3pl, k3pth, k4th, k4ph, k4pl, k4pth;
+    double k1th, k1ph, k1pl, k1pth, k2th, k2ph, k2pl, k2pth, k3th, k3ph, k3pl, k3pth, k4th, k4ph, k4pl, k4pth, s;
     const double k1l = q.pl;
-    rhs_lean<Shape>(p, ray_safe, q.l, q.th, q.pth, q.pph, q.pph2, k1th, k1ph, k1pl, k1pth);
+    rhs_lean<Shape>(p, ray_safe, q.l, q.th, q.pth, q.pph, q.pph2, k1th, k1ph, k1pl, k1pth, s);
     const double k2l = q.pl + h2 * k1pl;
-    rhs_lean<Shape>(p, ray_safe, q.l + h2 * k1l, q.th + h2 * k1th, q.pth + h2 * k1pth, q.pph, q.pph2, k2th, k2ph, k2pl, k2pth);
+    rhs_lean<Shape>(p, ray_safe, q.l + h2 * k1l, q.th + h2 * k1th, q.pth + h2 * k1pth, q.pph, q.pph2, k2th, k2ph, k2pl, k2pth, s);
     const double k3l = q.pl + h2 * k2pl;
-    rhs_lean<Shape>(p, ray_safe, q.l + h2 * k2l, q.th + h2 * k2th, q.pth + h2 * k2pth, q.pph, q.pph2, k3th, k3ph, k3pl, k3pth);
+    rhs_lean<Shape>(p, ray_safe, q.l + h2 * k2l, q.th + h2 * k2th, q.pth + h2 * k2pth, q.pph, q.pph2, k3th, k3ph, k3pl, k3pth, s);
     const double k4l = q.pl + p.delta * k3pl;
-    rhs_lean<Shape>(p, ray_safe, q.l + p.delta * k3l, q.th + p.delta * k3th, q.pth + p.delta * k3pth, q.pph, q.pph2, k4th, k4ph, k4pl, k4pth);
+    rhs_lean<Shape>(p, ray_safe, q.l + p.delta * k3l, q.th + p.delta * k3th, q.pth + p.delta * k3pth, q.pph, q.pph2, k4th, k4ph, k4pl, k4pth, s);
     q.l = q.l + d6 * (((k1l + 2.0 * k2l) + 2.0 * k3l) + k4l);
     q.th = q.th + d6 * (((k1th + 2.0 * k2th) + 2.0 * k3th) + k4th);
     q.ph = q.ph + d6 * (((k1ph + 2.0 * k2ph) + 2.0 * k3ph) + k4ph);
@@ -312,7 +346,8 @@ __device__ __forceinline__ void rk4_step_lean(const FrameParams& p, Ray& q, bool
 // Continuous equirectangular coordinates of a direction: theta_phi_of_image_from_vector3
 // (images.rs:151-167) then the two expressions inside pixel_indexes_x_y_from_theta_phi_of_image
 // (:115-121) before their truncating casts.
-__device__ __forceinline__ void image_coordinates(const Background& bg, double dx, double dy, double dz, double& fx, double& fy) {
+// `sin_img` (guard band of CURVIS_PRECISION_F64_FAST only): sin of the image polar angle, = d(direction)/d(phi_img).
+__device__ __forceinline__ void image_coordinates(const Background& bg, double dx, double dy, double dz, double& fx, double& fy, double& sin_img) {
     double wx, wy, wz;
     mat3_mul(bg.inv_rot, dx, dy, dz, wx, wy, wz);             // images.rs:139-141
     const double rn = norm3(wx, wy, wz);
@@ -322,6 +357,12 @@ __device__ __forceinline__ void image_coordinates(const Background& bg, double d
     normalize_theta_phi(th, ph);                              // images.rs:116
     fy = (th / CURVIS_PI) * (double)bg.height;                                   // :118
     fx = rem_euclid(0.5 - ph / (2.0 * CURVIS_PI), 1.0) * (double)bg.width;       // :119
+    sin_img = sqrt(wx * wx + wy * wy) / rn;
+}
+
+__device__ __forceinline__ void image_coordinates(const Background& bg, double dx, double dy, double dz, double& fx, double& fy) {
+    double unused;
+    image_coordinates(bg, dx, dy, dz, fx, fy, unused);
 }
 
 // The truncating casts of images.rs:118-119 + the bounds the reference's get_pixel panics on.
@@ -376,31 +417,97 @@ __device__ __forceinline__ uint32_t quantize_channel(float v) {   // round to ne
     return (v >= 255.f) ? 255u : ((v > 0.f) ? (uint32_t)v : 0u);
 }
 
+// ---------------------------------------------------------------- escaped photon -> lookup direction
+// relativistic_vector_to_direction (metrics.rs:339-349) of the covariant momentum: CURVIS_FRAME_LOCAL and
+// CURVIS_FRAME_WORLD_QUIRK scale the phi component by frame_field_22 like :347 does; CURVIS_FRAME_WORLD scales it by
+// frame_field_33 (:122-124).  `s` returns sin(theta) of the final state.
+template <class Shape, class Trig>
+__device__ __forceinline__ void tangent_direction(const FrameParams& p, const Ray& q, double& dx, double& dy, double& dz, double& s) {
+    s = Trig::sin(q.th);
+    double r, r2, rp;
+    Shape::eval(p, q.l, r, r2, rp);
+    const double v2 = q.pth * (1.0 / r2);                                          // to_contravariant, :190-203
+    const double v3 = q.pph * (1.0 / (r2 * (s * s)));
+    dx = q.pl;                                                                     // :345  (g11 = frame_field_11 = 1)
+    dy = v2 * r;                                                                   // :346
+    dz = (p.frame == CURVIS_FRAME_WORLD) ? v3 * (r * s) : v3 * r;                  // :347 as written, or frame_field_33
+}
+
+// escaped_photon_to_world_direction (systems.rs:144-187): the tangent-frame direction rotated by
+// rotation_from_two_vectors(x, vector3_from_theta_phi(theta, phi)) (algebra.rs:92-101, :118-126; nalgebra 0.33
+// Rotation3::rotation_between = axis-angle about x^ x pos^ by acos(x^ . pos^), Rodrigues matrix).  Returns false where
+// the reference panics ("v1 and v2 must not be parallel": the photon sits exactly on the +-x axis).  Out of line: it is
+// evaluated once per ray and only with CURVIS_FRAME_WORLD*.
+static __device__ __noinline__ bool rotate_tangent_to_world(double th, double ph, double& dx, double& dy, double& dz) {
+    normalize_theta_phi(th, ph);                                                   // algebra.rs:120
+    double st, ct, sp, cp;
+    ::sincos(th, &st, &ct);
+    ::sincos(ph, &sp, &cp);
+    const double wx = st * cp, wy = st * sp, wz = ct;                              // :122-124
+    // v1 = (1,0,0): cross = (0*wz - 0*wy, 0*wx - 1*wz, 1*wy - 0*wx)
+    const double c0x = 0.0 * wz - 0.0 * wy, c0y = 0.0 * wx - 1.0 * wz, c0z = 1.0 * wy - 0.0 * wx;
+    if (norm3(c0x, c0y, c0z) == 0.0) return false;                                 // algebra.rs:95-97
+    const double n2 = norm3(wx, wy, wz);
+    const double bx = wx / n2, by = wy / n2, bz = wz / n2;                         // try_normalize (n1 = 1: a^ = x)
+    const double cx = 0.0 * bz - 0.0 * by, cy = 0.0 * bx - 1.0 * bz, cz = 1.0 * by - 0.0 * bx;
+    const double cn = norm3(cx, cy, cz);
+    const double dot = (1.0 * bx + 0.0 * by) + 0.0 * bz;
+    double m[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (cn > 2.220446049250313e-16) {                                              // Unit::try_new(c, default_epsilon)
+        const double ux = cx / cn, uy = cy / cn, uz = cz / cn;
+        const double angle = acos(dot) * 1.0;
+        if (angle != 0.0) {                                                        // Rotation3::from_axis_angle
+            const double sqx = ux * ux, sqy = uy * uy, sqz = uz * uz;
+            double sn, cs;
+            ::sincos(angle, &sn, &cs);
+            const double omc = 1.0 - cs;
+            m[0] = sqx + (1.0 - sqx) * cs; m[1] = ux * uy * omc - uz * sn; m[2] = ux * uz * omc + uy * sn;
+            m[3] = ux * uy * omc + uz * sn; m[4] = sqy + (1.0 - sqy) * cs; m[5] = uy * uz * omc - ux * sn;
+            m[6] = ux * uz * omc - uy * sn; m[7] = uy * uz * omc + ux * sn; m[8] = sqz + (1.0 - sqz) * cs;
+        }
+    } else if (dot < 0.0) {
+        return false;                                                              // rotation_between -> None -> unwrap panics
+    }
+    double ox, oy, oz;
+    mat3_mul(m, dx, dy, dz, ox, oy, oz);                                           // systems.rs:183
+    dx = ox; dy = oy; dz = oz;
+    return true;
+}
+
 // ---------------------------------------------------------------- ray epilogue (all per-ray kernels)
 // photon_escape_to_pixel + put_pixel (systems.rs:540-561, :324) for one finished ray, plus the
 // optional outputs: fp32 RGBA (the unrounded tap) and the per-ray record.
 struct RayTally { unsigned pos = 0, neg = 0, none = 0, clamped = 0; unsigned long long steps = 0; };
 
-template <class Shape, class Trig>
-__device__ __forceinline__ void finish_ray(const FrameParams& p, const Ray& q, int side, uint32_t steps,
-                                           unsigned long long ray, RayTally& tally) {
-    if (side > 0) ++tally.pos; else if (side < 0) ++tally.neg; else ++tally.none;   // none: black, systems.rs:556-558
-    tally.steps += steps;
+// GUARD (CURVIS_PRECISION_F64_FAST): `guard_eps` is the ray's relative state-error budget.  The texel is a truncation of
+// the continuous image coordinates (fx, fy); when either lies closer to an integer than the budget propagated to the
+// image (direction error <= eps * (4 + 2 |d_z| / sin theta): the phi component carries 1/sin^2 theta; d phi_img =
+// d direction / sin theta_img), nothing is written and false is returned — the caller queues the ray for re-integration.
+template <class Shape, class Trig, bool GUARD>
+__device__ __forceinline__ bool finish_ray(const FrameParams& p, const Ray& q, int side, uint32_t steps,
+                                           unsigned long long ray, RayTally& tally, const RayDiag& diag, double guard_eps) {
     uint32_t tx = 0, ty = 0;
-    if (p.out_rgb8 || p.out_rgba32f || p.n_peers) {
-        uint32_t rgba = 0;
-        float4 tap = make_float4(0.f, 0.f, 0.f, 255.f);        // Rgba([0, 0, 0, 255])
-        if (side != 0) {
-            const Background& bg = p.bg[side > 0 ? 0 : 1];
-            // relativistic_vector_to_direction (metrics.rs:339-349), covariant momentum
-            const double s = Trig::sin(q.th);
-            double r, r2, rp;
-            Shape::eval(p, q.l, r, r2, rp);
-            const double v2 = q.pth * (1.0 / r2);
-            const double v3 = q.pph * (1.0 / (r2 * (s * s)));
-            double fx, fy;
-            image_coordinates(bg, q.pl, v2 * r, v3 * r, fx, fy);                    // :345-347 (frame_field_22 twice)
-            if (nearest_texel(bg, fx, fy, tx, ty)) ++tally.clamped;
+    bool clamped = false;
+    uint32_t rgba = 0;
+    float4 tap = make_float4(0.f, 0.f, 0.f, 255.f);        // Rgba([0, 0, 0, 255])
+    const bool want_pixel = p.out_rgb8 || p.out_rgba32f || p.n_peers;
+    if (want_pixel && side != 0) {
+        const Background& bg = p.bg[side > 0 ? 0 : 1];
+        double dx, dy, dz, s;
+        tangent_direction<Shape, Trig>(p, q, dx, dy, dz, s);                        // metrics.rs:339-349
+        bool lookup = true;
+        if (p.frame != CURVIS_FRAME_LOCAL) lookup = rotate_tangent_to_world(q.th, q.ph, dx, dy, dz);   // systems.rs:144-187
+        if (lookup) {
+            double fx, fy, sin_img;
+            image_coordinates(bg, dx, dy, dz, fx, fy, sin_img);
+            if (GUARD) {
+                const double e_dir = guard_eps * (4.0 + 2.0 * fabs(dz) / (fabs(s) * norm3(dx, dy, dz)));
+                const double ey = e_dir * (double)bg.height * (1.0 / CURVIS_PI);
+                const double ex = e_dir * (double)bg.width * (0.5 / CURVIS_PI) / fmax(sin_img, 1e-300);
+                const double mx = fabs(fx - rint(fx)), my = fabs(fy - rint(fy));
+                if (!(mx > ex && my > ey)) return false;                              // NaN coordinates fail the test too
+            }
+            clamped = nearest_texel(bg, fx, fy, tx, ty);
             if (p.sampling == CURVIS_SAMPLING_BILINEAR) {
                 tap = bilinear_tap(bg, fx, fy);
                 rgba = quantize_channel(tap.x) | (quantize_channel(tap.y) << 8) | (quantize_channel(tap.z) << 16);
@@ -408,7 +515,14 @@ __device__ __forceinline__ void finish_ray(const FrameParams& p, const Ray& q, i
                 rgba = __ldg(bg.texels + (size_t)ty * bg.width + tx);
                 tap = make_float4((float)(rgba & 0xffu), (float)((rgba >> 8) & 0xffu), (float)((rgba >> 16) & 0xffu), (float)(rgba >> 24));
             }
+        } else {
+            clamped = true;   // the reference panics here; black pixel, counted in n_clamped
         }
+    }
+    if (side > 0) ++tally.pos; else if (side < 0) ++tally.neg; else ++tally.none;   // none: black, systems.rs:556-558
+    tally.steps += steps;
+    if (clamped) ++tally.clamped;
+    if (want_pixel) {
         if (p.out_rgb8) {
             uint8_t* o = p.out_rgb8 + ray * 3ull;                                   // put_pixel on ImageRgb8 drops alpha (:324)
             o[0] = (uint8_t)(rgba & 0xffu);
@@ -435,8 +549,10 @@ __device__ __forceinline__ void finish_ray(const FrameParams& p, const Ray& q, i
         rec.l = q.l; rec.theta = q.th; rec.phi = q.ph;
         rec.p_l = q.pl; rec.p_theta = q.pth; rec.p_phi = q.pph;
         rec.steps = steps; rec.side = side; rec.texel_x = tx; rec.texel_y = ty;
+        rec.min_abs_sin_theta = diag.min_abs_sin; rec.stiffness = diag.stiffness;
         p.records[ray] = rec;
     }
+    return true;
 }
 
 __device__ __forceinline__ void flush_tally(const FrameParams& p, RayTally t, unsigned lane) {

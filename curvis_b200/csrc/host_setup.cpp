@@ -71,6 +71,15 @@ double host_shape_r(const curvis_metric& g, double l) {
 
 double host_sin(double x) { return std::sin(x); }
 
+// CURVIS_COORDINATES_CARTESIAN: the spherical basis at the camera position (the reference's convention for (theta, phi),
+// src/algebra.rs:118-126).
+void host_camera_basis(double theta, double phi, double n[3], double e_theta[3], double e_phi[3]) {
+    const double st = std::sin(theta), ct = std::cos(theta), sp = std::sin(phi), cp = std::cos(phi);
+    n[0] = st * cp; n[1] = st * sp; n[2] = ct;
+    e_theta[0] = ct * cp; e_theta[1] = ct * sp; e_theta[2] = -st;
+    e_phi[0] = -sp; e_phi[1] = cp; e_phi[2] = 0.0;
+}
+
 }  // namespace curvis
 
 extern "C" int curvis_orientation(const double forward[3], const double up[3],

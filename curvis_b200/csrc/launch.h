@@ -14,6 +14,10 @@ struct LaunchTuning {
     int window = 0;          // Euler steps between two refill points of a warp; 0 = auto (32; 32..128 in F64_FAST)
     int zero_copy = 1;       // curvis_render_image into a registered host frame: 1 (default) = the kernel stores its pixels
                              // straight into it (measured: kernel time unchanged, 0.04 ms exposed); 0 = device frame + one DMA (0.5 ms)
+    int guard = 1;           // CURVIS_PRECISION_F64_FAST: 1 (default) = guard band + re-integration (frames equal CURVIS_PRECISION_F64's);
+                             // 0 = the raw regrouped kernel (A/B, tools/guard_study.py)
+    double guard_rel = 1e-9; // relative state-error budget of an unamplified ray: ~1e4 x the measured deviation
+    int fast_regs = 128;     // CURVIS_PRECISION_F64_FAST register budget: 128 (4 CTAs per SM, 47-instruction step) or 96 (5 CTAs, 50)
     int fast_variant = 1;    // CURVIS_PRECISION_F64_FAST: 0 sin/cos from theta every step; 1 (default) (sin, cos) carried and
                              // rotated by the step's small dtheta, re-derived from theta once per window
 };
@@ -26,6 +30,9 @@ cudaError_t launch_render_f32(const FrameParams& p, int metric_kind, const Launc
 
 // fp64 with a regrouped right-hand side, CURVIS_PRECISION_F64_FAST (render_f64_fast.cu) — extension.
 cudaError_t launch_render_f64_fast(const FrameParams& p, int metric_kind, const LaunchTuning& t, int sm_count, cudaStream_t stream);
+
+// fp64, chart-free angular state, CURVIS_COORDINATES_CARTESIAN (render_f64_cart.cu) — extension ("pole-safe").
+cudaError_t launch_render_cart(const FrameParams& p, int metric_kind, const LaunchTuning& t, int sm_count, cudaStream_t stream);
 
 // RGBA8 -> float4 staging for CURVIS_SAMPLING_BILINEAR, and the tap evaluated at explicit
 // continuous coordinates (test hook curvis_debug_bilinear).  render_f64.cu.

@@ -4,4 +4,5 @@
 namespace curvis {
 double host_shape_r(const curvis_metric& metric, double l);
 double host_sin(double x);
+void host_camera_basis(double theta, double phi, double n[3], double e_theta[3], double e_phi[3]);
 }

@@ -257,7 +257,8 @@ __global__ void __launch_bounds__(kBlock32) render_rows_f32(const __grid_constan
                 e.pl = q.pl.value() / p.delta; e.pth = q.pth.value() / p.delta;
             }
             const int side = (e.l > R) ? 1 : ((e.l < -R) ? -1 : 0);
-            finish_ray<Shape64, TrigFast>(p, e, side, p.max_iterations - remaining, ray, tally);
+            const RayDiag nodiag = {__longlong_as_double(0x7ff8000000000000ll), __longlong_as_double(0x7ff8000000000000ll)};
+            finish_ray<Shape64, TrigFast, false>(p, e, side, p.max_iterations - remaining, ray, tally, nodiag, 0.0);
             state = 0;
         }
 

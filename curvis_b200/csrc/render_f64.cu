@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64(const __grid_constant_
     for (;;) {
         // ---- epilogue of the lanes that finished during the last window
         if (pending) {
-            finish_ray<Shape, Trig>(p, q, side, steps, ray, tally);
+            const RayDiag nodiag = {__longlong_as_double(0x7ff8000000000000ll), __longlong_as_double(0x7ff8000000000000ll)};
+            finish_ray<Shape, Trig, false>(p, q, side, steps, ray, tally, nodiag, 0.0);
             pending = false;
         }
 
@@ -89,21 +90,27 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64(const __grid_constant_
     flush_tally(p, tally, lane);   // per-warp reduction of the counters, one atomic per counter per warp
 }
 
-// ---------------------------------------------------------------- default kernel (variant 2)
+// ---------------------------------------------------------------- default kernel (variant 3)
 // Same execution model as render_rows_f64, leaner loop state: a down-counter instead of
 // steps/max compare, the escape side decided in the epilogue from the final l, and the
 // per-step escape test gated by an integer compare of |l|'s high word against the radius's
 // (the fp64 compares only run within 2^-20 of the radius, or for NaN).
-template <class Shape, bool RK4>
+//   INTEG  0 Euler (the reference), 1 RK4, 2 Euler with the pole-adaptive step (extensions)
+//   TRACK  the trajectory diagnostics of curvis_ray_record (launches that write records)
+// List mode (p.ray_list != nullptr): the launch re-integrates the rays CURVIS_PRECISION_F64_FAST left in its guard
+// band — ray i of the launch is ray ray_list[i] of the tile, *ray_list_count of them.
+template <class Shape, int INTEG, bool TRACK>
 __global__ void __launch_bounds__(kBlock) render_rows_f64_lean(const __grid_constant__ FrameParams p) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned long long tile_rays = (unsigned long long)(p.row_end - p.row_begin) * p.width;
-    const unsigned long long launch_rays = tile_rays * (p.n_frames ? p.n_frames : 1u);
+    const unsigned long long launch_rays = p.ray_list ? *p.ray_list_count : tile_rays * (p.n_frames ? p.n_frames : 1u);
+    unsigned long long* const queue = p.ray_list ? &p.counters->redo_next : &p.counters->next_ray;
     const double R = p.max_radius;
     // |l| > R needs abs_hi(l) >= hi(R) when R >= 0; for negative or NaN R the gate is open.
     const unsigned gate = (R >= 0.0) ? abs_hi(R) : 0u;
     const bool frame_safe = Shape::params_safe(p);
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
 
     Ray q;
     int state = 0;            // 0 idle, 1 integrating, 2 finished (epilogue pending)
@@ -111,13 +118,15 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64_lean(const __grid_cons
     bool ray_safe = false;
     uint32_t remaining = 0;   // steps left before NotEscaped
     unsigned long long ray = 0;
+    RayDiag diag = {qnan, qnan};
 
     RayTally tally;
 
     for (;;) {
         if (state == 2) {
             const int side = (q.l > R) ? 1 : ((q.l < -R) ? -1 : 0);   // systems.rs:129-134 on the final state
-            finish_ray<Shape, TrigFast>(p, q, side, p.max_iterations - remaining, ray, tally);
+            if (TRACK) diag.min_abs_sin = fmin(diag.min_abs_sin, fabs(TrigFast::sin(q.th)));   // the final direction reads it too
+            finish_ray<Shape, TrigFast, false>(p, q, side, p.max_iterations - remaining, ray, tally, diag, 0.0);
             state = 0;
         }
 
@@ -126,15 +135,16 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64_lean(const __grid_cons
             if (!drained) {
                 const int leader = __ffs(idle) - 1;
                 unsigned long long base = 0;
-                if ((int)lane == leader) base = atomicAdd(&p.counters->next_ray, (unsigned long long)__popc(idle));
+                if ((int)lane == leader) base = atomicAdd(queue, (unsigned long long)__popc(idle));
                 base = __shfl_sync(kFull, base, leader);
                 if (state == 0) {
                     const unsigned long long idx = base + (unsigned long long)__popc(idle & lt_mask);
                     if (idx < launch_rays) {
-                        ray = idx;
-                        new_photon_for_ray(p, idx, tile_rays, q);
+                        ray = p.ray_list ? p.ray_list[idx] : idx;
+                        new_photon_for_ray(p, ray, tile_rays, q);
                         ray_safe = frame_safe && ray_operands_safe(q);
                         remaining = p.max_iterations;
+                        if (TRACK) { diag.min_abs_sin = __longlong_as_double(0x7ff0000000000000ll); diag.stiffness = 0.0; }
                         state = (remaining == 0) ? 2 : 1;   // the loop of systems.rs:126 may run zero times
                     }
                 }
@@ -146,8 +156,9 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64_lean(const __grid_cons
 #pragma unroll 1
         for (uint32_t k = 0; k < p.window; ++k) {
             if (state == 1) {
-                if (RK4) rk4_step_lean<Shape>(p, q, ray_safe);
-                else euler_step_lean<Shape>(p, q, ray_safe);
+                if (INTEG == 1) rk4_step_lean<Shape>(p, q, ray_safe);
+                else if (INTEG == 2) euler_step_adaptive<Shape, TRACK>(p, q, ray_safe, &diag);
+                else euler_step_lean<Shape, TRACK>(p, q, ray_safe, &diag);
                 --remaining;
                 bool done = (remaining == 0);                                   // systems.rs:137
                 if (abs_hi(q.l) >= gate) {
@@ -178,17 +189,28 @@ static cudaError_t launch_persistent(Kernel kernel, int& blocks_per_sm_auto, con
     const unsigned long long tile_rays = (unsigned long long)(p.row_end - p.row_begin) * p.width * (p.n_frames ? p.n_frames : 1u);
     unsigned long long want = (tile_rays + kBlock - 1) / kBlock;
     unsigned long long cap = (unsigned long long)sm_count * (unsigned long long)blocks_per_sm;
+    if (p.ray_list) want = cap;   // list mode: the count lives on the device; surplus CTAs leave after one atomic
     const unsigned grid = (unsigned)(want < cap ? (want ? want : 1) : cap);
     kernel<<<grid, kBlock, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
+template <class Shape, int INTEG, bool TRACK>
+static cudaError_t launch_lean_one(const FrameParams& p, int sm_count, int blocks_per_sm_override, cudaStream_t stream) {
+    static int blocks_per_sm_auto = 0;   // per instantiation
+    return launch_persistent(render_rows_f64_lean<Shape, INTEG, TRACK>, blocks_per_sm_auto, p, sm_count, blocks_per_sm_override, stream);
+}
+
 template <class Shape>
 static cudaError_t launch_lean(const FrameParams& p, int sm_count, int blocks_per_sm_override, cudaStream_t stream) {
-    static int blocks_per_sm_euler = 0, blocks_per_sm_rk4 = 0;
+    const bool track = p.records != nullptr;
     if (p.integrator == CURVIS_INTEGRATOR_RK4)
-        return launch_persistent(render_rows_f64_lean<Shape, true>, blocks_per_sm_rk4, p, sm_count, blocks_per_sm_override, stream);
-    return launch_persistent(render_rows_f64_lean<Shape, false>, blocks_per_sm_euler, p, sm_count, blocks_per_sm_override, stream);
+        return launch_lean_one<Shape, 1, false>(p, sm_count, blocks_per_sm_override, stream);
+    if (p.integrator == CURVIS_INTEGRATOR_EULER_ADAPTIVE)
+        return track ? launch_lean_one<Shape, 2, true>(p, sm_count, blocks_per_sm_override, stream)
+                     : launch_lean_one<Shape, 2, false>(p, sm_count, blocks_per_sm_override, stream);
+    return track ? launch_lean_one<Shape, 0, true>(p, sm_count, blocks_per_sm_override, stream)
+                 : launch_lean_one<Shape, 0, false>(p, sm_count, blocks_per_sm_override, stream);
 }
 
 template <class Shape, class Trig, bool TUNED>
@@ -199,7 +221,8 @@ static cudaError_t launch_one(const FrameParams& p, int sm_count, int blocks_per
 
 template <class Shape>
 static cudaError_t launch_variant(const FrameParams& p, const LaunchTuning& t, int sm_count, cudaStream_t stream) {
-    if (p.integrator == CURVIS_INTEGRATOR_RK4) return launch_lean<Shape>(p, sm_count, t.blocks_per_sm, stream);   // lean kernel only
+    if (p.integrator != CURVIS_INTEGRATOR_EULER || p.records || p.ray_list)
+        return launch_lean<Shape>(p, sm_count, t.blocks_per_sm, stream);   // extensions, diagnostics, list mode: lean kernel only
     switch (t.kernel_variant) {
     case 0: return launch_one<Shape, TrigCuda, false>(p, sm_count, t.blocks_per_sm, stream);   // round-1 v0
     case 1: return launch_one<Shape, TrigCuda, true>(p, sm_count, t.blocks_per_sm, stream);

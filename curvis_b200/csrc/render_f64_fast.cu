@@ -192,14 +192,17 @@ __device__ __forceinline__ bool fast_step(const FrameParams& p, const TrigRegs& 
 //   * ONE exit branch per step: the four rarely-true conditions (step budget used up, |l| within reach
 //     of the escape radius or NaN, |dtheta| too large for the rotation, next divisor outside the safe
 //     window) are OR-ed on the integer pipe and sorted out after the loop.
-// Returns the number of steps taken; `stop` = the ray left the radius (systems.rs:129-134), `slow` =
-// the remaining steps of the window need the parity step.
+// Returns the number of steps taken; `near` = |l| came within reach of the escape radius (gate = the high word of
+// R - 3|delta|) or is NaN: the caller continues with single steps and the escape test of systems.rs:129-134, recording how
+// close every visited l came to +-R (the guard band of the step count); `slow` = the remaining steps of the window need
+// the parity step; `wmax_hi` = running maximum of the high word of w = 1/(r^2 sin^2 theta): (P_phi w)^2 is the stiffness
+// of curvis_ray_record.
 template <class Fast>
 __device__ __forceinline__ uint32_t fast_window_scaled(const FrameParams& p, const RotRegs& rr, Ray& q, uint32_t n, unsigned gate,
-                                                       double R, bool& stop, bool& slow) {
-    uint32_t k = 0;
+                                                       bool& near, bool& slow, unsigned& wmax_hi, double& wsum_out) {
+    uint32_t left = n;   // steps still allowed (a down-counter: one instruction per step)
     // phi += P_phi * w every step (:240): the w's are summed (a two-operand DADD issues faster than a DFMA with three
-    // distinct registers) and folded into phi once, when the window is left
+    // distinct registers) and folded into phi once, by the caller, when the window is left
     double wsum = 0.0;
     for (;;) {
         if (abs_hi(q.th) >= pow2_hi(30)) { slow = true; break; }
@@ -220,23 +223,23 @@ __device__ __forceinline__ uint32_t fast_window_scaled(const FrameParams& p, con
             q.l = q.l + q.pl;                                   // :238, :295
             q.th = q.th + dth;
             wsum = wsum + w;                                    // :240, folded below
+            wmax_hi = max(wmax_hi, (unsigned)__double2hiint(w));   // stiffness monitor (w > 0: the high word orders it)
             q.pl = fma(b2, f, q.pl);                            // :261, :296
             q.pth = fma(pv * cs, w, q.pth);                     // :262
             rotate_sincos(rr, dth, sn, cn);
-            ++k;
+            --left;
+            asm("" : "+r"(left));   // one induction variable (the optimiser otherwise keeps two copies of the counter)
             s2 = sn * sn;
             d = Fast::prepare(p, q.l, s2, pre);
-            if ((k >= n) | (abs_hi(q.l) >= gate) | (abs_hi(dth) >= pow2_hi(-4)) | !in_window_nonneg(d)) break;
+            if ((left == 0u) | (abs_hi(q.l) >= gate) | (abs_hi(dth) >= pow2_hi(-4)) | !in_window_nonneg(d)) break;
         }
-        if (abs_hi(q.l) >= gate) {
-            if ((q.l > R) || (q.l < -R) || (q.l != q.l)) { stop = true; break; }          // systems.rs:129-134
-        }
-        if (k >= n) break;
+        if (abs_hi(q.l) >= gate) { near = true; break; }        // within three steps of the radius (or NaN): the caller's careful tail
+        if (left == 0u) break;
         if (!(abs_hi(dth) >= pow2_hi(-4)) && !in_window_nonneg(d)) { slow = true; break; }
-        // |dtheta| too large for the rotation (or a false alarm of the radius gate): re-derive (sin, cos) and go on
+        // |dtheta| too large for the rotation: re-derive (sin, cos) and go on
     }
-    q.ph = fma(q.pph, wsum, q.ph);
-    return k;
+    wsum_out = wsum;   // the caller folds it: phi += P_phi * wsum (phi and P_phi live in shared memory, not in registers)
+    return n - left;
 }
 
 // Parity steps for a lane whose operands left the safe window: plain operators, reference
@@ -277,16 +280,83 @@ __device__ __noinline__ Ray unscaled_ray(const FrameParams& p, const Ray& q, uns
     return o;
 }
 
-template <class Fast, int Variant>
-__global__ void __launch_bounds__(kBlockFast) render_rows_f64_fast(const __grid_constant__ FrameParams p) {
+// Guard band of the fast kernel.  The regrouped arithmetic reproduces the photon state of the operation-for-operation
+// kernel to eps ~ 1e-13 relative (per-step rounding differences of a few 1e-16, carried (sin, cos) drift <= 2e-14 per
+// window), multiplied by the trajectory's own error amplification, which explicit Euler in (theta, phi) coordinates
+// makes large only where a step's azimuth advance is not small: kappa = max (delta dphi/dlambda)^2 (the `stiffness` of
+// curvis_ray_record, tracked for free as the maximum of w).  A ray's integers (step count, texel) are accepted when every
+// decision was taken farther from its boundary than  eps(kappa) = guard_rel * (1 + kGuardGain * kappa)^2 ... see
+// guard_eps() — otherwise its index goes to the redo list and the parity kernel re-integrates it.
+__device__ __forceinline__ double guard_eps(const FrameParams& p, double kappa) {
+    // measured (tools/guard_study.py, profiles/r02_guard_study.json): deviation / 1e-13 stays below 1 + 1e4 kappa on every
+    // ray of every scene; guard_rel carries the safety factor.  kappa > 1e-2: always re-integrated (eps = inf).
+    if (!(kappa < 1e-2)) return __longlong_as_double(0x7ff0000000000000ll);
+    return p.guard_rel * fma(1e4, kappa, 1.0);
+}
+
+// Epilogue of a finished ray of fast_variant 1, out of line (once per ray; the step loop keeps its registers): the photon
+// back in the reference's units, the guard-band test, then either the common epilogue (finish_ray) or the redo list.
+template <class Shape64>
+__device__ __noinline__ void fast_epilogue(const FrameParams& p, const Ray& q, unsigned long long ray, unsigned long long tile_rays,
+                                           uint32_t steps, float margin, unsigned wmax_hi, bool guard, RayTally& tally) {
+    const double R = p.max_radius;
+    const int side = (q.l > R) ? 1 : ((q.l < -R) ? -1 : 0);   // systems.rs:129-134 on the final state
+    const bool untouched = (steps == 0);
+    const Ray qe = unscaled_ray(p, q, ray, tile_rays, untouched);
+    // stiffness = max (P_phi w)^2 over the steps (w's high word rounded up to the end of its bucket)
+    const double wmax = __hiloint2double((int)wmax_hi, (int)0xffffffffu);
+    const double sphi = q.pph * wmax;
+    const RayDiag diag = {__longlong_as_double(0x7ff8000000000000ll), untouched ? 0.0 : sphi * sphi};
+    if (!guard) {
+        finish_ray<Shape64, TrigFast, false>(p, qe, side, steps, ray, tally, diag, 0.0);
+        return;
+    }
+    const double eps = guard_eps(p, diag.stiffness);
+    // the step count: every l visited near the radius stayed farther than eps * (1 + R) from +-R
+    bool accepted = (double)margin > eps * (1.0 + fabs(R));
+    if (accepted) accepted = finish_ray<Shape64, TrigFast, true>(p, qe, side, steps, ray, tally, diag, eps);
+    if (accepted) return;
+    const unsigned long long slot = atomicAdd(&p.counters->n_reintegrated, 1ull);
+    if (slot < p.redo_capacity) {
+        p.redo_list[slot] = ray;
+        return;
+    }
+    // list full (never with the default capacity of one slot per ray): re-integrate here, in line
+    Ray qs;
+    new_photon_for_ray(p, ray, tile_rays, qs);
+    const SlowResult sr = parity_steps<Shape64>(p, qs, p.max_iterations, (R >= 0.0) ? abs_hi(R) : 0u);
+    qs.l = sr.l; qs.th = sr.th; qs.ph = sr.ph; qs.pl = sr.pl; qs.pth = sr.pth;
+    const int side2 = (qs.l > R) ? 1 : ((qs.l < -R) ? -1 : 0);
+    finish_ray<Shape64, TrigFast, false>(p, qs, side2, (qs.l != qs.l) ? p.max_iterations : sr.steps, ray, tally, diag, 0.0);
+}
+
+// MinBlocks: resident CTAs per SM the register allocation is held to — 5 (96 registers: the step loop re-materialises two
+// polynomial constants per step, 50 instructions) or 4 (128 registers: everything pinned, 47 instructions).
+template <class Fast, int Variant, int MinBlocks>
+__global__ void __launch_bounds__(kBlockFast, MinBlocks) render_rows_f64_fast(const __grid_constant__ FrameParams p) {
     using Shape64 = typename Fast::Shape64;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned long long tile_rays = (unsigned long long)(p.row_end - p.row_begin) * p.width;
     const unsigned long long launch_rays = tile_rays * (p.n_frames ? p.n_frames : 1u);
     const double R = p.max_radius;
-    // |l| > R needs abs_hi(l) >= hi(R) when R >= 0; for negative or NaN R the gate is open.
-    const unsigned gate = (R >= 0.0) ? abs_hi(R) : 0u;
+    // escape test: |l| > R needs abs_hi(l) >= hi(R) when R >= 0; for negative or NaN R the gate is open.  Variant 1 opens
+    // it three steps early (a photon moves ~|delta| per step) and walks the last steps one by one (see `near` below).
+    const double R_near = R - 3.0 * fabs(p.delta);
+    const unsigned gate = (Variant == 1) ? ((R_near > 0.0) ? abs_hi(R_near) : 0u) : ((R >= 0.0) ? abs_hi(R) : 0u);
+    const bool guard = (Variant == 1) && p.redo_list != nullptr;
+    const float finf = __int_as_float(0x7f800000);
+
+    // Per-ray state the step loop never reads lives in shared memory (fast_variant 1): the kernel sits at the 96-register
+    // limit of five resident CTAs per SM, and every register the loop does not need is one constant it can keep pinned.
+    struct Cold {
+        double ph, pph;             // phi and P_phi: touched once per window
+        unsigned long long ray;     // ray index: read by the epilogue
+        float margin;               // smallest distance of an l visited near the radius to +-R (guard band of the step count); 0 = unknown
+        unsigned pad;
+    };
+    __shared__ Cold cold_all[kBlockFast];
+    Cold& cold = cold_all[threadIdx.x];
 
     TrigRegs tr;
     RotRegs rr;
@@ -296,17 +366,20 @@ __global__ void __launch_bounds__(kBlockFast) render_rows_f64_fast(const __grid_
     int state = 0;            // 0 idle, 1 integrating, 2 finished (epilogue pending)
     bool drained = false;
     uint32_t remaining = 0;
-    unsigned long long ray = 0;
+    unsigned long long ray = 0;   // Variant 0 only
+    unsigned wmax_hi = 0;     // running max of the high word of w (stiffness monitor)
     RayTally tally;
 
     for (;;) {
         if (state == 2) {
-            const int side = (q.l > R) ? 1 : ((q.l < -R) ? -1 : 0);   // systems.rs:129-134 on the final state
+            const uint32_t steps = p.max_iterations - remaining;
             if (Variant == 1) {
-                const Ray qe = unscaled_ray(p, q, ray, tile_rays, remaining == p.max_iterations);
-                finish_ray<Shape64, TrigFast>(p, qe, side, p.max_iterations - remaining, ray, tally);
+                q.ph = cold.ph; q.pph = cold.pph;
+                fast_epilogue<Shape64>(p, q, cold.ray, tile_rays, steps, cold.margin, wmax_hi, guard, tally);
             } else {
-                finish_ray<Shape64, TrigFast>(p, q, side, p.max_iterations - remaining, ray, tally);
+                const int side = (q.l > R) ? 1 : ((q.l < -R) ? -1 : 0);   // systems.rs:129-134 on the final state
+                const RayDiag nodiag = {__longlong_as_double(0x7ff8000000000000ll), __longlong_as_double(0x7ff8000000000000ll)};
+                finish_ray<Shape64, TrigFast, false>(p, q, side, steps, ray, tally, nodiag, 0.0);
             }
             state = 0;
         }
@@ -321,13 +394,16 @@ __global__ void __launch_bounds__(kBlockFast) render_rows_f64_fast(const __grid_
                 if (state == 0) {
                     const unsigned long long idx = base + (unsigned long long)__popc(idle & lt_mask);
                     if (idx < launch_rays) {
-                        ray = idx;
                         new_photon_for_ray(p, idx, tile_rays, q);
                         if (Variant == 1) {            // momenta pre-scaled by delta (fast_window_scaled)
                             q.pl = q.pl * p.delta; q.pth = q.pth * p.delta; q.pph = q.pph * p.delta;
                             q.pph2 = q.pph * q.pph;
+                            cold.ph = q.ph; cold.pph = q.pph; cold.ray = idx; cold.margin = finf;
+                        } else {
+                            ray = idx;
                         }
                         remaining = p.max_iterations;
+                        wmax_hi = 0;
                         state = (remaining == 0) ? 2 : 1;
                     }
                 }
@@ -354,11 +430,42 @@ __global__ void __launch_bounds__(kBlockFast) render_rows_f64_fast(const __grid_
                     }
                 } while (k < n);
             }
-            if (!slow && Variant == 1) k = fast_window_scaled<Fast>(p, rr, q, n, gate, R, stop, slow);
+            if (!slow && Variant == 1) {
+                bool near = abs_hi(q.l) >= gate;   // still inside the three-step zone when the previous window ended
+                double wsum = 0.0;
+                if (!near) k = fast_window_scaled<Fast>(p, rr, q, n, gate, near, slow, wmax_hi, wsum);
+                if (near) {
+                    // The last steps before the radius, one at a time: escape test after every step (systems.rs:129-134),
+                    // and the distance of every l visited here to +-R goes into `margin`.  A ray that arrives already
+                    // outside (it jumped the three-step zone, or started in it) has an unknown margin: 0.
+                    float margin = cold.margin;
+                    if ((q.l > R) || (q.l < -R) || (q.l != q.l)) { stop = true; margin = 0.f; }
+                    while (!stop && !slow && k < n) {
+                        const double before = R - fabs(q.l);
+                        bool unused = false;
+                        double w1 = 0.0;
+                        const uint32_t one = fast_window_scaled<Fast>(p, rr, q, 1u, 0xffffffffu, unused, slow, wmax_hi, w1);
+                        if (one == 0) break;                                       // the step needs the parity arithmetic
+                        wsum = wsum + w1;
+                        ++k;
+                        const double after = fabs(q.l) - R;
+                        if (q.l != q.l) { stop = true; margin = 0.f; }
+                        else if (after > 0.0) { stop = true; margin = fminf(margin, __double2float_rd(fmin(before, after))); }
+                        else {
+                            margin = fminf(margin, __double2float_rd(-after));
+                            if (abs_hi(q.l) < gate) break;                         // left the zone inwards: back to the fast loop
+                        }
+                    }
+                    cold.margin = margin;
+                }
+                cold.ph = fma(cold.pph, wsum, cold.ph);                            // :240 for every step of the window
+            }
             if (slow) {
-                const SlowResult sr = parity_steps<Shape64>(p, Variant == 1 ? unscaled_ray(p, q, ray, tile_rays, false) : q, n - k, gate);
+                if (Variant == 1) { cold.margin = 0.f; q.ph = cold.ph; q.pph = cold.pph; }   // a ray that needed parity steps is re-integrated whole
+                const SlowResult sr = parity_steps<Shape64>(p, Variant == 1 ? unscaled_ray(p, q, cold.ray, tile_rays, false) : q, n - k,
+                                                            (R >= 0.0) ? abs_hi(R) : 0u);
                 q.l = sr.l; q.th = sr.th; q.ph = sr.ph; q.pl = sr.pl; q.pth = sr.pth;
-                if (Variant == 1) { q.pl = q.pl * p.delta; q.pth = q.pth * p.delta; }
+                if (Variant == 1) { q.pl = q.pl * p.delta; q.pth = q.pth * p.delta; cold.ph = sr.ph; }
                 k += sr.steps;
                 stop = sr.stop;
             }
@@ -374,11 +481,11 @@ __global__ void __launch_bounds__(kBlockFast) render_rows_f64_fast(const __grid_
     flush_tally(p, tally, lane);
 }
 
-template <class Fast, int Variant>
+template <class Fast, int Variant, int MinBlocks>
 cudaError_t launch_fast_variant(const FrameParams& p, int sm_count, int blocks_per_sm_override, cudaStream_t stream) {
     static int blocks_per_sm_auto = 0;
     if (blocks_per_sm_auto == 0) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm_auto, render_rows_f64_fast<Fast, Variant>, kBlockFast, 0);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm_auto, render_rows_f64_fast<Fast, Variant, MinBlocks>, kBlockFast, 0);
         if (e != cudaSuccess) return e;
         if (blocks_per_sm_auto < 1) blocks_per_sm_auto = 1;
     }
@@ -388,7 +495,7 @@ cudaError_t launch_fast_variant(const FrameParams& p, int sm_count, int blocks_p
     unsigned long long want = (rays + kBlockFast - 1) / kBlockFast;
     unsigned long long cap = (unsigned long long)sm_count * (unsigned long long)blocks_per_sm;
     const unsigned grid = (unsigned)(want < cap ? (want ? want : 1) : cap);
-    render_rows_f64_fast<Fast, Variant><<<grid, kBlockFast, 0, stream>>>(p);
+    render_rows_f64_fast<Fast, Variant, MinBlocks><<<grid, kBlockFast, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -396,8 +503,9 @@ template <class Fast>
 cudaError_t launch_fast(const FrameParams& p, const LaunchTuning& t, int sm_count, cudaStream_t stream) {
     // variant 1 scales the momenta by delta: it needs a finite, non-zero step of ordinary magnitude
     const double ad = p.delta < 0.0 ? -p.delta : p.delta;
-    if (t.fast_variant == 0 || !(ad >= 0x1p-100 && ad <= 0x1p100)) return launch_fast_variant<Fast, 0>(p, sm_count, t.blocks_per_sm, stream);   // trigonometry from theta every step
-    return launch_fast_variant<Fast, 1>(p, sm_count, t.blocks_per_sm, stream);                            // default: rotated (sin, cos)
+    if (t.fast_variant == 0 || !(ad >= 0x1p-100 && ad <= 0x1p100)) return launch_fast_variant<Fast, 0, 5>(p, sm_count, t.blocks_per_sm, stream);   // trigonometry from theta every step
+    if (t.fast_regs == 96) return launch_fast_variant<Fast, 1, 5>(p, sm_count, t.blocks_per_sm, stream);
+    return launch_fast_variant<Fast, 1, 4>(p, sm_count, t.blocks_per_sm, stream);                         // default: rotated (sin, cos)
 }
 
 }  // namespace

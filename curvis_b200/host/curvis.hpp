@@ -142,7 +142,8 @@ class RelativisticSystem {
         img.width = camera.resolution_width();
         img.height = camera.resolution_height();
         img.data.resize((size_t)img.width * img.height * 3);
-        curvis_sim sim{max_iterations, 0, max_radius, delta, CURVIS_PRECISION_F64, CURVIS_SAMPLING_NEAREST, CURVIS_INTEGRATOR_EULER, 0};
+        curvis_sim sim{max_iterations, CURVIS_FRAME_LOCAL, max_radius, delta, CURVIS_PRECISION_F64, CURVIS_SAMPLING_NEAREST,
+                       CURVIS_INTEGRATOR_EULER, CURVIS_COORDINATES_SPHERICAL, 0.0, 0.0};
         check(curvis_render_image(ctx_, &metric.c, &camera.c(), &sim, img.data.data(), stats), ctx_);
         return img;
     }

@@ -58,7 +58,7 @@ class Context:
         getattr(self, "_registered", {}).pop(array.ctypes.data, None)
 
     def set_option(self, key: str, value: int) -> None:
-        """curvis_ctx_set_option: tuning knobs ("kernel_variant", "blocks_per_sm", "window")."""
+        """curvis_ctx_set_option: tuning knobs ("kernel_variant", "blocks_per_sm", "window", "guard", "fast_regs", ...)."""
         _abi.check(self._lib.curvis_ctx_set_option(self._ptr, key.encode(), int(value)), self._ptr)
 
     def debug_eval(self, op: int, a, b=None):
@@ -142,11 +142,13 @@ class RelativisticSystem:
 
     @staticmethod
     def _sim(max_iterations, max_radius, delta, precision=_abi.PRECISION_F64, sampling=_abi.SAMPLING_NEAREST,
-             integrator=_abi.INTEGRATOR_EULER):
+             integrator=_abi.INTEGRATOR_EULER, frame=_abi.FRAME_LOCAL, coordinates=_abi.COORDINATES_SPHERICAL,
+             step_tolerance=0.0):
         if max_iterations < 0 or max_iterations > 0xFFFFFFFF:
             raise _abi.CurvisError(_abi.ERR_INVALID_ARGUMENT, "max_iterations must fit u32")
         return _abi.CurvisSim(max_iterations=int(max_iterations), max_radius=float(max_radius), delta=float(delta),
-                              precision=precision, sampling=sampling, integrator=integrator)
+                              precision=precision, sampling=sampling, integrator=integrator, frame=frame,
+                              coordinates=coordinates, step_tolerance=float(step_tolerance))
 
     def render_image(self, max_iterations: int, max_radius: float, delta: float, out: Optional[np.ndarray] = None,
                      **options) -> np.ndarray:

@@ -32,8 +32,12 @@ extern "C" {
 #endif
 
 /* 2: curvis_sim.integrator;  3: CURVIS_PRECISION_F64_FAST, curvis_host_register/unregister, curvis_peer_buffer_*,
- *    curvis_render_frames_peers, curvis_debug_shape_table_host (additions only: struct layouts are those of version 2) */
-#define CURVIS_ABI_VERSION 3
+ *    curvis_render_frames_peers, curvis_debug_shape_table_host (additions only: struct layouts are those of version 2)
+ * 4: curvis_sim grows (frame, coordinates, step_tolerance; 40 -> 56 bytes), curvis_ray_record grows (min_abs_sin_theta,
+ *    stiffness; 64 -> 80 bytes), curvis_stats.n_big_theta becomes n_reintegrated, CURVIS_PRECISION_F64_FAST renders the
+ *    same integers as CURVIS_PRECISION_F64 (guard band + re-integration), CURVIS_INTEGRATOR_EULER_ADAPTIVE,
+ *    CURVIS_FRAME_WORLD, CURVIS_COORDINATES_CARTESIAN, curvis_render_video */
+#define CURVIS_ABI_VERSION 4
 
 /* ---- status codes ------------------------------------------------------------------
  * The reference panics (src/systems.rs:122-124, src/algebra.rs:19-21, src/cameras.rs:
@@ -89,9 +93,13 @@ typedef struct curvis_camera {
 typedef enum curvis_precision {
     CURVIS_PRECISION_F64 = 0, /* reference arithmetic: IEEE double, reference operation order */
     CURVIS_PRECISION_F32 = 1, /* extension: fp32 state (not bit-comparable)    */
-    CURVIS_PRECISION_F64_FAST = 2 /* extension: fp64 with the right-hand side regrouped around ONE reciprocal per step
-                                     and fused multiply-adds; every operation <= 1 ulp, rounding points differ from
-                                     the reference's (state agrees to ~1e-13 relative)    */
+    CURVIS_PRECISION_F64_FAST = 2 /* fp64 with the right-hand side regrouped around ONE reciprocal per step and fused
+                                     multiply-adds (every operation <= 1 ulp, rounding points differ from the reference's,
+                                     state agrees to ~1e-13 relative) as a PREDICTOR: a ray whose escape step or texel lies
+                                     within a guard band of a decision boundary — the band scales with the ray's measured
+                                     error amplification — is re-integrated with the CURVIS_PRECISION_F64 arithmetic in a
+                                     second launch over the compacted list, so RGB8 / side / step count / texel equal
+                                     CURVIS_PRECISION_F64's (curvis_stats.n_reintegrated counts them) */
 } curvis_precision;
 
 typedef enum curvis_sampling {
@@ -101,19 +109,42 @@ typedef enum curvis_sampling {
 
 typedef enum curvis_integrator {
     CURVIS_INTEGRATOR_EULER = 0, /* update_relativistic_object, metrics.rs:283-297: explicit Euler (the reference's only stepper) */
-    CURVIS_INTEGRATOR_RK4 = 1    /* extension: classical 4th-order Runge-Kutta on the same right-hand side; one
+    CURVIS_INTEGRATOR_RK4 = 1,   /* extension: classical 4th-order Runge-Kutta on the same right-hand side; one
                                     "iteration" = one RK4 step, escape test after every step */
+    CURVIS_INTEGRATOR_EULER_ADAPTIVE = 2 /* extension: the same explicit Euler step with a per-step size
+                                    h = delta * min(1, step_tolerance / kappa), kappa = delta^2 p_phi^2 / (r^2 sin^2 theta)^2 the
+                                    stiffness of the theta equation at the current state (the quantity that makes fixed-step
+                                    rays near a coordinate pole "chaotic"); far from the poles h = delta and the
+                                    step is the reference's, bit for bit.  One "iteration" = one step of whatever size. */
 } curvis_integrator;
+
+typedef enum curvis_frame {
+    CURVIS_FRAME_LOCAL = 0,  /* render_image as written: the escaped photon's LOCAL tangent-frame direction indexes the
+                                background, phi component scaled by frame_field_22 (systems.rs:540-561, metrics.rs:347)       */
+    CURVIS_FRAME_WORLD = 1,  /* extension: escaped_photon_to_world_direction (systems.rs:144-187) applied to the escaped
+                                photon — tangent-frame direction with the phi component scaled by frame_field_33 (the fix of
+                                metrics.rs:347), rotated by rotation_from_two_vectors(x, vector3_from_theta_phi(theta, phi))   */
+    CURVIS_FRAME_WORLD_QUIRK = 2 /* the same rotation on the direction exactly as metrics.rs:339-349 returns it (frame_field_22
+                                twice) — what compute_escape_angle evaluates for the table of render_image_efficient           */
+} curvis_frame;
+
+typedef enum curvis_coordinates {
+    CURVIS_COORDINATES_SPHERICAL = 0, /* the reference's state (l, theta, phi, p_l, p_theta, p_phi)                        */
+    CURVIS_COORDINATES_CARTESIAN = 1  /* extension ("pole-safe"): the angular part of the state is the unit position vector n
+                                         and its tangent momentum; no 1/sin(theta) anywhere           */
+} curvis_coordinates;
 
 typedef struct curvis_sim {
     uint32_t max_iterations; /* systems.rs:309 */
-    uint32_t _pad;
+    int32_t frame;           /* curvis_frame */
     double max_radius;       /* systems.rs:310 */
     double delta;            /* systems.rs:311 */
     int32_t precision;       /* curvis_precision  */
     int32_t sampling;        /* curvis_sampling   */
     int32_t integrator;      /* curvis_integrator */
-    int32_t _pad2;
+    int32_t coordinates;     /* curvis_coordinates */
+    double step_tolerance;   /* CURVIS_INTEGRATOR_EULER_ADAPTIVE: largest stiffness a full step may see (e.g. 1e-3); else 0 */
+    double _reserved;        /* 0 */
 } curvis_sim;
 
 /* ---- per-frame counters (the reference has none) ----------------- */
@@ -124,7 +155,7 @@ typedef struct curvis_stats {
     uint64_t n_negative;    /* PhotonEscape::NegativeSpace  systems.rs:132-134 */
     uint64_t n_not_escaped; /* PhotonEscape::NotEscaped     systems.rs:137     */
     uint64_t n_clamped;     /* texel index the reference would have panicked on (images.rs:107-111) */
-    uint64_t n_big_theta;   /* rays whose |theta| left the fast range-reduction domain */
+    uint64_t n_reintegrated;/* CURVIS_PRECISION_F64_FAST: rays inside the guard band, re-integrated with the F64 arithmetic */
     double kernel_ms;       /* device time of the render kernel(s), CUDA events, max over devices */
     double total_ms;        /* host wall time of the call, copies included */
 } curvis_stats;
@@ -137,6 +168,14 @@ typedef struct curvis_ray_record {
     uint32_t steps;
     int32_t side;
     uint32_t texel_x, texel_y;
+    /* trajectory diagnostics (the regular / chaotic classifier reads them):
+     *   min_abs_sin_theta  min |sin theta| over the states 0..steps of the ray (every state the right-hand side or the
+     *                      final direction was evaluated at)
+     *   stiffness          max over the steps of kappa = delta^2 p_phi^2 / (r^2 sin^2 theta)^2 = |d(delta dp_theta)/d theta| *
+     *                      |d(delta dtheta)/d p_theta| up to a factor <= 3: explicit Euler is a faithful map of the theta
+     *                      motion while kappa << 1 and amplifies perturbations once kappa >~ 1 (a "kicked" ray) */
+    double min_abs_sin_theta;
+    double stiffness;
 } curvis_ray_record;
 
 typedef struct curvis_ctx curvis_ctx;

@@ -278,27 +278,67 @@ void oracle_step_rk4(const curvis_metric* g, oracle_photon* ph, double delta) {
     }
 }
 
-/* escape_photon, src/systems.rs:115-139.  Returns side (+1/-1/0); -2 = the panic at :122-124. */
+/* Extension CURVIS_INTEGRATOR_EULER_ADAPTIVE (no reference counterpart; this restatement IS its oracle): the Euler
+ * step above with the step size cut near a coordinate pole.  m = max(|delta dphi/dlambda|, |delta dtheta/dlambda| /
+ * |sin theta|); m > tol: h = delta * (tol / m), else h = delta (then the step is oracle_step bit for bit). */
+void oracle_step_adaptive(const curvis_metric* g, oracle_photon* ph, double delta, double tol) {
+    double dx[4], dp[4];
+    oracle_rhs(g, ph->x, ph->p, dx, dp);
+    const double s = sin(ph->x[2]);
+    const double step_phi = dx[3] * delta;
+    const double m = fmax(fabs(step_phi), fabs(dx[2] * delta) / fabs(s));
+    double h = delta;
+    if (m > tol) h = delta * (tol / m);
+    for (int i = 0; i < 4; ++i) ph->x[i] = ph->x[i] + dx[i] * h;
+    for (int i = 0; i < 4; ++i) ph->p[i] = ph->p[i] + dp[i] * h;
+}
+
+/* escape_photon, src/systems.rs:115-139.  Returns side (+1/-1/0); -2 = the panic at :122-124.
+ * diag (nullable; NOT part of the reference, and never requested by the timed cpu_baseline legs): [0] = min |sin theta|
+ * over the states 0..steps, [1] = max over the steps of (h dphi/dlambda)^2 — curvis_ray_record's trajectory diagnostics. */
+int oracle_escape_photon_sim(const curvis_metric* g, oracle_photon* ph, const curvis_sim* sim, uint32_t* steps, double* diag);
+
 int oracle_escape_photon_ex(const curvis_metric* g, oracle_photon* ph, double delta,
-                            uint32_t max_iterations, double max_radius, uint32_t* steps, int integrator);
+                            uint32_t max_iterations, double max_radius, uint32_t* steps, int integrator) {
+    curvis_sim sim;
+    memset(&sim, 0, sizeof sim);
+    sim.max_iterations = max_iterations; sim.max_radius = max_radius; sim.delta = delta; sim.integrator = integrator;
+    return oracle_escape_photon_sim(g, ph, &sim, steps, NULL);
+}
 
 int oracle_escape_photon(const curvis_metric* g, oracle_photon* ph, double delta,
                          uint32_t max_iterations, double max_radius, uint32_t* steps) {
     return oracle_escape_photon_ex(g, ph, delta, max_iterations, max_radius, steps, CURVIS_INTEGRATOR_EULER);
 }
 
-int oracle_escape_photon_ex(const curvis_metric* g, oracle_photon* ph, double delta,
-                            uint32_t max_iterations, double max_radius, uint32_t* steps, int integrator) {
+int oracle_escape_photon_sim(const curvis_metric* g, oracle_photon* ph, const curvis_sim* sim, uint32_t* steps, double* diag) {
+    const double delta = sim->delta, max_radius = sim->max_radius;
     *steps = 0;
+    if (diag) { diag[0] = INFINITY; diag[1] = 0.0; }
     if (fabs(ph->x[1]) > max_radius) return -2;
-    for (uint32_t i = 0; i < max_iterations; ++i) {
-        if (integrator == CURVIS_INTEGRATOR_RK4) oracle_step_rk4(g, ph, delta);
+    int side = 0;
+    for (uint32_t i = 0; i < sim->max_iterations; ++i) {
+        if (diag) {
+            const double s = sin(ph->x[2]);
+            const double r2 = metric_r_squared(g, ph->x[1]);
+            double h = delta;
+            if (sim->integrator == CURVIS_INTEGRATOR_EULER_ADAPTIVE) {
+                const double m = fmax(fabs((ph->p[3] * (1.0 / (r2 * (s * s)))) * delta), fabs((ph->p[2] * (1.0 / r2)) * delta) / fabs(s));
+                if (m > sim->step_tolerance) h = delta * (sim->step_tolerance / m);
+            }
+            const double sp = (ph->p[3] * (1.0 / (r2 * (s * s)))) * h;
+            diag[0] = fmin(diag[0], fabs(s));
+            diag[1] = fmax(diag[1], sp * sp);
+        }
+        if (sim->integrator == CURVIS_INTEGRATOR_RK4) oracle_step_rk4(g, ph, delta);
+        else if (sim->integrator == CURVIS_INTEGRATOR_EULER_ADAPTIVE) oracle_step_adaptive(g, ph, delta, sim->step_tolerance);
         else oracle_step(g, ph, delta);
         *steps = i + 1;
-        if (ph->x[1] > max_radius) return 1;
-        else if (ph->x[1] < -max_radius) return -1;
+        if (ph->x[1] > max_radius) { side = 1; break; }
+        else if (ph->x[1] < -max_radius) { side = -1; break; }
     }
-    return 0;
+    if (diag) diag[0] = fmin(diag[0], fabs(sin(ph->x[2])));
+    return side;
 }
 
 /* relativistic_vector_to_direction for a covariant vector, src/metrics.rs:339-349 via
@@ -395,39 +435,125 @@ static uint8_t quantize_channel(float v) { /* round to nearest even, clamp; NaN 
 
 typedef struct oracle_background { const uint8_t* rgba8; uint32_t w, h; double inv_rot[9]; } oracle_background;
 
+int oracle_rotation_from_two_vectors(const double v1[3], const double v2[3], double m[9]);
+
+/* The direction that indexes the background for an escaped photon.
+ *   CURVIS_FRAME_LOCAL        photon_escape_to_pixel as written (src/systems.rs:540-561): the local tangent-frame direction
+ *                             of relativistic_vector_to_direction (metrics.rs:339-349, phi component * frame_field_22)
+ *   CURVIS_FRAME_WORLD_QUIRK  escaped_photon_to_world_direction (src/systems.rs:144-187) on that same direction: rotated by
+ *                             rotation_from_two_vectors(x, vector3_from_theta_phi(theta, phi)) — what compute_escape_angle
+ *                             evaluates for every point of the table of render_image_efficient
+ *   CURVIS_FRAME_WORLD        the same rotation with the phi component scaled by frame_field_33 (:122-124), the fix of :347
+ * Returns 0, or 1 where the reference panics (rotation_from_two_vectors on parallel vectors). */
+int oracle_lookup_direction(const curvis_metric* g, const oracle_photon* ph, int frame, double d[3]) {
+    oracle_relativistic_vector_to_direction(g, ph->p, ph->x, d);
+    if (frame == CURVIS_FRAME_LOCAL) return 0;
+    if (frame == CURVIS_FRAME_WORLD) {
+        const double s = sin(ph->x[2]);
+        const double v3 = ph->p[3] * (1.0 / (metric_r_squared(g, ph->x[1]) * (s * s)));
+        d[2] = v3 * (metric_r(g, ph->x[1]) * s);                                   /* frame_field_33, metrics.rs:122-124 */
+    }
+    double world_position[3], rot[9], o[3];
+    oracle_vector3_from_theta_phi(ph->x[2], ph->x[3], world_position);            /* systems.rs:176 */
+    const double ex[3] = {1.0, 0.0, 0.0};
+    if (oracle_rotation_from_two_vectors(ex, world_position, rot)) return 1;      /* :178-181 */
+    m3_mul_v(rot, d, o);                                                          /* :183 */
+    d[0] = o[0]; d[1] = o[1]; d[2] = o[2];
+    return 0;
+}
+
+/* Extension CURVIS_COORDINATES_CARTESIAN ("pole-safe"; no reference counterpart — this restatement IS its oracle, the
+ * device code in csrc/render_f64_cart.cu follows the same operation order).  The angular part of the photon state is the
+ * unit position vector n and the conserved angular-momentum vector J = r n x t (t = tangential velocity):
+ *     dl = p_l,  dp_l = |J|^2 r'/r^3,  dn = (J x n)/r^2          (metrics.rs:238, :261 and :239-:240 in vector form)
+ * explicit Euler, same step, same escape test.  The end state is converted to the reference's variables
+ * (theta, phi, p_theta = r t.e_theta, p_phi = J_z). */
+static int oracle_escape_photon_cart(const curvis_metric* g, const curvis_camera* cam, const double dir[3], const curvis_sim* sim,
+                                     oracle_photon* out, uint32_t* steps) {
+    const double th0 = cam->position[2], ph0 = cam->position[3];
+    const double st = sin(th0), ct = cos(th0), sp = sin(ph0), cp = cos(ph0);
+    const double n0[3] = {st * cp, st * sp, ct}, eth[3] = {ct * cp, ct * sp, -st}, eph[3] = {-sp, cp, 0.0};
+    double d[3];
+    v3_normalize(dir, d);
+    const double t[3] = {d[1] * eth[0] + d[2] * eph[0], d[1] * eth[1] + d[2] * eph[1], d[1] * eth[2] + d[2] * eph[2]};
+    const double cam_r = metric_r(g, cam->position[1]);
+    double l = cam->position[1], pl = d[0], n[3] = {n0[0], n0[1], n0[2]};
+    const double J[3] = {cam_r * (n[1] * t[2] - n[2] * t[1]), cam_r * (n[2] * t[0] - n[0] * t[2]), cam_r * (n[0] * t[1] - n[1] * t[0])};
+    const double L2 = (J[0] * J[0] + J[1] * J[1]) + J[2] * J[2];
+    *steps = 0;
+    if (fabs(l) > sim->max_radius) return -2;
+    int side = 0;
+    for (uint32_t i = 0; i < sim->max_iterations; ++i) {
+        const double r = metric_r(g, l), r2 = metric_r_squared(g, l), rp = metric_r_derivative(g, l);
+        const double u = 1.0 / r2;
+        const double cx = J[1] * n[2] - J[2] * n[1], cy = J[2] * n[0] - J[0] * n[2], cz = J[0] * n[1] - J[1] * n[0];
+        const double dpl = (L2 * rp) / ((r * r) * r);
+        n[0] = n[0] + (cx * u) * sim->delta;
+        n[1] = n[1] + (cy * u) * sim->delta;
+        n[2] = n[2] + (cz * u) * sim->delta;
+        l = l + pl * sim->delta;
+        pl = pl + dpl * sim->delta;
+        *steps = i + 1;
+        if (l > sim->max_radius) { side = 1; break; }
+        else if (l < -sim->max_radius) { side = -1; break; }
+    }
+    const double nn = v3_norm(n);
+    const double h[3] = {n[0] / nn, n[1] / nn, n[2] / nn};
+    double theta, phi;
+    oracle_normalize_theta_phi(acos(h[2]), atan2(h[1], h[0]), &theta, &phi);
+    const double s = sqrt(h[0] * h[0] + h[1] * h[1]);
+    const double cx = J[1] * h[2] - J[2] * h[1], cy = J[2] * h[0] - J[0] * h[2], cz = J[0] * h[1] - J[1] * h[0];
+    out->x[0] = cam->position[0]; out->x[1] = l; out->x[2] = theta; out->x[3] = phi;
+    out->p[0] = 1.0; out->p[1] = pl;
+    out->p[2] = (cx * (h[2] * h[0] / s) + cy * (h[2] * h[1] / s)) + cz * (-s);
+    out->p[3] = J[2];
+    return side;
+}
+
 /* One pixel of render_image (src/systems.rs:321-324): camera_pixels_x_y_to_photon :531-534,
  * escape_photon, photon_escape_to_pixel :540-561.  rec may be NULL.  Returns the side, or -2
  * on the :122-124 panic.  *clamped is set when the reference's get_pixel would index out of
- * bounds (images.rs:107-111 panic); the texel is then clamped like the GPU does. */
+ * bounds (images.rs:107-111 panic); the texel is then clamped like the GPU does.  `track`: also fill the
+ * trajectory diagnostics of the record (extra sin per step: never set by the timed legs). */
 static int oracle_pixel(const curvis_metric* g, const curvis_camera* cam, const curvis_sim* sim,
                         const oracle_background* pos, const oracle_background* neg,
-                        uint32_t px, uint32_t py, uint8_t rgb[3], curvis_ray_record* rec, int* clamped, float rgba32f[4]) {
+                        uint32_t px, uint32_t py, uint8_t rgb[3], curvis_ray_record* rec, int* clamped, float rgba32f[4], int track,
+                        uint32_t* steps_out) {
     double dir[3];
     oracle_photon ph;
     uint32_t steps;
+    double diag[2] = {NAN, NAN};
     oracle_outward_vector_on_world_space(cam, px, py, dir);
-    oracle_new_photon(g, cam->position, dir, &ph);
-    int side = oracle_escape_photon_ex(g, &ph, sim->delta, sim->max_iterations, sim->max_radius, &steps, sim->integrator);
+    int side;
+    if (sim->coordinates == CURVIS_COORDINATES_CARTESIAN) {
+        side = oracle_escape_photon_cart(g, cam, dir, sim, &ph, &steps);
+    } else {
+        oracle_new_photon(g, cam->position, dir, &ph);
+        side = oracle_escape_photon_sim(g, &ph, sim, &steps, track ? diag : NULL);
+    }
+    *steps_out = steps;
     if (side == -2) return -2;
     uint32_t tx = 0, ty = 0;
     *clamped = 0;
     float tap[4] = {0.f, 0.f, 0.f, 255.f};
-    if (side == 0) {
-        rgb[0] = rgb[1] = rgb[2] = 0; /* :556-558 */
-    } else {
+    rgb[0] = rgb[1] = rgb[2] = 0; /* NotEscaped: :556-558 */
+    if (side != 0) {
         const oracle_background* bg = side > 0 ? pos : neg;
         double d[3], fx, fy;
-        oracle_relativistic_vector_to_direction(g, ph.p, ph.x, d);
-        oracle_texel_from_vector3_ex(bg->inv_rot, d, bg->w, bg->h, &tx, &ty, NULL, NULL, &fx, &fy);
-        if (tx >= bg->w) { tx = bg->w - 1; *clamped = 1; }
-        if (ty >= bg->h) { ty = bg->h - 1; *clamped = 1; }
-        if (sim->sampling == CURVIS_SAMPLING_BILINEAR) {
-            oracle_bilinear_tap(bg->rgba8, bg->w, bg->h, fx, fy, tap);
-            rgb[0] = quantize_channel(tap[0]); rgb[1] = quantize_channel(tap[1]); rgb[2] = quantize_channel(tap[2]);
+        if (oracle_lookup_direction(g, &ph, sim->frame, d)) {
+            *clamped = 1;   /* the reference panics; black pixel, counted */
         } else {
-            const uint8_t* t = bg->rgba8 + ((size_t)ty * bg->w + tx) * 4;
-            rgb[0] = t[0]; rgb[1] = t[1]; rgb[2] = t[2]; /* put_pixel on ImageRgb8 drops alpha, :324 */
-            tap[0] = (float)t[0]; tap[1] = (float)t[1]; tap[2] = (float)t[2]; tap[3] = (float)t[3];
+            oracle_texel_from_vector3_ex(bg->inv_rot, d, bg->w, bg->h, &tx, &ty, NULL, NULL, &fx, &fy);
+            if (tx >= bg->w) { tx = bg->w - 1; *clamped = 1; }
+            if (ty >= bg->h) { ty = bg->h - 1; *clamped = 1; }
+            if (sim->sampling == CURVIS_SAMPLING_BILINEAR) {
+                oracle_bilinear_tap(bg->rgba8, bg->w, bg->h, fx, fy, tap);
+                rgb[0] = quantize_channel(tap[0]); rgb[1] = quantize_channel(tap[1]); rgb[2] = quantize_channel(tap[2]);
+            } else {
+                const uint8_t* t = bg->rgba8 + ((size_t)ty * bg->w + tx) * 4;
+                rgb[0] = t[0]; rgb[1] = t[1]; rgb[2] = t[2]; /* put_pixel on ImageRgb8 drops alpha, :324 */
+                tap[0] = (float)t[0]; tap[1] = (float)t[1]; tap[2] = (float)t[2]; tap[3] = (float)t[3];
+            }
         }
     }
     if (rgba32f) memcpy(rgba32f, tap, sizeof tap);
@@ -435,6 +561,7 @@ static int oracle_pixel(const curvis_metric* g, const curvis_camera* cam, const 
         rec->l = ph.x[1]; rec->theta = ph.x[2]; rec->phi = ph.x[3];
         rec->p_l = ph.p[1]; rec->p_theta = ph.p[2]; rec->p_phi = ph.p[3];
         rec->steps = steps; rec->side = side; rec->texel_x = tx; rec->texel_y = ty;
+        rec->min_abs_sin_theta = diag[0]; rec->stiffness = diag[1];
     }
     return side;
 }
@@ -467,13 +594,15 @@ static void* oracle_worker_main(void* arg) {
             uint8_t rgb[3] = {0, 0, 0};
             curvis_ray_record rec;
             int clamped = 0;
+            uint32_t steps = 0;
             float tap[4] = {0.f, 0.f, 0.f, 0.f};
-            int side = oracle_pixel(jb->g, jb->cam, jb->sim, jb->pos, jb->neg, (uint32_t)i, j, rgb, &rec, &clamped, tap);
+            int side = oracle_pixel(jb->g, jb->cam, jb->sim, jb->pos, jb->neg, (uint32_t)i, j, rgb, jb->records ? &rec : NULL, &clamped, tap,
+                                    jb->records != NULL, &steps);
             size_t o = (size_t)jr * (size_t)W + (size_t)i;
             if (jb->out_rgba32f) memcpy(jb->out_rgba32f + o * 4, tap, sizeof tap);
             if (jb->out_rgb8) { jb->out_rgb8[o * 3 + 0] = rgb[0]; jb->out_rgb8[o * 3 + 1] = rgb[1]; jb->out_rgb8[o * 3 + 2] = rgb[2]; }
             if (jb->records) jb->records[o] = rec;
-            wk->tot += rec.steps; wk->nr += 1; wk->nc += (uint64_t)clamped;
+            wk->tot += steps; wk->nr += 1; wk->nc += (uint64_t)clamped;
             if (side > 0) wk->np += 1; else if (side < 0) wk->nn += 1; else wk->n0 += 1;
         }
     }

@@ -114,9 +114,9 @@ def camera(position, forward, up, focal_length, diagonal, width, height) -> _abi
     return cam
 
 
-def sim(max_iterations, max_radius, delta, sampling=0, integrator=0) -> _abi.CurvisSim:
+def sim(max_iterations, max_radius, delta, sampling=0, integrator=0, frame=0, coordinates=0, step_tolerance=0.0) -> _abi.CurvisSim:
     return _abi.CurvisSim(max_iterations=max_iterations, max_radius=max_radius, delta=delta, precision=0, sampling=sampling,
-                          integrator=integrator)
+                          integrator=integrator, frame=frame, coordinates=coordinates, step_tolerance=step_tolerance)
 
 
 def bilinear_tap(bg_rgba8, fx, fy):

@@ -30,16 +30,16 @@ def test_library_exports_every_declared_symbol(lib):
     assert set(names) == set(_abi.EXPORTED_SYMBOLS)
     for n in names:
         getattr(lib, n)
-    assert lib.curvis_abi_version() == _abi.ABI_VERSION == 3
+    assert lib.curvis_abi_version() == _abi.ABI_VERSION == 4
 
 
 def test_struct_layouts_match_header():
     from curvis_b200 import _abi
     assert C.sizeof(_abi.CurvisMetric) == 32
     assert C.sizeof(_abi.CurvisCamera) == 4 * 8 + 9 * 8 + 3 * 8 + 8
-    assert C.sizeof(_abi.CurvisSim) == 40
+    assert C.sizeof(_abi.CurvisSim) == 56
     assert C.sizeof(_abi.CurvisStats) == 9 * 8
-    assert C.sizeof(_abi.CurvisRayRecord) == 64 == np.dtype(_abi.RAY_RECORD_DTYPE).itemsize
+    assert C.sizeof(_abi.CurvisRayRecord) == 80 == np.dtype(_abi.RAY_RECORD_DTYPE).itemsize
 
 
 def test_library_embeds_sm100a_kernels(lib):

@@ -222,7 +222,10 @@ def test_oracle_reproduces_golden(oracle, name):
     rgb, rec, st = oracle.render_rows(g, cam, s, bp, bn, threads=os.cpu_count() or 1)
     gold = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
     assert (rgb == gold["rgb"]).all()
-    assert rec.tobytes() == gold["rec"].tobytes()       # bit-exact final states, NaNs included
+    # bit-exact final states, NaNs included.  The fixtures were written with the ABI-3 record (the first ten fields); they are
+    # kept as they are, so the refactored oracle (diagnostics, frames, coordinates) is pinned to the round-1 one.
+    for field in gold["rec"].dtype.names:
+        assert rec[field].tobytes() == gold["rec"][field].tobytes(), field
     assert st["total_steps"] == int(gold["total_steps"])
 
 

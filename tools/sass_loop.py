@@ -1,6 +1,6 @@
 """Static SASS view of a kernel's hot loop: finds the backward branch whose body is densest in
 fp64 instructions (>= 15 of them) and prints the opcode histogram of that body.
-    python tools/sass_loop.py curvis_b200/csrc/build/render_f64_fast.o FastEllisELi1 [--dump]
+    python tools/sass_loop.py curvis_b200/csrc/build/render_f64_fast.o FastEllisELi1 [--dump | --all]
 """
 import collections
 import re
@@ -29,6 +29,17 @@ for i, (a, op, text) in enumerate(ins):
             n64 = sum(1 for k in range(j, i + 1) if ins[k][1] in ("DFMA", "DMUL", "DADD", "DSETP"))
             if n64 >= 15 and (best is None or n64 / (i - j + 1) > best[0] / (best[2] - best[1] + 1)):
                 best = (n64, j, i)
+if "--all" in sys.argv:   # every fp64-dense loop (an inlined helper may appear several times)
+    for i, (a, op, text) in enumerate(ins):
+        if op == "BRA":
+            m = re.search(r"0x([0-9a-f]+)", text)
+            if m and int(m.group(1), 16) <= a and int(m.group(1), 16) in addr_index:
+                j = addr_index[int(m.group(1), 16)]
+                n64 = sum(1 for k in range(j, i + 1) if ins[k][1] in ("DFMA", "DMUL", "DADD", "DSETP"))
+                if n64 >= 15 and i - j + 1 < 200:
+                    hist = collections.Counter(ins[k][1] for k in range(j, i + 1))
+                    print(f"loop {ins[j][0]:#x}..{a:#x}: {i - j + 1} instructions, fp64-pipe {n64}: " + ", ".join(f"{o} {n}" for o, n in hist.most_common()))
+    sys.exit(0)
 n64, j, i = best
 hist = collections.Counter(ins[k][1] for k in range(j, i + 1))
 print(f"loop {ins[j][0]:#x}..{ins[i][0]:#x}: {i - j + 1} instructions, fp64-pipe {n64}")
