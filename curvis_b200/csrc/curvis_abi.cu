@@ -144,8 +144,11 @@ static cudaError_t launch_render(const FrameParams& p, const curvis_metric* metr
         r.ray_list_count = &p.counters->n_reintegrated;
         r.redo_list = nullptr;
         r.window = 32;
+        LaunchTuning rt = t;
+        rt.blocks_per_sm = t.redo_blocks_per_sm;
+        rt.kernel_variant = 4;
         g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
-        return launch_render_f64(r, metric->kind, t, sm_count, stream);
+        return launch_render_f64(r, metric->kind, rt, sm_count, stream);
     }
     return launch_render_f64(p, metric->kind, t, sm_count, stream);
 }
@@ -702,13 +705,14 @@ extern "C" int curvis_measure_fma_peak(curvis_ctx* ctx, double* fp64_tflops, dou
 extern "C" int curvis_ctx_set_option(curvis_ctx* ctx, const char* key, int64_t value) {
     if (!ctx || !key) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "null argument");
     const std::string k(key);
-    if (k == "kernel_variant" && value >= 0 && value <= 3) ctx->tuning.kernel_variant = (int)value;
+    if (k == "kernel_variant" && value >= 0 && value <= 4) ctx->tuning.kernel_variant = (int)value;
     else if (k == "blocks_per_sm" && value >= 0 && value <= 32) ctx->tuning.blocks_per_sm = (int)value;
     else if (k == "window" && value >= 0 && value <= 4096) ctx->tuning.window = (int)value;
     else if (k == "fast_variant" && value >= 0 && value <= 1) ctx->tuning.fast_variant = (int)value;
     else if (k == "zero_copy" && value >= 0 && value <= 1) ctx->tuning.zero_copy = (int)value;
     else if (k == "guard" && value >= 0 && value <= 1) ctx->tuning.guard = (int)value;
     else if (k == "fast_regs" && (value == 96 || value == 128)) ctx->tuning.fast_regs = (int)value;
+    else if (k == "redo_blocks_per_sm" && value >= 0 && value <= 32) ctx->tuning.redo_blocks_per_sm = (int)value;
     else if (k == "guard_rel_e15" && value >= 1 && value <= 1000000000000ll) ctx->tuning.guard_rel = (double)value * 1e-15;
     else return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "unknown option or value out of range: " + k);
     return CURVIS_OK;
@@ -734,6 +738,28 @@ extern "C" int curvis_debug_eval(curvis_ctx* ctx, int op, const double* a, const
     if (e != cudaSuccess) rc = cuda_fail(ctx, e, "curvis_debug_eval");
     cudaFree(da); cudaFree(db); cudaFree(dout);
     return rc;
+}
+
+extern "C" int curvis_debug_rhs_check(curvis_ctx* ctx, const curvis_metric* metric, uint64_t n_samples, uint64_t seed, uint64_t mismatches[4]) {
+    if (!ctx || !metric || !mismatches) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "null argument");
+    int rc = curvis_metric_validate(metric);
+    if (rc != CURVIS_OK) return fail(ctx, rc, thread_error());
+    DeviceState& d = ctx->devs[0];
+    CURVIS_CUDA(ctx, cudaSetDevice(d.ordinal));
+    FrameParams p;
+    std::memset(&p, 0, sizeof p);
+    p.rho = metric->rho; p.m = metric->m; p.a = metric->a;
+    unsigned long long* d_bad = nullptr;
+    CURVIS_CUDA(ctx, cudaMalloc(&d_bad, 4 * sizeof(unsigned long long)));
+    cudaError_t e = cudaMemsetAsync(d_bad, 0, 4 * sizeof(unsigned long long), d.stream);
+    if (e == cudaSuccess) e = launch_debug_rhs_check(p, metric->kind, seed, n_samples, d_bad, d.stream);
+    unsigned long long h[4] = {0, 0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_bad, sizeof h, cudaMemcpyDeviceToHost, d.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+    cudaFree(d_bad);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "curvis_debug_rhs_check");
+    for (int k = 0; k < 4; ++k) mismatches[k] = h[k];
+    return CURVIS_OK;
 }
 
 extern "C" int curvis_render_image_efficient(curvis_ctx* ctx, const curvis_metric* metric, const curvis_camera* camera,

@@ -51,6 +51,13 @@ struct ShapeEllis {  // metrics.rs:417-421
         r = sqrt_rn_unguarded(r2);
         rp = div_rn_unguarded(l, r);
     }
+    // The same values with the by-products the shared-reciprocal step needs: yr ~ 1/r (<= 2 ulp), from the square root's
+    // own Newton iteration; r' = l / r through one correction step on yr.
+    static __device__ __forceinline__ void eval_shared(const FrameParams& p, double l, double& r, double& r2, double& rp, double& yr) {
+        r2 = p.rho * p.rho + l * l;
+        r = sqrt_rn_with_rsqrt(r2, yr);
+        rp = div_corrected(l, r, yr);
+    }
     static __device__ __forceinline__ bool params_safe(const FrameParams& p) { return exponent_in(p.rho, -100, 100); }
 };
 
@@ -75,6 +82,10 @@ struct ShapeInterstellar {  // metrics.rs:461-485
     static __device__ __forceinline__ void eval_fast(const FrameParams& p, double l, double& r, double& r2, double& rp) {
         eval(p, l, r, r2, rp);
     }
+    static __device__ __forceinline__ void eval_shared(const FrameParams& p, double l, double& r, double& r2, double& rp, double& yr) {
+        eval(p, l, r, r2, rp);
+        yr = rcp_approx(r);       // r >= rho > 0
+    }
     static __device__ __forceinline__ bool params_safe(const FrameParams& p) {
         return exponent_in(p.rho, -100, 100) && exponent_in(p.m, -100, 100) && exponent_in(p.a, -100, 100);
     }
@@ -87,6 +98,10 @@ struct ShapeFlat {  // metrics.rs:501-505
     }
     static __device__ __forceinline__ void eval_fast(const FrameParams& p, double l, double& r, double& r2, double& rp) {
         eval(p, l, r, r2, rp);
+    }
+    static __device__ __forceinline__ void eval_shared(const FrameParams& p, double l, double& r, double& r2, double& rp, double& yr) {
+        eval(p, l, r, r2, rp);
+        yr = rcp_approx(l);       // either sign; |l| is inside the safe window
     }
     static __device__ __forceinline__ bool params_safe(const FrameParams&) { return true; }
 };
@@ -240,7 +255,7 @@ __device__ __forceinline__ void euler_step_tuned(const FrameParams& p, Ray& q, b
 // instruction holds the scheduler's dispatch port for two cycles, so every fp64 op removed is
 // worth two integer ops (profiles/r01_f64_v2_ncu_summary.txt).  Arithmetic is unchanged.
 // Right-hand side of the geodesic equations at a state (metrics.rs:223-270), lean form.
-template <class Shape>
+template <class Shape, bool SHARED = true>
 __device__ __forceinline__ void rhs_lean(const FrameParams& p, bool ray_safe, double l, double th, double pth, double pph, double pph2,
                                          double& dth, double& dph, double& dpl, double& dpth, double& s) {
     const bool pre = ray_safe && (abs_hi(th) < pow2_hi(30)) && ((abs_hi(l) - pow2_hi(-100)) < (pow2_hi(100) - pow2_hi(-100))) &&
@@ -249,16 +264,35 @@ __device__ __forceinline__ void rhs_lean(const FrameParams& p, bool ray_safe, do
     if (pre) sincos_fast(th, s, c);
     else TrigFast::sincos(th, s, c);
     if (pre && abs_hi(s) >= pow2_hi(-60)) {
-        double r, r2, rp;
-        Shape::eval_fast(p, l, r, r2, rp);
-        const double s2 = s * s;
-        const double g22c = rcp_rn_unguarded(r2);
-        const double g33c = rcp_rn_unguarded(r2 * s2);
-        dth = pth * g22c;
-        dph = pph * g33c;
-        const double b2 = pth * pth + div_rn_unguarded(pph2, s2);
-        dpl = div_rn_unguarded(b2 * rp, (r * r) * r);
-        dpth = pph2 * div_rn_unguarded(c, r2 * (s2 * s));
+        if (SHARED) {
+            // kernel_variant 4 (default): the same seven roundings, the six divisors' reciprocals built from TWO seeds —
+            // yr ~ 1/r (a by-product of the square root) and ys ~ 1/sin^2 theta — and one correction step each
+            // (ieee_f64.cuh: div_corrected / rcp_corrected): 77 fp64-pipe instructions per step instead of 100.
+            double r, r2, rp, yr;
+            Shape::eval_shared(p, l, r, r2, rp, yr);
+            const double s2 = s * s;
+            const double yr2 = yr * yr;                                        // ~ 1/r^2
+            const double ys = rcp_approx(s2);                                  // ~ 1/sin^2
+            const double yrs = yr2 * ys;                                       // ~ 1/(r^2 sin^2)
+            const double g22c = rcp_corrected(r2, yr2);                        // :90
+            const double g33c = rcp_corrected(r2 * s2, yrs);                   // :93
+            dth = pth * g22c;
+            dph = pph * g33c;
+            const double b2 = pth * pth + div_corrected(pph2, s2, ys);         // :257
+            dpl = div_corrected(b2 * rp, (r * r) * r, yr2 * yr);               // :261
+            dpth = pph2 * div_corrected(c, r2 * (s2 * s), yrs * (ys * s));     // :262
+        } else {
+            double r, r2, rp;
+            Shape::eval_fast(p, l, r, r2, rp);
+            const double s2 = s * s;
+            const double g22c = rcp_rn_unguarded(r2);
+            const double g33c = rcp_rn_unguarded(r2 * s2);
+            dth = pth * g22c;
+            dph = pph * g33c;
+            const double b2 = pth * pth + div_rn_unguarded(pph2, s2);
+            dpl = div_rn_unguarded(b2 * rp, (r * r) * r);
+            dpth = pph2 * div_rn_unguarded(c, r2 * (s2 * s));
+        }
     } else {
         double r, r2, rp;
         Shape::eval(p, l, r, r2, rp);
@@ -277,10 +311,10 @@ __device__ __forceinline__ void rhs_lean(const FrameParams& p, bool ray_safe, do
 // the right-hand side was evaluated at, and the stiffness max (delta dphi/dlambda)^2 = max delta^2 p_phi^2 / (r^2 sin^2)^2.
 struct RayDiag { double min_abs_sin, stiffness; };
 
-template <class Shape, bool TRACK = false>
+template <class Shape, bool TRACK = false, bool SHARED = true>
 __device__ __forceinline__ void euler_step_lean(const FrameParams& p, Ray& q, bool ray_safe, RayDiag* diag = nullptr) {
     double dth, dph, dpl, dpth, s;
-    rhs_lean<Shape>(p, ray_safe, q.l, q.th, q.pth, q.pph, q.pph2, dth, dph, dpl, dpth, s);
+    rhs_lean<Shape, SHARED>(p, ray_safe, q.l, q.th, q.pth, q.pph, q.pph2, dth, dph, dpl, dpth, s);
     if (TRACK) {
         const double step_phi = dph * p.delta;
         diag->min_abs_sin = fmin(diag->min_abs_sin, fabs(s));

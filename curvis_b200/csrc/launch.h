@@ -8,16 +8,19 @@ namespace curvis {
 
 // Tuning knobs of a context (curvis_ctx_set_option).
 struct LaunchTuning {
-    int kernel_variant = 3;  // 0 plain operators + CUDA sincos (round-1 v0); 1 unguarded IEEE sequences + CUDA sincos;
-                             // 2 + in-kernel sincos; 3 (default) lean loop: integer-pipe guards, gated escape test
+    int kernel_variant = 4;  // 0 plain operators + CUDA sincos (round-1 v0); 1 unguarded IEEE sequences + CUDA sincos;
+                             // 2 + in-kernel sincos; 3 lean loop: integer-pipe guards, gated escape test;
+                             // 4 (default) the lean loop with the step's six reciprocals built from two seeds
     int blocks_per_sm = 0;   // 0 = occupancy maximum
     int window = 0;          // Euler steps between two refill points of a warp; 0 = auto (32; 32..128 in F64_FAST)
     int zero_copy = 1;       // curvis_render_image into a registered host frame: 1 (default) = the kernel stores its pixels
                              // straight into it (measured: kernel time unchanged, 0.04 ms exposed); 0 = device frame + one DMA (0.5 ms)
     int guard = 1;           // CURVIS_PRECISION_F64_FAST: 1 (default) = guard band + re-integration (frames equal CURVIS_PRECISION_F64's);
                              // 0 = the raw regrouped kernel (A/B, tools/guard_study.py)
-    double guard_rel = 1e-9; // relative state-error budget of an unamplified ray: ~1e4 x the measured deviation
-    int fast_regs = 128;     // CURVIS_PRECISION_F64_FAST register budget: 128 (4 CTAs per SM, 47-instruction step) or 96 (5 CTAs, 50)
+    double guard_rel = 1e-9; // relative state-error budget of a ray with stiffness < 1 (render_f64_fast.cu: guard_eps)
+    int redo_blocks_per_sm = 2;   // CTAs per SM of the re-integration launch (a few per cent of the frame's rays: fewer, fuller warps)
+    int fast_regs = 96;      // CURVIS_PRECISION_F64_FAST register budget: 96 (5 CTAs per SM, 50-instruction step; measured 36.2 ms per 4K
+                             // Ellis frame) or 128 (4 CTAs, 47 instructions; 37.4 ms)
     int fast_variant = 1;    // CURVIS_PRECISION_F64_FAST: 0 sin/cos from theta every step; 1 (default) (sin, cos) carried and
                              // rotated by the step's small dtheta, re-derived from theta once per window
 };
@@ -43,6 +46,10 @@ cudaError_t launch_debug_bilinear(const Background& bg, const double* fx, const 
 cudaError_t launch_debug_eval(int op, const double* a, const double* b, double* out, size_t n, cudaStream_t stream);
 
 
+
+// Right-hand side of kernel_variant 4 against the plain operators on n pseudo-random states (test hook, curvis_debug_rhs_check).
+cudaError_t launch_debug_rhs_check(const FrameParams& p, int metric_kind, unsigned long long seed, unsigned long long n,
+                                   unsigned long long* d_mismatches, cudaStream_t stream);
 
 // F(x) (which = 0) / G(x) (which = 1) of the Interstellar shape-function table as the fast kernel
 // evaluates them (test hook, curvis_debug_eval ops 13 / 14).  render_f64_fast.cu.

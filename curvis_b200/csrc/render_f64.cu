@@ -97,9 +97,11 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64(const __grid_constant_
 // (the fp64 compares only run within 2^-20 of the radius, or for NaN).
 //   INTEG  0 Euler (the reference), 1 RK4, 2 Euler with the pole-adaptive step (extensions)
 //   TRACK  the trajectory diagnostics of curvis_ray_record (launches that write records)
+//   SHARED the step's six reciprocals from two seeds + one correction each (kernel_variant 4, default) or one full
+//          correctly-rounded sequence per quotient (kernel_variant 3); same roundings, geodesic_f64.cuh: rhs_lean
 // List mode (p.ray_list != nullptr): the launch re-integrates the rays CURVIS_PRECISION_F64_FAST left in its guard
 // band — ray i of the launch is ray ray_list[i] of the tile, *ray_list_count of them.
-template <class Shape, int INTEG, bool TRACK>
+template <class Shape, int INTEG, bool TRACK, bool SHARED>
 __global__ void __launch_bounds__(kBlock) render_rows_f64_lean(const __grid_constant__ FrameParams p) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64_lean(const __grid_cons
             if (state == 1) {
                 if (INTEG == 1) rk4_step_lean<Shape>(p, q, ray_safe);
                 else if (INTEG == 2) euler_step_adaptive<Shape, TRACK>(p, q, ray_safe, &diag);
-                else euler_step_lean<Shape, TRACK>(p, q, ray_safe, &diag);
+                else euler_step_lean<Shape, TRACK, SHARED>(p, q, ray_safe, &diag);
                 --remaining;
                 bool done = (remaining == 0);                                   // systems.rs:137
                 if (abs_hi(q.l) >= gate) {
@@ -195,22 +197,23 @@ static cudaError_t launch_persistent(Kernel kernel, int& blocks_per_sm_auto, con
     return cudaGetLastError();
 }
 
-template <class Shape, int INTEG, bool TRACK>
+template <class Shape, int INTEG, bool TRACK, bool SHARED>
 static cudaError_t launch_lean_one(const FrameParams& p, int sm_count, int blocks_per_sm_override, cudaStream_t stream) {
     static int blocks_per_sm_auto = 0;   // per instantiation
-    return launch_persistent(render_rows_f64_lean<Shape, INTEG, TRACK>, blocks_per_sm_auto, p, sm_count, blocks_per_sm_override, stream);
+    return launch_persistent(render_rows_f64_lean<Shape, INTEG, TRACK, SHARED>, blocks_per_sm_auto, p, sm_count, blocks_per_sm_override, stream);
 }
 
 template <class Shape>
-static cudaError_t launch_lean(const FrameParams& p, int sm_count, int blocks_per_sm_override, cudaStream_t stream) {
+static cudaError_t launch_lean(const FrameParams& p, int sm_count, int blocks_per_sm_override, bool shared, cudaStream_t stream) {
     const bool track = p.records != nullptr;
     if (p.integrator == CURVIS_INTEGRATOR_RK4)
-        return launch_lean_one<Shape, 1, false>(p, sm_count, blocks_per_sm_override, stream);
+        return launch_lean_one<Shape, 1, false, true>(p, sm_count, blocks_per_sm_override, stream);
     if (p.integrator == CURVIS_INTEGRATOR_EULER_ADAPTIVE)
-        return track ? launch_lean_one<Shape, 2, true>(p, sm_count, blocks_per_sm_override, stream)
-                     : launch_lean_one<Shape, 2, false>(p, sm_count, blocks_per_sm_override, stream);
-    return track ? launch_lean_one<Shape, 0, true>(p, sm_count, blocks_per_sm_override, stream)
-                 : launch_lean_one<Shape, 0, false>(p, sm_count, blocks_per_sm_override, stream);
+        return track ? launch_lean_one<Shape, 2, true, true>(p, sm_count, blocks_per_sm_override, stream)
+                     : launch_lean_one<Shape, 2, false, true>(p, sm_count, blocks_per_sm_override, stream);
+    if (track) return launch_lean_one<Shape, 0, true, true>(p, sm_count, blocks_per_sm_override, stream);
+    return shared ? launch_lean_one<Shape, 0, false, true>(p, sm_count, blocks_per_sm_override, stream)
+                  : launch_lean_one<Shape, 0, false, false>(p, sm_count, blocks_per_sm_override, stream);
 }
 
 template <class Shape, class Trig, bool TUNED>
@@ -222,12 +225,13 @@ static cudaError_t launch_one(const FrameParams& p, int sm_count, int blocks_per
 template <class Shape>
 static cudaError_t launch_variant(const FrameParams& p, const LaunchTuning& t, int sm_count, cudaStream_t stream) {
     if (p.integrator != CURVIS_INTEGRATOR_EULER || p.records || p.ray_list)
-        return launch_lean<Shape>(p, sm_count, t.blocks_per_sm, stream);   // extensions, diagnostics, list mode: lean kernel only
+        return launch_lean<Shape>(p, sm_count, t.blocks_per_sm, true, stream);   // extensions, diagnostics, list mode: lean kernel only
     switch (t.kernel_variant) {
     case 0: return launch_one<Shape, TrigCuda, false>(p, sm_count, t.blocks_per_sm, stream);   // round-1 v0
     case 1: return launch_one<Shape, TrigCuda, true>(p, sm_count, t.blocks_per_sm, stream);
     case 2: return launch_one<Shape, TrigFast, true>(p, sm_count, t.blocks_per_sm, stream);
-    default: return launch_lean<Shape>(p, sm_count, t.blocks_per_sm, stream);                  // default (3)
+    case 3: return launch_lean<Shape>(p, sm_count, t.blocks_per_sm, false, stream);           // one full division sequence per quotient
+    default: return launch_lean<Shape>(p, sm_count, t.blocks_per_sm, true, stream);            // default (4): shared reciprocals
     }
 }
 
@@ -262,6 +266,50 @@ __global__ void debug_eval_kernel(int op, const double* a, const double* b, doub
     default: break;
     }
     out[i] = r;
+}
+
+// Test hook (curvis_debug_rhs_check): the right-hand side of kernel_variant 4 (shared reciprocals, one correction step per
+// quotient) against the plain operators on pseudo-random photon states; counts the outputs that differ in any bit.
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long& x) {
+    unsigned long long z = (x += 0x9e3779b97f4a7c15ull);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ double unit_double(unsigned long long& x) { return (double)(splitmix64(x) >> 11) * (1.0 / 9007199254740992.0); }
+
+template <class Shape>
+__global__ void debug_rhs_check_kernel(const FrameParams p, unsigned long long seed, unsigned long long n, unsigned long long* mismatches) {
+    unsigned long long bad[4] = {0, 0, 0, 0};
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned long long x = seed + i * 0x632be59bd9b4e019ull;
+        const int mode = (int)(i & 3);
+        double l = (unit_double(x) * 2.0 - 1.0) * (mode == 0 ? 100.0 : mode == 1 ? 5.0 : mode == 2 ? 0.3 : 30.0);
+        double th = unit_double(x) * CURVIS_PI;
+        if (mode == 2) th = unit_double(x) * 0.05 + 1e-4;
+        if (mode == 3) th = CURVIS_PI - unit_double(x) * 0.01;
+        if (Shape::kind == CURVIS_METRIC_FLAT) l = fabs(l) + 1e-3;
+        const double pth = (unit_double(x) * 2.0 - 1.0) * 6.0;
+        const double pph = (unit_double(x) * 2.0 - 1.0) * 6.0 * sin(th);
+        const double pph2 = pph * pph;
+        double a[4], b[4], s;
+        rhs_lean<Shape, true>(p, true, l, th, pth, pph, pph2, a[0], a[1], a[2], a[3], s);
+        rhs_lean<Shape, true>(p, false, l, th, pth, pph, pph2, b[0], b[1], b[2], b[3], s);   // ray_safe = false: plain operators
+        for (int k = 0; k < 4; ++k) bad[k] += (__double_as_longlong(a[k]) != __double_as_longlong(b[k])) ? 1ull : 0ull;
+    }
+    for (int k = 0; k < 4; ++k)
+        if (bad[k]) atomicAdd(&mismatches[k], bad[k]);
+}
+
+cudaError_t launch_debug_rhs_check(const FrameParams& p, int metric_kind, unsigned long long seed, unsigned long long n,
+                                   unsigned long long* d_mismatches, cudaStream_t stream) {
+    switch (metric_kind) {
+    case CURVIS_METRIC_ELLIS: debug_rhs_check_kernel<ShapeEllis><<<148 * 8, 256, 0, stream>>>(p, seed, n, d_mismatches); break;
+    case CURVIS_METRIC_INTERSTELLAR: debug_rhs_check_kernel<ShapeInterstellar><<<148 * 8, 256, 0, stream>>>(p, seed, n, d_mismatches); break;
+    case CURVIS_METRIC_FLAT: debug_rhs_check_kernel<ShapeFlat><<<148 * 8, 256, 0, stream>>>(p, seed, n, d_mismatches); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
 }
 
 __global__ void texels_to_float4_kernel(const uint32_t* texels, float4* out, size_t n) {

@@ -74,6 +74,13 @@ class Context:
         _abi.check(self._lib.curvis_debug_eval(self._ptr, op, a.ctypes.data_as(dp), bp, out.ctypes.data_as(dp), a.size), self._ptr)
         return out
 
+    def debug_rhs_check(self, metric, n_samples: int, seed: int = 1):
+        """curvis_debug_rhs_check: mismatching bits of kernel_variant 4's right-hand side vs the plain operators."""
+        bad = (C.c_uint64 * 4)()
+        m = metric.as_c()
+        _abi.check(self._lib.curvis_debug_rhs_check(self._ptr, C.byref(m), int(n_samples), int(seed), bad), self._ptr)
+        return list(bad)
+
     def measure_fma_peak(self):
         f64, f32 = C.c_double(), C.c_double()
         _abi.check(self._lib.curvis_measure_fma_peak(self._ptr, C.byref(f64), C.byref(f32)), self._ptr)

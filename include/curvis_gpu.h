@@ -356,8 +356,13 @@ int curvis_measure_fma_peak(curvis_ctx* ctx, double* fp64_tflops, double* fp32_t
 
 /* Tuning knobs of a context; results never depend on them (tests/test_gpu_parity.py).
  *   "kernel_variant": 0 plain `/`, sqrt and CUDA sincos; 1 unguarded IEEE sequences + CUDA
- *                     sincos; 2 unguarded IEEE sequences + in-kernel sincos; 3 (default) the same
- *                     arithmetic in the lean loop (integer-pipe guards, gated escape test)
+ *                     sincos; 2 unguarded IEEE sequences + in-kernel sincos; 3 the same
+ *                     arithmetic in the lean loop (integer-pipe guards, gated escape test); 4 (default) the lean loop
+ *                     with the step's six reciprocals built from two seeds and one correction step each
+ *   "guard":          CURVIS_PRECISION_F64_FAST: 1 (default) guard band + re-integration; 0 the raw regrouped kernel (A/B)
+ *   "guard_rel_e15":  the guard's relative budget in units of 1e-15 (default 1000000 = 1e-9)
+ *   "fast_regs":      96 (default) / 128: register budget of the fast kernel (5 / 4 resident CTAs per SM)
+ *   "redo_blocks_per_sm": resident CTAs per SM of the re-integration launch (default 2)
  *   "blocks_per_sm":  resident CTAs per SM of the persistent grid (0 = occupancy maximum)
  *   "window":         Euler steps between two refill points of a warp (0 = default: 32; for
  *                     CURVIS_PRECISION_F64_FAST 32..128, growing with the expected ray length)
@@ -378,6 +383,12 @@ int curvis_ctx_set_option(curvis_ctx* ctx, const char* key, int64_t value);
  *   13 / 14 its Interstellar shape functions a atan a - ln(1 + a^2)/2 and (2/pi) atan a (table; 0 for a <= 0)
  *   15 / 16 the same two functions as CURVIS_PRECISION_F32 evaluates them (fp32 table; a is rounded to float)   */
 int curvis_debug_eval(curvis_ctx* ctx, int op, const double* a, const double* b, double* out, size_t n);
+
+/* Test hook of kernel_variant 4 (the default CURVIS_PRECISION_F64 step: the six reciprocals of metrics.rs:257-262 from two
+ * MUFU seeds and one correction step each): evaluates the right-hand side of n_samples pseudo-random photon states both
+ * ways — shared reciprocals vs. the plain IEEE operators — and returns in mismatches[0..3] how many of the outputs
+ * dtheta, dphi, dp_l, dp_theta differ in any bit. */
+int curvis_debug_rhs_check(curvis_ctx* ctx, const curvis_metric* metric, uint64_t n_samples, uint64_t seed, uint64_t mismatches[4]);
 
 /* Test hook, host only (no GPU needed): the piecewise-polynomial table of the Interstellar shape
  * functions that CURVIS_PRECISION_F64_FAST uploads to every device (csrc/shape_table.h), evaluated on

@@ -87,7 +87,7 @@ def study(name, metric, cam_args, sim, W, H, ctx, bp, bn, rows=None):
             "max_rel_dev": float(np.nanmax(np.abs(recraw["stiffness"][same_steps] / np.maximum(kappa[same_steps], 1e-300) - 1.0))) if same_steps.any() else None},
     })
     bins = []
-    edges = [0.0] + [10.0 ** e for e in range(-8, 3)] + [np.inf]
+    edges = [0.0] + [10.0 ** e for e in range(-8, 17)] + [np.inf]
     for lo, hi in zip(edges[:-1], edges[1:]):
         m = (kappa >= lo) & (kappa < hi)
         if not m.any():
@@ -98,7 +98,10 @@ def study(name, metric, cam_args, sim, W, H, ctx, bp, bn, rows=None):
         if me.any():
             row.update({"dir_dev_max": float(dev_dir[me].max()), "dir_dev_p99": float(np.quantile(dev_dir[me], 0.99)),
                         "eps_dir_max": float(eps_dir[me].max()), "eps_dir_p999": float(np.quantile(eps_dir[me], 0.999)),
-                        "eps_state_max": float(eps_state[me].max()), "eps_state_p999": float(np.quantile(eps_state[me], 0.999))})
+                        "eps_state_max": float(eps_state[me].max()), "eps_state_p999": float(np.quantile(eps_state[me], 0.999)),
+                        "dev_l_max": float(np.abs(rec64["l"] - recraw["l"])[me].max()), "p_l_abs_max": float(np.abs(rec64["p_l"][me]).max()),
+                        "dev_l_per_step_length_max": float((np.abs(rec64["l"] - recraw["l"]) / (np.abs(rec64["p_l"]) * abs(sim[2]) + 1e-300))[me].max()),
+                        "dev_pl_rel_max": float((np.abs(rec64["p_l"] - recraw["p_l"]) / (np.abs(rec64["p_l"]) + 1e-300))[me].max())})
         bins.append(row)
     out["by_stiffness"] = bins
     # the rays the raw kernel got wrong: where do they sit?
@@ -131,22 +134,25 @@ def timing(ctx, bp, bn):
         system = cv.RelativisticSystem(metric, cv.SphericalImage(bp), cv.SphericalImage(bn), cam, context=ctx)
         sim = (40000, 100.0, 0.05)
         res = {}
-        for regs in (128, 96):
+        for regs, guard, redo in ((128, 0, 2), (96, 0, 2), (96, 1, 1), (96, 1, 2), (96, 1, 3), (96, 1, 5)):
             ctx.set_option("fast_regs", regs)
-            for guard in (0, 1):
-                ctx.set_option("guard", guard)
-                ms = []
-                for _ in range(4):
-                    st = system.render_rows_device(*sim, 0, H, frame.data_ptr(), stream.cuda_stream, want_stats=True, precision=_abi.PRECISION_F64_FAST)
-                    ms.append(st["kernel_ms"])
-                res[f"regs{regs}_guard{guard}"] = {"kernel_ms": min(ms[1:]), "n_reintegrated": int(st["n_reintegrated"])}
-        ms = []
-        for _ in range(3):
-            st = system.render_rows_device(*sim, 0, H, frame.data_ptr(), stream.cuda_stream, want_stats=True, precision=_abi.PRECISION_F64)
-            ms.append(st["kernel_ms"])
-        res["f64_strict"] = {"kernel_ms": min(ms[1:])}
-        ctx.set_option("fast_regs", 128)
+            ctx.set_option("guard", guard)
+            ctx.set_option("redo_blocks_per_sm", redo)
+            ms = []
+            for _ in range(4):
+                st = system.render_rows_device(*sim, 0, H, frame.data_ptr(), stream.cuda_stream, want_stats=True, precision=_abi.PRECISION_F64_FAST)
+                ms.append(st["kernel_ms"])
+            res[f"regs{regs}_guard{guard}_redo{redo}"] = {"kernel_ms": min(ms[1:]), "n_reintegrated": int(st["n_reintegrated"])}
+        for variant in (3, 4):
+            ctx.set_option("kernel_variant", variant)
+            ms = []
+            for _ in range(3):
+                st = system.render_rows_device(*sim, 0, H, frame.data_ptr(), stream.cuda_stream, want_stats=True, precision=_abi.PRECISION_F64)
+                ms.append(st["kernel_ms"])
+            res[f"f64_strict_variant{variant}"] = {"kernel_ms": min(ms[1:])}
+        ctx.set_option("fast_regs", 96)
         ctx.set_option("guard", 1)
+        ctx.set_option("redo_blocks_per_sm", 2)
         out[mname] = res
     return out
 
