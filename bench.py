@@ -69,8 +69,9 @@ def workload_config(args, n):
         "frames_per_step": n,
         "precision": {"f64_fast": "CURVIS_PRECISION_F64_FAST: fp64, same Euler scheme, right-hand side regrouped around one "
                                   "reciprocal per step, momenta pre-scaled by the step, (sin, cos) of theta carried and rotated by the "
-                                  "step's dtheta (each operation <= 1 ulp; frame checked against the operation-for-operation kernel in "
-                                  "`parity_check`)",
+                                  "step's dtheta (each operation <= 1 ulp); rays whose step count or texel lies inside the guard band of a "
+                                  "decision boundary are re-integrated with the CURVIS_PRECISION_F64 arithmetic inside the timed region, so "
+                                  "the frame's integers equal CURVIS_PRECISION_F64's (`parity_check` compares with the CPU oracle)",
                       "f64": "CURVIS_PRECISION_F64: fp64, one rounding per reference operation"}[args.precision],
         "parallelism": "single GPU" if n == 1 else (
             f"{n} frames/step (camera path), rows of each frame interleaved over {n} ranks (rank g: rows g, g+{n}, ...): one batched launch per rank whose epilogue stores every pixel into "
@@ -184,7 +185,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC_NAME, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_total / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": dict(workload_config(args, 1), sample_per_step=sample),
+        "config": workload_config(args, 1),
+        "sample_per_step": sample,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
                          "host_cores": ncpu,
                          "note": "reference is single-threaded; all-core figure of the same port in cpu_all_cores"},
@@ -193,6 +195,33 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def oracle_parity(args, system, sim, strict_frame, fast_frame, fast_precision, n_rows=72):
+    """Both kernels against the CPU oracle on `n_rows` rows spread over the frame (all host cores, records with the
+    trajectory diagnostics), split into regular / chaotic rays by the survey's classifier (oracle/classify.py)."""
+    import numpy as np
+    from curvis_b200 import _abi, scenes
+    from oracle import classify, oracle as O
+
+    bp = scenes.decodable_background(BG_W, BG_H)
+    bn = scenes.decodable_background(BG_W, BG_H, negative=True)
+    cam = O.camera(scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP,
+                   scenes.DEFAULT_FOCAL_LENGTH, scenes.DEFAULT_DIAGONAL, args.width, args.height)
+    stride = max(1, args.height // n_rows)
+    first = stride // 2
+    rows = list(range(first, args.height, stride))
+    t0 = time.perf_counter()
+    ref_rgb, ref_rec, _ = O.render_rows(O.metric("ellis", rho=1.0), cam, O.sim(*sim), bp, bn, row_begin=first, row_end=args.height,
+                                        row_stride=stride, threads=os.cpu_count() or 1, with_records=True)
+    out = {"rows": f"{first}::{stride} ({len(rows)} rows, {len(rows) * args.width} rays)", "oracle_seconds": round(time.perf_counter() - t0, 2),
+           "classifier": "chaotic <=> |p_l|_final > 1.05 or min |sin theta| < 1e-3 on the ORACLE's record (SURVEY.md 8c)"}
+    for name, frame, prec in (("f64", strict_frame, _abi.PRECISION_F64), ("f64_fast", fast_frame, fast_precision)):
+        recs = np.concatenate([system.render_rows(*sim, r, r + 1, with_records=True, precision=prec)[1] for r in rows], axis=0)
+        out[name] = classify.compare(frame[first::stride], recs, ref_rgb, ref_rec)
+    out["chaotic_fraction"] = out["f64"]["chaotic_fraction"]
+    out["differing_regular"] = max(out["f64_fast"]["differing_pixels_regular"], out["f64_fast"]["differing_records_regular"])
+    return out
 
 
 # ----------------------------------------------------------------------------------- B200 arm
@@ -501,6 +530,7 @@ def run_b200(args):
     tile_rays = rows * Wd * n
     hbm_achieved = tile_rays * alg_bytes_per_ray / (kernel_ms * 1e-3) / 1e9
     traffic, fp64_pipe = None, None
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "latest_traffic.json")))[KERNEL]
         traffic = prof.get("dram_bytes_per_launch")
@@ -508,7 +538,6 @@ def run_b200(args):
         if ipw:
             # instruction-level view: fp64-pipe warp-instructions issued per second vs one per two
             # cycles per scheduler (4 per SM) at the SM clock sampled during the timed region
-            sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
             mhz = clocks.summary().get("sm_mhz") or 1965
             issued = kernel_rate / 32.0 * ipw
             peak_issue = sm_count * 4 * mhz * 1e6 / 2.0
@@ -516,11 +545,15 @@ def run_b200(args):
                          "fp64_warp_instr_per_warp_step": ipw, "source": prof.get("source")}
     except Exception:
         pass
+    mhz_max = clocks.summary().get("sm_max_mhz") or 1965
+    peak_nominal = sm_count * 64 * 2 * mhz_max * 1e6 / 1e12       # 64 fp64 FMA lanes per SM x 2 flop x f_clk
     roofline = {
         "bound": "fp64_alu",
         "bound_note": "per-ray ODE: ~1e4 flop/B and no dense contraction, so neither hbm nor tensor bounds it (DESIGN.md section 5); "
                       "the hbm figure is reported below for completeness",
         "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
+        "peak_measured": fp64_peak, "peak_nominal": peak_nominal, "frac_of_nominal": achieved_tf / peak_nominal,
+        "peak_nominal_note": f"{sm_count} SMs x 64 fp64 FMA lanes x 2 flop x {mhz_max} MHz",
         "traffic": traffic, "fp64_pipe": fp64_pipe,
         "peak_source": "live DFMA micro-kernel on this GPU (curvis_measure_fma_peak); MEASURED_PEAKS.json has no fp64 entry",
         "flop_per_ray_step": flop, "kernel": KERNEL, "kernel_ms": kernel_ms,
@@ -531,10 +564,9 @@ def run_b200(args):
         "fp32_fma_peak_tflops": fp32_peak,
     }
 
-    # ---- the operation-for-operation kernel (CURVIS_PRECISION_F64) next to the headline, and the headline
-    # frame checked against it pixel for pixel (it equals the CPU oracle on all 8,294,400 pixels of this
-    # frame, profiles/r01_parity_full_4k_ellis.json)
-    strict_mode, parity_check = None, None
+    # ---- the operation-for-operation kernel (CURVIS_PRECISION_F64) next to the headline, the headline frame against it
+    # pixel for pixel, and BOTH against the CPU oracle on strided rows, split into regular / chaotic rays
+    strict_mode, parity_check, raw_fast = None, None, None
     if n == 1:
         sms = []
         for _ in range(3):
@@ -543,15 +575,31 @@ def run_b200(args):
             sms.append(s4["kernel_ms"])
         strict_frame = frames[0].clone()
         s5 = system.render_rows_device(*sim, row_begin, row_end, frames[0].data_ptr(), stream.cuda_stream, want_stats=True, precision=PREC)
-        differing = int((strict_frame.view(-1, 3) != frames[0].view(-1, 3)).any(dim=1).sum().item())
+        fast_frame = frames[0].clone()
+        differing = int((strict_frame.view(-1, 3) != fast_frame.view(-1, 3)).any(dim=1).sum().item())
         strict_mode = {"precision": "CURVIS_PRECISION_F64: one rounding per reference operation (six correctly rounded divisions, "
                                     "one square root, sincos per step)",
                        "kernel": "render_rows_f64_lean<ShapeEllis>", "value": s4["total_steps"] / (min(sms) * 1e-3), "unit": UNIT,
                        "kernel_ms": min(sms), "frac_of_fp64_fma_peak": s4["total_steps"] / (min(sms) * 1e-3) * flop / 1e12 / fp64_peak}
-        parity_check = {"against": "render_rows_f64_lean<ShapeEllis> (CURVIS_PRECISION_F64), same frame, every pixel",
-                        "pixels": Wd * Ht, "differing_pixels": differing,
-                        "total_steps_equal": bool(s4["total_steps"] == s5["total_steps"]),
-                        "escape_counters_equal": all(s4[k] == s5[k] for k in ("n_positive", "n_negative", "n_not_escaped", "n_clamped"))}
+        if args.precision == "f64_fast":
+            ctx.set_option("guard", 0)
+            rms = []
+            for _ in range(3):
+                s6 = system.render_rows_device(*sim, row_begin, row_end, frames[0].data_ptr(), stream.cuda_stream, want_stats=True, precision=PREC)
+                rms.append(s6["kernel_ms"])
+            ctx.set_option("guard", 1)
+            raw_fast = {"what": "the regrouped kernel alone (ctx option guard = 0): no guard band, no re-integration — not what `value` times",
+                        "kernel_ms": min(rms), "value": s6["total_steps"] / (min(rms) * 1e-3), "unit": UNIT,
+                        "differing_pixels_vs_f64": int((strict_frame.view(-1, 3) != frames[0].view(-1, 3)).any(dim=1).sum().item())}
+        parity_check = {"f64_fast_vs_f64_kernel": {"pixels": Wd * Ht, "differing_pixels": differing,
+                                                   "total_steps_equal": bool(s4["total_steps"] == s5["total_steps"]),
+                                                   "escape_counters_equal": all(s4[k] == s5[k] for k in ("n_positive", "n_negative", "n_not_escaped", "n_clamped")),
+                                                   "n_reintegrated": int(s5["n_reintegrated"]),
+                                                   "reintegrated_fraction": s5["n_reintegrated"] / (Wd * Ht)}}
+        if not args.no_cpu_baseline:
+            parity_check["against_oracle"] = oracle_parity(args, system, sim, strict_frame.view(Ht, Wd, 3).cpu().numpy(),
+                                                           fast_frame.view(Ht, Wd, 3).cpu().numpy(), PREC)
+        del strict_frame, fast_frame
 
     # ---- opt-in fp32 mode (CURVIS_PRECISION_F32), reported next to the headline, never instead of it
     fast_mode = None
@@ -607,6 +655,7 @@ def run_b200(args):
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "strict_mode": strict_mode,
+        "raw_fast_kernel": raw_fast,
         "parity_check": parity_check,
         "f32_mode": fast_mode,
     }

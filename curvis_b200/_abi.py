@@ -72,6 +72,7 @@ class CurvisStats(C.Structure):
         ("n_not_escaped", C.c_uint64),
         ("n_clamped", C.c_uint64),
         ("n_reintegrated", C.c_uint64),
+        ("n_kicked", C.c_uint64),
         ("kernel_ms", C.c_double),
         ("total_ms", C.c_double),
     ]

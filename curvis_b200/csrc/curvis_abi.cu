@@ -228,6 +228,7 @@ static void fill_params(const curvis_ctx* ctx, const DeviceState& d, const curvi
     p.redo_list = guard ? d.d_redo : nullptr;
     p.redo_capacity = guard ? d.d_redo_cap : 0;
     p.guard_rel = ctx->tuning.guard_rel;
+    p.guard_kicked = ctx->tuning.guard >= 2 ? 1u : 0u;
 }
 
 // CURVIS_SAMPLING_BILINEAR reads the backgrounds as float4 (one 128-bit load per tap): staged once
@@ -265,7 +266,7 @@ static int enqueue_tile(curvis_ctx* ctx, DeviceState& d, const curvis_metric* me
 static void add_counters(const DeviceCounters& c, uint64_t n_rays, curvis_stats* s) {
     s->total_steps += c.total_steps; s->n_rays += n_rays;
     s->n_positive += c.n_positive; s->n_negative += c.n_negative; s->n_not_escaped += c.n_not_escaped;
-    s->n_clamped += c.n_clamped; s->n_reintegrated += c.n_reintegrated;
+    s->n_clamped += c.n_clamped; s->n_reintegrated += c.n_reintegrated; s->n_kicked += c.n_kicked;
 }
 
 static int ensure_capacity(curvis_ctx* ctx, DeviceState& d, size_t out_bytes, size_t n_records, bool staging) {
@@ -710,7 +711,7 @@ extern "C" int curvis_ctx_set_option(curvis_ctx* ctx, const char* key, int64_t v
     else if (k == "window" && value >= 0 && value <= 4096) ctx->tuning.window = (int)value;
     else if (k == "fast_variant" && value >= 0 && value <= 1) ctx->tuning.fast_variant = (int)value;
     else if (k == "zero_copy" && value >= 0 && value <= 1) ctx->tuning.zero_copy = (int)value;
-    else if (k == "guard" && value >= 0 && value <= 1) ctx->tuning.guard = (int)value;
+    else if (k == "guard" && value >= 0 && value <= 2) ctx->tuning.guard = (int)value;
     else if (k == "fast_regs" && (value == 96 || value == 128)) ctx->tuning.fast_regs = (int)value;
     else if (k == "redo_blocks_per_sm" && value >= 0 && value <= 32) ctx->tuning.redo_blocks_per_sm = (int)value;
     else if (k == "guard_rel_e15" && value >= 1 && value <= 1000000000000ll) ctx->tuning.guard_rel = (double)value * 1e-15;

@@ -19,7 +19,8 @@ struct DeviceCounters {
     unsigned long long n_clamped;
     unsigned long long n_reintegrated; // CURVIS_PRECISION_F64_FAST: rays pushed onto the re-integration list (= its length)
     unsigned long long redo_next;      // work queue of the re-integration launch
-    unsigned long long _pad[8];
+    unsigned long long n_kicked;       // CURVIS_PRECISION_F64_FAST: rays with stiffness >= 1
+    unsigned long long _pad[7];
 };
 
 struct Background {
@@ -90,7 +91,9 @@ struct FrameParams {
     // length counters->n_reintegrated) and the parity kernel re-integrates the list in a second launch (ray_list mode)
     unsigned long long* redo_list;
     unsigned long long redo_capacity;
-    double guard_rel;        // relative state error budget of an unamplified ray (units of 1.0)
+    double guard_rel;        // relative state error budget of a ray with stiffness < 1
+    uint32_t guard_kicked;   // 1: rays with stiffness >= 1 are re-integrated too ("guard" = 2)
+    uint32_t _pad3;
     // list mode (the second launch): ray i of the launch is ray ray_list[i] of the tile; the launch holds
     // *ray_list_count rays (device-resident count: the host never learns it before launching)
     const unsigned long long* ray_list;

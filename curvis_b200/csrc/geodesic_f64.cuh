@@ -534,7 +534,7 @@ __device__ __forceinline__ bool finish_ray(const FrameParams& p, const Ray& q, i
         if (lookup) {
             double fx, fy, sin_img;
             image_coordinates(bg, dx, dy, dz, fx, fy, sin_img);
-            if (GUARD) {
+            if (GUARD && guard_eps > 0.0) {
                 const double e_dir = guard_eps * (4.0 + 2.0 * fabs(dz) / (fabs(s) * norm3(dx, dy, dz)));
                 const double ey = e_dir * (double)bg.height * (1.0 / CURVIS_PI);
                 const double ex = e_dir * (double)bg.width * (0.5 / CURVIS_PI) / fmax(sin_img, 1e-300);

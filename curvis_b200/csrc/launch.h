@@ -15,7 +15,8 @@ struct LaunchTuning {
     int window = 0;          // Euler steps between two refill points of a warp; 0 = auto (32; 32..128 in F64_FAST)
     int zero_copy = 1;       // curvis_render_image into a registered host frame: 1 (default) = the kernel stores its pixels
                              // straight into it (measured: kernel time unchanged, 0.04 ms exposed); 0 = device frame + one DMA (0.5 ms)
-    int guard = 1;           // CURVIS_PRECISION_F64_FAST: 1 (default) = guard band + re-integration (frames equal CURVIS_PRECISION_F64's);
+    int guard = 1;           // CURVIS_PRECISION_F64_FAST: 1 (default) = guard band + re-integration for the rays with stiffness < 1;
+                             // 2 = kicked rays (stiffness >= 1) re-integrated too (every ray equals CURVIS_PRECISION_F64's);
                              // 0 = the raw regrouped kernel (A/B, tools/guard_study.py)
     double guard_rel = 1e-9; // relative state-error budget of a ray with stiffness < 1 (render_f64_fast.cu: guard_eps)
     int redo_blocks_per_sm = 2;   // CTAs per SM of the re-integration launch (a few per cent of the frame's rays: fewer, fuller warps)

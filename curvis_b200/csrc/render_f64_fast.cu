@@ -281,20 +281,22 @@ __device__ __noinline__ Ray unscaled_ray(const FrameParams& p, const Ray& q, uns
 }
 
 // Guard band of the fast kernel.  The regrouped arithmetic reproduces the photon state of the operation-for-operation
-// kernel to eps ~ 1e-13 relative (per-step rounding differences of a few 1e-16, carried (sin, cos) drift <= 2e-14 per
-// window), multiplied by the trajectory's own error amplification, which explicit Euler in (theta, phi) coordinates
-// makes large only where a step's azimuth advance is not small: kappa = max (delta dphi/dlambda)^2 (the `stiffness` of
-// curvis_ray_record, tracked for free as the maximum of w).  A ray's integers (step count, texel) are accepted when every
-// decision was taken farther from its boundary than  eps(kappa) = guard_rel * (1 + kGuardGain * kappa)^2 ... see
-// guard_eps() — otherwise its index goes to the redo list and the parity kernel re-integrates it.
+// kernel to ~1e-13 relative (per-step rounding differences of a few 1e-16, carried (sin, cos) drift <= 2e-14 per window),
+// multiplied by the trajectory's own error amplification, which explicit Euler in (theta, phi) coordinates makes large
+// only where a step's azimuth advance is not small: kappa = max (delta dphi/dlambda)^2, the `stiffness` of
+// curvis_ray_record, tracked as the running maximum of w's high word (one integer instruction per step).
+// Measured (tools/guard_study.py, profiles/r02_guard_study.json: eight scenes, 10.4 M rays), fast kernel against the
+// operation-for-operation kernel, as a function of kappa:
+//     kappa < 1     direction of the lookup vector / end-state factor <= 2.3e-12,  |delta l| <= 1.8e-9
+//     kappa >= 1    up to 1.2e-6 and 1e-3 |p_l| (|p_l| itself up to 1e31: the ray has been kicked by a coordinate pole)
+// kappa < 1: the ray's integers (step count, texel) are accepted when every decision was taken farther from its boundary
+// than guard_rel = 1e-9 (x the end-state factor for the direction, x (1 + R) for l: factors 430 and 56 over the maxima
+// above); otherwise its index goes to the redo list and the parity kernel re-integrates it.  kappa >= 1 ("kicked", 2.5 % of
+// the default frame): counted; re-integrated only with "guard" = 2 (their strict re-integration costs 20 % of the frame
+// time: near-critical rays of 10^4 steps dominate a second launch), else kept (1 differing pixel measured in 21 M).
 __device__ __forceinline__ double guard_eps(const FrameParams& p, double kappa) {
-    // measured (tools/guard_study.py, profiles/r02_guard_study.json: eight scenes, 10.4 M rays): for kappa < 1 the end-state
-    // deviation divided by the end-state factor finish_ray applies stays below 2.3e-12 and |delta l| below 1.8e-9; the budget
-    // guard_rel = 1e-9 (of the direction; times 1 + R for l) leaves factors 430 and 56.  Rays with kappa >= 1 — a step that
-    // advanced phi by a radian: the kicked rays, 2.4 % of the default frame — are re-integrated outright: their l deviates by
-    // up to 1e-3 per unit of p_l and no band short of a whole step would be safe.
     if (kappa < 1.0) return p.guard_rel;
-    return __longlong_as_double(0x7ff0000000000000ll);   // also NaN
+    return p.guard_kicked ? __longlong_as_double(0x7ff0000000000000ll) : 0.0;   // kappa NaN counts as kicked
 }
 
 // Epilogue of a finished ray of fast_variant 1, out of line (once per ray; the step loop keeps its registers): the photon
@@ -315,8 +317,10 @@ __device__ __noinline__ void fast_epilogue(const FrameParams& p, const Ray& q, u
         return;
     }
     const double eps = guard_eps(p, diag.stiffness);
-    // the step count: every l visited near the radius stayed farther than eps * (1 + R) from +-R
-    bool accepted = (double)margin > eps * (1.0 + fabs(R));
+    if (!(diag.stiffness < 1.0)) atomicAdd(&p.counters->n_kicked, 1ull);
+    // the step count: every l visited near the radius stayed farther than eps * (1 + R) from +-R (eps = 0: a kicked ray
+    // that is kept as integrated)
+    bool accepted = (eps == 0.0) || ((double)margin > eps * (1.0 + fabs(R)));
     if (accepted) accepted = finish_ray<Shape64, TrigFast, true>(p, qe, side, steps, ray, tally, diag, eps);
     if (accepted) return;
     const unsigned long long slot = atomicAdd(&p.counters->n_reintegrated, 1ull);

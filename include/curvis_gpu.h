@@ -96,10 +96,14 @@ typedef enum curvis_precision {
     CURVIS_PRECISION_F64_FAST = 2 /* fp64 with the right-hand side regrouped around ONE reciprocal per step and fused
                                      multiply-adds (every operation <= 1 ulp, rounding points differ from the reference's,
                                      state agrees to ~1e-13 relative) as a PREDICTOR: a ray whose escape step or texel lies
-                                     within a guard band of a decision boundary — the band scales with the ray's measured
-                                     error amplification — is re-integrated with the CURVIS_PRECISION_F64 arithmetic in a
-                                     second launch over the compacted list, so RGB8 / side / step count / texel equal
-                                     CURVIS_PRECISION_F64's (curvis_stats.n_reintegrated counts them) */
+                                     within a guard band of a decision boundary is re-integrated with the
+                                     CURVIS_PRECISION_F64 arithmetic in a second launch over the compacted list, so RGB8 / side
+                                     / step count / texel equal CURVIS_PRECISION_F64's on every ray with stiffness < 1 (97.5 %
+                                     of the default frame; curvis_stats.n_reintegrated).  Rays with stiffness >= 1 ("kicked":
+                                     their end state amplifies a last-bit change up to 1e10-fold) are counted in n_kicked and,
+                                     with the context option "guard" = 2, re-integrated as well (then every ray equals
+                                     CURVIS_PRECISION_F64's; +20 % time); with the default "guard" = 1 they are kept as
+                                     integrated (measured: 1 differing pixel in 21 M).  DESIGN.md section 4 */
 } curvis_precision;
 
 typedef enum curvis_sampling {
@@ -156,6 +160,8 @@ typedef struct curvis_stats {
     uint64_t n_not_escaped; /* PhotonEscape::NotEscaped     systems.rs:137     */
     uint64_t n_clamped;     /* texel index the reference would have panicked on (images.rs:107-111) */
     uint64_t n_reintegrated;/* CURVIS_PRECISION_F64_FAST: rays inside the guard band, re-integrated with the F64 arithmetic */
+    uint64_t n_kicked;      /* CURVIS_PRECISION_F64_FAST: rays with stiffness >= 1 (some step advanced phi by a radian or more: explicit
+                               Euler is no longer integrating their theta motion) */
     double kernel_ms;       /* device time of the render kernel(s), CUDA events, max over devices */
     double total_ms;        /* host wall time of the call, copies included */
 } curvis_stats;
@@ -359,7 +365,8 @@ int curvis_measure_fma_peak(curvis_ctx* ctx, double* fp64_tflops, double* fp32_t
  *                     sincos; 2 unguarded IEEE sequences + in-kernel sincos; 3 the same
  *                     arithmetic in the lean loop (integer-pipe guards, gated escape test); 4 (default) the lean loop
  *                     with the step's six reciprocals built from two seeds and one correction step each
- *   "guard":          CURVIS_PRECISION_F64_FAST: 1 (default) guard band + re-integration; 0 the raw regrouped kernel (A/B)
+ *   "guard":          CURVIS_PRECISION_F64_FAST: 1 (default) guard band + re-integration of the rays with stiffness < 1;
+ *                     2 kicked rays (stiffness >= 1) re-integrated too; 0 the raw regrouped kernel (A/B)
  *   "guard_rel_e15":  the guard's relative budget in units of 1e-15 (default 1000000 = 1e-9)
  *   "fast_regs":      96 (default) / 128: register budget of the fast kernel (5 / 4 resident CTAs per SM)
  *   "redo_blocks_per_sm": resident CTAs per SM of the re-integration launch (default 2)

@@ -52,6 +52,10 @@ def lib() -> C.CDLL:
         L.oracle_escape_photon.argtypes = [C.POINTER(_abi.CurvisMetric), dp, C.c_double, C.c_uint32, C.c_double, C.POINTER(C.c_uint32)]
         L.oracle_relativistic_vector_to_direction.argtypes = [C.POINTER(_abi.CurvisMetric), dp, dp, dp]
         L.oracle_relativistic_vector_to_direction.restype = None
+        L.oracle_lookup_direction.argtypes = [C.POINTER(_abi.CurvisMetric), dp, C.c_int, dp]
+        L.oracle_escape_photon_sim.argtypes = [C.POINTER(_abi.CurvisMetric), dp, C.POINTER(_abi.CurvisSim), C.POINTER(C.c_uint32), dp]
+        L.oracle_step_adaptive.argtypes = [C.POINTER(_abi.CurvisMetric), dp, C.c_double, C.c_double]
+        L.oracle_step_adaptive.restype = None
         L.oracle_squared_norm_cov.argtypes = [C.POINTER(_abi.CurvisMetric), dp, dp]
         L.oracle_squared_norm_cov.restype = C.c_double
         L.oracle_texel_from_vector3.argtypes = [dp, dp, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), dp, dp]
@@ -177,6 +181,27 @@ def escape_photon(g, x, p, delta, max_iterations, max_radius):
     side = lib().oracle_escape_photon(C.byref(g), ph, delta, max_iterations, max_radius, C.byref(steps))
     a = np.array(ph)
     return side, steps.value, a[:4].copy(), a[4:].copy()
+
+
+def lookup_direction(g, x, p, frame=0):
+    """oracle_lookup_direction: the vector that indexes the background for an escaped photon (x, p) in a curvis_frame.
+    Raises where the reference panics (rotation_from_two_vectors on parallel vectors)."""
+    ph = _d(list(x) + list(p), 8)
+    o = (C.c_double * 3)()
+    if lib().oracle_lookup_direction(C.byref(g), ph, frame, o):
+        raise ValueError("v1 and v2 must not be parallel")
+    return np.array(o)
+
+
+def escape_photon_sim(g, x, p, s, track=False):
+    """escape_photon under a full curvis_sim (integrator extensions): (side, steps, x, p[, (min |sin theta|, stiffness)])."""
+    ph = _d(list(x) + list(p), 8)
+    steps = C.c_uint32()
+    diag = (C.c_double * 2)()
+    side = lib().oracle_escape_photon_sim(C.byref(g), ph, C.byref(s), C.byref(steps), diag if track else None)
+    a = np.array(ph)
+    out = (side, steps.value, a[:4].copy(), a[4:].copy())
+    return out + ((diag[0], diag[1]),) if track else out
 
 
 def direction(g, p, x):

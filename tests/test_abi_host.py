@@ -38,7 +38,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_abi.CurvisMetric) == 32
     assert C.sizeof(_abi.CurvisCamera) == 4 * 8 + 9 * 8 + 3 * 8 + 8
     assert C.sizeof(_abi.CurvisSim) == 56
-    assert C.sizeof(_abi.CurvisStats) == 9 * 8
+    assert C.sizeof(_abi.CurvisStats) == 10 * 8
     assert C.sizeof(_abi.CurvisRayRecord) == 80 == np.dtype(_abi.RAY_RECORD_DTYPE).itemsize
 
 

@@ -1,15 +1,17 @@
-"""CURVIS_PRECISION_F64_FAST — fp64 with the right-hand side regrouped around one reciprocal per
-step (render_f64_fast.cu).  It has no operation-for-operation counterpart in the reference, so
-its bar is stated here, against the same oracle as the parity kernel:
+"""CURVIS_PRECISION_F64_FAST — fp64 with the right-hand side regrouped around one reciprocal per step
+(render_f64_fast.cu) plus the guard band that sends every ray near a decision boundary back through the
+operation-for-operation arithmetic.  Its bar, against the same oracle as the parity kernel:
 
-* integer / byte results (RGB8, escape side, step count, texel index, counters): identical to the
-  oracle on >= 99.999 % of rays of every tested frame (measured: every ray of every frame below,
-  and all but 1 of 8.3 M pixels of the full Interstellar 4K frame);
+* integer / byte results (RGB8, escape side, step count, texel index, counters): IDENTICAL to the oracle on every ray
+  the oracle classifies as regular (oracle/classify.py) and on every ray with stiffness < 1 (the rays
+  the guard band covers by construction); chaotic / kicked rays are counted and printed, and at most 1e-5 of all rays
+  may differ (measured: 1 pixel in 21 M).  With the context option "guard" = 2 every ray is identical
+  (tests/test_gpu_baseline_configs.py::test_full_identity_mode_guard_2);
 * floating-point state: final l and p_l within rtol 1e-9 on >= 99.9 % of escaped rays (the rest are
-  the chaotic rays that graze a coordinate pole, where 1 ulp is amplified without bound), end
-  direction within 1e-5 rad (BASELINE.json north_star) on >= 99.99 %;
+  the kicked rays, where 1 ulp is amplified up to 1e10-fold), end direction within 1e-5 rad
+  (BASELINE.json north_star) on >= 99.99 %;
 * exotic cases (NaN rays of the Flat metric, NotEscaped, zero iterations, negative delta): exactly
-  the parity kernel's output — such rays take the parity step.
+  the parity kernel's output — such rays are re-integrated.
 """
 import os
 import sys
@@ -110,6 +112,15 @@ def _compare_with_oracle(frame, rec, ref_frame, ref_rec, name):
            (rec["texel_x"] != ref_rec["texel_x"]) | (rec["texel_y"] != ref_rec["texel_y"]))
     n_bad = int(bad.sum())
     assert n_bad <= max(0, int(MAX_DIFFERING_FRACTION * n)), f"{name}: {n_bad} of {n} rays differ from the oracle"
+    if "min_abs_sin_theta" in ref_rec.dtype.names:       # live oracle records (the golden fixtures predate the diagnostics)
+        from oracle import classify
+        chaotic = classify.chaotic_mask(ref_rec)
+        with np.errstate(invalid="ignore"):
+            kicked = ~(ref_rec["stiffness"] < 1.0)
+        print(f"[parity] {name}: {n} rays, chaotic {int(chaotic.sum())}, kicked {int(kicked.sum())}, differing {n_bad} "
+              f"(regular {int((bad & ~chaotic).sum())}, stiffness < 1 {int((bad & ~kicked).sum())})")
+        assert int((bad & ~chaotic).sum()) == 0, f"{name}: a regular ray differs from the oracle"
+        assert int((bad & ~kicked).sum()) == 0, f"{name}: a ray with stiffness < 1 differs from the oracle (guard band)"
     assert rec["p_phi"].tobytes() == ref_rec["p_phi"].tobytes(), f"{name}: p_phi is conserved and never recomputed"
     ok = (ref_rec["side"] != 0) & ~bad & np.isfinite(ref_rec["l"]) & np.isfinite(ref_rec["theta"])
     if ok.any():
