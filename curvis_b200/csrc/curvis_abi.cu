@@ -44,6 +44,8 @@ struct DeviceState {
     CameraBlock* d_cameras = nullptr; size_t d_cameras_cap = 0;   // batched launches
     double2* d_shape_tab = nullptr;   // Interstellar shape-function table (shape_table.h), uploaded at context creation
     float4* d_shape_tab32 = nullptr;  // its fp32 edition
+    double2* d_inv_tab = nullptr;     // per-metric table of 1/r and r' (shape_table.h), rebuilt when (rho, m) change
+    double inv_tab_rho = 0.0, inv_tab_m = 0.0;
     cudaEvent_t chunk_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // pipelined read-back
     // CURVIS_PRECISION_F64_FAST: indices of the rays inside the guard band, re-integrated by the parity kernel
     unsigned long long* d_redo = nullptr; size_t d_redo_cap = 0;
@@ -62,6 +64,8 @@ struct curvis_ctx {
     bool bg_set[2] = {false, false};
     curvis::LaunchTuning tuning;
     std::string err;
+    std::vector<double> inv_tab_host;   // host copy of the last per-metric shape table built (shared by the devices)
+    double inv_tab_host_rho = 0.0, inv_tab_host_m = 0.0;
     // caller-owned frame buffers page-locked by curvis_host_register: frames are DMA'd straight into them
     struct HostRegion { uint8_t* base; size_t bytes; };
     std::vector<HostRegion> host_regions;
@@ -163,6 +167,24 @@ static cudaError_t launch_fence(DeviceState& d, cudaStream_t stream) {
     return e;
 }
 
+// CURVIS_PRECISION_F64_FAST + Interstellar: the per-metric table of 1/r(x) and r'(x) (shape_table.h) on device d, built on
+// the host (~20 ms) the first time a (rho, m) pair is seen and uploaded stream-ordered.
+static int ensure_inverse_table(curvis_ctx* ctx, DeviceState& d, const curvis_metric* metric, const curvis_sim* sim, cudaStream_t stream) {
+    if (sim->precision != CURVIS_PRECISION_F64_FAST || metric->kind != CURVIS_METRIC_INTERSTELLAR) return CURVIS_OK;
+    if (d.d_inv_tab && d.inv_tab_rho == metric->rho && d.inv_tab_m == metric->m) return CURVIS_OK;
+    const size_t n = kInvTabIntervals * kShapeTabDoubles;
+    if (ctx->inv_tab_host.size() != n || ctx->inv_tab_host_rho != metric->rho || ctx->inv_tab_host_m != metric->m) {
+        ctx->inv_tab_host.resize(n);
+        build_interstellar_inverse_table(metric->rho, metric->m, ctx->inv_tab_host.data());
+        ctx->inv_tab_host_rho = metric->rho; ctx->inv_tab_host_m = metric->m;
+    }
+    if (!d.d_inv_tab) CURVIS_CUDA(ctx, cudaMalloc(&d.d_inv_tab, n * sizeof(double)));
+    CURVIS_CUDA(ctx, cudaMemcpyAsync(d.d_inv_tab, ctx->inv_tab_host.data(), n * sizeof(double), cudaMemcpyHostToDevice, stream));
+    CURVIS_CUDA(ctx, cudaStreamSynchronize(stream));   // the host copy may be rebuilt by the next call
+    d.inv_tab_rho = metric->rho; d.inv_tab_m = metric->m;
+    return CURVIS_OK;
+}
+
 // The redo list of CURVIS_PRECISION_F64_FAST: one slot per ray of the launch (8 bytes each; a 4K frame: 66 MB), grown on demand.
 static int ensure_redo(curvis_ctx* ctx, DeviceState& d, const curvis_sim* sim, size_t rays) {
     if (sim->precision != CURVIS_PRECISION_F64_FAST || !ctx->tuning.guard || ctx->tuning.fast_variant != 1) return CURVIS_OK;
@@ -214,6 +236,9 @@ static void fill_params(const curvis_ctx* ctx, const DeviceState& d, const curvi
     p.d_xscale = 2.0 / (3.14159265358979323846 * metric->m);
     p.shape_tab = d.d_shape_tab;
     p.shape_tab32 = d.d_shape_tab32;
+    p.inv_tab = d.d_inv_tab;
+    p.d_xoff = -metric->a * p.d_xscale;
+    p.fast_l_limit = metric->kind == CURVIS_METRIC_INTERSTELLAR ? interstellar_table_l_limit(metric->m, metric->a) : HUGE_VAL;
     // below this |l| no escape test is needed in the fp32 kernel (4 steps of slack at |p_l| <= ~1.3)
     p.f_near_radius = (float)(std::fabs(sim->max_radius) - 6.0 * std::fabs(sim->delta) - 1e-3 * std::fabs(sim->max_radius));
     for (int s = 0; s < 2; ++s) {
@@ -252,6 +277,8 @@ static int enqueue_tile(curvis_ctx* ctx, DeviceState& d, const curvis_metric* me
     int frc = ensure_float_backgrounds(ctx, d, sim, stream);
     if (frc != CURVIS_OK) return frc;
     frc = ensure_redo(ctx, d, sim, (size_t)(row_end - row_begin) * cam->resolution_width);
+    if (frc != CURVIS_OK) return frc;
+    frc = ensure_inverse_table(ctx, d, metric, sim, stream);
     if (frc != CURVIS_OK) return frc;
     FrameParams p;
     fill_params(ctx, d, metric, cam, sim, row_begin, row_end, d_out, d_records, p);
@@ -336,6 +363,7 @@ static void release_device(DeviceState& d) {
     if (d.d_cameras) cudaFree(d.d_cameras);
     if (d.d_shape_tab) cudaFree(d.d_shape_tab);
     if (d.d_shape_tab32) cudaFree(d.d_shape_tab32);
+    if (d.d_inv_tab) cudaFree(d.d_inv_tab);
     if (d.d_redo) cudaFree(d.d_redo);
     for (auto& ev : d.chunk_done) if (ev) cudaEventDestroy(ev);
     if (d.ev_begin) cudaEventDestroy(d.ev_begin);
@@ -508,6 +536,8 @@ static int render_frames_impl(curvis_ctx* ctx, const curvis_metric* metric,
     {
         const uint32_t rows_launch = (row_end - row_begin + row_stride - 1) / row_stride;
         int rrc = ensure_redo(ctx, d, sim, (size_t)rows_launch * cameras[0].resolution_width * n_frames);
+        if (rrc != CURVIS_OK) return rrc;
+        rrc = ensure_inverse_table(ctx, d, metric, sim, st);
         if (rrc != CURVIS_OK) return rrc;
     }
     std::vector<CameraBlock> blocks(n_frames);
@@ -741,6 +771,30 @@ extern "C" int curvis_debug_eval(curvis_ctx* ctx, int op, const double* a, const
     return rc;
 }
 
+extern "C" int curvis_debug_inverse_shape(curvis_ctx* ctx, const curvis_metric* metric, const double* x, double* y, double* g, size_t n) {
+    if (!ctx || !metric || !x || !y || !g) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "null argument");
+    if (metric->kind != CURVIS_METRIC_INTERSTELLAR) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "the inverse shape table belongs to the Interstellar metric");
+    int rc = curvis_metric_validate(metric);
+    if (rc != CURVIS_OK) return fail(ctx, rc, thread_error());
+    DeviceState& d = ctx->devs[0];
+    CURVIS_CUDA(ctx, cudaSetDevice(d.ordinal));
+    curvis_sim sim; std::memset(&sim, 0, sizeof sim); sim.precision = CURVIS_PRECISION_F64_FAST;
+    rc = ensure_inverse_table(ctx, d, metric, &sim, d.stream);
+    if (rc != CURVIS_OK) return rc;
+    double *dx = nullptr, *dy = nullptr, *dg = nullptr;
+    const size_t bytes = (n ? n : 1) * sizeof(double);
+    cudaError_t e = cudaSuccess;
+    if ((e = cudaMalloc(&dx, bytes)) == cudaSuccess && (e = cudaMalloc(&dy, bytes)) == cudaSuccess && (e = cudaMalloc(&dg, bytes)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(dx, x, n * sizeof(double), cudaMemcpyHostToDevice, d.stream)) == cudaSuccess &&
+        (e = launch_debug_inverse_shape(d.d_inv_tab, dx, dy, dg, n, d.stream)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(y, dy, n * sizeof(double), cudaMemcpyDeviceToHost, d.stream)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(g, dg, n * sizeof(double), cudaMemcpyDeviceToHost, d.stream)) == cudaSuccess)
+        e = cudaStreamSynchronize(d.stream);
+    cudaFree(dx); cudaFree(dy); cudaFree(dg);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "curvis_debug_inverse_shape");
+    return CURVIS_OK;
+}
+
 extern "C" int curvis_debug_rhs_check(curvis_ctx* ctx, const curvis_metric* metric, uint64_t n_samples, uint64_t seed, uint64_t mismatches[4]) {
     if (!ctx || !metric || !mismatches) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "null argument");
     int rc = curvis_metric_validate(metric);
@@ -796,6 +850,7 @@ extern "C" int curvis_render_image_efficient(curvis_ctx* ctx, const curvis_metri
         int r = ensure_capacity(ctx, d, 1, n, false);
         if (r != CURVIS_OK) return cuda_rc = r;
         if ((r = ensure_redo(ctx, d, sim, n)) != CURVIS_OK) return cuda_rc = r;
+        if ((r = ensure_inverse_table(ctx, d, metric, sim, d.stream)) != CURVIS_OK) return cuda_rc = r;
         if (launch_fence(d, d.stream) != cudaSuccess) return cuda_rc = fail(ctx, CURVIS_ERR_CUDA, "launch fence");
         cudaError_t e = cudaMemcpyAsync(d_dirs, dirs, n * 3 * sizeof(double), cudaMemcpyHostToDevice, d.stream);
         if (e != cudaSuccess) return cuda_rc = cuda_fail(ctx, e, "cudaMemcpyAsync(ray directions)");

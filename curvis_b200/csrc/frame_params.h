@@ -74,6 +74,10 @@ struct FrameParams {
     // Interstellar shape-function table of CURVIS_PRECISION_F64_FAST (shape_table.h), resident per device
     const double2* shape_tab;
     const float4* shape_tab32;   // the fp32 edition for CURVIS_PRECISION_F32
+    // per-metric table of 1/r and r' (shape_table.h: build_interstellar_inverse_table), x = fma(|l|, d_xscale, d_xoff), and
+    // the |l| beyond which x leaves the table (+inf for the other metrics)
+    const double2* inv_tab;
+    double d_xoff, fast_l_limit;
     // scene (systems.rs:70-71): [0] = background_positive, [1] = background_negative
     Background bg[2];
     // Fused render + all-gather (curvis_render_frames_peers): n_peers > 0 = every finished ray stores its RGB8

@@ -55,6 +55,8 @@ cudaError_t launch_debug_rhs_check(const FrameParams& p, int metric_kind, unsign
 // F(x) (which = 0) / G(x) (which = 1) of the Interstellar shape-function table as the fast kernel
 // evaluates them (test hook, curvis_debug_eval ops 13 / 14).  render_f64_fast.cu.
 cudaError_t launch_debug_shape(const double2* tab, int which, const double* x, double* out, size_t n, cudaStream_t stream);
+// Y(x) = 1/r and G(x) of the per-metric table as fast_variant 1 evaluates them (x given; test hook curvis_debug_inverse_shape).
+cudaError_t launch_debug_inverse_shape(const double2* tab, const double* x, double* y, double* g, size_t n, cudaStream_t stream);
 // The same for the fp32 table of CURVIS_PRECISION_F32 (ops 15 / 16; x is rounded to float first).  render_f32.cu.
 cudaError_t launch_debug_shape32(const float4* tab, int which, const double* x, double* out, size_t n, cudaStream_t stream);
 

@@ -68,6 +68,7 @@ struct FastEllis {   // metrics.rs:417-421 : r^2 = rho^2 + l^2, r' = l/r  =>  r'
         v = w * pre.r2;
         f = l * (u * u);
     }
+    static __device__ __forceinline__ bool beyond(const FrameParams&, double) { return false; }
 };
 
 // r(l) > 0 and r'(l) given: one reciprocal of r*sin^2 yields 1/r and 1/sin^2.
@@ -123,6 +124,7 @@ __device__ __forceinline__ void shape_fg(const FrameParams& p, double x, double&
 
 struct FastInterstellar {   // metrics.rs:461-485 with the uniform divisor pi*m folded into d_xscale
     using Shape64 = ShapeInterstellar;
+    // fast_variant 0: r and r' through the parameter-free table of F and G (library functions outside its range).
     // One path for the whole l axis: x <= 0 on the plateau |l| <= a fails the table's range test and comes back as
     // F = G = 0 from the library branch (a ray spends at most a step or two there), so the step carries no branch on l.
     static __device__ __forceinline__ void shape(const FrameParams& p, double l, double& r, double& rp) {
@@ -137,14 +139,32 @@ struct FastInterstellar {   // metrics.rs:461-485 with the uniform divisor pi*m 
         shape(p, l, r, rp);
         return factors_from_r(p, r, rp, s2, w, u, v, ud, fd);
     }
-    using Pre = PreFromR;
+    // fast_variant 1 (default): Y = 1/r and G = |r'| from the per-metric table (shape_table.h) — six 128-bit loads and two
+    // degree-5 Horner chains; the step's one reciprocal is then 1/sin^2 theta alone.  No branch, no call: every x below the
+    // table (the plateau, x <= 0 included) reads the constant row through an unsigned min; x beyond it never gets here
+    // (beyond(): the kernel's radius gate).  42 fp64-pipe instructions per step.
+    struct Pre { double y, rp; };
     static __device__ __forceinline__ double prepare(const FrameParams& p, double l, double s2, Pre& pre) {
-        shape(p, l, pre.r, pre.rp);
-        return pre.r * s2;
+        const double x = fma(fabs(l), p.d_xscale, p.d_xoff);
+        const unsigned hi = (unsigned)__double2hiint(x);
+        const unsigned idx = min((hi >> kShapeTabShift) - kInvTabBase, (unsigned)kInvTabConstRow);
+        const double c = __hiloint2double((int)((hi & ~((1u << kShapeTabShift) - 1u)) | (1u << (kShapeTabShift - 1))), 0);
+        const double t = x - c;
+        const double2* e = p.inv_tab + (size_t)idx * (kShapeTabDoubles / 2);
+        const double2 a01 = __ldg(e), a23 = __ldg(e + 1), a45 = __ldg(e + 2);
+        const double2 b01 = __ldg(e + 3), b23 = __ldg(e + 4), b45 = __ldg(e + 5);
+        pre.y = fma(t, fma(t, fma(t, fma(t, fma(t, a45.y, a45.x), a23.y), a23.x), a01.y), a01.x);
+        const double G = fma(t, fma(t, fma(t, fma(t, fma(t, b45.y, b45.x), b23.y), b23.x), b01.y), b01.x);
+        pre.rp = copysign(G, l);
+        return s2;
     }
-    static __device__ __forceinline__ void finish(const Pre& pre, double y0, double, double s2, double& w, double& u, double& v, double& f) {
-        finish_from_r(pre, y0, s2, w, u, v, f);
+    static __device__ __forceinline__ void finish(const Pre& pre, double y0, double, double, double& w, double& u, double& v, double& f) {
+        v = y0;                        // 1/sin^2
+        u = pre.y * pre.y;             // 1/r^2
+        w = u * v;
+        f = pre.rp * (pre.y * u);      // r'/r^3
     }
+    static __device__ __forceinline__ bool beyond(const FrameParams& p, double l) { return !(fabs(l) < p.fast_l_limit); }
 };
 
 struct FastFlat {   // metrics.rs:501-505: r = l, r' = 1 (r may be negative: take the parity step then)
@@ -160,6 +180,7 @@ struct FastFlat {   // metrics.rs:501-505: r = l, r' = 1 (r may be negative: tak
     static __device__ __forceinline__ void finish(const Pre& pre, double y0, double, double s2, double& w, double& u, double& v, double& f) {
         finish_from_r(pre, y0, s2, w, u, v, f);
     }
+    static __device__ __forceinline__ bool beyond(const FrameParams&, double) { return false; }
 };
 
 // One forward-Euler step (metrics.rs:283-297) with the regrouped right-hand side.  Returns
@@ -349,7 +370,7 @@ __global__ void __launch_bounds__(kBlockFast, MinBlocks) render_rows_f64_fast(co
     const double R = p.max_radius;
     // escape test: |l| > R needs abs_hi(l) >= hi(R) when R >= 0; for negative or NaN R the gate is open.  Variant 1 opens
     // it three steps early (a photon moves ~|delta| per step) and walks the last steps one by one (see `near` below).
-    const double R_near = R - 3.0 * fabs(p.delta);
+    const double R_near = fmin(R - 3.0 * fabs(p.delta), p.fast_l_limit);   // (the Interstellar table's reach, else +inf)
     const unsigned gate = (Variant == 1) ? ((R_near > 0.0) ? abs_hi(R_near) : 0u) : ((R >= 0.0) ? abs_hi(R) : 0u);
     const bool guard = (Variant == 1) && p.redo_list != nullptr;
     const float finf = __int_as_float(0x7f800000);
@@ -448,6 +469,7 @@ __global__ void __launch_bounds__(kBlockFast, MinBlocks) render_rows_f64_fast(co
                     float margin = cold.margin;
                     if ((q.l > R) || (q.l < -R) || (q.l != q.l)) { stop = true; margin = 0.f; }
                     while (!stop && !slow && k < n) {
+                        if (Fast::beyond(p, q.l)) { slow = true; break; }         // past the shape table: parity steps
                         const double before = R - fabs(q.l);
                         bool unused = false;
                         double w1 = 0.0;
@@ -525,6 +547,29 @@ __global__ void debug_shape_kernel(const double2* tab, int which, const double* 
     double F, G;
     shape_fg(p, x[i], F, G);
     out[i] = which ? G : F;
+}
+
+__global__ void debug_inverse_shape_kernel(const double2* tab, const double* x, double* y, double* g, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    FrameParams p;
+    p.inv_tab = tab;
+    p.d_xscale = 1.0; p.d_xoff = 0.0;          // prepare() reads x = fma(|l|, 1, 0): feed |l| = x (x < 0 through the sign below)
+    FastInterstellar::Pre pre;
+    const double xi = x[i];
+    if (xi >= 0.0 || xi != xi) {
+        FastInterstellar::prepare(p, xi, 1.0, pre);
+    } else {                                      // negative x (the plateau): |l| cannot express it, shift through xoff
+        p.d_xoff = xi;
+        FastInterstellar::prepare(p, 0.0, 1.0, pre);
+    }
+    y[i] = pre.y; g[i] = fabs(pre.rp);
+}
+
+cudaError_t launch_debug_inverse_shape(const double2* tab, const double* x, double* y, double* g, size_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    debug_inverse_shape_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(tab, x, y, g, n);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_debug_shape(const double2* tab, int which, const double* x, double* out, size_t n, cudaStream_t stream) {

@@ -1,7 +1,12 @@
 // shape_table.cpp — host-side generation of the table described in shape_table.h (x87 long double:
 // 64-bit significand, glibc atanl / log1pl).
 #include "shape_table.h"
+#include <cfloat>
 #include <cmath>
+
+// The Chebyshev fits below need a 64-bit significand: with long double == double (e.g. -mlong-double-64) the coefficients
+// would silently lose several bits and the fast kernels would drift with no signal.
+static_assert(LDBL_MANT_DIG >= 64, "shape_table.cpp needs an extended-precision long double (x87 or IEEE quad)");
 
 namespace curvis {
 
@@ -14,14 +19,23 @@ long double shape_g(long double x) { return (2.0L / kPiL) * atanl(x); }
 
 // Monomial coefficients (in tau = t / w, |tau| <= 1) of the degree-(N-1) interpolant of f through
 // the N Chebyshev nodes of [c - w, c + w]: Chebyshev coefficients by the discrete cosine sums,
-// then the T_j -> monomial recurrence.
-template <int N>
-void fit(long double (*f)(long double), long double c, long double w, long double mono[N]) {
+// then the T_j -> monomial recurrence.  F: any callable long double -> long double.
+template <int N, class F>
+void fit(F f, long double c, long double w, long double mono[N]) {
+    static long double node[N], basis[N][N];
+    static bool ready = false;
+    if (!ready) {      // (single-threaded callers: context creation / first launch of a metric)
+        for (int k = 0; k < N; ++k) {
+            node[k] = cosl(kPiL * (2 * k + 1) / (2 * N));
+            for (int j = 0; j < N; ++j) basis[j][k] = cosl(j * kPiL * (2 * k + 1) / (2 * N));
+        }
+        ready = true;
+    }
     long double fv[N], cj[N];
-    for (int k = 0; k < N; ++k) fv[k] = f(c + w * cosl(kPiL * (2 * k + 1) / (2 * N)));
+    for (int k = 0; k < N; ++k) fv[k] = f(c + w * node[k]);
     for (int j = 0; j < N; ++j) {
         long double s = 0.0L;
-        for (int k = 0; k < N; ++k) s += fv[k] * cosl(j * kPiL * (2 * k + 1) / (2 * N));
+        for (int k = 0; k < N; ++k) s += fv[k] * basis[j][k];
         cj[j] = s * 2.0L / N;
     }
     cj[0] *= 0.5L;
@@ -64,6 +78,38 @@ void build(Real* out, int per_binade_log2) {
 
 void build_interstellar_shape_table(double* out) { build<kShapeTabDegree + 1, double>(out, kShapeTabK); }
 
+void build_interstellar_inverse_table(double rho, double m, double* out) {
+    constexpr int N = kShapeTabDegree + 1;
+    const int per_binade = 1 << kShapeTabK;
+    const long double rho_l = rho, m_l = m;
+    auto inv_r = [rho_l, m_l](long double x) { return 1.0L / (rho_l + m_l * shape_f(x)); };
+    size_t idx = 0;
+    for (int e = kInvTabEmin; e < kShapeTabEmax; ++e) {
+        const long double x0 = ldexpl(1.0L, e);
+        const int wexp = e - kShapeTabK - 1;
+        const long double w = ldexpl(1.0L, wexp);
+        for (int j = 0; j < per_binade; ++j, ++idx) {
+            const long double c = x0 + (2 * j + 1) * w;
+            long double my[N], mg[N];
+            fit<N>(inv_r, c, w, my);
+            fit<N>(shape_g, c, w, mg);
+            double* o = out + idx * 2 * N;
+            for (int k = 0; k < N; ++k) {
+                o[k] = (double)ldexpl(my[k], -k * wexp);
+                o[N + k] = (double)ldexpl(mg[k], -k * wexp);
+            }
+        }
+    }
+    double* o = out + kInvTabConstRow * 2 * N;     // the plateau: r = rho, r' = 0 (metrics.rs:470, :482)
+    for (int k = 0; k < 2 * N; ++k) o[k] = 0.0;
+    o[0] = (double)(1.0L / rho_l);
+}
+
+double interstellar_table_l_limit(double m, double a) {
+    const double xscale = 2.0 / (3.14159265358979323846 * m);
+    return a + ldexp(1.0, kShapeTabEmax) * (1.0 - 0x1p-20) / xscale;
+}
+
 void build_interstellar_shape_table_f32(float* out) { build<kShapeTab32Degree + 1, float>(out, kShapeTab32K); }
 
 }  // namespace curvis
@@ -71,6 +117,37 @@ void build_interstellar_shape_table_f32(float* out) { build<kShapeTab32Degree + 
 // Test hook (include/curvis_gpu.h): the host-built table evaluated on the host exactly as the kernel
 // evaluates it (index from the high word, exact t, two fma Horner chains).  No GPU involved; it lets
 // the CPU test-suite check the generator.  Returns 0 when x is outside the table's range.
+// Test hook: the per-metric inverse table evaluated on the host exactly as FastInterstellar::prepare evaluates it
+// (x = fma(|l|, xscale, xoff) is the caller's business: this takes x).  y[i] = 1/(rho + m F(x)), g[i] = (2/pi) atan x;
+// x below 2^kInvTabEmin (or <= 0) reads the constant row.  Returns 1 when every x was below 2^kShapeTabEmax.
+extern "C" int curvis_debug_inverse_table_host(double rho, double m, const double* x, double* y, double* g, size_t n) {
+    using namespace curvis;
+    double* table = new double[kInvTabIntervals * kShapeTabDoubles];
+    build_interstellar_inverse_table(rho, m, table);
+    int all = 1;
+    for (size_t i = 0; i < n; ++i) {
+        unsigned long long bits;
+        __builtin_memcpy(&bits, &x[i], 8);
+        const unsigned hi = (unsigned)(bits >> 32);
+        unsigned idx = (hi >> kShapeTabShift) - kInvTabBase;
+        if (x[i] >= ldexp(1.0, kShapeTabEmax)) { y[i] = g[i] = NAN; all = 0; continue; }
+        if (idx > (unsigned)kInvTabConstRow) idx = (unsigned)kInvTabConstRow;
+        const unsigned long long cbits = (unsigned long long)((hi & ~((1u << kShapeTabShift) - 1u)) | (1u << (kShapeTabShift - 1))) << 32;
+        double c;
+        __builtin_memcpy(&c, &cbits, 8);
+        const double t = x[i] - c;
+        const double* a = table + (size_t)idx * kShapeTabDoubles;
+        double Y = a[kShapeTabDegree], G = a[kShapeTabDoubles - 1];
+        for (int k = kShapeTabDegree - 1; k >= 0; --k) {
+            Y = fma(t, Y, a[k]);
+            G = fma(t, G, a[kShapeTabDegree + 1 + k]);
+        }
+        y[i] = Y; g[i] = G;
+    }
+    delete[] table;
+    return all;
+}
+
 extern "C" int curvis_debug_shape_table_host(const double* x, double* f, double* g, size_t n) {
     using namespace curvis;
     static double* table = nullptr;

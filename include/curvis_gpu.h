@@ -391,6 +391,14 @@ int curvis_ctx_set_option(curvis_ctx* ctx, const char* key, int64_t value);
  *   15 / 16 the same two functions as CURVIS_PRECISION_F32 evaluates them (fp32 table; a is rounded to float)   */
 int curvis_debug_eval(curvis_ctx* ctx, int op, const double* a, const double* b, double* out, size_t n);
 
+/* Test hooks of the per-metric Interstellar table CURVIS_PRECISION_F64_FAST reads (csrc/shape_table.h): y[i] = 1/r =
+ * 1/(rho + m (x atan x - ln(1 + x^2)/2)), g[i] = (2/pi) atan x at x[i] = 2(|l| - a)/(pi m); every x below 2^-40 (zero and
+ * negative included: the plateau |l| <= a) reads the constant row y = 1/rho, g = 0.  _host: the table built and evaluated
+ * on the host with the kernel's arithmetic, no GPU needed (returns 1 when every x was below the table's end 2^16, else 0
+ * and NaN entries); the other evaluates on the context's first device. */
+int curvis_debug_inverse_table_host(double rho, double m, const double* x, double* y, double* g, size_t n);
+int curvis_debug_inverse_shape(curvis_ctx* ctx, const curvis_metric* metric, const double* x, double* y, double* g, size_t n);
+
 /* Test hook of kernel_variant 4 (the default CURVIS_PRECISION_F64 step: the six reciprocals of metrics.rs:257-262 from two
  * MUFU seeds and one correction step each): evaluates the right-hand side of n_samples pseudo-random photon states both
  * ways — shared reciprocals vs. the plain IEEE operators — and returns in mismatches[0..3] how many of the outputs

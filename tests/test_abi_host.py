@@ -175,3 +175,39 @@ def test_interstellar_shape_table_host(lib):
     fo, go = np.empty_like(out), np.empty_like(out)
     assert lib.curvis_debug_shape_table_host(out.ctypes.data_as(dp), fo.ctypes.data_as(dp), go.ctypes.data_as(dp), out.size) == 0
     assert np.isnan(fo).all() and np.isnan(go).all()
+
+
+@pytest.mark.parametrize("rho,m", [(1.0, 0.1), (2.5, 0.03), (0.7, 1.5)])
+def test_interstellar_inverse_table_host(lib, rho, m):
+    """The per-metric table the default fast kernel reads (csrc/shape_table.h: build_interstellar_inverse_table):
+    Y(x) = 1 / (rho + m F(x)) and G(x), evaluated on the host with the kernel's arithmetic, against x87 long double:
+    <= 2.5 ulp for 1/r (1/r behaves like 1/x, whose degree-5 interpolation error on 2^-7-wide intervals is ~2^-53), <= 2 ulp
+    for G; everything below 2^-40 — zero and negative x, the plateau |l| <= a of metrics.rs:470 / :482 — reads r = rho, r' = 0."""
+    import ctypes as C
+    import numpy as np
+    rng = np.random.default_rng(20261017)
+    edges = np.ldexp(1.0, np.arange(-40, 17))
+    x = np.concatenate([np.exp(rng.uniform(np.log(2.0 ** -40), np.log(2.0 ** 16), 400_000)),
+                        np.exp(rng.uniform(np.log(0.25), np.log(1024.0), 400_000)),
+                        edges[:-1], np.nextafter(edges[1:], 0.0), np.nextafter(edges[:-1], np.inf)])
+    y, g = np.empty_like(x), np.empty_like(x)
+    dp = C.POINTER(C.c_double)
+    assert lib.curvis_debug_inverse_table_host(rho, m, x.ctypes.data_as(dp), y.ctypes.data_as(dp), g.ctypes.data_as(dp), x.size) == 1
+    xl = x.astype(np.longdouble)
+    TWO_OVER_PI = np.longdouble(2) / (4 * np.arctan(np.longdouble(1)))
+    want_y = 1 / (np.longdouble(rho) + np.longdouble(m) * (xl * np.arctan(xl) - np.log1p(xl * xl) / 2))
+    want_g = TWO_OVER_PI * np.arctan(xl)
+
+    def ulps(got, want):
+        return np.abs((got.astype(np.longdouble) - want) / np.spacing(np.abs(want.astype(np.float64))).astype(np.longdouble)).astype(np.float64)
+
+    assert ulps(y, want_y).max() <= 2.5, ulps(y, want_y).max()
+    assert ulps(g, want_g).max() <= 2.0
+    low = np.array([0.0, -0.0, -1.0, -1e300, 2.0 ** -41, 5e-324])
+    yo, go = np.empty_like(low), np.empty_like(low)
+    assert lib.curvis_debug_inverse_table_host(rho, m, low.ctypes.data_as(dp), yo.ctypes.data_as(dp), go.ctypes.data_as(dp), low.size) == 1
+    assert (yo == 1.0 / rho).all() and (go == 0.0).all()
+    out = np.array([2.0 ** 16, 1e30])
+    yo, go = np.empty_like(out), np.empty_like(out)
+    assert lib.curvis_debug_inverse_table_host(rho, m, out.ctypes.data_as(dp), yo.ctypes.data_as(dp), go.ctypes.data_as(dp), out.size) == 0
+    assert np.isnan(yo).all()

@@ -93,11 +93,13 @@ def test_world_frame_matches_its_oracle(gpu_ctx, oracle, kind, frame_name):
         chaotic = classify.chaotic_mask(ref_rec)
         print(f"[{frame_name} {kind} precision {precision}] differing {int(bad.sum())} (regular {int((bad & ~chaotic).sum())}) of {W * H}")
         assert int((bad & ~chaotic).sum()) == 0
-        assert int(bad.sum()) <= 2
-    # the frame mode changes the lookup only: same photons
-    base = system.render_rows(*sim, 0, H, with_records=True)
-    for f in ("l", "theta", "phi", "p_l", "p_theta", "p_phi", "steps", "side"):
-        assert rec[f].tobytes() == base[1][f].tobytes() or precision != _abi.PRECISION_F64
+        # the rotation reads sin / cos of the END POSITION's theta and phi, which wander to 1e8 on kicked rays: CUDA's and
+        # glibc's reductions of such arguments agree to an ulp of the angle, i.e. ~1e-8 rad — enough to flip a texel now and then
+        assert int(bad.sum()) <= max(2, int(2e-3 * chaotic.sum())), (int(bad.sum()), int(chaotic.sum()))
+        if precision == _abi.PRECISION_F64:      # the frame mode changes the lookup only: same photons
+            base = system.render_rows(*sim, 0, H, with_records=True)
+            for f in ("l", "theta", "phi", "p_l", "p_theta", "p_phi", "steps", "side"):
+                assert rec[f].tobytes() == base[1][f].tobytes(), f
 
 
 def test_world_frame_central_column_carries_the_table_angle(gpu_ctx, oracle):

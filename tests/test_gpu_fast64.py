@@ -242,3 +242,24 @@ def test_fast64_rejects_rk4(gpu_ctx):
     with pytest.raises(cv.CurvisError) as e:
         sysm.render_image(10, 100.0, 0.05, precision=_abi.PRECISION_F64_FAST, integrator=_abi.INTEGRATOR_RK4)
     assert e.value.code == _abi.ERR_UNSUPPORTED
+
+
+def test_interstellar_inverse_table_on_device(gpu_ctx):
+    """The per-metric table of 1/r and r' that fast_variant 1 reads (csrc/shape_table.h): the device evaluation equals the
+    host evaluation of the same table bit for bit (tests/test_abi_host.py holds the host side to <= 2.5 ulp of long double),
+    and the table is rebuilt when the metric parameters change."""
+    import ctypes as C
+    import curvis_b200 as cv
+    from curvis_b200 import _abi
+    lib = _abi.load_library()
+    rng = np.random.default_rng(11)
+    x = np.concatenate([np.exp(rng.uniform(np.log(2.0 ** -40), np.log(2.0 ** 16), 500_000)), np.array([0.0, -1.0, 2.0 ** -41, 1e-300]),
+                        np.ldexp(1.0, np.arange(-40, 16))])
+    dp = C.POINTER(C.c_double)
+    for rho, m in ((1.0, 0.1), (2.0, 0.37), (1.0, 0.1)):
+        metric = cv.InterstellarMetric(m, 1e-4, rho)
+        y, g, hy, hg = (np.empty_like(x) for _ in range(4))
+        mc = metric.as_c()
+        _abi.check(lib.curvis_debug_inverse_shape(gpu_ctx.ptr, C.byref(mc), x.ctypes.data_as(dp), y.ctypes.data_as(dp), g.ctypes.data_as(dp), x.size), gpu_ctx.ptr)
+        assert lib.curvis_debug_inverse_table_host(rho, m, x.ctypes.data_as(dp), hy.ctypes.data_as(dp), hg.ctypes.data_as(dp), x.size) == 1
+        assert y.tobytes() == hy.tobytes() and g.tobytes() == hg.tobytes(), (rho, m)
