@@ -197,6 +197,95 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def strong_scaling(args, cv, system, sim, PREC, ctx, rank, n, local, dev, stream, dist, interleaved_rows, scenes, iters=5):
+    """ONE frame over N ranks (strong scaling).  Forms: `fused` = rows interleaved over the ranks, every pixel stored into
+    every rank's complete frame over NVLink by the render kernel, 4-byte all-reduce as the barrier; `nccl` = contiguous row
+    tiles + ONE ncclAllGather of the frame (what BASELINE configs[3] names).  Reference: the same frame rendered whole by one
+    rank (all ranks do it at once, max over ranks).  Device time (CUDA events), max over ranks, per frame."""
+    import torch
+    out = {}
+    token = torch.zeros(1, dtype=torch.int32, device=dev)
+    keep_camera = system.camera
+    for label, (Ws, Hs) in (("3840x2160", (3840, 2160)), ("7680x4320", (7680, 4320))):
+        if Hs % n:
+            continue
+        cam = cv.Camera(scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP, scenes.DEFAULT_FOCAL_LENGTH,
+                        scenes.DEFAULT_DIAGONAL, Ws, Hs)
+        system.camera = cam
+        fbytes = Ws * Hs * 3
+        rows = Hs // n
+        mine = cv.PeerBuffer.create(ctx, fbytes)
+        handles = [None] * n
+        dist.all_gather_object(handles, mine.handle)
+        bufs = [mine if r == rank else cv.PeerBuffer.open(ctx, handles[r], fbytes) for r in range(n)]
+        gathered = mine.as_tensor(local)
+        tile = torch.empty(rows * Ws * 3, dtype=torch.uint8, device=dev)
+        full = torch.empty(fbytes, dtype=torch.uint8, device=dev)
+        whole = torch.empty(fbytes, dtype=torch.uint8, device=dev)
+        r0, r1, stride = interleaved_rows(Hs, rank, n)
+
+        def fused():
+            system.render_frames_peers([cam], *sim, r0, r1, [b.ptr for b in bufs], stream.cuda_stream, row_stride=stride, precision=PREC)
+            dist.all_reduce(token)
+
+        def nccl():
+            system.render_rows_device(*sim, rank * rows, (rank + 1) * rows, tile.data_ptr(), stream.cuda_stream, precision=PREC)
+            dist.all_gather_into_tensor(full, tile)
+
+        def single():
+            system.render_rows_device(*sim, 0, Hs, whole.data_ptr(), stream.cuda_stream, precision=PREC)
+
+        def timed(fn):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1) / iters], dtype=torch.float64, device=dev)
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            return float(ms.item())
+
+        st = system.render_rows_device(*sim, 0, Hs, whole.data_ptr(), stream.cuda_stream, want_stats=True, precision=PREC)
+        steps = int(st["total_steps"])
+        kernel_single_ms = st["kernel_ms"]
+        t_single, t_fused, t_nccl = timed(single), timed(fused), timed(nccl)
+        # this rank's own kernel inside the split frame (the slowest rank bounds the frame)
+        kst = system.render_frames_peers([cam], *sim, r0, r1, [b.ptr for b in bufs], stream.cuda_stream, row_stride=stride, precision=PREC, want_stats=True)
+        kms = torch.tensor([kst["kernel_ms"]], dtype=torch.float64, device=dev)
+        kmax, kmin = kms.clone(), kms.clone()
+        dist.all_reduce(kmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kmin, op=dist.ReduceOp.MIN)
+        dist.all_reduce(token)
+        torch.cuda.synchronize()
+        bad = torch.stack([(gathered.view(-1, 3) != whole.view(-1, 3)).any(dim=1).sum(), (full.view(-1, 3) != whole.view(-1, 3)).any(dim=1).sum()]).to(torch.int64)
+        dist.all_reduce(bad)
+        out[label] = {
+            "ray_steps": steps, "one_rank_ms": t_single, "one_rank_kernel_ms": kernel_single_ms,
+            "fused_peer_stores": {"ms_per_frame": t_fused, "speedup": t_single / t_fused, "ray_steps_per_s": steps / (t_fused * 1e-3),
+                                  "rank_kernel_ms_max": float(kmax.item()), "rank_kernel_ms_min": float(kmin.item()),
+                                  "ideal_ms": t_single / n,
+                                  "limiter": "the slowest rank's persistent kernel (its drain tail does not shrink with the tile) + the "
+                                             "all-reduce barrier: ms_per_frame - rank_kernel_ms_max is the barrier, rank_kernel_ms_max - ideal_ms the tail/imbalance"},
+            "nccl_all_gather": {"ms_per_frame": t_nccl, "speedup": t_single / t_nccl, "ray_steps_per_s": steps / (t_nccl * 1e-3),
+                                "gather_bytes": fbytes},
+            "differing_pixels_vs_one_rank": {"fused": int(bad[0].item()), "nccl": int(bad[1].item()), "pixels_checked": n * Ws * Hs},
+        }
+        torch.cuda.synchronize()
+        del gathered
+        for r, b in enumerate(bufs):
+            if r != rank:
+                b.close()
+        dist.barrier()
+        mine.close()
+    system.camera = keep_camera
+    return out
+
+
 def oracle_parity(args, system, sim, strict_frame, fast_frame, fast_precision, n_rows=72):
     """Both kernels against the CPU oracle on `n_rows` rows spread over the frame (all host cores, records with the
     trajectory diagnostics), split into regular / chaotic rays by the survey's classifier (oracle/classify.py)."""
@@ -473,6 +562,12 @@ def run_b200(args):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = steps_per_job_step * args.steps / float(e2e_s.item())
 
+    # ---- strong scaling (BASELINE configs[3] and north_star's ">= 6x at 8 GPUs" for ONE frame): one 4K and one 8K Ellis frame
+    # at the default settings split over the N ranks, both exchange forms, against the same frame rendered whole by one rank
+    strong = None
+    if n > 1:
+        strong = strong_scaling(args, cv, system, sim, PREC, ctx, rank, n, local, dev, stream, dist, interleaved_rows, scenes)
+
     if peers_mode:                                  # unmap the peers' buffers, then (after everybody has) free this rank's
         torch.cuda.synchronize()
         frames[:] = []
@@ -647,6 +742,7 @@ def run_b200(args):
                 "note": ("backgrounds are part of the scene (`&self`, uploaded once: %.1f ms); per-frame input = metric+camera+sim structs; " % background_upload_ms) +
                         ("the RGB8 frame lands in a caller buffer registered once with curvis_host_register (the kernel stores into it over PCIe)"
                          if n == 1 else "every rank renders its tiles of the N frames into all ranks' frame buffers, rank r copies complete frame r to its pinned host buffer (DMA under the next render)")},
+        "strong_scaling": strong,
         "gather": (args.gather if n > 1 else None),
         "gather_check": gather_check,
         "e2e_pageable": e2e_pageable,

@@ -23,7 +23,9 @@ def interleaved_rows(height: int, rank: int, world: int) -> Tuple[int, int, int]
     (throat-grazing) rays; a contiguous tile of central rows holds ~3 % more Euler steps than the mean."""
     if world < 1 or not (0 <= rank < world):
         raise ValueError("rank/world out of range")
-    return rank, height, world
+    # more ranks than rows: the surplus ranks own an EMPTY tile (row_begin == row_end), like row_tile — a begin beyond the
+    # end would be rejected by the library and leave the other ranks waiting at the step barrier
+    return min(rank, height), height, world
 
 
 def frame_offset(frame: int, row: int, height: int, width: int) -> int:

@@ -22,10 +22,36 @@ from . import _abi
 from .systems import Context, RelativisticSystem
 
 
+def _to_u8(samples: np.ndarray) -> np.ndarray:
+    """16-bit samples to 8 bits the way the `image` crate converts a pixel (image 0.25: (x + 128) / 257, i.e. rounding
+    x * 255 / 65535), which is what DynamicImage::get_pixel returns for a 16-bit image."""
+    return ((samples.astype(np.uint32) + 128) // 257).astype(np.uint8)
+
+
 def load_image(path: str) -> np.ndarray:
-    """images.rs:7-11 + what DynamicImage::get_pixel yields (:107-111): RGBA8 texels."""
+    """images.rs:7-11 + what DynamicImage::get_pixel yields (:107-111): RGBA8 texels.  8-bit images go through PIL's
+    RGBA conversion (the same bytes the `image` crate hands out).  16-bit images are converted explicitly with the crate's
+    rounding — PIL's own conversion of "I;16" clips to 255 and of 16-bit RGB truncates to the high byte, which would put
+    texels one level (or, for 16-bit grey, everything) off the reference's."""
     from PIL import Image
     with Image.open(path) as im:
+        if im.mode in ("I;16", "I;16L", "I;16B", "I;16N", "I"):          # 16-bit greyscale (PIL loads some as 32-bit "I")
+            g = np.asarray(im)
+            if g.dtype.itemsize > 2 and int(g.max(initial=0)) > 65535:
+                raise ValueError(f"{path}: greyscale samples beyond 16 bits are not supported")
+            g8 = _to_u8(g.astype(np.uint32))
+            out = np.empty(g8.shape + (4,), dtype=np.uint8)
+            out[..., 0] = out[..., 1] = out[..., 2] = g8
+            out[..., 3] = 255
+            return np.ascontiguousarray(out)
+        arr = np.asarray(im)
+        if arr.dtype == np.uint16:                                        # 16-bit RGB / RGBA (e.g. decoded by a plugin)
+            a8 = _to_u8(arr)
+            if a8.ndim == 2:
+                a8 = np.repeat(a8[..., None], 3, axis=2)
+            if a8.shape[2] == 3:
+                a8 = np.concatenate([a8, np.full(a8.shape[:2] + (1,), 255, dtype=np.uint8)], axis=2)
+            return np.ascontiguousarray(a8[..., :4])
         return np.ascontiguousarray(np.asarray(im.convert("RGBA"), dtype=np.uint8))
 
 

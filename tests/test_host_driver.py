@@ -116,3 +116,33 @@ def test_cli_errors_exit_1(capsys):
     assert "not found" in capsys.readouterr().err
     assert main([]) == 1
     assert main(["custom"]) == 1
+
+
+def test_load_image_converts_16_bit_like_the_image_crate(tmp_path):
+    """DynamicImage::get_pixel on a 16-bit image returns (x + 128) / 257 per sample (image 0.25); PIL's own conversions clip
+    ("I;16") or truncate (16-bit RGB) instead."""
+    import numpy as np
+    from PIL import Image
+    from curvis_b200.rendering import load_image
+    g = (np.arange(6 * 8, dtype=np.uint32).reshape(6, 8) * 1371 % 65536).astype(np.uint16)
+    g[0, :4] = [0, 127, 128, 65535]
+    Image.fromarray(g).save(tmp_path / "g16.png")
+    got = load_image(str(tmp_path / "g16.png"))
+    want = ((g.astype(np.uint32) + 128) // 257).astype(np.uint8)
+    assert got.shape == (6, 8, 4) and (got[..., 3] == 255).all()
+    for c in range(3):
+        assert (got[..., c] == want).all()
+    rgb = np.random.default_rng(3).integers(0, 256, (5, 7, 3), dtype=np.uint8)
+    Image.fromarray(rgb).save(tmp_path / "rgb8.png")
+    got8 = load_image(str(tmp_path / "rgb8.png"))
+    assert (got8[..., :3] == rgb).all() and (got8[..., 3] == 255).all()
+
+
+def test_shipped_camera_paths_are_the_reference_files():
+    """paths/path_through.csv and path_orbit.csv are INPUT DATA of BASELINE config 5: shipped byte for byte (round 1
+    regenerated them with numpy and 0.33 % of the entries differed in the last bit)."""
+    import hashlib
+    import os
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "curvis_b200", "paths")
+    sums = {f: hashlib.sha256(open(os.path.join(root, f), "rb").read()).hexdigest() for f in ("path_through.csv", "path_orbit.csv")}
+    assert sums == {"path_through.csv": "747b87a2179125188d3cae3f79cace8571aaaa76ebf3b1f27f18f6a9d0e9ac3d", "path_orbit.csv": "fe3872182c0743643b358bbdc0128145a862a7e54db3bbcf23823ffefec3b5ed"}

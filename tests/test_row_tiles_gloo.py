@@ -81,6 +81,11 @@ def test_interleaved_rows_partition():
             owned = [list(range(*interleaved_rows(H, r, world))) for r in range(world)]
             assert sorted(sum(owned, [])) == list(range(H))
             assert max(len(o) for o in owned) - min(len(o) for o in owned) <= 1
+    # more ranks than rows: the surplus ranks own an empty tile whose bounds the library accepts (row_begin <= row_end <= H)
+    for H, world in ((1, 8), (3, 8), (5, 7)):
+        owned = [interleaved_rows(H, r, world) for r in range(world)]
+        assert all(b <= e <= H for b, e, _ in owned)
+        assert sorted(sum((list(range(*o)) for o in owned), [])) == list(range(H))
     assert frame_offset(0, 0, 2160, 3840) == 0 and frame_offset(2, 5, 2160, 3840) == (2 * 2160 + 5) * 3840 * 3
     with pytest.raises(ValueError):
         interleaved_rows(10, 3, 3)
