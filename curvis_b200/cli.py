@@ -42,6 +42,12 @@ def get_cli() -> argparse.ArgumentParser:
     vid.add_argument("-v", "--video-settings", dest="video_settings")
     vid.add_argument("--frames", type=int, default=None, help="render only the first N frames")
     vid.add_argument("--corrected-interpolation", action="store_true")
+    vid.add_argument("--sharding", choices=["frames", "rows"], default="frames",
+                     help="several --devices: frames = frame i rendered whole by device i mod N (default); rows = every frame "
+                          "row-interleaved over the devices")
+    vid.add_argument("--encoder-threads", type=int, default=8)
+    vid.add_argument("--compress-level", type=int, default=3, help="PNG deflate level of the written frames")
+    vid.add_argument("--no-write", action="store_true", help="render without writing PNG files (timing)")
     subs.add_parser("custom")
     return ap
 
@@ -77,8 +83,9 @@ def main(argv=None) -> int:
         out = _output_folder(args.output_folder)
         metric = instantiate_metric(S.metric_settings_from_file(args.metric_settings))
         camera, simulation = _load(S.CameraSettings, args.camera_settings), _load(S.SimulationSettings, args.simulation_settings)
-        ctx = Context([int(d) for d in args.devices.split(",")] if args.devices else None)
+        devices = [int(d) for d in args.devices.split(",")] if args.devices else None
         if args.command == "image":
+            ctx = Context(devices)
             image = _load(S.ImageSettings, args.image_settings)
             settings = ImageRenderingSettings.from_settings(bg1, bg2, out, image, camera, simulation)
             path = ImageRenderingSystem(metric, settings, context=ctx, renderer=args.renderer, precision=args.precision).render()
@@ -86,9 +93,17 @@ def main(argv=None) -> int:
         else:
             video = _load(S.VideoSettings, args.video_settings)
             settings = VideoRenderingSettings.from_settings(bg1, bg2, out, video, camera, simulation)
-            system = VideoRenderingSystem(metric, settings, context=ctx, renderer=args.renderer,
+            system = VideoRenderingSystem(metric, settings, renderer=args.renderer, devices=devices, sharding=args.sharding,
                                           corrected_interpolation=args.corrected_interpolation, precision=args.precision)
-            print(f"Frames in {system.render(max_frames=args.frames)}")
+            try:
+                folder = system.render(max_frames=args.frames, encoder_threads=args.encoder_threads, compress_level=args.compress_level,
+                                       write_frames=not args.no_write)
+            finally:
+                if system.last_render_info:
+                    info = system.last_render_info
+                    print(f"{info['frames']} frames on {info['devices']} device(s) in {info['wall_s']:.2f} s "
+                          f"({info['frames_per_s']:.1f} frames/s, PNG {'written' if info['png_written'] else 'not written'})")
+            print(f"Frames in {folder}")
         return 0
     except Exception as e:                                          # main.rs:219-227: print the error, exit 1
         print(f"Error: {e}", file=sys.stderr)

@@ -656,6 +656,27 @@ extern "C" int curvis_render_rows(curvis_ctx* ctx, const curvis_metric* metric,
     return CURVIS_OK;
 }
 
+// One device's share of a frame whose rows are INTERLEAVED over the context's devices: rows row_begin, row_begin + stride, ...
+// (n_rows of them).  d_frame != nullptr: the kernel stores every pixel at its place in that complete frame (a mapped host
+// frame: zero copy); else the rows go, packed, to d_out_packed.
+static int enqueue_rows_strided(curvis_ctx* ctx, DeviceState& d, const curvis_metric* metric, const curvis_camera* cam, const curvis_sim* sim,
+                                uint32_t row_begin, uint32_t stride, uint32_t n_rows, uint8_t* d_out_packed, uint8_t* d_frame, cudaStream_t stream) {
+    CURVIS_CUDA(ctx, launch_fence(d, stream));
+    int rc = ensure_float_backgrounds(ctx, d, sim, stream);
+    if (rc != CURVIS_OK) return rc;
+    if ((rc = ensure_redo(ctx, d, sim, (size_t)n_rows * cam->resolution_width)) != CURVIS_OK) return rc;
+    if ((rc = ensure_inverse_table(ctx, d, metric, sim, stream)) != CURVIS_OK) return rc;
+    FrameParams p;
+    fill_params(ctx, d, metric, cam, sim, row_begin, row_begin + n_rows, d_frame ? nullptr : d_out_packed, nullptr, p);
+    p.row_stride = stride;
+    if (d_frame) { p.n_peers = 1; p.out_peers[0] = d_frame; }
+    CURVIS_CUDA(ctx, cudaMemsetAsync(d.d_counters, 0, sizeof(DeviceCounters), stream));
+    CURVIS_CUDA(ctx, cudaEventRecord(d.ev_begin, stream));
+    if (n_rows) CURVIS_CUDA(ctx, launch_render(p, metric, sim, ctx->tuning, d.sm_count, stream));
+    CURVIS_CUDA(ctx, cudaEventRecord(d.ev_end, stream));
+    return CURVIS_OK;
+}
+
 extern "C" int curvis_render_image(curvis_ctx* ctx, const curvis_metric* metric,
                                    const curvis_camera* camera, const curvis_sim* sim,
                                    uint8_t* out_rgb8, curvis_stats* stats) {
@@ -666,9 +687,44 @@ extern "C" int curvis_render_image(curvis_ctx* ctx, const curvis_metric* metric,
     const uint32_t W = camera->resolution_width, H = camera->resolution_height;
     const size_t n = ctx->devs.size();
     const bool direct = ctx->is_registered(out_rgb8, (size_t)W * H * 3);
-    // Row tiles: device g renders rows [g*H/n, (g+1)*H/n) — every pixel is independent
-    // (systems.rs:316-326 carries no state between iterations), so no exchange is needed:
-    // each device copies its tile straight into its slice of the host frame.
+    if (n > 1) {
+        // Several devices: rows INTERLEAVED (device g renders rows g, g + n, ...), so every device gets the same mix of
+        // short and long rays (a contiguous tile of central rows carries ~3 % more steps than the mean).
+        // Every pixel is independent (systems.rs:316-326), so no exchange is needed: into a registered frame the kernels store
+        // their pixels in place; otherwise each device's packed rows are scattered by one strided copy.
+        for (size_t g = 0; g < n; ++g) {
+            DeviceState& d = ctx->devs[g];
+            d.row_begin = (uint32_t)g;
+            d.row_end = (g < H) ? (uint32_t)((H - g + n - 1) / n) : 0u;      // here: the NUMBER of rows of this device
+            const size_t bytes = (size_t)d.row_end * W * 3;
+            CURVIS_CUDA(ctx, cudaSetDevice(d.ordinal));
+            const bool in_place = direct && ctx->tuning.zero_copy;
+            uint8_t* d_frame = nullptr;
+            if (in_place) CURVIS_CUDA(ctx, cudaHostGetDevicePointer((void**)&d_frame, out_rgb8, 0));
+            else if ((rc = ensure_capacity(ctx, d, bytes + 1, 0, false)) != CURVIS_OK) return rc;
+            rc = enqueue_rows_strided(ctx, d, metric, camera, sim, d.row_begin < H ? d.row_begin : H, (uint32_t)n, d.row_end, d.d_out, d_frame, d.stream);
+            if (rc != CURVIS_OK) return rc;
+            CURVIS_CUDA(ctx, cudaMemcpyAsync(d.h_counters, d.d_counters, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, d.stream));
+            if (bytes && !in_place)
+                CURVIS_CUDA(ctx, cudaMemcpy2DAsync(out_rgb8 + g * (size_t)W * 3, n * (size_t)W * 3, d.d_out, (size_t)W * 3, (size_t)W * 3, d.row_end,
+                                                   cudaMemcpyDeviceToHost, d.stream));
+        }
+        if (stats) std::memset(stats, 0, sizeof *stats);
+        for (size_t g = 0; g < n; ++g) {
+            DeviceState& d = ctx->devs[g];
+            CURVIS_CUDA(ctx, cudaSetDevice(d.ordinal));
+            CURVIS_CUDA(ctx, cudaStreamSynchronize(d.stream));
+            if (stats) {
+                add_counters(*d.h_counters, (uint64_t)d.row_end * W, stats);
+                float ms = 0.f;
+                CURVIS_CUDA(ctx, cudaEventElapsedTime(&ms, d.ev_begin, d.ev_end));
+                if (ms > stats->kernel_ms) stats->kernel_ms = ms;
+            }
+        }
+        if (stats) stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        return CURVIS_OK;
+    }
+    // One device: the whole frame, straight into a registered caller frame or through the pinned staging buffer.
     for (size_t g = 0; g < n; ++g) {
         DeviceState& d = ctx->devs[g];
         d.row_begin = (uint32_t)((uint64_t)H * g / n);

@@ -177,10 +177,14 @@ class ImageRenderingSystem:
 
 
 class VideoRenderingSystem:
-    """rendering.rs:170-327."""
+    """rendering.rs:170-327.  Extensions (absent from the single-threaded reference): ``devices`` — CUDA ordinals the frames
+    are spread over; ``sharding`` — "frames" (default for more than one device: frame i is rendered whole by device
+    i mod N, one context, host thread and pinned frame ring per device, no exchange at all) or "rows" (every frame
+    row-interleaved over the devices of ONE context by curvis_render_image)."""
 
     def __init__(self, metric, settings: VideoRenderingSettings, context: Optional[Context] = None, renderer: str = "efficient",
-                 corrected_interpolation: bool = False, precision: str = "f64"):
+                 corrected_interpolation: bool = False, precision: str = "f64", devices: Optional[List[int]] = None,
+                 sharding: str = "frames"):
         self.video_rendering_settings = settings
         self.renderer = renderer
         self.precision = PRECISIONS[precision]
@@ -190,7 +194,17 @@ class VideoRenderingSystem:
         t0 = self.interpolator.min_time()
         camera = Camera(self.interpolator.camera_position(t0), self.interpolator.camera_forward(t0), self.interpolator.camera_up(t0),
                         settings.camera_focal_length, settings.camera_diagonal, settings.resolution_x, settings.resolution_y)
-        self.relativistic_system = RelativisticSystem(metric, image_1, image_2, camera, context=context)
+        if sharding not in ("frames", "rows"):
+            raise ValueError("sharding must be 'frames' or 'rows'")
+        self.sharding = sharding
+        if devices is not None and len(devices) > 1 and sharding == "frames" and context is None:
+            # one context (and later one host thread) per device: distinct contexts may run concurrently (curvis_gpu.h)
+            self.systems = [RelativisticSystem(metric, image_1, image_2, camera, context=Context([d])) for d in devices]
+        else:
+            ctx = context if context is not None else (Context(list(devices)) if devices else None)
+            self.systems = [RelativisticSystem(metric, image_1, image_2, camera, context=ctx)]
+        self.relativistic_system = self.systems[0]
+        self.last_render_info: Optional[dict] = None
 
     def times_of_frames(self) -> List[float]:                      # rendering.rs:224-238
         min_time, max_time = self.interpolator.min_time(), self.interpolator.max_time()
@@ -206,22 +220,33 @@ class VideoRenderingSystem:
         cam.update_position(self.interpolator.camera_position(t))
         cam.update_orientation(self.interpolator.camera_forward(t), self.interpolator.camera_up(t))
 
-    def render_frame(self) -> np.ndarray:
+    def camera_at(self, t: float) -> Camera:
+        """The camera update_camera(t) would leave behind, as a fresh object (frames in flight keep their own)."""
         s = self.video_rendering_settings
+        return Camera(self.interpolator.camera_position(t), self.interpolator.camera_forward(t), self.interpolator.camera_up(t),
+                      s.camera_focal_length, s.camera_diagonal, s.resolution_x, s.resolution_y)
+
+    def render_frame(self, system: Optional[RelativisticSystem] = None, out=None) -> np.ndarray:
+        s = self.video_rendering_settings
+        system = system if system is not None else self.relativistic_system
         if self.renderer == "per_pixel":
-            return self.relativistic_system.render_image(s.max_iterations_propagation, s.escape_radius, s.ray_integration_step,
-                                                         precision=self.precision)
-        return self.relativistic_system.render_image_efficient(
+            return system.render_image(s.max_iterations_propagation, s.escape_radius, s.ray_integration_step, out=out,
+                                       precision=self.precision)
+        return system.render_image_efficient(
             s.max_iterations_propagation, s.escape_radius, s.ray_integration_step, s.alphas_num, s.max_iterations_sampling,
             s.sampling_convergence_threshold_1,
             s.sampling_convergence_threshold_1,                     # rendering.rs:305-306 passes threshold_1 twice
-            precision=self.precision)
+            out=out, precision=self.precision)
 
-    def render(self, max_frames: Optional[int] = None, verbose: bool = True, encoder_threads: int = 8) -> str:
+    def render(self, max_frames: Optional[int] = None, verbose: bool = True, encoder_threads: int = 8, compress_level: int = 3,
+               write_frames: bool = True) -> str:
         """The frame loop of rendering.rs:258-327.  Rendering a 4K frame takes milliseconds on
         the GPU while its PNG encode takes a sizeable fraction of a second on one core, so frames
-        are handed to a pool of encoder threads (zlib releases the GIL) and the loop only waits
-        when ``2 * encoder_threads`` frames are in flight."""
+        are handed to a pool of encoder threads (zlib releases the GIL).  With several devices every device has its own
+        host thread, context and ring of page-locked frames; frame i goes to device i mod N.  Camera updates are evaluated
+        in frame order first: where the reference panics (its interpolator's last-frame bug, interpolation.rs:63-91) the
+        frames before that point are rendered and written, then the error is raised — what the reference leaves on disk."""
+        import time
         from concurrent.futures import ThreadPoolExecutor
         s = self.video_rendering_settings
         times = self.times_of_frames()
@@ -235,18 +260,58 @@ class VideoRenderingSystem:
         os.mkdir(tmp_folder)
         if verbose:
             print(f"Rendering {len(times)} frames...")
-        pending = []
-        with ThreadPoolExecutor(max_workers=max(1, encoder_threads)) as pool:
+        cameras, failure = [], None
+        for t in times:
             try:
-                for index, t in enumerate(times):
+                cameras.append(self.camera_at(t))                   # may raise on the last frame, like the reference panics
+            except Exception as e:                                  # noqa: BLE001 — re-raised below, after the frames before it
+                failure = e
+                break
+        n_dev = len(self.systems)
+        shape = (s.resolution_y, s.resolution_x, 3)
+        ring = 3                                                    # frames in flight per device (render, encode, encode)
+        t_start = time.perf_counter()
+        render_s = [0.0] * n_dev
+
+        def device_worker(g: int, pool) -> None:
+            system = self.systems[g]
+            buffers = [np.empty(shape, dtype=np.uint8) for _ in range(ring)]
+            for b in buffers:
+                system.context.register_host_buffer(b)              # the kernel stores its pixels straight into the frame
+            busy = [None] * ring
+            try:
+                for k, index in enumerate(range(g, len(cameras), n_dev)):
+                    slot = k % ring
+                    if busy[slot] is not None:
+                        busy[slot].result()                          # its previous frame has been encoded
                     if verbose:
                         print(f"Rendering frame {index + 1}/{len(times)}...")
-                    self.update_camera(t)                           # may raise on the last frame, like the reference panics
-                    frame = self.render_frame()
-                    pending.append(pool.submit(save_image, frame, os.path.join(tmp_folder, f"frame_{index}.png"), 3))
-                    while len(pending) > 2 * max(1, encoder_threads):
-                        pending.pop(0).result()
+                    system.camera = cameras[index]
+                    t0 = time.perf_counter()
+                    frame = self.render_frame(system, out=buffers[slot])
+                    render_s[g] += time.perf_counter() - t0
+                    busy[slot] = pool.submit(save_image, frame, os.path.join(tmp_folder, f"frame_{index}.png"), compress_level) \
+                        if write_frames else None
             finally:
-                for f in pending:
-                    f.result()
+                for f in busy:
+                    if f is not None:
+                        f.result()
+                for b in buffers:
+                    system.context.unregister_host_buffer(b)
+
+        with ThreadPoolExecutor(max_workers=max(1, encoder_threads)) as pool:
+            if n_dev == 1:
+                device_worker(0, pool)
+            else:
+                with ThreadPoolExecutor(max_workers=n_dev) as devices_pool:
+                    for f in [devices_pool.submit(device_worker, g, pool) for g in range(n_dev)]:
+                        f.result()
+        wall = time.perf_counter() - t_start
+        self.last_render_info = {"frames": len(cameras), "devices": n_dev, "sharding": self.sharding if n_dev > 1 or self.systems[0].context.device_count() > 1 else "single device",
+                                 "wall_s": wall, "frames_per_s": len(cameras) / wall if wall > 0 else None,
+                                 "render_s_per_device": render_s, "png_written": write_frames, "compress_level": compress_level}
+        if self.systems[0] is self.relativistic_system and cameras:
+            self.relativistic_system.camera = cameras[-1]           # where the reference's loop leaves the camera
+        if failure is not None:
+            raise failure
         return tmp_folder

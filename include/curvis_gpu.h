@@ -268,10 +268,16 @@ int curvis_host_unregister(curvis_ctx* ctx, void* ptr);
 
 /* ---- the hot path -------------------------------------------------------------------- */
 
-/* RelativisticSystem::render_image (src/systems.rs:307-330).  Renders the whole frame,
- * row-tiled over the context's devices, into the HOST buffer `out_rgb8`
- * (W*H*3 bytes, row-major: out[(y*W + x)*3 + c], the layout of DynamicImage::ImageRgb8).
- * `stats` may be NULL. */
+/* RelativisticSystem::render_image (src/systems.rs:307-330).  Renders the whole frame into the HOST buffer `out_rgb8`
+ * (W*H*3 bytes, row-major: out[(y*W + x)*3 + c], the layout of DynamicImage::ImageRgb8).  With several devices in the
+ * context the rows are interleaved over them (device g renders rows g, g + n, ...: equal work for every device; pixels are
+ * independent, so there is no exchange — each device stores or copies its rows to their places in the frame).
+ * `stats` may be NULL.
+ *
+ * One launch in flight per context: every launch of a context shares its per-device scratch (work-queue cursor, counters,
+ * batched cameras, re-integration list, timing events).  Launches passed the SAME stream are ordered by the stream; a launch
+ * on a different stream than the context's previous one first waits (cudaStreamWaitEvent) for that launch to finish.  Use
+ * one context per concurrent pipeline. */
 int curvis_render_image(curvis_ctx* ctx, const curvis_metric* metric,
                         const curvis_camera* camera, const curvis_sim* sim,
                         uint8_t* out_rgb8, curvis_stats* stats);

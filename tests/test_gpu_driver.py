@@ -75,3 +75,33 @@ def test_cli_video_frames(tmp_path, oracle):
         ref, _ = oracle.render_image_efficient(oracle.metric("interstellar"), ocam, oracle.sim(40000, 100.0, 0.05), bp, bn, 100, 100, 1e-5, 1e-5)
         got = np.asarray(Image.open(out / "tmp" / f"frame_{index}.png"))
         assert (got == ref).all(axis=2).mean() >= 0.999, index
+
+
+@pytest.mark.parametrize("sharding", ["frames", "rows"])
+def test_video_over_several_devices_through_the_product_api(tmp_path, sharding):
+    """VideoRenderingSystem(devices=[...]): the frame loop of rendering.rs:258-327 spread over the visible GPUs — frame
+    sharding (one context + host thread per device) or row sharding (one multi-device context) — writes the same PNGs as
+    one device.  With one visible GPU the device list is [0, 0]: two contexts on the same device still exercise the path."""
+    import torch
+    from PIL import Image
+    import curvis_b200 as cv
+    from curvis_b200 import settings as S
+    from curvis_b200.rendering import VideoRenderingSettings, VideoRenderingSystem
+    p1, p2, _, _ = _write_backgrounds(tmp_path)
+    n = torch.cuda.device_count()
+    devices = list(range(n)) if n >= 2 else ([0, 0] if sharding == "frames" else [0])
+    camera = S.CameraSettings.default()
+    camera.resolution_x, camera.resolution_y = 160, 90
+    video, simulation = S.VideoSettings.default(), S.SimulationSettings.default()
+    outs = {}
+    for label, devs in (("one", [0]), ("many", devices)):
+        out = tmp_path / f"video_{label}"
+        out.mkdir()
+        settings = VideoRenderingSettings.from_settings(p1, p2, str(out), video, camera, simulation)
+        system = VideoRenderingSystem(cv.InterstellarMetric(0.1, 1e-4, 1.0), settings, renderer="per_pixel", precision="f64_fast",
+                                      devices=devs, sharding=sharding)
+        folder = system.render(max_frames=7, verbose=False, encoder_threads=4)
+        assert system.last_render_info["frames"] == 7
+        outs[label] = [np.asarray(Image.open(os.path.join(folder, f"frame_{i}.png"))) for i in range(7)]
+    for a, b in zip(outs["one"], outs["many"]):
+        assert a.shape == (90, 160, 3) and (a == b).all()

@@ -265,6 +265,18 @@ def test_in_process_multi_device_frame(oracle):
     a = multi.render_image(40000, 100.0, 0.05)
     b = single.render_image(40000, 100.0, 0.05)
     assert (a == b).all() and multi.last_stats["total_steps"] == single.last_stats["total_steps"]
+    # a frame registered with curvis_host_register: every device's kernel stores its interleaved rows in place
+    from curvis_b200 import _abi
+    reg = np.zeros((H, W, 3), dtype=np.uint8)
+    multi.context.register_host_buffer(reg)
+    try:
+        for precision in (_abi.PRECISION_F64, _abi.PRECISION_F64_FAST):
+            reg[:] = 0
+            multi.render_image(40000, 100.0, 0.05, out=reg, precision=precision)
+            assert (reg == b).all(), precision
+            assert multi.last_stats["total_steps"] == single.last_stats["total_steps"] and multi.last_stats["n_rays"] == W * H
+    finally:
+        multi.context.unregister_host_buffer(reg)
     ref, _, _ = oracle.render_rows(oracle.metric("ellis"), oracle.camera(scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD,
                                    scenes.DEFAULT_UP, 15.0, 43.0, W, H), oracle.sim(40000, 100.0, 0.05), bp, bn, threads=os.cpu_count() or 1)
     assert (a == ref).all()
