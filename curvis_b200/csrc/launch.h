@@ -20,8 +20,9 @@ struct LaunchTuning {
                              // 0 = the raw regrouped kernel (A/B, tools/guard_study.py)
     double guard_rel = 1e-9; // relative state-error budget of a ray with stiffness < 1 (render_f64_fast.cu: guard_eps)
     int redo_blocks_per_sm = 2;   // CTAs per SM of the re-integration launch (a few per cent of the frame's rays: fewer, fuller warps)
-    int fast_regs = 96;      // CURVIS_PRECISION_F64_FAST register budget: 96 (5 CTAs per SM, 50-instruction step; measured 36.2 ms per 4K
-                             // Ellis frame) or 128 (4 CTAs, 47 instructions; 37.4 ms)
+    int fast_regs = 0;       // CURVIS_PRECISION_F64_FAST register budget: 96 (5 CTAs per SM; Ellis: 50-instruction step, 36.4 ms per 4K
+                             // frame) or 128 (4 CTAs; Ellis 47 instructions, 37.5 ms; Interstellar 71 instead of 76: 59.2 against
+                             // 60.2 ms); 0 (default) = 96 for Ellis / Flat, 128 for Interstellar
     int fast_variant = 1;    // CURVIS_PRECISION_F64_FAST: 0 sin/cos from theta every step; 1 (default) (sin, cos) carried and
                              // rotated by the step's small dtheta, re-derived from theta once per window
 };

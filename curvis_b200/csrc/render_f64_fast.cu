@@ -533,8 +533,9 @@ cudaError_t launch_fast(const FrameParams& p, const LaunchTuning& t, int sm_coun
     // variant 1 scales the momenta by delta: it needs a finite, non-zero step of ordinary magnitude
     const double ad = p.delta < 0.0 ? -p.delta : p.delta;
     if (t.fast_variant == 0 || !(ad >= 0x1p-100 && ad <= 0x1p100)) return launch_fast_variant<Fast, 0, 5>(p, sm_count, t.blocks_per_sm, stream);   // trigonometry from theta every step
-    if (t.fast_regs == 96) return launch_fast_variant<Fast, 1, 5>(p, sm_count, t.blocks_per_sm, stream);
-    return launch_fast_variant<Fast, 1, 4>(p, sm_count, t.blocks_per_sm, stream);                         // default: rotated (sin, cos)
+    const int regs = t.fast_regs ? t.fast_regs : (Fast::Shape64::kind == CURVIS_METRIC_INTERSTELLAR ? 128 : 96);
+    if (regs == 96) return launch_fast_variant<Fast, 1, 5>(p, sm_count, t.blocks_per_sm, stream);         // default: rotated (sin, cos)
+    return launch_fast_variant<Fast, 1, 4>(p, sm_count, t.blocks_per_sm, stream);
 }
 
 }  // namespace

@@ -374,7 +374,8 @@ int curvis_measure_fma_peak(curvis_ctx* ctx, double* fp64_tflops, double* fp32_t
  *   "guard":          CURVIS_PRECISION_F64_FAST: 1 (default) guard band + re-integration of the rays with stiffness < 1;
  *                     2 kicked rays (stiffness >= 1) re-integrated too; 0 the raw regrouped kernel (A/B)
  *   "guard_rel_e15":  the guard's relative budget in units of 1e-15 (default 1000000 = 1e-9)
- *   "fast_regs":      96 (default) / 128: register budget of the fast kernel (5 / 4 resident CTAs per SM)
+ *   "fast_regs":      96 / 128: register budget of the fast kernel (5 / 4 resident CTAs per SM); 0 (default) = 96 for
+ *                     Ellis and Flat, 128 for Interstellar (the measured optimum of each)
  *   "redo_blocks_per_sm": resident CTAs per SM of the re-integration launch (default 2)
  *   "blocks_per_sm":  resident CTAs per SM of the persistent grid (0 = occupancy maximum)
  *   "window":         Euler steps between two refill points of a warp (0 = default: 32; for

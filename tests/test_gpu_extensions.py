@@ -122,9 +122,14 @@ def test_world_frame_central_column_carries_the_table_angle(gpu_ctx, oracle):
         assert (side, steps) == (int(rec["side"][row, col]), int(rec["steps"][row, col]))
         if side == 0:
             continue
-        # compute_escape_angle's world direction is (cos angle, sin angle, .) / norm in the x-y plane: its azimuth is `angle`
-        fx = ((0.5 - angle / (2 * math.pi)) % 1.0) * 8192
-        dx = abs(int(rec["texel_x"][row, col]) - int(fx))
-        assert min(dx, 8192 - dx) <= 1, (row, angle, rec["texel_x"][row, col], fx)
+        # compute_escape_angle's `angle` is the 3-D angle between the world direction w and the x axis (systems.rs:246-251:
+        # acos of w.x after normalisation, mirrored for w.y < 0); the texel the GPU looked up gives w's azimuth and polar
+        # angle to half a texel: cos(angle) = cos(azimuth) sin(polar)
+        az = (0.5 - (int(rec["texel_x"][row, col]) + 0.5) / 8192.0) * 2 * math.pi
+        pol = (int(rec["texel_y"][row, col]) + 0.5) / 4096.0 * math.pi
+        got = math.acos(max(-1.0, min(1.0, math.cos(az) * math.sin(pol))))
+        if math.sin(az) < 0.0:
+            got = 2 * math.pi - got
+        assert abs(got - angle) <= 3 * (2 * math.pi / 8192), (row, angle, got)
         checked += 1
     assert checked >= 100
