@@ -79,8 +79,14 @@ static __device__ double kRotPinned[2] = {-0.00019839655223880117, 0.00042187738
 struct RotRegs {
     double sin2, tan2;                    // leading coefficients: vector registers (see kPinned)
     __device__ __forceinline__ void load() {
-        asm volatile("ld.global.f64 %0, [%1];" : "=d"(sin2) : "l"(kRotPinned));
-        asm volatile("ld.global.f64 %0, [%1];" : "=d"(tan2) : "l"(kRotPinned + 1));
+        // The address carries a per-thread zero the compiler cannot see through (the lane id times the top bit of the cycle counter), so the
+        // loads are not promoted to the uniform datapath: a coefficient living in a uniform register would force its
+        // partner constant into a vector register by two moves EVERY step (a DFMA takes one uniform operand).
+        unsigned lane_id;
+        asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane_id));
+        const unsigned long long zero = (unsigned long long)lane_id * ((unsigned long long)clock64() >> 63);
+        asm volatile("ld.global.f64 %0, [%1];" : "=d"(sin2) : "l"(kRotPinned + zero));
+        asm volatile("ld.global.f64 %0, [%1];" : "=d"(tan2) : "l"(kRotPinned + 1 + zero));
     }
 };
 

@@ -208,7 +208,9 @@ __device__ __forceinline__ void euler_step(const FrameParams& p, Ray& q) {
 // instead of one guard + branch each.  `ray_safe` carries the per-ray part of the check
 // (p_phi^2 and the frame parameters, constant along a ray).  Outside the window — rays grazing
 // the coordinate poles (sin theta -> 0), NaN/Inf states — the plain operators are used.
-__device__ __forceinline__ bool ray_operands_safe(const Ray& q) { return exponent_in(q.pph2, -200, 200); }
+// p_phi^2 == 0 exactly (the rays of the image's central row, fired along a meridian) is safe as well: every quotient it
+// enters is an exact zero in the unguarded sequences as in the plain operators.
+__device__ __forceinline__ bool ray_operands_safe(const Ray& q) { return exponent_in(q.pph2, -200, 200) || q.pph2 == 0.0; }
 
 template <class Shape, class Trig>
 __device__ __forceinline__ void euler_step_tuned(const FrameParams& p, Ray& q, bool ray_safe) {
