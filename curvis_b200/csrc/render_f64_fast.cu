@@ -213,14 +213,15 @@ __device__ __forceinline__ bool fast_step(const FrameParams& p, const TrigRegs& 
 //   * ONE exit branch per step: the four rarely-true conditions (step budget used up, |l| within reach
 //     of the escape radius or NaN, |dtheta| too large for the rotation, next divisor outside the safe
 //     window) are OR-ed on the integer pipe and sorted out after the loop.
-// Returns the number of steps taken; `near` = |l| came within reach of the escape radius (gate = the high word of
-// R - 3|delta|) or is NaN: the caller continues with single steps and the escape test of systems.rs:129-134, recording how
-// close every visited l came to +-R (the guard band of the step count); `slow` = the remaining steps of the window need
-// the parity step; `wmax_hi` = running maximum of the high word of w = 1/(r^2 sin^2 theta): (P_phi w)^2 is the stiffness
-// of curvis_ray_record.
+// Returns the number of steps taken; `near` = the last step took |l| to the radius gate (the high word of R: |l| within
+// 2^-20 R of the radius or beyond it; for Interstellar also the end of the shape table) or made it NaN: the caller runs the
+// escape test of systems.rs:129-134 and records how close the step came to +-R on either side — `last_b2`, `last_f` (the
+// factors of that step's p_l increment) let it reconstruct the l the step started from; `slow` = the remaining steps of
+// the window need the parity step; `wmax_hi` = running maximum of the high word of w = 1/(r^2 sin^2 theta): (P_phi w)^2 is
+// the stiffness of curvis_ray_record.
 template <class Fast>
 __device__ __forceinline__ uint32_t fast_window_scaled(const FrameParams& p, const RotRegs& rr, Ray& q, uint32_t n, unsigned gate,
-                                                       bool& near, bool& slow, unsigned& wmax_hi, double& wsum_out) {
+                                                       bool& near, bool& slow, unsigned& wmax_hi, double& wsum_out, double& last_b2, double& last_f) {
     uint32_t left = n;   // steps still allowed (a down-counter: one instruction per step)
     // phi += P_phi * w every step (:240): the w's are summed (a two-operand DADD issues faster than a DFMA with three
     // distinct registers) and folded into phi once, by the caller, when the window is left
@@ -247,6 +248,7 @@ __device__ __forceinline__ uint32_t fast_window_scaled(const FrameParams& p, con
             wmax_hi = max(wmax_hi, (unsigned)__double2hiint(w));   // stiffness monitor (w > 0: the high word orders it)
             q.pl = fma(b2, f, q.pl);                            // :261, :296
             q.pth = fma(pv * cs, w, q.pth);                     // :262
+            last_b2 = b2; last_f = f;                           // read after the loop only (the step that reached the radius)
             rotate_sincos(rr, dth, sn, cn);
             --left;
             asm("" : "+r"(left));   // one induction variable (the optimiser otherwise keeps two copies of the counter)
@@ -254,7 +256,7 @@ __device__ __forceinline__ uint32_t fast_window_scaled(const FrameParams& p, con
             d = Fast::prepare(p, q.l, s2, pre);
             if ((left == 0u) | (abs_hi(q.l) >= gate) | (abs_hi(dth) >= pow2_hi(-4)) | !in_window_nonneg(d)) break;
         }
-        if (abs_hi(q.l) >= gate) { near = true; break; }        // within three steps of the radius (or NaN): the caller's careful tail
+        if (abs_hi(q.l) >= gate) { near = true; break; }        // |l| >= R (1 - 2^-20), or past the shape table, or NaN: the caller's business
         if (left == 0u) break;
         if (!(abs_hi(dth) >= pow2_hi(-4)) && !in_window_nonneg(d)) { slow = true; break; }
         // |dtheta| too large for the rotation: re-derive (sin, cos) and go on
@@ -368,10 +370,10 @@ __global__ void __launch_bounds__(kBlockFast, MinBlocks) render_rows_f64_fast(co
     const unsigned long long tile_rays = (unsigned long long)(p.row_end - p.row_begin) * p.width;
     const unsigned long long launch_rays = tile_rays * (p.n_frames ? p.n_frames : 1u);
     const double R = p.max_radius;
-    // escape test: |l| > R needs abs_hi(l) >= hi(R) when R >= 0; for negative or NaN R the gate is open.  Variant 1 opens
-    // it three steps early (a photon moves ~|delta| per step) and walks the last steps one by one (see `near` below).
-    const double R_near = fmin(R - 3.0 * fabs(p.delta), p.fast_l_limit);   // (the Interstellar table's reach, else +inf)
-    const unsigned gate = (Variant == 1) ? ((R_near > 0.0) ? abs_hi(R_near) : 0u) : ((R >= 0.0) ? abs_hi(R) : 0u);
+    // escape test: |l| > R needs abs_hi(l) >= hi(R) when R >= 0; for negative or NaN R the gate is open.  Variant 1 also
+    // closes it at the end of the Interstellar shape table (+inf for the other metrics).
+    const double R_gate = (Variant == 1) ? fmin(R, p.fast_l_limit) : R;
+    const unsigned gate = (R_gate >= 0.0) ? abs_hi(R_gate) : 0u;
     const bool guard = (Variant == 1) && p.redo_list != nullptr;
     const float finf = __int_as_float(0x7f800000);
 
@@ -459,35 +461,26 @@ __global__ void __launch_bounds__(kBlockFast, MinBlocks) render_rows_f64_fast(co
                 } while (k < n);
             }
             if (!slow && Variant == 1) {
-                bool near = abs_hi(q.l) >= gate;   // still inside the three-step zone when the previous window ended
-                double wsum = 0.0;
-                if (!near) k = fast_window_scaled<Fast>(p, rr, q, n, gate, near, slow, wmax_hi, wsum);
-                if (near) {
-                    // The last steps before the radius, one at a time: escape test after every step (systems.rs:129-134),
-                    // and the distance of every l visited here to +-R goes into `margin`.  A ray that arrives already
-                    // outside (it jumped the three-step zone, or started in it) has an unknown margin: 0.
-                    float margin = cold.margin;
-                    if ((q.l > R) || (q.l < -R) || (q.l != q.l)) { stop = true; margin = 0.f; }
-                    while (!stop && !slow && k < n) {
-                        if (Fast::beyond(p, q.l)) { slow = true; break; }         // past the shape table: parity steps
-                        const double before = R - fabs(q.l);
-                        bool unused = false;
-                        double w1 = 0.0;
-                        const uint32_t one = fast_window_scaled<Fast>(p, rr, q, 1u, 0xffffffffu, unused, slow, wmax_hi, w1);
-                        if (one == 0) break;                                       // the step needs the parity arithmetic
-                        wsum = wsum + w1;
-                        ++k;
-                        const double after = fabs(q.l) - R;
-                        if (q.l != q.l) { stop = true; margin = 0.f; }
-                        else if (after > 0.0) { stop = true; margin = fminf(margin, __double2float_rd(fmin(before, after))); }
-                        else {
-                            margin = fminf(margin, __double2float_rd(-after));
-                            if (abs_hi(q.l) < gate) break;                         // left the zone inwards: back to the fast loop
-                        }
-                    }
-                    cold.margin = margin;
-                }
+                bool near = false;
+                double wsum = 0.0, b2 = 0.0, f = 0.0;
+                k = fast_window_scaled<Fast>(p, rr, q, n, gate, near, slow, wmax_hi, wsum, b2, f);
                 cold.ph = fma(cold.pph, wsum, cold.ph);                            // :240 for every step of the window
+                if (near) {
+                    // The step just taken brought |l| to the radius gate.  Escape test (systems.rs:129-134), and the guard
+                    // band of the step count: how far the step landed beyond +-R, and how far inside it started —
+                    // l_before = l - P_l_before, P_l_before = P_l - b2 f (the fma of :261 undone to an ulp).  A step that
+                    // ends inside the gate's sliver (|l| in [R (1 - 2^-20), R]) records its distance and goes on.
+                    const double after = fabs(q.l) - R;
+                    if (q.l != q.l) { stop = true; cold.margin = 0.f; }
+                    else if (after > 0.0) {
+                        const double before = R - fabs(q.l - (q.pl - b2 * f));
+                        stop = true;
+                        cold.margin = fminf(cold.margin, __double2float_rd(fmin(before, after)));
+                    } else {
+                        cold.margin = fminf(cold.margin, __double2float_rd(-after));
+                        if (Fast::beyond(p, q.l)) slow = true;                     // past the shape table: parity steps
+                    }
+                }
             }
             if (slow) {
                 if (Variant == 1) { cold.margin = 0.f; q.ph = cold.ph; q.pph = cold.pph; }   // a ray that needed parity steps is re-integrated whole
