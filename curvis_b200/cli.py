@@ -29,6 +29,13 @@ def _common(sub):
                      help="f64 = one rounding per reference operation; f64_fast = the same fp64 Euler iteration regrouped for the "
                           "GPU (3x faster, same frames); f32 = fp32 right-hand side (per_pixel renderer only)")
     sub.add_argument("--devices", default=None, help="comma-separated CUDA ordinals (default: all visible)")
+    sub.add_argument("--frame", choices=["local", "world", "world_quirk"], default="local",
+                     help="per_pixel renderer: local = render_image as written (systems.rs:540-561); world = escaped_photon_to_world_direction "
+                          "(systems.rs:144-187) with frame_field_33; world_quirk = the same rotation with metrics.rs:347 as written")
+    sub.add_argument("--coordinates", choices=["spherical", "cartesian"], default="spherical",
+                     help="per_pixel renderer: cartesian = chart-free angular state, no coordinate poles (f64 only)")
+    sub.add_argument("--integrator", choices=["euler", "rk4", "euler_adaptive"], default="euler", help="per_pixel renderer, f64 only")
+    sub.add_argument("--step-tolerance", type=float, default=0.01, help="euler_adaptive: largest azimuth / polar advance of one step")
 
 
 def get_cli() -> argparse.ArgumentParser:
@@ -50,6 +57,23 @@ def get_cli() -> argparse.ArgumentParser:
     vid.add_argument("--no-write", action="store_true", help="render without writing PNG files (timing)")
     subs.add_parser("custom")
     return ap
+
+
+def _sim_options(args) -> dict:
+    """The curvis_sim extension fields (include/curvis_gpu.h) of the per-pixel renderer; all defaults = the reference."""
+    from . import _abi
+    opts = {}
+    if args.frame != "local":
+        opts["frame"] = {"world": _abi.FRAME_WORLD, "world_quirk": _abi.FRAME_WORLD_QUIRK}[args.frame]
+    if args.coordinates == "cartesian":
+        opts["coordinates"] = _abi.COORDINATES_CARTESIAN
+    if args.integrator != "euler":
+        opts["integrator"] = {"rk4": _abi.INTEGRATOR_RK4, "euler_adaptive": _abi.INTEGRATOR_EULER_ADAPTIVE}[args.integrator]
+        if args.integrator == "euler_adaptive":
+            opts["step_tolerance"] = args.step_tolerance
+    if opts and args.renderer != "per_pixel":
+        raise S.SettingsError("--frame / --coordinates / --integrator belong to --renderer per_pixel")
+    return opts
 
 
 def _existing(path: str) -> str:
@@ -88,13 +112,15 @@ def main(argv=None) -> int:
             ctx = Context(devices)
             image = _load(S.ImageSettings, args.image_settings)
             settings = ImageRenderingSettings.from_settings(bg1, bg2, out, image, camera, simulation)
-            path = ImageRenderingSystem(metric, settings, context=ctx, renderer=args.renderer, precision=args.precision).render()
+            path = ImageRenderingSystem(metric, settings, context=ctx, renderer=args.renderer, precision=args.precision,
+                                        sim_options=_sim_options(args)).render()
             print(f"Saved {path}")
         else:
             video = _load(S.VideoSettings, args.video_settings)
             settings = VideoRenderingSettings.from_settings(bg1, bg2, out, video, camera, simulation)
             system = VideoRenderingSystem(metric, settings, renderer=args.renderer, devices=devices, sharding=args.sharding,
-                                          corrected_interpolation=args.corrected_interpolation, precision=args.precision)
+                                          corrected_interpolation=args.corrected_interpolation, precision=args.precision,
+                                          sim_options=_sim_options(args))
             try:
                 folder = system.render(max_frames=args.frames, encoder_threads=args.encoder_threads, compress_level=args.compress_level,
                                        write_frames=not args.no_write)

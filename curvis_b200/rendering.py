@@ -147,10 +147,11 @@ class ImageRenderingSystem:
     """rendering.rs:20-117."""
 
     def __init__(self, metric, settings: ImageRenderingSettings, context: Optional[Context] = None, renderer: str = "efficient",
-                 precision: str = "f64"):
+                 precision: str = "f64", sim_options: Optional[dict] = None):
         self.image_rendering_settings = settings
         self.renderer = renderer
         self.precision = PRECISIONS[precision]
+        self.sim_options = dict(sim_options or {})     # curvis_sim extensions of the per-pixel renderer (frame, coordinates, ...)
         image_1 = load_image_as_spherical_image(settings.path_to_background_image_1)
         image_2 = load_image_as_spherical_image(settings.path_to_background_image_2)
         camera = Camera(settings.camera_position, settings.camera_forward, settings.camera_up, settings.camera_focal_length,
@@ -161,7 +162,7 @@ class ImageRenderingSystem:
         s = self.image_rendering_settings
         if self.renderer == "per_pixel":
             return self.relativistic_system.render_image(s.max_iterations_propagation, s.escape_radius, s.ray_integration_step,
-                                                         precision=self.precision)
+                                                         precision=self.precision, **self.sim_options)
         return self.relativistic_system.render_image_efficient(
             s.max_iterations_propagation, s.escape_radius, s.ray_integration_step, s.alphas_num, s.max_iterations_sampling,
             s.sampling_convergence_threshold_1, s.sampling_convergence_threshold_2, precision=self.precision)
@@ -184,10 +185,11 @@ class VideoRenderingSystem:
 
     def __init__(self, metric, settings: VideoRenderingSettings, context: Optional[Context] = None, renderer: str = "efficient",
                  corrected_interpolation: bool = False, precision: str = "f64", devices: Optional[List[int]] = None,
-                 sharding: str = "frames"):
+                 sharding: str = "frames", sim_options: Optional[dict] = None):
         self.video_rendering_settings = settings
         self.renderer = renderer
         self.precision = PRECISIONS[precision]
+        self.sim_options = dict(sim_options or {})
         self.interpolator = Interpolator.from_file(settings.filepath_to_camera_path, corrected=corrected_interpolation)
         image_1 = load_image_as_spherical_image(settings.filepath_to_background_image_1)
         image_2 = load_image_as_spherical_image(settings.filepath_to_background_image_2)
@@ -231,7 +233,7 @@ class VideoRenderingSystem:
         system = system if system is not None else self.relativistic_system
         if self.renderer == "per_pixel":
             return system.render_image(s.max_iterations_propagation, s.escape_radius, s.ray_integration_step, out=out,
-                                       precision=self.precision)
+                                       precision=self.precision, **self.sim_options)
         return system.render_image_efficient(
             s.max_iterations_propagation, s.escape_radius, s.ray_integration_step, s.alphas_num, s.max_iterations_sampling,
             s.sampling_convergence_threshold_1,

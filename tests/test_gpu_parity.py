@@ -380,3 +380,39 @@ def test_fused_render_and_gather_into_peer_buffers(gpu_ctx):
     finally:
         for b in bufs:
             b.close()
+
+
+def test_launches_on_two_streams_of_one_context_do_not_race(gpu_ctx):
+    """The asynchronous entry points accept any caller stream but share the context's per-device scratch (work-queue cursor,
+    counters, batched cameras, re-integration list).  A launch on a different stream than the previous one waits for it
+    (curvis_gpu.h: one launch in flight per context), so alternating streams renders the same frames as one stream."""
+    import torch
+    import curvis_b200 as cv
+    from curvis_b200 import _abi, scenes
+    W, H, sim = 640, 360, (40000, 100.0, 0.05)
+    bp, bn = scenes.noise_background(1024, 512, 5), scenes.noise_background(1024, 512, 6)
+    cams = [cv.Camera((0.0, 5.0 + 0.3 * f, 1.3 + 0.05 * f, 0.2 * f), (-1.0, 0.1 * f, 0.05), (0.0, 0.0, 1.0), 15.0, 43.0, W, H) for f in range(4)]
+    system = cv.RelativisticSystem(cv.EllisMetric(1.0), cv.SphericalImage(bp), cv.SphericalImage(bn), cams[0], context=gpu_ctx)
+    dev = torch.device("cuda", 0)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    for precision in (_abi.PRECISION_F64, _abi.PRECISION_F64_FAST):
+        want = []
+        for cam in cams:
+            system.camera = cam
+            want.append(system.render_image(*sim, precision=precision).copy())
+        outs = [torch.zeros(H * W * 3, dtype=torch.uint8, device=dev) for _ in cams]
+        for i, cam in enumerate(cams):                 # back to back, no synchronisation in between, alternating streams
+            system.camera = cam
+            system.render_rows_device(*sim, 0, H, outs[i].data_ptr(), streams[i & 1].cuda_stream, precision=precision)
+        batch = torch.zeros(2 * H * W * 3, dtype=torch.uint8, device=dev)
+        system.render_frames_device(cams[:2], *sim, 0, H, batch.data_ptr(), streams[0].cuda_stream, precision=precision)
+        system.camera = cams[3]
+        last = torch.zeros(H * W * 3, dtype=torch.uint8, device=dev)
+        system.render_rows_device(*sim, 0, H, last.data_ptr(), streams[1].cuda_stream, precision=precision)
+        torch.cuda.synchronize()
+        for i in range(4):
+            assert (outs[i].cpu().numpy().reshape(H, W, 3) == want[i]).all(), (precision, i)
+        got = batch.cpu().numpy().reshape(2, H, W, 3)
+        assert (got[0] == want[0]).all() and (got[1] == want[1]).all()
+        assert (last.cpu().numpy().reshape(H, W, 3) == want[3]).all()
+    system.camera = cams[0]
