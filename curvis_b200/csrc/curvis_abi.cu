@@ -227,6 +227,11 @@ static void fill_params(const curvis_ctx* ctx, const DeviceState& d, const curvi
     p.max_iterations = sim->max_iterations; p.sampling = (uint32_t)sim->sampling;
     p.integrator = (uint32_t)sim->integrator;
     p.max_radius = sim->max_radius; p.delta = sim->delta;
+    {
+        uint64_t bits;
+        std::memcpy(&bits, &sim->max_radius, 8);
+        p.gate_hi = (sim->max_radius >= 0.0) ? (uint32_t)((bits >> 32) & 0x7fffffffu) : 0u;
+    }
     p.row_begin = row_begin; p.row_end = row_end; p.row_stride = 1;
     p.f_rho = (float)metric->rho; p.f_rho2 = (float)(metric->rho * metric->rho);
     p.f_m = (float)metric->m; p.f_a = (float)metric->a;

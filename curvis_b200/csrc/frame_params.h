@@ -62,6 +62,8 @@ struct FrameParams {
     uint32_t max_iterations;
     uint32_t sampling;
     double max_radius, delta;
+    // escape-test gate: the high word of max_radius when it is >= 0, else 0 (|l| > R needs |l|'s high word >= it)
+    uint32_t gate_hi, _pad0;
     // tile of the frame this launch renders: rows [row_begin, row_end)
     uint32_t row_begin, row_end;
     // steps between two refill points of a warp (render_f64.cu), tuning knob

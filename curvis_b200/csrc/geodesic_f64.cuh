@@ -263,7 +263,7 @@ __device__ __forceinline__ void rhs_lean(const FrameParams& p, bool ray_safe, do
     const bool pre = ray_safe && (abs_hi(th) < pow2_hi(30)) && ((abs_hi(l) - pow2_hi(-100)) < (pow2_hi(100) - pow2_hi(-100))) &&
                      (abs_hi(pth) < pow2_hi(100));
     double c;
-    if (pre) sincos_fast(th, s, c);
+    if (pre) sincos_fast<true>(th, s, c);
     else TrigFast::sincos(th, s, c);
     if (pre && abs_hi(s) >= pow2_hi(-60)) {
         if (SHARED) {

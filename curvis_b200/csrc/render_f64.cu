@@ -109,8 +109,8 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64_lean(const __grid_cons
     const unsigned long long launch_rays = p.ray_list ? *p.ray_list_count : tile_rays * (p.n_frames ? p.n_frames : 1u);
     unsigned long long* const queue = p.ray_list ? &p.counters->redo_next : &p.counters->next_ray;
     const double R = p.max_radius;
-    // |l| > R needs abs_hi(l) >= hi(R) when R >= 0; for negative or NaN R the gate is open.
-    const unsigned gate = (R >= 0.0) ? abs_hi(R) : 0u;
+    // |l| > R needs abs_hi(l) >= hi(R) when R >= 0; for negative or NaN R the gate is open (computed on the host)
+    const unsigned gate = p.gate_hi;
     const bool frame_safe = Shape::params_safe(p);
     const double qnan = __longlong_as_double(0x7ff8000000000000ll);
 
@@ -155,24 +155,33 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64_lean(const __grid_cons
             if (__ballot_sync(kFull, state != 0) == 0u) break;
         }
 
+        // ---- up to `window` steps (escape_photon's loop body, systems.rs:126-135).  Every lane runs its own loop; the only
+        // per-step test is one integer compare of |l|'s high word against the radius's (host-computed: p.gate_hi) — the fp64
+        // escape test, five DSETP, runs after the loop, for the step that reached the gate.  Lanes reconverge at the end.
+        if (state == 1) {
+            const uint32_t n = min(p.window, remaining);
+            uint32_t k = 0;
+            bool near = false;
 #pragma unroll 1
-        for (uint32_t k = 0; k < p.window; ++k) {
-            if (state == 1) {
+            do {
                 if (INTEG == 1) rk4_step_lean<Shape>(p, q, ray_safe);
                 else if (INTEG == 2) euler_step_adaptive<Shape, TRACK>(p, q, ray_safe, &diag);
                 else euler_step_lean<Shape, TRACK, SHARED>(p, q, ray_safe, &diag);
-                --remaining;
-                bool done = (remaining == 0);                                   // systems.rs:137
-                if (abs_hi(q.l) >= gate) {
-                    done = done || (q.l > R) || (q.l < -R);                     // :129-134
-                    // A NaN l never compares true and never recovers (l += NaN): the reference would
-                    // spin through all remaining iterations and return NotEscaped.  Same result, same
-                    // step count, without the spinning.
-                    if (q.l != q.l) { remaining = 0; done = true; }
-                }
-                if (done) state = 2;
+                ++k;
+                if (abs_hi(q.l) >= gate) { near = true; break; }     // |l| >= R (1 - 2^-20), or NaN
+            } while (k < n);
+            remaining -= k;
+            bool done = (remaining == 0);                                       // systems.rs:137
+            if (near) {
+                done = done || (q.l > R) || (q.l < -R);                         // :129-134
+                // A NaN l never compares true and never recovers (l += NaN): the reference would
+                // spin through all remaining iterations and return NotEscaped.  Same result, same
+                // step count, without the spinning.
+                if (q.l != q.l) { remaining = 0; done = true; }
             }
+            if (done) state = 2;
         }
+        __syncwarp();
     }
 
     flush_tally(p, tally, lane);

@@ -27,14 +27,22 @@ constexpr double kPio2Lo = -1.4973849048591698e-33;
 constexpr double kRoundMagic = 6755399441055744.0;   // 1.5 * 2^52: adding it rounds to an integer in the low word
 constexpr double kTrigFastLimit = 1073741824.0;      // 2^30: beyond it fall back to ::sincos (Payne-Hanek)
 
-// sin and cos of x for |x| < kTrigFastLimit (caller guarantees it; NaN/Inf excluded).
+// sin and cos of x for |x| < kTrigFastLimit (caller guarantees it; NaN/Inf excluded).  CB = true reads the reduction's
+// constants from the constant bank as FMA operands instead of immediates (two UMOV per use): fewer issue slots in the
+// operation-for-operation kernel, where sincos runs every step; the regrouped kernel, which only re-derives (sin, cos) once
+// per window, keeps the immediates (its step loop is tuned to the uniform registers it has).  Same arithmetic either way.
+static __device__ __constant__ double kTrigReduce[5] = {0.6366197723675814, 6755399441055744.0, 1.5707963267948966,
+                                                        6.123233995736766e-17, -1.4973849048591698e-33};
+
+template <bool CB = false>
 __device__ __forceinline__ void sincos_fast(double x, double& s, double& c) {
-    const double t = fma(x, kTwoOverPi, kRoundMagic);
+    const double magic = CB ? kTrigReduce[1] : kRoundMagic;
+    const double t = fma(x, CB ? kTrigReduce[0] : kTwoOverPi, magic);
     const int k = __double2loint(t);                  // nearest integer to x*2/pi
-    const double q = t - kRoundMagic;
-    double r = fma(-q, kPio2Hi, x);
-    r = fma(-q, kPio2Mid, r);
-    r = fma(-q, kPio2Lo, r);
+    const double q = t - magic;
+    double r = fma(-q, CB ? kTrigReduce[2] : kPio2Hi, x);
+    r = fma(-q, CB ? kTrigReduce[3] : kPio2Mid, r);
+    r = fma(-q, CB ? kTrigReduce[4] : kPio2Lo, r);
     const double u = r * r;
     double sp = fma(u, kSinPoly[5], kSinPoly[4]);
     double cp = fma(u, kCosPoly[5], kCosPoly[4]);
