@@ -72,8 +72,9 @@ __device__ __forceinline__ void sin2_sincos(const TrigRegs& tr, double x, double
 // <= 2e-17 absolute).  12 fp64 instructions instead of 21.  The pair is re-derived from theta itself
 // (sincos_fast) at the start of every window of steps and after any step with |d| >= 2^-4, so its
 // rounding drift is bounded by one window (<= 128 steps * ~1.5e-16) instead of growing along the ray.
-static __device__ __constant__ double kRotSin[2] = {-0.16666666666666152, 0.008333333309682096};
-static __device__ __constant__ double kRotTan[2] = {0.04166666666674629, 0.00416666629980884};
+// (16-byte aligned: each pair is ONE LDCU.128 in the step loop, wherever the linker puts the other constants)
+static __device__ __constant__ __align__(16) double kRotSin[2] = {-0.16666666666666152, 0.008333333309682096};
+static __device__ __constant__ __align__(16) double kRotTan[2] = {0.04166666666674629, 0.00416666629980884};
 static __device__ double kRotPinned[2] = {-0.00019839655223880117, 0.0004218773803051587};   // S2, T2 (see kPinned)
 
 struct RotRegs {

@@ -34,5 +34,23 @@ for b in bufs:
     b.close()
 for prec in (_abi.PRECISION_F64, _abi.PRECISION_F64_FAST):
     sysm.render_image_efficient(2000, 30.0, 0.05, 30, 30, 1e-4, 1e-4, out=out, precision=prec)
+# round 2: the guard band's second launch in both modes, the extensions, two streams on one context
+for guard in (2, 1):
+    ctx.set_option("guard", guard)
+    for metric in (cv.EllisMetric(1.0), cv.InterstellarMetric(0.1, 1e-4, 1.0)):
+        sysm = cv.RelativisticSystem(metric, cv.SphericalImage(bp), cv.SphericalImage(bn), cam, context=ctx)
+        sysm.render_image(3000, 60.0, 0.05, precision=_abi.PRECISION_F64_FAST, out=out)
+        print("guard", guard, type(metric).__name__, sysm.last_stats["n_reintegrated"], sysm.last_stats["n_kicked"], flush=True)
+sysm = cv.RelativisticSystem(cv.EllisMetric(1.0), cv.SphericalImage(bp), cv.SphericalImage(bn), cam, context=ctx)
+for opts in (dict(integrator=_abi.INTEGRATOR_EULER_ADAPTIVE, step_tolerance=0.01), dict(coordinates=_abi.COORDINATES_CARTESIAN),
+             dict(frame=_abi.FRAME_WORLD), dict(frame=_abi.FRAME_WORLD_QUIRK, precision=_abi.PRECISION_F64_FAST), dict(integrator=_abi.INTEGRATOR_RK4)):
+    sysm.render_image(3000, 60.0, 0.05, out=out, **opts)
+    sysm.render_rows(3000, 60.0, 0.05, 5, 20, with_records=True, **opts)
+streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+tiles = [torch.empty(H * W * 3, dtype=torch.uint8, device="cuda:0") for _ in range(4)]
+for i in range(4):
+    sysm.render_rows_device(3000, 60.0, 0.05, 0, H, tiles[i].data_ptr(), streams[i & 1].cuda_stream, precision=_abi.PRECISION_F64_FAST)
+torch.cuda.synchronize()
+assert all((t == tiles[0]).all() for t in tiles)
 ctx.unregister_host_buffer(out)
 print("ok")
