@@ -254,12 +254,19 @@ def strong_scaling(args, cv, system, sim, PREC, ctx, rank, n, local, dev, stream
         steps = int(st["total_steps"])
         kernel_single_ms = st["kernel_ms"]
         t_single, t_fused, t_nccl = timed(single), timed(fused), timed(nccl)
+        ctx.set_option("guard", 0)          # the regrouped kernel alone: what the guard band's second launch costs at this tile size
+        t_fused_raw = timed(fused)
+        ctx.set_option("guard", 1)
         # this rank's own kernel inside the split frame (the slowest rank bounds the frame)
         kst = system.render_frames_peers([cam], *sim, r0, r1, [b.ptr for b in bufs], stream.cuda_stream, row_stride=stride, precision=PREC, want_stats=True)
         kms = torch.tensor([kst["kernel_ms"]], dtype=torch.float64, device=dev)
         kmax, kmin = kms.clone(), kms.clone()
         dist.all_reduce(kmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(kmin, op=dist.ReduceOp.MIN)
+        kall = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(n)]
+        dist.all_gather(kall, kms)
+        redo_all = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(n)]
+        dist.all_gather(redo_all, torch.tensor([kst["n_reintegrated"]], dtype=torch.int64, device=dev))
         dist.all_reduce(token)
         torch.cuda.synchronize()
         bad = torch.stack([(gathered.view(-1, 3) != whole.view(-1, 3)).any(dim=1).sum(), (full.view(-1, 3) != whole.view(-1, 3)).any(dim=1).sum()]).to(torch.int64)
@@ -268,9 +275,14 @@ def strong_scaling(args, cv, system, sim, PREC, ctx, rank, n, local, dev, stream
             "ray_steps": steps, "one_rank_ms": t_single, "one_rank_kernel_ms": kernel_single_ms,
             "fused_peer_stores": {"ms_per_frame": t_fused, "speedup": t_single / t_fused, "ray_steps_per_s": steps / (t_fused * 1e-3),
                                   "rank_kernel_ms_max": float(kmax.item()), "rank_kernel_ms_min": float(kmin.item()),
+                                  "rank_kernel_ms": [round(float(k.item()), 3) for k in kall],
+                                  "rank_rays_reintegrated": [int(r.item()) for r in redo_all],
+                                  "ms_per_frame_without_guard_band": t_fused_raw, "speedup_without_guard_band": t_single / t_fused_raw,
                                   "ideal_ms": t_single / n,
-                                  "limiter": "the slowest rank's persistent kernel (its drain tail does not shrink with the tile) + the "
-                                             "all-reduce barrier: ms_per_frame - rank_kernel_ms_max is the barrier, rank_kernel_ms_max - ideal_ms the tail/imbalance"},
+                                  "limiter": "fixed costs that do not shrink with the tile: ms_per_frame - rank_kernel_ms_max = the all-reduce "
+                                             "barrier; ms_per_frame - ms_per_frame_without_guard_band = the guard band's re-integration launch "
+                                             "(one strict ray's latency, ~0.6 ms); the rest of rank_kernel_ms_max - ideal_ms = the persistent "
+                                             "kernel's drain tail (one ray's latency, ~0.4 ms) + row imbalance"},
             "nccl_all_gather": {"ms_per_frame": t_nccl, "speedup": t_single / t_nccl, "ray_steps_per_s": steps / (t_nccl * 1e-3),
                                 "gather_bytes": fbytes},
             "differing_pixels_vs_one_rank": {"fused": int(bad[0].item()), "nccl": int(bad[1].item()), "pixels_checked": n * Ws * Hs},
