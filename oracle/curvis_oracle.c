@@ -17,6 +17,16 @@
  *   "PARITY UNPINNED": this restatement, reviewed line by line against the cited
  *   reference lines, is the oracle (plus SURVEY.md section 8c's independent probe
  *   values, which a separate numpy restatement produced).
+ *   What pins the PHYSICS independently of any restatement (tests/test_oracle_physics.py): the azimuth swept by
+ *   equatorial photons against the closed-form quadrature of the null geodesics of both metrics (for Ellis the
+ *   complete elliptic integral), first-order convergence of the Euler scheme, conserved p_t / p_phi; and the one
+ *   cross-check the reference offers between its two renderers (tests/test_oracle_extensions.py): the per-pixel
+ *   photon's world direction (oracle_lookup_direction) against compute_escape_angle, bit for bit on the equator.
+ *
+ * Extensions restated here because this file IS their oracle (no reference counterpart): RK4, bilinear tap,
+ * pole-adaptive Euler step (oracle_step_adaptive), world-frame lookup (oracle_lookup_direction, which follows
+ * src/systems.rs:144-187), chart-free coordinates (oracle_escape_photon_cart), and the trajectory diagnostics
+ * of curvis_ray_record (never computed by the timed cpu_baseline legs).
  *
  * Bit-faithfulness rules (why this should equal a Linux/glibc build of the reference):
  *   Rust never contracts a*b+c to an FMA and f64::{sin,cos,acos,atan,atan2,ln,sqrt}
