@@ -122,8 +122,8 @@ static int validate_frame(curvis_ctx* ctx, const curvis_metric* metric, const cu
     if (sim->coordinates != CURVIS_COORDINATES_SPHERICAL && sim->coordinates != CURVIS_COORDINATES_CARTESIAN)
         return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "unknown coordinates");
     if (sim->coordinates == CURVIS_COORDINATES_CARTESIAN &&
-        (sim->precision != CURVIS_PRECISION_F64 || sim->integrator != CURVIS_INTEGRATOR_EULER))
-        return fail(ctx, CURVIS_ERR_UNSUPPORTED, "CURVIS_COORDINATES_CARTESIAN is implemented for CURVIS_PRECISION_F64 with the Euler integrator");
+        (sim->precision == CURVIS_PRECISION_F32 || sim->integrator != CURVIS_INTEGRATOR_EULER))
+        return fail(ctx, CURVIS_ERR_UNSUPPORTED, "CURVIS_COORDINATES_CARTESIAN is implemented for the fp64 precisions with the Euler integrator");
     if (!ctx->bg_set[0] || !ctx->bg_set[1])
         return fail(ctx, CURVIS_ERR_NO_BACKGROUND, "both backgrounds must be set before rendering");
     // escape_photon panics when the photon starts beyond the radius (systems.rs:122-124);
@@ -136,7 +136,9 @@ static int validate_frame(curvis_ctx* ctx, const curvis_metric* metric, const cu
 static cudaError_t launch_render(const FrameParams& p, const curvis_metric* metric, const curvis_sim* sim,
                                  const LaunchTuning& t, int sm_count, cudaStream_t stream) {
     g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
-    if (sim->coordinates == CURVIS_COORDINATES_CARTESIAN) return launch_render_cart(p, metric->kind, t, sm_count, stream);
+    if (sim->coordinates == CURVIS_COORDINATES_CARTESIAN)
+        return sim->precision == CURVIS_PRECISION_F64_FAST ? launch_render_cart_fast(p, metric->kind, t, sm_count, stream)
+                                                           : launch_render_cart(p, metric->kind, t, sm_count, stream);
     if (sim->precision == CURVIS_PRECISION_F32) return launch_render_f32(p, metric->kind, t, sm_count, stream);
     if (sim->precision == CURVIS_PRECISION_F64_FAST) {
         cudaError_t e = launch_render_f64_fast(p, metric->kind, t, sm_count, stream);
@@ -187,7 +189,8 @@ static int ensure_inverse_table(curvis_ctx* ctx, DeviceState& d, const curvis_me
 
 // The redo list of CURVIS_PRECISION_F64_FAST: one slot per ray of the launch (8 bytes each; a 4K frame: 66 MB), grown on demand.
 static int ensure_redo(curvis_ctx* ctx, DeviceState& d, const curvis_sim* sim, size_t rays) {
-    if (sim->precision != CURVIS_PRECISION_F64_FAST || !ctx->tuning.guard || ctx->tuning.fast_variant != 1) return CURVIS_OK;
+    if (sim->precision != CURVIS_PRECISION_F64_FAST || !ctx->tuning.guard || ctx->tuning.fast_variant != 1 ||
+        sim->coordinates != CURVIS_COORDINATES_SPHERICAL) return CURVIS_OK;
     if (rays > d.d_redo_cap) {
         if (d.d_redo) cudaFree(d.d_redo);
         d.d_redo = nullptr; d.d_redo_cap = 0;
@@ -254,7 +257,8 @@ static void fill_params(const curvis_ctx* ctx, const DeviceState& d, const curvi
     }
     p.out_rgb8 = d_out; p.out_rgba32f = nullptr; p.records = d_records; p.counters = d.d_counters;
     p.frame = (uint32_t)sim->frame; p.coordinates = (uint32_t)sim->coordinates; p.step_tolerance = sim->step_tolerance;
-    const bool guard = sim->precision == CURVIS_PRECISION_F64_FAST && ctx->tuning.guard && ctx->tuning.fast_variant == 1;
+    const bool guard = sim->precision == CURVIS_PRECISION_F64_FAST && ctx->tuning.guard && ctx->tuning.fast_variant == 1 &&
+                       sim->coordinates == CURVIS_COORDINATES_SPHERICAL;
     p.redo_list = guard ? d.d_redo : nullptr;
     p.redo_capacity = guard ? d.d_redo_cap : 0;
     p.guard_rel = ctx->tuning.guard_rel;

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include "ieee_f64.cuh"
 #include "trig_f64.cuh"
+#include "shape_table.h"
 
 namespace curvis {
 
@@ -103,6 +104,23 @@ __device__ __forceinline__ void rotate_sincos(const RotRegs& rr, double d, doubl
     c = fma(-t, s, c);
     s = fma(sd, c, s);
     c = fma(-t, s, c);
+}
+
+// ---- Interstellar shape function from the per-metric table (shape_table.h: build_interstellar_inverse_table):
+// Y = 1/r(l) and G = |r'(l)| at x = fma(|l|, xscale, xoff), six 128-bit loads and two degree-5 Horner chains.  Every x below the
+// table (the plateau |l| <= a, x <= 0 included) reads the constant row through an unsigned min — no branch, no call; x beyond
+// the table must be kept out by the caller (FrameParams::fast_l_limit).
+__device__ __forceinline__ void interstellar_inverse_lookup(const double2* __restrict__ tab, double xscale, double xoff, double l, double& Y, double& G) {
+    const double x = fma(fabs(l), xscale, xoff);
+    const unsigned hi = (unsigned)__double2hiint(x);
+    const unsigned idx = min((hi >> kShapeTabShift) - kInvTabBase, (unsigned)kInvTabConstRow);
+    const double c = __hiloint2double((int)((hi & ~((1u << kShapeTabShift) - 1u)) | (1u << (kShapeTabShift - 1))), 0);
+    const double t = x - c;
+    const double2* e = tab + (size_t)idx * (kShapeTabDoubles / 2);
+    const double2 a01 = __ldg(e), a23 = __ldg(e + 1), a45 = __ldg(e + 2);
+    const double2 b01 = __ldg(e + 3), b23 = __ldg(e + 4), b45 = __ldg(e + 5);
+    Y = fma(t, fma(t, fma(t, fma(t, fma(t, a45.y, a45.x), a23.y), a23.x), a01.y), a01.x);
+    G = fma(t, fma(t, fma(t, fma(t, fma(t, b45.y, b45.x), b23.y), b23.x), b01.y), b01.x);
 }
 
 // d >= 0 by construction (a product of squares and a positive radius), so the high word is

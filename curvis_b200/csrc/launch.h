@@ -38,6 +38,8 @@ cudaError_t launch_render_f64_fast(const FrameParams& p, int metric_kind, const 
 
 // fp64, chart-free angular state, CURVIS_COORDINATES_CARTESIAN (render_f64_cart.cu) — extension ("pole-safe").
 cudaError_t launch_render_cart(const FrameParams& p, int metric_kind, const LaunchTuning& t, int sm_count, cudaStream_t stream);
+// the same scheme regrouped for the fp64 pipe (CURVIS_COORDINATES_CARTESIAN + CURVIS_PRECISION_F64_FAST)
+cudaError_t launch_render_cart_fast(const FrameParams& p, int metric_kind, const LaunchTuning& t, int sm_count, cudaStream_t stream);
 
 // RGBA8 -> float4 staging for CURVIS_SAMPLING_BILINEAR, and the tap evaluated at explicit
 // continuous coordinates (test hook curvis_debug_bilinear).  render_f64.cu.

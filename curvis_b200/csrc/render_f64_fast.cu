@@ -145,16 +145,8 @@ struct FastInterstellar {   // metrics.rs:461-485 with the uniform divisor pi*m 
     // (beyond(): the kernel's radius gate).  42 fp64-pipe instructions per step.
     struct Pre { double y, rp; };
     static __device__ __forceinline__ double prepare(const FrameParams& p, double l, double s2, Pre& pre) {
-        const double x = fma(fabs(l), p.d_xscale, p.d_xoff);
-        const unsigned hi = (unsigned)__double2hiint(x);
-        const unsigned idx = min((hi >> kShapeTabShift) - kInvTabBase, (unsigned)kInvTabConstRow);
-        const double c = __hiloint2double((int)((hi & ~((1u << kShapeTabShift) - 1u)) | (1u << (kShapeTabShift - 1))), 0);
-        const double t = x - c;
-        const double2* e = p.inv_tab + (size_t)idx * (kShapeTabDoubles / 2);
-        const double2 a01 = __ldg(e), a23 = __ldg(e + 1), a45 = __ldg(e + 2);
-        const double2 b01 = __ldg(e + 3), b23 = __ldg(e + 4), b45 = __ldg(e + 5);
-        pre.y = fma(t, fma(t, fma(t, fma(t, fma(t, a45.y, a45.x), a23.y), a23.x), a01.y), a01.x);
-        const double G = fma(t, fma(t, fma(t, fma(t, fma(t, b45.y, b45.x), b23.y), b23.x), b01.y), b01.x);
+        double G;
+        interstellar_inverse_lookup(p.inv_tab, p.d_xscale, p.d_xoff, l, pre.y, G);
         pre.rp = copysign(G, l);
         return s2;
     }

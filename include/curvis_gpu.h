@@ -135,7 +135,10 @@ typedef enum curvis_frame {
 typedef enum curvis_coordinates {
     CURVIS_COORDINATES_SPHERICAL = 0, /* the reference's state (l, theta, phi, p_l, p_theta, p_phi)                        */
     CURVIS_COORDINATES_CARTESIAN = 1  /* extension ("pole-safe"): the angular part of the state is the unit position vector n
-                                         and its tangent momentum; no 1/sin(theta) anywhere           */
+                                         and the conserved angular-momentum vector; no 1/sin(theta) anywhere (DESIGN.md
+                                         section 7).  CURVIS_PRECISION_F64: the oracle's operation order;
+                                         CURVIS_PRECISION_F64_FAST: the same scheme regrouped (17 fp64 instructions per
+                                         Ellis step, the fastest integrator of the library; no guard band)              */
 } curvis_coordinates;
 
 typedef struct curvis_sim {

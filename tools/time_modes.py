@@ -37,6 +37,16 @@ for mname, metric, sim in (("ellis_defaults", cv.EllisMetric(1.0), (40000, 100.0
         res[f"f64_variant{variant}"] = run(_abi.PRECISION_F64, reps=3, kernel_variant=variant)
     ctx.set_option("kernel_variant", 4)
     res["f32"] = run(_abi.PRECISION_F32)
+
+    def run_cart(precision):
+        ms = []
+        for _ in range(4):
+            system.render_image(*sim, precision=precision, coordinates=_abi.COORDINATES_CARTESIAN)
+            ms.append(system.last_stats["kernel_ms"])
+        st = system.last_stats
+        return {"kernel_ms": round(min(ms[1:]), 3), "total_steps": int(st["total_steps"]), "ray_steps_per_s": st["total_steps"] / (min(ms[1:]) * 1e-3)}
+    res["cartesian_f64"] = run_cart(_abi.PRECISION_F64)
+    res["cartesian_f64_fast"] = run_cart(_abi.PRECISION_F64_FAST)
     out[mname] = res
     print(mname, json.dumps(res), flush=True)
 if len(sys.argv) > 1:
