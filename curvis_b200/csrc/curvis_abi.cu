@@ -3,6 +3,7 @@
 // context's devices).  The boundary replaces RelativisticSystem::render_image
 // (reference src/systems.rs:307-330); there is no CPU compute path in this library.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -191,11 +192,14 @@ static int ensure_inverse_table(curvis_ctx* ctx, DeviceState& d, const curvis_me
 static int ensure_redo(curvis_ctx* ctx, DeviceState& d, const curvis_sim* sim, size_t rays) {
     if (sim->precision != CURVIS_PRECISION_F64_FAST || !ctx->tuning.guard || ctx->tuning.fast_variant != 1 ||
         sim->coordinates != CURVIS_COORDINATES_SPHERICAL) return CURVIS_OK;
-    if (rays > d.d_redo_cap) {
+    // one slot per ray up to 2^24 rays (128 MB: two 4K frames, half an 8K frame); beyond that an eighth of the launch (the
+    // band takes ~1e-3 of the rays, 2.5 % with "guard" = 2); a full list makes the kernel re-integrate in line (correct, slow)
+    const size_t want = rays <= (size_t(1) << 24) ? rays : std::max(size_t(1) << 24, rays / 8);
+    if (want > d.d_redo_cap) {
         if (d.d_redo) cudaFree(d.d_redo);
         d.d_redo = nullptr; d.d_redo_cap = 0;
-        CURVIS_CUDA(ctx, cudaMalloc(&d.d_redo, rays * sizeof(unsigned long long)));
-        d.d_redo_cap = rays;
+        CURVIS_CUDA(ctx, cudaMalloc(&d.d_redo, want * sizeof(unsigned long long)));
+        d.d_redo_cap = want;
     }
     return CURVIS_OK;
 }

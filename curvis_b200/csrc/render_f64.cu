@@ -106,7 +106,8 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64_lean(const __grid_cons
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned long long tile_rays = (unsigned long long)(p.row_end - p.row_begin) * p.width;
-    const unsigned long long launch_rays = p.ray_list ? *p.ray_list_count : tile_rays * (p.n_frames ? p.n_frames : 1u);
+    // (list mode: the count includes rays a full list turned away — those were re-integrated in line by the fast kernel)
+    const unsigned long long launch_rays = p.ray_list ? min(*p.ray_list_count, p.redo_capacity) : tile_rays * (p.n_frames ? p.n_frames : 1u);
     unsigned long long* const queue = p.ray_list ? &p.counters->redo_next : &p.counters->next_ray;
     const double R = p.max_radius;
     // |l| > R needs abs_hi(l) >= hi(R) when R >= 0; for negative or NaN R the gate is open (computed on the host)
