@@ -265,6 +265,8 @@ static void fill_params(const curvis_ctx* ctx, const DeviceState& d, const curvi
                        sim->coordinates == CURVIS_COORDINATES_SPHERICAL;
     p.redo_list = guard ? d.d_redo : nullptr;
     p.redo_capacity = guard ? d.d_redo_cap : 0;
+    if (guard && ctx->tuning.redo_capacity_limit > 0 && (unsigned long long)ctx->tuning.redo_capacity_limit < p.redo_capacity)
+        p.redo_capacity = (unsigned long long)ctx->tuning.redo_capacity_limit;
     p.guard_rel = ctx->tuning.guard_rel;
     p.guard_kicked = ctx->tuning.guard >= 2 ? 1u : 0u;
 }
@@ -813,6 +815,7 @@ extern "C" int curvis_ctx_set_option(curvis_ctx* ctx, const char* key, int64_t v
     else if (k == "guard" && value >= 0 && value <= 2) ctx->tuning.guard = (int)value;
     else if (k == "fast_regs" && (value == 0 || value == 96 || value == 128)) ctx->tuning.fast_regs = (int)value;
     else if (k == "redo_blocks_per_sm" && value >= 0 && value <= 32) ctx->tuning.redo_blocks_per_sm = (int)value;
+    else if (k == "redo_capacity_limit" && value >= 0) ctx->tuning.redo_capacity_limit = value;
     else if (k == "guard_rel_e15" && value >= 1 && value <= 1000000000000ll) ctx->tuning.guard_rel = (double)value * 1e-15;
     else return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "unknown option or value out of range: " + k);
     return CURVIS_OK;

@@ -19,6 +19,7 @@ struct LaunchTuning {
                              // 2 = kicked rays (stiffness >= 1) re-integrated too (every ray equals CURVIS_PRECISION_F64's);
                              // 0 = the raw regrouped kernel (A/B, tools/guard_study.py)
     double guard_rel = 1e-9; // relative state-error budget of a ray with stiffness < 1 (render_f64_fast.cu: guard_eps)
+    long long redo_capacity_limit = 0;   // test knob: cap the re-integration list (0 = automatic) to exercise the in-line fallback
     int redo_blocks_per_sm = 2;   // CTAs per SM of the re-integration launch (a few per cent of the frame's rays: fewer, fuller warps)
     int fast_regs = 0;       // CURVIS_PRECISION_F64_FAST register budget: 96 (5 CTAs per SM; Ellis: 50-instruction step, 36.4 ms per 4K
                              // frame) or 128 (4 CTAs; Ellis 47 instructions, 37.5 ms; Interstellar 71 instead of 76: 59.2 against

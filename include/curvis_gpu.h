@@ -380,6 +380,8 @@ int curvis_measure_fma_peak(curvis_ctx* ctx, double* fp64_tflops, double* fp32_t
  *   "fast_regs":      96 / 128: register budget of the fast kernel (5 / 4 resident CTAs per SM); 0 (default) = 96 for
  *                     Ellis and Flat, 128 for Interstellar (the measured optimum of each)
  *   "redo_blocks_per_sm": resident CTAs per SM of the re-integration launch (default 2)
+ *   "redo_capacity_limit": test knob — caps the re-integration list (0 = automatic: one slot per ray up to 2^24 rays); a ray
+ *                     that finds the list full is re-integrated in line by the fast kernel (same result, slower)
  *   "blocks_per_sm":  resident CTAs per SM of the persistent grid (0 = occupancy maximum)
  *   "window":         Euler steps between two refill points of a warp (0 = default: 32; for
  *                     CURVIS_PRECISION_F64_FAST 32..128, growing with the expected ray length)

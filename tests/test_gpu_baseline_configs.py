@@ -103,3 +103,31 @@ def test_full_identity_mode_guard_2(gpu_ctx, oracle, backgrounds):
         assert st0[k] == st1[k], k
     assert st1["n_reintegrated"] >= st1["n_kicked"] > 0
     print(f"[parity] guard=2: {st1['n_reintegrated']} of {W * H} rays re-integrated ({st1['n_kicked']} kicked)")
+
+
+def test_full_re_integration_list_falls_back_in_line(gpu_ctx):
+    """A ray that finds the re-integration list full is re-integrated by the fast kernel itself (plain operators): same
+    frame, same counters.  Forced here with the test knob "redo_capacity_limit"."""
+    import curvis_b200 as cv
+    from curvis_b200 import _abi, scenes
+    bp, bn = scenes.noise_background(512, 256, 3), scenes.noise_background(512, 256, 4)
+    W, H, sim = 320, 180, (40000, 100.0, 0.05)
+    cam_args = (scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP, 15.0, 43.0, W, H)
+    for metric in (cv.EllisMetric(1.0), cv.InterstellarMetric(0.1, 1e-4, 1.0)):
+        system = cv.RelativisticSystem(metric, cv.SphericalImage(bp), cv.SphericalImage(bn), cv.Camera(*cam_args), context=gpu_ctx)
+        strict, rec0 = system.render_rows(*sim, 0, H, with_records=True)
+        st0 = dict(system.last_stats)
+        gpu_ctx.set_option("guard", 2)
+        gpu_ctx.set_option("redo_capacity_limit", 37)
+        try:
+            fast, rec1 = system.render_rows(*sim, 0, H, with_records=True, precision=_abi.PRECISION_F64_FAST)
+            st1 = dict(system.last_stats)
+        finally:
+            gpu_ctx.set_option("guard", 1)
+            gpu_ctx.set_option("redo_capacity_limit", 0)
+        assert st1["n_reintegrated"] > 37
+        assert (strict == fast).all()
+        for f in ("steps", "side", "texel_x", "texel_y"):
+            assert (rec0[f] == rec1[f]).all(), f
+        for k in ("total_steps", "n_positive", "n_negative", "n_not_escaped", "n_clamped"):
+            assert st0[k] == st1[k], k
