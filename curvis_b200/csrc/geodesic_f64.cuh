@@ -163,6 +163,34 @@ __device__ __forceinline__ void new_photon_from_camera(const CameraBlock& cam, u
     new_photon_from_direction(cam, dx, dy, dz, q);
 }
 
+// The camera of ray `idx` (batched launches hold one per frame).
+__device__ __forceinline__ const CameraBlock& camera_for_ray(const FrameParams& p, unsigned long long idx, unsigned long long tile_rays) {
+    return (p.ray_dirs || p.n_frames <= 1) ? p.cam : p.cameras[idx / tile_rays];
+}
+
+// min sin(theta) along the geodesic of ray `idx`, squared, from its (unnormalised) tangent direction alone: the angular
+// momentum is L^2 = p_theta^2 + p_phi^2 / sin^2 theta_0 with p_theta ~ d_y, p_phi ~ d_z sin theta_0, and the orbit's closest
+// approach to the polar axis is sin theta_min = |p_phi| / L.  A scheduling hint (render_f64_fast.cu claims the rays that will
+// graze a pole first): no normalisation, no square root, never used for a result.
+__device__ __forceinline__ double min_sin2_of_ray(const FrameParams& p, unsigned long long idx, unsigned long long tile_rays) {
+    const CameraBlock& cam = camera_for_ray(p, idx, tile_rays);
+    double dy, dz;
+    if (p.ray_dirs) {
+        dy = p.ray_dirs[3 * idx + 1]; dz = p.ray_dirs[3 * idx + 2];
+    } else {
+        const unsigned long long r = (p.n_frames <= 1) ? idx : idx % tile_rays;
+        const uint32_t px = (uint32_t)(r % p.width), py = p.row_begin + (uint32_t)(r / p.width) * p.row_stride;
+        const double vx = cam.focal_length;
+        const double vy = -cam.sensor_width * (((double)px / (double)p.width) - 0.5);
+        const double vz = cam.sensor_height * (0.5 - ((double)py / (double)p.height));
+        dy = (cam.cam_to_world[3] * vx + cam.cam_to_world[4] * vy) + cam.cam_to_world[5] * vz;
+        dz = (cam.cam_to_world[6] * vx + cam.cam_to_world[7] * vy) + cam.cam_to_world[8] * vz;
+    }
+    const double s02 = cam.cam_sin_theta * cam.cam_sin_theta;
+    const double pph2 = dz * dz * s02;
+    return pph2 / (dy * dy + dz * dz);      // (NaN for a purely radial ray: neither walk's first test accepts it as long)
+}
+
 // Ray `idx` of a launch: frame = idx / tile_rays (batched launches), pixel = idx % tile_rays.
 __device__ __forceinline__ void new_photon_for_ray(const FrameParams& p, unsigned long long idx, unsigned long long tile_rays, Ray& q) {
     if (p.ray_dirs) {

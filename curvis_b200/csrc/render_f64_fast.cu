@@ -36,6 +36,7 @@ namespace curvis {
 namespace {
 
 constexpr int kBlockFast = 128;
+constexpr double kLongRaySin = 0.03;   // refill: rays whose orbit comes within asin(0.03) of the polar axis are claimed first
 constexpr unsigned kFullFast = 0xffffffffu;
 
 // Shape policies of the fast step.  factors() returns, for the current l and sin^2 theta:
@@ -406,16 +407,27 @@ __global__ void __launch_bounds__(kBlockFast, MinBlocks) render_rows_f64_fast(co
             state = 0;
         }
 
-        const unsigned idle = __ballot_sync(kFullFast, state == 0);
+        // ---- refill.  The queue is walked TWICE (tickets 0..N-1, then N..2N-1 for the same N rays): the first walk hands out
+        // only the rays predicted to be long — a photon whose angular momentum points almost along the polar axis
+        // (min sin theta = |p_phi| / L < kLongRaySin) will be kicked by the coordinate pole, and kicked rays are where the
+        // 10^4-step stragglers live (profiles/r02_latency_probe.json: the rows next to the image's central row take 10x the
+        // time of any other) — the second walk everything else.  Longest first: a 20,000-step ray needs 4 ms at full
+        // occupancy whenever it starts, so on a small tile (one 4K frame over 8 GPUs: 5 ms) it must start at once.  A
+        // rejected ticket costs the prediction only (the pixel's unnormalised direction: ~30 instructions).
+        unsigned idle = __ballot_sync(kFullFast, state == 0);
         if (idle) {
-            if (!drained) {
+            while (idle && !drained) {
                 const int leader = __ffs(idle) - 1;
                 unsigned long long base = 0;
                 if ((int)lane == leader) base = atomicAdd(&p.counters->next_ray, (unsigned long long)__popc(idle));
                 base = __shfl_sync(kFullFast, base, leader);
                 if (state == 0) {
-                    const unsigned long long idx = base + (unsigned long long)__popc(idle & lt_mask);
-                    if (idx < launch_rays) {
+                    const unsigned long long ticket = base + (unsigned long long)__popc(idle & lt_mask);
+                    if (ticket < 2ull * launch_rays) {
+                        const bool first_walk = ticket < launch_rays;
+                        const unsigned long long idx = first_walk ? ticket : ticket - launch_rays;
+                        const bool long_ray = min_sin2_of_ray(p, idx, tile_rays) < kLongRaySin * kLongRaySin;   // (NaN: second walk)
+                        if (long_ray == first_walk) {
                         new_photon_for_ray(p, idx, tile_rays, q);
                         if (Variant == 1) {            // momenta pre-scaled by delta (fast_window_scaled)
                             q.pl = q.pl * p.delta; q.pth = q.pth * p.delta; q.pph = q.pph * p.delta;
@@ -427,9 +439,11 @@ __global__ void __launch_bounds__(kBlockFast, MinBlocks) render_rows_f64_fast(co
                         remaining = p.max_iterations;
                         wmax_hi = 0;
                         state = (remaining == 0) ? 2 : 1;
+                        }
                     }
                 }
-                if (base + (unsigned long long)__popc(idle) >= launch_rays) drained = true;
+                if (base + (unsigned long long)__popc(idle) >= 2ull * launch_rays) drained = true;
+                idle = __ballot_sync(kFullFast, state == 0);
             }
             if (__ballot_sync(kFullFast, state != 0) == 0u) break;
         }
