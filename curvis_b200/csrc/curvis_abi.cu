@@ -240,6 +240,8 @@ static void fill_params(const curvis_ctx* ctx, const DeviceState& d, const curvi
         p.gate_hi = (sim->max_radius >= 0.0) ? (uint32_t)((bits >> 32) & 0x7fffffffu) : 0u;
     }
     p.row_begin = row_begin; p.row_end = row_end; p.row_stride = 1;
+    p.inv_width = 1.0 / (double)cam->resolution_width;
+    p.inv_tile_rays = 1.0 / ((double)(row_end - row_begin) * (double)cam->resolution_width);
     p.f_rho = (float)metric->rho; p.f_rho2 = (float)(metric->rho * metric->rho);
     p.f_m = (float)metric->m; p.f_a = (float)metric->a;
     p.f_xscale = (float)(2.0 / (3.14159265358979323846 * metric->m));
@@ -568,6 +570,7 @@ static int render_frames_impl(curvis_ctx* ctx, const curvis_metric* metric,
     const uint32_t n_rows = (row_end - row_begin + row_stride - 1) / row_stride;
     p.row_stride = row_stride;
     p.row_end = row_begin + n_rows;
+    p.inv_tile_rays = 1.0 / ((double)n_rows * (double)cameras[0].resolution_width);
     CURVIS_CUDA(ctx, cudaMemsetAsync(d.d_counters, 0, sizeof(DeviceCounters), st));
     CURVIS_CUDA(ctx, cudaEventRecord(d.ev_begin, st));
     if (row_end > row_begin) CURVIS_CUDA(ctx, launch_render(p, metric, sim, ctx->tuning, d.sm_count, st));

@@ -62,6 +62,8 @@ struct FrameParams {
     uint32_t max_iterations;
     uint32_t sampling;
     double max_radius, delta;
+    // 1 / width and 1 / (rays of one frame's tile), for splitting a ray index without 64-bit integer division (geodesic_f64.cuh)
+    double inv_width, inv_tile_rays;
     // escape-test gate: the high word of max_radius when it is >= 0, else 0 (|l| > R needs |l|'s high word >= it)
     uint32_t gate_hi, _pad0;
     // tile of the frame this launch renders: rows [row_begin, row_end)

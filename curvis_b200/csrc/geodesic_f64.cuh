@@ -163,44 +163,62 @@ __device__ __forceinline__ void new_photon_from_camera(const CameraBlock& cam, u
     new_photon_from_direction(cam, dx, dy, dz, q);
 }
 
-// The camera of ray `idx` (batched launches hold one per frame).
-__device__ __forceinline__ const CameraBlock& camera_for_ray(const FrameParams& p, unsigned long long idx, unsigned long long tile_rays) {
-    return (p.ray_dirs || p.n_frames <= 1) ? p.cam : p.cameras[idx / tile_rays];
+// Ray `idx` of a launch -> (frame, pixel column, row of the tile).  idx < 2^53 and the divisors are launch constants, so
+// the quotients come from one double multiplication by the host-computed reciprocal plus a one-step correction — the 64-bit
+// integer divisions this replaces are ~150 instructions each, and a warp pays them once per refill, not once per ray.
+__device__ __forceinline__ void split_ray_index(const FrameParams& p, unsigned long long idx, unsigned long long tile_rays,
+                                                unsigned long long& frame, uint32_t& px, uint32_t& k) {
+    unsigned long long r = idx;
+    frame = 0;
+    if (p.n_frames > 1) {
+        frame = (unsigned long long)((double)idx * p.inv_tile_rays);
+        if (frame * tile_rays > idx) --frame;
+        else if ((frame + 1) * tile_rays <= idx) ++frame;
+        r = idx - frame * tile_rays;
+    }
+    k = (uint32_t)((double)r * p.inv_width);
+    if ((unsigned long long)k * p.width > r) --k;
+    else if ((unsigned long long)(k + 1) * p.width <= r) ++k;
+    px = (uint32_t)(r - (unsigned long long)k * p.width);
 }
 
-// min sin(theta) along the geodesic of ray `idx`, squared, from its (unnormalised) tangent direction alone: the angular
-// momentum is L^2 = p_theta^2 + p_phi^2 / sin^2 theta_0 with p_theta ~ d_y, p_phi ~ d_z sin theta_0, and the orbit's closest
-// approach to the polar axis is sin theta_min = |p_phi| / L.  A scheduling hint (render_f64_fast.cu claims the rays that will
-// graze a pole first): no normalisation, no square root, never used for a result.
-__device__ __forceinline__ double min_sin2_of_ray(const FrameParams& p, unsigned long long idx, unsigned long long tile_rays) {
-    const CameraBlock& cam = camera_for_ray(p, idx, tile_rays);
-    double dy, dz;
+// The camera of frame `frame` of a launch (batched launches hold one per frame).
+__device__ __forceinline__ const CameraBlock& camera_of_frame(const FrameParams& p, unsigned long long frame) {
+    return (p.ray_dirs || p.n_frames <= 1) ? p.cam : p.cameras[frame];
+}
+
+// min sin(theta) along the geodesic of ray `idx`, squared, below `limit2`?  From the (unnormalised) tangent direction alone:
+// the angular momentum is L^2 = p_theta^2 + p_phi^2 / sin^2 theta_0 with p_theta ~ d_y, p_phi ~ d_z sin theta_0, and the
+// orbit's closest approach to the polar axis is sin theta_min = |p_phi| / L.  A scheduling hint (render_f64_fast.cu claims
+// the rays that will graze a pole first): no normalisation, no square root, no division, never used for a result.
+__device__ __forceinline__ bool ray_grazes_pole(const FrameParams& p, unsigned long long idx, unsigned long long tile_rays, double limit2) {
+    double dy, dz, s0;
     if (p.ray_dirs) {
-        dy = p.ray_dirs[3 * idx + 1]; dz = p.ray_dirs[3 * idx + 2];
+        dy = p.ray_dirs[3 * idx + 1]; dz = p.ray_dirs[3 * idx + 2]; s0 = p.cam.cam_sin_theta;
     } else {
-        const unsigned long long r = (p.n_frames <= 1) ? idx : idx % tile_rays;
-        const uint32_t px = (uint32_t)(r % p.width), py = p.row_begin + (uint32_t)(r / p.width) * p.row_stride;
+        unsigned long long f; uint32_t px, k;
+        split_ray_index(p, idx, tile_rays, f, px, k);
+        const CameraBlock& cam = camera_of_frame(p, f);
+        const uint32_t py = p.row_begin + k * p.row_stride;
         const double vx = cam.focal_length;
-        const double vy = -cam.sensor_width * (((double)px / (double)p.width) - 0.5);
+        const double vy = -cam.sensor_width * (((double)px * p.inv_width) - 0.5);
         const double vz = cam.sensor_height * (0.5 - ((double)py / (double)p.height));
         dy = (cam.cam_to_world[3] * vx + cam.cam_to_world[4] * vy) + cam.cam_to_world[5] * vz;
         dz = (cam.cam_to_world[6] * vx + cam.cam_to_world[7] * vy) + cam.cam_to_world[8] * vz;
+        s0 = cam.cam_sin_theta;
     }
-    const double s02 = cam.cam_sin_theta * cam.cam_sin_theta;
-    const double pph2 = dz * dz * s02;
-    return pph2 / (dy * dy + dz * dz);      // (NaN for a purely radial ray: neither walk's first test accepts it as long)
+    return (dz * dz) * (s0 * s0) < limit2 * (dy * dy + dz * dz);      // (NaN: false)
 }
 
 // Ray `idx` of a launch: frame = idx / tile_rays (batched launches), pixel = idx % tile_rays.
 __device__ __forceinline__ void new_photon_for_ray(const FrameParams& p, unsigned long long idx, unsigned long long tile_rays, Ray& q) {
     if (p.ray_dirs) {
         new_photon_from_direction(p.cam, p.ray_dirs[3 * idx], p.ray_dirs[3 * idx + 1], p.ray_dirs[3 * idx + 2], q);
-    } else if (p.n_frames <= 1) {
-        new_photon_from_camera(p.cam, p.width, p.height, (uint32_t)(idx % p.width), p.row_begin + (uint32_t)(idx / p.width) * p.row_stride, q);
-    } else {
-        const unsigned long long f = idx / tile_rays, r = idx % tile_rays;
-        new_photon_from_camera(p.cameras[f], p.width, p.height, (uint32_t)(r % p.width), p.row_begin + (uint32_t)(r / p.width) * p.row_stride, q);
+        return;
     }
+    unsigned long long f; uint32_t px, k;
+    split_ray_index(p, idx, tile_rays, f, px, k);
+    new_photon_from_camera(camera_of_frame(p, f), p.width, p.height, px, p.row_begin + k * p.row_stride, q);
 }
 
 // ---------------------------------------------------------------- one explicit Euler step
@@ -597,8 +615,8 @@ __device__ __forceinline__ bool finish_ray(const FrameParams& p, const Ray& q, i
         if (p.n_peers) {
             // fused all-gather: this pixel into the complete frame of every peer (frame_params.h)
             const unsigned long long tile_rays = (unsigned long long)(p.row_end - p.row_begin) * p.width;
-            const unsigned long long f = ray / tile_rays, in_tile = ray - f * tile_rays;
-            const unsigned long long k = in_tile / p.width, px = in_tile - k * p.width;
+            unsigned long long f; uint32_t px, k;
+            split_ray_index(p, ray, tile_rays, f, px, k);
             const size_t off = (((size_t)f * p.height + p.row_begin + (size_t)k * p.row_stride) * p.width + px) * 3;
             for (uint32_t i = 0; i < p.n_peers; ++i) {
                 uint8_t* o = p.out_peers[i] + off;

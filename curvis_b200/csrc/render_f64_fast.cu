@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(kBlockFast, MinBlocks) render_rows_f64_fast(co
                     if (ticket < 2ull * launch_rays) {
                         const bool first_walk = ticket < launch_rays;
                         const unsigned long long idx = first_walk ? ticket : ticket - launch_rays;
-                        const bool long_ray = min_sin2_of_ray(p, idx, tile_rays) < kLongRaySin * kLongRaySin;   // (NaN: second walk)
+                        const bool long_ray = ray_grazes_pole(p, idx, tile_rays, kLongRaySin * kLongRaySin);
                         if (long_ray == first_walk) {
                         new_photon_for_ray(p, idx, tile_rays, q);
                         if (Variant == 1) {            // momenta pre-scaled by delta (fast_window_scaled)
