@@ -50,6 +50,8 @@ struct DeviceState {
     cudaEvent_t chunk_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // pipelined read-back
     // CURVIS_PRECISION_F64_FAST: indices of the rays inside the guard band, re-integrated by the parity kernel
     unsigned long long* d_redo = nullptr; size_t d_redo_cap = 0;
+    // CURVIS_PRECISION_F64_FAST: indices of the rays the work queue hands out first (FrameParams::long_list)
+    unsigned long long* d_long = nullptr; size_t d_long_cap = 0;
     // the per-launch scratch above (counters, cameras, redo list, events) is shared by every launch of the context: a
     // launch on a stream other than the previous one's first waits for the previous launch (launch_fence)
     cudaStream_t last_stream = nullptr; bool launched = false;
@@ -142,6 +144,7 @@ static cudaError_t launch_render(const FrameParams& p, const curvis_metric* metr
                                                            : launch_render_cart(p, metric->kind, t, sm_count, stream);
     if (sim->precision == CURVIS_PRECISION_F32) return launch_render_f32(p, metric->kind, t, sm_count, stream);
     if (sim->precision == CURVIS_PRECISION_F64_FAST) {
+        if (render_f64_fast_has_prepass(p, t)) g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
         cudaError_t e = launch_render_f64_fast(p, metric->kind, t, sm_count, stream);
         if (e != cudaSuccess || !p.redo_list) return e;
         // second launch: the parity kernel over the rays the fast kernel left in its guard band (list mode; the list's
@@ -183,15 +186,29 @@ static int ensure_inverse_table(curvis_ctx* ctx, DeviceState& d, const curvis_me
     }
     if (!d.d_inv_tab) CURVIS_CUDA(ctx, cudaMalloc(&d.d_inv_tab, n * sizeof(double)));
     CURVIS_CUDA(ctx, cudaMemcpyAsync(d.d_inv_tab, ctx->inv_tab_host.data(), n * sizeof(double), cudaMemcpyHostToDevice, stream));
+    // the table's last row holds its own device address (the kernel reads it from there: fast_f64.cuh, InverseShapeCache::reset)
+    const unsigned long long self = (unsigned long long)(uintptr_t)d.d_inv_tab;
+    CURVIS_CUDA(ctx, cudaMemcpyAsync((double*)d.d_inv_tab + kInvTabSelfRow * kShapeTabDoubles, &self, sizeof self, cudaMemcpyHostToDevice, stream));
     CURVIS_CUDA(ctx, cudaStreamSynchronize(stream));   // the host copy may be rebuilt by the next call
     d.inv_tab_rho = metric->rho; d.inv_tab_m = metric->m;
     return CURVIS_OK;
 }
 
 // The redo list of CURVIS_PRECISION_F64_FAST: one slot per ray of the launch (8 bytes each; a 4K frame: 66 MB), grown on demand.
+// (Also the longest-first list of the same kernel: an eighth of the launch, at least 4096 slots; a list that overflows is ignored.)
 static int ensure_redo(curvis_ctx* ctx, DeviceState& d, const curvis_sim* sim, size_t rays) {
-    if (sim->precision != CURVIS_PRECISION_F64_FAST || !ctx->tuning.guard || ctx->tuning.fast_variant != 1 ||
+    if (sim->precision != CURVIS_PRECISION_F64_FAST || ctx->tuning.fast_variant != 1 ||
         sim->coordinates != CURVIS_COORDINATES_SPHERICAL) return CURVIS_OK;
+    if (ctx->tuning.longest_first) {
+        const size_t want_long = std::max(size_t(4096), rays / 8);
+        if (want_long > d.d_long_cap) {
+            if (d.d_long) cudaFree(d.d_long);
+            d.d_long = nullptr; d.d_long_cap = 0;
+            CURVIS_CUDA(ctx, cudaMalloc(&d.d_long, want_long * sizeof(unsigned long long)));
+            d.d_long_cap = want_long;
+        }
+    }
+    if (!ctx->tuning.guard) return CURVIS_OK;
     // one slot per ray up to 2^24 rays (128 MB: two 4K frames, half an 8K frame); beyond that an eighth of the launch (the
     // band takes ~1e-3 of the rays, 2.5 % with "guard" = 2); a full list makes the kernel re-integrate in line (correct, slow)
     const size_t want = rays <= (size_t(1) << 24) ? rays : std::max(size_t(1) << 24, rays / 8);
@@ -271,6 +288,10 @@ static void fill_params(const curvis_ctx* ctx, const DeviceState& d, const curvi
         p.redo_capacity = (unsigned long long)ctx->tuning.redo_capacity_limit;
     p.guard_rel = ctx->tuning.guard_rel;
     p.guard_kicked = ctx->tuning.guard >= 2 ? 1u : 0u;
+    const bool longest_first = sim->precision == CURVIS_PRECISION_F64_FAST && ctx->tuning.longest_first && ctx->tuning.fast_variant == 1 &&
+                               sim->coordinates == CURVIS_COORDINATES_SPHERICAL;
+    p.long_list = longest_first ? d.d_long : nullptr;
+    p.long_capacity = longest_first ? d.d_long_cap : 0;
 }
 
 // CURVIS_SAMPLING_BILINEAR reads the backgrounds as float4 (one 128-bit load per tap): staged once
@@ -382,6 +403,7 @@ static void release_device(DeviceState& d) {
     if (d.d_shape_tab32) cudaFree(d.d_shape_tab32);
     if (d.d_inv_tab) cudaFree(d.d_inv_tab);
     if (d.d_redo) cudaFree(d.d_redo);
+    if (d.d_long) cudaFree(d.d_long);
     for (auto& ev : d.chunk_done) if (ev) cudaEventDestroy(ev);
     if (d.ev_begin) cudaEventDestroy(d.ev_begin);
     if (d.ev_end) cudaEventDestroy(d.ev_end);
@@ -819,6 +841,7 @@ extern "C" int curvis_ctx_set_option(curvis_ctx* ctx, const char* key, int64_t v
     else if (k == "fast_regs" && (value == 0 || value == 96 || value == 128)) ctx->tuning.fast_regs = (int)value;
     else if (k == "redo_blocks_per_sm" && value >= 0 && value <= 32) ctx->tuning.redo_blocks_per_sm = (int)value;
     else if (k == "redo_capacity_limit" && value >= 0) ctx->tuning.redo_capacity_limit = value;
+    else if (k == "longest_first" && (value == 0 || value == 1)) ctx->tuning.longest_first = (int)value;
     else if (k == "guard_rel_e15" && value >= 1 && value <= 1000000000000ll) ctx->tuning.guard_rel = (double)value * 1e-15;
     else return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "unknown option or value out of range: " + k);
     return CURVIS_OK;

@@ -107,20 +107,53 @@ __device__ __forceinline__ void rotate_sincos(const RotRegs& rr, double d, doubl
 }
 
 // ---- Interstellar shape function from the per-metric table (shape_table.h: build_interstellar_inverse_table):
-// Y = 1/r(l) and G = |r'(l)| at x = fma(|l|, xscale, xoff), six 128-bit loads and two degree-5 Horner chains.  Every x below the
-// table (the plateau |l| <= a, x <= 0 included) reads the constant row through an unsigned min — no branch, no call; x beyond
-// the table must be kept out by the caller (FrameParams::fast_l_limit).
-__device__ __forceinline__ void interstellar_inverse_lookup(const double2* __restrict__ tab, double xscale, double xoff, double l, double& Y, double& G) {
-    const double x = fma(fabs(l), xscale, xoff);
+// U = 1/r(l)^2 and H = |r'(l)|/r(l)^3 at z = |l| - a, two degree-5 Horner chains on twelve coefficients.  Every z below the table
+// (the plateau |l| <= a, z <= 0 included) reads the constant row through an unsigned min — no branch, no call; z beyond the
+// table must be kept out by the caller (FrameParams::fast_l_limit).
+//
+// The coefficients are CACHED in the lane's registers and fetched again only when the step has left the interval.  Fetching
+// them every step made the L1 data pipe the bound of the Interstellar kernel, not the fp64 pipe: 96 bytes per lane and step
+// are 24 wavefronts of register write-back per warp-step whatever the addresses (profiles/r02_ncu_f64_fast_interstellar_
+// summary.txt: l1tex data-pipe 87 % of peak, fp64 pipe 65 %).  A photon advances x by ~0.3 per step and the intervals are
+// x/256 wide, so beyond x ~ 80 it stays several steps in one interval — and the lanes of a warp, claimed from neighbouring
+// pixels, change intervals on nearly the same steps, so whole quarter-warps skip the fetch.
+struct InverseShapeCache {
+    double2 a01, a23, a45, b01, b23, b45;
+    const double2* tab;
+    unsigned idx;
+    // The table's address is pinned in a register pair: it is read from the table's own last row (where the host wrote it,
+    // shape_table.h: kInvTabSelfRow) with a plain global load, so the compiler cannot know that it equals the kernel parameter.
+    // Left to itself ptxas re-loads the parameter from the constant bank, under the fetch's predicate, in the middle of the
+    // index -> address -> load chain of every step (an empty asm or an opaque zero offset do not stop it).
+    __device__ __forceinline__ void reset(const double2* table) {
+        unsigned long long self;
+        asm volatile("ld.global.u64 %0, [%1];" : "=l"(self) : "l"(table + kInvTabSelfRow * (kShapeTabDoubles / 2)));
+        tab = (const double2*)self;
+        idx = 0xffffffffu;                                                 // (no interval has this index)
+    }
+};
+
+__device__ __forceinline__ void interstellar_inverse_lookup(double a, double l, InverseShapeCache& k, double& U, double& H) {
+    const double x = fabs(l) - a;        // z
     const unsigned hi = (unsigned)__double2hiint(x);
-    const unsigned idx = min((hi >> kShapeTabShift) - kInvTabBase, (unsigned)kInvTabConstRow);
-    const double c = __hiloint2double((int)((hi & ~((1u << kShapeTabShift) - 1u)) | (1u << (kShapeTabShift - 1))), 0);
+    const unsigned idx = min((hi >> kInvTabShift) - kInvTabBase, (unsigned)kInvTabConstRow);
+    const double c = __hiloint2double((int)((hi & ~((1u << kInvTabShift) - 1u)) | (1u << (kInvTabShift - 1))), 0);
     const double t = x - c;
-    const double2* e = tab + (size_t)idx * (kShapeTabDoubles / 2);
-    const double2 a01 = __ldg(e), a23 = __ldg(e + 1), a45 = __ldg(e + 2);
-    const double2 b01 = __ldg(e + 3), b23 = __ldg(e + 4), b45 = __ldg(e + 5);
-    Y = fma(t, fma(t, fma(t, fma(t, fma(t, a45.y, a45.x), a23.y), a23.x), a01.y), a01.x);
-    G = fma(t, fma(t, fma(t, fma(t, fma(t, b45.y, b45.x), b23.y), b23.x), b01.y), b01.x);
+    if (idx != k.idx) {
+        const double2* e = k.tab + idx * (unsigned)(kShapeTabDoubles / 2);   // (32-bit offset: the table is < 2 MB)
+        k.a01 = __ldg(e); k.a23 = __ldg(e + 1); k.a45 = __ldg(e + 2);
+        k.b01 = __ldg(e + 3); k.b23 = __ldg(e + 4); k.b45 = __ldg(e + 5);
+        k.idx = idx;
+    }
+    U = fma(t, fma(t, fma(t, fma(t, fma(t, k.a45.y, k.a45.x), k.a23.y), k.a23.x), k.a01.y), k.a01.x);
+    H = fma(t, fma(t, fma(t, fma(t, fma(t, k.b45.y, k.b45.x), k.b23.y), k.b23.x), k.b01.y), k.b01.x);
+}
+
+// The same lookup without a cache (one-off evaluations: test hook).
+__device__ __forceinline__ void interstellar_inverse_lookup(const double2* __restrict__ tab, double a, double l, double& U, double& H) {
+    InverseShapeCache k;
+    k.reset(tab);
+    interstellar_inverse_lookup(a, l, k, U, H);
 }
 
 // d >= 0 by construction (a product of squares and a positive radius), so the high word is

@@ -20,7 +20,8 @@ struct DeviceCounters {
     unsigned long long n_reintegrated; // CURVIS_PRECISION_F64_FAST: rays pushed onto the re-integration list (= its length)
     unsigned long long redo_next;      // work queue of the re-integration launch
     unsigned long long n_kicked;       // CURVIS_PRECISION_F64_FAST: rays with stiffness >= 1
-    unsigned long long _pad[7];
+    unsigned long long n_long;         // CURVIS_PRECISION_F64_FAST: length of the longest-first list (render_f64_fast.cu: collect_long_rays)
+    unsigned long long _pad[6];
 };
 
 struct Background {
@@ -78,8 +79,8 @@ struct FrameParams {
     // Interstellar shape-function table of CURVIS_PRECISION_F64_FAST (shape_table.h), resident per device
     const double2* shape_tab;
     const float4* shape_tab32;   // the fp32 edition for CURVIS_PRECISION_F32
-    // per-metric table of 1/r and r' (shape_table.h: build_interstellar_inverse_table), x = fma(|l|, d_xscale, d_xoff), and
-    // the |l| beyond which x leaves the table (+inf for the other metrics)
+    // per-metric table of 1/r^2 and r'/r^3 as functions of z = |l| - a (shape_table.h: build_interstellar_inverse_table), and
+    // the |l| beyond which z leaves the table (+inf for the other metrics)
     const double2* inv_tab;
     double d_xoff, fast_l_limit;
     // scene (systems.rs:70-71): [0] = background_positive, [1] = background_negative
@@ -102,6 +103,10 @@ struct FrameParams {
     double guard_rel;        // relative state error budget of a ray with stiffness < 1
     uint32_t guard_kicked;   // 1: rays with stiffness >= 1 are re-integrated too ("guard" = 2)
     uint32_t _pad3;
+    // longest-first refill (render_f64_fast.cu): a pre-pass kernel lists the rays predicted to graze a coordinate pole (the
+    // 10^4-step stragglers); the work queue hands those out first.  Length in counters->n_long; a list that overflowed is ignored
+    unsigned long long* long_list;
+    unsigned long long long_capacity;
     // list mode (the second launch): ray i of the launch is ray ray_list[i] of the tile; the launch holds
     // *ray_list_count rays (device-resident count: the host never learns it before launching)
     const unsigned long long* ray_list;

@@ -24,6 +24,8 @@ struct LaunchTuning {
     int fast_regs = 0;       // CURVIS_PRECISION_F64_FAST register budget: 96 (5 CTAs per SM; Ellis: 50-instruction step, 36.4 ms per 4K
                              // frame) or 128 (4 CTAs; Ellis 47 instructions, 37.5 ms; Interstellar 71 instead of 76: 59.2 against
                              // 60.2 ms); 0 (default) = 96 for Ellis / Flat, 128 for Interstellar
+    int longest_first = 1;   // CURVIS_PRECISION_F64_FAST: 1 (default) = rays predicted to graze a coordinate pole are listed by a pre-pass
+                             // kernel and claimed first (launches of >= 2^15 rays); 0 = rays are claimed in index order
     int fast_variant = 1;    // CURVIS_PRECISION_F64_FAST: 0 sin/cos from theta every step; 1 (default) (sin, cos) carried and
                              // rotated by the step's small dtheta, re-derived from theta once per window
 };
@@ -36,6 +38,7 @@ cudaError_t launch_render_f32(const FrameParams& p, int metric_kind, const Launc
 
 // fp64 with a regrouped right-hand side, CURVIS_PRECISION_F64_FAST (render_f64_fast.cu) — extension.
 cudaError_t launch_render_f64_fast(const FrameParams& p, int metric_kind, const LaunchTuning& t, int sm_count, cudaStream_t stream);
+bool render_f64_fast_has_prepass(const FrameParams& p, const LaunchTuning& t);   // one more kernel in front of it (longest-first list)
 
 // fp64, chart-free angular state, CURVIS_COORDINATES_CARTESIAN (render_f64_cart.cu) — extension ("pole-safe").
 cudaError_t launch_render_cart(const FrameParams& p, int metric_kind, const LaunchTuning& t, int sm_count, cudaStream_t stream);

@@ -175,18 +175,19 @@ __global__ void __launch_bounds__(kBlockCart) render_rows_f64_cart(const __grid_
 // decision boundary (tests/test_gpu_extensions.py states the bar: there is no guard band here — an extension's extension).
 struct CartEllis {
     using Shape64 = ShapeEllis;
-    static __device__ __forceinline__ void factors(const FrameParams& p, double l, double& u, double& f) {
+    struct Cache { __device__ __forceinline__ void reset(const double2*) {} };
+    static __device__ __forceinline__ void factors(const FrameParams& p, double l, Cache&, double& u, double& f) {
         u = rcp_1ulp(fma(l, l, p.d_rho2));
         f = l * (u * u);                         // r'/r^3 = l / r^4
     }
 };
 struct CartInterstellar {
     using Shape64 = ShapeInterstellar;
-    static __device__ __forceinline__ void factors(const FrameParams& p, double l, double& u, double& f) {
-        double Y, G;
-        interstellar_inverse_lookup(p.inv_tab, p.d_xscale, p.d_xoff, l, Y, G);
-        u = Y * Y;
-        f = copysign(G, l) * (Y * u);
+    using Cache = InverseShapeCache;    // the table's coefficients stay in registers while the photon stays in one interval
+    static __device__ __forceinline__ void factors(const FrameParams& p, double l, Cache& cache, double& u, double& f) {
+        double H;
+        interstellar_inverse_lookup(p.a, l, cache, u, H);
+        f = copysign(H, l);
     }
 };
 
@@ -252,10 +253,12 @@ __global__ void __launch_bounds__(kBlockCart, 5) render_rows_cart_fast(const __g
             // (a ray already past the Interstellar table skips the regrouped steps: handled below)
             const bool near = (abs_hi(q.l) >= gate) && !(fabs(q.l) < p.fast_l_limit);
             if (!near) {
+                typename Fast::Cache cache;
+                cache.reset(p.inv_tab);
 #pragma unroll 1
                 do {
                     double u, f;
-                    Fast::factors(p, q.l, u, f);
+                    Fast::factors(p, q.l, cache, u, f);
                     const double cx = fma(q.jy, q.nz, -(q.jz * q.ny));
                     const double cy = fma(q.jz, q.nx, -(q.jx * q.nz));
                     const double cz = fma(q.jx, q.ny, -(q.jy * q.nx));

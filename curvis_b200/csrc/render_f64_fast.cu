@@ -36,7 +36,7 @@ namespace curvis {
 namespace {
 
 constexpr int kBlockFast = 128;
-constexpr double kLongRaySin = 0.03;   // refill: rays whose orbit comes within asin(0.03) of the polar axis are claimed first
+constexpr double kLongRaySin = 0.03;   // refill: near-critical rays whose orbit comes within asin(0.03) of the polar axis are claimed first
 constexpr unsigned kFullFast = 0xffffffffu;
 
 // Shape policies of the fast step.  factors() returns, for the current l and sin^2 theta:
@@ -59,7 +59,8 @@ struct FastEllis {   // metrics.rs:417-421 : r^2 = rho^2 + l^2, r' = l/r  =>  r'
     // divisor d = r^2 sin^2, finish() turns y0 = 1/d into w, u, v and f = r'/r^3 (no delta: the
     // momenta are pre-scaled, see fast_window_scaled).
     struct Pre { double r2; };
-    static __device__ __forceinline__ double prepare(const FrameParams& p, double l, double s2, Pre& pre) {
+    struct Cache { __device__ __forceinline__ void reset(const double2*) {} };
+    static __device__ __forceinline__ double prepare(const FrameParams& p, double l, double s2, Pre& pre, Cache&) {
         pre.r2 = fma(l, l, p.d_rho2);
         return pre.r2 * s2;
     }
@@ -140,22 +141,23 @@ struct FastInterstellar {   // metrics.rs:461-485 with the uniform divisor pi*m 
         shape(p, l, r, rp);
         return factors_from_r(p, r, rp, s2, w, u, v, ud, fd);
     }
-    // fast_variant 1 (default): Y = 1/r and G = |r'| from the per-metric table (shape_table.h) — six 128-bit loads and two
-    // degree-5 Horner chains; the step's one reciprocal is then 1/sin^2 theta alone.  No branch, no call: every x below the
-    // table (the plateau, x <= 0 included) reads the constant row through an unsigned min; x beyond it never gets here
-    // (beyond(): the kernel's radius gate).  42 fp64-pipe instructions per step.
-    struct Pre { double y, rp; };
-    static __device__ __forceinline__ double prepare(const FrameParams& p, double l, double s2, Pre& pre) {
-        double G;
-        interstellar_inverse_lookup(p.inv_tab, p.d_xscale, p.d_xoff, l, pre.y, G);
-        pre.rp = copysign(G, l);
+    // fast_variant 1 (default): U = 1/r^2 and H = |r'|/r^3 from the per-metric table (shape_table.h) — two degree-5 Horner chains on
+    // coefficients cached in registers while the photon stays in one interval (fast_f64.cuh); the step's one reciprocal is then
+    // 1/sin^2 theta alone.  No call: every x below the table (the plateau, x <= 0 included) reads the constant row through an
+    // unsigned min; x beyond it never gets here (beyond(): the kernel's radius gate).  41 fp64-pipe instructions per step.
+    struct Pre { double u, f; };
+    using Cache = InverseShapeCache;
+    static __device__ __forceinline__ double prepare(const FrameParams& p, double l, double s2, Pre& pre, Cache& cache) {
+        double H;
+        interstellar_inverse_lookup(p.a, l, cache, pre.u, H);
+        pre.f = copysign(H, l);        // r'/r^3
         return s2;
     }
     static __device__ __forceinline__ void finish(const Pre& pre, double y0, double, double, double& w, double& u, double& v, double& f) {
         v = y0;                        // 1/sin^2
-        u = pre.y * pre.y;             // 1/r^2
+        u = pre.u;                     // 1/r^2
         w = u * v;
-        f = pre.rp * (pre.y * u);      // r'/r^3
+        f = pre.f;
     }
     static __device__ __forceinline__ bool beyond(const FrameParams& p, double l) { return !(fabs(l) < p.fast_l_limit); }
 };
@@ -166,7 +168,8 @@ struct FastFlat {   // metrics.rs:501-505: r = l, r' = 1 (r may be negative: tak
         return factors_from_r(p, l, 1.0, s2, w, u, v, ud, fd);
     }
     using Pre = PreFromR;
-    static __device__ __forceinline__ double prepare(const FrameParams&, double l, double s2, Pre& pre) {
+    struct Cache { __device__ __forceinline__ void reset(const double2*) {} };
+    static __device__ __forceinline__ double prepare(const FrameParams&, double l, double s2, Pre& pre, Cache&) {
         pre.r = l; pre.rp = 1.0;
         return l * s2;
     }
@@ -219,13 +222,15 @@ __device__ __forceinline__ uint32_t fast_window_scaled(const FrameParams& p, con
     // phi += P_phi * w every step (:240): the w's are summed (a two-operand DADD issues faster than a DFMA with three
     // distinct registers) and folded into phi once, by the caller, when the window is left
     double wsum = 0.0;
+    typename Fast::Cache cache;   // Interstellar: the shape table's coefficients of the interval the photon is in
+    cache.reset(p.inv_tab);
     for (;;) {
         if (abs_hi(q.th) >= pow2_hi(30)) { slow = true; break; }
         double sn, cn;
         sincos_fast(q.th, sn, cn);
         typename Fast::Pre pre;
         double s2 = sn * sn;
-        double d = Fast::prepare(p, q.l, s2, pre);
+        double d = Fast::prepare(p, q.l, s2, pre, cache);
         if (!in_window_nonneg(d)) { slow = true; break; }
         double dth;
         for (;;) {
@@ -246,7 +251,7 @@ __device__ __forceinline__ uint32_t fast_window_scaled(const FrameParams& p, con
             --left;
             asm("" : "+r"(left));   // one induction variable (the optimiser otherwise keeps two copies of the counter)
             s2 = sn * sn;
-            d = Fast::prepare(p, q.l, s2, pre);
+            d = Fast::prepare(p, q.l, s2, pre, cache);
             if ((left == 0u) | (abs_hi(q.l) >= gate) | (abs_hi(dth) >= pow2_hi(-4)) | !in_window_nonneg(d)) break;
         }
         if (abs_hi(q.l) >= gate) { near = true; break; }        // |l| >= R (1 - 2^-20), or past the shape table, or NaN: the caller's business
@@ -369,6 +374,13 @@ __global__ void __launch_bounds__(kBlockFast, MinBlocks) render_rows_f64_fast(co
     const unsigned gate = (R_gate >= 0.0) ? abs_hi(R_gate) : 0u;
     const bool guard = (Variant == 1) && p.redo_list != nullptr;
     const float finf = __int_as_float(0x7f800000);
+    // longest-first list (written by collect_long_rays earlier on the stream); a list that overflowed is ignored
+    unsigned long long n_long = 0;
+    if (p.long_list) {
+        n_long = p.counters->n_long;
+        if (n_long > p.long_capacity) n_long = 0;
+    }
+    const unsigned long long n_tickets = launch_rays + n_long;
 
     // Per-ray state the step loop never reads lives in shared memory (fast_variant 1): the kernel sits at the 96-register
     // limit of five resident CTAs per SM, and every register the loop does not need is one constant it can keep pinned.
@@ -407,13 +419,15 @@ __global__ void __launch_bounds__(kBlockFast, MinBlocks) render_rows_f64_fast(co
             state = 0;
         }
 
-        // ---- refill.  The queue is walked TWICE (tickets 0..N-1, then N..2N-1 for the same N rays): the first walk hands out
-        // only the rays predicted to be long — a photon whose angular momentum points almost along the polar axis
-        // (min sin theta = |p_phi| / L < kLongRaySin) will be kicked by the coordinate pole, and kicked rays are where the
-        // 10^4-step stragglers live (profiles/r02_latency_probe.json: the rows next to the image's central row take 10x the
-        // time of any other) — the second walk everything else.  Longest first: a 20,000-step ray needs 4 ms at full
-        // occupancy whenever it starts, so on a small tile (one 4K frame over 8 GPUs: 5 ms) it must start at once.  A
-        // rejected ticket costs the prediction only (the pixel's unnormalised direction: ~30 instructions).
+        // ---- refill, longest first.  A pre-pass kernel (collect_long_rays, below) has listed the rays predicted to be long:
+        // near-critical photons whose orbit plane almost contains the polar axis (ray_predicted_long, geodesic_f64.cuh) — the
+        // rows next to the image's central row take 10x the time of any other (profiles/r02_latency_probe.json).  The queue's
+        // first n_long tickets hand out that list, the rest walk the ray indices and skip the listed ones.  A 20,000-step ray
+        // needs 4 ms at full occupancy whenever it starts, so on a small tile (one 4K frame over 8 GPUs: 5 ms) it must start at
+        // once.  A skipped ticket costs the prediction only (the pixel's unnormalised direction: ~40 instructions), and the
+        // lane takes another.  The list must stay SHORT (here 0.3 % of a frame): listing every pole-grazing ray (2.5 %) and
+        // starting them all at once cost 2-4 % of the frame — for two generations every warp of the GPU was in the slow,
+        // divergent pole-crossing code at the same time, with no regular warps to hide its latency behind.
         unsigned idle = __ballot_sync(kFullFast, state == 0);
         if (idle) {
             while (idle && !drained) {
@@ -423,26 +437,30 @@ __global__ void __launch_bounds__(kBlockFast, MinBlocks) render_rows_f64_fast(co
                 base = __shfl_sync(kFullFast, base, leader);
                 if (state == 0) {
                     const unsigned long long ticket = base + (unsigned long long)__popc(idle & lt_mask);
-                    if (ticket < 2ull * launch_rays) {
-                        const bool first_walk = ticket < launch_rays;
-                        const unsigned long long idx = first_walk ? ticket : ticket - launch_rays;
-                        const bool long_ray = ray_grazes_pole(p, idx, tile_rays, kLongRaySin * kLongRaySin);
-                        if (long_ray == first_walk) {
-                        new_photon_for_ray(p, idx, tile_rays, q);
-                        if (Variant == 1) {            // momenta pre-scaled by delta (fast_window_scaled)
-                            q.pl = q.pl * p.delta; q.pth = q.pth * p.delta; q.pph = q.pph * p.delta;
-                            q.pph2 = q.pph * q.pph;
-                            cold.ph = q.ph; cold.pph = q.pph; cold.ray = idx; cold.margin = finf;
-                        } else {
-                            ray = idx;
+                    if (ticket < n_tickets) {
+                        unsigned long long idx;
+                        bool take = true;
+                        if (ticket < n_long) idx = p.long_list[ticket];
+                        else {
+                            idx = ticket - n_long;
+                            if (n_long) take = !ray_predicted_long(p, idx, tile_rays, kLongRaySin * kLongRaySin);
                         }
-                        remaining = p.max_iterations;
-                        wmax_hi = 0;
-                        state = (remaining == 0) ? 2 : 1;
+                        if (take) {
+                            new_photon_for_ray(p, idx, tile_rays, q);
+                            if (Variant == 1) {            // momenta pre-scaled by delta (fast_window_scaled)
+                                q.pl = q.pl * p.delta; q.pth = q.pth * p.delta; q.pph = q.pph * p.delta;
+                                q.pph2 = q.pph * q.pph;
+                                cold.ph = q.ph; cold.pph = q.pph; cold.ray = idx; cold.margin = finf;
+                            } else {
+                                ray = idx;
+                            }
+                            remaining = p.max_iterations;
+                            wmax_hi = 0;
+                            state = (remaining == 0) ? 2 : 1;
                         }
                     }
                 }
-                if (base + (unsigned long long)__popc(idle) >= 2ull * launch_rays) drained = true;
+                if (base + (unsigned long long)__popc(idle) >= n_tickets) drained = true;
                 idle = __ballot_sync(kFullFast, state == 0);
             }
             if (__ballot_sync(kFullFast, state != 0) == 0u) break;
@@ -509,6 +527,31 @@ __global__ void __launch_bounds__(kBlockFast, MinBlocks) render_rows_f64_fast(co
     flush_tally(p, tally, lane);
 }
 
+// Pre-pass of the longest-first refill: the indices of the rays predicted to graze a coordinate pole, appended to
+// FrameParams::long_list in no particular order (one aggregated atomic per warp); counters->n_long counts every such ray,
+// listed or not (the render kernel ignores a list that overflowed).
+__global__ void __launch_bounds__(256) collect_long_rays(const __grid_constant__ FrameParams p) {
+    const unsigned long long tile_rays = (unsigned long long)(p.row_end - p.row_begin) * p.width;
+    const unsigned long long launch_rays = tile_rays * (p.n_frames ? p.n_frames : 1u);
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    // (whole warps iterate together: the bound is rounded up to a multiple of 32)
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < ((launch_rays + 31ull) & ~31ull); i += stride) {
+        const bool is_long = i < launch_rays && ray_predicted_long(p, i, tile_rays, kLongRaySin * kLongRaySin);
+        const unsigned m = __ballot_sync(kFullFast, is_long);
+        if (m) {
+            unsigned long long base = 0;
+            const int leader = __ffs(m) - 1;
+            if ((int)lane == leader) base = atomicAdd(&p.counters->n_long, (unsigned long long)__popc(m));
+            base = __shfl_sync(kFullFast, base, leader);
+            const unsigned long long slot = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+            if (is_long && slot < p.long_capacity) p.long_list[slot] = i;
+        }
+    }
+}
+
+constexpr unsigned long long kLongestFirstMinRays = 1ull << 15;   // smaller launches (the efficient renderer's table) skip the pre-pass
+
 template <class Fast, int Variant, int MinBlocks>
 cudaError_t launch_fast_variant(const FrameParams& p, int sm_count, int blocks_per_sm_override, cudaStream_t stream) {
     static int blocks_per_sm_auto = 0;
@@ -523,7 +566,15 @@ cudaError_t launch_fast_variant(const FrameParams& p, int sm_count, int blocks_p
     unsigned long long want = (rays + kBlockFast - 1) / kBlockFast;
     unsigned long long cap = (unsigned long long)sm_count * (unsigned long long)blocks_per_sm;
     const unsigned grid = (unsigned)(want < cap ? (want ? want : 1) : cap);
-    render_rows_f64_fast<Fast, Variant, MinBlocks><<<grid, kBlockFast, 0, stream>>>(p);
+    if (Variant == 1 && p.long_list && rays >= kLongestFirstMinRays) {
+        const unsigned long long blocks = (rays + 255) / 256;
+        collect_long_rays<<<(unsigned)(blocks < 8ull * sm_count ? blocks : 8ull * sm_count), 256, 0, stream>>>(p);
+        render_rows_f64_fast<Fast, Variant, MinBlocks><<<grid, kBlockFast, 0, stream>>>(p);
+    } else {
+        FrameParams q = p;
+        q.long_list = nullptr;
+        render_rows_f64_fast<Fast, Variant, MinBlocks><<<grid, kBlockFast, 0, stream>>>(q);
+    }
     return cudaGetLastError();
 }
 
@@ -552,18 +603,12 @@ __global__ void debug_shape_kernel(const double2* tab, int which, const double* 
 __global__ void debug_inverse_shape_kernel(const double2* tab, const double* x, double* y, double* g, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    FrameParams p;
-    p.inv_tab = tab;
-    p.d_xscale = 1.0; p.d_xoff = 0.0;          // prepare() reads x = fma(|l|, 1, 0): feed |l| = x (x < 0 through the sign below)
-    FastInterstellar::Pre pre;
+    // the lookup reads z = |l| - a: feed |l| = z, a = 0; negative z (the plateau) cannot be expressed by |l| and goes through a
     const double xi = x[i];
-    if (xi >= 0.0 || xi != xi) {
-        FastInterstellar::prepare(p, xi, 1.0, pre);
-    } else {                                      // negative x (the plateau): |l| cannot express it, shift through xoff
-        p.d_xoff = xi;
-        FastInterstellar::prepare(p, 0.0, 1.0, pre);
-    }
-    y[i] = pre.y; g[i] = fabs(pre.rp);
+    double U, H;
+    if (xi >= 0.0 || xi != xi) interstellar_inverse_lookup(tab, 0.0, xi, U, H);
+    else interstellar_inverse_lookup(tab, -xi, 0.0, U, H);
+    y[i] = U; g[i] = H;
 }
 
 cudaError_t launch_debug_inverse_shape(const double2* tab, const double* x, double* y, double* g, size_t n, cudaStream_t stream) {
@@ -576,6 +621,13 @@ cudaError_t launch_debug_shape(const double2* tab, int which, const double* x, d
     if (n == 0) return cudaSuccess;
     debug_shape_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(tab, which, x, out, n);
     return cudaGetLastError();
+}
+
+// Whether launch_render_f64_fast launches the longest-first pre-pass in front of the render kernel (the launch counter's business).
+bool render_f64_fast_has_prepass(const FrameParams& p, const LaunchTuning& t) {
+    const double ad = p.delta < 0.0 ? -p.delta : p.delta;
+    const unsigned long long rays = (unsigned long long)(p.row_end - p.row_begin) * p.width * (p.n_frames ? p.n_frames : 1u);
+    return t.fast_variant == 1 && (ad >= 0x1p-100 && ad <= 0x1p100) && p.long_list && rays >= kLongestFirstMinRays;
 }
 
 cudaError_t launch_render_f64_fast(const FrameParams& p, int metric_kind, const LaunchTuning& t, int sm_count, cudaStream_t stream) {

@@ -80,74 +80,76 @@ void build_interstellar_shape_table(double* out) { build<kShapeTabDegree + 1, do
 
 void build_interstellar_inverse_table(double rho, double m, double* out) {
     constexpr int N = kShapeTabDegree + 1;
-    const int per_binade = 1 << kShapeTabK;
+    const int per_binade = 1 << kInvTabK;
     const long double rho_l = rho, m_l = m;
-    auto inv_r = [rho_l, m_l](long double x) { return 1.0L / (rho_l + m_l * shape_f(x)); };
+    const long double xscale = 2.0L / (kPiL * m_l);                 // x = 2 (|l| - a) / (pi m), metrics.rs:463
+    auto inv_r2 = [=](long double z) { const long double r = rho_l + m_l * shape_f(z * xscale); return 1.0L / (r * r); };
+    auto force = [=](long double z) { const long double r = rho_l + m_l * shape_f(z * xscale); return shape_g(z * xscale) / (r * r * r); };
     size_t idx = 0;
-    for (int e = kInvTabEmin; e < kShapeTabEmax; ++e) {
-        const long double x0 = ldexpl(1.0L, e);
-        const int wexp = e - kShapeTabK - 1;
+    for (int e = kInvTabEmin; e < kInvTabEmax; ++e) {
+        const long double z0 = ldexpl(1.0L, e);
+        const int wexp = e - kInvTabK - 1;
         const long double w = ldexpl(1.0L, wexp);
         for (int j = 0; j < per_binade; ++j, ++idx) {
-            const long double c = x0 + (2 * j + 1) * w;
-            long double my[N], mg[N];
-            fit<N>(inv_r, c, w, my);
-            fit<N>(shape_g, c, w, mg);
+            const long double c = z0 + (2 * j + 1) * w;
+            long double mu[N], mh[N];
+            fit<N>(inv_r2, c, w, mu);
+            fit<N>(force, c, w, mh);
             double* o = out + idx * 2 * N;
             for (int k = 0; k < N; ++k) {
-                o[k] = (double)ldexpl(my[k], -k * wexp);
-                o[N + k] = (double)ldexpl(mg[k], -k * wexp);
+                o[k] = (double)ldexpl(mu[k], -k * wexp);
+                o[N + k] = (double)ldexpl(mh[k], -k * wexp);
             }
         }
     }
     double* o = out + kInvTabConstRow * 2 * N;     // the plateau: r = rho, r' = 0 (metrics.rs:470, :482)
     for (int k = 0; k < 2 * N; ++k) o[k] = 0.0;
-    o[0] = (double)(1.0L / rho_l);
+    o[0] = (double)(1.0L / (rho_l * rho_l));
+    for (int k = 0; k < 2 * N; ++k) out[kInvTabSelfRow * 2 * N + k] = 0.0;   // the device address goes here after the upload
 }
 
-double interstellar_table_l_limit(double m, double a) {
-    const double xscale = 2.0 / (3.14159265358979323846 * m);
-    return a + ldexp(1.0, kShapeTabEmax) * (1.0 - 0x1p-20) / xscale;
+double interstellar_table_l_limit(double, double a) {
+    return a + ldexp(1.0, kInvTabEmax) * (1.0 - 0x1p-20);
 }
 
 void build_interstellar_shape_table_f32(float* out) { build<kShapeTab32Degree + 1, float>(out, kShapeTab32K); }
 
 }  // namespace curvis
 
-// Test hook (include/curvis_gpu.h): the host-built table evaluated on the host exactly as the kernel
-// evaluates it (index from the high word, exact t, two fma Horner chains).  No GPU involved; it lets
-// the CPU test-suite check the generator.  Returns 0 when x is outside the table's range.
-// Test hook: the per-metric inverse table evaluated on the host exactly as FastInterstellar::prepare evaluates it
-// (x = fma(|l|, xscale, xoff) is the caller's business: this takes x).  y[i] = 1/(rho + m F(x)), g[i] = (2/pi) atan x;
-// x below 2^kInvTabEmin (or <= 0) reads the constant row.  Returns 1 when every x was below 2^kShapeTabEmax.
-extern "C" int curvis_debug_inverse_table_host(double rho, double m, const double* x, double* y, double* g, size_t n) {
+// Test hook: the per-metric table evaluated on the host exactly as FastInterstellar::prepare evaluates it (z = |l| - a is the
+// caller's business: this takes z).  y[i] = 1/(rho + m F(x))^2, g[i] = (2/pi) atan x / (rho + m F(x))^3 at x = 2 z / (pi m);
+// z below 2^kInvTabEmin (or <= 0) reads the constant row.  Returns 1 when every z was below 2^kInvTabEmax.
+extern "C" int curvis_debug_inverse_table_host(double rho, double m, const double* z, double* y, double* g, size_t n) {
     using namespace curvis;
     double* table = new double[kInvTabIntervals * kShapeTabDoubles];
     build_interstellar_inverse_table(rho, m, table);
     int all = 1;
     for (size_t i = 0; i < n; ++i) {
         unsigned long long bits;
-        __builtin_memcpy(&bits, &x[i], 8);
+        __builtin_memcpy(&bits, &z[i], 8);
         const unsigned hi = (unsigned)(bits >> 32);
-        unsigned idx = (hi >> kShapeTabShift) - kInvTabBase;
-        if (x[i] >= ldexp(1.0, kShapeTabEmax)) { y[i] = g[i] = NAN; all = 0; continue; }
+        unsigned idx = (hi >> kInvTabShift) - kInvTabBase;
+        if (z[i] >= ldexp(1.0, kInvTabEmax)) { y[i] = g[i] = NAN; all = 0; continue; }
         if (idx > (unsigned)kInvTabConstRow) idx = (unsigned)kInvTabConstRow;
-        const unsigned long long cbits = (unsigned long long)((hi & ~((1u << kShapeTabShift) - 1u)) | (1u << (kShapeTabShift - 1))) << 32;
+        const unsigned long long cbits = (unsigned long long)((hi & ~((1u << kInvTabShift) - 1u)) | (1u << (kInvTabShift - 1))) << 32;
         double c;
         __builtin_memcpy(&c, &cbits, 8);
-        const double t = x[i] - c;
+        const double t = z[i] - c;
         const double* a = table + (size_t)idx * kShapeTabDoubles;
-        double Y = a[kShapeTabDegree], G = a[kShapeTabDoubles - 1];
+        double U = a[kShapeTabDegree], H = a[kShapeTabDoubles - 1];
         for (int k = kShapeTabDegree - 1; k >= 0; --k) {
-            Y = fma(t, Y, a[k]);
-            G = fma(t, G, a[kShapeTabDegree + 1 + k]);
+            U = fma(t, U, a[k]);
+            H = fma(t, H, a[kShapeTabDegree + 1 + k]);
         }
-        y[i] = Y; g[i] = G;
+        y[i] = U; g[i] = H;
     }
     delete[] table;
     return all;
 }
 
+// Test hook (include/curvis_gpu.h): the host-built table evaluated on the host exactly as the kernel
+// evaluates it (index from the high word, exact t, two fma Horner chains).  No GPU involved; it lets
+// the CPU test-suite check the generator.  Returns 0 when x is outside the table's range.
 extern "C" int curvis_debug_shape_table_host(const double* x, double* f, double* g, size_t n) {
     using namespace curvis;
     static double* table = nullptr;

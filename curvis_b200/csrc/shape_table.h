@@ -31,21 +31,33 @@ constexpr unsigned kShapeTabBase = (unsigned)(1023 + kShapeTabEmin) << kShapeTab
 void build_interstellar_shape_table(double* out);
 
 // The per-metric edition the default fast kernel (fast_variant 1) reads: what the regrouped step needs from the shape
-// function is 1/r(l) and r'(l), so for a given (rho, m) the table holds, on the same intervals,
-//     Y(x) = 1 / (rho + m F(x))      and      G(x),
-// degree 5 each.  The step then takes its one reciprocal of sin^2 theta alone (u = Y^2, w = u / sin^2, r'/r^3 = G Y^3):
-// four fp64 instructions fewer than going through r, and the metric parameters leave the loop.  The range reaches down
-// to 2^kInvTabEmin, and one extra CONSTANT row (Y = 1/rho, G = 0: the plateau |l| <= a of the throat, metrics.rs:470 / :482)
-// receives every x below it — zero, negative, denormal — through an unsigned min of the index, so the step has no
-// branch and no call for the plateau; x >= 2^kShapeTabEmax is kept out of the loop by the step's radius gate.
-// 1/r behaves like 1/x for large x: the degree-5 interpolation error is ~2^-53 (the t^6 coefficient of 1/(1+t) is 1),
-// checked against long double in tests/test_abi_host.py (host) and tests/test_gpu_fast64.py (device): <= 2.5 ulp.
-constexpr int kInvTabEmin = -40;
-constexpr size_t kInvTabConstRow = (size_t)(kShapeTabEmax - kInvTabEmin) << kShapeTabK;   // index of the constant row
-constexpr size_t kInvTabIntervals = kInvTabConstRow + 1;
-constexpr unsigned kInvTabBase = (unsigned)(1023 + kInvTabEmin) << kShapeTabK;
+// function is 1/r(l)^2 (theta and phi advance by it) and r'(l)/r(l)^3 (the radial force), so for a given (rho, m) the table
+// holds exactly those two, as functions of z = |l| - a (the distance from the throat's plateau, ONE fp64 subtraction in the
+// step; x = 2 z / (pi m) is folded into the coefficients):
+//     U(z) = 1 / (rho + m F(x))^2      and      H(z) = G(x) / (rho + m F(x))^3,
+// degree 5 each, on 2^kInvTabK = 256 intervals per binade of z in [2^kInvTabEmin, 2^kInvTabEmax).  The step then takes its one
+// reciprocal of sin^2 theta alone (w = U / sin^2, r'/r^3 = sign(l) H): seven fp64 instructions fewer than going through r, and
+// the metric parameters leave the loop.  One extra CONSTANT row (U = 1/rho^2, H = 0: the plateau |l| <= a of the throat,
+// metrics.rs:470 / :482) receives every z below the range — zero, negative, denormal — through an unsigned min of the index, so the
+// step has no branch and no call for the plateau (at z = 2^-44 the neglected m F is < 1e-20 m for every m >= 1e-3); z >=
+// 2^kInvTabEmax is kept out of the loop by the step's radius gate (interstellar_table_l_limit).  Interval width: U behaves like
+// z^-2 and H like z^-3 for large z, whose seventh Taylor coefficients are 7 and 28 (1/z: 1), so the degree-5 interpolation
+// error on 2^-7-wide intervals would be 7 and 28 units of 2^-53; on 2^-8-wide intervals it is 2^-56 and 2^-54 and the result
+// is the rounding of the Horner evaluation.  Checked against long double in tests/test_abi_host.py (host) and
+// tests/test_gpu_fast64.py (device, bit-identical to the host evaluation).
+// (Round-2 history: the first per-metric table held Y = 1/r and G = |r'| as functions of x on 128 intervals per binade;
+// u = Y^2 and r'/r^3 = G Y^3 cost three more multiplications per step, and x = fma(|l|, xscale, xoff) needed its addend
+// re-loaded into a vector register every step.)
+constexpr int kInvTabK = 8;                   // 2^8 intervals per binade
+constexpr int kInvTabEmin = -44;
+constexpr int kInvTabEmax = 14;               // z < 16384
+constexpr unsigned kInvTabShift = 20 - kInvTabK;
+constexpr size_t kInvTabConstRow = (size_t)(kInvTabEmax - kInvTabEmin) << kInvTabK;   // index of the constant row
+constexpr size_t kInvTabSelfRow = kInvTabConstRow + 1;   // one more row: its first 8 bytes hold the device address of the table itself (fast_f64.cuh)
+constexpr size_t kInvTabIntervals = kInvTabConstRow + 2;
+constexpr unsigned kInvTabBase = (unsigned)(1023 + kInvTabEmin) << kInvTabK;
 void build_interstellar_inverse_table(double rho, double m, double* out);   // out[kInvTabIntervals * kShapeTabDoubles]
-// |l| below which x = (|l| - a) 2/(pi m) stays inside the table (with a margin of one part in 2^20)
+// |l| below which z = |l| - a stays inside the table (with a margin of one part in 2^20)
 double interstellar_table_l_limit(double m, double a);
 
 // The fp32 edition for CURVIS_PRECISION_F32 (render_f32.cu): 2^4 intervals per binade of the same range,

@@ -382,6 +382,8 @@ int curvis_measure_fma_peak(curvis_ctx* ctx, double* fp64_tflops, double* fp32_t
  *   "redo_blocks_per_sm": resident CTAs per SM of the re-integration launch (default 2)
  *   "redo_capacity_limit": test knob — caps the re-integration list (0 = automatic: one slot per ray up to 2^24 rays); a ray
  *                     that finds the list full is re-integrated in line by the fast kernel (same result, slower)
+ *   "longest_first":  CURVIS_PRECISION_F64_FAST: 1 (default) a pre-pass kernel lists the rays predicted to graze a coordinate
+ *                     pole (the 10^4-step stragglers) and the work queue hands them out first; 0 rays are claimed in index order
  *   "blocks_per_sm":  resident CTAs per SM of the persistent grid (0 = occupancy maximum)
  *   "window":         Euler steps between two refill points of a warp (0 = default: 32; for
  *                     CURVIS_PRECISION_F64_FAST 32..128, growing with the expected ray length)
@@ -403,13 +405,13 @@ int curvis_ctx_set_option(curvis_ctx* ctx, const char* key, int64_t value);
  *   15 / 16 the same two functions as CURVIS_PRECISION_F32 evaluates them (fp32 table; a is rounded to float)   */
 int curvis_debug_eval(curvis_ctx* ctx, int op, const double* a, const double* b, double* out, size_t n);
 
-/* Test hooks of the per-metric Interstellar table CURVIS_PRECISION_F64_FAST reads (csrc/shape_table.h): y[i] = 1/r =
- * 1/(rho + m (x atan x - ln(1 + x^2)/2)), g[i] = (2/pi) atan x at x[i] = 2(|l| - a)/(pi m); every x below 2^-40 (zero and
- * negative included: the plateau |l| <= a) reads the constant row y = 1/rho, g = 0.  _host: the table built and evaluated
- * on the host with the kernel's arithmetic, no GPU needed (returns 1 when every x was below the table's end 2^16, else 0
+/* Test hooks of the per-metric Interstellar table CURVIS_PRECISION_F64_FAST reads (csrc/shape_table.h): with r = rho + m (x atan x
+ * - ln(1 + x^2)/2) at x = 2 z/(pi m), y[i] = 1/r^2 and g[i] = (2/pi) atan x / r^3 for z[i] = |l| - a; every z below 2^-44 (zero
+ * and negative included: the plateau |l| <= a) reads the constant row y = 1/rho^2, g = 0.  _host: the table built and evaluated
+ * on the host with the kernel's arithmetic, no GPU needed (returns 1 when every z was below the table's end 2^14, else 0
  * and NaN entries); the other evaluates on the context's first device. */
-int curvis_debug_inverse_table_host(double rho, double m, const double* x, double* y, double* g, size_t n);
-int curvis_debug_inverse_shape(curvis_ctx* ctx, const curvis_metric* metric, const double* x, double* y, double* g, size_t n);
+int curvis_debug_inverse_table_host(double rho, double m, const double* z, double* y, double* g, size_t n);
+int curvis_debug_inverse_shape(curvis_ctx* ctx, const curvis_metric* metric, const double* z, double* y, double* g, size_t n);
 
 /* Test hook of kernel_variant 4 (the default CURVIS_PRECISION_F64 step: the six reciprocals of metrics.rs:257-262 from two
  * MUFU seeds and one correction step each): evaluates the right-hand side of n_samples pseudo-random photon states both

@@ -180,34 +180,37 @@ def test_interstellar_shape_table_host(lib):
 @pytest.mark.parametrize("rho,m", [(1.0, 0.1), (2.5, 0.03), (0.7, 1.5)])
 def test_interstellar_inverse_table_host(lib, rho, m):
     """The per-metric table the default fast kernel reads (csrc/shape_table.h: build_interstellar_inverse_table):
-    Y(x) = 1 / (rho + m F(x)) and G(x), evaluated on the host with the kernel's arithmetic, against x87 long double:
-    <= 2.5 ulp for 1/r (1/r behaves like 1/x, whose degree-5 interpolation error on 2^-7-wide intervals is ~2^-53), <= 2 ulp
-    for G; everything below 2^-40 — zero and negative x, the plateau |l| <= a of metrics.rs:470 / :482 — reads r = rho, r' = 0."""
+    U(z) = 1 / (rho + m F(x))^2 and H(z) = G(x) / (rho + m F(x))^3 at x = 2 z / (pi m), z = |l| - a — the two combinations the
+    regrouped step needs — evaluated on the host with the kernel's arithmetic, against x87 long double: <= 2 ulp each (256
+    intervals per binade: the degree-5 interpolation error is below 2^-54, what is left is the rounding of the Horner
+    evaluation); everything below 2^-44 — zero and negative z, the plateau |l| <= a of metrics.rs:470 / :482 — reads r = rho,
+    r' = 0."""
     import ctypes as C
     import numpy as np
     rng = np.random.default_rng(20261017)
-    edges = np.ldexp(1.0, np.arange(-40, 17))
-    x = np.concatenate([np.exp(rng.uniform(np.log(2.0 ** -40), np.log(2.0 ** 16), 400_000)),
-                        np.exp(rng.uniform(np.log(0.25), np.log(1024.0), 400_000)),
+    edges = np.ldexp(1.0, np.arange(-44, 15))
+    z = np.concatenate([np.exp(rng.uniform(np.log(2.0 ** -44), np.log(2.0 ** 14), 400_000)),
+                        np.exp(rng.uniform(np.log(0.01), np.log(200.0), 400_000)),
                         edges[:-1], np.nextafter(edges[1:], 0.0), np.nextafter(edges[:-1], np.inf)])
-    y, g = np.empty_like(x), np.empty_like(x)
+    y, g = np.empty_like(z), np.empty_like(z)
     dp = C.POINTER(C.c_double)
-    assert lib.curvis_debug_inverse_table_host(rho, m, x.ctypes.data_as(dp), y.ctypes.data_as(dp), g.ctypes.data_as(dp), x.size) == 1
-    xl = x.astype(np.longdouble)
-    TWO_OVER_PI = np.longdouble(2) / (4 * np.arctan(np.longdouble(1)))
-    want_y = 1 / (np.longdouble(rho) + np.longdouble(m) * (xl * np.arctan(xl) - np.log1p(xl * xl) / 2))
-    want_g = TWO_OVER_PI * np.arctan(xl)
+    assert lib.curvis_debug_inverse_table_host(rho, m, z.ctypes.data_as(dp), y.ctypes.data_as(dp), g.ctypes.data_as(dp), z.size) == 1
+    PI = 4 * np.arctan(np.longdouble(1))
+    xl = z.astype(np.longdouble) * (np.longdouble(2) / (PI * np.longdouble(m)))
+    r = np.longdouble(rho) + np.longdouble(m) * (xl * np.arctan(xl) - np.log1p(xl * xl) / 2)
+    want_y = 1 / (r * r)
+    want_g = (np.longdouble(2) / PI) * np.arctan(xl) / (r * r * r)
 
     def ulps(got, want):
         return np.abs((got.astype(np.longdouble) - want) / np.spacing(np.abs(want.astype(np.float64))).astype(np.longdouble)).astype(np.float64)
 
-    assert ulps(y, want_y).max() <= 2.5, ulps(y, want_y).max()
-    assert ulps(g, want_g).max() <= 2.0
-    low = np.array([0.0, -0.0, -1.0, -1e300, 2.0 ** -41, 5e-324])
+    assert ulps(y, want_y).max() <= 2.0, ulps(y, want_y).max()
+    assert ulps(g, want_g).max() <= 2.0, ulps(g, want_g).max()
+    low = np.array([0.0, -0.0, -1.0, -1e300, 2.0 ** -45, 5e-324])
     yo, go = np.empty_like(low), np.empty_like(low)
     assert lib.curvis_debug_inverse_table_host(rho, m, low.ctypes.data_as(dp), yo.ctypes.data_as(dp), go.ctypes.data_as(dp), low.size) == 1
-    assert (yo == 1.0 / rho).all() and (go == 0.0).all()
-    out = np.array([2.0 ** 16, 1e30])
+    assert (yo == float(1 / (np.longdouble(rho) * np.longdouble(rho)))).all() and (go == 0.0).all()
+    out = np.array([2.0 ** 14, 1e30])
     yo, go = np.empty_like(out), np.empty_like(out)
     assert lib.curvis_debug_inverse_table_host(rho, m, out.ctypes.data_as(dp), yo.ctypes.data_as(dp), go.ctypes.data_as(dp), out.size) == 0
     assert np.isnan(yo).all()

@@ -245,16 +245,16 @@ def test_fast64_rejects_rk4(gpu_ctx):
 
 
 def test_interstellar_inverse_table_on_device(gpu_ctx):
-    """The per-metric table of 1/r and r' that fast_variant 1 reads (csrc/shape_table.h): the device evaluation equals the
-    host evaluation of the same table bit for bit (tests/test_abi_host.py holds the host side to <= 2.5 ulp of long double),
-    and the table is rebuilt when the metric parameters change."""
+    """The per-metric table of 1/r^2 and r'/r^3 (as functions of z = |l| - a) that fast_variant 1 reads (csrc/shape_table.h): the
+    device evaluation equals the host evaluation of the same table bit for bit (tests/test_abi_host.py holds the host side to
+    <= 2 ulp of long double), and the table is rebuilt when the metric parameters change."""
     import ctypes as C
     import curvis_b200 as cv
     from curvis_b200 import _abi
     lib = _abi.load_library()
     rng = np.random.default_rng(11)
-    x = np.concatenate([np.exp(rng.uniform(np.log(2.0 ** -40), np.log(2.0 ** 16), 500_000)), np.array([0.0, -1.0, 2.0 ** -41, 1e-300]),
-                        np.ldexp(1.0, np.arange(-40, 16))])
+    x = np.concatenate([np.exp(rng.uniform(np.log(2.0 ** -44), np.log(2.0 ** 14), 500_000)), np.array([0.0, -1.0, 2.0 ** -45, 1e-300]),
+                        np.ldexp(1.0, np.arange(-44, 14))])
     dp = C.POINTER(C.c_double)
     for rho, m in ((1.0, 0.1), (2.0, 0.37), (1.0, 0.1)):
         metric = cv.InterstellarMetric(m, 1e-4, rho)
