@@ -144,7 +144,7 @@ static cudaError_t launch_render(const FrameParams& p, const curvis_metric* metr
                                                            : launch_render_cart(p, metric->kind, t, sm_count, stream);
     if (sim->precision == CURVIS_PRECISION_F32) return launch_render_f32(p, metric->kind, t, sm_count, stream);
     if (sim->precision == CURVIS_PRECISION_F64_FAST) {
-        if (render_f64_fast_has_prepass(p, t)) g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+        if (render_f64_fast_has_prepass(p, t, sm_count)) g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
         cudaError_t e = launch_render_f64_fast(p, metric->kind, t, sm_count, stream);
         if (e != cudaSuccess || !p.redo_list) return e;
         // second launch: the parity kernel over the rays the fast kernel left in its guard band (list mode; the list's
@@ -841,7 +841,7 @@ extern "C" int curvis_ctx_set_option(curvis_ctx* ctx, const char* key, int64_t v
     else if (k == "fast_regs" && (value == 0 || value == 96 || value == 128)) ctx->tuning.fast_regs = (int)value;
     else if (k == "redo_blocks_per_sm" && value >= 0 && value <= 32) ctx->tuning.redo_blocks_per_sm = (int)value;
     else if (k == "redo_capacity_limit" && value >= 0) ctx->tuning.redo_capacity_limit = value;
-    else if (k == "longest_first" && (value == 0 || value == 1)) ctx->tuning.longest_first = (int)value;
+    else if (k == "longest_first" && value >= 0 && value <= 2) ctx->tuning.longest_first = (int)value;
     else if (k == "guard_rel_e15" && value >= 1 && value <= 1000000000000ll) ctx->tuning.guard_rel = (double)value * 1e-15;
     else return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "unknown option or value out of range: " + k);
     return CURVIS_OK;

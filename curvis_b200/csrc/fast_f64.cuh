@@ -118,7 +118,7 @@ __device__ __forceinline__ void rotate_sincos(const RotRegs& rr, double d, doubl
 // x/256 wide, so beyond x ~ 80 it stays several steps in one interval — and the lanes of a warp, claimed from neighbouring
 // pixels, change intervals on nearly the same steps, so whole quarter-warps skip the fetch.
 struct InverseShapeCache {
-    double2 a01, a23, a45, b01, b23, b45;
+    double a0, a1, a2, a3, a4, a5, b0, b1, b2, b3, b4, b5;
     const double2* tab;
     unsigned idx;
     // The table's address is pinned in a register pair: it is read from the table's own last row (where the host wrote it,
@@ -140,13 +140,15 @@ __device__ __forceinline__ void interstellar_inverse_lookup(double a, double l, 
     const double c = __hiloint2double((int)((hi & ~((1u << kInvTabShift) - 1u)) | (1u << (kInvTabShift - 1))), 0);
     const double t = x - c;
     if (idx != k.idx) {
+        // three 256-bit loads (sm_100: LDG.E.256; a row is 96 bytes, the table 256-byte aligned)
         const double2* e = k.tab + idx * (unsigned)(kShapeTabDoubles / 2);   // (32-bit offset: the table is < 2 MB)
-        k.a01 = __ldg(e); k.a23 = __ldg(e + 1); k.a45 = __ldg(e + 2);
-        k.b01 = __ldg(e + 3); k.b23 = __ldg(e + 4); k.b45 = __ldg(e + 5);
+        asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(k.a0), "=d"(k.a1), "=d"(k.a2), "=d"(k.a3) : "l"(e));
+        asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(k.a4), "=d"(k.a5), "=d"(k.b0), "=d"(k.b1) : "l"(e + 2));
+        asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(k.b2), "=d"(k.b3), "=d"(k.b4), "=d"(k.b5) : "l"(e + 4));
         k.idx = idx;
     }
-    U = fma(t, fma(t, fma(t, fma(t, fma(t, k.a45.y, k.a45.x), k.a23.y), k.a23.x), k.a01.y), k.a01.x);
-    H = fma(t, fma(t, fma(t, fma(t, fma(t, k.b45.y, k.b45.x), k.b23.y), k.b23.x), k.b01.y), k.b01.x);
+    U = fma(t, fma(t, fma(t, fma(t, fma(t, k.a5, k.a4), k.a3), k.a2), k.a1), k.a0);
+    H = fma(t, fma(t, fma(t, fma(t, fma(t, k.b5, k.b4), k.b3), k.b2), k.b1), k.b0);
 }
 
 // The same lookup without a cache (one-off evaluations: test hook).

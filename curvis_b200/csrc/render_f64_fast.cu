@@ -64,7 +64,7 @@ struct FastEllis {   // metrics.rs:417-421 : r^2 = rho^2 + l^2, r' = l/r  =>  r'
         pre.r2 = fma(l, l, p.d_rho2);
         return pre.r2 * s2;
     }
-    static __device__ __forceinline__ void finish(const Pre& pre, double y0, double l, double s2, double& w, double& u, double& v, double& f) {
+    static __device__ __forceinline__ void finish(const FrameParams&, const Pre& pre, Cache&, double y0, double l, double s2, double& w, double& u, double& v, double& f) {
         w = y0;
         u = w * s2;
         v = w * pre.r2;
@@ -145,19 +145,17 @@ struct FastInterstellar {   // metrics.rs:461-485 with the uniform divisor pi*m 
     // coefficients cached in registers while the photon stays in one interval (fast_f64.cuh); the step's one reciprocal is then
     // 1/sin^2 theta alone.  No call: every x below the table (the plateau, x <= 0 included) reads the constant row through an
     // unsigned min; x beyond it never gets here (beyond(): the kernel's radius gate).  41 fp64-pipe instructions per step.
-    struct Pre { double u, f; };
+    // The lookup sits in finish(), i.e. at the head of the step it serves: nothing but the photon is carried from one trip of the
+    // loop to the next (looked up a step ahead, in prepare(), U and H changed registers by four moves per step).
+    struct Pre {};
     using Cache = InverseShapeCache;
-    static __device__ __forceinline__ double prepare(const FrameParams& p, double l, double s2, Pre& pre, Cache& cache) {
+    static __device__ __forceinline__ double prepare(const FrameParams&, double, double s2, Pre&, Cache&) { return s2; }
+    static __device__ __forceinline__ void finish(const FrameParams& p, const Pre&, Cache& cache, double y0, double l, double, double& w, double& u, double& v, double& f) {
         double H;
-        interstellar_inverse_lookup(p.a, l, cache, pre.u, H);
-        pre.f = copysign(H, l);        // r'/r^3
-        return s2;
-    }
-    static __device__ __forceinline__ void finish(const Pre& pre, double y0, double, double, double& w, double& u, double& v, double& f) {
+        interstellar_inverse_lookup(p.a, l, cache, u, H);   // u = 1/r^2
         v = y0;                        // 1/sin^2
-        u = pre.u;                     // 1/r^2
         w = u * v;
-        f = pre.f;
+        f = copysign(H, l);            // r'/r^3
     }
     static __device__ __forceinline__ bool beyond(const FrameParams& p, double l) { return !(fabs(l) < p.fast_l_limit); }
 };
@@ -173,7 +171,7 @@ struct FastFlat {   // metrics.rs:501-505: r = l, r' = 1 (r may be negative: tak
         pre.r = l; pre.rp = 1.0;
         return l * s2;
     }
-    static __device__ __forceinline__ void finish(const Pre& pre, double y0, double, double s2, double& w, double& u, double& v, double& f) {
+    static __device__ __forceinline__ void finish(const FrameParams&, const Pre& pre, Cache&, double y0, double, double s2, double& w, double& u, double& v, double& f) {
         finish_from_r(pre, y0, s2, w, u, v, f);
     }
     static __device__ __forceinline__ bool beyond(const FrameParams&, double) { return false; }
@@ -235,7 +233,7 @@ __device__ __forceinline__ uint32_t fast_window_scaled(const FrameParams& p, con
         double dth;
         for (;;) {
             double w, u, v, f;
-            Fast::finish(pre, rcp_1ulp(d), q.l, s2, w, u, v, f);
+            Fast::finish(p, pre, cache, rcp_1ulp(d), q.l, s2, w, u, v, f);
             const double cs = sn * cn;
             dth = q.pth * u;                                    // metrics.rs:239
             const double pv = q.pph2 * v;                       // p_phi^2 / sin^2
@@ -358,8 +356,8 @@ __device__ __noinline__ void fast_epilogue(const FrameParams& p, const Ray& q, u
     finish_ray<Shape64, TrigFast, false>(p, qs, side2, (qs.l != qs.l) ? p.max_iterations : sr.steps, ray, tally, diag, 0.0);
 }
 
-// MinBlocks: resident CTAs per SM the register allocation is held to — 5 (96 registers: the step loop re-materialises two
-// polynomial constants per step, 50 instructions) or 4 (128 registers: everything pinned, 47 instructions).
+// MinBlocks: resident CTAs per SM the register allocation is held to — 5 (96 registers, the default: five warps per scheduler
+// hide more of the step's dependency chains than four) or 4 (128 registers), kept for A/B ("fast_regs").
 template <class Fast, int Variant, int MinBlocks>
 __global__ void __launch_bounds__(kBlockFast, MinBlocks) render_rows_f64_fast(const __grid_constant__ FrameParams p) {
     using Shape64 = typename Fast::Shape64;
@@ -550,10 +548,22 @@ __global__ void __launch_bounds__(256) collect_long_rays(const __grid_constant__
     }
 }
 
-constexpr unsigned long long kLongestFirstMinRays = 1ull << 15;   // smaller launches (the efficient renderer's table) skip the pre-pass
+// When the pre-pass runs ("longest_first" = 2, the default): launches of at least 2^15 rays (the efficient renderer's table skips
+// it) and of at most 64 rays per lane of the grid.  A 20,000-step straggler takes ~4 ms whenever it starts; in a launch of 87 rays
+// per lane (a whole 4K frame on one GPU, 37 ms) it is claimed half-way in index order and ends long before the kernel does, and
+// starting 27,000 slow rays at once only costs (measured +0.25 ms Ellis, +0.3-0.5 ms Interstellar); in a launch of 11 rays per lane
+// (the same frame over 8 GPUs, 5 ms) it must start first (Interstellar central tile: 9.5 -> 8.3 ms).
+constexpr unsigned long long kLongestFirstMinRays = 1ull << 15;
+constexpr unsigned long long kLongestFirstMaxRaysPerLane = 64;
+
+__host__ bool longest_first_wanted(const FrameParams& p, int mode, int sm_count) {
+    const unsigned long long rays = (unsigned long long)(p.row_end - p.row_begin) * p.width * (p.n_frames ? p.n_frames : 1u);
+    if (!p.long_list || mode == 0 || rays < kLongestFirstMinRays) return false;
+    return mode == 1 || rays <= kLongestFirstMaxRaysPerLane * (unsigned long long)sm_count * 5ull * kBlockFast;
+}
 
 template <class Fast, int Variant, int MinBlocks>
-cudaError_t launch_fast_variant(const FrameParams& p, int sm_count, int blocks_per_sm_override, cudaStream_t stream) {
+cudaError_t launch_fast_variant(const FrameParams& p, int sm_count, int blocks_per_sm_override, int longest_first, cudaStream_t stream) {
     static int blocks_per_sm_auto = 0;
     if (blocks_per_sm_auto == 0) {
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm_auto, render_rows_f64_fast<Fast, Variant, MinBlocks>, kBlockFast, 0);
@@ -566,7 +576,7 @@ cudaError_t launch_fast_variant(const FrameParams& p, int sm_count, int blocks_p
     unsigned long long want = (rays + kBlockFast - 1) / kBlockFast;
     unsigned long long cap = (unsigned long long)sm_count * (unsigned long long)blocks_per_sm;
     const unsigned grid = (unsigned)(want < cap ? (want ? want : 1) : cap);
-    if (Variant == 1 && p.long_list && rays >= kLongestFirstMinRays) {
+    if (Variant == 1 && longest_first_wanted(p, longest_first, sm_count)) {
         const unsigned long long blocks = (rays + 255) / 256;
         collect_long_rays<<<(unsigned)(blocks < 8ull * sm_count ? blocks : 8ull * sm_count), 256, 0, stream>>>(p);
         render_rows_f64_fast<Fast, Variant, MinBlocks><<<grid, kBlockFast, 0, stream>>>(p);
@@ -582,10 +592,10 @@ template <class Fast>
 cudaError_t launch_fast(const FrameParams& p, const LaunchTuning& t, int sm_count, cudaStream_t stream) {
     // variant 1 scales the momenta by delta: it needs a finite, non-zero step of ordinary magnitude
     const double ad = p.delta < 0.0 ? -p.delta : p.delta;
-    if (t.fast_variant == 0 || !(ad >= 0x1p-100 && ad <= 0x1p100)) return launch_fast_variant<Fast, 0, 5>(p, sm_count, t.blocks_per_sm, stream);   // trigonometry from theta every step
-    const int regs = t.fast_regs ? t.fast_regs : (Fast::Shape64::kind == CURVIS_METRIC_INTERSTELLAR ? 128 : 96);
-    if (regs == 96) return launch_fast_variant<Fast, 1, 5>(p, sm_count, t.blocks_per_sm, stream);         // default: rotated (sin, cos)
-    return launch_fast_variant<Fast, 1, 4>(p, sm_count, t.blocks_per_sm, stream);
+    if (t.fast_variant == 0 || !(ad >= 0x1p-100 && ad <= 0x1p100)) return launch_fast_variant<Fast, 0, 5>(p, sm_count, t.blocks_per_sm, 0, stream);   // trigonometry from theta every step
+    const int regs = t.fast_regs ? t.fast_regs : 96;
+    if (regs == 96) return launch_fast_variant<Fast, 1, 5>(p, sm_count, t.blocks_per_sm, t.longest_first, stream);         // default: rotated (sin, cos)
+    return launch_fast_variant<Fast, 1, 4>(p, sm_count, t.blocks_per_sm, t.longest_first, stream);
 }
 
 }  // namespace
@@ -624,10 +634,9 @@ cudaError_t launch_debug_shape(const double2* tab, int which, const double* x, d
 }
 
 // Whether launch_render_f64_fast launches the longest-first pre-pass in front of the render kernel (the launch counter's business).
-bool render_f64_fast_has_prepass(const FrameParams& p, const LaunchTuning& t) {
+bool render_f64_fast_has_prepass(const FrameParams& p, const LaunchTuning& t, int sm_count) {
     const double ad = p.delta < 0.0 ? -p.delta : p.delta;
-    const unsigned long long rays = (unsigned long long)(p.row_end - p.row_begin) * p.width * (p.n_frames ? p.n_frames : 1u);
-    return t.fast_variant == 1 && (ad >= 0x1p-100 && ad <= 0x1p100) && p.long_list && rays >= kLongestFirstMinRays;
+    return t.fast_variant == 1 && (ad >= 0x1p-100 && ad <= 0x1p100) && longest_first_wanted(p, t.longest_first, sm_count);
 }
 
 cudaError_t launch_render_f64_fast(const FrameParams& p, int metric_kind, const LaunchTuning& t, int sm_count, cudaStream_t stream) {

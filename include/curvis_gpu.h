@@ -377,13 +377,14 @@ int curvis_measure_fma_peak(curvis_ctx* ctx, double* fp64_tflops, double* fp32_t
  *   "guard":          CURVIS_PRECISION_F64_FAST: 1 (default) guard band + re-integration of the rays with stiffness < 1;
  *                     2 kicked rays (stiffness >= 1) re-integrated too; 0 the raw regrouped kernel (A/B)
  *   "guard_rel_e15":  the guard's relative budget in units of 1e-15 (default 1000000 = 1e-9)
- *   "fast_regs":      96 / 128: register budget of the fast kernel (5 / 4 resident CTAs per SM); 0 (default) = 96 for
- *                     Ellis and Flat, 128 for Interstellar (the measured optimum of each)
+ *   "fast_regs":      96 / 128: register budget of the fast kernel (5 / 4 resident CTAs per SM); 0 (default) = 96
  *   "redo_blocks_per_sm": resident CTAs per SM of the re-integration launch (default 2)
  *   "redo_capacity_limit": test knob — caps the re-integration list (0 = automatic: one slot per ray up to 2^24 rays); a ray
  *                     that finds the list full is re-integrated in line by the fast kernel (same result, slower)
- *   "longest_first":  CURVIS_PRECISION_F64_FAST: 1 (default) a pre-pass kernel lists the rays predicted to graze a coordinate
- *                     pole (the 10^4-step stragglers) and the work queue hands them out first; 0 rays are claimed in index order
+ *   "longest_first":  CURVIS_PRECISION_F64_FAST: a pre-pass kernel lists the rays predicted to be the 10^4-step stragglers (near-
+ *                     critical photons grazing a coordinate pole) and the work queue hands them out first: 1 always, 0 never
+ *                     (index order), 2 (default) in launches of at most 64 rays per lane of the grid — one frame split over
+ *                     several GPUs — where one straggler's latency is comparable to the kernel's
  *   "blocks_per_sm":  resident CTAs per SM of the persistent grid (0 = occupancy maximum)
  *   "window":         Euler steps between two refill points of a warp (0 = default: 32; for
  *                     CURVIS_PRECISION_F64_FAST 32..128, growing with the expected ray length)

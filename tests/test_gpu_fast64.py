@@ -106,6 +106,41 @@ def test_fast_variants_render_the_same_frames(gpu_ctx):
         gpu_ctx.set_option("fast_variant", 1)
 
 
+def test_scheduling_options_do_not_change_a_ray(gpu_ctx):
+    """ctx options "longest_first" (pre-pass list of the predicted stragglers, claimed first) and "fast_regs" (96 / 128 registers:
+    5 / 4 resident CTAs per SM) only change the ORDER in which rays are integrated: every record — state, steps, side, texel —
+    and every counter is byte-identical, and the pre-pass shows up as one more kernel launch.  Frames: the default camera
+    (stragglers next to the central row) and a tilted one (the pole-grazing wedge is oblique), batched frames included."""
+    import curvis_b200 as cv
+    from curvis_b200 import _abi, scenes
+    lib = _abi.load_library()
+    bp, bn = scenes.noise_background(1024, 512, 5), scenes.noise_background(1024, 512, 6)
+    W, H, sim = 480, 270, (40000, 100.0, 0.05)
+    cams = [cv.Camera(scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP, 15.0, 43.0, W, H),
+            cv.Camera((0.0, -4.0, 1.1, 2.0), (0.9, 0.3, -0.2), (0.1, 0.2, 1.0), 12.0, 43.0, W, H)]
+    try:
+        for metric in (cv.EllisMetric(1.0), cv.InterstellarMetric(0.1, 1e-4, 1.0)):
+            for cam in cams:
+                sysm = cv.RelativisticSystem(metric, cv.SphericalImage(bp), cv.SphericalImage(bn), cam, context=gpu_ctx)
+                out = {}
+                for lf, regs in ((0, 0), (1, 0), (2, 0), (1, 128)):
+                    gpu_ctx.set_option("longest_first", lf)
+                    gpu_ctx.set_option("fast_regs", regs)
+                    n0 = lib.curvis_kernel_launch_count()
+                    frame, rec = sysm.render_rows(*sim, 0, H, with_records=True, precision=_abi.PRECISION_F64_FAST)
+                    out[(lf, regs)] = (frame, rec, dict(sysm.last_stats), lib.curvis_kernel_launch_count() - n0)
+                f0, r0, s0, n_launch0 = out[(0, 0)]
+                assert n_launch0 == 2                                  # render + re-integration
+                assert out[(1, 0)][3] == 3 and out[(2, 0)][3] == 3      # + the pre-pass (129,600 rays: under 64 per lane)
+                for key, (f, r, st, _) in out.items():
+                    assert f.tobytes() == f0.tobytes() and r.tobytes() == r0.tobytes(), (type(metric).__name__, key)
+                    for k in ("total_steps", "n_positive", "n_negative", "n_not_escaped", "n_clamped", "n_reintegrated", "n_kicked"):
+                        assert st[k] == s0[k], (key, k)
+    finally:
+        gpu_ctx.set_option("longest_first", 2)
+        gpu_ctx.set_option("fast_regs", 0)
+
+
 def _compare_with_oracle(frame, rec, ref_frame, ref_rec, name):
     n = ref_rec.size
     bad = ((frame != ref_frame).any(axis=2) | (rec["side"] != ref_rec["side"]) | (rec["steps"] != ref_rec["steps"]) |

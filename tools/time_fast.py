@@ -33,7 +33,7 @@ for mname, metric, sim in (("ellis_defaults", cv.EllisMetric(1.0), (40000, 100.0
     # an eighth of the frame around the central rows (what one of 8 ranks would render with contiguous tiles): the stragglers' tile
     for lf in (0, 1):
         res[f"rows945_1215_guard1_lf{lf}"] = run(rows=(945, 1215), longest_first=lf)
-    ctx.set_option("longest_first", 1)
+    ctx.set_option("longest_first", 2)
     out[mname] = res
     print(mname, json.dumps(res), flush=True)
 if len(sys.argv) > 1:

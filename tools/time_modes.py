@@ -34,7 +34,7 @@ for mname, metric, sim in (("ellis_defaults", cv.EllisMetric(1.0), (40000, 100.0
         res[f"fast_guard1_redo{redo}"] = run(_abi.PRECISION_F64_FAST, redo_blocks_per_sm=redo)
     ctx.set_option("redo_blocks_per_sm", 2)
     res["fast_guard1_longest_first0"] = run(_abi.PRECISION_F64_FAST, longest_first=0)
-    ctx.set_option("longest_first", 1)
+    ctx.set_option("longest_first", 2)
     for variant in (3, 4):
         res[f"f64_variant{variant}"] = run(_abi.PRECISION_F64, reps=3, kernel_variant=variant)
     ctx.set_option("kernel_variant", 4)
