@@ -114,9 +114,9 @@ __device__ __forceinline__ void rotate_sincos(const RotRegs& rr, double d, doubl
 // The coefficients are CACHED in the lane's registers and fetched again only when the step has left the interval.  Fetching
 // them every step made the L1 data pipe the bound of the Interstellar kernel, not the fp64 pipe: 96 bytes per lane and step
 // are 24 wavefronts of register write-back per warp-step whatever the addresses (profiles/r02_ncu_f64_fast_interstellar_
-// summary.txt: l1tex data-pipe 87 % of peak, fp64 pipe 65 %).  A photon advances x by ~0.3 per step and the intervals are
-// x/256 wide, so beyond x ~ 80 it stays several steps in one interval — and the lanes of a warp, claimed from neighbouring
-// pixels, change intervals on nearly the same steps, so whole quarter-warps skip the fetch.
+// v1_summary.txt: l1tex data-pipe 87 % of peak, fp64 pipe 65 %).  A photon advances |l| by ~0.05 per step and the intervals are
+// z/128 wide, so beyond z ~ 6 it stays several steps in one interval (a third of all lane-steps fetch) — and the lanes of a
+// warp, claimed from neighbouring pixels, change intervals on nearly the same steps, so whole quarter-warps skip the fetch.
 struct InverseShapeCache {
     double a0, a1, a2, a3, a4, a5, b0, b1, b2, b3, b4, b5;
     const double2* tab;

@@ -35,20 +35,25 @@ void build_interstellar_shape_table(double* out);
 // holds exactly those two, as functions of z = |l| - a (the distance from the throat's plateau, ONE fp64 subtraction in the
 // step; x = 2 z / (pi m) is folded into the coefficients):
 //     U(z) = 1 / (rho + m F(x))^2      and      H(z) = G(x) / (rho + m F(x))^3,
-// degree 5 each, on 2^kInvTabK = 256 intervals per binade of z in [2^kInvTabEmin, 2^kInvTabEmax).  The step then takes its one
+// degree 5 each, on 2^kInvTabK = 128 intervals per binade of z in [2^kInvTabEmin, 2^kInvTabEmax).  The step then takes its one
 // reciprocal of sin^2 theta alone (w = U / sin^2, r'/r^3 = sign(l) H): seven fp64 instructions fewer than going through r, and
 // the metric parameters leave the loop.  One extra CONSTANT row (U = 1/rho^2, H = 0: the plateau |l| <= a of the throat,
 // metrics.rs:470 / :482) receives every z below the range — zero, negative, denormal — through an unsigned min of the index, so the
 // step has no branch and no call for the plateau (at z = 2^-44 the neglected m F is < 1e-20 m for every m >= 1e-3); z >=
-// 2^kInvTabEmax is kept out of the loop by the step's radius gate (interstellar_table_l_limit).  Interval width: U behaves like
-// z^-2 and H like z^-3 for large z, whose seventh Taylor coefficients are 7 and 28 (1/z: 1), so the degree-5 interpolation
-// error on 2^-7-wide intervals would be 7 and 28 units of 2^-53; on 2^-8-wide intervals it is 2^-56 and 2^-54 and the result
-// is the rounding of the Horner evaluation.  Checked against long double in tests/test_abi_host.py (host) and
-// tests/test_gpu_fast64.py (device, bit-identical to the host evaluation).
-// (Round-2 history: the first per-metric table held Y = 1/r and G = |r'| as functions of x on 128 intervals per binade;
-// u = Y^2 and r'/r^3 = G Y^3 cost three more multiplications per step, and x = fma(|l|, xscale, xoff) needed its addend
-// re-loaded into a vector register every step.)
-constexpr int kInvTabK = 8;                   // 2^8 intervals per binade
+// 2^kInvTabEmax is kept out of the loop by the step's radius gate (interstellar_table_l_limit).
+// Accuracy and interval width: U behaves like z^-2 and H like z^-3 for large z, whose seventh Taylor coefficients are 7 and 28
+// (1/z: 1), so on 2^-7-wide intervals the degree-5 interpolation error reaches 8 resp. 28 units of 2^-53 (relative; 14 / 48 in
+// the transition zone x ~ 1 of a large-m metric) at the START of a binade, falls 64-fold towards its end, and is 0.8 resp. 2.9
+// units r.m.s. — the size of the Horner evaluation's own rounding.  2^-8-wide intervals keep both below 2 units everywhere,
+// but the hot part of the table (z in [2^-6, 2^7): 320 KB) then no longer fits the L1: hit rate 99.8 % -> 91 %, 4K frame
+// 53.1 -> 55.9 ms.  What the guard band has to cover does not depend on the choice (tools/guard_study_interstellar.py, four
+// scenes, rays with stiffness < 1: direction 9.6e-13 against 9.6e-13, l 6.0e-9 against 6.1e-9): the deviation from the
+// operation-for-operation kernel comes from the regrouped roundings of 2000 steps, not from the table.  Checked against long
+// double in tests/test_abi_host.py (host) and tests/test_gpu_fast64.py (device, bit-identical to the host evaluation).
+// (Round-2 history: the first per-metric table held Y = 1/r and G = |r'| as functions of x; u = Y^2 and r'/r^3 = G Y^3 cost
+// three more multiplications per step, and x = fma(|l|, xscale, xoff) needed its addend re-loaded into a vector register
+// every step.)
+constexpr int kInvTabK = 7;                   // 2^7 intervals per binade
 constexpr int kInvTabEmin = -44;
 constexpr int kInvTabEmax = 14;               // z < 16384
 constexpr unsigned kInvTabShift = 20 - kInvTabK;

@@ -181,10 +181,13 @@ def test_interstellar_shape_table_host(lib):
 def test_interstellar_inverse_table_host(lib, rho, m):
     """The per-metric table the default fast kernel reads (csrc/shape_table.h: build_interstellar_inverse_table):
     U(z) = 1 / (rho + m F(x))^2 and H(z) = G(x) / (rho + m F(x))^3 at x = 2 z / (pi m), z = |l| - a — the two combinations the
-    regrouped step needs — evaluated on the host with the kernel's arithmetic, against x87 long double: <= 2 ulp each (256
-    intervals per binade: the degree-5 interpolation error is below 2^-54, what is left is the rounding of the Horner
-    evaluation); everything below 2^-44 — zero and negative z, the plateau |l| <= a of metrics.rs:470 / :482 — reads r = rho,
-    r' = 0."""
+    regrouped step needs — evaluated on the host with the kernel's arithmetic, against x87 long double.  Degree 5 on 128
+    intervals per binade: U ~ z^-2 and H ~ z^-3 have seventh Taylor coefficients 7 and 28, so the interpolation error reaches 8
+    resp. 28-48 units of 2^-53 (relative) at the START of a binade and falls 64-fold towards its end — r.m.s. 0.8 resp. 2.9
+    units, the size of the rounding of the Horner evaluation.  (256 intervals per binade hold both below 2 units everywhere,
+    but the table then falls out of the L1 and the 4K frame costs 5 % more; the fast kernel's deviation from the
+    operation-for-operation kernel is the same with either: tools/guard_study_interstellar.py.)  Everything below 2^-44 — zero
+    and negative z, the plateau |l| <= a of metrics.rs:470 / :482 — reads r = rho, r' = 0."""
     import ctypes as C
     import numpy as np
     rng = np.random.default_rng(20261017)
@@ -201,11 +204,12 @@ def test_interstellar_inverse_table_host(lib, rho, m):
     want_y = 1 / (r * r)
     want_g = (np.longdouble(2) / PI) * np.arctan(xl) / (r * r * r)
 
-    def ulps(got, want):
-        return np.abs((got.astype(np.longdouble) - want) / np.spacing(np.abs(want.astype(np.float64))).astype(np.longdouble)).astype(np.float64)
+    def units(got, want):      # relative error in units of 2^-53
+        return (np.abs((got.astype(np.longdouble) - want) / want) * np.longdouble(2.0 ** 53)).astype(np.float64)
 
-    assert ulps(y, want_y).max() <= 2.0, ulps(y, want_y).max()
-    assert ulps(g, want_g).max() <= 2.0, ulps(g, want_g).max()
+    eu, eh = units(y, want_y), units(g, want_g)
+    assert eu.max() <= 16.0 and np.sqrt((eu ** 2).mean()) <= 2.0, (eu.max(), np.sqrt((eu ** 2).mean()))
+    assert eh.max() <= 56.0 and np.sqrt((eh ** 2).mean()) <= 5.5, (eh.max(), np.sqrt((eh ** 2).mean()))
     low = np.array([0.0, -0.0, -1.0, -1e300, 2.0 ** -45, 5e-324])
     yo, go = np.empty_like(low), np.empty_like(low)
     assert lib.curvis_debug_inverse_table_host(rho, m, low.ctypes.data_as(dp), yo.ctypes.data_as(dp), go.ctypes.data_as(dp), low.size) == 1
