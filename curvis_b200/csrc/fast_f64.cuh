@@ -93,8 +93,10 @@ struct RotRegs {
 };
 
 // (s, c) = (sin, cos)(theta)  ->  (sin, cos)(theta + d), |d| < 2^-4.
-__device__ __forceinline__ void rotate_sincos(const RotRegs& rr, double d, double& s, double& c) {
+// v_out = d*d (the caller's |d| < 2^-4 test reads its high word: v >= 0 needs no sign mask)
+__device__ __forceinline__ void rotate_sincos(const RotRegs& rr, double d, double& s, double& c, double& v_out) {
     const double v = d * d;
+    v_out = v;
     double sp = fma(v, rr.sin2, kRotSin[1]);
     double tp = fma(v, rr.tan2, kRotTan[1]);
     sp = fma(v, sp, kRotSin[0]);
@@ -104,6 +106,10 @@ __device__ __forceinline__ void rotate_sincos(const RotRegs& rr, double d, doubl
     c = fma(-t, s, c);
     s = fma(sd, c, s);
     c = fma(-t, s, c);
+}
+__device__ __forceinline__ void rotate_sincos(const RotRegs& rr, double d, double& s, double& c) {
+    double v;
+    rotate_sincos(rr, d, s, c, v);
 }
 
 // ---- Interstellar shape function from the per-metric table (shape_table.h: build_interstellar_inverse_table):
