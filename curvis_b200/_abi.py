@@ -123,6 +123,7 @@ EXPORTED_SYMBOLS = (
     "curvis_debug_shape_table_host", "curvis_host_register", "curvis_host_unregister",
     "curvis_peer_buffer_create", "curvis_peer_buffer_open", "curvis_peer_buffer_close", "curvis_peer_buffer_destroy",
     "curvis_render_frames_peers", "curvis_debug_rhs_check", "curvis_debug_inverse_table_host", "curvis_debug_inverse_shape",
+    "curvis_debug_fn_table_host",
 )
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcurvis_b200.so")
@@ -186,6 +187,7 @@ def load_library() -> C.CDLL:
     lib.curvis_host_unregister.argtypes = [vp, vp]
     lib.curvis_debug_shape_table_host.argtypes = [dp, dp, dp, C.c_size_t]
     lib.curvis_debug_inverse_table_host.argtypes = [C.c_double, C.c_double, dp, dp, dp, C.c_size_t]
+    lib.curvis_debug_fn_table_host.argtypes = [C.c_int, dp, dp, C.c_size_t]
     lib.curvis_debug_inverse_shape.argtypes = [vp, C.POINTER(CurvisMetric), dp, dp, dp, C.c_size_t]
     lib.curvis_debug_rhs_check.argtypes = [vp, C.POINTER(CurvisMetric), C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
     for name in EXPORTED_SYMBOLS:

@@ -45,6 +45,8 @@ struct DeviceState {
     CameraBlock* d_cameras = nullptr; size_t d_cameras_cap = 0;   // batched launches
     double2* d_shape_tab = nullptr;   // Interstellar shape-function table (shape_table.h), uploaded at context creation
     float4* d_shape_tab32 = nullptr;  // its fp32 edition
+    double* d_atan_tab = nullptr;     // atan / ln tables of the operation-for-operation Interstellar step (shape_table.h)
+    double* d_log_tab = nullptr;
     double2* d_inv_tab = nullptr;     // per-metric table of 1/r and r' (shape_table.h), rebuilt when (rho, m) change
     double inv_tab_rho = 0.0, inv_tab_m = 0.0;
     cudaEvent_t chunk_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // pipelined read-back
@@ -267,6 +269,9 @@ static void fill_params(const curvis_ctx* ctx, const DeviceState& d, const curvi
     p.d_xscale = 2.0 / (3.14159265358979323846 * metric->m);
     p.shape_tab = d.d_shape_tab;
     p.shape_tab32 = d.d_shape_tab32;
+    p.atan_tab = d.d_atan_tab; p.log_tab = d.d_log_tab;
+    p.d_pim = 3.14159265358979323846 * metric->m;          // PI * self.m (metrics.rs:461), one rounding
+    p.d_pim_rcp = 1.0 / p.d_pim;                           // correctly rounded (IEEE division on the host)
     p.inv_tab = d.d_inv_tab;
     p.d_xoff = -metric->a * p.d_xscale;
     p.fast_l_limit = metric->kind == CURVIS_METRIC_INTERSTELLAR ? interstellar_table_l_limit(metric->m, metric->a) : HUGE_VAL;
@@ -400,6 +405,8 @@ static void release_device(DeviceState& d) {
     if (d.d_records) cudaFree(d.d_records);
     if (d.d_cameras) cudaFree(d.d_cameras);
     if (d.d_shape_tab) cudaFree(d.d_shape_tab);
+    if (d.d_atan_tab) cudaFree(d.d_atan_tab);
+    if (d.d_log_tab) cudaFree(d.d_log_tab);
     if (d.d_shape_tab32) cudaFree(d.d_shape_tab32);
     if (d.d_inv_tab) cudaFree(d.d_inv_tab);
     if (d.d_redo) cudaFree(d.d_redo);
@@ -447,6 +454,9 @@ extern "C" int curvis_ctx_create(const int* devices, int n_devices, curvis_ctx**
     build_interstellar_shape_table(shape_tab.data());
     std::vector<float> shape_tab32(kShapeTab32Intervals * kShapeTab32Floats);
     build_interstellar_shape_table_f32(shape_tab32.data());
+    std::vector<double> atan_tab(kAtanTabIntervals * kFnTabDoubles), log_tab(kLogTabIntervals * kFnTabDoubles);
+    build_atan_table(atan_tab.data());
+    build_log_table(log_tab.data());
     for (size_t i = 0; i < ords.size(); ++i) {
         DeviceState& d = ctx->devs[i];
         const int ord = ords[i];
@@ -467,6 +477,11 @@ extern "C" int curvis_ctx_create(const int* devices, int n_devices, curvis_ctx**
             else if ((e = cudaMalloc(&d.d_shape_tab, shape_tab.size() * sizeof(double))) != cudaSuccess) rc = cuda_fail(nullptr, e, "cudaMalloc(shape table)");
             else if ((e = cudaMemcpy(d.d_shape_tab, shape_tab.data(), shape_tab.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess)
                 rc = cuda_fail(nullptr, e, "cudaMemcpy(shape table)");
+            else if ((e = cudaMalloc(&d.d_atan_tab, atan_tab.size() * sizeof(double))) != cudaSuccess ||
+                     (e = cudaMalloc(&d.d_log_tab, log_tab.size() * sizeof(double))) != cudaSuccess) rc = cuda_fail(nullptr, e, "cudaMalloc(atan / ln tables)");
+            else if ((e = cudaMemcpy(d.d_atan_tab, atan_tab.data(), atan_tab.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
+                     (e = cudaMemcpy(d.d_log_tab, log_tab.data(), log_tab.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess)
+                rc = cuda_fail(nullptr, e, "cudaMemcpy(atan / ln tables)");
             else if ((e = cudaMalloc(&d.d_shape_tab32, shape_tab32.size() * sizeof(float))) != cudaSuccess) rc = cuda_fail(nullptr, e, "cudaMalloc(shape table f32)");
             else if ((e = cudaMemcpy(d.d_shape_tab32, shape_tab32.data(), shape_tab32.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess)
                 rc = cuda_fail(nullptr, e, "cudaMemcpy(shape table f32)");
@@ -861,6 +876,7 @@ extern "C" int curvis_debug_eval(curvis_ctx* ctx, int op, const double* a, const
         (!b || (e = cudaMemcpyAsync(db, b, bytes, cudaMemcpyHostToDevice, d.stream)) == cudaSuccess) &&
         (e = (op == 13 || op == 14)   ? launch_debug_shape(d.d_shape_tab, op - 13, da, dout, n, d.stream)
              : (op == 15 || op == 16) ? launch_debug_shape32(d.d_shape_tab32, op - 15, da, dout, n, d.stream)
+             : (op == 17 || op == 18) ? launch_debug_atan_log(d.d_atan_tab, d.d_log_tab, op - 17, da, dout, n, d.stream)
                                       : launch_debug_eval(op, da, db, dout, n, d.stream)) == cudaSuccess &&
         (e = cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, d.stream)) == cudaSuccess)
         e = cudaStreamSynchronize(d.stream);

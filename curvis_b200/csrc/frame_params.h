@@ -79,6 +79,11 @@ struct FrameParams {
     // Interstellar shape-function table of CURVIS_PRECISION_F64_FAST (shape_table.h), resident per device
     const double2* shape_tab;
     const float4* shape_tab32;   // the fp32 edition for CURVIS_PRECISION_F32
+    // atan and ln tables of the operation-for-operation Interstellar step (shape_table.h), and pi m with its correctly rounded
+    // reciprocal (host): x = 2 (|l| - a) / (pi m) is then one correctly rounded quotient in three fp64 instructions
+    const double* atan_tab;
+    const double* log_tab;
+    double d_pim, d_pim_rcp;
     // per-metric table of 1/r^2 and r'/r^3 as functions of z = |l| - a (shape_table.h: build_interstellar_inverse_table), and
     // the |l| beyond which z leaves the table (+inf for the other metrics)
     const double2* inv_tab;

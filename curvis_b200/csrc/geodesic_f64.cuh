@@ -11,6 +11,7 @@
 #include "frame_params.h"
 #include "ieee_f64.cuh"
 #include "trig_f64.cuh"
+#include "shape_table.h"
 
 namespace curvis {
 
@@ -77,13 +78,54 @@ struct ShapeInterstellar {  // metrics.rs:461-485
         }
         r2 = r * r;      // :474
     }
-    // atan/log dominate this metric; the generic evaluation is kept (its one division has a
-    // uniform divisor) and only the step's six divisions take the unguarded path.
+    // The lean kernels' evaluation (kernel_variant >= 1; operands inside the safe window, params_safe() below): the same
+    // operations in the same order, with
+    //   * x = 2 (|l| - a) / (pi m) as ONE correctly rounded quotient in three instructions: the divisor is a launch constant, the
+    //     host supplies its correctly rounded reciprocal y, and q0 = a y; rem = fma(-b, q0, a); q = fma(rem, y, q0) is RN(a / b)
+    //     (the value before the last rounding is within 2^-106 of the quotient, closer than a quotient of two doubles comes to
+    //     a rounding boundary);
+    //   * atan x and ln(1 + x^2) from tables (shape_table.h: <= 1 ulp of the exact values, like the CUDA library's — whose two
+    //     calls were two thirds of this metric's step).  1 + x^2 is formed as the reference forms it (two roundings) and THEN
+    //     looked up.  Outside the tables (x < 2^-10: the first 1.6e-4 m beyond the plateau; x >= 2^16) the library is called.
+    static __device__ __forceinline__ void atan_log(const FrameParams& p, double x, double& at, double& lg) {
+        const unsigned hx = (unsigned)__double2hiint(x);
+        const unsigned ix = (hx >> kShapeTabShift) - kShapeTabBase;
+        const double y = 1.0 + x * x;
+        if (ix < (unsigned)kAtanTabIntervals) {
+            const double cx = __hiloint2double((int)((hx & ~((1u << kShapeTabShift) - 1u)) | (1u << (kShapeTabShift - 1))), 0);
+            const double tx = x - cx;
+            const double2* a = reinterpret_cast<const double2*>(p.atan_tab) + ix * 3u;
+            const double2 a01 = __ldg(a), a23 = __ldg(a + 1), a45 = __ldg(a + 2);
+            at = fma(tx, fma(tx, fma(tx, fma(tx, fma(tx, a45.y, a45.x), a23.y), a23.x), a01.y), a01.x);
+            const unsigned hy = (unsigned)__double2hiint(y);              // 1 <= y < 2^33
+            const unsigned iy = (hy >> kShapeTabShift) - kLogTabBase;
+            const double cy = __hiloint2double((int)((hy & ~((1u << kShapeTabShift) - 1u)) | (1u << (kShapeTabShift - 1))), 0);
+            const double ty = y - cy;
+            const double2* b = reinterpret_cast<const double2*>(p.log_tab) + iy * 3u;
+            const double2 b01 = __ldg(b), b23 = __ldg(b + 1), b45 = __ldg(b + 2);
+            lg = fma(ty, fma(ty, fma(ty, fma(ty, fma(ty, b45.y, b45.x), b23.y), b23.x), b01.y), b01.x);
+        } else {
+            at = atan(x);
+            lg = log(y);
+        }
+    }
     static __device__ __forceinline__ void eval_fast(const FrameParams& p, double l, double& r, double& r2, double& rp) {
-        eval(p, l, r, r2, rp);
+        const double al = fabs(l);
+        if (al > p.a) {
+            const double x = div_corrected(2.0 * (al - p.a), p.d_pim, p.d_pim_rcp);   // :461
+            double at, lg;
+            atan_log(p, x, at, lg);
+            r = p.rho + p.m * (x * at - lg / 2.0);                             // :467-468
+            const double sg = (l != l) ? l : copysign(1.0, l);                 // f64::signum
+            rp = (2.0 / CURVIS_PI) * sg * at;                                  // :479-480
+        } else {
+            r = p.rho;   // :470
+            rp = 0.0;    // :482
+        }
+        r2 = r * r;      // :474
     }
     static __device__ __forceinline__ void eval_shared(const FrameParams& p, double l, double& r, double& r2, double& rp, double& yr) {
-        eval(p, l, r, r2, rp);
+        eval_fast(p, l, r, r2, rp);
         yr = rcp_approx(r);       // r >= rho > 0
     }
     static __device__ __forceinline__ bool params_safe(const FrameParams& p) {

@@ -64,6 +64,8 @@ cudaError_t launch_debug_rhs_check(const FrameParams& p, int metric_kind, unsign
 cudaError_t launch_debug_shape(const double2* tab, int which, const double* x, double* out, size_t n, cudaStream_t stream);
 // Y(x) = 1/r and G(x) of the per-metric table as fast_variant 1 evaluates them (x given; test hook curvis_debug_inverse_shape).
 cudaError_t launch_debug_inverse_shape(const double2* tab, const double* x, double* y, double* g, size_t n, cudaStream_t stream);
+// atan x (which = 0) / ln(1 + x^2) (which = 1) as the operation-for-operation Interstellar step evaluates them (ops 17 / 18).  render_f64.cu.
+cudaError_t launch_debug_atan_log(const double* atan_tab, const double* log_tab, int which, const double* x, double* out, size_t n, cudaStream_t stream);
 // The same for the fp32 table of CURVIS_PRECISION_F32 (ops 15 / 16; x is rounded to float first).  render_f32.cu.
 cudaError_t launch_debug_shape32(const float4* tab, int which, const double* x, double* out, size_t n, cudaStream_t stream);
 

@@ -346,6 +346,22 @@ cudaError_t launch_debug_bilinear(const Background& bg, const double* fx, const 
     return cudaGetLastError();
 }
 
+__global__ void debug_atan_log_kernel(const double* atan_tab, const double* log_tab, int which, const double* x, double* out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    FrameParams p;
+    p.atan_tab = atan_tab; p.log_tab = log_tab;
+    double at, lg;
+    ShapeInterstellar::atan_log(p, x[i], at, lg);
+    out[i] = which ? lg : at;
+}
+
+cudaError_t launch_debug_atan_log(const double* atan_tab, const double* log_tab, int which, const double* x, double* out, size_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    debug_atan_log_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(atan_tab, log_tab, which, x, out, n);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_debug_eval(int op, const double* a, const double* b, double* out, size_t n, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     debug_eval_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(op, a, b, out, n);

@@ -112,6 +112,26 @@ double interstellar_table_l_limit(double, double a) {
     return a + ldexp(1.0, kInvTabEmax) * (1.0 - 0x1p-20);
 }
 
+// One function on 2^kShapeTabK intervals per binade of [2^emin, 2^emax): degree-5 coefficients in t = x - midpoint.
+template <class F>
+static void build_one(F f, int emin, int emax, double* out) {
+    constexpr int N = kShapeTabDegree + 1;
+    size_t idx = 0;
+    for (int e = emin; e < emax; ++e) {
+        const long double x0 = ldexpl(1.0L, e);
+        const int wexp = e - kShapeTabK - 1;
+        const long double w = ldexpl(1.0L, wexp);
+        for (int j = 0; j < (1 << kShapeTabK); ++j, ++idx) {
+            long double mono[N];
+            fit<N>(f, x0 + (2 * j + 1) * w, w, mono);
+            for (int k = 0; k < N; ++k) out[idx * N + k] = (double)ldexpl(mono[k], -k * wexp);
+        }
+    }
+}
+
+void build_atan_table(double* out) { build_one([](long double x) { return atanl(x); }, kShapeTabEmin, kShapeTabEmax, out); }
+void build_log_table(double* out) { build_one([](long double y) { return logl(y); }, 0, kLogTabEmax, out); }
+
 void build_interstellar_shape_table_f32(float* out) { build<kShapeTab32Degree + 1, float>(out, kShapeTab32K); }
 
 }  // namespace curvis
@@ -144,6 +164,38 @@ extern "C" int curvis_debug_inverse_table_host(double rho, double m, const doubl
         y[i] = U; g[i] = H;
     }
     delete[] table;
+    return all;
+}
+
+// Test hook: the atan (which = 0) / ln (which = 1) tables of the operation-for-operation kernel evaluated on the host exactly as
+// the kernel evaluates them.  Returns 1 when every argument was inside the table's range (NaN entries otherwise).
+extern "C" int curvis_debug_fn_table_host(int which, const double* x, double* out, size_t n) {
+    using namespace curvis;
+    static double* tabs[2] = {nullptr, nullptr};
+    if (!tabs[0]) {
+        double* a = new double[kAtanTabIntervals * kFnTabDoubles];
+        double* l = new double[kLogTabIntervals * kFnTabDoubles];
+        build_atan_table(a); build_log_table(l);
+        tabs[1] = l; tabs[0] = a;
+    }
+    const unsigned base = which ? kLogTabBase : kShapeTabBase;
+    const size_t count = which ? kLogTabIntervals : kAtanTabIntervals;
+    int all = 1;
+    for (size_t i = 0; i < n; ++i) {
+        unsigned long long bits;
+        __builtin_memcpy(&bits, &x[i], 8);
+        const unsigned hi = (unsigned)(bits >> 32);
+        const unsigned idx = (hi >> kShapeTabShift) - base;
+        if (idx >= (unsigned)count) { out[i] = NAN; all = 0; continue; }
+        const unsigned long long cbits = (unsigned long long)((hi & ~((1u << kShapeTabShift) - 1u)) | (1u << (kShapeTabShift - 1))) << 32;
+        double c;
+        __builtin_memcpy(&c, &cbits, 8);
+        const double t = x[i] - c;
+        const double* a = tabs[which ? 1 : 0] + (size_t)idx * kFnTabDoubles;
+        double v = a[kShapeTabDegree];
+        for (int k = kShapeTabDegree - 1; k >= 0; --k) v = fma(t, v, a[k]);
+        out[i] = v;
+    }
     return all;
 }
 

@@ -65,6 +65,25 @@ void build_interstellar_inverse_table(double rho, double m, double* out);   // o
 // |l| below which z = |l| - a stays inside the table (with a margin of one part in 2^20)
 double interstellar_table_l_limit(double m, double a);
 
+// atan and ln for the operation-for-operation kernel (CURVIS_PRECISION_F64, geodesic_f64.cuh: ShapeInterstellar::eval_fast).  The
+// reference evaluates r(l) as rho + m (x atan x - ln(1 + x^2)/2), operation by operation (metrics.rs:467-468); so does that
+// kernel, and two thirds of its Interstellar step were the CUDA library's atan and log (branches, ~80 fp64-pipe instructions, a
+// 370 ns dependency chain).  These tables give the same two functions to <= 1.5 ulp of the exact values — the class of the CUDA
+// library (2 ulp for atan, 1 for log); no libm is bit-identical to another anyway — in one table row and one degree-5 Horner
+// chain each:
+//   * atan(x) on x in [2^kShapeTabEmin, 2^kShapeTabEmax), the intervals of the F/G table above;
+//   * ln(y) on y in [1, 2^kLogTabEmax), 2^kShapeTabK intervals per binade (y = 1 + x^2 < 2^33 for every x of the atan table).
+//     Near y = 1, where ln -> 0, the polynomial's ABSOLUTE error (< 2^-55) is what holds: ln(1 + x^2) enters r as m ln/2 beside
+//     rho, and the reference's own 1 + x*x has already rounded x^2 to 2^-53 there.
+// Outside those ranges the kernel calls the library.
+constexpr int kLogTabEmax = 33;
+constexpr size_t kAtanTabIntervals = kShapeTabIntervals;
+constexpr size_t kLogTabIntervals = (size_t)kLogTabEmax << kShapeTabK;
+constexpr unsigned kLogTabBase = (unsigned)1023 << kShapeTabK;
+constexpr int kFnTabDoubles = kShapeTabDegree + 1;            // per interval: a0..a5
+void build_atan_table(double* out);   // out[kAtanTabIntervals * kFnTabDoubles]
+void build_log_table(double* out);    // out[kLogTabIntervals * kFnTabDoubles]
+
 // The fp32 edition for CURVIS_PRECISION_F32 (render_f32.cu): 2^4 intervals per binade of the same range,
 // degree-3 polynomials, 8 floats per interval (F a0..a3, then G b0..b3): two 128-bit loads and six FFMA
 // replace atanf + logf.  Relative error ~1e-7 (the fp32 rounding floor).

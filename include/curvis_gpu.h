@@ -403,7 +403,9 @@ int curvis_ctx_set_option(curvis_ctx* ctx, const char* key, int64_t value);
  *   7 a/b   8 sqrt(a)   9 1/a   (the compiler's IEEE operators, for reference)
  *   10 the <= 1 ulp reciprocal of CURVIS_PRECISION_F64_FAST   11 / 12 its sin^2(a) / sin(a)cos(a)
  *   13 / 14 its Interstellar shape functions a atan a - ln(1 + a^2)/2 and (2/pi) atan a (table; 0 for a <= 0)
- *   15 / 16 the same two functions as CURVIS_PRECISION_F32 evaluates them (fp32 table; a is rounded to float)   */
+ *   15 / 16 the same two functions as CURVIS_PRECISION_F32 evaluates them (fp32 table; a is rounded to float)
+ *   17 / 18 atan a and ln(1 + a^2) as the CURVIS_PRECISION_F64 Interstellar step evaluates them (tables inside a in [2^-10, 2^16),
+ *           the CUDA library outside)   */
 int curvis_debug_eval(curvis_ctx* ctx, int op, const double* a, const double* b, double* out, size_t n);
 
 /* Test hooks of the per-metric Interstellar table CURVIS_PRECISION_F64_FAST reads (csrc/shape_table.h): with r = rho + m (x atan x
@@ -425,6 +427,11 @@ int curvis_debug_rhs_check(curvis_ctx* ctx, const curvis_metric* metric, uint64_
  * the host with the kernel's arithmetic: f[i] = x atan x - ln(1 + x^2)/2, g[i] = (2/pi) atan x.  Returns 1
  * when every x[i] lay inside the table's range [2^-10, 2^16), else 0 (those entries are NaN). */
 int curvis_debug_shape_table_host(const double* x, double* f, double* g, size_t n);
+
+/* Test hook, host only: the atan (which = 0, x in [2^-10, 2^16)) and ln (which = 1, argument in [1, 2^33)) tables of the
+ * CURVIS_PRECISION_F64 Interstellar step (csrc/shape_table.h), evaluated on the host with the kernel's arithmetic.  Returns 1
+ * when every argument lay inside the table's range, else 0 (those entries are NaN).  On the device: curvis_debug_eval ops 17 / 18. */
+int curvis_debug_fn_table_host(int which, const double* x, double* out, size_t n);
 
 /* Test hook of CURVIS_SAMPLING_BILINEAR: the fp32 tap of background `side` at explicit continuous
  * texel coordinates (fx in [0,W), fy in [0,H]; texel centres at integer + 0.5; wrap in x, clamp in

@@ -218,3 +218,56 @@ def test_interstellar_inverse_table_host(lib, rho, m):
     yo, go = np.empty_like(out), np.empty_like(out)
     assert lib.curvis_debug_inverse_table_host(rho, m, out.ctypes.data_as(dp), yo.ctypes.data_as(dp), go.ctypes.data_as(dp), out.size) == 0
     assert np.isnan(yo).all()
+
+
+def test_strict_interstellar_atan_and_log_tables_host(lib):
+    """atan and ln as the CURVIS_PRECISION_F64 Interstellar step evaluates them (csrc/shape_table.h: degree-5 pieces, 128 per
+    binade), on the host with the kernel's arithmetic against x87 long double: <= 1.5 ulp for atan on [2^-10, 2^16); for ln on
+    [1, 2^33) <= 1.6 ulp or, next to 1 where ln -> 0, 2^-55 absolute (ln(1 + x^2) enters r as m ln / 2 beside rho: only its
+    absolute error is seen, and the reference's own 1 + x*x has already rounded x^2 to 2^-53 there).  Arguments outside the tables are refused."""
+    import ctypes as C
+    import numpy as np
+    rng = np.random.default_rng(5)
+    dp = C.POINTER(C.c_double)
+
+    def run(which, x):
+        out = np.empty_like(x)
+        rc = lib.curvis_debug_fn_table_host(which, x.ctypes.data_as(dp), out.ctypes.data_as(dp), x.size)
+        return rc, out
+
+    x = np.concatenate([np.exp(rng.uniform(np.log(2.0 ** -10), np.log(2.0 ** 16), 1_000_000)), np.ldexp(1.0, np.arange(-10, 16)),
+                        np.nextafter(np.ldexp(1.0, np.arange(-9, 17)), 0.0)])
+    rc, at = run(0, x)
+    assert rc == 1
+    want = np.arctan(x.astype(np.longdouble))
+    err = np.abs((at.astype(np.longdouble) - want) / np.spacing(np.abs(want.astype(np.float64))).astype(np.longdouble)).astype(np.float64)
+    assert err.max() <= 1.5, err.max()        # (the CUDA library documents 2 ulp for atan, 1 for log)
+    y = np.concatenate([np.exp(rng.uniform(0.0, np.log(2.0 ** 33), 1_000_000)), 1.0 + np.exp(rng.uniform(np.log(2.0 ** -52), 0.0, 200_000)),
+                        np.array([1.0, np.nextafter(1.0, 2.0), 2.0, np.nextafter(2.0 ** 33, 0.0)])])
+    rc, lg = run(1, y)
+    assert rc == 1
+    want = np.log(y.astype(np.longdouble))
+    abs_err = np.abs(lg.astype(np.longdouble) - want).astype(np.float64)
+    ulp = np.spacing(np.abs(want.astype(np.float64)))
+    assert (abs_err <= np.maximum(1.6 * ulp, 2.0 ** -55)).all(), (abs_err / np.maximum(1.6 * ulp, 2.0 ** -55)).max()
+    for which, bad in ((0, np.array([2.0 ** -11, 2.0 ** 16, 0.0, -1.0])), (1, np.array([0.5, 2.0 ** 33, 0.0, -2.0]))):
+        rc, out = run(which, bad)
+        assert rc == 0 and np.isnan(out).all()
+
+
+def test_quotient_from_a_correctly_rounded_reciprocal_is_correctly_rounded():
+    """The CURVIS_PRECISION_F64 Interstellar step forms x = 2 (|l| - a) / (pi m) as q0 = a y; rem = fma(-b, q0, a); q = fma(rem, y, q0)
+    with y = RN(1 / b) supplied by the host (csrc/geodesic_f64.cuh: ShapeInterstellar::eval_fast): that is RN(a / b).  Checked here
+    with exact rational arithmetic standing in for the two fused operations."""
+    from fractions import Fraction
+    import numpy as np
+    rng = np.random.default_rng(99)
+    a = np.ldexp(rng.uniform(1.0, 2.0, 20_000), rng.integers(-40, 10, 20_000))
+    b = np.concatenate([np.ldexp(rng.uniform(1.0, 2.0, 19_000), rng.integers(-20, 20, 19_000)),
+                        np.pi * rng.uniform(1e-3, 10.0, 1_000)])                 # pi m for plausible m
+    for ai, bi in zip(a.tolist(), b.tolist()):
+        y = 1.0 / bi
+        q0 = ai * y
+        rem = float(Fraction(ai) - Fraction(bi) * Fraction(q0))                   # one rounding (the first FMA; nearly always exact)
+        q = float(Fraction(rem) * Fraction(y) + Fraction(q0))                     # one rounding (the second FMA)
+        assert q == ai / bi

@@ -118,3 +118,27 @@ def test_kernel_variants_render_identical_frames(gpu_ctx, oracle):
             assert (rec[f] == ref_rec[f]).all(), (variant, blocks, window, f)
     with pytest.raises(cv.CurvisError):
         ctx.set_option("no_such_option", 1)
+
+
+def test_strict_interstellar_atan_and_log_on_device(gpu_ctx):
+    """atan x and ln(1 + x^2) as the CURVIS_PRECISION_F64 Interstellar step evaluates them (csrc/geodesic_f64.cuh:
+    ShapeInterstellar::atan_log): inside the tables bit-identical to the host evaluation of the same tables
+    (tests/test_abi_host.py holds that to <= 1.5 ulp of long double), outside them the CUDA library."""
+    import ctypes as C
+    from curvis_b200 import _abi
+    lib = _abi.load_library()
+    dp = C.POINTER(C.c_double)
+    rng = np.random.default_rng(23)
+    x = np.concatenate([np.exp(rng.uniform(np.log(2.0 ** -10), np.log(2.0 ** 16), 1_000_000)), np.ldexp(1.0, np.arange(-10, 16))])
+    at, lg = gpu_ctx.debug_eval(17, x), gpu_ctx.debug_eval(18, x)
+    y = 1.0 + x * x                                   # the reference's two roundings (metrics.rs:468)
+    hat, hlg = np.empty_like(x), np.empty_like(x)
+    assert lib.curvis_debug_fn_table_host(0, x.ctypes.data_as(dp), hat.ctypes.data_as(dp), x.size) == 1
+    assert lib.curvis_debug_fn_table_host(1, y.ctypes.data_as(dp), hlg.ctypes.data_as(dp), x.size) == 1
+    assert at.tobytes() == hat.tobytes() and lg.tobytes() == hlg.tobytes()
+    # outside the tables: the library functions (<= 2 ulp)
+    out = np.concatenate([np.exp(rng.uniform(np.log(1e-12), np.log(2.0 ** -10), 10_000)), np.exp(rng.uniform(np.log(2.0 ** 16), np.log(1e12), 10_000))])
+    ol = out.astype(np.longdouble)
+    for got, want in ((gpu_ctx.debug_eval(17, out), np.arctan(ol)), (gpu_ctx.debug_eval(18, out), np.log((1.0 + out * out).astype(np.longdouble)))):
+        err = np.abs((got.astype(np.longdouble) - want) / np.spacing(np.abs(want.astype(np.float64))).astype(np.longdouble)).astype(np.float64)
+        assert err.max() <= 2.0
