@@ -228,6 +228,10 @@ def strong_scaling(args, cv, system, sim, PREC, ctx, rank, n, local, dev, stream
             system.render_frames_peers([cam], *sim, r0, r1, [b.ptr for b in bufs], stream.cuda_stream, row_stride=stride, precision=PREC)
             dist.all_reduce(token)
 
+        def fused_contiguous():     # the same fused launch on CONTIGUOUS row tiles (what the NCCL form renders)
+            system.render_frames_peers([cam], *sim, rank * rows, (rank + 1) * rows, [b.ptr for b in bufs], stream.cuda_stream, row_stride=1, precision=PREC)
+            dist.all_reduce(token)
+
         def nccl():
             system.render_rows_device(*sim, rank * rows, (rank + 1) * rows, tile.data_ptr(), stream.cuda_stream, precision=PREC)
             dist.all_gather_into_tensor(full, tile)
@@ -254,6 +258,12 @@ def strong_scaling(args, cv, system, sim, PREC, ctx, rank, n, local, dev, stream
         steps = int(st["total_steps"])
         kernel_single_ms = st["kernel_ms"]
         t_single, t_fused, t_nccl = timed(single), timed(fused), timed(nccl)
+        gathered.zero_()
+        dist.barrier()
+        t_fused_contig = timed(fused_contiguous)
+        torch.cuda.synchronize()
+        bad_contig = (gathered.view(-1, 3) != whole.view(-1, 3)).any(dim=1).sum().to(torch.int64)
+        dist.all_reduce(bad_contig)
         ctx.set_option("guard", 0)          # the regrouped kernel alone: what the guard band's second launch costs at this tile size
         t_fused_raw = timed(fused)
         ctx.set_option("guard", 1)
@@ -277,6 +287,8 @@ def strong_scaling(args, cv, system, sim, PREC, ctx, rank, n, local, dev, stream
                                   "rank_kernel_ms_max": float(kmax.item()), "rank_kernel_ms_min": float(kmin.item()),
                                   "rank_kernel_ms": [round(float(k.item()), 3) for k in kall],
                                   "rank_rays_reintegrated": [int(r.item()) for r in redo_all],
+                                  "ms_per_frame_contiguous_tiles": t_fused_contig, "speedup_contiguous_tiles": t_single / t_fused_contig,
+                                  "differing_pixels_contiguous_tiles": int(bad_contig.item()),
                                   "ms_per_frame_without_guard_band": t_fused_raw, "speedup_without_guard_band": t_single / t_fused_raw,
                                   "ideal_ms": t_single / n,
                                   "limiter": "fixed costs that do not shrink with the tile: ms_per_frame - rank_kernel_ms_max = the all-reduce "
@@ -366,7 +378,7 @@ def run_b200(args):
     background_upload_ms = (time.perf_counter() - t_up0) * 1e3
     sim = (scenes.DEFAULT_MAX_ITERATIONS, scenes.DEFAULT_ESCAPE_RADIUS, scenes.DEFAULT_STEP)
     PREC = {"f64_fast": _abi.PRECISION_F64_FAST, "f64": _abi.PRECISION_F64}[args.precision]
-    KERNEL = {"f64_fast": "render_rows_f64_fast<FastEllis, 1, 5>", "f64": "render_rows_f64_lean<ShapeEllis, 0, 0, 1>"}[args.precision]
+    KERNEL = {"f64_fast": "render_rows_f64_fast<FastEllis, 1, 5, 0>", "f64": "render_rows_f64_lean<ShapeEllis, 0, 0, 1>"}[args.precision]
 
     stream = torch.cuda.current_stream()
     frames = [torch.empty(Ht * Wd * 3, dtype=torch.uint8, device=dev) for _ in range(n)]   # complete frames
