@@ -764,6 +764,36 @@ def run_b200(args):
                               "instructions per step; checked against its own oracle restatement (tests/test_gpu_extensions.py)",
                       "kernel_ms": min(cms), "total_steps": int(s7["total_steps"]), "value": s7["total_steps"] / (min(cms) * 1e-3), "unit": UNIT}
 
+    # ---- the row next to the path: render_image_efficient, what the reference's binary runs — a table of escape angles
+    # (sampler on the host, its photons integrated by the kernels above) + one cheap kernel per pixel.  Wall time per 4K frame
+    # through the host-buffer call into a registered frame, both metrics, table photons in F64 and in F64_FAST.
+    efficient = None
+    if n == 1 and args.width == W4K and args.height == H4K:
+        import numpy as np
+        efficient = {"what": "curvis_render_image_efficient (systems.rs:333-527), 3840x2160 into a registered host frame, wall ms per frame "
+                             "(reference defaults: 100 initial points, 100 refinement passes, thresholds 1e-5)"}
+        ebuf = np.empty((Ht, Wd, 3), dtype=np.uint8)
+        ctx.register_host_buffer(ebuf)
+        try:
+            for mname, metric in (("ellis", cv.EllisMetric(1.0)), ("interstellar", cv.InterstellarMetric(0.1, 1e-4, 1.0))):
+                esys = cv.RelativisticSystem(metric, cv.SphericalImage(bp), cv.SphericalImage(bn), system.camera, context=ctx)
+                res = {}
+                for pname, prec in (("f64", _abi.PRECISION_F64), ("f64_fast", _abi.PRECISION_F64_FAST)):
+                    walls = []
+                    for _ in range(4):
+                        t0 = time.perf_counter()
+                        esys.render_image_efficient(*sim, 100, 100, 1e-5, 1e-5, out=ebuf, precision=prec)
+                        walls.append((time.perf_counter() - t0) * 1e3)
+                    info = esys.last_efficient_info
+                    res[pname] = {"wall_ms": min(walls[1:]), "table_ms": info.get("table_ms"), "table_points": info.get("table_points")}
+                    if pname == "f64":
+                        ref_frame = ebuf.copy()
+                    else:
+                        res[pname]["differing_pixels_vs_f64_table"] = int((ebuf != ref_frame).any(axis=2).sum())
+                efficient[mname] = res
+        finally:
+            ctx.unregister_host_buffer(ebuf)
+
     cpu_baseline = None
     if n == 1 and not args.no_cpu_baseline:
         one, sample = oracle_sample(args, rows_per_step=60, threads=1)
@@ -796,6 +826,7 @@ def run_b200(args):
         "parity_check": parity_check,
         "f32_mode": fast_mode,
         "chart_free_mode": chart_free,
+        "efficient_renderer": efficient,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

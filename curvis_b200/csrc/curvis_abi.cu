@@ -972,6 +972,11 @@ extern "C" int curvis_render_image_efficient(curvis_ctx* ctx, const curvis_metri
         eq.resolution_width = (uint32_t)n; eq.resolution_height = 1;
         fill_params(ctx, d, metric, &eq, sim, 0, 1, nullptr, d.d_records, p);
         p.ray_dirs = d_dirs;
+        // The table's photons carry no integer decision for a guard band to protect (the sampler reads escape angles, and its table
+        // is accurate to ~5e-4 rad): with CURVIS_PRECISION_F64_FAST they take the raw regrouped kernel.  They are equatorial, so
+        // the band would flag every one of them (theta = pi/2 sits exactly on a texel edge) and the pass would cost the strict
+        // launch on top of the fast one.
+        p.redo_list = nullptr; p.redo_capacity = 0;
         if ((e = cudaMemsetAsync(d.d_counters, 0, sizeof(DeviceCounters), d.stream)) != cudaSuccess ||
             (e = launch_render(p, metric, sim, ctx->tuning, d.sm_count, d.stream)) != cudaSuccess ||
             (e = cudaMemcpyAsync(out, d.d_records, n * sizeof(curvis_ray_record), cudaMemcpyDeviceToHost, d.stream)) != cudaSuccess ||

@@ -52,5 +52,17 @@ for i in range(4):
     sysm.render_rows_device(3000, 60.0, 0.05, 0, H, tiles[i].data_ptr(), streams[i & 1].cuda_stream, precision=_abi.PRECISION_F64_FAST)
 torch.cuda.synchronize()
 assert all((t == tiles[0]).all() for t in tiles)
+# round 2, later: the longest-first pre-pass + list (launches of >= 2^15 rays), the cached Interstellar table, the strict kernel's atan / ln tables
+W2, H2 = 256, 144
+cam2 = cv.Camera(scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP, 15.0, 43.0, W2, H2)
+for lf in (1, 2, 0):
+    ctx.set_option("longest_first", lf)
+    for metric in (cv.EllisMetric(1.0), cv.InterstellarMetric(0.1, 1e-4, 1.0)):
+        sysm = cv.RelativisticSystem(metric, cv.SphericalImage(bp), cv.SphericalImage(bn), cam2, context=ctx)
+        a = sysm.render_image(400, 12.0, 0.1, precision=_abi.PRECISION_F64_FAST)
+        b = sysm.render_image(400, 12.0, 0.1, precision=_abi.PRECISION_F64)
+        assert (a == b).all()
+        print("longest_first", lf, type(metric).__name__, sysm.last_stats["total_steps"], flush=True)
+ctx.set_option("longest_first", 2)
 ctx.unregister_host_buffer(out)
 print("ok")
