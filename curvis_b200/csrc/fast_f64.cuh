@@ -143,7 +143,7 @@ __device__ __forceinline__ void interstellar_inverse_lookup(double a, double l, 
     const double x = fabs(l) - a;        // z
     const unsigned hi = (unsigned)__double2hiint(x);
     const unsigned idx = min((hi >> kInvTabShift) - kInvTabBase, (unsigned)kInvTabConstRow);
-    const double c = __hiloint2double((int)((hi & ~((1u << kInvTabShift) - 1u)) | (1u << (kInvTabShift - 1))), 0);
+    const double c = __hiloint2double((int)(hi & ~((1u << kInvTabShift) - 1u)), 0);   // the interval's lower edge: z's low mantissa bits cleared
     const double t = x - c;
     if (idx != k.idx) {
         // three 256-bit loads (sm_100: LDG.E.256; a row is 96 bytes, the table 256-byte aligned)

@@ -95,10 +95,23 @@ void build_interstellar_inverse_table(double rho, double m, double* out) {
             long double mu[N], mh[N];
             fit<N>(inv_r2, c, w, mu);
             fit<N>(force, c, w, mh);
+            // The kernel measures t from the interval's LOWER edge (z with its low mantissa bits cleared: one mask instead of
+            // mask + midpoint bit), so the polynomials are re-expanded about tau = -1: tau = sigma - 1, sigma in [0, 2].
+            long double su[N], sh[N];
+            for (int jj = 0; jj < N; ++jj) {
+                long double au = 0.0L, ah = 0.0L, binom = 1.0L;          // binom = C(k, jj)
+                for (int k = jj; k < N; ++k) {
+                    const long double sign = ((k - jj) & 1) ? -1.0L : 1.0L;
+                    au += mu[k] * binom * sign;
+                    ah += mh[k] * binom * sign;
+                    binom = binom * (k + 1) / (k + 1 - jj);
+                }
+                su[jj] = au; sh[jj] = ah;
+            }
             double* o = out + idx * 2 * N;
             for (int k = 0; k < N; ++k) {
-                o[k] = (double)ldexpl(mu[k], -k * wexp);
-                o[N + k] = (double)ldexpl(mh[k], -k * wexp);
+                o[k] = (double)ldexpl(su[k], -k * wexp);
+                o[N + k] = (double)ldexpl(sh[k], -k * wexp);
             }
         }
     }
@@ -151,7 +164,7 @@ extern "C" int curvis_debug_inverse_table_host(double rho, double m, const doubl
         unsigned idx = (hi >> kInvTabShift) - kInvTabBase;
         if (z[i] >= ldexp(1.0, kInvTabEmax)) { y[i] = g[i] = NAN; all = 0; continue; }
         if (idx > (unsigned)kInvTabConstRow) idx = (unsigned)kInvTabConstRow;
-        const unsigned long long cbits = (unsigned long long)((hi & ~((1u << kInvTabShift) - 1u)) | (1u << (kInvTabShift - 1))) << 32;
+        const unsigned long long cbits = (unsigned long long)(hi & ~((1u << kInvTabShift) - 1u)) << 32;     // the interval's lower edge
         double c;
         __builtin_memcpy(&c, &cbits, 8);
         const double t = z[i] - c;
