@@ -356,12 +356,14 @@ __device__ __forceinline__ void euler_step_tuned(const FrameParams& p, Ray& q, b
 // Right-hand side of the geodesic equations at a state (metrics.rs:223-270), lean form.
 template <class Shape, bool SHARED = true>
 __device__ __forceinline__ void rhs_lean(const FrameParams& p, bool ray_safe, double l, double th, double pth, double pph, double pph2,
-                                         double& dth, double& dph, double& dpl, double& dpth, double& s) {
+                                         double& dth, double& dph, double& dpl, double& dpth, double& s, const TrigPins* pins = nullptr) {
     const bool pre = ray_safe && (abs_hi(th) < pow2_hi(30)) && ((abs_hi(l) - pow2_hi(-100)) < (pow2_hi(100) - pow2_hi(-100))) &&
                      (abs_hi(pth) < pow2_hi(100));
     double c;
-    if (pre) sincos_fast<true>(th, s, c);
-    else TrigFast::sincos(th, s, c);
+    if (pre) {
+        if (pins) sincos_fast_pinned(*pins, th, s, c);     // (the render kernel's step: constants pinned in registers)
+        else sincos_fast<true>(th, s, c);
+    } else TrigFast::sincos(th, s, c);
     if (pre && abs_hi(s) >= pow2_hi(-60)) {
         if (SHARED) {
             // kernel_variant 4 (default): the same seven roundings, the six divisors' reciprocals built from TWO seeds —
@@ -411,9 +413,9 @@ __device__ __forceinline__ void rhs_lean(const FrameParams& p, bool ray_safe, do
 struct RayDiag { double min_abs_sin, stiffness; };
 
 template <class Shape, bool TRACK = false, bool SHARED = true>
-__device__ __forceinline__ void euler_step_lean(const FrameParams& p, Ray& q, bool ray_safe, RayDiag* diag = nullptr) {
+__device__ __forceinline__ void euler_step_lean(const FrameParams& p, Ray& q, bool ray_safe, RayDiag* diag = nullptr, const TrigPins* pins = nullptr) {
     double dth, dph, dpl, dpth, s;
-    rhs_lean<Shape, SHARED>(p, ray_safe, q.l, q.th, q.pth, q.pph, q.pph2, dth, dph, dpl, dpth, s);
+    rhs_lean<Shape, SHARED>(p, ray_safe, q.l, q.th, q.pth, q.pph, q.pph2, dth, dph, dpl, dpth, s, pins);
     if (TRACK) {
         const double step_phi = dph * p.delta;
         diag->min_abs_sin = fmin(diag->min_abs_sin, fabs(s));

@@ -122,6 +122,8 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64_lean(const __grid_cons
     uint32_t remaining = 0;   // steps left before NotEscaped
     unsigned long long ray = 0;
     RayDiag diag = {qnan, qnan};
+    TrigPins pins;            // three constants of the step's sincos, pinned in registers (trig_f64.cuh)
+    pins.load();
 
     RayTally tally;
 
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64_lean(const __grid_cons
             do {
                 if (INTEG == 1) rk4_step_lean<Shape>(p, q, ray_safe);
                 else if (INTEG == 2) euler_step_adaptive<Shape, TRACK>(p, q, ray_safe, &diag);
-                else euler_step_lean<Shape, TRACK, SHARED>(p, q, ray_safe, &diag);
+                else euler_step_lean<Shape, TRACK, SHARED>(p, q, ray_safe, &diag, &pins);
                 ++k;
                 if (abs_hi(q.l) >= gate) { near = true; break; }     // |l| >= R (1 - 2^-20), or NaN
             } while (k < n);

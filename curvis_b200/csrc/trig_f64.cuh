@@ -64,6 +64,48 @@ __device__ __forceinline__ void sincos_fast(double x, double& s, double& c) {
     c = __hiloint2double(__double2hiint(b) ^ (((k + 1) & 2) << 30), __double2loint(b));
 }
 
+// The three constants of sincos_fast that meet another constant in the same FMA (an fp64 instruction takes ONE uniform /
+// constant-bank operand, so the other must sit in a vector register): the rounding magic and the two leading coefficients.
+// Left to itself ptxas re-loads them (LDC) every step — six issue slots of the operation-for-operation kernel's step; read once
+// per kernel through a plain global load they stay in registers (the same trick as fast_f64.cuh: kPinned).
+static __device__ double kTrigPinned[3] = {6755399441055744.0, 1.5912475864762696e-10, -1.1379094621237813e-11};   // magic, kSinPoly[5], kCosPoly[5]
+
+struct TrigPins {
+    double magic, sin5, cos5;
+    __device__ __forceinline__ void load() {
+        asm volatile("ld.global.f64 %0, [%1];" : "=d"(magic) : "l"(kTrigPinned));
+        asm volatile("ld.global.f64 %0, [%1];" : "=d"(sin5) : "l"(kTrigPinned + 1));
+        asm volatile("ld.global.f64 %0, [%1];" : "=d"(cos5) : "l"(kTrigPinned + 2));
+    }
+};
+
+// sincos_fast<true> with those three in registers: the same operations on the same values.
+__device__ __forceinline__ void sincos_fast_pinned(const TrigPins& tp, double x, double& s, double& c) {
+    const double t = fma(x, kTrigReduce[0], tp.magic);
+    const int k = __double2loint(t);
+    const double q = t - tp.magic;
+    double r = fma(-q, kTrigReduce[2], x);
+    r = fma(-q, kTrigReduce[3], r);
+    r = fma(-q, kTrigReduce[4], r);
+    const double u = r * r;
+    double sp = fma(u, tp.sin5, kSinPoly[4]);
+    double cp = fma(u, tp.cos5, kCosPoly[4]);
+    sp = fma(u, sp, kSinPoly[3]);
+    cp = fma(u, cp, kCosPoly[3]);
+    sp = fma(u, sp, kSinPoly[2]);
+    cp = fma(u, cp, kCosPoly[2]);
+    sp = fma(u, sp, kSinPoly[1]);
+    cp = fma(u, cp, kCosPoly[1]);
+    sp = fma(u, sp, kSinPoly[0]);
+    cp = fma(u, cp, kCosPoly[0]);
+    const double sr = fma(r * u, sp, r);
+    const double cr = fma(u * u, cp, fma(u, -0.5, 1.0));
+    const double a = (k & 1) ? cr : sr;
+    const double b = (k & 1) ? sr : cr;
+    s = __hiloint2double(__double2hiint(a) ^ ((k & 2) << 30), __double2loint(a));
+    c = __hiloint2double(__double2hiint(b) ^ (((k + 1) & 2) << 30), __double2loint(b));
+}
+
 struct TrigFast {
     static __device__ __forceinline__ void sincos(double x, double& s, double& c) {
         if (fabs(x) < kTrigFastLimit) sincos_fast(x, s, c);
