@@ -686,7 +686,7 @@ def run_b200(args):
 
     # ---- the operation-for-operation kernel (CURVIS_PRECISION_F64) next to the headline, the headline frame against it
     # pixel for pixel, and BOTH against the CPU oracle on strided rows, split into regular / chaotic rays
-    strict_mode, parity_check, raw_fast = None, None, None
+    strict_mode, parity_check, raw_fast, full_identity = None, None, None, None
     if n == 1:
         sms = []
         for _ in range(3):
@@ -712,6 +712,20 @@ def run_b200(args):
             raw_fast = {"what": "the regrouped kernel alone (ctx option guard = 0): no guard band, no re-integration — not what `value` times",
                         "kernel_ms": min(rms), "value": s6["total_steps"] / (min(rms) * 1e-3), "unit": UNIT,
                         "differing_pixels_vs_f64": int((strict_frame.view(-1, 3) != frames[0].view(-1, 3)).any(dim=1).sum().item())}
+            # guard = 2: the kicked rays (stiffness >= 1) are re-integrated too, so EVERY ray of the frame carries the
+            # operation-for-operation arithmetic — identity with CURVIS_PRECISION_F64 by construction, not by measurement
+            ctx.set_option("guard", 2)
+            gms = []
+            for _ in range(3):
+                s7 = system.render_rows_device(*sim, row_begin, row_end, frames[0].data_ptr(), stream.cuda_stream, want_stats=True, precision=PREC)
+                gms.append(s7["kernel_ms"])
+            ctx.set_option("guard", 1)
+            full_identity = {"what": "ctx option guard = 2: every ray outside the guard band's certificate (the kicked rays included) is re-integrated "
+                                     "with the CURVIS_PRECISION_F64 arithmetic — not what `value` times",
+                             "kernel_ms": min(gms), "value": s7["total_steps"] / (min(gms) * 1e-3), "unit": UNIT,
+                             "n_reintegrated": int(s7["n_reintegrated"]), "n_kicked": int(s7["n_kicked"]),
+                             "differing_pixels_vs_f64": int((strict_frame.view(-1, 3) != frames[0].view(-1, 3)).any(dim=1).sum().item()),
+                             "speedup_vs_f64_kernel": min(sms) / min(gms)}
         parity_check = {"f64_fast_vs_f64_kernel": {"pixels": Wd * Ht, "differing_pixels": differing,
                                                    "total_steps_equal": bool(s4["total_steps"] == s5["total_steps"]),
                                                    "escape_counters_equal": all(s4[k] == s5[k] for k in ("n_positive", "n_negative", "n_not_escaped", "n_clamped")),
@@ -823,6 +837,7 @@ def run_b200(args):
         "cpu_baseline": cpu_baseline,
         "strict_mode": strict_mode,
         "raw_fast_kernel": raw_fast,
+        "full_identity_mode": full_identity,
         "parity_check": parity_check,
         "f32_mode": fast_mode,
         "chart_free_mode": chart_free,

@@ -855,6 +855,7 @@ extern "C" int curvis_ctx_set_option(curvis_ctx* ctx, const char* key, int64_t v
     else if (k == "guard" && value >= 0 && value <= 2) ctx->tuning.guard = (int)value;
     else if (k == "fast_regs" && (value == 0 || value == 96 || value == 128)) ctx->tuning.fast_regs = (int)value;
     else if (k == "redo_blocks_per_sm" && value >= 0 && value <= 32) ctx->tuning.redo_blocks_per_sm = (int)value;
+    else if (k == "redo_ahead" && value >= 0 && value <= 1) ctx->tuning.redo_ahead = (int)value;
     else if (k == "redo_capacity_limit" && value >= 0) ctx->tuning.redo_capacity_limit = value;
     else if (k == "longest_first" && value >= 0 && value <= 2) ctx->tuning.longest_first = (int)value;
     else if (k == "guard_rel_e15" && value >= 1 && value <= 1000000000000ll) ctx->tuning.guard_rel = (double)value * 1e-15;

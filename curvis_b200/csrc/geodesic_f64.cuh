@@ -354,6 +354,25 @@ __device__ __forceinline__ void euler_step_tuned(const FrameParams& p, Ray& q, b
 // instruction holds the scheduler's dispatch port for two cycles, so every fp64 op removed is
 // worth two integer ops (profiles/r01_f64_v2_ncu_summary.txt).  Arithmetic is unchanged.
 // Right-hand side of the geodesic equations at a state (metrics.rs:223-270), lean form.
+// The shared-reciprocal right-hand side (kernel_variant 4) from its parts: the shape function at l (r, r^2, r', yr ~ 1/r) and
+// (sin, cos) of theta.  The same seven roundings as the plain operators: the six divisors' reciprocals are built from TWO seeds —
+// yr (a by-product of the square root) and ys ~ 1/sin^2 theta — and one correction step each (ieee_f64.cuh: div_corrected /
+// rcp_corrected): 77 fp64-pipe instructions per step instead of 100.
+__device__ __forceinline__ void rhs_shared_from(double r, double r2, double rp, double yr, double s, double c, double pth, double pph, double pph2,
+                                                double& dth, double& dph, double& dpl, double& dpth) {
+    const double s2 = s * s;
+    const double yr2 = yr * yr;                                        // ~ 1/r^2
+    const double ys = rcp_approx(s2);                                  // ~ 1/sin^2
+    const double yrs = yr2 * ys;                                       // ~ 1/(r^2 sin^2)
+    const double g22c = rcp_corrected(r2, yr2);                        // metrics.rs:90
+    const double g33c = rcp_corrected(r2 * s2, yrs);                   // :93
+    dth = pth * g22c;
+    dph = pph * g33c;
+    const double b2 = pth * pth + div_corrected(pph2, s2, ys);         // :257
+    dpl = div_corrected(b2 * rp, (r * r) * r, yr2 * yr);               // :261
+    dpth = pph2 * div_corrected(c, r2 * (s2 * s), yrs * (ys * s));     // :262
+}
+
 template <class Shape, bool SHARED = true>
 __device__ __forceinline__ void rhs_lean(const FrameParams& p, bool ray_safe, double l, double th, double pth, double pph, double pph2,
                                          double& dth, double& dph, double& dpl, double& dpth, double& s, const TrigPins* pins = nullptr) {
@@ -366,22 +385,10 @@ __device__ __forceinline__ void rhs_lean(const FrameParams& p, bool ray_safe, do
     } else TrigFast::sincos(th, s, c);
     if (pre && abs_hi(s) >= pow2_hi(-60)) {
         if (SHARED) {
-            // kernel_variant 4 (default): the same seven roundings, the six divisors' reciprocals built from TWO seeds —
-            // yr ~ 1/r (a by-product of the square root) and ys ~ 1/sin^2 theta — and one correction step each
-            // (ieee_f64.cuh: div_corrected / rcp_corrected): 77 fp64-pipe instructions per step instead of 100.
+            // kernel_variant 4 (default): rhs_shared_from
             double r, r2, rp, yr;
             Shape::eval_shared(p, l, r, r2, rp, yr);
-            const double s2 = s * s;
-            const double yr2 = yr * yr;                                        // ~ 1/r^2
-            const double ys = rcp_approx(s2);                                  // ~ 1/sin^2
-            const double yrs = yr2 * ys;                                       // ~ 1/(r^2 sin^2)
-            const double g22c = rcp_corrected(r2, yr2);                        // :90
-            const double g33c = rcp_corrected(r2 * s2, yrs);                   // :93
-            dth = pth * g22c;
-            dph = pph * g33c;
-            const double b2 = pth * pth + div_corrected(pph2, s2, ys);         // :257
-            dpl = div_corrected(b2 * rp, (r * r) * r, yr2 * yr);               // :261
-            dpth = pph2 * div_corrected(c, r2 * (s2 * s), yrs * (ys * s));     // :262
+            rhs_shared_from(r, r2, rp, yr, s, c, pth, pph, pph2, dth, dph, dpl, dpth);
         } else {
             double r, r2, rp;
             Shape::eval_fast(p, l, r, r2, rp);
@@ -426,6 +433,60 @@ __device__ __forceinline__ void euler_step_lean(const FrameParams& p, Ray& q, bo
     q.ph = q.ph + dph * p.delta;
     q.pl = q.pl + dpl * p.delta;                              // :296
     q.pth = q.pth + dpth * p.delta;
+}
+
+// ---- the same step in LATENCY form (list mode of render_rows_f64_lean: the guard band's re-integration launch).
+// That launch holds a few hundred rays — at most one warp per scheduler — so its duration is ONE ray's dependent chain times
+// its step count, not the fp64 pipe's throughput.  Inside one step the chain is  theta -> sincos (13 dependent operations) ->
+// 1/sin^2 -> quotient -> p_theta  (28 operations, 530 cycles measured), but the NEXT step's two long evaluations depend on
+// little of this one: its shape function needs only l + delta p_l (one operation into the step), its sincos only
+// theta + delta p_theta / r^2 (six operations).  euler_steps_ahead() carries both across the loop's back edge — the step loop
+// computes the right-hand side from the carried parts, updates the state and starts the next step's parts in the SAME basic
+// block, so the two chains overlap with the quotients.  Same operations on the same values: nothing is rounded differently;
+// the look-ahead of the last step is discarded.  States outside the unguarded sequences' window take rhs_lean's own path.
+struct StepParts { double r, r2, rp, yr, s, c; };
+
+template <class Shape>
+__device__ __forceinline__ bool look_ahead(const FrameParams& p, const TrigPins& pins, bool ray_safe, const Ray& q, StepParts& a) {
+    const bool pre = ray_safe && (abs_hi(q.th) < pow2_hi(30)) && ((abs_hi(q.l) - pow2_hi(-100)) < (pow2_hi(100) - pow2_hi(-100))) &&
+                     (abs_hi(q.pth) < pow2_hi(100));                // rhs_lean's test
+    sincos_fast_pinned(pins, q.th, a.s, a.c);                       // (speculative: plain arithmetic on any operand)
+    Shape::eval_shared(p, q.l, a.r, a.r2, a.rp, a.yr);
+    return pre && abs_hi(a.s) >= pow2_hi(-60);
+}
+
+// Up to n Euler steps; stops after the step that takes |l| to the radius gate (`near`).  Returns the steps taken.
+template <class Shape>
+__device__ __forceinline__ uint32_t euler_steps_ahead(const FrameParams& p, const TrigPins& pins, bool ray_safe, Ray& q, uint32_t n, unsigned gate, bool& near) {
+    uint32_t k = 0;
+    StepParts a;
+    bool ok = look_ahead<Shape>(p, pins, ray_safe, q, a);
+    for (;;) {
+        if (!ok) {                                                  // outside the window: the general step
+            euler_step_lean<Shape, false, true>(p, q, ray_safe, nullptr, &pins);
+            ++k;
+            if (abs_hi(q.l) >= gate) { near = true; break; }
+            if (k >= n) break;
+            ok = look_ahead<Shape>(p, pins, ray_safe, q, a);
+            continue;
+        }
+        bool at_gate;
+        do {
+            double dth, dph, dpl, dpth;
+            rhs_shared_from(a.r, a.r2, a.rp, a.yr, a.s, a.c, q.pth, q.pph, q.pph2, dth, dph, dpl, dpth);
+            q.l = q.l + q.pl * p.delta;                             // metrics.rs:295
+            q.th = q.th + dth * p.delta;
+            q.ph = q.ph + dph * p.delta;
+            q.pl = q.pl + dpl * p.delta;                            // :296
+            q.pth = q.pth + dpth * p.delta;
+            ++k;
+            ok = look_ahead<Shape>(p, pins, ray_safe, q, a);
+            at_gate = abs_hi(q.l) >= gate;
+        } while (ok & !at_gate & (k < n));
+        if (at_gate) { near = true; break; }
+        if (k >= n) break;
+    }
+    return k;
 }
 
 // CURVIS_INTEGRATOR_EULER_ADAPTIVE (extension; its oracle is oracle_step_adaptive, same operation order): the explicit

@@ -21,6 +21,8 @@ struct LaunchTuning {
     double guard_rel = 1e-9; // relative state-error budget of a ray with stiffness < 1 (render_f64_fast.cu: guard_eps)
     long long redo_capacity_limit = 0;   // test knob: cap the re-integration list (0 = automatic) to exercise the in-line fallback
     int redo_blocks_per_sm = 2;   // CTAs per SM of the re-integration launch (a few per cent of the frame's rays: fewer, fuller warps)
+    int redo_ahead = 1;      // the re-integration launch runs the step loop in latency form (geodesic_f64.cuh: euler_steps_ahead: the next
+                             // step's shape function and sincos overlap this step's quotients); 0 = the throughput form of the frame kernel (A/B)
     int fast_regs = 0;       // CURVIS_PRECISION_F64_FAST register budget: 96 (5 CTAs per SM) or 128 (4 CTAs); 0 (default) = 96.  4K frames,
                              // 96 against 128: Ellis 36.6 / 37.1 ms, Interstellar 55.6 / 58.2 ms (profiles/r02_time_fast.json)
     int longest_first = 2;   // CURVIS_PRECISION_F64_FAST: rays predicted to be stragglers (near-critical, pole-grazing) are listed by a pre-pass

@@ -101,7 +101,9 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64(const __grid_constant_
 //          correctly-rounded sequence per quotient (kernel_variant 3); same roundings, geodesic_f64.cuh: rhs_lean
 // List mode (p.ray_list != nullptr): the launch re-integrates the rays CURVIS_PRECISION_F64_FAST left in its guard
 // band — ray i of the launch is ray ray_list[i] of the tile, *ray_list_count of them.
-template <class Shape, int INTEG, bool TRACK, bool SHARED>
+// AHEAD: the step loop in latency form (geodesic_f64.cuh: euler_steps_ahead) — list mode, where a few hundred rays leave the
+// launch bound by one ray's dependent chain.  Same arithmetic; more registers (no occupancy to protect).
+template <class Shape, int INTEG, bool TRACK, bool SHARED, bool AHEAD = false>
 __global__ void __launch_bounds__(kBlock) render_rows_f64_lean(const __grid_constant__ FrameParams p) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -165,14 +167,17 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64_lean(const __grid_cons
             const uint32_t n = min(p.window, remaining);
             uint32_t k = 0;
             bool near = false;
+            if (AHEAD) k = euler_steps_ahead<Shape>(p, pins, ray_safe, q, n, gate, near);
+            else {
 #pragma unroll 1
-            do {
-                if (INTEG == 1) rk4_step_lean<Shape>(p, q, ray_safe);
-                else if (INTEG == 2) euler_step_adaptive<Shape, TRACK>(p, q, ray_safe, &diag);
-                else euler_step_lean<Shape, TRACK, SHARED>(p, q, ray_safe, &diag, &pins);
-                ++k;
-                if (abs_hi(q.l) >= gate) { near = true; break; }     // |l| >= R (1 - 2^-20), or NaN
-            } while (k < n);
+                do {
+                    if (INTEG == 1) rk4_step_lean<Shape>(p, q, ray_safe);
+                    else if (INTEG == 2) euler_step_adaptive<Shape, TRACK>(p, q, ray_safe, &diag);
+                    else euler_step_lean<Shape, TRACK, SHARED>(p, q, ray_safe, &diag, &pins);
+                    ++k;
+                    if (abs_hi(q.l) >= gate) { near = true; break; }     // |l| >= R (1 - 2^-20), or NaN
+                } while (k < n);
+            }
             remaining -= k;
             bool done = (remaining == 0);                                       // systems.rs:137
             if (near) {
@@ -209,15 +214,17 @@ static cudaError_t launch_persistent(Kernel kernel, int& blocks_per_sm_auto, con
     return cudaGetLastError();
 }
 
-template <class Shape, int INTEG, bool TRACK, bool SHARED>
+template <class Shape, int INTEG, bool TRACK, bool SHARED, bool AHEAD = false>
 static cudaError_t launch_lean_one(const FrameParams& p, int sm_count, int blocks_per_sm_override, cudaStream_t stream) {
     static int blocks_per_sm_auto = 0;   // per instantiation
-    return launch_persistent(render_rows_f64_lean<Shape, INTEG, TRACK, SHARED>, blocks_per_sm_auto, p, sm_count, blocks_per_sm_override, stream);
+    return launch_persistent(render_rows_f64_lean<Shape, INTEG, TRACK, SHARED, AHEAD>, blocks_per_sm_auto, p, sm_count, blocks_per_sm_override, stream);
 }
 
 template <class Shape>
-static cudaError_t launch_lean(const FrameParams& p, int sm_count, int blocks_per_sm_override, bool shared, cudaStream_t stream) {
+static cudaError_t launch_lean(const FrameParams& p, int sm_count, int blocks_per_sm_override, bool shared, bool ahead, cudaStream_t stream) {
     const bool track = p.records != nullptr;
+    if (ahead && p.ray_list && p.integrator == CURVIS_INTEGRATOR_EULER && !track)
+        return launch_lean_one<Shape, 0, false, true, true>(p, sm_count, blocks_per_sm_override, stream);   // re-integration list: latency form
     if (p.integrator == CURVIS_INTEGRATOR_RK4)
         return launch_lean_one<Shape, 1, false, true>(p, sm_count, blocks_per_sm_override, stream);
     if (p.integrator == CURVIS_INTEGRATOR_EULER_ADAPTIVE)
@@ -237,13 +244,13 @@ static cudaError_t launch_one(const FrameParams& p, int sm_count, int blocks_per
 template <class Shape>
 static cudaError_t launch_variant(const FrameParams& p, const LaunchTuning& t, int sm_count, cudaStream_t stream) {
     if (p.integrator != CURVIS_INTEGRATOR_EULER || p.records || p.ray_list)
-        return launch_lean<Shape>(p, sm_count, t.blocks_per_sm, true, stream);   // extensions, diagnostics, list mode: lean kernel only
+        return launch_lean<Shape>(p, sm_count, t.blocks_per_sm, true, t.redo_ahead != 0, stream);   // extensions, diagnostics, list mode: lean kernel only
     switch (t.kernel_variant) {
     case 0: return launch_one<Shape, TrigCuda, false>(p, sm_count, t.blocks_per_sm, stream);   // round-1 v0
     case 1: return launch_one<Shape, TrigCuda, true>(p, sm_count, t.blocks_per_sm, stream);
     case 2: return launch_one<Shape, TrigFast, true>(p, sm_count, t.blocks_per_sm, stream);
-    case 3: return launch_lean<Shape>(p, sm_count, t.blocks_per_sm, false, stream);           // one full division sequence per quotient
-    default: return launch_lean<Shape>(p, sm_count, t.blocks_per_sm, true, stream);            // default (4): shared reciprocals
+    case 3: return launch_lean<Shape>(p, sm_count, t.blocks_per_sm, false, false, stream);    // one full division sequence per quotient
+    default: return launch_lean<Shape>(p, sm_count, t.blocks_per_sm, true, false, stream);     // default (4): shared reciprocals
     }
 }
 
