@@ -699,7 +699,7 @@ def run_b200(args):
         differing = int((strict_frame.view(-1, 3) != fast_frame.view(-1, 3)).any(dim=1).sum().item())
         strict_mode = {"precision": "CURVIS_PRECISION_F64: one rounding per reference operation (six correctly rounded divisions, "
                                     "one square root, sincos per step)",
-                       "kernel": "render_rows_f64_lean<ShapeEllis, 0, 0, 1> (kernel_variant 4: the six reciprocals of a step from two seeds)",
+                       "kernel": "render_rows_f64_lean<ShapeEllis, 0, 0, 1, 1> (kernel_variant 5: the six reciprocals of a step from two seeds, the next step's shape function and sincos carried across the loop's back edge)",
                        "value": s4["total_steps"] / (min(sms) * 1e-3), "unit": UNIT,
                        "kernel_ms": min(sms), "frac_of_fp64_fma_peak": s4["total_steps"] / (min(sms) * 1e-3) * flop / 1e12 / fp64_peak}
         if args.precision == "f64_fast":

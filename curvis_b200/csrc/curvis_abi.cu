@@ -847,7 +847,7 @@ extern "C" int curvis_measure_fma_peak(curvis_ctx* ctx, double* fp64_tflops, dou
 extern "C" int curvis_ctx_set_option(curvis_ctx* ctx, const char* key, int64_t value) {
     if (!ctx || !key) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "null argument");
     const std::string k(key);
-    if (k == "kernel_variant" && value >= 0 && value <= 4) ctx->tuning.kernel_variant = (int)value;
+    if (k == "kernel_variant" && value >= 0 && value <= 5) ctx->tuning.kernel_variant = (int)value;
     else if (k == "blocks_per_sm" && value >= 0 && value <= 32) ctx->tuning.blocks_per_sm = (int)value;
     else if (k == "window" && value >= 0 && value <= 4096) ctx->tuning.window = (int)value;
     else if (k == "fast_variant" && value >= 0 && value <= 1) ctx->tuning.fast_variant = (int)value;

@@ -8,9 +8,12 @@ namespace curvis {
 
 // Tuning knobs of a context (curvis_ctx_set_option).
 struct LaunchTuning {
-    int kernel_variant = 4;  // 0 plain operators + CUDA sincos (round-1 v0); 1 unguarded IEEE sequences + CUDA sincos;
+    int kernel_variant = 5;  // 0 plain operators + CUDA sincos (round-1 v0); 1 unguarded IEEE sequences + CUDA sincos;
                              // 2 + in-kernel sincos; 3 lean loop: integer-pipe guards, gated escape test;
-                             // 4 (default) the lean loop with the step's six reciprocals built from two seeds
+                             // 4 the lean loop with the step's six reciprocals built from two seeds;
+                             // 5 (default) 4 with the next step's shape function and sincos carried across the loop's back edge
+                             //   (geodesic_f64.cuh: euler_steps_ahead — 117 instructions per Ellis step instead of 131, and a
+                             //   shorter dependent chain); every variant performs the same operations on the same values
     int blocks_per_sm = 0;   // 0 = occupancy maximum
     int window = 0;          // Euler steps between two refill points of a warp; 0 = auto (32; 32..128 in F64_FAST)
     int zero_copy = 1;       // curvis_render_image into a registered host frame: 1 (default) = the kernel stores its pixels

@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64_lean(const __grid_cons
     unsigned long long ray = 0;
     RayDiag diag = {qnan, qnan};
     TrigPins pins;            // three constants of the step's sincos, pinned in registers (trig_f64.cuh)
-    pins.load();
+    pins.load(AHEAD && Shape::kAheadPinHalf);
 
     RayTally tally;
 
@@ -223,7 +223,7 @@ static cudaError_t launch_lean_one(const FrameParams& p, int sm_count, int block
 template <class Shape>
 static cudaError_t launch_lean(const FrameParams& p, int sm_count, int blocks_per_sm_override, bool shared, bool ahead, cudaStream_t stream) {
     const bool track = p.records != nullptr;
-    if (ahead && p.ray_list && p.integrator == CURVIS_INTEGRATOR_EULER && !track)
+    if (ahead && p.integrator == CURVIS_INTEGRATOR_EULER && !track)
         return launch_lean_one<Shape, 0, false, true, true>(p, sm_count, blocks_per_sm_override, stream);   // re-integration list: latency form
     if (p.integrator == CURVIS_INTEGRATOR_RK4)
         return launch_lean_one<Shape, 1, false, true>(p, sm_count, blocks_per_sm_override, stream);
@@ -244,12 +244,13 @@ static cudaError_t launch_one(const FrameParams& p, int sm_count, int blocks_per
 template <class Shape>
 static cudaError_t launch_variant(const FrameParams& p, const LaunchTuning& t, int sm_count, cudaStream_t stream) {
     if (p.integrator != CURVIS_INTEGRATOR_EULER || p.records || p.ray_list)
-        return launch_lean<Shape>(p, sm_count, t.blocks_per_sm, true, t.redo_ahead != 0, stream);   // extensions, diagnostics, list mode: lean kernel only
+        return launch_lean<Shape>(p, sm_count, t.blocks_per_sm, true, p.ray_list && t.redo_ahead != 0, stream);   // extensions, diagnostics, list mode: lean kernel only
     switch (t.kernel_variant) {
     case 0: return launch_one<Shape, TrigCuda, false>(p, sm_count, t.blocks_per_sm, stream);   // round-1 v0
     case 1: return launch_one<Shape, TrigCuda, true>(p, sm_count, t.blocks_per_sm, stream);
     case 2: return launch_one<Shape, TrigFast, true>(p, sm_count, t.blocks_per_sm, stream);
     case 3: return launch_lean<Shape>(p, sm_count, t.blocks_per_sm, false, false, stream);    // one full division sequence per quotient
+    case 5: return launch_lean<Shape>(p, sm_count, t.blocks_per_sm, true, true, stream);      // 4 with the step loop in latency form (A/B)
     default: return launch_lean<Shape>(p, sm_count, t.blocks_per_sm, true, false, stream);     // default (4): shared reciprocals
     }
 }

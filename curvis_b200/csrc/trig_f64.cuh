@@ -68,14 +68,18 @@ __device__ __forceinline__ void sincos_fast(double x, double& s, double& c) {
 // constant-bank operand, so the other must sit in a vector register): the rounding magic and the two leading coefficients.
 // Left to itself ptxas re-loads them (LDC) every step — six issue slots of the operation-for-operation kernel's step; read once
 // per kernel through a plain global load they stay in registers (the same trick as fast_f64.cuh: kPinned).
-static __device__ double kTrigPinned[3] = {6755399441055744.0, 1.5912475864762696e-10, -1.1379094621237813e-11};   // magic, kSinPoly[5], kCosPoly[5]
+// `half` = 0.5: cos r's fma(u, -0.5, 1.0) and the square root's fma(e, 0.375, 0.5) each hold two constants; pinned (an option:
+// two more registers), the second one costs no instruction (ptxas otherwise builds it with two moves per use).
+static __device__ double kTrigPinned[4] = {6755399441055744.0, 1.5912475864762696e-10, -1.1379094621237813e-11, 0.5};   // magic, kSinPoly[5], kCosPoly[5], 1/2
 
 struct TrigPins {
-    double magic, sin5, cos5;
-    __device__ __forceinline__ void load() {
+    double magic, sin5, cos5, half;
+    __device__ __forceinline__ void load(bool pin_half = false) {
         asm volatile("ld.global.f64 %0, [%1];" : "=d"(magic) : "l"(kTrigPinned));
         asm volatile("ld.global.f64 %0, [%1];" : "=d"(sin5) : "l"(kTrigPinned + 1));
         asm volatile("ld.global.f64 %0, [%1];" : "=d"(cos5) : "l"(kTrigPinned + 2));
+        half = 0.5;                                                  // (a literal to the compiler unless pinned)
+        if (pin_half) asm volatile("ld.global.f64 %0, [%1];" : "=d"(half) : "l"(kTrigPinned + 3));
     }
 };
 
@@ -99,7 +103,7 @@ __device__ __forceinline__ void sincos_fast_pinned(const TrigPins& tp, double x,
     sp = fma(u, sp, kSinPoly[0]);
     cp = fma(u, cp, kCosPoly[0]);
     const double sr = fma(r * u, sp, r);
-    const double cr = fma(u * u, cp, fma(u, -0.5, 1.0));
+    const double cr = fma(u * u, cp, fma(u, -tp.half, 1.0));
     const double a = (k & 1) ? cr : sr;
     const double b = (k & 1) ? sr : cr;
     s = __hiloint2double(__double2hiint(a) ^ ((k & 2) << 30), __double2loint(a));

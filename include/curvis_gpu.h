@@ -372,8 +372,11 @@ int curvis_measure_fma_peak(curvis_ctx* ctx, double* fp64_tflops, double* fp32_t
 /* Tuning knobs of a context; results never depend on them (tests/test_gpu_parity.py).
  *   "kernel_variant": 0 plain `/`, sqrt and CUDA sincos; 1 unguarded IEEE sequences + CUDA
  *                     sincos; 2 unguarded IEEE sequences + in-kernel sincos; 3 the same
- *                     arithmetic in the lean loop (integer-pipe guards, gated escape test); 4 (default) the lean loop
- *                     with the step's six reciprocals built from two seeds and one correction step each
+ *                     arithmetic in the lean loop (integer-pipe guards, gated escape test); 4 the lean loop
+ *                     with the step's six reciprocals built from two seeds and one correction step each; 5 (default) 4 with
+ *                     the next step's shape function and sincos carried across the loop's back edge (fewer instructions, a
+ *                     shorter dependent chain; the form the re-integration launch of CURVIS_PRECISION_F64_FAST runs too)
+ *   "redo_ahead":     1 (default) the re-integration launch runs that latency form; 0 the form of variant 4 (A/B)
  *   "guard":          CURVIS_PRECISION_F64_FAST: 1 (default) guard band + re-integration of the rays with stiffness < 1;
  *                     2 kicked rays (stiffness >= 1) re-integrated too; 0 the raw regrouped kernel (A/B)
  *   "guard_rel_e15":  the guard's relative budget in units of 1e-15 (default 1000000 = 1e-9)

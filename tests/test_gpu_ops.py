@@ -108,7 +108,8 @@ def test_kernel_variants_render_identical_frames(gpu_ctx, oracle):
                                          threads=8)
     ctx = cv.Context([0])
     sysm = cv.RelativisticSystem(cv.EllisMetric(1.0), cv.SphericalImage(bp), cv.SphericalImage(bn), cv.Camera(*cam_args), context=ctx)
-    for variant, blocks, window in [(0, 0, 16), (1, 0, 16), (2, 0, 16), (3, 0, 16), (3, 3, 7), (3, 1, 64), (2, 2, 1)]:
+    for variant, blocks, window in [(0, 0, 16), (1, 0, 16), (2, 0, 16), (3, 0, 16), (3, 3, 7), (3, 1, 64), (2, 2, 1),
+                                    (4, 0, 16), (4, 2, 5), (5, 0, 16), (5, 3, 7), (5, 1, 1), (5, 0, 0)]:
         ctx.set_option("kernel_variant", variant)
         ctx.set_option("blocks_per_sm", blocks)
         ctx.set_option("window", window)

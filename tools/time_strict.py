@@ -13,7 +13,7 @@ cam = cv.Camera(scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD, scenes.D
 for name, metric, sim in (("ellis", cv.EllisMetric(1.0), (40000, 100.0, 0.05)), ("interstellar", cv.InterstellarMetric(0.1, 1e-4, 1.0), (40000, 100.0, 0.05)),
                           ("interstellar c3", cv.InterstellarMetric(0.1, 1e-4, 1.0), (2000, 45.0, 0.05))):
     system = cv.RelativisticSystem(metric, cv.SphericalImage(bp), cv.SphericalImage(bn), cam, context=ctx)
-    for variant in (3, 4):
+    for variant in (4, 5):
         ctx.set_option("kernel_variant", variant)
         ms = [system.render_rows_device(*sim, 0, H, frame.data_ptr(), stream.cuda_stream, want_stats=True, precision=_abi.PRECISION_F64)["kernel_ms"] for _ in range(4)]
         print(name, "variant", variant, [round(m, 2) for m in ms], flush=True)
