@@ -1,5 +1,5 @@
 """Round-2 ncu target (GPU box, under ncu): one 4K default frame per kernel after one warm-up frame each —
-  Ellis F64_FAST (main + re-integration launch), Interstellar F64_FAST (main + re-integration), Ellis F64 (kernel_variant 4),
+  Ellis F64_FAST (main + re-integration launch), Interstellar F64_FAST (main + re-integration), Ellis F64 (kernel_variant 5, the default),
   Ellis chart-free coordinates.  6 warm-up launches, then the same 6 launches to capture (ncu -s 6 -c 6)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
