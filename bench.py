@@ -254,6 +254,26 @@ def strong_scaling(args, cv, system, sim, PREC, ctx, rank, n, local, dev, stream
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             return float(ms.item())
 
+        def timeline(render, iters=8):
+            """Where a frame's time goes on each rank: `busy` = the rank's own launches (pre-pass + render + re-integration
+            + peer stores), `wait` = from its last kernel to the end of the all-reduce (the slowest rank's surplus + the
+            collective), per iteration, CUDA events on the launching stream; all ranks' means."""
+            ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(iters)]
+            for _ in range(2):
+                render(); dist.all_reduce(token)
+            torch.cuda.synchronize()
+            dist.barrier()
+            for e in ev:
+                e[0].record(); render(); e[1].record(); dist.all_reduce(token); e[2].record()
+            torch.cuda.synchronize()
+            busy = [e[0].elapsed_time(e[1]) for e in ev]
+            wait = [e[1].elapsed_time(e[2]) for e in ev]
+            mine_t = torch.tensor([sum(busy) / iters, max(busy), min(busy), sum(wait) / iters], dtype=torch.float64, device=dev)
+            allr = [torch.zeros(4, dtype=torch.float64, device=dev) for _ in range(n)]
+            dist.all_gather(allr, mine_t)
+            return {"rank_busy_ms_mean": [round(float(a[0]), 3) for a in allr], "rank_busy_ms_max": [round(float(a[1]), 3) for a in allr],
+                    "rank_busy_ms_min": [round(float(a[2]), 3) for a in allr], "rank_wait_ms_mean": [round(float(a[3]), 3) for a in allr]}
+
         st = system.render_rows_device(*sim, 0, Hs, whole.data_ptr(), stream.cuda_stream, want_stats=True, precision=PREC)
         steps = int(st["total_steps"])
         kernel_single_ms = st["kernel_ms"]
@@ -264,8 +284,10 @@ def strong_scaling(args, cv, system, sim, PREC, ctx, rank, n, local, dev, stream
         torch.cuda.synchronize()
         bad_contig = (gathered.view(-1, 3) != whole.view(-1, 3)).any(dim=1).sum().to(torch.int64)
         dist.all_reduce(bad_contig)
+        tl = timeline(lambda: system.render_frames_peers([cam], *sim, r0, r1, [b.ptr for b in bufs], stream.cuda_stream, row_stride=stride, precision=PREC))
         ctx.set_option("guard", 0)          # the regrouped kernel alone: what the guard band's second launch costs at this tile size
         t_fused_raw = timed(fused)
+        tl_raw = timeline(lambda: system.render_frames_peers([cam], *sim, r0, r1, [b.ptr for b in bufs], stream.cuda_stream, row_stride=stride, precision=PREC))
         ctx.set_option("guard", 1)
         # this rank's own kernel inside the split frame (the slowest rank bounds the frame)
         kst = system.render_frames_peers([cam], *sim, r0, r1, [b.ptr for b in bufs], stream.cuda_stream, row_stride=stride, precision=PREC, want_stats=True)
@@ -291,9 +313,11 @@ def strong_scaling(args, cv, system, sim, PREC, ctx, rank, n, local, dev, stream
                                   "differing_pixels_contiguous_tiles": int(bad_contig.item()),
                                   "ms_per_frame_without_guard_band": t_fused_raw, "speedup_without_guard_band": t_single / t_fused_raw,
                                   "ideal_ms": t_single / n,
-                                  "limiter": "fixed costs that do not shrink with the tile: ms_per_frame - rank_kernel_ms_max = the all-reduce "
-                                             "barrier; ms_per_frame - ms_per_frame_without_guard_band = the guard band's re-integration launch "
-                                             "(one strict ray's latency, ~0.6 ms); the rest of rank_kernel_ms_max - ideal_ms = the persistent "
+                                  "timeline": tl, "timeline_without_guard_band": tl_raw,
+                                  "limiter": "fixed costs that do not shrink with the tile: a frame takes max over ranks of `timeline.rank_busy_ms` "
+                                             "(that rank's launches; run-to-run spread in _min/_max: which warp a 10^4-step ray shares its scheduler with) "
+                                             "+ the all-reduce (`rank_wait_ms` of the slowest rank); ms_per_frame - ms_per_frame_without_guard_band = the guard "
+                                             "band's re-integration launch (one strict ray's latency, ~0.5 ms); the rest of busy - ideal_ms = the persistent "
                                              "kernel's drain tail (one ray's latency, ~0.4 ms) + row imbalance"},
             "nccl_all_gather": {"ms_per_frame": t_nccl, "speedup": t_single / t_nccl, "ray_steps_per_s": steps / (t_nccl * 1e-3),
                                 "gather_bytes": fbytes},
