@@ -37,6 +37,7 @@ sys.path.insert(0, ROOT)
 
 W4K, H4K = 3840, 2160
 BG_W, BG_H = 8192, 4096
+BLOCK_WIDTH = 64          # --tiles blocks: pixels of a row per block (curvis_render_frames_peers_blocks)
 FLOP_PER_STEP = {"ellis": 33, "interstellar": 43}   # SURVEY.md 8a canonical count after CSE
 METRIC_NAME = "ray_steps_per_sec"
 UNIT = "ray-steps/s"
@@ -55,6 +56,9 @@ def parse():
                     help="N > 1: peers (default) = the render kernel stores every pixel into the complete frames of all ranks over "
                          "NVLink (fused render + all-gather, curvis_render_frames_peers) and a 4-byte all-reduce is the step barrier; "
                          "nccl = tiles rendered locally, then one coalesced NCCL all-gather per step")
+    ap.add_argument("--tiles", default="rows", choices=["blocks", "rows"],
+                    help="N > 1, fused gather: what is interleaved over the ranks — whole rows (default) or blocks of 64 pixels of a "
+                         "row (every rank owns an N-th of every row; measured 2 %% slower at N = 8: profiles/r02_bench_n8_block_tiles.json)")
     ap.add_argument("--precision", default="f64_fast", choices=["f64_fast", "f64"],
                     help="f64_fast (default): fp64, right-hand side regrouped around one reciprocal per step "
                          "(CURVIS_PRECISION_F64_FAST); f64: one rounding per reference operation (CURVIS_PRECISION_F64)")
@@ -74,7 +78,9 @@ def workload_config(args, n):
                                   "the frame's integers equal CURVIS_PRECISION_F64's (`parity_check` compares with the CPU oracle)",
                       "f64": "CURVIS_PRECISION_F64: fp64, one rounding per reference operation"}[args.precision],
         "parallelism": "single GPU" if n == 1 else (
-            f"{n} frames/step (camera path), rows of each frame interleaved over {n} ranks (rank g: rows g, g+{n}, ...): one batched launch per rank whose epilogue stores every pixel into "
+            f"{n} frames/step (camera path), " + (f"{BLOCK_WIDTH}-pixel blocks of the rows of each frame interleaved over {n} ranks (rank g: blocks g, g+{n}, ... in row-major order — an {n}-th of every row)"
+                                                   if args.tiles == "blocks" else f"rows of each frame interleaved over {n} ranks (rank g: rows g, g+{n}, ...)") +
+            ": one batched launch per rank whose epilogue stores every pixel into "
             f"the complete frames of all {n} ranks over NVLink peer memory (fused render + all-gather), then a 4-byte NCCL all-reduce as the step barrier"
             if args.gather == "peers" else
             f"{n} frames/step (camera path), each row-tiled over {n} ranks: one batched launch per rank + the {n} NCCL all-gathers of row tiles "
@@ -228,6 +234,17 @@ def strong_scaling(args, cv, system, sim, PREC, ctx, rank, n, local, dev, stream
             system.render_frames_peers([cam], *sim, r0, r1, [b.ptr for b in bufs], stream.cuda_stream, row_stride=stride, precision=PREC)
             dist.all_reduce(token)
 
+        from curvis_b200.distributed import interleaved_blocks
+        b0, b1, bstride, bw = interleaved_blocks(Hs, Ws, rank, n, BLOCK_WIDTH)
+
+        def render_blocks(**kw):
+            return system.render_frames_peers([cam], *sim, b0, b1, [b.ptr for b in bufs], stream.cuda_stream, row_stride=bstride, block_width=bw,
+                                              precision=PREC, **kw)
+
+        def fused_blocks():         # blocks of BLOCK_WIDTH pixels of a row interleaved over the ranks: every row is shared by all
+            render_blocks()
+            dist.all_reduce(token)
+
         def fused_contiguous():     # the same fused launch on CONTIGUOUS row tiles (what the NCCL form renders)
             system.render_frames_peers([cam], *sim, rank * rows, (rank + 1) * rows, [b.ptr for b in bufs], stream.cuda_stream, row_stride=1, precision=PREC)
             dist.all_reduce(token)
@@ -280,6 +297,16 @@ def strong_scaling(args, cv, system, sim, PREC, ctx, rank, n, local, dev, stream
         t_single, t_fused, t_nccl = timed(single), timed(fused), timed(nccl)
         gathered.zero_()
         dist.barrier()
+        t_blocks = timed(fused_blocks)
+        tl_blocks = timeline(render_blocks)
+        torch.cuda.synchronize()
+        bad_blocks = (gathered.view(-1, 3) != whole.view(-1, 3)).any(dim=1).sum().to(torch.int64)
+        dist.all_reduce(bad_blocks)
+        ctx.set_option("guard", 0)
+        t_blocks_raw = timed(fused_blocks)
+        ctx.set_option("guard", 1)
+        gathered.zero_()
+        dist.barrier()
         t_fused_contig = timed(fused_contiguous)
         torch.cuda.synchronize()
         bad_contig = (gathered.view(-1, 3) != whole.view(-1, 3)).any(dim=1).sum().to(torch.int64)
@@ -319,6 +346,11 @@ def strong_scaling(args, cv, system, sim, PREC, ctx, rank, n, local, dev, stream
                                              "+ the all-reduce (`rank_wait_ms` of the slowest rank); ms_per_frame - ms_per_frame_without_guard_band = the guard "
                                              "band's re-integration launch (one strict ray's latency, ~0.5 ms); the rest of busy - ideal_ms = the persistent "
                                              "kernel's drain tail (one ray's latency, ~0.4 ms) + row imbalance"},
+            "fused_peer_stores_blocks": {"what": "the fused form with blocks of %d pixels of a row interleaved over the ranks instead of whole rows "
+                                                 "(curvis_render_frames_peers_blocks): every rank owns an N-th of every row" % bw,
+                                         "ms_per_frame": t_blocks, "speedup": t_single / t_blocks, "ray_steps_per_s": steps / (t_blocks * 1e-3),
+                                         "ms_per_frame_without_guard_band": t_blocks_raw, "speedup_without_guard_band": t_single / t_blocks_raw,
+                                         "differing_pixels_vs_one_rank": int(bad_blocks.item()), "timeline": tl_blocks},
             "nccl_all_gather": {"ms_per_frame": t_nccl, "speedup": t_single / t_nccl, "ray_steps_per_s": steps / (t_nccl * 1e-3),
                                 "gather_bytes": fbytes},
             "differing_pixels_vs_one_rank": {"fused": int(bad[0].item()), "nccl": int(bad[1].item()), "pixels_checked": n * Ws * Hs},
@@ -369,7 +401,7 @@ def run_b200(args):
 
     import curvis_b200 as cv
     from curvis_b200 import _abi, scenes
-    from curvis_b200.distributed import interleaved_rows
+    from curvis_b200.distributed import interleaved_blocks, interleaved_rows
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -455,9 +487,14 @@ def run_b200(args):
         cur = peer_sets[k & 1]
         # interleaved rows: rank g renders rows g, g+n, g+2n, ... of every frame — the same mix of short (sky) and
         # long (throat-grazing) rays on every rank; a contiguous tile of central rows holds ~3 % more steps than the mean
-        r0, r1, stride = interleaved_rows(Ht, rank, n)
+        # (--tiles blocks: the same with 64-pixel blocks of a row instead of rows — the two or three rows of a frame that hold
+        # its 10^4-step rays are then shared by all ranks)
+        if args.tiles == "blocks":
+            r0, r1, stride, bw = interleaved_blocks(Ht, Wd, rank, n, BLOCK_WIDTH)
+        else:
+            (r0, r1, stride), bw = interleaved_rows(Ht, rank, n), 0
         st = system.render_frames_peers(cameras, *sim, r0, r1, [b.ptr for b in cur], stream.cuda_stream,
-                                        want_stats=want_stats, row_stride=stride, precision=PREC)
+                                        want_stats=want_stats, row_stride=stride, block_width=bw, precision=PREC)
         # this rank's read-back of step k-1 (which read set (k-1)&1) must have finished before the barrier of step k lets
         # anybody launch step k+1 into that set
         stream.wait_event(copied[0])

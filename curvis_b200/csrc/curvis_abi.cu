@@ -259,6 +259,8 @@ static void fill_params(const curvis_ctx* ctx, const DeviceState& d, const curvi
         p.gate_hi = (sim->max_radius >= 0.0) ? (uint32_t)((bits >> 32) & 0x7fffffffu) : 0u;
     }
     p.row_begin = row_begin; p.row_end = row_end; p.row_stride = 1;
+    p.frame_width = cam->resolution_width; p.blocks_per_row = 1;
+    p.inv_frame_width = 1.0 / (double)cam->resolution_width; p.inv_blocks_per_row = 1.0;
     p.inv_width = 1.0 / (double)cam->resolution_width;
     p.inv_tile_rays = 1.0 / ((double)(row_end - row_begin) * (double)cam->resolution_width);
     p.f_rho = (float)metric->rho; p.f_rho2 = (float)(metric->rho * metric->rho);
@@ -559,12 +561,23 @@ static int render_frames_impl(curvis_ctx* ctx, const curvis_metric* metric,
                               const curvis_camera* cameras, uint32_t n_frames, const curvis_sim* sim,
                               uint32_t row_begin, uint32_t row_end,
                               void* d_out_rgb8_tiles, void* const* d_peer_frames, uint32_t n_peers, uint32_t row_stride, void* stream,
-                              curvis_stats* stats) {
+                              curvis_stats* stats, uint32_t block_width = 0) {
+    // block_width != 0 (curvis_render_frames_peers_blocks): row_begin / row_end / row_stride count BLOCKS of block_width pixels
+    // of a frame row, numbered row-major over the frame (frame_params.h)
     const auto t0 = std::chrono::steady_clock::now();
     if (!ctx) return fail(nullptr, CURVIS_ERR_INVALID_ARGUMENT, "null context");
     if (!cameras || n_frames == 0) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "no cameras");
+    uint32_t blocks_per_row = 1;
+    if (block_width) {
+        const uint32_t W0 = cameras[0].resolution_width;
+        if (W0 == 0 || W0 % block_width) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "block_width must divide the frame width");
+        blocks_per_row = W0 / block_width;
+        if (row_begin > row_end || (uint64_t)row_end > (uint64_t)cameras[0].resolution_height * blocks_per_row)
+            return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "block range outside the frame");
+    }
+    const uint32_t tile_width = block_width ? block_width : cameras[0].resolution_width;
     for (uint32_t f = 0; f < n_frames; ++f) {
-        int rc = validate_frame(ctx, metric, &cameras[f], sim, row_begin, row_end);
+        int rc = block_width ? validate_frame(ctx, metric, &cameras[f], sim, 0, 0) : validate_frame(ctx, metric, &cameras[f], sim, row_begin, row_end);
         if (rc != CURVIS_OK) return rc;
         if (cameras[f].resolution_width != cameras[0].resolution_width || cameras[f].resolution_height != cameras[0].resolution_height)
             return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "all frames of a batch must share one resolution");
@@ -589,7 +602,7 @@ static int render_frames_impl(curvis_ctx* ctx, const curvis_metric* metric,
     }
     {
         const uint32_t rows_launch = (row_end - row_begin + row_stride - 1) / row_stride;
-        int rrc = ensure_redo(ctx, d, sim, (size_t)rows_launch * cameras[0].resolution_width * n_frames);
+        int rrc = ensure_redo(ctx, d, sim, (size_t)rows_launch * tile_width * n_frames);
         if (rrc != CURVIS_OK) return rrc;
         rrc = ensure_inverse_table(ctx, d, metric, sim, st);
         if (rrc != CURVIS_OK) return rrc;
@@ -607,7 +620,9 @@ static int render_frames_impl(curvis_ctx* ctx, const curvis_metric* metric,
     const uint32_t n_rows = (row_end - row_begin + row_stride - 1) / row_stride;
     p.row_stride = row_stride;
     p.row_end = row_begin + n_rows;
-    p.inv_tile_rays = 1.0 / ((double)n_rows * (double)cameras[0].resolution_width);
+    p.width = tile_width; p.inv_width = 1.0 / (double)tile_width;
+    p.blocks_per_row = blocks_per_row; p.inv_blocks_per_row = 1.0 / (double)blocks_per_row;
+    p.inv_tile_rays = 1.0 / ((double)n_rows * (double)tile_width);
     CURVIS_CUDA(ctx, cudaMemsetAsync(d.d_counters, 0, sizeof(DeviceCounters), st));
     CURVIS_CUDA(ctx, cudaEventRecord(d.ev_begin, st));
     if (row_end > row_begin) CURVIS_CUDA(ctx, launch_render(p, metric, sim, ctx->tuning, d.sm_count, st));
@@ -616,7 +631,7 @@ static int render_frames_impl(curvis_ctx* ctx, const curvis_metric* metric,
         CURVIS_CUDA(ctx, cudaMemcpyAsync(d.h_counters, d.d_counters, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, st));
         CURVIS_CUDA(ctx, cudaStreamSynchronize(st));
         std::memset(stats, 0, sizeof *stats);
-        add_counters(*d.h_counters, (uint64_t)n_rows * cameras[0].resolution_width * n_frames, stats);
+        add_counters(*d.h_counters, (uint64_t)n_rows * tile_width * n_frames, stats);
         float ms = 0.f;
         CURVIS_CUDA(ctx, cudaEventElapsedTime(&ms, d.ev_begin, d.ev_end));
         stats->kernel_ms = ms;
@@ -638,6 +653,14 @@ extern "C" int curvis_render_frames_peers(curvis_ctx* ctx, const curvis_metric* 
     if (n_peers == 0) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "curvis_render_frames_peers: no peer buffers");
     if (row_stride == 0) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "curvis_render_frames_peers: row_stride must be at least 1");
     return render_frames_impl(ctx, metric, cameras, n_frames, sim, row_begin, row_end, nullptr, d_frames, n_peers, row_stride, stream, stats);
+}
+
+extern "C" int curvis_render_frames_peers_blocks(curvis_ctx* ctx, const curvis_metric* metric, const curvis_camera* cameras, uint32_t n_frames,
+                                                 const curvis_sim* sim, uint32_t block_begin, uint32_t block_end, uint32_t block_stride,
+                                                 uint32_t block_width, void* const* d_frames, uint32_t n_peers, void* stream, curvis_stats* stats) {
+    if (n_peers == 0) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "curvis_render_frames_peers_blocks: no peer buffers");
+    if (block_stride == 0 || block_width == 0) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "curvis_render_frames_peers_blocks: block_stride and block_width must be at least 1");
+    return render_frames_impl(ctx, metric, cameras, n_frames, sim, block_begin, block_end, nullptr, d_frames, n_peers, block_stride, stream, stats, block_width);
 }
 
 extern "C" int curvis_peer_buffer_create(curvis_ctx* ctx, size_t bytes, void** d_ptr, uint8_t ipc_handle[CURVIS_IPC_HANDLE_BYTES]) {

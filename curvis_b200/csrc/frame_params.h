@@ -97,6 +97,12 @@ struct FrameParams {
     // row_stride > 1 (peers launches only): the launch renders rows row_begin + k*row_stride, k in [0, row_end - row_begin)
     // — interleaved row ownership, which gives every rank statistically the same work
     uint32_t n_peers, row_stride;
+    // Block tiles (curvis_render_frames_peers_blocks): the "rows" above are BLOCKS of `width` consecutive pixels of a frame row,
+    // numbered row-major over the frame (blocks_per_row = frame_width / width of them per row): interleaving blocks instead of
+    // rows splits EVERY row over the ranks — the 10^4-step rays of a frame sit in two or three rows.  Whole rows: width =
+    // frame_width, blocks_per_row = 1.  frame_width and height are what the camera and the output addresses see.
+    uint32_t frame_width, blocks_per_row;
+    double inv_frame_width, inv_blocks_per_row;
     // curvis_sim extensions (all 0 in parity mode): curvis_frame, curvis_coordinates, adaptive-step tolerance
     uint32_t frame, coordinates;
     double step_tolerance;

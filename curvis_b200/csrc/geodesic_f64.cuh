@@ -227,6 +227,18 @@ __device__ __forceinline__ void split_ray_index(const FrameParams& p, unsigned l
     px = (uint32_t)(r - (unsigned long long)k * p.width);
 }
 
+// Row k of the tile, position i in it -> the pixel (px, py) of the frame.  Whole rows: (i, row_begin + k row_stride); block
+// tiles (frame_params.h): block v = row_begin + k row_stride is block v % blocks_per_row of frame row v / blocks_per_row.
+__device__ __forceinline__ void tile_pixel(const FrameParams& p, uint32_t k, uint32_t i, uint32_t& px, uint32_t& py) {
+    const uint32_t v = p.row_begin + k * p.row_stride;
+    if (p.blocks_per_row <= 1u) { px = i; py = v; return; }
+    uint32_t y = (uint32_t)((double)v * p.inv_blocks_per_row);
+    if (y * p.blocks_per_row > v) --y;
+    else if ((y + 1u) * p.blocks_per_row <= v) ++y;
+    py = y;
+    px = (v - y * p.blocks_per_row) * p.width + i;
+}
+
 // The camera of frame `frame` of a launch (batched launches hold one per frame).
 __device__ __forceinline__ const CameraBlock& camera_of_frame(const FrameParams& p, unsigned long long frame) {
     return (p.ray_dirs || p.n_frames <= 1) ? p.cam : p.cameras[frame];
@@ -249,9 +261,10 @@ __device__ __forceinline__ bool ray_predicted_long(const FrameParams& p, unsigne
         unsigned long long f; uint32_t px, k;
         split_ray_index(p, idx, tile_rays, f, px, k);
         const CameraBlock& cam = camera_of_frame(p, f);
-        const uint32_t py = p.row_begin + k * p.row_stride;
+        uint32_t py;
+        tile_pixel(p, k, px, px, py);
         const double vx = cam.focal_length;
-        const double vy = -cam.sensor_width * (((double)px * p.inv_width) - 0.5);
+        const double vy = -cam.sensor_width * (((double)px * p.inv_frame_width) - 0.5);
         const double vz = cam.sensor_height * (0.5 - ((double)py / (double)p.height));
         dx = (cam.cam_to_world[0] * vx + cam.cam_to_world[1] * vy) + cam.cam_to_world[2] * vz;
         dy = (cam.cam_to_world[3] * vx + cam.cam_to_world[4] * vy) + cam.cam_to_world[5] * vz;
@@ -272,7 +285,9 @@ __device__ __forceinline__ void new_photon_for_ray(const FrameParams& p, unsigne
     }
     unsigned long long f; uint32_t px, k;
     split_ray_index(p, idx, tile_rays, f, px, k);
-    new_photon_from_camera(camera_of_frame(p, f), p.width, p.height, px, p.row_begin + k * p.row_stride, q);
+    uint32_t py;
+    tile_pixel(p, k, px, px, py);
+    new_photon_from_camera(camera_of_frame(p, f), p.frame_width, p.height, px, py, q);
 }
 
 // ---------------------------------------------------------------- one explicit Euler step
@@ -742,7 +757,9 @@ __device__ __forceinline__ bool finish_ray(const FrameParams& p, const Ray& q, i
             const unsigned long long tile_rays = (unsigned long long)(p.row_end - p.row_begin) * p.width;
             unsigned long long f; uint32_t px, k;
             split_ray_index(p, ray, tile_rays, f, px, k);
-            const size_t off = (((size_t)f * p.height + p.row_begin + (size_t)k * p.row_stride) * p.width + px) * 3;
+            uint32_t py;
+            tile_pixel(p, k, px, px, py);
+            const size_t off = (((size_t)f * p.height + py) * p.frame_width + px) * 3;
             for (uint32_t i = 0; i < p.n_peers; ++i) {
                 uint8_t* o = p.out_peers[i] + off;
                 o[0] = (uint8_t)(rgba & 0xffu);

@@ -55,13 +55,13 @@ __device__ __forceinline__ void new_photon_cart_for_ray(const FrameParams& p, un
     double dx, dy, dz;
     if (p.ray_dirs) {
         new_photon_cart(p.cam, p.ray_dirs[3 * idx], p.ray_dirs[3 * idx + 1], p.ray_dirs[3 * idx + 2], q);
-    } else if (p.n_frames <= 1) {
-        outward_vector_on_world_space(p.cam, p.width, p.height, (uint32_t)(idx % p.width), p.row_begin + (uint32_t)(idx / p.width) * p.row_stride, dx, dy, dz);
-        new_photon_cart(p.cam, dx, dy, dz, q);
     } else {
-        const unsigned long long f = idx / tile_rays, r = idx % tile_rays;
-        outward_vector_on_world_space(p.cameras[f], p.width, p.height, (uint32_t)(r % p.width), p.row_begin + (uint32_t)(r / p.width) * p.row_stride, dx, dy, dz);
-        new_photon_cart(p.cameras[f], dx, dy, dz, q);
+        unsigned long long f; uint32_t px, py, k;
+        split_ray_index(p, idx, tile_rays, f, px, k);
+        tile_pixel(p, k, px, px, py);
+        const CameraBlock& cam = camera_of_frame(p, f);
+        outward_vector_on_world_space(cam, p.frame_width, p.height, px, py, dx, dy, dz);
+        new_photon_cart(cam, dx, dy, dz, q);
     }
 }
 

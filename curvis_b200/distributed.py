@@ -28,6 +28,24 @@ def interleaved_rows(height: int, rank: int, world: int) -> Tuple[int, int, int]
     return min(rank, height), height, world
 
 
+def interleaved_blocks(height: int, width: int, rank: int, world: int, block_width: int = 64) -> Tuple[int, int, int, int]:
+    """(block_begin, block_end, block_stride, block_width) of rank ``rank`` when blocks of ``block_width`` pixels of a row
+    are interleaved over the ranks — the arguments of curvis_render_frames_peers_blocks.  Every rank owns a ``world``-th of
+    EVERY row, so the two or three rows of a frame that hold its 10^4-step rays are shared by all ranks.  A block width
+    that does not divide the frame width falls back to whole rows (block_width = width)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("rank/world out of range")
+    if block_width <= 0 or width % block_width:
+        block_width = width
+    n_blocks = height * (width // block_width)
+    return min(rank, n_blocks), n_blocks, world, block_width
+
+
+def block_owner(row: int, col: int, width: int, world: int, block_width: int) -> int:
+    """The rank that renders pixel (col, row) under interleaved_blocks."""
+    return (row * (width // block_width) + col // block_width) % world
+
+
 def frame_offset(frame: int, row: int, height: int, width: int) -> int:
     """Byte offset of row ``row`` of frame ``frame`` in a buffer of complete RGB8 frames (frame-major) — where
     curvis_render_frames_peers stores it in every peer's buffer (csrc/geodesic_f64.cuh: finish_ray)."""

@@ -235,19 +235,28 @@ class RelativisticSystem:
         return None
 
     def render_frames_peers(self, cameras, max_iterations: int, max_radius: float, delta: float, row_begin: int, row_end: int,
-                            frame_ptrs, stream_ptr: int = 0, want_stats: bool = False, row_stride: int = 1, **options):
+                            frame_ptrs, stream_ptr: int = 0, want_stats: bool = False, row_stride: int = 1,
+                            block_width: int = 0, **options):
         """Fused render + all-gather (curvis_render_frames_peers): rows row_begin, row_begin + row_stride, ...
         (< row_end) of one frame per camera in ONE launch, every pixel stored into the complete-frames buffer of every peer
-        (``frame_ptrs``: device pointers — this rank's PeerBuffer and the opened ones of its peers)."""
+        (``frame_ptrs``: device pointers — this rank's PeerBuffer and the opened ones of its peers).  ``block_width`` > 0
+        (curvis_render_frames_peers_blocks): the three row arguments count blocks of that many pixels of a row, numbered
+        row-major over the frame (distributed.interleaved_blocks)."""
         arr = (_abi.CurvisCamera * len(cameras))(*[c.as_c() if hasattr(c, "as_c") else c for c in cameras])
         ptrs = (C.c_void_p * len(frame_ptrs))(*[C.c_void_p(int(x)) for x in frame_ptrs])
         sim = self._sim(max_iterations, max_radius, delta, **options)
         stats = _abi.CurvisStats() if want_stats else None
         m = self.metric.as_c()
-        _abi.check(self._lib.curvis_render_frames_peers(
-            self.context.ptr, C.byref(m), arr, len(cameras), C.byref(sim), int(row_begin), int(row_end), int(row_stride),
-            ptrs, len(frame_ptrs), C.c_void_p(stream_ptr) if stream_ptr else None, C.byref(stats) if stats is not None else None),
-            self.context.ptr)
+        if block_width:
+            _abi.check(self._lib.curvis_render_frames_peers_blocks(
+                self.context.ptr, C.byref(m), arr, len(cameras), C.byref(sim), int(row_begin), int(row_end), int(row_stride), int(block_width),
+                ptrs, len(frame_ptrs), C.c_void_p(stream_ptr) if stream_ptr else None, C.byref(stats) if stats is not None else None),
+                self.context.ptr)
+        else:
+            _abi.check(self._lib.curvis_render_frames_peers(
+                self.context.ptr, C.byref(m), arr, len(cameras), C.byref(sim), int(row_begin), int(row_end), int(row_stride),
+                ptrs, len(frame_ptrs), C.c_void_p(stream_ptr) if stream_ptr else None, C.byref(stats) if stats is not None else None),
+                self.context.ptr)
         if stats is not None:
             self.last_stats = stats.as_dict()
             return self.last_stats

@@ -347,7 +347,7 @@ def test_fused_render_and_gather_into_peer_buffers(gpu_ctx):
     frames into both buffers.  The result equals curvis_render_image of each frame, for every precision."""
     import torch
     import curvis_b200 as cv
-    from curvis_b200 import _abi, scenes
+    from curvis_b200 import _abi, distributed, scenes
     bp, bn = scenes.decodable_background(1024, 512), scenes.decodable_background(1024, 512, True)
     W, H, sim = 160, 90, (300, 12.0, 0.1)
     cams = [cv.Camera((0.0, 5.0 + 0.3 * f, 1.4, 0.2 * f), scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP, 15.0, 43.0, W, H) for f in range(2)]
@@ -375,6 +375,36 @@ def test_fused_render_and_gather_into_peer_buffers(gpu_ctx):
                 for b in bufs:
                     got = b.as_tensor().cpu().numpy().reshape(2, H, W, 3)
                     assert (got[0] == want[0]).all() and (got[1] == want[1]).all(), (prec, tiles)
+            # block tiles (curvis_render_frames_peers_blocks): blocks of 32 / 16 / 160 pixels of a row interleaved over 3 / 5 / 2
+            # "ranks" — every rank owns a share of every row; the last case is whole rows through the blocks entry point
+            for bw, world in ((32, 3), (16, 5), (160, 2)):
+                for b in bufs:
+                    b.as_tensor().fill_(7)
+                total = 0
+                for g in range(world):
+                    b0, b1, stride, width_b = distributed.interleaved_blocks(H, W, g, world, bw)
+                    assert width_b == bw
+                    st = sysm.render_frames_peers(cams, *sim, b0, b1, [b.ptr for b in bufs], want_stats=True, row_stride=stride,
+                                                  block_width=width_b, precision=prec)
+                    total += st["n_rays"]
+                assert total == 2 * W * H
+                torch.cuda.synchronize()
+                for b in bufs:
+                    got = b.as_tensor().cpu().numpy().reshape(2, H, W, 3)
+                    assert (got[0] == want[0]).all() and (got[1] == want[1]).all(), (prec, bw, world)
+        # the chart-free kernels share the tile geometry
+        cart = dict(coordinates=_abi.COORDINATES_CARTESIAN)
+        want = sysm.render_image(*sim, **cart).copy()
+        bufs[0].as_tensor().fill_(7)
+        for g in range(3):
+            b0, b1, stride, width_b = distributed.interleaved_blocks(H, W, g, 3, 32)
+            sysm.render_frames_peers(cams[:1], *sim, b0, b1, [bufs[0].ptr], row_stride=stride, block_width=width_b, **cart)
+        torch.cuda.synchronize()
+        assert (bufs[0].as_tensor().cpu().numpy()[: W * H * 3].reshape(H, W, 3) == want).all()
+        with pytest.raises(cv.CurvisError):
+            sysm.render_frames_peers(cams, *sim, 0, H, [b.ptr for b in bufs], block_width=48)       # does not divide the width
+        with pytest.raises(cv.CurvisError):
+            sysm.render_frames_peers(cams, *sim, 0, H * 5 + 1, [b.ptr for b in bufs], block_width=32)   # beyond the last block
         with pytest.raises(cv.CurvisError):
             sysm.render_frames_peers(cams, *sim, 0, H, [b.ptr for b in bufs] * 5)    # more than CURVIS_MAX_PEERS
     finally:

@@ -89,3 +89,28 @@ def test_interleaved_rows_partition():
     assert frame_offset(0, 0, 2160, 3840) == 0 and frame_offset(2, 5, 2160, 3840) == (2 * 2160 + 5) * 3840 * 3
     with pytest.raises(ValueError):
         interleaved_rows(10, 3, 3)
+
+
+def test_interleaved_blocks_partition():
+    """curvis_render_frames_peers_blocks' ownership: every block of every row belongs to exactly one rank, every rank owns an
+    equal share (+-1 block) of the frame AND of every single row that has at least `world` blocks."""
+    from curvis_b200.distributed import block_owner, interleaved_blocks
+    for H, W, bw in ((9, 160, 32), (2160, 3840, 64), (4320, 7680, 64), (7, 96, 96), (5, 100, 64)):
+        for world in (1, 2, 3, 8):
+            tiles = [interleaved_blocks(H, W, r, world, bw) for r in range(world)]
+            width_b = tiles[0][3]
+            assert all(t[3] == width_b for t in tiles) and W % width_b == 0       # (a width that does not divide: whole rows)
+            per_row = W // width_b
+            owned = [list(range(b, e, s)) for b, e, s, _ in tiles]
+            assert sorted(sum(owned, [])) == list(range(H * per_row))
+            assert max(len(o) for o in owned) - min(len(o) for o in owned) <= 1
+            if per_row >= world and H <= 16:
+                for row in range(H):
+                    counts = [sum(1 for v in o if v // per_row == row) for o in owned]
+                    assert max(counts) - min(counts) <= 1, (H, W, bw, world, row)
+            for r, o in enumerate(owned[:2]):
+                for v in o[:5]:
+                    assert block_owner(v // per_row, (v % per_row) * width_b, W, world, width_b) == r
+    assert interleaved_blocks(3, 64, 7, 8, 64) == (3, 3, 8, 64)                  # surplus rank: an empty tile
+    with pytest.raises(ValueError):
+        interleaved_blocks(10, 64, 3, 3)
