@@ -122,7 +122,7 @@ EXPORTED_SYMBOLS = (
     "curvis_render_frames_device", "curvis_render_image_efficient", "curvis_render_rows_rgba32f", "curvis_debug_bilinear",
     "curvis_debug_shape_table_host", "curvis_host_register", "curvis_host_unregister",
     "curvis_peer_buffer_create", "curvis_peer_buffer_open", "curvis_peer_buffer_close", "curvis_peer_buffer_destroy",
-    "curvis_render_frames_peers", "curvis_render_frames_peers_blocks", "curvis_debug_rhs_check", "curvis_debug_inverse_table_host", "curvis_debug_inverse_shape",
+    "curvis_render_frames_peers", "curvis_render_frames_peers_blocks", "curvis_debug_last_step_shares", "curvis_debug_rhs_check", "curvis_debug_inverse_table_host", "curvis_debug_inverse_shape",
     "curvis_debug_fn_table_host",
 )
 
@@ -186,6 +186,7 @@ def load_library() -> C.CDLL:
     lib.curvis_render_frames_peers_blocks.argtypes = [vp, C.POINTER(CurvisMetric), C.POINTER(CurvisCamera), C.c_uint32, C.POINTER(CurvisSim),
                                                       C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp), C.c_uint32, vp,
                                                       C.POINTER(CurvisStats)]
+    lib.curvis_debug_last_step_shares.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.curvis_host_register.argtypes = [vp, vp, C.c_size_t]
     lib.curvis_host_unregister.argtypes = [vp, vp]
     lib.curvis_debug_shape_table_host.argtypes = [dp, dp, dp, C.c_size_t]

@@ -146,7 +146,7 @@ static cudaError_t launch_render(const FrameParams& p, const curvis_metric* metr
                                                            : launch_render_cart(p, metric->kind, t, sm_count, stream);
     if (sim->precision == CURVIS_PRECISION_F32) return launch_render_f32(p, metric->kind, t, sm_count, stream);
     if (sim->precision == CURVIS_PRECISION_F64_FAST) {
-        if (render_f64_fast_has_prepass(p, t, sm_count)) g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+        if (render_f64_fast_has_prepass(p, metric->kind, t, sm_count)) g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
         cudaError_t e = launch_render_f64_fast(p, metric->kind, t, sm_count, stream);
         if (e != cudaSuccess || !p.redo_list) return e;
         // second launch: the parity kernel over the rays the fast kernel left in its guard band (list mode; the list's
@@ -883,6 +883,14 @@ extern "C" int curvis_ctx_set_option(curvis_ctx* ctx, const char* key, int64_t v
     else if (k == "longest_first" && value >= 0 && value <= 2) ctx->tuning.longest_first = (int)value;
     else if (k == "guard_rel_e15" && value >= 1 && value <= 1000000000000ll) ctx->tuning.guard_rel = (double)value * 1e-15;
     else return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "unknown option or value out of range: " + k);
+    return CURVIS_OK;
+}
+
+extern "C" int curvis_debug_last_step_shares(curvis_ctx* ctx, uint64_t slot_steps[64], uint64_t sm_steps[192]) {
+    if (!ctx || !slot_steps || !sm_steps) return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "null argument");
+    const DeviceCounters& c = *ctx->devs[0].h_counters;   // as read back by the last launch that asked for stats
+    for (int i = 0; i < 64; ++i) slot_steps[i] = c.slot_steps[i];
+    for (int i = 0; i < 192; ++i) sm_steps[i] = c.sm_steps[i];
     return CURVIS_OK;
 }
 

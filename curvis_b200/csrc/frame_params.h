@@ -21,7 +21,12 @@ struct DeviceCounters {
     unsigned long long redo_next;      // work queue of the re-integration launch
     unsigned long long n_kicked;       // CURVIS_PRECISION_F64_FAST: rays with stiffness >= 1
     unsigned long long n_long;         // CURVIS_PRECISION_F64_FAST: length of the longest-first list (render_f64_fast.cu: collect_long_rays)
-    unsigned long long _pad[6];
+    unsigned long long long_next;      // work queue of the longest-first list (claimed by the favoured warp slots first)
+    unsigned long long _pad[5];
+    // diagnostics (curvis_debug_last_step_shares): Euler steps executed per hardware warp slot (%warpid) and per SM (%smid) — every
+    // warp of a persistent launch lives as long as the kernel, so these are the shares of the issue slots the scheduler handed out
+    unsigned long long slot_steps[64];
+    unsigned long long sm_steps[192];
 };
 
 struct Background {

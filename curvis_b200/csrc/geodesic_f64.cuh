@@ -793,6 +793,11 @@ __device__ __forceinline__ void flush_tally(const FrameParams& p, RayTally t, un
         if (t.neg) atomicAdd(&p.counters->n_negative, (unsigned long long)t.neg);
         if (t.none) atomicAdd(&p.counters->n_not_escaped, (unsigned long long)t.none);
         if (t.clamped) atomicAdd(&p.counters->n_clamped, (unsigned long long)t.clamped);
+        unsigned warpid, smid;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(warpid));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        atomicAdd(&p.counters->slot_steps[warpid & 63u], t.steps);
+        if (smid < 192u) atomicAdd(&p.counters->sm_steps[smid], t.steps);
     }
 }
 

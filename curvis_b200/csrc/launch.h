@@ -29,8 +29,9 @@ struct LaunchTuning {
     int fast_regs = 0;       // CURVIS_PRECISION_F64_FAST register budget: 96 (5 CTAs per SM) or 128 (4 CTAs); 0 (default) = 96.  4K frames,
                              // 96 against 128: Ellis 36.6 / 37.1 ms, Interstellar 55.6 / 58.2 ms (profiles/r02_time_fast.json)
     int longest_first = 2;   // CURVIS_PRECISION_F64_FAST: rays predicted to be stragglers (near-critical, pole-grazing) are listed by a pre-pass
-                             // kernel and claimed first: 1 = always, 0 = never (index order), 2 (default) = in launches of at most 64
-                             // rays per lane of the grid, where the straggler's latency is comparable to the kernel's (render_f64_fast.cu)
+                             // kernel and claimed first, by the warp slots the schedulers favour: 1 = always, 0 = never (index order),
+                             // 2 (default) = Ellis: always; the other metrics: in launches of at most 64 rays per lane of the grid, where
+                             // the straggler's latency is comparable to the kernel's (render_f64_fast.cu)
     int fast_variant = 1;    // CURVIS_PRECISION_F64_FAST: 0 sin/cos from theta every step; 1 (default) (sin, cos) carried and
                              // rotated by the step's small dtheta, re-derived from theta once per window
 };
@@ -43,7 +44,7 @@ cudaError_t launch_render_f32(const FrameParams& p, int metric_kind, const Launc
 
 // fp64 with a regrouped right-hand side, CURVIS_PRECISION_F64_FAST (render_f64_fast.cu) — extension.
 cudaError_t launch_render_f64_fast(const FrameParams& p, int metric_kind, const LaunchTuning& t, int sm_count, cudaStream_t stream);
-bool render_f64_fast_has_prepass(const FrameParams& p, const LaunchTuning& t, int sm_count);   // one more kernel in front of it (longest-first list)
+bool render_f64_fast_has_prepass(const FrameParams& p, int metric_kind, const LaunchTuning& t, int sm_count);   // one more kernel in front of it (longest-first list)
 
 // fp64, chart-free angular state, CURVIS_COORDINATES_CARTESIAN (render_f64_cart.cu) — extension ("pole-safe").
 cudaError_t launch_render_cart(const FrameParams& p, int metric_kind, const LaunchTuning& t, int sm_count, cudaStream_t stream);

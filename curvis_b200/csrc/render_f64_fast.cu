@@ -38,6 +38,7 @@ namespace {
 constexpr int kBlockFast = 128;
 constexpr double kLongRaySin = 0.03;   // refill: near-critical rays whose orbit comes within asin(0.03) of the polar axis are claimed first
 constexpr unsigned kFullFast = 0xffffffffu;
+constexpr unsigned kFavouredSlots = 8;   // hardware warp slots (%warpid) that claim the longest-first list first: the first two resident CTAs of an SM
 
 // Shape policies of the fast step.  factors() returns, for the current l and sin^2 theta:
 //   w = 1/(r^2 sin^2), u = 1/r^2, v = 1/sin^2, fd = delta * r'(l)/r(l)^3; false when an operand
@@ -80,6 +81,10 @@ struct FastEllis {   // metrics.rs:417-421 : r^2 = rho^2 + l^2, r' = l/r  =>  r'
     }
     static __device__ __forceinline__ bool at_gate(const Pre& pre, unsigned key) { return (unsigned)__double2hiint(pre.r2) >= key; }
     static constexpr bool kGateFromSquares = true;
+    // longest-first refill in launches of any size ("longest_first" = 2): with the listed rays in the favoured warp slots a whole 4K
+    // frame gains 1.1 % (35.29 -> 34.89 ms); the Interstellar kernel loses 0.7 % there (its listed rays run the slow pole-crossing
+    // code all at once) and keeps the rule "at most 64 rays per lane"
+    static constexpr bool kLongFirstWholeFrames = true;
 };
 
 // r(l) > 0 and r'(l) given: one reciprocal of r*sin^2 yields 1/r and 1/sin^2.
@@ -170,6 +175,7 @@ struct FastInterstellar {   // metrics.rs:461-485 with the uniform divisor pi*m 
     static __device__ __forceinline__ unsigned gate_key(const FrameParams&, double) { return 0u; }
     static __device__ __forceinline__ bool at_gate(const Pre&, unsigned) { return false; }
     static constexpr bool kGateFromSquares = false;
+    static constexpr bool kLongFirstWholeFrames = false;
 };
 
 struct FastFlat {   // metrics.rs:501-505: r = l, r' = 1 (r may be negative: take the parity step then)
@@ -190,6 +196,7 @@ struct FastFlat {   // metrics.rs:501-505: r = l, r' = 1 (r may be negative: tak
     static __device__ __forceinline__ unsigned gate_key(const FrameParams&, double) { return 0u; }
     static __device__ __forceinline__ bool at_gate(const Pre&, unsigned) { return false; }
     static constexpr bool kGateFromSquares = false;
+    static constexpr bool kLongFirstWholeFrames = false;
 };
 
 // One forward-Euler step (metrics.rs:283-297) with the regrouped right-hand side.  Returns
@@ -407,7 +414,19 @@ __global__ void __launch_bounds__(kBlockFast, MinBlocks) render_rows_f64_fast(co
         n_long = p.counters->n_long;
         if (n_long > p.long_capacity) n_long = 0;
     }
-    const unsigned long long n_tickets = launch_rays + n_long;
+    // The warp schedulers do not share a saturated fp64 pipe evenly: a warp's share falls with its hardware slot (%warpid).
+    // Over a whole 4K frame the five warps of a scheduler executed 1.65 / 1.51 / 1.08 / 0.55 / 0.21 of the mean
+    // (tools/scheduler_shares.py, profiles/r02_scheduler_shares.json) — a 20,000-step ray takes 2.7 ms in a warp of the first
+    // resident CTA of its SM and 20 ms in one of the fifth.  The listed rays are therefore claimed by the favoured slots first;
+    // the other warps take from the list only once the index walk is exhausted (so the list is consumed whatever slots the
+    // launch got).
+    bool favoured = false;
+    if (LongFirst) {
+        unsigned warpid;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(warpid));
+        favoured = warpid < kFavouredSlots;
+    }
+    bool long_drained = (n_long == 0);
 
     // Per-ray state the step loop never reads lives in shared memory (fast_variant 1): the kernel sits at the 96-register
     // limit of five resident CTAs per SM, and every register the loop does not need is one constant it can keep pinned.
@@ -458,21 +477,22 @@ __global__ void __launch_bounds__(kBlockFast, MinBlocks) render_rows_f64_fast(co
         unsigned idle = __ballot_sync(kFullFast, state == 0);
         if (idle) {
             if (LongFirst) {
-                while (idle && !drained) {
+                while (idle && !(drained && long_drained)) {
+                    // favoured slots: the list first, then the index walk; the others: the index walk, then what is left of the list
+                    const bool from_list = !long_drained && (favoured || drained);
+                    unsigned long long* const queue = from_list ? &p.counters->long_next : &p.counters->next_ray;
+                    const unsigned long long queue_end = from_list ? n_long : launch_rays;
                     const int leader = __ffs(idle) - 1;
                     unsigned long long base = 0;
-                    if ((int)lane == leader) base = atomicAdd(&p.counters->next_ray, (unsigned long long)__popc(idle));
+                    if ((int)lane == leader) base = atomicAdd(queue, (unsigned long long)__popc(idle));
                     base = __shfl_sync(kFullFast, base, leader);
                     if (state == 0) {
                         const unsigned long long ticket = base + (unsigned long long)__popc(idle & lt_mask);
-                        if (ticket < n_tickets) {
-                            unsigned long long idx;
+                        if (ticket < queue_end) {
+                            unsigned long long idx = ticket;
                             bool take = true;
-                            if (ticket < n_long) idx = p.long_list[ticket];
-                            else {
-                                idx = ticket - n_long;
-                                if (n_long) take = !ray_predicted_long(p, idx, tile_rays, kLongRaySin * kLongRaySin);
-                            }
+                            if (from_list) idx = p.long_list[ticket];
+                            else if (n_long) take = !ray_predicted_long(p, idx, tile_rays, kLongRaySin * kLongRaySin);   // (listed: somebody's list ticket)
                             if (take) {
                                 new_photon_for_ray(p, idx, tile_rays, q);
                                 q.pl = q.pl * p.delta; q.pth = q.pth * p.delta; q.pph = q.pph * p.delta;   // (Variant 1 only)
@@ -484,7 +504,10 @@ __global__ void __launch_bounds__(kBlockFast, MinBlocks) render_rows_f64_fast(co
                             }
                         }
                     }
-                    if (base + (unsigned long long)__popc(idle) >= n_tickets) drained = true;
+                    if (base + (unsigned long long)__popc(idle) >= queue_end) {
+                        if (from_list) long_drained = true;
+                        else drained = true;
+                    }
                     idle = __ballot_sync(kFullFast, state == 0);
                 }
             } else if (!drained) {                 // rays in index order
@@ -605,10 +628,10 @@ __global__ void __launch_bounds__(256) collect_long_rays(const __grid_constant__
 constexpr unsigned long long kLongestFirstMinRays = 1ull << 15;
 constexpr unsigned long long kLongestFirstMaxRaysPerLane = 64;
 
-__host__ bool longest_first_wanted(const FrameParams& p, int mode, int sm_count) {
+__host__ bool longest_first_wanted(const FrameParams& p, int mode, int sm_count, bool whole_frames) {
     const unsigned long long rays = (unsigned long long)(p.row_end - p.row_begin) * p.width * (p.n_frames ? p.n_frames : 1u);
     if (!p.long_list || mode == 0 || rays < kLongestFirstMinRays) return false;
-    return mode == 1 || rays <= kLongestFirstMaxRaysPerLane * (unsigned long long)sm_count * 5ull * kBlockFast;
+    return mode == 1 || whole_frames || rays <= kLongestFirstMaxRaysPerLane * (unsigned long long)sm_count * 5ull * kBlockFast;
 }
 
 template <class Fast, int Variant, int MinBlocks>
@@ -625,7 +648,7 @@ cudaError_t launch_fast_variant(const FrameParams& p, int sm_count, int blocks_p
     unsigned long long want = (rays + kBlockFast - 1) / kBlockFast;
     unsigned long long cap = (unsigned long long)sm_count * (unsigned long long)blocks_per_sm;
     const unsigned grid = (unsigned)(want < cap ? (want ? want : 1) : cap);
-    if (Variant == 1 && longest_first_wanted(p, longest_first, sm_count)) {
+    if (Variant == 1 && longest_first_wanted(p, longest_first, sm_count, Fast::kLongFirstWholeFrames)) {
         const unsigned long long blocks = (rays + 255) / 256;
         collect_long_rays<<<(unsigned)(blocks < 8ull * sm_count ? blocks : 8ull * sm_count), 256, 0, stream>>>(p);
         render_rows_f64_fast<Fast, Variant, MinBlocks, Variant == 1><<<grid, kBlockFast, 0, stream>>>(p);
@@ -681,9 +704,9 @@ cudaError_t launch_debug_shape(const double2* tab, int which, const double* x, d
 }
 
 // Whether launch_render_f64_fast launches the longest-first pre-pass in front of the render kernel (the launch counter's business).
-bool render_f64_fast_has_prepass(const FrameParams& p, const LaunchTuning& t, int sm_count) {
+bool render_f64_fast_has_prepass(const FrameParams& p, int metric_kind, const LaunchTuning& t, int sm_count) {
     const double ad = p.delta < 0.0 ? -p.delta : p.delta;
-    return t.fast_variant == 1 && (ad >= 0x1p-100 && ad <= 0x1p100) && longest_first_wanted(p, t.longest_first, sm_count);
+    return t.fast_variant == 1 && (ad >= 0x1p-100 && ad <= 0x1p100) && longest_first_wanted(p, t.longest_first, sm_count, metric_kind == CURVIS_METRIC_ELLIS /* FastEllis::kLongFirstWholeFrames */);
 }
 
 cudaError_t launch_render_f64_fast(const FrameParams& p, int metric_kind, const LaunchTuning& t, int sm_count, cudaStream_t stream) {

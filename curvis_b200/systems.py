@@ -81,6 +81,12 @@ class Context:
         _abi.check(self._lib.curvis_debug_rhs_check(self._ptr, C.byref(m), int(n_samples), int(seed), bad), self._ptr)
         return list(bad)
 
+    def last_step_shares(self):
+        """curvis_debug_last_step_shares: Euler steps per hardware warp slot (64) and per SM (192) of the last launch with stats."""
+        slots, sms = (C.c_uint64 * 64)(), (C.c_uint64 * 192)()
+        _abi.check(self._lib.curvis_debug_last_step_shares(self._ptr, slots, sms), self._ptr)
+        return list(slots), list(sms)
+
     def measure_fma_peak(self):
         f64, f32 = C.c_double(), C.c_double()
         _abi.check(self._lib.curvis_measure_fma_peak(self._ptr, C.byref(f64), C.byref(f32)), self._ptr)

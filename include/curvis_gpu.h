@@ -429,6 +429,11 @@ int curvis_debug_eval(curvis_ctx* ctx, int op, const double* a, const double* b,
 int curvis_debug_inverse_table_host(double rho, double m, const double* z, double* y, double* g, size_t n);
 int curvis_debug_inverse_shape(curvis_ctx* ctx, const curvis_metric* metric, const double* z, double* y, double* g, size_t n);
 
+/* Diagnostics of the last launch that returned stats (first device): Euler steps executed per hardware warp slot (%warpid, 64
+ * entries) and per SM (%smid, 192 entries).  Every warp of a persistent launch lives as long as the kernel, so the entries are
+ * the shares of issue slots the warp schedulers handed out (tools/scheduler_shares.py). */
+int curvis_debug_last_step_shares(curvis_ctx* ctx, uint64_t slot_steps[64], uint64_t sm_steps[192]);
+
 /* Test hook of kernel_variant 4 (the default CURVIS_PRECISION_F64 step: the six reciprocals of metrics.rs:257-262 from two
  * MUFU seeds and one correction step each): evaluates the right-hand side of n_samples pseudo-random photon states both
  * ways — shared reciprocals vs. the plain IEEE operators — and returns in mismatches[0..3] how many of the outputs
