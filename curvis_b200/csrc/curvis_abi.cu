@@ -259,6 +259,7 @@ static void fill_params(const curvis_ctx* ctx, const DeviceState& d, const curvi
         p.gate_hi = (sim->max_radius >= 0.0) ? (uint32_t)((bits >> 32) & 0x7fffffffu) : 0u;
     }
     p.row_begin = row_begin; p.row_end = row_end; p.row_stride = 1;
+    p.favoured_slots = (uint32_t)ctx->tuning.favoured_slots;
     p.frame_width = cam->resolution_width; p.blocks_per_row = 1;
     p.inv_frame_width = 1.0 / (double)cam->resolution_width; p.inv_blocks_per_row = 1.0;
     p.inv_width = 1.0 / (double)cam->resolution_width;
@@ -881,6 +882,7 @@ extern "C" int curvis_ctx_set_option(curvis_ctx* ctx, const char* key, int64_t v
     else if (k == "redo_ahead" && value >= 0 && value <= 1) ctx->tuning.redo_ahead = (int)value;
     else if (k == "redo_capacity_limit" && value >= 0) ctx->tuning.redo_capacity_limit = value;
     else if (k == "longest_first" && value >= 0 && value <= 2) ctx->tuning.longest_first = (int)value;
+    else if (k == "favoured_slots" && value >= 0 && value <= 64) ctx->tuning.favoured_slots = (int)value;
     else if (k == "guard_rel_e15" && value >= 1 && value <= 1000000000000ll) ctx->tuning.guard_rel = (double)value * 1e-15;
     else return fail(ctx, CURVIS_ERR_INVALID_ARGUMENT, "unknown option or value out of range: " + k);
     return CURVIS_OK;

@@ -106,6 +106,8 @@ struct FrameParams {
     // numbered row-major over the frame (blocks_per_row = frame_width / width of them per row): interleaving blocks instead of
     // rows splits EVERY row over the ranks — the 10^4-step rays of a frame sit in two or three rows.  Whole rows: width =
     // frame_width, blocks_per_row = 1.  frame_width and height are what the camera and the output addresses see.
+    uint32_t favoured_slots;   // longest-first refill: hardware warp slots (%warpid <) that claim the list first (render_f64_fast.cu)
+    uint32_t _pad4;
     uint32_t frame_width, blocks_per_row;
     double inv_frame_width, inv_blocks_per_row;
     // curvis_sim extensions (all 0 in parity mode): curvis_frame, curvis_coordinates, adaptive-step tolerance

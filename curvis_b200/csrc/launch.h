@@ -32,6 +32,9 @@ struct LaunchTuning {
                              // kernel and claimed first, by the warp slots the schedulers favour: 1 = always, 0 = never (index order),
                              // 2 (default) = Ellis: always; the other metrics: in launches of at most 64 rays per lane of the grid, where
                              // the straggler's latency is comparable to the kernel's (render_f64_fast.cu)
+    int favoured_slots = 8;  // longest-first refill: the listed rays are claimed first by the warps in hardware slots %warpid < this (the first two
+                             // resident CTAs of an SM: 1.65x / 1.51x the mean share of their scheduler); 0 = no warp is favoured (the list is taken
+                             // when the index walk is exhausted), 64 = every warp (round 2's first form)
     int fast_variant = 1;    // CURVIS_PRECISION_F64_FAST: 0 sin/cos from theta every step; 1 (default) (sin, cos) carried and
                              // rotated by the step's small dtheta, re-derived from theta once per window
 };

@@ -38,7 +38,6 @@ namespace {
 constexpr int kBlockFast = 128;
 constexpr double kLongRaySin = 0.03;   // refill: near-critical rays whose orbit comes within asin(0.03) of the polar axis are claimed first
 constexpr unsigned kFullFast = 0xffffffffu;
-constexpr unsigned kFavouredSlots = 8;   // hardware warp slots (%warpid) that claim the longest-first list first: the first two resident CTAs of an SM
 
 // Shape policies of the fast step.  factors() returns, for the current l and sin^2 theta:
 //   w = 1/(r^2 sin^2), u = 1/r^2, v = 1/sin^2, fd = delta * r'(l)/r(l)^3; false when an operand
@@ -424,7 +423,7 @@ __global__ void __launch_bounds__(kBlockFast, MinBlocks) render_rows_f64_fast(co
     if (LongFirst) {
         unsigned warpid;
         asm volatile("mov.u32 %0, %%warpid;" : "=r"(warpid));
-        favoured = warpid < kFavouredSlots;
+        favoured = warpid < p.favoured_slots;
     }
     bool long_drained = (n_long == 0);
 

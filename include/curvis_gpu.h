@@ -394,6 +394,8 @@ int curvis_measure_fma_peak(curvis_ctx* ctx, double* fp64_tflops, double* fp32_t
  *   "redo_blocks_per_sm": resident CTAs per SM of the re-integration launch (default 2)
  *   "redo_capacity_limit": test knob — caps the re-integration list (0 = automatic: one slot per ray up to 2^24 rays); a ray
  *                     that finds the list full is re-integrated in line by the fast kernel (same result, slower)
+ *   "favoured_slots": the warps in hardware slots %warpid < this claim the longest-first list first (default 8: a scheduler gives
+ *                     its five warps 1.65 / 1.51 / 1.08 / 0.55 / 0.21 of the mean share in slot order); 0 none, 64 all
  *   "longest_first":  CURVIS_PRECISION_F64_FAST: a pre-pass kernel lists the rays predicted to be the 10^4-step stragglers (near-
  *                     critical photons grazing a coordinate pole) and the work queue hands them out first: 1 always, 0 never
  *                     (index order), 2 (default) in launches of at most 64 rays per lane of the grid — one frame split over

@@ -123,15 +123,18 @@ def test_scheduling_options_do_not_change_a_ray(gpu_ctx):
             for cam in cams:
                 sysm = cv.RelativisticSystem(metric, cv.SphericalImage(bp), cv.SphericalImage(bn), cam, context=gpu_ctx)
                 out = {}
-                for lf, regs in ((0, 0), (1, 0), (2, 0), (1, 128)):
+                # (the third entry: "favoured_slots" — 0: no warp takes the list before the index walk is exhausted, i.e. the path a
+                # launch takes whose warps all sit in unfavoured hardware slots; 64: every warp takes it first)
+                for lf, regs, slots in ((0, 0, 8), (1, 0, 8), (2, 0, 8), (1, 128, 8), (1, 0, 0), (1, 0, 64), (1, 0, 3)):
                     gpu_ctx.set_option("longest_first", lf)
                     gpu_ctx.set_option("fast_regs", regs)
+                    gpu_ctx.set_option("favoured_slots", slots)
                     n0 = lib.curvis_kernel_launch_count()
                     frame, rec = sysm.render_rows(*sim, 0, H, with_records=True, precision=_abi.PRECISION_F64_FAST)
-                    out[(lf, regs)] = (frame, rec, dict(sysm.last_stats), lib.curvis_kernel_launch_count() - n0)
-                f0, r0, s0, n_launch0 = out[(0, 0)]
+                    out[(lf, regs, slots)] = (frame, rec, dict(sysm.last_stats), lib.curvis_kernel_launch_count() - n0)
+                f0, r0, s0, n_launch0 = out[(0, 0, 8)]
                 assert n_launch0 == 2                                  # render + re-integration
-                assert out[(1, 0)][3] == 3 and out[(2, 0)][3] == 3      # + the pre-pass (129,600 rays: under 64 per lane)
+                assert out[(1, 0, 8)][3] == 3 and out[(2, 0, 8)][3] == 3      # + the pre-pass (129,600 rays: under 64 per lane)
                 for key, (f, r, st, _) in out.items():
                     assert f.tobytes() == f0.tobytes() and r.tobytes() == r0.tobytes(), (type(metric).__name__, key)
                     for k in ("total_steps", "n_positive", "n_negative", "n_not_escaped", "n_clamped", "n_reintegrated", "n_kicked"):
@@ -139,6 +142,7 @@ def test_scheduling_options_do_not_change_a_ray(gpu_ctx):
     finally:
         gpu_ctx.set_option("longest_first", 2)
         gpu_ctx.set_option("fast_regs", 0)
+        gpu_ctx.set_option("favoured_slots", 8)
 
 
 def _compare_with_oracle(frame, rec, ref_frame, ref_rec, name):
