@@ -146,7 +146,8 @@ static cudaError_t launch_render(const FrameParams& p, const curvis_metric* metr
                                                            : launch_render_cart(p, metric->kind, t, sm_count, stream);
     if (sim->precision == CURVIS_PRECISION_F32) return launch_render_f32(p, metric->kind, t, sm_count, stream);
     if (sim->precision == CURVIS_PRECISION_F64_FAST) {
-        if (render_f64_fast_has_prepass(p, metric->kind, t, sm_count)) g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+        const bool prepass = render_f64_fast_has_prepass(p, metric->kind, t, sm_count);
+        if (prepass) g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
         cudaError_t e = launch_render_f64_fast(p, metric->kind, t, sm_count, stream);
         if (e != cudaSuccess || !p.redo_list) return e;
         // second launch: the parity kernel over the rays the fast kernel left in its guard band (list mode; the list's
@@ -155,6 +156,7 @@ static cudaError_t launch_render(const FrameParams& p, const curvis_metric* metr
         r.ray_list = p.redo_list;
         r.ray_list_count = &p.counters->n_reintegrated;
         r.redo_list = nullptr;
+        r.list_from_end = prepass ? 0u : 1u;
         r.window = 32;
         LaunchTuning rt = t;
         rt.blocks_per_sm = t.redo_blocks_per_sm;

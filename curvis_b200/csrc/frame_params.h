@@ -107,7 +107,7 @@ struct FrameParams {
     // rows splits EVERY row over the ranks — the 10^4-step rays of a frame sit in two or three rows.  Whole rows: width =
     // frame_width, blocks_per_row = 1.  frame_width and height are what the camera and the output addresses see.
     uint32_t favoured_slots;   // longest-first refill: hardware warp slots (%warpid <) that claim the list first (render_f64_fast.cu)
-    uint32_t _pad4;
+    uint32_t list_from_end;    // list mode: walk ray_list from its last entry (render_f64.cu)
     uint32_t frame_width, blocks_per_row;
     double inv_frame_width, inv_blocks_per_row;
     // curvis_sim extensions (all 0 in parity mode): curvis_frame, curvis_coordinates, adaptive-step tolerance

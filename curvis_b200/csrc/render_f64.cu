@@ -147,7 +147,10 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64_lean(const __grid_cons
                 if (state == 0) {
                     const unsigned long long idx = base + (unsigned long long)__popc(idle & lt_mask);
                     if (idx < launch_rays) {
-                        ray = p.ray_list ? p.ray_list[idx] : idx;
+                        // (list mode: the fast kernel appended the rays as they finished.  Where it claimed its predicted stragglers first,
+                        // the longest rays are near the list's head; where it walked the indices they are its last entries, and the list is
+                        // walked from its end — with guard = 2, when the list outnumbers the launch's lanes, they must start first)
+                        ray = p.ray_list ? p.ray_list[p.list_from_end ? launch_rays - 1ull - idx : idx] : idx;
                         new_photon_for_ray(p, ray, tile_rays, q);
                         ray_safe = frame_safe && ray_operands_safe(q);
                         remaining = p.max_iterations;

@@ -342,3 +342,22 @@ def test_guard_band_holds_on_random_scenes(gpu_ctx):
         assert abs(s1["total_steps"] - s0["total_steps"]) <= int(bad.sum()) * sim[0]
     print(f"[guard] 16 random scenes, {total} rays: kicked {kicked_total}, re-integrated {reintegrated}, differing (all kicked) {differing_kicked}")
     assert differing_kicked <= max(1, int(1e-5 * total))
+
+
+def test_step_shares_account_for_every_step(gpu_ctx):
+    """curvis_debug_last_step_shares: the per-warp-slot and per-SM step counts of the last launch (what tools/scheduler_shares.py reads
+    the schedulers' unfairness from) each add up to the launch's total_steps, re-integration launch included; no slot beyond the
+    resident warps of an SM is used."""
+    import curvis_b200 as cv
+    from curvis_b200 import _abi, scenes
+    bp, bn = scenes.noise_background(512, 256, 3), scenes.noise_background(512, 256, 4)
+    W, H, sim = 320, 180, (40000, 100.0, 0.05)
+    cam = cv.Camera(scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP, 15.0, 43.0, W, H)
+    sysm = cv.RelativisticSystem(cv.EllisMetric(1.0), cv.SphericalImage(bp), cv.SphericalImage(bn), cam, context=gpu_ctx)
+    for prec in (_abi.PRECISION_F64_FAST, _abi.PRECISION_F64):
+        sysm.render_rows(*sim, 0, H, precision=prec)
+        slots, sms = gpu_ctx.last_step_shares()
+        total = sysm.last_stats["total_steps"]
+        assert sum(slots) == total and sum(sms) == total and total > 0
+        assert all(s == 0 for s in slots[32:])          # at most 5 CTAs x 4 warps per SM: slots 0..19 (0..31 with headroom)
+        assert sum(1 for s in sms if s) > 100           # the launch covered the GPU
