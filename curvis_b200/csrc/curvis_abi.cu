@@ -164,6 +164,7 @@ static cudaError_t launch_render(const FrameParams& p, const curvis_metric* metr
         g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
         return launch_render_f64(r, metric->kind, rt, sm_count, stream);
     }
+    if (render_f64_has_prepass(p, t, sm_count)) g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
     return launch_render_f64(p, metric->kind, t, sm_count, stream);
 }
 
@@ -201,8 +202,10 @@ static int ensure_inverse_table(curvis_ctx* ctx, DeviceState& d, const curvis_me
 // The redo list of CURVIS_PRECISION_F64_FAST: one slot per ray of the launch (8 bytes each; a 4K frame: 66 MB), grown on demand.
 // (Also the longest-first list of the same kernel: an eighth of the launch, at least 4096 slots; a list that overflows is ignored.)
 static int ensure_redo(curvis_ctx* ctx, DeviceState& d, const curvis_sim* sim, size_t rays) {
-    if (sim->precision != CURVIS_PRECISION_F64_FAST || ctx->tuning.fast_variant != 1 ||
-        sim->coordinates != CURVIS_COORDINATES_SPHERICAL) return CURVIS_OK;
+    const bool strict_list = sim->precision == CURVIS_PRECISION_F64 && sim->coordinates == CURVIS_COORDINATES_SPHERICAL &&
+                             sim->integrator == CURVIS_INTEGRATOR_EULER;       // the longest-first list of the default kernel
+    if (!strict_list && (sim->precision != CURVIS_PRECISION_F64_FAST || ctx->tuning.fast_variant != 1 ||
+                         sim->coordinates != CURVIS_COORDINATES_SPHERICAL)) return CURVIS_OK;
     if (ctx->tuning.longest_first) {
         const size_t want_long = std::max(size_t(4096), rays / 8);
         if (want_long > d.d_long_cap) {
@@ -212,7 +215,7 @@ static int ensure_redo(curvis_ctx* ctx, DeviceState& d, const curvis_sim* sim, s
             d.d_long_cap = want_long;
         }
     }
-    if (!ctx->tuning.guard) return CURVIS_OK;
+    if (!ctx->tuning.guard || strict_list) return CURVIS_OK;
     // one slot per ray up to 2^24 rays (128 MB: two 4K frames, half an 8K frame); beyond that an eighth of the launch (the
     // band takes ~1e-3 of the rays, 2.5 % with "guard" = 2); a full list makes the kernel re-integrate in line (correct, slow)
     const size_t want = rays <= (size_t(1) << 24) ? rays : std::max(size_t(1) << 24, rays / 8);
@@ -298,8 +301,9 @@ static void fill_params(const curvis_ctx* ctx, const DeviceState& d, const curvi
         p.redo_capacity = (unsigned long long)ctx->tuning.redo_capacity_limit;
     p.guard_rel = ctx->tuning.guard_rel;
     p.guard_kicked = ctx->tuning.guard >= 2 ? 1u : 0u;
-    const bool longest_first = sim->precision == CURVIS_PRECISION_F64_FAST && ctx->tuning.longest_first && ctx->tuning.fast_variant == 1 &&
-                               sim->coordinates == CURVIS_COORDINATES_SPHERICAL;
+    const bool longest_first = ctx->tuning.longest_first && sim->coordinates == CURVIS_COORDINATES_SPHERICAL &&
+                               ((sim->precision == CURVIS_PRECISION_F64_FAST && ctx->tuning.fast_variant == 1) ||
+                                (sim->precision == CURVIS_PRECISION_F64 && sim->integrator == CURVIS_INTEGRATOR_EULER));
     p.long_list = longest_first ? d.d_long : nullptr;
     p.long_capacity = longest_first ? d.d_long_cap : 0;
 }

@@ -31,7 +31,8 @@ struct LaunchTuning {
     int longest_first = 2;   // CURVIS_PRECISION_F64_FAST: rays predicted to be stragglers (near-critical, pole-grazing) are listed by a pre-pass
                              // kernel and claimed first, by the warp slots the schedulers favour: 1 = always, 0 = never (index order),
                              // 2 (default) = Ellis: always; the other metrics: in launches of at most 64 rays per lane of the grid, where
-                             // the straggler's latency is comparable to the kernel's (render_f64_fast.cu)
+                             // the straggler's latency is comparable to the kernel's (render_f64_fast.cu).  CURVIS_PRECISION_F64 (kernel_variant 5)
+                             // follows the same rule for its tiles (render_f64.cu: lean_longest_first)
     int favoured_slots = 8;  // longest-first refill: the listed rays are claimed first by the warps in hardware slots %warpid < this (the first two
                              // resident CTAs of an SM: 1.65x / 1.51x the mean share of their scheduler); 0 = no warp is favoured (the list is taken
                              // when the index walk is exhausted), 64 = every warp (round 2's first form)
@@ -48,6 +49,13 @@ cudaError_t launch_render_f32(const FrameParams& p, int metric_kind, const Launc
 // fp64 with a regrouped right-hand side, CURVIS_PRECISION_F64_FAST (render_f64_fast.cu) — extension.
 cudaError_t launch_render_f64_fast(const FrameParams& p, int metric_kind, const LaunchTuning& t, int sm_count, cudaStream_t stream);
 bool render_f64_fast_has_prepass(const FrameParams& p, int metric_kind, const LaunchTuning& t, int sm_count);   // one more kernel in front of it (longest-first list)
+
+// The longest-first pre-pass (render_f64_fast.cu: collect_long_rays writes FrameParams::long_list) and the rule that decides whether a
+// launch runs it, shared with the operation-for-operation kernel; kLongRaySin2 is the predicate's limit on sin^2 theta_min.
+constexpr double kLongRaySin2 = 0.03 * 0.03;
+bool longest_first_prepass_wanted(const FrameParams& p, int mode, int sm_count, bool whole_frames);
+cudaError_t launch_collect_long_rays(const FrameParams& p, int sm_count, cudaStream_t stream);
+bool render_f64_has_prepass(const FrameParams& p, const LaunchTuning& t, int sm_count);   // CURVIS_PRECISION_F64 launches it too (whole Euler frames / tiles)
 
 // fp64, chart-free angular state, CURVIS_COORDINATES_CARTESIAN (render_f64_cart.cu) — extension ("pole-safe").
 cudaError_t launch_render_cart(const FrameParams& p, int metric_kind, const LaunchTuning& t, int sm_count, cudaStream_t stream);

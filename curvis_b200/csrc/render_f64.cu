@@ -103,7 +103,11 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64(const __grid_constant_
 // band — ray i of the launch is ray ray_list[i] of the tile, *ray_list_count of them.
 // AHEAD: the step loop in latency form (geodesic_f64.cuh: euler_steps_ahead) — list mode, where a few hundred rays leave the
 // launch bound by one ray's dependent chain.  Same arithmetic; more registers (no occupancy to protect).
-template <class Shape, int INTEG, bool TRACK, bool SHARED, bool AHEAD = false>
+// LONGFIRST: the longest-first refill of render_f64_fast.cu — a pre-pass has listed the rays predicted to take 10^4 steps, and the
+// warps in the hardware slots the schedulers favour claim them first (this kernel's five warps per scheduler get 2.02 / 1.53 /
+// 0.92 / 0.39 / 0.14 of the mean share in %warpid order: a 20,000-step ray needs 5 ms in the first resident CTA of its SM and
+// 70 ms in the fifth).
+template <class Shape, int INTEG, bool TRACK, bool SHARED, bool AHEAD = false, bool LONGFIRST = false>
 __global__ void __launch_bounds__(kBlock) render_rows_f64_lean(const __grid_constant__ FrameParams p) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -128,6 +132,16 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64_lean(const __grid_cons
     pins.load(AHEAD && Shape::kAheadPinHalf);
 
     RayTally tally;
+    unsigned long long n_long = 0;
+    bool favoured = false;
+    if (LONGFIRST) {
+        n_long = p.counters->n_long;
+        if (n_long > p.long_capacity) n_long = 0;      // a list that overflowed is ignored
+        unsigned warpid;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(warpid));
+        favoured = warpid < p.favoured_slots;
+    }
+    bool long_drained = (n_long == 0);
 
     for (;;) {
         if (state == 2) {
@@ -137,9 +151,41 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64_lean(const __grid_cons
             state = 0;
         }
 
-        const unsigned idle = __ballot_sync(kFull, state == 0);
+        unsigned idle = __ballot_sync(kFull, state == 0);
         if (idle) {
-            if (!drained) {
+            if (LONGFIRST) {
+                // favoured slots: the list first, then the index walk (skipping the listed rays); the others: the walk, then what is left
+                while (idle && !(drained && long_drained)) {
+                    const bool from_list = !long_drained && (favoured || drained);
+                    unsigned long long* const qu = from_list ? &p.counters->long_next : queue;
+                    const unsigned long long qu_end = from_list ? n_long : launch_rays;
+                    const int leader = __ffs(idle) - 1;
+                    unsigned long long base = 0;
+                    if ((int)lane == leader) base = atomicAdd(qu, (unsigned long long)__popc(idle));
+                    base = __shfl_sync(kFull, base, leader);
+                    if (state == 0) {
+                        const unsigned long long ticket = base + (unsigned long long)__popc(idle & lt_mask);
+                        if (ticket < qu_end) {
+                            unsigned long long idx = ticket;
+                            bool take = true;
+                            if (from_list) idx = p.long_list[ticket];
+                            else if (n_long) take = !ray_predicted_long(p, idx, tile_rays, kLongRaySin2);
+                            if (take) {
+                                ray = idx;
+                                new_photon_for_ray(p, ray, tile_rays, q);
+                                ray_safe = frame_safe && ray_operands_safe(q);
+                                remaining = p.max_iterations;
+                                state = (remaining == 0) ? 2 : 1;
+                            }
+                        }
+                    }
+                    if (base + (unsigned long long)__popc(idle) >= qu_end) {
+                        if (from_list) long_drained = true;
+                        else drained = true;
+                    }
+                    idle = __ballot_sync(kFull, state == 0);
+                }
+            } else if (!drained) {
                 const int leader = __ffs(idle) - 1;
                 unsigned long long base = 0;
                 if ((int)lane == leader) base = atomicAdd(queue, (unsigned long long)__popc(idle));
@@ -217,11 +263,23 @@ static cudaError_t launch_persistent(Kernel kernel, int& blocks_per_sm_auto, con
     return cudaGetLastError();
 }
 
-template <class Shape, int INTEG, bool TRACK, bool SHARED, bool AHEAD = false>
+template <class Shape, int INTEG, bool TRACK, bool SHARED, bool AHEAD = false, bool LONGFIRST = false>
 static cudaError_t launch_lean_one(const FrameParams& p, int sm_count, int blocks_per_sm_override, cudaStream_t stream) {
     static int blocks_per_sm_auto = 0;   // per instantiation
-    return launch_persistent(render_rows_f64_lean<Shape, INTEG, TRACK, SHARED, AHEAD>, blocks_per_sm_auto, p, sm_count, blocks_per_sm_override, stream);
+    return launch_persistent(render_rows_f64_lean<Shape, INTEG, TRACK, SHARED, AHEAD, LONGFIRST>, blocks_per_sm_auto, p, sm_count, blocks_per_sm_override, stream);
 }
+
+// The default kernel's launches that run the longest-first pre-pass: plain Euler tiles (no records, not the re-integration list) of
+// at least 2^15 rays and at most 64 rays per lane — one rank's share of a frame split over several GPUs (rows 7, 15, ... of a 4K
+// frame: 11.2 .. 12.3 ms in index order, 10.97 +- 0.02 with the list).  A whole frame on one GPU does not need it: its stragglers end
+// before the kernel does even in the slowest slot, and the instantiation with the list handling is 1-2 % slower (4K Ellis 85.5
+// against 83.9 ms).
+static bool lean_longest_first(const FrameParams& p, const LaunchTuning& t, int sm_count) {
+    return t.kernel_variant >= 5 && p.integrator == CURVIS_INTEGRATOR_EULER && !p.records && !p.ray_list && !p.ray_dirs &&
+           longest_first_prepass_wanted(p, t.longest_first, sm_count, false);
+}
+
+bool render_f64_has_prepass(const FrameParams& p, const LaunchTuning& t, int sm_count) { return lean_longest_first(p, t, sm_count); }
 
 template <class Shape>
 static cudaError_t launch_lean(const FrameParams& p, int sm_count, int blocks_per_sm_override, bool shared, bool ahead, cudaStream_t stream) {
@@ -253,7 +311,13 @@ static cudaError_t launch_variant(const FrameParams& p, const LaunchTuning& t, i
     case 1: return launch_one<Shape, TrigCuda, true>(p, sm_count, t.blocks_per_sm, stream);
     case 2: return launch_one<Shape, TrigFast, true>(p, sm_count, t.blocks_per_sm, stream);
     case 3: return launch_lean<Shape>(p, sm_count, t.blocks_per_sm, false, false, stream);    // one full division sequence per quotient
-    case 5: return launch_lean<Shape>(p, sm_count, t.blocks_per_sm, true, true, stream);      // 4 with the step loop in latency form (A/B)
+    case 5:                                                                                   // 4 with the step loop in latency form
+        if (lean_longest_first(p, t, sm_count)) {
+            cudaError_t e = launch_collect_long_rays(p, sm_count, stream);
+            if (e != cudaSuccess) return e;
+            return launch_lean_one<Shape, 0, false, true, true, true>(p, sm_count, t.blocks_per_sm, stream);
+        }
+        return launch_lean<Shape>(p, sm_count, t.blocks_per_sm, true, true, stream);
     default: return launch_lean<Shape>(p, sm_count, t.blocks_per_sm, true, false, stream);     // default (4): shared reciprocals
     }
 }

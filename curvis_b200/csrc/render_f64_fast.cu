@@ -702,6 +702,18 @@ cudaError_t launch_debug_shape(const double2* tab, int which, const double* x, d
     return cudaGetLastError();
 }
 
+// The longest-first pre-pass for the operation-for-operation kernel (render_f64.cu: the same list, the same rule).
+bool longest_first_prepass_wanted(const FrameParams& p, int mode, int sm_count, bool whole_frames) {
+    return longest_first_wanted(p, mode, sm_count, whole_frames);
+}
+
+cudaError_t launch_collect_long_rays(const FrameParams& p, int sm_count, cudaStream_t stream) {
+    const unsigned long long rays = (unsigned long long)(p.row_end - p.row_begin) * p.width * (p.n_frames ? p.n_frames : 1u);
+    const unsigned long long blocks = (rays + 255) / 256;
+    collect_long_rays<<<(unsigned)(blocks < 8ull * sm_count ? blocks : 8ull * sm_count), 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
 // Whether launch_render_f64_fast launches the longest-first pre-pass in front of the render kernel (the launch counter's business).
 bool render_f64_fast_has_prepass(const FrameParams& p, int metric_kind, const LaunchTuning& t, int sm_count) {
     const double ad = p.delta < 0.0 ? -p.delta : p.delta;

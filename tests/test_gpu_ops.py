@@ -143,3 +143,39 @@ def test_strict_interstellar_atan_and_log_on_device(gpu_ctx):
     for got, want in ((gpu_ctx.debug_eval(17, out), np.arctan(ol)), (gpu_ctx.debug_eval(18, out), np.log((1.0 + out * out).astype(np.longdouble)))):
         err = np.abs((got.astype(np.longdouble) - want) / np.spacing(np.abs(want.astype(np.float64))).astype(np.longdouble)).astype(np.float64)
         assert err.max() <= 2.0
+
+
+def test_strict_kernel_longest_first_does_not_change_a_ray(gpu_ctx):
+    """CURVIS_PRECISION_F64 launches of >= 2^15 rays run the longest-first pre-pass too (kernel_variant 5): the listed rays are
+    claimed first by the favoured warp slots, the index walk skips them.  Only the ORDER changes: frame, records and counters are
+    byte-identical with the list off, with nobody favoured (the list is taken last) and with everybody favoured; the pre-pass
+    shows up as one more launch."""
+    import curvis_b200 as cv
+    from curvis_b200 import _abi, scenes
+    lib = _abi.load_library()
+    bp, bn = scenes.noise_background(512, 256, 7), scenes.noise_background(512, 256, 8)
+    W, H, sim = 320, 180, (40000, 100.0, 0.05)
+    try:
+        for metric in (cv.EllisMetric(1.0), cv.InterstellarMetric(0.1, 1e-4, 1.0)):
+            for cam in (cv.Camera(scenes.DEFAULT_CAMERA_POSITION, scenes.DEFAULT_FORWARD, scenes.DEFAULT_UP, 15.0, 43.0, W, H),
+                        cv.Camera((0.0, -4.0, 1.1, 2.0), (0.9, 0.3, -0.2), (0.1, 0.2, 1.0), 12.0, 43.0, W, H)):
+                sysm = cv.RelativisticSystem(metric, cv.SphericalImage(bp), cv.SphericalImage(bn), cam, context=gpu_ctx)
+                out = {}
+                for lf, slots in ((0, 8), (2, 8), (1, 0), (1, 64), (1, 5)):
+                    gpu_ctx.set_option("longest_first", lf)
+                    gpu_ctx.set_option("favoured_slots", slots)
+                    n0 = lib.curvis_kernel_launch_count()
+                    frame = sysm.render_rows(*sim, 0, H, precision=_abi.PRECISION_F64).copy()
+                    out[(lf, slots)] = (frame, dict(sysm.last_stats), lib.curvis_kernel_launch_count() - n0)
+                f0, s0, n_launch0 = out[(0, 8)]
+                assert n_launch0 == 1 and out[(2, 8)][2] == 2 and out[(1, 0)][2] == 2
+                for key, (f, st, _) in out.items():
+                    assert f.tobytes() == f0.tobytes(), (type(metric).__name__, key)
+                    for k in ("total_steps", "n_positive", "n_negative", "n_not_escaped", "n_clamped"):
+                        assert st[k] == s0[k], (key, k)
+                # records launches keep the index order (no pre-pass) and agree with the frame above
+                frame_r, rec = sysm.render_rows(*sim, 0, H, with_records=True, precision=_abi.PRECISION_F64)
+                assert frame_r.tobytes() == f0.tobytes() and int(rec["steps"].sum()) == s0["total_steps"]
+    finally:
+        gpu_ctx.set_option("longest_first", 2)
+        gpu_ctx.set_option("favoured_slots", 8)
