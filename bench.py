@@ -434,7 +434,9 @@ def run_b200(args):
     background_upload_ms = (time.perf_counter() - t_up0) * 1e3
     sim = (scenes.DEFAULT_MAX_ITERATIONS, scenes.DEFAULT_ESCAPE_RADIUS, scenes.DEFAULT_STEP)
     PREC = {"f64_fast": _abi.PRECISION_F64_FAST, "f64": _abi.PRECISION_F64}[args.precision]
-    KERNEL = {"f64_fast": "render_rows_f64_fast<FastEllis, 1, 5, 0>", "f64": "render_rows_f64_lean<ShapeEllis, 0, 0, 1>"}[args.precision]
+    KERNEL = {"f64_fast": "render_rows_f64_fast<FastEllis, 1, 5, 1>", "f64": "render_rows_f64_lean<ShapeEllis, 0, 0, 1, 1>"}[args.precision]
+    KERNEL_NOTE = {"f64_fast": "the longest-first instantiation; collect_long_rays runs before it and render_rows_f64_lean<ShapeEllis, 0, 0, 1, 1> in list "
+                               "mode (the guard band's re-integration) after it, both inside kernel_ms", "f64": "kernel_variant 5"}[args.precision]
 
     stream = torch.cuda.current_stream()
     frames = [torch.empty(Ht * Wd * 3, dtype=torch.uint8, device=dev) for _ in range(n)]   # complete frames
@@ -737,7 +739,7 @@ def run_b200(args):
         "peak_nominal_note": f"{sm_count} SMs x 64 fp64 FMA lanes x 2 flop x {mhz_max} MHz",
         "traffic": traffic, "fp64_pipe": fp64_pipe,
         "peak_source": "live DFMA micro-kernel on this GPU (curvis_measure_fma_peak); MEASURED_PEAKS.json has no fp64 entry",
-        "flop_per_ray_step": flop, "kernel": KERNEL, "kernel_ms": kernel_ms,
+        "flop_per_ray_step": flop, "kernel": KERNEL, "kernel_note": KERNEL_NOTE, "kernel_ms": kernel_ms,
         "kernel_ray_steps_per_s": kernel_rate,
         "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",

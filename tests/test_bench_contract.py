@@ -41,3 +41,17 @@ def test_b200_arm_refuses_to_run_without_a_gpu(built):
         pytest.skip("a GPU is visible")
     r = _run("--steps", "1", "--warmup", "0")
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_bench_kernel_labels_have_an_ncu_record():
+    """bench.py looks its ncu figures (roofline.traffic, fp64_pipe) up by the kernel label: a label without a record in
+    profiles/latest_traffic.json would silently drop them from the line."""
+    import json, os, re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "bench.py")).read()
+    m = re.search(r'KERNEL = \{"f64_fast": "([^"]+)", "f64": "([^"]+)"\}', src)
+    assert m, "bench.py: KERNEL labels not found"
+    prof = json.load(open(os.path.join(root, "profiles", "latest_traffic.json")))
+    for label in m.groups():
+        assert label in prof, label
+        assert prof[label]["dram_bytes_per_launch"] > 0 and os.path.exists(os.path.join(root, prof[label]["source"].split(" ")[0]))
