@@ -466,10 +466,10 @@ __global__ void __launch_bounds__(kBlockFast, MinBlocks) render_rows_f64_fast(co
 
         // ---- refill, longest first.  A pre-pass kernel (collect_long_rays, below) has listed the rays predicted to be long:
         // near-critical photons whose orbit plane almost contains the polar axis (ray_predicted_long, geodesic_f64.cuh) — the
-        // rows next to the image's central row take 10x the time of any other (profiles/r02_latency_probe.json).  The queue's
-        // first n_long tickets hand out that list, the rest walk the ray indices and skip the listed ones.  A 20,000-step ray
-        // needs 4 ms at full occupancy whenever it starts, so on a small tile (one 4K frame over 8 GPUs: 5 ms) it must start at
-        // once.  A skipped ticket costs the prediction only (the pixel's unnormalised direction: ~40 instructions), and the
+        // rows next to the image's central row take 10x the time of any other (profiles/r02_latency_probe.json).  One queue
+        // (counters->long_next) hands out that list, the other (next_ray) walks the ray indices and skips the listed ones; which
+        // a warp draws from first depends on its hardware slot (`favoured`, above).  A 20,000-step ray needs 2.7 ms in a favoured
+        // slot whenever it starts, so on a small tile (one 4K frame over 8 GPUs: 4.5 ms) it must start at once.  A skipped ticket costs the prediction only (the pixel's unnormalised direction: ~40 instructions), and the
         // lane takes another.  The list must stay SHORT (here 0.3 % of a frame): listing every pole-grazing ray (2.5 %) and
         // starting them all at once cost 2-4 % of the frame — for two generations every warp of the GPU was in the slow,
         // divergent pole-crossing code at the same time, with no regular warps to hide its latency behind.
@@ -620,10 +620,11 @@ __global__ void __launch_bounds__(256) collect_long_rays(const __grid_constant__
 }
 
 // When the pre-pass runs ("longest_first" = 2, the default): launches of at least 2^15 rays (the efficient renderer's table skips
-// it) and of at most 64 rays per lane of the grid.  A 20,000-step straggler takes ~4 ms whenever it starts; in a launch of 87 rays
-// per lane (a whole 4K frame on one GPU, 37 ms) it is claimed half-way in index order and ends long before the kernel does, and
-// starting 27,000 slow rays at once only costs (measured +0.25 ms Ellis, +0.3-0.5 ms Interstellar); in a launch of 11 rays per lane
-// (the same frame over 8 GPUs, 5 ms) it must start first (Interstellar central tile: 9.5 -> 8.3 ms).
+// it) and of at most 64 rays per lane of the grid — or of any size where the metric's policy says so (`whole_frames`:
+// FastEllis::kLongFirstWholeFrames).  In a launch of 11 rays per lane (a 4K frame over 8 GPUs, 4.5 ms) a 20,000-step straggler must
+// start first and in a favoured slot (tile time 4.47 .. 5.83 ms -> 4.50 .. 4.53).  In a launch of 87 rays per lane (a whole 4K frame
+// on one GPU) the index order claims it half-way through: in an unfavoured slot it then outlasts the Ellis kernel (35.29 -> 34.89 ms
+// with the list), while the Interstellar kernel, 50 % longer, absorbs it and only pays for 27,000 slow rays starting at once (+0.4 ms).
 constexpr unsigned long long kLongestFirstMinRays = 1ull << 15;
 constexpr unsigned long long kLongestFirstMaxRaysPerLane = 64;
 
