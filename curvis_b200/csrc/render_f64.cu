@@ -101,8 +101,9 @@ __global__ void __launch_bounds__(kBlock) render_rows_f64(const __grid_constant_
 //          correctly-rounded sequence per quotient (kernel_variant 3); same roundings, geodesic_f64.cuh: rhs_lean
 // List mode (p.ray_list != nullptr): the launch re-integrates the rays CURVIS_PRECISION_F64_FAST left in its guard
 // band — ray i of the launch is ray ray_list[i] of the tile, *ray_list_count of them.
-// AHEAD: the step loop in latency form (geodesic_f64.cuh: euler_steps_ahead) — list mode, where a few hundred rays leave the
-// launch bound by one ray's dependent chain.  Same arithmetic; more registers (no occupancy to protect).
+// AHEAD: the step loop in latency form (geodesic_f64.cuh: euler_steps_ahead).  Built for list mode, where a few hundred rays leave the
+// launch bound by one ray's dependent chain; its merged loop is also shorter (117 against 131 instructions per Ellis step), so whole
+// frames run it too (kernel_variant 5, the default).  Same arithmetic.
 // LONGFIRST: the longest-first refill of render_f64_fast.cu — a pre-pass has listed the rays predicted to take 10^4 steps, and the
 // warps in the hardware slots the schedulers favour claim them first (this kernel's five warps per scheduler get 2.02 / 1.53 /
 // 0.92 / 0.39 / 0.14 of the mean share in %warpid order: a 20,000-step ray needs 5 ms in the first resident CTA of its SM and
@@ -285,7 +286,7 @@ template <class Shape>
 static cudaError_t launch_lean(const FrameParams& p, int sm_count, int blocks_per_sm_override, bool shared, bool ahead, cudaStream_t stream) {
     const bool track = p.records != nullptr;
     if (ahead && p.integrator == CURVIS_INTEGRATOR_EULER && !track)
-        return launch_lean_one<Shape, 0, false, true, true>(p, sm_count, blocks_per_sm_override, stream);   // re-integration list: latency form
+        return launch_lean_one<Shape, 0, false, true, true>(p, sm_count, blocks_per_sm_override, stream);   // latency form (re-integration list; whole frames)
     if (p.integrator == CURVIS_INTEGRATOR_RK4)
         return launch_lean_one<Shape, 1, false, true>(p, sm_count, blocks_per_sm_override, stream);
     if (p.integrator == CURVIS_INTEGRATOR_EULER_ADAPTIVE)
@@ -318,7 +319,7 @@ static cudaError_t launch_variant(const FrameParams& p, const LaunchTuning& t, i
             return launch_lean_one<Shape, 0, false, true, true, true>(p, sm_count, t.blocks_per_sm, stream);
         }
         return launch_lean<Shape>(p, sm_count, t.blocks_per_sm, true, true, stream);
-    default: return launch_lean<Shape>(p, sm_count, t.blocks_per_sm, true, false, stream);     // default (4): shared reciprocals
+    default: return launch_lean<Shape>(p, sm_count, t.blocks_per_sm, true, false, stream);     // 4: shared reciprocals, one step per trip of the loop
     }
 }
 
